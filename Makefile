@@ -1,0 +1,36 @@
+# Builds libhispmv_cuda.so (the C-ABI CUDA engine), the pyhispmv pybind11 module and the oracle.
+# sm_100a only -- there is no other target.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CXX       := g++
+PY        ?= python
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -Ihispmv_b200/csrc --expt-relaxed-constexpr
+PKG       := hispmv_b200
+CSRC      := $(PKG)/csrc
+OBJDIR    := build/obj
+OBJS      := $(OBJDIR)/capi.o $(OBJDIR)/spmv.o $(OBJDIR)/gemv.o $(OBJDIR)/partition.o $(OBJDIR)/synth.o
+LIB       := $(PKG)/libhispmv_cuda.so
+PYEXT     := $(PKG)/pyhispmv$(shell $(PY) -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
+PYINC     := $(shell $(PY) -c "import sysconfig,pybind11;print('-I'+sysconfig.get_paths()['include'],'-I'+pybind11.get_include())")
+
+all: $(LIB) $(PYEXT) oracle
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh include/hispmv.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+$(LIB): $(OBJS)
+	$(NVCC) -shared $(ARCH) -o $@ $(OBJS) -lcudart
+
+$(PYEXT): $(CSRC)/pyhispmv_bindings.cpp include/hispmv.h $(LIB)
+	$(CXX) -O2 -std=c++17 -fPIC -shared -fvisibility=hidden $(PYINC) -Iinclude $< -o $@ \
+	    -L$(PKG) -lhispmv_cuda -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -rf build $(LIB) $(PKG)/pyhispmv*.so
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

@@ -1,0 +1,810 @@
+// C-ABI of libhispmv_cuda.so (see include/hispmv.h for the reference interfaces each entry replaces).
+// Host-side state only: contexts, matrix handles, plans; all arithmetic happens in spmv.cu / gemv.cu /
+// partition.cu.  No CPU compute path exists here on purpose.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace hispmv {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+  if (e == cudaSuccess) return HISPMV_OK;
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  g_last_error = buf;
+  cudaGetLastError();  // clear the sticky-less error so later calls can proceed
+  return e == cudaErrorMemoryAllocation ? HISPMV_FULL : HISPMV_ERR_CUDA;
+}
+
+struct Matrix {
+  bool dense = false;
+  int32_t rows = 0, cols = 0;          // global shape
+  int32_t row_begin = 0, row_end = 0;  // local row block
+  int64_t nnz = 0;
+  // sparse
+  int32_t* d_row_ptr = nullptr;
+  int32_t* d_col = nullptr;
+  float* d_val = nullptr;
+  RowStats stats{};
+  int kernel = HISPMV_KERNEL_AUTO, lanes = 0;
+  bool forced = false;
+  int32_t tile_items = 0;
+  int64_t num_tiles = 0;
+  int32_t* d_tile_row = nullptr;
+  int64_t* d_tile_nnz = nullptr;
+  float* d_carry = nullptr;
+  int32_t* d_split_rows = nullptr;
+  int64_t num_split = 0;
+  // dense
+  float* d_a = nullptr;
+  int64_t ld = 0;
+
+  int32_t local_rows() const { return row_end - row_begin; }
+  void free_plan() {
+    cudaFree(d_tile_row);
+    cudaFree(d_tile_nnz);
+    cudaFree(d_carry);
+    cudaFree(d_split_rows);
+    d_tile_row = nullptr;
+    d_tile_nnz = nullptr;
+    d_carry = nullptr;
+    d_split_rows = nullptr;
+    num_tiles = 0;
+    num_split = 0;
+    tile_items = 0;
+  }
+  int64_t device_bytes() const {
+    if (dense) return (int64_t)local_rows() * ld * 4;
+    int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
+    if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 4 + num_split * 4;
+    return b;
+  }
+  ~Matrix() {
+    free_plan();
+    cudaFree(d_row_ptr);
+    cudaFree(d_col);
+    cudaFree(d_val);
+    cudaFree(d_a);
+  }
+};
+
+}  // namespace hispmv
+
+using namespace hispmv;
+
+struct hispmv_ctx {
+  int device = 0;
+  int flags = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // second lane for pipelined linear()
+  cudaEvent_t ev_bias = nullptr;
+  int shard_part = 0, shard_parts = 1;
+  int64_t mem_limit = 0;
+  std::vector<Matrix*> mats;
+  int selected = -1;
+  bool committed = false;
+  // device staging for the host-buffer calls (two lanes)
+  float* d_x[2] = {nullptr, nullptr};
+  float* d_y[2] = {nullptr, nullptr};
+  float* d_bias = nullptr;
+  int64_t cap_x = 0, cap_y = 0;
+
+  int64_t used_bytes() const {
+    int64_t b = 0;
+    for (auto* m : mats) b += m->device_bytes();
+    return b;
+  }
+};
+
+namespace {
+
+struct DeviceGuard {
+  int prev = 0;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess) ok = true;
+    cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (ok) cudaSetDevice(prev);
+  }
+};
+
+int ensure_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
+  if (n_x > c->cap_x) {
+    for (int l = 0; l < 2; ++l) {
+      cudaFree(c->d_x[l]);
+      c->d_x[l] = nullptr;
+      HISPMV_CUDA(cudaMalloc((void**)&c->d_x[l], (size_t)n_x * 4));
+    }
+    c->cap_x = n_x;
+  }
+  if (n_y > c->cap_y) {
+    for (int l = 0; l < 2; ++l) {
+      cudaFree(c->d_y[l]);
+      c->d_y[l] = nullptr;
+      HISPMV_CUDA(cudaMalloc((void**)&c->d_y[l], (size_t)n_y * 4));
+    }
+    cudaFree(c->d_bias);
+    c->d_bias = nullptr;
+    HISPMV_CUDA(cudaMalloc((void**)&c->d_bias, (size_t)n_y * 4));
+    c->cap_y = n_y;
+  }
+  return HISPMV_OK;
+}
+
+// Build (or rebuild) the execution plan of a sparse matrix: histogram -> selector -> merge tiles.
+int plan_sparse(hispmv_ctx* c, Matrix* m) {
+  m->free_plan();
+  int st = row_stats_device(m->d_row_ptr, m->local_rows(), &m->stats, c->stream);
+  if (st != HISPMV_OK) return st;
+  if (!m->forced) {
+    select_kernel(m->stats, m->cols, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0, &m->kernel, &m->lanes);
+  } else if (m->nnz == 0 || m->local_rows() == 0) {
+    m->kernel = HISPMV_KERNEL_EMPTY;
+  }
+  if (m->kernel == HISPMV_KERNEL_CSR_VECTOR && m->lanes == 0) {
+    int k, l;
+    select_kernel(m->stats, m->cols, 0, &k, &l);
+    m->lanes = l ? l : 2;
+  }
+  if (m->kernel == HISPMV_KERNEL_MERGE) {
+    m->tile_items = merge_tile_items_for(m->stats);
+    if (const char* e = getenv("HISPMV_MERGE_TILE")) {
+      const int v = atoi(e);
+      if (merge_tile_items_supported(v)) m->tile_items = v;
+    }
+    st = merge_tiles_device(m->d_row_ptr, m->local_rows(), m->nnz, m->tile_items, &m->num_tiles, &m->d_tile_row,
+                            &m->d_tile_nnz, c->stream);
+    if (st != HISPMV_OK) return st;
+    HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, (size_t)m->num_tiles * sizeof(float)));
+    st = split_rows_device(m->d_row_ptr, m->local_rows(), m->d_tile_row, m->d_tile_nnz, m->num_tiles,
+                           &m->d_split_rows, &m->num_split, c->stream);
+    if (st != HISPMV_OK) return st;
+  }
+  HISPMV_CUDA(cudaStreamSynchronize(c->stream));
+  return HISPMV_OK;
+}
+
+int check_capacity(hispmv_ctx* c, int64_t extra) {
+  if (c->mem_limit > 0 && c->used_bytes() + extra > c->mem_limit) {
+    set_error("device memory limit reached");
+    return HISPMV_FULL;
+  }
+  return HISPMV_OK;
+}
+
+// Takes ownership of a full-matrix device CSR, shards it if requested, plans it, registers the handle.
+int adopt_csr(hispmv_ctx* c, int32_t* d_row_ptr, int32_t* d_col, float* d_val, int64_t nnz, int32_t rows,
+              int32_t cols) {
+  Matrix* m = new Matrix();
+  m->rows = rows;
+  m->cols = cols;
+  m->d_row_ptr = d_row_ptr;
+  m->d_col = d_col;
+  m->d_val = d_val;
+  m->nnz = nnz;
+  m->row_begin = 0;
+  m->row_end = rows;
+  int st = HISPMV_OK;
+  if (c->shard_parts > 1) {
+    std::vector<int32_t> bounds(c->shard_parts + 1);
+    st = shard_bounds_device(d_row_ptr, rows, nnz, c->shard_parts, bounds.data(), c->stream);
+    if (st == HISPMV_OK) {
+      int32_t *rp = nullptr, *cl = nullptr;
+      float* vl = nullptr;
+      int64_t lnnz = 0;
+      const int32_t rb = bounds[c->shard_part], re = bounds[c->shard_part + 1];
+      st = csr_slice_device(d_row_ptr, d_col, d_val, rb, re, &rp, &cl, &vl, &lnnz, c->stream);
+      if (st == HISPMV_OK) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(m->d_row_ptr);
+        cudaFree(m->d_col);
+        cudaFree(m->d_val);
+        m->d_row_ptr = rp;
+        m->d_col = cl;
+        m->d_val = vl;
+        m->nnz = lnnz;
+        m->row_begin = rb;
+        m->row_end = re;
+      }
+    }
+  }
+  if (st == HISPMV_OK) st = check_capacity(c, m->device_bytes());
+  if (st == HISPMV_OK) st = plan_sparse(c, m);
+  if (st != HISPMV_OK) {
+    delete m;
+    return st;
+  }
+  c->mats.push_back(m);
+  return (int)c->mats.size() - 1;
+}
+
+int add_coo_common(hispmv_ctx* c, const int32_t* r, const int32_t* cc, const float* v, int64_t nnz, int32_t rows,
+                   int32_t cols, bool on_device) {
+  if (!c || rows < 0 || cols < 0 || nnz < 0 || (nnz > 0 && (!r || !cc || !v))) {
+    set_error("add_sparse_coo: bad arguments");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  int st = check_capacity(c, nnz * 8 + ((int64_t)rows + 1) * 4);
+  if (st != HISPMV_OK) return st;
+  int32_t *d_r = nullptr, *d_c = nullptr;
+  float* d_v = nullptr;
+  const int32_t *ur = r, *uc = cc;
+  const float* uv = v;
+  if (!on_device && nnz > 0) {
+    st = check_cuda(cudaMalloc((void**)&d_r, nnz * 4), "cudaMalloc(coo rows)", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)&d_c, nnz * 4), "cudaMalloc(coo cols)", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)&d_v, nnz * 4), "cudaMalloc(coo vals)", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaMemcpyAsync(d_r, r, nnz * 4, cudaMemcpyHostToDevice, c->stream), "H2D rows", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaMemcpyAsync(d_c, cc, nnz * 4, cudaMemcpyHostToDevice, c->stream), "H2D cols", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaMemcpyAsync(d_v, v, nnz * 4, cudaMemcpyHostToDevice, c->stream), "H2D vals", __FILE__, __LINE__);
+    ur = d_r;
+    uc = d_c;
+    uv = d_v;
+  }
+  int32_t *rp = nullptr, *cl = nullptr;
+  float* vl = nullptr;
+  if (st == HISPMV_OK) st = coo_to_csr_device(ur, uc, uv, nnz, rows, cols, &rp, &cl, &vl, c->stream);
+  cudaFree(d_r);
+  cudaFree(d_c);
+  cudaFree(d_v);
+  if (st != HISPMV_OK) return st;
+  return adopt_csr(c, rp, cl, vl, nnz, rows, cols);
+}
+
+int add_csr_common(hispmv_ctx* c, const int32_t* row_ptr, const int32_t* col, const float* val, int32_t rows,
+                   int32_t cols, bool on_device) {
+  if (!c || rows < 0 || cols < 0 || !row_ptr) {
+    set_error("add_sparse_csr: bad arguments");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  int32_t last = 0, first = 0;
+  if (on_device) {
+    HISPMV_CUDA(cudaMemcpy(&last, row_ptr + rows, 4, cudaMemcpyDeviceToHost));
+    HISPMV_CUDA(cudaMemcpy(&first, row_ptr, 4, cudaMemcpyDeviceToHost));
+  } else {
+    last = row_ptr[rows];
+    first = row_ptr[0];
+  }
+  if (first != 0 || last < 0) {
+    set_error("add_sparse_csr: row_ptr must start at 0 and be non-decreasing");
+    return HISPMV_ERR_ARG;
+  }
+  const int64_t nnz = last;
+  int st = check_capacity(c, nnz * 8 + ((int64_t)rows + 1) * 4);
+  if (st != HISPMV_OK) return st;
+  int32_t* rp = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)&rp, ((size_t)rows + 1) * 4));
+  st = check_cuda(cudaMemcpyAsync(rp, row_ptr, ((size_t)rows + 1) * 4, kind, c->stream), "copy row_ptr", __FILE__, __LINE__);
+  int32_t* cl = nullptr;
+  float* vl = nullptr;
+  if (st == HISPMV_OK) st = alloc_padded_nnz_arrays(col, val, nnz, kind, &cl, &vl, c->stream);
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamSynchronize(c->stream), "sync", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    cudaFree(rp);
+    cudaFree(cl);
+    cudaFree(vl);
+    return st;
+  }
+  return adopt_csr(c, rp, cl, vl, nnz, rows, cols);
+}
+
+int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, bool on_device) {
+  if (!c || rows < 0 || cols < 0 || ((int64_t)rows * cols > 0 && !a)) {
+    set_error("add_dense: bad arguments");
+    return HISPMV_ERR_ARG;
+  }
+  if (!(c->flags & HISPMV_FLAG_DENSE_OVERLAY)) {
+    // the reference asserts dense_overlay in prepareDenseMtxForFPGA (common/src/spmv-helper.cpp:718)
+    set_error("create_dense_handle needs dense_overlay=True");
+    return HISPMV_ERR_STATE;
+  }
+  DeviceGuard g(c->device);
+  Matrix* m = new Matrix();
+  m->dense = true;
+  m->kernel = HISPMV_KERNEL_GEMV;
+  m->rows = rows;
+  m->cols = cols;
+  m->row_begin = (int32_t)(((int64_t)rows * c->shard_part) / c->shard_parts);
+  m->row_end = (int32_t)(((int64_t)rows * (c->shard_part + 1)) / c->shard_parts);
+  m->ld = ((int64_t)cols + 3) & ~3LL;
+  if (m->ld == 0) m->ld = 4;
+  m->nnz = (int64_t)m->local_rows() * cols;
+  int st = check_capacity(c, m->device_bytes());
+  const size_t bytes = (size_t)std::max<int64_t>(1, (int64_t)m->local_rows() * m->ld) * 4;
+  if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)&m->d_a, bytes), "cudaMalloc(dense)", __FILE__, __LINE__);
+  if (st == HISPMV_OK && m->ld != cols) st = check_cuda(cudaMemsetAsync(m->d_a, 0, bytes, c->stream), "memset", __FILE__, __LINE__);
+  if (st == HISPMV_OK && m->local_rows() > 0 && cols > 0)
+    st = check_cuda(cudaMemcpy2DAsync(m->d_a, (size_t)m->ld * 4, a + (int64_t)m->row_begin * cols, (size_t)cols * 4,
+                                      (size_t)cols * 4, (size_t)m->local_rows(),
+                                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream),
+                    "copy dense", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamSynchronize(c->stream), "sync", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    delete m;
+    return st;
+  }
+  c->mats.push_back(m);
+  return (int)c->mats.size() - 1;
+}
+
+int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
+               int relu, cudaStream_t s) {
+  Epilogue ep{alpha, beta, d_bias, relu};
+  if (beta != 0.0f && !d_bias) {
+    set_error("run: bias is required when beta != 0");
+    return HISPMV_ERR_ARG;
+  }
+  if (m->dense) {
+    DenseDev D;
+    D.rows = m->local_rows();
+    D.cols = m->cols;
+    D.ld = m->ld;
+    D.a = m->d_a;
+    return launch_gemv(D, d_x, d_y, ep, c->sm_count, s);
+  }
+  CsrDev A;
+  A.rows = m->local_rows();
+  A.cols = m->cols;
+  A.nnz = m->nnz;
+  A.row_ptr = m->d_row_ptr;
+  A.col = m->d_col;
+  A.val = m->d_val;
+  switch (m->kernel) {
+    case HISPMV_KERNEL_EMPTY: return launch_empty(A.rows, d_y, ep, s);
+    case HISPMV_KERNEL_CSR_SCALAR: return launch_csr_scalar(A, d_x, d_y, ep, s);
+    case HISPMV_KERNEL_CSR_VECTOR: return launch_csr_vector(A, m->lanes, d_x, d_y, ep, s);
+    case HISPMV_KERNEL_MERGE: {
+      MergePlan P;
+      P.tile_items = m->tile_items;
+      P.num_tiles = m->num_tiles;
+      P.tile_row = m->d_tile_row;
+      P.tile_nnz = m->d_tile_nnz;
+      P.carry = m->d_carry;
+      return launch_merge(A, P, d_x, d_y, ep, s);
+    }
+    default: set_error("run: matrix has no plan"); return HISPMV_ERR_STATE;
+  }
+}
+
+Matrix* get_matrix(hispmv_ctx* c, int64_t idx) {
+  if (!c) {
+    set_error("null context");
+    return nullptr;
+  }
+  if (idx < 0 || idx >= (int64_t)c->mats.size()) {
+    set_error("Matrix idx out of range");
+    return nullptr;
+  }
+  return c->mats[(size_t)idx];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* hispmv_last_error(void) { return g_last_error.c_str(); }
+int hispmv_version(void) { return 100; }
+
+int hispmv_create(hispmv_ctx** out, int device_id, int flags) {
+  if (!out) return HISPMV_ERR_ARG;
+  *out = nullptr;
+  int n = 0;
+  HISPMV_CUDA(cudaGetDeviceCount(&n));
+  if (device_id < 0 || device_id >= n) {
+    set_error("hispmv_create: no such CUDA device");
+    return HISPMV_ERR_CUDA;
+  }
+  cudaDeviceProp prop;
+  HISPMV_CUDA(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) {
+    set_error(std::string("hispmv_create: device '") + prop.name +
+              "' is not sm_100 (B200); this library ships sm_100a code only and has no fallback");
+    return HISPMV_ERR_CUDA;
+  }
+  DeviceGuard g(device_id);
+  hispmv_ctx* c = new hispmv_ctx();
+  c->device = device_id;
+  c->flags = flags;
+  c->sm_count = prop.multiProcessorCount;
+  int st = check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaEventCreateWithFlags(&c->ev_bias, cudaEventDisableTiming), "event", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    delete c;
+    return st;
+  }
+  *out = c;
+  return HISPMV_OK;
+}
+
+void hispmv_destroy(hispmv_ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->stream2);
+  for (auto* m : c->mats) delete m;
+  for (int l = 0; l < 2; ++l) {
+    cudaFree(c->d_x[l]);
+    cudaFree(c->d_y[l]);
+  }
+  cudaFree(c->d_bias);
+  cudaEventDestroy(c->ev_bias);
+  cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->stream2);
+  delete c;
+}
+
+int hispmv_set_shard(hispmv_ctx* c, int part, int n_parts) {
+  if (!c || n_parts < 1 || part < 0 || part >= n_parts) {
+    set_error("set_shard: need 0 <= part < n_parts");
+    return HISPMV_ERR_ARG;
+  }
+  c->shard_part = part;
+  c->shard_parts = n_parts;
+  return HISPMV_OK;
+}
+
+int hispmv_shard_bounds(const int32_t* row_ptr, int32_t rows, int n_parts, int32_t* bounds) {
+  if (!row_ptr || !bounds || rows < 0 || n_parts < 1) {
+    set_error("shard_bounds: bad arguments");
+    return HISPMV_ERR_ARG;
+  }
+  // host row_ptr in, host bounds out; the search itself runs on the current device like every other
+  // partition artefact (one tiny kernel), so there is a single implementation to keep bit-exact.
+  int32_t* d = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)&d, ((size_t)rows + 1) * 4));
+  int st = check_cuda(cudaMemcpy(d, row_ptr, ((size_t)rows + 1) * 4, cudaMemcpyHostToDevice), "H2D", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = shard_bounds_device(d, rows, row_ptr[rows], n_parts, bounds, 0);
+  cudaFree(d);
+  return st;
+}
+
+int hispmv_set_memory_limit(hispmv_ctx* c, int64_t bytes) {
+  if (!c || bytes < 0) return HISPMV_ERR_ARG;
+  c->mem_limit = bytes;
+  return HISPMV_OK;
+}
+
+int hispmv_add_sparse_coo(hispmv_ctx* c, const int32_t* r, const int32_t* cc, const float* v, int64_t nnz,
+                          int32_t rows, int32_t cols) {
+  return add_coo_common(c, r, cc, v, nnz, rows, cols, false);
+}
+int hispmv_add_sparse_coo_dev(hispmv_ctx* c, const int32_t* r, const int32_t* cc, const float* v, int64_t nnz,
+                              int32_t rows, int32_t cols) {
+  return add_coo_common(c, r, cc, v, nnz, rows, cols, true);
+}
+int hispmv_add_sparse_csr(hispmv_ctx* c, const int32_t* rp, const int32_t* ci, const float* v, int32_t rows,
+                          int32_t cols) {
+  return add_csr_common(c, rp, ci, v, rows, cols, false);
+}
+int hispmv_add_sparse_csr_dev(hispmv_ctx* c, const int32_t* rp, const int32_t* ci, const float* v, int32_t rows,
+                              int32_t cols) {
+  return add_csr_common(c, rp, ci, v, rows, cols, true);
+}
+int hispmv_add_dense(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols) {
+  return add_dense_common(c, a, rows, cols, false);
+}
+int hispmv_add_dense_dev(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols) {
+  return add_dense_common(c, a, rows, cols, true);
+}
+
+int hispmv_commit(hispmv_ctx* c) {
+  if (!c) return HISPMV_ERR_ARG;
+  // Matrices are uploaded and planned when they are added (the GPU has no separate "sync BO" step), so
+  // commit only fences outstanding work.  Idempotent; handles may still be added afterwards.
+  DeviceGuard g(c->device);
+  HISPMV_CUDA(cudaStreamSynchronize(c->stream));
+  c->committed = true;
+  return HISPMV_OK;
+}
+
+int hispmv_num_matrices(hispmv_ctx* c) { return c ? (int)c->mats.size() : HISPMV_ERR_ARG; }
+
+int hispmv_select(hispmv_ctx* c, uint32_t idx) {
+  if (!get_matrix(c, idx)) return c ? HISPMV_ERR_INDEX : HISPMV_ERR_ARG;
+  c->selected = (int)idx;
+  return HISPMV_OK;
+}
+
+int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (m->dense) {
+    set_error("force_kernel: dense handles always use the GeMV kernel");
+    return HISPMV_ERR_ARG;
+  }
+  if (kernel != HISPMV_KERNEL_AUTO && kernel != HISPMV_KERNEL_CSR_SCALAR && kernel != HISPMV_KERNEL_CSR_VECTOR &&
+      kernel != HISPMV_KERNEL_MERGE) {
+    set_error("force_kernel: unknown kernel");
+    return HISPMV_ERR_ARG;
+  }
+  if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) {
+    set_error("force_kernel: lanes must be 0,2,4,8,16,32");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  m->forced = kernel != HISPMV_KERNEL_AUTO;
+  m->kernel = kernel;
+  m->lanes = lanes;
+  return plan_sparse(c, m);
+}
+
+int hispmv_run_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
+                   void* stream) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  DeviceGuard g(c->device);
+  return run_matrix(c, m, d_x, d_bias, d_y, alpha, beta, 0, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
+                      void* stream) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  DeviceGuard g(c->device);
+  return run_matrix(c, m, d_x, d_bias, d_y, 1.0f, d_bias ? 1.0f : 0.0f, relu, stream ? (cudaStream_t)stream : c->stream);
+}
+
+int hispmv_sync(hispmv_ctx* c) {
+  if (!c) return HISPMV_ERR_ARG;
+  DeviceGuard g(c->device);
+  HISPMV_CUDA(cudaStreamSynchronize(c->stream));
+  HISPMV_CUDA(cudaStreamSynchronize(c->stream2));
+  return HISPMV_OK;
+}
+
+int hispmv_launches_per_run(hispmv_ctx* c, int idx) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (m->local_rows() <= 0) return 0;
+  if (!m->dense && m->kernel == HISPMV_KERNEL_MERGE) return m->num_tiles > 1 ? 2 : 1;
+  return 1;
+}
+
+int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float alpha, float beta) {
+  if (!c) return HISPMV_ERR_ARG;
+  if (c->selected < 0) {
+    set_error("Run Kernel called before selecting a matrix");  // reference: assert, fpga_handle.cpp:292
+    return HISPMV_ERR_STATE;
+  }
+  if (!x || !y || (beta != 0.0f && !bias)) {
+    set_error("run: null vector");
+    return HISPMV_ERR_ARG;
+  }
+  Matrix* m = c->mats[(size_t)c->selected];
+  DeviceGuard g(c->device);
+  const int64_t n_y = m->local_rows();
+  int st = ensure_staging(c, m->cols, n_y);
+  if (st != HISPMV_OK) return st;
+  cudaStream_t s = c->stream;
+  if (m->cols > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s));
+  if (bias && n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, s));
+  st = run_matrix(c, m, c->d_x[0], bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s);
+  if (st != HISPMV_OK) return st;
+  if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(y, c->d_y[0], (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
+  HISPMV_CUDA(cudaStreamSynchronize(s));
+  return HISPMV_OK;
+}
+
+int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const float* bias, float* y_out) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (!x || !y_out || !bias) {
+    set_error("linear: null vector");
+    return HISPMV_ERR_ARG;
+  }
+  if (m->cols <= 0) {
+    set_error("linear: matrix has no columns");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  const int64_t num_vecs = x_len / m->cols;  // reference: integer division, remainder ignored (fpga_handle.cpp:336)
+  const int64_t n_y = m->local_rows();
+  int st = ensure_staging(c, m->cols, n_y);
+  if (st != HISPMV_OK) return st;
+  cudaStream_t lanes[2] = {c->stream, c->stream2};
+  if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, lanes[0]));
+  HISPMV_CUDA(cudaEventRecord(c->ev_bias, lanes[0]));
+  HISPMV_CUDA(cudaStreamWaitEvent(lanes[1], c->ev_bias, 0));
+  // Vectors alternate between two stream lanes so the copy of vector v+1 overlaps the kernel of vector v
+  // (the reference overlaps host fill with the FPGA run the same way, fpga_handle.cpp:366-379).
+  for (int64_t v = 0; v < num_vecs; ++v) {
+    const int l = (int)(v & 1);
+    HISPMV_CUDA(cudaMemcpyAsync(c->d_x[l], x + v * m->cols, (size_t)m->cols * 4, cudaMemcpyHostToDevice, lanes[l]));
+    st = run_matrix(c, m, c->d_x[l], c->d_bias, c->d_y[l], 1.0f, 1.0f, 0, lanes[l]);
+    if (st != HISPMV_OK) return st;
+    if (n_y > 0)
+      HISPMV_CUDA(cudaMemcpyAsync(y_out + v * n_y, c->d_y[l], (size_t)n_y * 4, cudaMemcpyDeviceToHost, lanes[l]));
+  }
+  HISPMV_CUDA(cudaStreamSynchronize(lanes[0]));
+  HISPMV_CUDA(cudaStreamSynchronize(lanes[1]));
+  return HISPMV_OK;
+}
+
+int hispmv_matrix_info_get(hispmv_ctx* c, int idx, hispmv_matrix_info* out) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (!out) return HISPMV_ERR_ARG;
+  memset(out, 0, sizeof(*out));
+  out->rows = m->rows;
+  out->cols = m->cols;
+  out->row_begin = m->row_begin;
+  out->row_end = m->row_end;
+  out->nnz = m->nnz;
+  out->is_dense = m->dense;
+  out->kernel = m->kernel;
+  out->vector_lanes = m->lanes;
+  out->tile_items = m->tile_items;
+  out->num_tiles = m->num_tiles;
+  out->num_split_rows = m->num_split;
+  out->max_row_nnz = m->dense ? m->cols : m->stats.max_row_nnz;
+  out->empty_rows = m->dense ? 0 : m->stats.empty_rows;
+  if (!m->dense)
+    for (int i = 0; i < HISPMV_HIST_BINS; ++i) out->hist[i] = m->stats.hist[i];
+  out->device_bytes = m->device_bytes();
+  return HISPMV_OK;
+}
+
+int hispmv_plan_csr(hispmv_ctx* c, int idx, int32_t* row_ptr, int32_t* col_idx, float* vals) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (m->dense) {
+    set_error("plan_csr: dense handle");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  if (row_ptr) HISPMV_CUDA(cudaMemcpy(row_ptr, m->d_row_ptr, ((size_t)m->local_rows() + 1) * 4, cudaMemcpyDeviceToHost));
+  if (col_idx && m->nnz) HISPMV_CUDA(cudaMemcpy(col_idx, m->d_col, (size_t)m->nnz * 4, cudaMemcpyDeviceToHost));
+  if (vals && m->nnz) HISPMV_CUDA(cudaMemcpy(vals, m->d_val, (size_t)m->nnz * 4, cudaMemcpyDeviceToHost));
+  return HISPMV_OK;
+}
+
+int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_nnz) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (!m->d_tile_row) {
+    set_error("plan_tiles: matrix is not planned for the merge kernel");
+    return HISPMV_ERR_STATE;
+  }
+  DeviceGuard g(c->device);
+  if (tile_row) HISPMV_CUDA(cudaMemcpy(tile_row, m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
+  if (tile_nnz) HISPMV_CUDA(cudaMemcpy(tile_nnz, m->d_tile_nnz, (size_t)(m->num_tiles + 1) * 8, cudaMemcpyDeviceToHost));
+  return HISPMV_OK;
+}
+
+int hispmv_plan_split_rows(hispmv_ctx* c, int idx, int32_t* rows_out) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  DeviceGuard g(c->device);
+  if (rows_out && m->num_split > 0)
+    HISPMV_CUDA(cudaMemcpy(rows_out, m->d_split_rows, (size_t)m->num_split * 4, cudaMemcpyDeviceToHost));
+  return HISPMV_OK;
+}
+
+// Matrix Market reader with the semantics of HiSpmvHandle::loadMtx (common/src/spmv-helper.cpp:34-136):
+// banner "%%MatrixMarket matrix coordinate {real|integer|pattern} {general|symmetric|skew-symmetric}",
+// comment lines skipped, 1-based indices, pattern entries get 1.0, explicit zeros are dropped, symmetric
+// and skew-symmetric files are expanded with (c, r, +-v) for off-diagonal entries.
+int hispmv_load_mtx(hispmv_ctx* c, const char* path) {
+  if (!c || !path) return HISPMV_ERR_ARG;
+  FILE* f = fopen(path, "rb");
+  if (!f) {
+    set_error(std::string("Error: Unable to open file ") + path);
+    return HISPMV_ERR_IO;
+  }
+  std::string data;
+  {
+    fseek(f, 0, SEEK_END);
+    const long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    data.resize(sz > 0 ? (size_t)sz : 0);
+    if (sz > 0 && fread(&data[0], 1, (size_t)sz, f) != (size_t)sz) {
+      fclose(f);
+      set_error("Error: short read");
+      return HISPMV_ERR_IO;
+    }
+    fclose(f);
+  }
+  const char* p = data.c_str();
+  const char* end = p + data.size();
+  auto next_line = [&](std::string& out) -> bool {
+    if (p >= end) return false;
+    const char* q = (const char*)memchr(p, '\n', end - p);
+    if (!q) q = end;
+    out.assign(p, q - p);
+    p = q < end ? q + 1 : end;
+    return true;
+  };
+  std::string line;
+  if (!next_line(line)) {
+    set_error("Error: Not a valid Matrix Market file.");
+    return HISPMV_ERR_IO;
+  }
+  std::string h[5];
+  {
+    std::istringstream hs(line);
+    for (auto& s : h) hs >> s;
+  }
+  if (h[0] != "%%MatrixMarket" || h[1] != "matrix") {
+    set_error("Error: Not a valid Matrix Market file.");
+    return HISPMV_ERR_IO;
+  }
+  if (h[2] != "coordinate") {
+    set_error("Error: Only sparse matrices in 'coordinate' format are supported.");
+    return HISPMV_ERR_IO;
+  }
+  const bool pattern = h[3] == "pattern";
+  if (h[3] != "real" && h[3] != "integer" && !pattern) {
+    set_error("Error: Unsupported data type.");
+    return HISPMV_ERR_IO;
+  }
+  const bool symm = h[4] == "symmetric", skew = h[4] == "skew-symmetric";
+  if (h[4] != "general" && !symm && !skew) {
+    set_error("Error: Unsupported symmetry type. Only 'general', 'symmetric', and 'skew-symmetric' are supported.");
+    return HISPMV_ERR_IO;
+  }
+  do {
+    if (!next_line(line)) {
+      set_error("Error: missing size line");
+      return HISPMV_ERR_IO;
+    }
+  } while (!line.empty() && line[0] == '%');
+  long long rows = 0, cols = 0, nnz_decl = 0;
+  if (sscanf(line.c_str(), "%lld %lld %lld", &rows, &cols, &nnz_decl) != 3 || rows < 0 || cols < 0 ||
+      rows > INT32_MAX || cols > INT32_MAX) {
+    set_error("Error: bad size line");
+    return HISPMV_ERR_IO;
+  }
+  std::vector<int32_t> R, C;
+  std::vector<float> V;
+  const size_t reserve = (size_t)nnz_decl * ((symm || skew) ? 2 : 1);
+  R.reserve(reserve);
+  C.reserve(reserve);
+  V.reserve(reserve);
+  while (p < end) {
+    char* q;
+    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+    if (p >= end) break;
+    const long r = strtol(p, &q, 10);
+    if (q == p) break;
+    p = q;
+    const long cc = strtol(p, &q, 10);
+    if (q == p) break;
+    p = q;
+    float v = 1.0f;
+    if (!pattern) {
+      v = strtof(p, &q);
+      if (q == p) break;
+      p = q;
+    }
+    while (p < end && *p != '\n') ++p;  // rest of the line
+    if (v == 0) continue;
+    R.push_back((int32_t)(r - 1));
+    C.push_back((int32_t)(cc - 1));
+    V.push_back(v);
+    if ((symm || skew) && r != cc) {
+      R.push_back((int32_t)(cc - 1));
+      C.push_back((int32_t)(r - 1));
+      V.push_back(skew ? -v : v);
+    }
+  }
+  return hispmv_add_sparse_coo(c, R.data(), C.data(), V.data(), (int64_t)R.size(), (int32_t)rows, (int32_t)cols);
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// Device-side helpers: streaming 128-bit loads with cache hints, warp reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hispmv {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// Matrix values / column indices are read exactly once per SpMV: bypass L1 allocation and mark the
+// line evict-first in L2 so the stream does not push x (the only reused operand) out of the 126 MB L2.
+// On sm_100a the plain .L2::evict_first qualifier exists only on 256-bit loads (LDG.E.NA.EFL2.256); the
+// narrower loads carry the same priority through an L2 cache-hint policy operand.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ int4 ld_stream_i4(const int32_t* p, uint64_t pol) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const float* p, uint64_t pol) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ int ld_stream_i1(const int32_t* p, uint64_t pol) {
+  int r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ float ld_stream_f1(const float* p, uint64_t pol) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+  return r;
+}
+// 256-bit streaming load (sm_100+): 8 consecutive 32-bit words from a 32-byte aligned address.
+struct alignas(32) Words8 {
+  uint32_t w[8];
+};
+__device__ __forceinline__ Words8 ld_stream_256(const void* p) {
+  Words8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                 "=r"(r.w[7])
+               : "l"(p));
+  return r;
+}
+// x gathers: read-only path, allocate in L1, prefer to keep in L2.
+__device__ __forceinline__ float ld_x(const float* p, uint64_t pol) {
+  float r;
+  asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d);
+  return v;
+}
+
+template <int LANES>
+__device__ __forceinline__ float subwarp_sum(float v) {
+#pragma unroll
+  for (int d = LANES / 2; d > 0; d >>= 1) v += __shfl_down_sync(kFullMask, v, d, LANES);
+  return v;
+}
+
+__device__ __forceinline__ float finish(float ax, float alpha, float beta, const float* bias, int64_t r, int relu) {
+  float v = alpha * ax;
+  if (beta != 0.0f) v = fmaf(beta, bias[r], v);
+  if (relu) v = fmaxf(v, 0.0f);
+  return v;
+}
+
+}  // namespace hispmv

@@ -1,0 +1,183 @@
+// Dense-overlay GeMV for sm_100a: y = alpha * A x + beta * bias, A row-major fp32, batch 1.
+//
+// Replaces the reference's dense overlay -- prepareDenseMtxForFPGA (common/src/spmv-helper.cpp:717-750)
+// feeding ComputeAB in DENSE_MODE (automation_tool/assets/base_functions.cpp:188-226, out = a0*x[c] +
+// a1*x[c+1]) and Compute_C (base_functions.cpp:535).  Batch-1 GeMV is 0.5 flop/byte: a pure HBM
+// stream, so no tensor cores.  Design:
+//   * A is stored with a leading dimension padded to 4 floats, so every row starts 16-byte aligned and
+//     the stream is nothing but 128-bit evict-first loads (each element is read exactly once).
+//   * x is staged once per CTA in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier), then
+//     re-read from shared memory for every row the CTA owns.
+//   * A CTA owns a contiguous block of rows and all its threads sweep the columns of R rows at a time
+//     (R*unroll independent 16-byte loads in flight per thread); a shuffle + shared-memory reduction
+//     finishes each group of R rows.  Row blocks are sized so the grid is one wave of
+//     sm_count * CTAS_PER_SM CTAs.
+#include "device_utils.cuh"
+#include "internal.h"
+
+namespace hispmv {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <int THREADS, int R, bool STAGE_X>
+__global__ void __launch_bounds__(THREADS)
+    gemv_rowblock_kernel(DenseDev A, const float* __restrict__ x, float* __restrict__ y, Epilogue ep,
+                         int rows_per_cta) {
+  constexpr int WARPS = THREADS / 32;
+  extern __shared__ __align__(16) float s_x[];  // STAGE_X: ld floats (cols rounded up to 4, tail zeroed)
+  __shared__ float s_red[2][WARPS][R];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const uint64_t ps = policy_evict_first();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncol4 = (int)(A.ld >> 2);
+
+  if (STAGE_X) {
+    const bool bulk_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    const int full = bulk_ok ? (A.cols & ~3) : 0;  // floats moved by the bulk engine
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid == 0 && full > 0) {
+      mbar_expect_tx(&s_bar, (uint32_t)full * 4u);
+      // <= 64 KB per request keeps each copy well inside the engine's comfort zone
+      for (int off = 0; off < full; off += 16384) {
+        const int n = min(16384, full - off);
+        bulk_g2s(s_x + off, x + off, (uint32_t)n * 4u, &s_bar);
+      }
+    }
+    for (int c = full + tid; c < (int)A.ld; c += THREADS) s_x[c] = c < A.cols ? x[c] : 0.0f;
+    if (full > 0) mbar_wait(&s_bar, 0);
+    __syncthreads();
+  }
+
+  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t rend = min((int64_t)A.rows, rbeg + rows_per_cta);
+  int buf = 0;
+  for (int64_t r = rbeg; r < rend; r += R) {
+    float acc[R];
+#pragma unroll
+    for (int q = 0; q < R; ++q) acc[q] = 0.0f;
+    const float* arow = A.a + r * A.ld;
+    const int nr = (int)min((int64_t)R, rend - r);
+    if (nr == R) {
+#pragma unroll 2
+      for (int c4 = tid; c4 < ncol4; c4 += THREADS) {
+        float4 a[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) a[q] = ld_stream_f4(arow + (int64_t)q * A.ld + 4 * c4, ps);
+        float4 xv;
+        if (STAGE_X) {
+          xv = reinterpret_cast<const float4*>(s_x)[c4];
+        } else {
+          const int c = 4 * c4;
+          xv.x = c < A.cols ? __ldg(x + c) : 0.f;
+          xv.y = c + 1 < A.cols ? __ldg(x + c + 1) : 0.f;
+          xv.z = c + 2 < A.cols ? __ldg(x + c + 2) : 0.f;
+          xv.w = c + 3 < A.cols ? __ldg(x + c + 3) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          acc[q] = fmaf(a[q].x, xv.x, acc[q]);
+          acc[q] = fmaf(a[q].y, xv.y, acc[q]);
+          acc[q] = fmaf(a[q].z, xv.z, acc[q]);
+          acc[q] = fmaf(a[q].w, xv.w, acc[q]);
+        }
+      }
+    } else {
+      for (int c4 = tid; c4 < ncol4; c4 += THREADS) {
+        float4 xv;
+        if (STAGE_X) {
+          xv = reinterpret_cast<const float4*>(s_x)[c4];
+        } else {
+          const int c = 4 * c4;
+          xv.x = c < A.cols ? __ldg(x + c) : 0.f;
+          xv.y = c + 1 < A.cols ? __ldg(x + c + 1) : 0.f;
+          xv.z = c + 2 < A.cols ? __ldg(x + c + 2) : 0.f;
+          xv.w = c + 3 < A.cols ? __ldg(x + c + 3) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          if (q < nr) {
+            const float4 a = ld_stream_f4(arow + (int64_t)q * A.ld + 4 * c4, ps);
+            acc[q] = fmaf(a.x, xv.x, acc[q]);
+            acc[q] = fmaf(a.y, xv.y, acc[q]);
+            acc[q] = fmaf(a.z, xv.z, acc[q]);
+            acc[q] = fmaf(a.w, xv.w, acc[q]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) acc[q] = warp_sum(acc[q]);
+    if (lane == 0) {
+#pragma unroll
+      for (int q = 0; q < R; ++q) s_red[buf][warp][q] = acc[q];
+    }
+    __syncthreads();
+    if (tid < nr) {
+      float s = 0.0f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s += s_red[buf][w][tid];
+      y[r + tid] = finish(s, ep.alpha, ep.beta, ep.bias, r + tid, ep.relu);
+    }
+    buf ^= 1;  // the next group writes the other buffer, so one barrier per group is enough
+  }
+}
+
+int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm_count, cudaStream_t s) {
+  if (A.rows <= 0) return HISPMV_OK;
+  constexpr int THREADS = 256, R = 4;
+  const size_t x_bytes = (size_t)A.ld * sizeof(float);
+  const bool stage = x_bytes <= 160 * 1024;
+  int ctas_per_sm = 4;
+  if (stage) {
+    while (ctas_per_sm > 1 && (x_bytes + 1024) * ctas_per_sm > 200 * 1024) --ctas_per_sm;
+  }
+  int64_t grid = (int64_t)sm_count * ctas_per_sm;
+  if (grid > A.rows) grid = A.rows;
+  const int rows_per_cta = (int)((A.rows + grid - 1) / grid);
+  grid = (A.rows + rows_per_cta - 1) / rows_per_cta;
+  if (stage) {
+    auto k = gemv_rowblock_kernel<THREADS, R, true>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      attr_set = true;
+    }
+    k<<<(int)grid, THREADS, x_bytes, s>>>(A, x, y, ep, rows_per_cta);
+  } else {
+    gemv_rowblock_kernel<THREADS, R, false><<<(int)grid, THREADS, 0, s>>>(A, x, y, ep, rows_per_cta);
+  }
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+}  // namespace hispmv

@@ -1,0 +1,100 @@
+// Internal declarations shared by the translation units of libhispmv_cuda.so.
+// Nothing here is part of the C-ABI (see include/hispmv.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "hispmv.h"
+
+namespace hispmv {
+
+void set_error(const std::string& msg);
+// returns HISPMV_OK or records the CUDA error text and returns HISPMV_ERR_CUDA / HISPMV_FULL (OOM)
+int check_cuda(cudaError_t e, const char* what, const char* file, int line);
+#define HISPMV_CUDA(expr)                                                    \
+  do {                                                                       \
+    int _st = ::hispmv::check_cuda((expr), #expr, __FILE__, __LINE__);       \
+    if (_st != HISPMV_OK) return _st;                                        \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Device-side matrix as the kernels see it.
+// ---------------------------------------------------------------------------------------------
+struct CsrDev {
+  int32_t rows = 0;       // local rows (row block held by this GPU)
+  int32_t cols = 0;
+  int64_t nnz = 0;
+  const int32_t* row_ptr = nullptr;  // rows+1, rebased to 0
+  const int32_t* col = nullptr;      // nnz, padded to a multiple of 4 plus 4 (zeros)
+  const float* val = nullptr;        // nnz, same padding
+};
+
+struct MergePlan {
+  int32_t tile_items = 0;        // merge items per CTA (THREADS * ITEMS_PER_THREAD of the instantiation used)
+  int64_t num_tiles = 0;
+  const int32_t* tile_row = nullptr;   // num_tiles+1
+  const int64_t* tile_nnz = nullptr;   // num_tiles+1
+  float* carry = nullptr;              // num_tiles: partial sum of the row left open at each tile's end
+};
+
+struct RowStats {
+  int64_t hist[HISPMV_HIST_BINS];
+  int64_t nnz;
+  int32_t rows;
+  int32_t max_row_nnz;
+  int32_t empty_rows;
+};
+
+// ---- partition.cu ---------------------------------------------------------------------------
+// COO (device) -> CSR (device).  Entries are ordered by (row, col, value) exactly like the reference's
+// per-row std::sort over (col, val) pairs (common/src/spmv-helper.cpp:216; gpu/src/spmvHelper.cpp:139).
+// Outputs are cudaMalloc'ed by the callee; col/val carry the 128-bit padding described in CsrDev.
+int coo_to_csr_device(const int32_t* d_rows, const int32_t* d_cols, const float* d_vals, int64_t nnz, int32_t rows,
+                      int32_t cols, int32_t** d_row_ptr, int32_t** d_col, float** d_val, cudaStream_t stream);
+// Row-length histogram (power-of-two bins) + max / empty counts, computed on the device.
+int row_stats_device(const int32_t* d_row_ptr, int32_t rows, RowStats* out, cudaStream_t stream);
+// Merge-path tile start coordinates for `tile_items` items per tile; arrays cudaMalloc'ed by the callee.
+int merge_tiles_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int32_t tile_items, int64_t* num_tiles,
+                       int32_t** d_tile_row, int64_t** d_tile_nnz, cudaStream_t stream);
+// Rows whose nonzeros span more than one tile, ascending.  d_out cudaMalloc'ed by the callee (may be null if 0).
+int split_rows_device(const int32_t* d_row_ptr, int32_t rows, const int32_t* d_tile_row, const int64_t* d_tile_nnz,
+                      int64_t num_tiles, int32_t** d_out, int64_t* count, cudaStream_t stream);
+// Slice [row_begin,row_end) out of a device CSR into fresh, padded arrays with row_ptr rebased to 0.
+int csr_slice_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t row_begin,
+                     int32_t row_end, int32_t** o_row_ptr, int32_t** o_col, float** o_val, int64_t* o_nnz,
+                     cudaStream_t stream);
+// Pad-copy col/val (device->device or host->device, given by `kind`) into freshly allocated padded arrays.
+int alloc_padded_nnz_arrays(const int32_t* src_col, const float* src_val, int64_t nnz, cudaMemcpyKind kind,
+                            int32_t** d_col, float** d_val, cudaStream_t stream);
+// nnz-balanced split points from a device row_ptr: bounds[k] = lower_bound(row_ptr, k*nnz/n_parts).
+int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int n_parts, int32_t* h_bounds,
+                        cudaStream_t stream);
+
+// The runtime selector (pure host integer arithmetic over RowStats; restated in oracle/).
+void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* kernel, int* lanes);
+// tile_items the merge kernel instantiation uses for a matrix with these stats
+int merge_tile_items_for(const RowStats& st);
+
+// ---- spmv.cu --------------------------------------------------------------------------------
+struct Epilogue {
+  float alpha, beta;
+  const float* bias;  // may be null when beta == 0
+  int relu;           // fused max(.,0) (device-resident chained layers only)
+};
+int launch_csr_scalar(const CsrDev& A, const float* x, float* y, Epilogue ep, cudaStream_t s);
+int launch_csr_vector(const CsrDev& A, int lanes, const float* x, float* y, Epilogue ep, cudaStream_t s);
+int launch_merge(const CsrDev& A, const MergePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
+int launch_empty(int32_t rows, float* y, Epilogue ep, cudaStream_t s);
+bool merge_tile_items_supported(int tile_items);
+
+// ---- gemv.cu --------------------------------------------------------------------------------
+struct DenseDev {
+  int32_t rows = 0, cols = 0;
+  int64_t ld = 0;           // leading dimension in floats (multiple of 4 so every row is 16-byte aligned)
+  const float* a = nullptr;
+};
+int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm_count, cudaStream_t s);
+
+}  // namespace hispmv

@@ -1,0 +1,476 @@
+// GPU-side partitioner: COO -> CSR, row-length histogram, runtime kernel selector, merge-path tile
+// descriptors with heavy rows split across CTAs, nnz-balanced row blocks for multi-GPU.
+//
+// Replaces the reference's host preprocessing (semantics, not structure):
+//   tileAndPad(COO)     count / prefix / bucket / sort rows by column    common/src/spmv-helper.cpp:139-227
+//   cooToCsr            the same as a flat CSR                           gpu/src/spmvHelper.cpp:117-156
+//   balanceWorkload     which rows must be shared between PEs            common/src/spmv-helper.cpp:265-347
+//   computeTileSize / prepareTile  the balanced schedule                 common/src/spmv-helper.cpp:429-638
+//   DSE.getBestConfig   per-matrix configuration choice                  automation_tool/src/dse.py:23-95
+//
+// Integer outputs (row_ptr, col order, tile coordinates, split-row list, shard bounds, kernel choice)
+// are bit-exact against the single-threaded restatement in oracle/oracle.c.
+// CUB (shipped with the CUDA toolkit) provides the radix sort and the prefix sum; everything else is
+// written here.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "internal.h"
+
+namespace hispmv {
+
+namespace {
+
+struct DevBuf {  // RAII for scratch allocations inside one call
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    if (bytes == 0) bytes = 16;
+    return check_cuda(cudaMalloc(&p, bytes), "cudaMalloc(scratch)", __FILE__, __LINE__);
+  }
+  template <typename T>
+  T* as() {
+    return static_cast<T*>(p);
+  }
+};
+
+inline int blocks_for(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
+
+// order-preserving map float -> uint32 (so that an unsigned radix sort orders like operator< on float)
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void iota_and_valkey_kernel(const float* __restrict__ vals, int64_t nnz, uint32_t* __restrict__ key,
+                                       uint32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) {
+    if (key) key[i] = float_order_key(vals[i]);
+    idx[i] = (uint32_t)i;
+  }
+}
+
+// key64 = row:col of entry idx[i]; also validates the index ranges (the reference does not; we refuse)
+__global__ void make_rowcol_key_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ cols,
+                                       const uint32_t* __restrict__ idx, int64_t nnz, int32_t n_rows, int32_t n_cols,
+                                       uint64_t* __restrict__ key, int* __restrict__ bad) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) {
+    const uint32_t e = idx ? idx[i] : (uint32_t)i;
+    const int32_t r = rows[e], c = cols[e];
+    if (r < 0 || r >= n_rows || c < 0 || c >= n_cols) *bad = 1;
+    key[i] = ((uint64_t)(uint32_t)r << 32) | (uint32_t)c;
+  }
+}
+
+__global__ void has_adjacent_dup_kernel(const uint64_t* __restrict__ key, int64_t nnz, int* __restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + 1 < nnz && key[i] == key[i + 1]) *flag = 1;
+}
+
+__global__ void scatter_sorted_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ idx,
+                                      const float* __restrict__ vals, int64_t nnz, int64_t padded,
+                                      int32_t* __restrict__ col, float* __restrict__ val) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) {
+    col[i] = (int32_t)(uint32_t)(key[i] & 0xffffffffu);
+    val[i] = vals[idx[i]];
+  } else if (i < padded) {
+    col[i] = 0;
+    val[i] = 0.0f;
+  }
+}
+
+// row_ptr[r] = number of sorted entries whose row is < r  (lower bound on the high half of the key)
+__global__ void row_ptr_from_sorted_kernel(const uint64_t* __restrict__ key, int64_t nnz, int32_t rows,
+                                           int32_t* __restrict__ row_ptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > rows) return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)(key[mid] >> 32) < r) lo = mid + 1; else hi = mid;
+  }
+  row_ptr[r] = (int32_t)lo;
+}
+
+__global__ void row_stats_kernel(const int32_t* __restrict__ row_ptr, int32_t rows,
+                                 unsigned long long* __restrict__ hist, int* __restrict__ max_len) {
+  __shared__ unsigned int s_hist[HISPMV_HIST_BINS];
+  __shared__ int s_max;
+  if (threadIdx.x < HISPMV_HIST_BINS) s_hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int local_max = 0;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += stride) {
+    const int len = row_ptr[r + 1] - row_ptr[r];
+    const int bin = len <= 0 ? 0 : 32 - __clz(len);
+    atomicAdd(&s_hist[bin], 1u);
+    local_max = max(local_max, len);
+  }
+  atomicMax(&s_max, local_max);
+  __syncthreads();
+  if (threadIdx.x < HISPMV_HIST_BINS && s_hist[threadIdx.x])
+    atomicAdd(&hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
+  if (threadIdx.x == 0) atomicMax(max_len, s_max);
+}
+
+// Merge-path diagonal search over (row ends) x (nonzero indices); see oracle_merge_tiles.
+__global__ void merge_tiles_kernel(const int32_t* __restrict__ row_ptr, int32_t rows, int64_t nnz, int32_t tile_items,
+                                   int64_t num_tiles, int32_t* __restrict__ tile_row, int64_t* __restrict__ tile_nnz) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > num_tiles) return;
+  const int64_t total = (int64_t)rows + nnz;
+  int64_t diag = t * (int64_t)tile_items;
+  if (diag > total) diag = total;
+  int64_t lo = diag > nnz ? diag - nnz : 0;
+  int64_t hi = diag < rows ? diag : rows;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)row_ptr[mid + 1] <= diag - mid - 1) lo = mid + 1; else hi = mid;
+  }
+  tile_row[t] = (int32_t)lo;
+  tile_nnz[t] = diag - lo;
+}
+
+// flag[t-1] = 1 when boundary t (1 <= t < num_tiles) is the first one that cuts row tile_row[t]
+// after at least one of its nonzeros.
+__global__ void split_flag_kernel(const int32_t* __restrict__ row_ptr, int32_t rows,
+                                  const int32_t* __restrict__ tile_row, const int64_t* __restrict__ tile_nnz,
+                                  int64_t num_tiles, int32_t* __restrict__ flag) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (t >= num_tiles) return;
+  const int32_t r = tile_row[t];
+  int f = 0;
+  if (r < rows && tile_nnz[t] > (int64_t)row_ptr[r]) {
+    f = 1;
+    if (t > 1 && tile_row[t - 1] == r && tile_nnz[t - 1] > (int64_t)row_ptr[r]) f = 0;
+  }
+  flag[t - 1] = f;
+}
+
+__global__ void split_scatter_kernel(const int32_t* __restrict__ tile_row, const int32_t* __restrict__ flag,
+                                     const int32_t* __restrict__ pos, int64_t n, int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && flag[i]) out[pos[i]] = tile_row[i + 1];
+}
+
+__global__ void rebase_row_ptr_kernel(const int32_t* __restrict__ src, int32_t row_begin, int32_t n_rows,
+                                      int32_t* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= n_rows) dst[i] = src[row_begin + i] - src[row_begin];
+}
+
+__global__ void zero_pad_kernel(int32_t* col, float* val, int64_t nnz, int64_t padded) {
+  const int64_t i = nnz + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < padded) {
+    col[i] = 0;
+    val[i] = 0.0f;
+  }
+}
+
+__global__ void shard_bounds_kernel(const int32_t* __restrict__ row_ptr, int32_t rows, int64_t nnz, int n_parts,
+                                    int32_t* __restrict__ bounds) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_parts) return;
+  if (k == 0) { bounds[0] = 0; return; }
+  if (k == n_parts) { bounds[k] = rows; return; }
+  const int64_t target = (nnz * (int64_t)k) / n_parts;
+  int64_t lo = 0, hi = rows;  // first row index r with row_ptr[r] >= target
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)row_ptr[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  bounds[k] = (int32_t)lo;
+}
+
+inline int64_t padded_nnz(int64_t nnz) { return ((nnz + 3) & ~(int64_t)3) + 4; }
+
+}  // namespace
+
+int alloc_padded_nnz_arrays(const int32_t* src_col, const float* src_val, int64_t nnz, cudaMemcpyKind kind,
+                            int32_t** d_col, float** d_val, cudaStream_t stream) {
+  const int64_t pad = padded_nnz(nnz);
+  *d_col = nullptr;
+  *d_val = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)d_col, pad * sizeof(int32_t)));
+  int st = check_cuda(cudaMalloc((void**)d_val, pad * sizeof(float)), "cudaMalloc(val)", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    cudaFree(*d_col);
+    *d_col = nullptr;
+    return st;
+  }
+  if (nnz > 0) {
+    HISPMV_CUDA(cudaMemcpyAsync(*d_col, src_col, nnz * sizeof(int32_t), kind, stream));
+    HISPMV_CUDA(cudaMemcpyAsync(*d_val, src_val, nnz * sizeof(float), kind, stream));
+  }
+  zero_pad_kernel<<<1, 32, 0, stream>>>(*d_col, *d_val, nnz, pad);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int coo_to_csr_device(const int32_t* d_rows, const int32_t* d_cols, const float* d_vals, int64_t nnz, int32_t rows,
+                      int32_t cols, int32_t** d_row_ptr, int32_t** d_col, float** d_val, cudaStream_t stream) {
+  *d_row_ptr = nullptr;
+  *d_col = nullptr;
+  *d_val = nullptr;
+  if (nnz >= (int64_t)INT32_MAX) {
+    set_error("coo_to_csr: nnz must be below 2^31 per GPU (int32 row_ptr, as in the reference)");
+    return HISPMV_ERR_ARG;
+  }
+  const int64_t pad = padded_nnz(nnz);
+  DevBuf key_a, key_b, idx_a, idx_b, vkey_a, vkey_b, tmp, flags;
+  int st;
+  if ((st = key_a.alloc(nnz * 8)) || (st = key_b.alloc(nnz * 8)) || (st = idx_a.alloc(nnz * 4)) ||
+      (st = idx_b.alloc(nnz * 4)) || (st = flags.alloc(2 * sizeof(int))))
+    return st;
+  HISPMV_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), stream));
+  int* d_bad = flags.as<int>();
+  int* d_dup = flags.as<int>() + 1;
+  const int B = 256;
+
+  cub::DoubleBuffer<uint64_t> keys(key_a.as<uint64_t>(), key_b.as<uint64_t>());
+  cub::DoubleBuffer<uint32_t> idx(idx_a.as<uint32_t>(), idx_b.as<uint32_t>());
+  int end_bit = 64;  // only sort the bits that can be set
+  {
+    int rb = 1, cb = 1;
+    while (rb < 32 && (1LL << rb) < (int64_t)rows) ++rb;
+    while (cb < 32 && (1LL << cb) < (int64_t)cols) ++cb;
+    end_bit = 32 + rb;
+    (void)cb;
+  }
+
+  if (nnz > 0) {
+    // pass 1: sort by (row, col) only
+    iota_and_valkey_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(d_vals, nnz, nullptr, idx.Current());
+    make_rowcol_key_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(d_rows, d_cols, nullptr, nnz, rows, cols,
+                                                                 keys.Current(), d_bad);
+    HISPMV_CUDA(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, idx, nnz, 0, end_bit, stream));
+    if ((st = tmp.alloc(tmp_bytes))) return st;
+    HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, keys, idx, nnz, 0, end_bit, stream));
+    has_adjacent_dup_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), nnz, d_dup);
+    int h_flags[2];
+    HISPMV_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, stream));
+    HISPMV_CUDA(cudaStreamSynchronize(stream));
+    if (h_flags[0]) {
+      set_error("coo_to_csr: a row or column index is outside [0,rows) x [0,cols)");
+      return HISPMV_ERR_ARG;
+    }
+    if (h_flags[1]) {
+      // Duplicated (row, col) pairs: the reference orders them by value (std::sort over (col, val) pairs,
+      // spmv-helper.cpp:216).  Redo as an LSD sort: value key first, then a stable sort on (row, col).
+      if ((st = vkey_a.alloc(nnz * 4)) || (st = vkey_b.alloc(nnz * 4))) return st;
+      cub::DoubleBuffer<uint32_t> vkeys(vkey_a.as<uint32_t>(), vkey_b.as<uint32_t>());
+      iota_and_valkey_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(d_vals, nnz, vkeys.Current(), idx.Current());
+      size_t tb2 = 0;
+      HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb2, vkeys, idx, nnz, 0, 32, stream));
+      if (tb2 > tmp_bytes) {
+        if ((st = tmp.alloc(tb2))) return st;
+        tmp_bytes = tb2;
+      }
+      HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb2, vkeys, idx, nnz, 0, 32, stream));
+      make_rowcol_key_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(d_rows, d_cols, idx.Current(), nnz, rows, cols,
+                                                                   keys.Current(), d_bad);
+      size_t tb3 = 0;
+      HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb3, keys, idx, nnz, 0, end_bit, stream));
+      if (tb3 > tmp_bytes) {
+        if ((st = tmp.alloc(tb3))) return st;
+        tmp_bytes = tb3;
+      }
+      HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb3, keys, idx, nnz, 0, end_bit, stream));
+    }
+  }
+
+  HISPMV_CUDA(cudaMalloc((void**)d_row_ptr, ((size_t)rows + 1) * sizeof(int32_t)));
+  st = check_cuda(cudaMalloc((void**)d_col, pad * sizeof(int32_t)), "cudaMalloc(col)", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)d_val, pad * sizeof(float)), "cudaMalloc(val)", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    cudaFree(*d_row_ptr);
+    cudaFree(*d_col);
+    *d_row_ptr = nullptr;
+    *d_col = nullptr;
+    return st;
+  }
+  scatter_sorted_kernel<<<blocks_for(pad, B), B, 0, stream>>>(keys.Current(), idx.Current(), d_vals, nnz, pad, *d_col,
+                                                              *d_val);
+  row_ptr_from_sorted_kernel<<<blocks_for((int64_t)rows + 1, B), B, 0, stream>>>(keys.Current(), nnz, rows,
+                                                                                 *d_row_ptr);
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaStreamSynchronize(stream));  // scratch buffers die at scope exit
+  return HISPMV_OK;
+}
+
+int row_stats_device(const int32_t* d_row_ptr, int32_t rows, RowStats* out, cudaStream_t stream) {
+  DevBuf buf;
+  int st;
+  const size_t bytes = HISPMV_HIST_BINS * sizeof(unsigned long long) + sizeof(int) * 2;
+  if ((st = buf.alloc(bytes))) return st;
+  HISPMV_CUDA(cudaMemsetAsync(buf.p, 0, bytes, stream));
+  unsigned long long* d_hist = buf.as<unsigned long long>();
+  int* d_max = reinterpret_cast<int*>(d_hist + HISPMV_HIST_BINS);
+  if (rows > 0) {
+    const int grid = (int)std::min<int64_t>(blocks_for(rows, 256), 148 * 16);
+    row_stats_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, rows, d_hist, d_max);
+    HISPMV_CUDA(cudaGetLastError());
+  }
+  unsigned long long h_hist[HISPMV_HIST_BINS];
+  int h_max = 0;
+  int32_t h_last = 0;
+  HISPMV_CUDA(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last, d_row_ptr + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  for (int i = 0; i < HISPMV_HIST_BINS; ++i) out->hist[i] = (int64_t)h_hist[i];
+  out->rows = rows;
+  out->nnz = h_last;
+  out->max_row_nnz = h_max;
+  out->empty_rows = (int32_t)h_hist[0];
+  return HISPMV_OK;
+}
+
+int merge_tiles_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int32_t tile_items, int64_t* num_tiles,
+                       int32_t** d_tile_row, int64_t** d_tile_nnz, cudaStream_t stream) {
+  const int64_t total = (int64_t)rows + nnz;
+  const int64_t nt = std::max<int64_t>(1, (total + tile_items - 1) / tile_items);
+  *num_tiles = nt;
+  *d_tile_row = nullptr;
+  *d_tile_nnz = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)d_tile_row, (nt + 1) * sizeof(int32_t)));
+  int st = check_cuda(cudaMalloc((void**)d_tile_nnz, (nt + 1) * sizeof(int64_t)), "cudaMalloc(tile_nnz)", __FILE__,
+                      __LINE__);
+  if (st != HISPMV_OK) {
+    cudaFree(*d_tile_row);
+    *d_tile_row = nullptr;
+    return st;
+  }
+  merge_tiles_kernel<<<blocks_for(nt + 1, 256), 256, 0, stream>>>(d_row_ptr, rows, nnz, tile_items, nt, *d_tile_row,
+                                                                  *d_tile_nnz);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int split_rows_device(const int32_t* d_row_ptr, int32_t rows, const int32_t* d_tile_row, const int64_t* d_tile_nnz,
+                      int64_t num_tiles, int32_t** d_out, int64_t* count, cudaStream_t stream) {
+  *d_out = nullptr;
+  *count = 0;
+  const int64_t n = num_tiles - 1;  // interior boundaries
+  if (n <= 0) return HISPMV_OK;
+  DevBuf flag, pos, tmp;
+  int st;
+  if ((st = flag.alloc(n * sizeof(int32_t))) || (st = pos.alloc(n * sizeof(int32_t)))) return st;
+  split_flag_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(d_row_ptr, rows, d_tile_row, d_tile_nnz, num_tiles,
+                                                            flag.as<int32_t>());
+  size_t tb = 0;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.as<int32_t>(), pos.as<int32_t>(), n, stream));
+  if ((st = tmp.alloc(tb))) return st;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.as<int32_t>(), pos.as<int32_t>(), n, stream));
+  int32_t last_pos = 0, last_flag = 0;
+  HISPMV_CUDA(cudaMemcpyAsync(&last_pos, pos.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&last_flag, flag.as<int32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  const int64_t cnt = (int64_t)last_pos + last_flag;
+  *count = cnt;
+  if (cnt > 0) {
+    HISPMV_CUDA(cudaMalloc((void**)d_out, cnt * sizeof(int32_t)));
+    split_scatter_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(d_tile_row, flag.as<int32_t>(), pos.as<int32_t>(), n,
+                                                                 *d_out);
+    HISPMV_CUDA(cudaGetLastError());
+    HISPMV_CUDA(cudaStreamSynchronize(stream));
+  }
+  return HISPMV_OK;
+}
+
+int csr_slice_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t row_begin,
+                     int32_t row_end, int32_t** o_row_ptr, int32_t** o_col, float** o_val, int64_t* o_nnz,
+                     cudaStream_t stream) {
+  int32_t h[2] = {0, 0};
+  HISPMV_CUDA(cudaMemcpyAsync(&h[0], d_row_ptr + row_begin, 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h[1], d_row_ptr + row_end, 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  const int64_t nnz = (int64_t)h[1] - h[0];
+  const int32_t n_rows = row_end - row_begin;
+  *o_nnz = nnz;
+  *o_row_ptr = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)o_row_ptr, ((size_t)n_rows + 1) * sizeof(int32_t)));
+  rebase_row_ptr_kernel<<<blocks_for((int64_t)n_rows + 1, 256), 256, 0, stream>>>(d_row_ptr, row_begin, n_rows,
+                                                                                  *o_row_ptr);
+  int st = alloc_padded_nnz_arrays(d_col + h[0], d_val + h[0], nnz, cudaMemcpyDeviceToDevice, o_col, o_val, stream);
+  if (st != HISPMV_OK) {
+    cudaFree(*o_row_ptr);
+    *o_row_ptr = nullptr;
+    return st;
+  }
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int n_parts, int32_t* h_bounds,
+                        cudaStream_t stream) {
+  DevBuf b;
+  int st;
+  if ((st = b.alloc((n_parts + 1) * sizeof(int32_t)))) return st;
+  shard_bounds_kernel<<<blocks_for(n_parts + 1, 64), 64, 0, stream>>>(d_row_ptr, rows, nnz, n_parts, b.as<int32_t>());
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaMemcpyAsync(h_bounds, b.p, (n_parts + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  return HISPMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Runtime selector.  Pure integer arithmetic on the row-length histogram so that the CPU restatement
+// (oracle/oracle.c: oracle_select_kernel) reproduces the decision bit for bit.
+//
+// The FPGA design space (channels A:B:C, pre-accumulator, row-distribution network; dse.py:23-95)
+// collapses on a GPU to one question: is the row-length distribution regular enough that a fixed number
+// of lanes per row keeps every lane busy, or must work be balanced by nonzeros with heavy rows split?
+//   mean  = ceil(nnz / rows);  lanes = largest power of two <= mean, clamped to [2, 32]
+//   MERGE       if row splitting is allowed and any of
+//                 heavy       max row  > 32 * max(mean, 4)      (one row would serialise a sub-warp)
+//                 hollow      more than half of the rows are empty
+//                 underfilled rows * lanes < 148 SMs * 1024 threads (too few rows to fill the GPU)
+//   CSR_SCALAR  else if mean <= 2
+//   CSR_VECTOR  else, with `lanes` lanes per row
+// ------------------------------------------------------------------------------------------------
+void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* kernel, int* lanes) {
+  (void)cols;
+  *lanes = 0;
+  if (st.rows <= 0 || st.nnz <= 0) {
+    *kernel = HISPMV_KERNEL_EMPTY;
+    return;
+  }
+  const int64_t mean = (st.nnz + st.rows - 1) / st.rows;
+  int l = 2;
+  while (l < 32 && (int64_t)l * 2 <= mean) l *= 2;
+  const bool heavy = (int64_t)st.max_row_nnz > 32 * std::max<int64_t>(mean, 4);
+  const bool hollow = (int64_t)st.empty_rows * 2 > (int64_t)st.rows;
+  const bool underfilled = (int64_t)st.rows * l < 148LL * 1024;
+  if (allow_split_rows && (heavy || hollow || underfilled)) {
+    *kernel = HISPMV_KERNEL_MERGE;
+    return;
+  }
+  if (mean <= 2) {
+    *kernel = HISPMV_KERNEL_CSR_SCALAR;
+    return;
+  }
+  *kernel = HISPMV_KERNEL_CSR_VECTOR;
+  *lanes = l;
+}
+
+int merge_tile_items_for(const RowStats& st) {
+  // small problems: smaller tiles so that there are enough CTAs to cover 148 SMs
+  const int64_t total = (int64_t)st.rows + st.nnz;
+  if (total < 148LL * 4 * 1792) return 128 * 7;
+  return 256 * 7;
+}
+
+}  // namespace hispmv

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's accelerator handle, over the C-ABI.
+
+`Engine` has the reference's method names and argument meaning (pyhispmv/src/pyhispmv_bindings.cpp:6-39:
+create_dense_handle / create_sparse_handle / load_matrices / select_matrix / run_kernel / linear) and adds
+device-resident variants that take torch CUDA tensors (`run_dev`, `linear_dev`) so benchmarks and chained
+layers never cross PCIe.  The compiled `pyhispmv` module is the drop-in users import; this class is what
+bench.py, the sharded runner and the tests drive.  torch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import lib, check
+
+
+def _np(a, dtype) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a: np.ndarray) -> C.c_void_p:
+    return C.c_void_p(a.ctypes.data)
+
+
+def _dptr(t) -> C.c_void_p:
+    """Device pointer of a torch CUDA tensor (None -> NULL)."""
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_cuda or not t.is_contiguous():
+        raise ValueError("expected a contiguous CUDA tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    """One GPU, many matrices.  Mirrors FpgaHandle (pyhispmv/include/fpga_handle.h:9-74)."""
+
+    def __init__(self, device_id: int = 0, dense_overlay: bool = True, row_dist_net: bool = True,
+                 shard: Optional[Sequence[int]] = None, memory_limit: int = 0):
+        flags = (capi.FLAG_DENSE_OVERLAY if dense_overlay else 0) | (capi.FLAG_ROW_DIST_NET if row_dist_net else 0)
+        ctx = C.c_void_p()
+        check(lib.hispmv_create(C.byref(ctx), device_id, flags), "hispmv_create")
+        self._ctx = ctx
+        self.device_id = device_id
+        if shard is not None:
+            check(lib.hispmv_set_shard(self._ctx, int(shard[0]), int(shard[1])), "hispmv_set_shard")
+        if memory_limit:
+            check(lib.hispmv_set_memory_limit(self._ctx, int(memory_limit)), "hispmv_set_memory_limit")
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            lib.hispmv_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the reference surface -------------------------------------------------------------------
+    def create_dense_handle(self, flattened_dense_values, rows: int, cols: int) -> int:
+        a = _np(flattened_dense_values, np.float32).reshape(-1)
+        if a.size < rows * cols:
+            raise ValueError("flattened_dense_values is shorter than rows*cols")
+        return check(lib.hispmv_add_dense(self._ctx, _ptr(a), rows, cols), "create_dense_handle")
+
+    def create_sparse_handle(self, coo_rows, coo_cols, coo_values, rows: int, cols: int) -> int:
+        r, c, v = _np(coo_rows, np.int32), _np(coo_cols, np.int32), _np(coo_values, np.float32)
+        if not (r.size == c.size == v.size):
+            raise ValueError("coo_rows, coo_cols and coo_values differ in length")
+        return check(lib.hispmv_add_sparse_coo(self._ctx, _ptr(r), _ptr(c), _ptr(v), r.size, rows, cols),
+                     "create_sparse_handle")
+
+    def load_matrices(self) -> None:
+        check(lib.hispmv_commit(self._ctx), "load_matrices")
+
+    def select_matrix(self, matrix_idx: int) -> None:
+        if matrix_idx < 0:
+            raise IndexError("Matrix idx out of range")
+        check(lib.hispmv_select(self._ctx, matrix_idx), "select_matrix")
+        self._selected = matrix_idx
+
+    def run_kernel(self, x, bias, y: np.ndarray, alpha: float, beta: float) -> None:
+        if not (isinstance(y, np.ndarray) and y.dtype == np.float32 and y.flags.c_contiguous):
+            raise TypeError("y must be a C-contiguous float32 numpy array (it is written in place)")
+        xs, bs = _np(x, np.float32), _np(bias, np.float32)
+        check(lib.hispmv_run(self._ctx, _ptr(xs), _ptr(bs), _ptr(y), alpha, beta), "run_kernel")
+
+    def linear(self, matrix_idx: int, x, bias) -> np.ndarray:
+        info = self.matrix_info(matrix_idx)
+        xs, bs = _np(x, np.float32).reshape(-1), _np(bias, np.float32)
+        n_y = info["row_end"] - info["row_begin"]
+        num_vecs = xs.size // info["cols"]
+        y = np.empty(num_vecs * n_y, dtype=np.float32)
+        check(lib.hispmv_linear(self._ctx, matrix_idx, _ptr(xs), xs.size, _ptr(bs), _ptr(y)), "linear")
+        return y
+
+    # ---- beyond the reference: CSR / device inputs, plans ---------------------------------------------
+    def create_sparse_handle_csr(self, row_ptr, col_idx, values, rows: int, cols: int) -> int:
+        rp, ci, v = _np(row_ptr, np.int32), _np(col_idx, np.int32), _np(values, np.float32)
+        return check(lib.hispmv_add_sparse_csr(self._ctx, _ptr(rp), _ptr(ci), _ptr(v), rows, cols),
+                     "create_sparse_handle_csr")
+
+    def create_sparse_handle_csr_dev(self, d_row_ptr: int, d_col: int, d_val: int, rows: int, cols: int) -> int:
+        return check(lib.hispmv_add_sparse_csr_dev(self._ctx, C.c_void_p(d_row_ptr), C.c_void_p(d_col),
+                                                   C.c_void_p(d_val), rows, cols), "create_sparse_handle_csr_dev")
+
+    def create_sparse_handle_coo_dev(self, rows_t, cols_t, vals_t, rows: int, cols: int) -> int:
+        return check(lib.hispmv_add_sparse_coo_dev(self._ctx, _dptr(rows_t), _dptr(cols_t), _dptr(vals_t),
+                                                   rows_t.numel(), rows, cols), "create_sparse_handle_coo_dev")
+
+    def create_dense_handle_dev(self, a_t, rows: int, cols: int) -> int:
+        return check(lib.hispmv_add_dense_dev(self._ctx, _dptr(a_t), rows, cols), "create_dense_handle_dev")
+
+    def load_mtx(self, path: str) -> int:
+        return check(lib.hispmv_load_mtx(self._ctx, path.encode()), "load_mtx")
+
+    def force_kernel(self, matrix_idx: int, kernel: int, lanes: int = 0) -> None:
+        check(lib.hispmv_force_kernel(self._ctx, matrix_idx, kernel, lanes), "force_kernel")
+
+    def run_dev(self, matrix_idx: int, x, bias, y, alpha: float = 1.0, beta: float = 0.0, stream: int = 0) -> None:
+        """y = alpha*A@x + beta*bias on torch CUDA tensors, asynchronous on `stream` (a cudaStream_t int;
+        0 = the engine's own stream)."""
+        check(lib.hispmv_run_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), alpha, beta,
+                                 C.c_void_p(stream)), "run_dev")
+
+    def linear_dev(self, matrix_idx: int, x, bias, y, relu: bool = False, stream: int = 0) -> None:
+        check(lib.hispmv_linear_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), int(relu),
+                                    C.c_void_p(stream)), "linear_dev")
+
+    def sync(self) -> None:
+        check(lib.hispmv_sync(self._ctx), "sync")
+
+    def launches_per_run(self, matrix_idx: int) -> int:
+        return check(lib.hispmv_launches_per_run(self._ctx, matrix_idx), "launches_per_run")
+
+    def num_matrices(self) -> int:
+        return lib.hispmv_num_matrices(self._ctx)
+
+    def matrix_info(self, matrix_idx: int) -> dict:
+        info = capi.MatrixInfo()
+        check(lib.hispmv_matrix_info_get(self._ctx, matrix_idx, C.byref(info)), "matrix_info")
+        d = {name: getattr(info, name) for name, _ in capi.MatrixInfo._fields_ if name != "hist"}
+        d["hist"] = list(info.hist)
+        d["is_dense"] = bool(info.is_dense)
+        d["kernel_name"] = capi.KERNEL_NAMES.get(info.kernel, "?")
+        return d
+
+    def plan_csr(self, matrix_idx: int):
+        info = self.matrix_info(matrix_idx)
+        n = info["row_end"] - info["row_begin"]
+        rp = np.empty(n + 1, np.int32)
+        ci = np.empty(info["nnz"], np.int32)
+        v = np.empty(info["nnz"], np.float32)
+        check(lib.hispmv_plan_csr(self._ctx, matrix_idx, _ptr(rp), _ptr(ci), _ptr(v)), "plan_csr")
+        return rp, ci, v
+
+    def plan_tiles(self, matrix_idx: int):
+        info = self.matrix_info(matrix_idx)
+        tr = np.empty(info["num_tiles"] + 1, np.int32)
+        tn = np.empty(info["num_tiles"] + 1, np.int64)
+        check(lib.hispmv_plan_tiles(self._ctx, matrix_idx, _ptr(tr), _ptr(tn)), "plan_tiles")
+        return tr, tn
+
+    def plan_split_rows(self, matrix_idx: int) -> np.ndarray:
+        info = self.matrix_info(matrix_idx)
+        out = np.empty(info["num_split_rows"], np.int32)
+        check(lib.hispmv_plan_split_rows(self._ctx, matrix_idx, _ptr(out)), "plan_split_rows")
+        return out
+
+
+def shard_bounds(row_ptr, n_parts: int) -> np.ndarray:
+    rp = _np(row_ptr, np.int32)
+    out = np.empty(n_parts + 1, np.int32)
+    check(lib.hispmv_shard_bounds(_ptr(rp), rp.size - 1, n_parts, _ptr(out)), "shard_bounds")
+    return out

@@ -1,0 +1,162 @@
+/*
+ * hispmv.h -- C-ABI of libhispmv_cuda.so: the B200 (sm_100a) SpMV / GeMV engine behind HiSpMV's plugin surface.
+ *
+ * This is the drop-in boundary.  Everything above it (the `pyhispmv` pybind11 module, the apps/ scripts,
+ * a cgo/ctypes/JNI binding) sees plain pointers and sizes; everything below it is hand-written CUDA.
+ * There is no CPU fallback and no backend dispatch: every entry point fails with HISPMV_ERR_CUDA when no
+ * sm_100 device is usable.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo):
+ *
+ *   hispmv_create            FpgaHandle::FpgaHandle                 pyhispmv/src/fpga_handle.cpp:40-154
+ *   hispmv_destroy           (reference never frees; no dtor)       pyhispmv/include/fpga_handle.h:9-74
+ *   hispmv_add_sparse_coo    FpgaHandle::createSparseMtxHandle      pyhispmv/src/fpga_handle.cpp:156-207
+ *                            -> HiSpmvHandle::prepareSparseMtxForFPGA common/src/spmv-helper.cpp:648-715
+ *   hispmv_add_sparse_csr    same, for callers that already hold CSR (cpu/src/main.cpp:26-32)
+ *   hispmv_add_dense         FpgaHandle::createDenseMtxHandle       pyhispmv/src/fpga_handle.cpp:209-250
+ *                            -> HiSpmvHandle::prepareDenseMtxForFPGA common/src/spmv-helper.cpp:717-750
+ *   hispmv_commit            FpgaHandle::loadMatrices               pyhispmv/src/fpga_handle.cpp:252-264
+ *   hispmv_select            FpgaHandle::selectMatrix               pyhispmv/src/fpga_handle.cpp:266-283
+ *   hispmv_run               FpgaHandle::runKernel                  pyhispmv/src/fpga_handle.cpp:286-321
+ *   hispmv_linear            FpgaHandle::runLinear                  pyhispmv/src/fpga_handle.cpp:323-388
+ *   hispmv_run_dev           the SpMV() kernel invocation itself    automation_tool/assets/top_function.cpp:1-47,
+ *                            y = beta*c_in + alpha*(A x)            automation_tool/assets/base_functions.cpp:535
+ *   hispmv_plan_* / hispmv_matrix_info
+ *                            balanceWorkload's shared-row list and the tiling facts the reference prints
+ *                            common/src/spmv-helper.cpp:242-347; automation_tool/src/dse.py:23-95 (selector)
+ *   hispmv_load_mtx          HiSpmvHandle::loadMtx                  common/src/spmv-helper.cpp:34-136
+ *
+ * Semantics kept from the reference: COO input is unsorted, duplicates are kept as separate entries and
+ * therefore summed, explicit zeros are kept, indices are int32 and values fp32; handle indices are handed
+ * out in creation order; -1 means "device memory full" (fpga_handle.cpp:192-195,235-238);
+ * run computes y = alpha * A x + beta * bias (base_functions.cpp:535); linear uses alpha = beta = 1
+ * (fpga_handle.cpp:351-352) on len(x)/cols vectors one after the other.
+ * Differences (documented in INTEGRATION.md): errors are returned, never exit(); commit is idempotent and
+ * handles may be added after it; destroy frees device memory.
+ */
+#ifndef HISPMV_H_
+#define HISPMV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hispmv_ctx hispmv_ctx;
+
+/* status codes (negative = failure).  HISPMV_FULL keeps the reference's -1 sentinel. */
+enum {
+  HISPMV_OK = 0,
+  HISPMV_FULL = -1,         /* device memory exhausted while adding a matrix */
+  HISPMV_ERR_ARG = -2,      /* bad argument / misuse (reference: assert) */
+  HISPMV_ERR_INDEX = -3,    /* matrix index out of range (reference: exit(1), fpga_handle.cpp:267-270) */
+  HISPMV_ERR_CUDA = -4,     /* CUDA runtime failure, no usable device */
+  HISPMV_ERR_STATE = -5,    /* run before select, dense handle while dense_overlay is off, ... */
+  HISPMV_ERR_IO = -6        /* Matrix Market file problems */
+};
+
+/* kernel strategies the runtime selector chooses between (hispmv_matrix_info.kernel) */
+enum {
+  HISPMV_KERNEL_AUTO = 0,        /* let the row-length histogram decide */
+  HISPMV_KERNEL_CSR_SCALAR = 1,  /* one thread per row: very short, regular rows */
+  HISPMV_KERNEL_CSR_VECTOR = 2,  /* a sub-warp of 2..32 lanes per row: regular rows */
+  HISPMV_KERNEL_MERGE = 3,       /* merge-path tiles, heavy rows split across CTAs, carry-out fix-up */
+  HISPMV_KERNEL_GEMV = 4,        /* dense overlay: streaming row-major GeMV */
+  HISPMV_KERNEL_EMPTY = 5        /* nnz == 0: y = beta * bias */
+};
+
+/* ctor flags: the reference's hardware switches that still mean something on a GPU */
+enum {
+  HISPMV_FLAG_DENSE_OVERLAY = 1, /* dense_overlay: allow hispmv_add_dense (spmv-helper.cpp:718 asserts it) */
+  HISPMV_FLAG_ROW_DIST_NET = 2   /* row_dist_net: allow heavy rows to be split across CTAs (merge kernel) */
+};
+
+#define HISPMV_HIST_BINS 33
+
+typedef struct hispmv_matrix_info {
+  int32_t rows, cols;       /* global shape as given by the caller */
+  int32_t row_begin, row_end; /* the row block this context holds (whole matrix unless sharded) */
+  int64_t nnz;              /* nonzeros held locally (dense: local_rows*cols) */
+  int32_t is_dense;
+  int32_t kernel;           /* HISPMV_KERNEL_* actually planned */
+  int32_t vector_lanes;     /* sub-warp width when kernel == CSR_VECTOR */
+  int32_t tile_items;       /* merge items (row ends + nonzeros) per CTA when kernel == MERGE */
+  int64_t num_tiles;        /* merge tiles (CTAs) */
+  int64_t num_split_rows;   /* rows whose nonzeros span more than one tile (the "shared rows") */
+  int32_t max_row_nnz;
+  int32_t empty_rows;
+  int64_t hist[HISPMV_HIST_BINS]; /* hist[0]: empty rows; hist[k]: rows with 2^(k-1) <= nnz < 2^k */
+  int64_t device_bytes;     /* HBM held by this matrix, incl. plan metadata */
+} hispmv_matrix_info;
+
+const char* hispmv_last_error(void);
+int hispmv_version(void);
+
+/* device_id: CUDA ordinal.  flags: HISPMV_FLAG_*.  Fails (no fallback) if the device is not sm_100. */
+int hispmv_create(hispmv_ctx** out, int device_id, int flags);
+void hispmv_destroy(hispmv_ctx* ctx);
+
+/* Row-block sharding for one-process-per-GPU runs: after this call every matrix added keeps only part
+ * `part` of `n_parts` -- contiguous, nnz-balanced row blocks for sparse matrices (split points =
+ * lower_bound(row_ptr, k*nnz/n_parts); rows are never split across GPUs), equal row blocks for dense.
+ * y and bias passed to run/linear then have row_end-row_begin entries; x stays full length. */
+int hispmv_set_shard(hispmv_ctx* ctx, int part, int n_parts);
+/* The split points themselves (n_parts+1 entries, bounds[0]=0, bounds[n_parts]=rows) from a HOST row_ptr. */
+int hispmv_shard_bounds(const int32_t* row_ptr, int32_t rows, int n_parts, int32_t* bounds);
+/* Optional cap on the HBM the context may hold (bytes; 0 = device capacity).  The reference's cap is
+ * 256 MiB per HBM channel (fpga_handle.h:12). */
+int hispmv_set_memory_limit(hispmv_ctx* ctx, int64_t bytes);
+
+/* ---- adding matrices: return handle index >= 0, HISPMV_FULL (-1), or another negative status ---- */
+int hispmv_add_sparse_coo(hispmv_ctx* ctx, const int32_t* coo_rows, const int32_t* coo_cols, const float* coo_vals,
+                          int64_t nnz, int32_t rows, int32_t cols);
+int hispmv_add_sparse_csr(hispmv_ctx* ctx, const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
+                          int32_t rows, int32_t cols);
+int hispmv_add_dense(hispmv_ctx* ctx, const float* a_rowmajor, int32_t rows, int32_t cols);
+/* device-resident inputs (benchmarks and generators that must not cross PCIe); arrays are copied. */
+int hispmv_add_sparse_coo_dev(hispmv_ctx* ctx, const int32_t* d_rows, const int32_t* d_cols, const float* d_vals,
+                              int64_t nnz, int32_t rows, int32_t cols);
+int hispmv_add_sparse_csr_dev(hispmv_ctx* ctx, const int32_t* d_row_ptr, const int32_t* d_col_idx,
+                              const float* d_vals, int32_t rows, int32_t cols);
+int hispmv_add_dense_dev(hispmv_ctx* ctx, const float* d_a_rowmajor, int32_t rows, int32_t cols);
+
+int hispmv_commit(hispmv_ctx* ctx);
+int hispmv_num_matrices(hispmv_ctx* ctx);
+int hispmv_select(hispmv_ctx* ctx, uint32_t idx);
+
+/* Force a strategy for matrix idx (HISPMV_KERNEL_*; lanes only for CSR_VECTOR, 0 = auto) and re-plan.
+ * Used by the selector tests and the per-kernel benchmarks. */
+int hispmv_force_kernel(hispmv_ctx* ctx, int idx, int kernel, int lanes);
+
+/* ---- host-buffer calls (synchronous; copies inside, like the reference's BO syncs) ---- */
+int hispmv_run(hispmv_ctx* ctx, const float* x, const float* bias, float* y, float alpha, float beta);
+int hispmv_linear(hispmv_ctx* ctx, int idx, const float* x, int64_t x_len, const float* bias, float* y_out);
+
+/* ---- device-buffer calls (asynchronous on `stream`, a cudaStream_t; NULL = the context's stream) ---- */
+int hispmv_run_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha,
+                   float beta, void* stream);
+/* y = relu?(A x + bias) for chained layers that stay on the device. */
+int hispmv_linear_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
+                      void* stream);
+int hispmv_sync(hispmv_ctx* ctx);
+/* number of kernels one hispmv_run_dev of matrix idx launches (for bench.py's gpu_launches) */
+int hispmv_launches_per_run(hispmv_ctx* ctx, int idx);
+
+/* ---- plan introspection: the bit-exact integer contract ---- */
+int hispmv_matrix_info_get(hispmv_ctx* ctx, int idx, hispmv_matrix_info* out);
+/* Copy the device CSR of the local row block back to the host (row_ptr rebased to 0).  Any pointer may be
+ * NULL to skip that array.  Sizes: local_rows+1, nnz, nnz. */
+int hispmv_plan_csr(hispmv_ctx* ctx, int idx, int32_t* row_ptr, int32_t* col_idx, float* vals);
+/* Merge-path tile start coordinates: num_tiles+1 entries each (last = (local_rows, nnz)). */
+int hispmv_plan_tiles(hispmv_ctx* ctx, int idx, int32_t* tile_row, int64_t* tile_nnz);
+/* Sorted ids of the rows split across tiles (num_split_rows entries). */
+int hispmv_plan_split_rows(hispmv_ctx* ctx, int idx, int32_t* rows_out);
+
+/* ---- Matrix Market ingest: real/integer/pattern x general/symmetric/skew-symmetric ---- */
+int hispmv_load_mtx(hispmv_ctx* ctx, const char* path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HISPMV_H_ */

@@ -1,0 +1,441 @@
+/*
+ * oracle.c -- TEST INFRASTRUCTURE.  CPU restatement of the reference's algorithms on the SpMV/GeMV hot
+ * path, plus single-threaded restatements of the GPU partitioner's integer artefacts.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+ * liboracle.so.  The product (hispmv_b200/) never links, imports or calls anything in oracle/.
+ *
+ * Pinning: the floating-point routines here are checked (tests/test_oracle_pins.py) against the
+ * UNMODIFIED reference code compiled into oracle/_ref/ (cpu_spmv, mkl_spmv, naive_gemv, mkl_gemv,
+ * cooToCsr, cpuSpMV, HiSpmvHandle::cpuSequential / tileAndPad) and against golden vectors generated from
+ * those binaries (tests/golden/).  The reference holds no golden vectors of its own; MKL's
+ * summation order is not specified, so parity against mkl_sparse_s_mv / sgemv is tolerance-based:
+ * |y - y_ref| / (sum_j |a_ij||x_j| + |beta*y0_i|) <= 1e-5.
+ *
+ * Each function cites the reference file:line it follows (paths relative to /root/reference).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * COO -> CSR.  gpu/src/spmvHelper.cpp:117-156 (cooToCsr) and common/src/spmv-helper.cpp:139-227
+ * (tileAndPad): group by row, sort each row's (col, val) pairs lexicographically (std::sort on
+ * std::pair<int,float>), duplicates kept as separate entries.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int col;
+  float val;
+} colval_t;
+
+static int cmp_colval(const void* a, const void* b) {
+  const colval_t* x = (const colval_t*)a;
+  const colval_t* y = (const colval_t*)b;
+  if (x->col != y->col) return x->col < y->col ? -1 : 1;
+  if (x->val < y->val) return -1;
+  if (y->val < x->val) return 1;
+  return 0;
+}
+
+int oracle_coo_to_csr(int rows, int64_t nnz, const int* coo_r, const int* coo_c, const float* coo_v, int* row_ptr,
+                      int* col, float* val) {
+  int64_t i;
+  int r;
+  int* fill;
+  colval_t* tmp;
+  memset(row_ptr, 0, sizeof(int) * ((size_t)rows + 1));
+  for (i = 0; i < nnz; ++i) {
+    if (coo_r[i] < 0 || coo_r[i] >= rows) return -1;
+    row_ptr[coo_r[i] + 1]++;
+  }
+  for (r = 0; r < rows; ++r) row_ptr[r + 1] += row_ptr[r];
+  fill = (int*)malloc(sizeof(int) * ((size_t)rows + 1));
+  tmp = (colval_t*)malloc(sizeof(colval_t) * (size_t)(nnz ? nnz : 1));
+  memcpy(fill, row_ptr, sizeof(int) * ((size_t)rows + 1));
+  for (i = 0; i < nnz; ++i) {
+    const int p = fill[coo_r[i]]++;
+    tmp[p].col = coo_c[i];
+    tmp[p].val = coo_v[i];
+  }
+  for (r = 0; r < rows; ++r) qsort(tmp + row_ptr[r], (size_t)(row_ptr[r + 1] - row_ptr[r]), sizeof(colval_t), cmp_colval);
+  for (i = 0; i < nnz; ++i) {
+    col[i] = tmp[i].col;
+    val[i] = tmp[i].val;
+  }
+  free(fill);
+  free(tmp);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 SpMV in the reference's naive orders.
+ * ---------------------------------------------------------------------------------------------- */
+/* cpu/src/main.cpp:11-23 (cpu_spmv): C[i] *= beta; C[i] += alpha*value*B[col] in CSR order, in place. */
+void oracle_spmv_csr_f32(int rows, const int* row_ptr, const int* col, const float* val, const float* x, float* y,
+                         float alpha, float beta) {
+  int i, j;
+  for (i = 0; i < rows; ++i) {
+    float c = y[i] * beta;
+    for (j = row_ptr[i]; j < row_ptr[i + 1]; ++j) c += alpha * val[j] * x[col[j]];
+    y[i] = c;
+  }
+}
+
+/* common/src/spmv-helper.cpp:812-833 (cpuSequential, sparse branch): Cout[row] += value*B[col] in COO
+ * order starting from Cout as given (the host passes zeros), then Cout = alpha*Cout + beta*Cin. */
+void oracle_spmv_coo_f32(int rows, int64_t nnz, const int* coo_r, const int* coo_c, const float* coo_v, const float* x,
+                         const float* c_in, float alpha, float beta, float* c_out) {
+  int64_t i;
+  int r;
+  for (i = 0; i < nnz; ++i) c_out[coo_r[i]] += coo_v[i] * x[coo_c[i]];
+  for (r = 0; r < rows; ++r) c_out[r] = (alpha * c_out[r]) + (beta * c_in[r]);
+}
+
+/* gpu/src/spmvHelper.cpp:223-233 (cpuSpMV): y *= beta; y[row] += alpha*value*x[col] in COO order. */
+void oracle_spmv_coo_inplace_f32(int rows, int64_t nnz, const int* coo_r, const int* coo_c, const float* coo_v,
+                                 const float* x, float* y, float alpha, float beta) {
+  int64_t i;
+  int r;
+  for (r = 0; r < rows; ++r) y[r] *= beta;
+  for (i = 0; i < nnz; ++i) y[coo_r[i]] += alpha * coo_v[i] * x[coo_c[i]];
+}
+
+/* cpu/src/main.cpp:53-71 (naive_gemv): acc += A[i][j]*x[j]; y = alpha*acc + beta*y. */
+void oracle_gemv_f32(int rows, int cols, const float* a, const float* x, float* y, float alpha, float beta) {
+  int i, j;
+  for (i = 0; i < rows; ++i) {
+    float acc = 0.0f;
+    const float* ai = a + (size_t)i * cols;
+    for (j = 0; j < cols; ++j) acc += ai[j] * x[j];
+    y[i] = alpha * acc + beta * y[i];
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * float64 reference + the normaliser of the stated tolerance:
+ *   y64[i]   = alpha * sum_j a_ij x_j + beta * y0_i          (accumulated in double)
+ *   scale[i] = |alpha| * sum_j |a_ij||x_j| + |beta*y0_i|
+ * (semantics: automation_tool/assets/base_functions.cpp:535, y = beta*c_in + alpha*(A x)).
+ * ---------------------------------------------------------------------------------------------- */
+void oracle_spmv_csr_f64(int rows, const int* row_ptr, const int* col, const float* val, const float* x,
+                         const float* y0, float alpha, float beta, double* y64, double* scale) {
+  int i;
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (i = 0; i < rows; ++i) {
+    double s = 0.0, a = 0.0;
+    int j;
+    for (j = row_ptr[i]; j < row_ptr[i + 1]; ++j) {
+      const double p = (double)val[j] * (double)x[col[j]];
+      s += p;
+      a += fabs(p);
+    }
+    {
+      const double b = y0 ? (double)beta * (double)y0[i] : 0.0;
+      y64[i] = (double)alpha * s + b;
+      if (scale) scale[i] = fabs((double)alpha) * a + fabs(b);
+    }
+  }
+}
+
+void oracle_gemv_f64(int rows, int cols, const float* a, const float* x, const float* y0, float alpha, float beta,
+                     double* y64, double* scale) {
+  int i;
+#pragma omp parallel for schedule(static)
+  for (i = 0; i < rows; ++i) {
+    double s = 0.0, ab = 0.0;
+    const float* ai = a + (size_t)i * cols;
+    int j;
+    for (j = 0; j < cols; ++j) {
+      const double p = (double)ai[j] * (double)x[j];
+      s += p;
+      ab += fabs(p);
+    }
+    {
+      const double b = y0 ? (double)beta * (double)y0[i] : 0.0;
+      y64[i] = (double)alpha * s + b;
+      if (scale) scale[i] = fabs((double)alpha) * ab + fabs(b);
+    }
+  }
+}
+
+/* max_i |y[i]-y64[i]| / scale[i]  (rows with scale == 0 must match exactly, else +inf) */
+double oracle_max_scaled_error(int rows, const float* y, const double* y64, const double* scale, int* argmax) {
+  double worst = 0.0;
+  int i, at = -1;
+  for (i = 0; i < rows; ++i) {
+    const double d = fabs((double)y[i] - y64[i]);
+    double e;
+    if (scale[i] > 0.0) e = d / scale[i];
+    else e = d == 0.0 ? 0.0 : INFINITY;
+    if (!(e <= worst)) {  /* also catches NaN */
+      worst = e;
+      at = i;
+    }
+  }
+  if (argmax) *argmax = at;
+  return worst;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Partitioner restatements (single-threaded).  These restate hispmv_b200/csrc/partition.cu, the GPU
+ * replacement for common/src/spmv-helper.cpp:265-347 (balanceWorkload) and :429-638 (schedule), and
+ * automation_tool/src/dse.py:23-95 (config choice).  Integer-exact by construction.
+ * ---------------------------------------------------------------------------------------------- */
+#define ORACLE_HIST_BINS 33
+
+/* hist[0]: empty rows; hist[k]: rows with 2^(k-1) <= nnz < 2^k */
+void oracle_row_stats(int rows, const int* row_ptr, int64_t* hist, int* max_row_nnz, int* empty_rows) {
+  int i, mx = 0;
+  memset(hist, 0, sizeof(int64_t) * ORACLE_HIST_BINS);
+  for (i = 0; i < rows; ++i) {
+    const int len = row_ptr[i + 1] - row_ptr[i];
+    int bin = 0, l = len;
+    while (l > 0) {
+      ++bin;
+      l >>= 1;
+    }
+    hist[bin]++;
+    if (len > mx) mx = len;
+  }
+  *max_row_nnz = mx;
+  *empty_rows = (int)hist[0];
+}
+
+/* kernel ids as in include/hispmv.h */
+enum { K_SCALAR = 1, K_VECTOR = 2, K_MERGE = 3, K_EMPTY = 5 };
+
+void oracle_select_kernel(int rows, int64_t nnz, int max_row_nnz, int empty_rows, int allow_split_rows, int* kernel,
+                          int* lanes) {
+  int64_t mean, m4;
+  int l = 2;
+  *lanes = 0;
+  if (rows <= 0 || nnz <= 0) {
+    *kernel = K_EMPTY;
+    return;
+  }
+  mean = (nnz + rows - 1) / rows;
+  while (l < 32 && (int64_t)l * 2 <= mean) l *= 2;
+  m4 = mean > 4 ? mean : 4;
+  {
+    const int heavy = (int64_t)max_row_nnz > 32 * m4;
+    const int hollow = (int64_t)empty_rows * 2 > (int64_t)rows;
+    const int underfilled = (int64_t)rows * l < 148LL * 1024;
+    if (allow_split_rows && (heavy || hollow || underfilled)) {
+      *kernel = K_MERGE;
+      return;
+    }
+  }
+  if (mean <= 2) {
+    *kernel = K_SCALAR;
+    return;
+  }
+  *kernel = K_VECTOR;
+  *lanes = l;
+}
+
+int oracle_merge_tile_items(int rows, int64_t nnz) {
+  const int64_t total = (int64_t)rows + nnz;
+  if (total < 148LL * 4 * 1792) return 128 * 7;
+  return 256 * 7;
+}
+
+/* Merge-path tile start coordinates: tile t starts at diagonal min(t*tile_items, rows+nnz) of the merge
+ * of the row-end list (row_ptr[1..rows]) with the nonzero indices 0..nnz-1.  num_tiles+1 entries. */
+int64_t oracle_merge_tiles(int rows, const int* row_ptr, int tile_items, int* tile_row, int64_t* tile_nnz) {
+  const int64_t nnz = row_ptr[rows];
+  const int64_t total = (int64_t)rows + nnz;
+  int64_t nt = (total + tile_items - 1) / tile_items, t;
+  if (nt < 1) nt = 1;
+  if (!tile_row) return nt;
+  for (t = 0; t <= nt; ++t) {
+    int64_t diag = t * (int64_t)tile_items, lo, hi;
+    if (diag > total) diag = total;
+    lo = diag > nnz ? diag - nnz : 0;
+    hi = diag < rows ? diag : rows;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)row_ptr[mid + 1] <= diag - mid - 1) lo = mid + 1;
+      else hi = mid;
+    }
+    tile_row[t] = (int)lo;
+    tile_nnz[t] = diag - lo;
+  }
+  return nt;
+}
+
+/* Rows cut by a tile boundary after at least one of their nonzeros, ascending, no repeats: the rows whose
+ * partial sums travel through the carry-out array (analogue of balanceWorkload's shared-row list). */
+int64_t oracle_split_rows(int rows, const int* row_ptr, int64_t num_tiles, const int* tile_row,
+                          const int64_t* tile_nnz, int* out) {
+  int64_t t, n = 0;
+  int last = -1;
+  for (t = 1; t < num_tiles; ++t) {
+    const int r = tile_row[t];
+    if (r < rows && tile_nnz[t] > (int64_t)row_ptr[r] && r != last) {
+      if (out) out[n] = r;
+      ++n;
+      last = r;
+    }
+  }
+  return n;
+}
+
+/* nnz-balanced contiguous row blocks: bounds[k] = first row r with row_ptr[r] >= k*nnz/n_parts. */
+void oracle_shard_bounds(int rows, const int* row_ptr, int n_parts, int* bounds) {
+  const int64_t nnz = row_ptr[rows];
+  int k;
+  bounds[0] = 0;
+  bounds[n_parts] = rows;
+  for (k = 1; k < n_parts; ++k) {
+    const int64_t target = (nnz * (int64_t)k) / n_parts;
+    int64_t lo = 0, hi = rows;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if ((int64_t)row_ptr[mid] < target) lo = mid + 1;
+      else hi = mid;
+    }
+    bounds[k] = (int)lo;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Synthetic matrix generators (restating hispmv_b200/csrc/synth.cu; see include/hispmv_synth.h).
+ * ---------------------------------------------------------------------------------------------- */
+static uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static uint64_t hash_row(uint64_t seed, int64_t r) { return mix64(mix64(seed) ^ (uint64_t)r); }
+static uint64_t hash_entry(uint64_t seed, int64_t r, int64_t k) {
+  return mix64(hash_row(seed ^ 0xA5A5A5A5A5A5A5A5ull, r) + (uint64_t)k * 0xD1342543DE82EF95ull);
+}
+
+enum { SYNTH_POWERLAW = 1, SYNTH_UNIFORM = 2, SYNTH_STENCIL27 = 3 };
+
+int oracle_synth_row_len(int kind, uint64_t seed, const int64_t* p, int64_t r) {
+  if (kind == SYNTH_POWERLAW) {
+    const uint64_t u = hash_row(seed, r) >> 32;
+    const uint64_t len = (uint64_t)p[0] / (u + 1);
+    return (int)(len < (uint64_t)p[1] ? len : (uint64_t)p[1]);
+  }
+  if (kind == SYNTH_UNIFORM) {
+    const uint64_t h = hash_row(seed, r) & (uint64_t)p[1];
+    return (int)(p[0] + __builtin_popcountll(h));
+  }
+  if (kind == SYNTH_STENCIL27) {
+    const int64_t nx = p[0], ny = p[1], nz = p[2];
+    const int64_t ix = r % nx, iy = (r / nx) % ny, iz = r / (nx * ny);
+    const int cx = 1 + (ix > 0) + (ix < nx - 1);
+    const int cy = 1 + (iy > 0) + (iy < ny - 1);
+    const int cz = 1 + (iz > 0) + (iz < nz - 1);
+    return cx * cy * cz;
+  }
+  return 0;
+}
+
+void oracle_synth_entry(int kind, uint64_t seed, int cols, const int64_t* p, int64_t r, int k, int len, int* col,
+                        float* val) {
+  const uint64_t h = hash_entry(seed, r, k);
+  *val = (float)((int32_t)(h & 0xFFFFFF) - 0x800000) * (1.0f / 8388608.0f);
+  if (kind == SYNTH_STENCIL27) {
+    const int64_t nx = p[0], ny = p[1];
+    const int64_t ix = r % nx, iy = (r / nx) % ny, iz = r / (nx * ny);
+    const int cx = 1 + (ix > 0) + (ix < nx - 1);
+    const int cy = 1 + (iy > 0) + (iy < ny - 1);
+    const int a = k / (cy * cx), b = (k / cx) % cy, c = k % cx;
+    const int64_t dz = a - (iz > 0), dy = b - (iy > 0), dx = c - (ix > 0);
+    *col = (int)(r + dz * nx * ny + dy * nx + dx);
+    return;
+  }
+  {
+    /* -ffp-contract=off (oracle/Makefile): every operation below is a single IEEE double operation */
+    const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+    const double q = ((double)k + u) / (double)len;
+    double w = q;
+    const int gamma = kind == SYNTH_POWERLAW ? (int)p[2] : 1;
+    int g;
+    int64_t c;
+    for (g = 1; g < gamma; ++g) w = w * q;
+    c = (int64_t)(w * (double)cols);
+    if (c >= cols) c = cols - 1;
+    *col = (int)c;
+  }
+}
+
+/* whole row block [row_begin,row_end) as CSR (row_ptr rebased to 0).  Call with col == NULL to size. */
+int64_t oracle_synth_csr(int kind, uint64_t seed, int cols, const int64_t* p, int row_begin, int row_end, int* row_ptr,
+                         int* col, float* val) {
+  int64_t nnz = 0;
+  int r;
+  for (r = row_begin; r < row_end; ++r) {
+    const int len = oracle_synth_row_len(kind, seed, p, r);
+    if (row_ptr) row_ptr[r - row_begin] = (int)nnz;
+    if (col) {
+      int k;
+      for (k = 0; k < len; ++k) oracle_synth_entry(kind, seed, cols, p, r, k, len, col + nnz + k, val + nnz + k);
+    }
+    nnz += len;
+  }
+  if (row_ptr) row_ptr[row_end - row_begin] = (int)nnz;
+  return nnz;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Matrix Market reader, restating HiSpmvHandle::loadMtx (common/src/spmv-helper.cpp:34-136): banner
+ * check, comment skip, 1-based indices, pattern -> 1.0f, zeros dropped, symmetric / skew-symmetric
+ * expansion (mirror entry right after the original).  Two-pass: call with outputs NULL to count.
+ * Returns the entry count or a negative error.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t oracle_load_mtx(const char* path, int* rows, int* cols, int* coo_r, int* coo_c, float* coo_v) {
+  FILE* f = fopen(path, "r");
+  char line[1024], h0[64], h1[64], h2[64], h3[64], h4[64];
+  int pattern, symm, skew;
+  long long nr, nc, nz;
+  int64_t n = 0;
+  if (!f) return -1;
+  if (!fgets(line, sizeof(line), f)) { fclose(f); return -2; }
+  h0[0] = h1[0] = h2[0] = h3[0] = h4[0] = 0;
+  sscanf(line, "%63s %63s %63s %63s %63s", h0, h1, h2, h3, h4);
+  if (strcmp(h0, "%%MatrixMarket") || strcmp(h1, "matrix")) { fclose(f); return -2; }
+  if (strcmp(h2, "coordinate")) { fclose(f); return -3; }
+  pattern = !strcmp(h3, "pattern");
+  if (strcmp(h3, "real") && strcmp(h3, "integer") && !pattern) { fclose(f); return -4; }
+  symm = !strcmp(h4, "symmetric");
+  skew = !strcmp(h4, "skew-symmetric");
+  if (strcmp(h4, "general") && !symm && !skew) { fclose(f); return -5; }
+  do {
+    if (!fgets(line, sizeof(line), f)) { fclose(f); return -6; }
+  } while (line[0] == '%');
+  if (sscanf(line, "%lld %lld %lld", &nr, &nc, &nz) != 3) { fclose(f); return -6; }
+  *rows = (int)nr;
+  *cols = (int)nc;
+  while (fgets(line, sizeof(line), f)) {
+    long r, c;
+    float v = 1.0f;
+    char* q = line;
+    char* e;
+    r = strtol(q, &e, 10);
+    if (e == q) continue;
+    q = e;
+    c = strtol(q, &e, 10);
+    if (e == q) continue;
+    q = e;
+    if (!pattern) {
+      v = strtof(q, &e);
+      if (e == q) continue;
+    }
+    if (v == 0) continue;
+    if (coo_r) { coo_r[n] = (int)r - 1; coo_c[n] = (int)c - 1; coo_v[n] = v; }
+    ++n;
+    if ((symm || skew) && r != c) {
+      if (coo_r) { coo_r[n] = (int)c - 1; coo_c[n] = (int)r - 1; coo_v[n] = skew ? -v : v; }
+      ++n;
+    }
+  }
+  fclose(f);
+  return n;
+}

@@ -1,0 +1,136 @@
+// TEST INFRASTRUCTURE (oracle/) -- C-ABI doorway into the UNMODIFIED reference host library
+// /root/reference/common/src/spmv-helper.cpp (compiled where it lies, against the stub TAPA/XRT headers in
+// oracle/stubs/, into oracle/_ref/libref_common.so):
+//   HiSpmvHandle::cpuSequential             common/src/spmv-helper.cpp:812-833
+//   HiSpmvHandle::tileAndPad(COO)           common/src/spmv-helper.cpp:139-227   (private)
+//   HiSpmvHandle::prepareSparseMtxForFPGA   common/src/spmv-helper.cpp:648-715   (shared-row list)
+//   HiSpmvHandle::loadMtx                   common/src/spmv-helper.cpp:34-136    (private)
+// The private members are reached by re-declaring access for this translation unit only; the reference
+// sources themselves are compiled untouched.
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+#include <sstream>
+
+#define private public
+#include "spmv-helper.h"  // reference header (common/include)
+#undef private
+#include "fpga-power.h"
+
+// The XRT power sampler (common/src/fpga-power.cpp) is not built; give its symbols empty bodies so that
+// spmv-helper.cpp's fpgaRun links.  fpgaRun is never called by the oracle.
+FpgaPowerMonitor::FpgaPowerMonitor() : isMonitoring(false), debug(false) {}
+FpgaPowerMonitor::~FpgaPowerMonitor() {}
+void FpgaPowerMonitor::startMonitoring(const int, bool) {}
+void FpgaPowerMonitor::stopMonitoring() {}
+float FpgaPowerMonitor::getAveragePower(size_t& n) const { n = 0; return 0.f; }
+float FpgaPowerMonitor::getMaxPower() const { return 0.f; }
+
+namespace {
+struct Quiet {  // the reference prints configuration banners on every call
+  std::streambuf* old;
+  std::ostringstream sink;
+  Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+  ~Quiet() { std::cout.rdbuf(old); }
+};
+HiSpmvHandle* make_handle(int a, int b, int c, int urams, int lat, int dense, int pre, int rdn) {
+  return new HiSpmvHandle(a, b, c, 512, urams, lat, dense != 0, pre != 0, rdn != 0);
+}
+}  // namespace
+
+extern "C" {
+
+// Cout = alpha * (A*B) + beta * Cin, COO order, fp32 (the reference's own self-check oracle).
+void ref_common_cpu_sequential(int rows, int cols, int64_t nnz, const int* r, const int* c, const float* v,
+                               const float* x, const float* c_in, float alpha, float beta, float* c_out) {
+  Quiet q;
+  HiSpmvHandle* h = make_handle(24, 1, 1, 2, 5, 1, 0, 1);
+  h->rows = rows;
+  h->cols = cols;
+  h->nnz = (int)nnz;
+  h->coo_mtx.rows.assign(r, r + nnz);
+  h->coo_mtx.cols.assign(c, c + nnz);
+  h->coo_mtx.values.assign(v, v + nnz);
+  std::vector<float> B(x, x + cols), Cin(c_in, c_in + rows), Cout(rows, 0.0f);
+  h->cpuSequential(B, Cin, alpha, beta, Cout);
+  std::memcpy(c_out, Cout.data(), sizeof(float) * rows);
+  delete h;
+}
+
+// COO -> per-tile CSR through the reference's tileAndPad, flattened back to one global CSR
+// (column tiles are visited in ascending order, so concatenating them keeps each row sorted).
+int ref_common_coo_to_csr(int rows, int cols, int64_t nnz, const int* r, const int* c, const float* v, int* row_ptr,
+                          int* col, float* val) {
+  Quiet q;
+  HiSpmvHandle* h = make_handle(24, 1, 1, 2, 5, 1, 0, 1);
+  h->rows = rows;
+  h->cols = cols;
+  h->nnz = (int)nnz;
+  COOMatrix_t coo;
+  coo.rows.assign(r, r + nnz);
+  coo.cols.assign(c, c + nnz);
+  coo.values.assign(v, v + nnz);
+  auto tiles = h->tileAndPad(coo);
+  int64_t out = 0;
+  row_ptr[0] = 0;
+  for (int gr = 0; gr < rows; ++gr) {
+    const int ti = gr / h->tile_rows, lr = gr % h->tile_rows;
+    for (int tj = 0; tj < h->col_tiles; ++tj) {
+      const CSRMatrix_t& t = tiles[ti][tj];
+      for (int k = t.row_offsets[lr]; k < t.row_offsets[lr + 1]; ++k) {
+        col[out] = tj * h->tile_cols + t.col_indices[k];
+        val[out] = t.values[k];
+        ++out;
+      }
+    }
+    row_ptr[gr + 1] = (int)out;
+  }
+  delete h;
+  return out == nnz ? 0 : -1;
+}
+
+// The reference's "shared rows" (rows processed by all PEs) for a given hardware configuration.
+// Returns the count; ids (ascending) are written when out != NULL and capacity suffices.
+int ref_common_shared_rows(int num_ch_a, int urams, int rows, int cols, int64_t nnz, const int* r, const int* c,
+                           const float* v, int* out, int capacity) {
+  Quiet q;
+  HiSpmvHandle* h = make_handle(num_ch_a, 1, 1, urams, 5, 1, 0, 1);
+  std::vector<int> rv(r, r + nnz), cv(c, c + nnz);
+  std::vector<float> vv(v, v + nnz);
+  h->prepareSparseMtxForFPGA(rows, cols, rv, cv, vv);
+  int n = 0;
+  for (int id : h->shared_row_indices) {
+    if (out && n < capacity) out[n] = id;
+    ++n;
+  }
+  delete h;
+  return n;
+}
+
+static COOMatrix_t g_coo;
+static int g_rows, g_cols;
+int ref_common_load_mtx(const char* path, int* rows, int* cols, int64_t* nnz) {
+  Quiet q;
+  HiSpmvHandle* h = make_handle(24, 1, 1, 2, 5, 1, 0, 1);
+  int st = 0;
+  try {
+    g_coo = h->loadMtx(path);
+    g_rows = h->rows;
+    g_cols = h->cols;
+  } catch (const std::exception&) {
+    st = -1;
+  }
+  delete h;
+  if (st) return st;
+  *rows = g_rows;
+  *cols = g_cols;
+  *nnz = (int64_t)g_coo.rows.size();
+  return 0;
+}
+void ref_common_load_mtx_fetch(int* r, int* c, float* v) {
+  std::memcpy(r, g_coo.rows.data(), sizeof(int) * g_coo.rows.size());
+  std::memcpy(c, g_coo.cols.data(), sizeof(int) * g_coo.cols.size());
+  std::memcpy(v, g_coo.values.data(), sizeof(float) * g_coo.values.size());
+  g_coo = COOMatrix_t();
+}
+}

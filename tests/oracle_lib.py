@@ -1,0 +1,234 @@
+"""ctypes loaders for the checker libraries under oracle/ (TEST INFRASTRUCTURE).
+
+  liboracle.so                 oracle/oracle.c, our CPU restatement
+  _ref/libref_cpu.so           the reference's cpu/ path (cpu_spmv, mkl_spmv, naive_gemv, mkl_gemv, .mtx reader)
+  _ref/libref_gpuhelper.so     the reference's gpu/src/spmvHelper.cpp (cooToCsr, cpuSpMV, loadMtx)
+  _ref/libref_common.so        the reference's common/ host library (cpuSequential, tileAndPad, shared rows)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    """(Re)build oracle/ with its Makefile.  _ref/ targets are only attempted where /root/reference exists."""
+    if force or not os.path.exists(os.path.join(ORACLE_DIR, "liboracle.so")) or os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+
+
+def have_ref() -> bool:
+    return all(os.path.exists(os.path.join(REF_DIR, f))
+               for f in ("libref_cpu.so", "libref_gpuhelper.so", "libref_common.so"))
+
+
+_cache = {}
+
+
+def oracle() -> C.CDLL:
+    if "oracle" in _cache:
+        return _cache["oracle"]
+    path = os.path.join(ORACLE_DIR, "liboracle.so")
+    if not os.path.exists(path):
+        build()
+    lib = C.CDLL(path)
+    i, i64, f, d, vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_void_p
+    lib.oracle_coo_to_csr.argtypes = [i, i64, _i32p, _i32p, _f32p, _i32p, _i32p, _f32p]
+    lib.oracle_coo_to_csr.restype = i
+    lib.oracle_spmv_csr_f32.argtypes = [i, _i32p, _i32p, _f32p, _f32p, _f32p, f, f]
+    lib.oracle_spmv_coo_f32.argtypes = [i, i64, _i32p, _i32p, _f32p, _f32p, _f32p, f, f, _f32p]
+    lib.oracle_spmv_coo_inplace_f32.argtypes = [i, i64, _i32p, _i32p, _f32p, _f32p, _f32p, f, f]
+    lib.oracle_gemv_f32.argtypes = [i, i, _f32p, _f32p, _f32p, f, f]
+    lib.oracle_spmv_csr_f64.argtypes = [i, _i32p, _i32p, _f32p, _f32p, vp, f, f, _f64p, vp]
+    lib.oracle_gemv_f64.argtypes = [i, i, _f32p, _f32p, vp, f, f, _f64p, vp]
+    lib.oracle_max_scaled_error.argtypes = [i, _f32p, _f64p, _f64p, C.POINTER(i)]
+    lib.oracle_max_scaled_error.restype = d
+    lib.oracle_row_stats.argtypes = [i, _i32p, _i64p, C.POINTER(i), C.POINTER(i)]
+    lib.oracle_select_kernel.argtypes = [i, i64, i, i, i, C.POINTER(i), C.POINTER(i)]
+    lib.oracle_merge_tile_items.argtypes = [i, i64]
+    lib.oracle_merge_tile_items.restype = i
+    lib.oracle_merge_tiles.argtypes = [i, _i32p, i, vp, vp]
+    lib.oracle_merge_tiles.restype = i64
+    lib.oracle_split_rows.argtypes = [i, _i32p, i64, _i32p, _i64p, vp]
+    lib.oracle_split_rows.restype = i64
+    lib.oracle_shard_bounds.argtypes = [i, _i32p, i, _i32p]
+    lib.oracle_synth_row_len.argtypes = [i, C.c_uint64, _i64p, i64]
+    lib.oracle_synth_row_len.restype = i
+    lib.oracle_synth_csr.argtypes = [i, C.c_uint64, i, _i64p, i, i, vp, vp, vp]
+    lib.oracle_synth_csr.restype = i64
+    lib.oracle_load_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), vp, vp, vp]
+    lib.oracle_load_mtx.restype = i64
+    _cache["oracle"] = lib
+    return lib
+
+
+def _ref(name: str) -> C.CDLL:
+    if name in _cache:
+        return _cache[name]
+    path = os.path.join(REF_DIR, name)
+    if not os.path.exists(path):
+        if os.path.isdir("/root/reference"):
+            build(force=True)
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built (needs /root/reference at build time)")
+    _cache[name] = C.CDLL(path)
+    return _cache[name]
+
+
+def ref_cpu() -> C.CDLL:
+    lib = _ref("libref_cpu.so")
+    i, i64, f, d = C.c_int, C.c_int64, C.c_float, C.c_double
+    lib.ref_set_threads.argtypes = [i]
+    lib.ref_get_threads.restype = i
+    lib.ref_cpu_spmv.argtypes = [_i32p, _i32p, _f32p, i, i, i64, _f32p, _f32p, f, f]
+    lib.ref_mkl_spmv.argtypes = [_i32p, _i32p, _f32p, i, i, i64, _f32p, _f32p, f, f, i]
+    lib.ref_mkl_spmv.restype = d
+    lib.ref_naive_gemv.argtypes = [_f32p, i, i, _f32p, _f32p, f, f]
+    lib.ref_naive_gemv.restype = d
+    lib.ref_mkl_gemv.argtypes = [_f32p, i, i, _f32p, _f32p, f, f, i]
+    lib.ref_mkl_gemv.restype = d
+    lib.ref_read_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64)]
+    lib.ref_read_mtx.restype = i
+    lib.ref_read_mtx_fetch.argtypes = [_i32p, _i32p, _f32p]
+    return lib
+
+
+def ref_gpuhelper() -> C.CDLL:
+    lib = _ref("libref_gpuhelper.so")
+    i, i64, f = C.c_int, C.c_int64, C.c_float
+    lib.ref_gpu_coo_to_csr.argtypes = [i, i, i64, _i32p, _i32p, _f32p, _i32p, _i32p, _f32p]
+    lib.ref_gpu_cpu_spmv.argtypes = [i, i64, _i32p, _i32p, _f32p, i, _f32p, _f32p, f, f]
+    lib.ref_gpu_load_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64)]
+    lib.ref_gpu_load_mtx_fetch.argtypes = [_i32p, _i32p, _f32p]
+    return lib
+
+
+def ref_common() -> C.CDLL:
+    lib = _ref("libref_common.so")
+    i, i64, f = C.c_int, C.c_int64, C.c_float
+    lib.ref_common_cpu_sequential.argtypes = [i, i, i64, _i32p, _i32p, _f32p, _f32p, _f32p, f, f, _f32p]
+    lib.ref_common_coo_to_csr.argtypes = [i, i, i64, _i32p, _i32p, _f32p, _i32p, _i32p, _f32p]
+    lib.ref_common_coo_to_csr.restype = i
+    lib.ref_common_shared_rows.argtypes = [i, i, i, i, i64, _i32p, _i32p, _f32p, C.c_void_p, i]
+    lib.ref_common_shared_rows.restype = i
+    lib.ref_common_load_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64)]
+    lib.ref_common_load_mtx_fetch.argtypes = [_i32p, _i32p, _f32p]
+    return lib
+
+
+# ---- convenience wrappers (numpy in, numpy out) ---------------------------------------------------
+def coo_to_csr(rows, r, c, v):
+    r, c, v = (np.ascontiguousarray(r, np.int32), np.ascontiguousarray(c, np.int32), np.ascontiguousarray(v, np.float32))
+    rp = np.zeros(rows + 1, np.int32)
+    ci = np.zeros(r.size, np.int32)
+    vv = np.zeros(r.size, np.float32)
+    st = oracle().oracle_coo_to_csr(rows, r.size, r, c, v, rp, ci, vv)
+    if st != 0:
+        raise ValueError("oracle_coo_to_csr: row index out of range")
+    return rp, ci, vv
+
+
+def spmv_f64(rp, ci, v, x, y0=None, alpha=1.0, beta=0.0):
+    rows = rp.size - 1
+    y64 = np.zeros(rows, np.float64)
+    scale = np.zeros(rows, np.float64)
+    y0p = None if y0 is None else np.ascontiguousarray(y0, np.float32)
+    oracle().oracle_spmv_csr_f64(rows, np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32),
+                                 np.ascontiguousarray(v, np.float32), np.ascontiguousarray(x, np.float32),
+                                 None if y0p is None else y0p.ctypes.data, alpha, beta, y64, scale.ctypes.data)
+    return y64, scale
+
+
+def gemv_f64(a, rows, cols, x, y0=None, alpha=1.0, beta=0.0):
+    y64 = np.zeros(rows, np.float64)
+    scale = np.zeros(rows, np.float64)
+    y0p = None if y0 is None else np.ascontiguousarray(y0, np.float32)
+    oracle().oracle_gemv_f64(rows, cols, np.ascontiguousarray(a, np.float32).reshape(-1),
+                             np.ascontiguousarray(x, np.float32), None if y0p is None else y0p.ctypes.data, alpha,
+                             beta, y64, scale.ctypes.data)
+    return y64, scale
+
+
+def max_scaled_error(y, y64, scale):
+    at = C.c_int(-1)
+    e = oracle().oracle_max_scaled_error(y.size, np.ascontiguousarray(y, np.float32), y64, scale, C.byref(at))
+    return float(e), at.value
+
+
+def merge_tiles(rp, tile_items):
+    rp = np.ascontiguousarray(rp, np.int32)
+    rows = rp.size - 1
+    nt = oracle().oracle_merge_tiles(rows, rp, tile_items, None, None)
+    tr = np.zeros(nt + 1, np.int32)
+    tn = np.zeros(nt + 1, np.int64)
+    oracle().oracle_merge_tiles(rows, rp, tile_items, tr.ctypes.data, tn.ctypes.data)
+    return tr, tn
+
+
+def split_rows(rp, tr, tn):
+    rp = np.ascontiguousarray(rp, np.int32)
+    rows = rp.size - 1
+    nt = tr.size - 1
+    n = oracle().oracle_split_rows(rows, rp, nt, tr, tn, None)
+    out = np.zeros(n, np.int32)
+    if n:
+        oracle().oracle_split_rows(rows, rp, nt, tr, tn, out.ctypes.data)
+    return out
+
+
+def row_stats(rp):
+    rp = np.ascontiguousarray(rp, np.int32)
+    hist = np.zeros(33, np.int64)
+    mx, em = C.c_int(), C.c_int()
+    oracle().oracle_row_stats(rp.size - 1, rp, hist, C.byref(mx), C.byref(em))
+    return hist, mx.value, em.value
+
+
+def select_kernel(rows, nnz, max_row, empty_rows, allow_split=1):
+    k, l = C.c_int(), C.c_int()
+    oracle().oracle_select_kernel(rows, nnz, max_row, empty_rows, allow_split, C.byref(k), C.byref(l))
+    return k.value, l.value
+
+
+def shard_bounds(rp, n_parts):
+    rp = np.ascontiguousarray(rp, np.int32)
+    out = np.zeros(n_parts + 1, np.int32)
+    oracle().oracle_shard_bounds(rp.size - 1, rp, n_parts, out)
+    return out
+
+
+def synth_csr(kind, seed, cols, params, row_begin, row_end):
+    p = np.asarray(params, np.int64)
+    n = row_end - row_begin
+    nnz = oracle().oracle_synth_csr(kind, seed, cols, p, row_begin, row_end, None, None, None)
+    rp = np.zeros(n + 1, np.int32)
+    ci = np.zeros(max(nnz, 1), np.int32)
+    v = np.zeros(max(nnz, 1), np.float32)
+    oracle().oracle_synth_csr(kind, seed, cols, p, row_begin, row_end, rp.ctypes.data, ci.ctypes.data, v.ctypes.data)
+    return rp, ci[:nnz], v[:nnz]
+
+
+def load_mtx(path):
+    r_, c_ = C.c_int(), C.c_int()
+    n = oracle().oracle_load_mtx(path.encode(), C.byref(r_), C.byref(c_), None, None, None)
+    if n < 0:
+        raise IOError(f"oracle_load_mtx failed with {n}")
+    r = np.zeros(max(n, 1), np.int32)
+    c = np.zeros(max(n, 1), np.int32)
+    v = np.zeros(max(n, 1), np.float32)
+    oracle().oracle_load_mtx(path.encode(), C.byref(r_), C.byref(c_), r.ctypes.data, c.ctypes.data, v.ctypes.data)
+    return r[:n], c[:n], v[:n], r_.value, c_.value

@@ -1,0 +1,384 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI / the pyhispmv plugin, against the oracle.
+
+Bars: bit-exact for every integer artefact (CSR, tile coordinates, split rows, shard bounds, selector);
+floating point per element |y - y64| / (|alpha| sum_j |a_ij x_j| + |beta y0_i|) <= 1e-5 (north_star), with the
+float64 restatement as y64.  Where oracle/_ref is present the reference's own MKL result is held to the same
+bar beside ours.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+ALPHA, BETA = np.float32(0.85), np.float32(-2.06)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from hispmv_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _rand_coo(rng, rows, cols, nnz, dup=0.0):
+    r = rng.integers(0, rows, nnz).astype(np.int32)
+    c = rng.integers(0, cols, nnz).astype(np.int32)
+    v = rng.standard_normal(nnz).astype(np.float32)
+    if dup and nnz:
+        k = int(nnz * dup)
+        src, dst = rng.integers(0, nnz, k), rng.integers(0, nnz, k)
+        r[dst], c[dst] = r[src], c[src]
+    return r, c, v
+
+
+def _check_run(eng, idx, rp, ci, vv, rows, cols, rng, alpha=ALPHA, beta=BETA):
+    x = rng.standard_normal(cols).astype(np.float32)
+    y0 = rng.standard_normal(rows).astype(np.float32)
+    y = np.full(rows, np.nan, np.float32)
+    eng.select_matrix(idx)
+    eng.run_kernel(x, y0, y, float(alpha), float(beta))
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, y0, alpha, beta)
+    err, at = ol.max_scaled_error(y, y64, scale)
+    assert err <= TOL, (err, at, eng.matrix_info(idx)["kernel_name"])
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------
+# integer contract
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols,nnz,dup", [(1, 1, 1, 0), (5, 9, 0, 0), (64, 64, 700, 0.3), (3000, 777, 50000, 0.05),
+                                                (100000, 100000, 1000000, 0.0), (50000, 10000, 1000000, 0.01)])
+def test_coo_to_csr_bit_exact(eng, rows, cols, nnz, dup):
+    rng = np.random.default_rng(nnz + rows)
+    r, c, v = _rand_coo(rng, rows, cols, nnz, dup)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    assert idx >= 0
+    rp, ci, vv = eng.plan_csr(idx)
+    rp2, ci2, vv2 = ol.coo_to_csr(rows, r, c, v)
+    assert np.array_equal(rp, rp2)
+    assert np.array_equal(ci, ci2)
+    assert np.array_equal(vv.view(np.uint32), vv2.view(np.uint32))
+    info = eng.matrix_info(idx)
+    hist, mx, em = ol.row_stats(rp2)
+    assert info["hist"] == hist.tolist() and info["max_row_nnz"] == mx and info["empty_rows"] == em
+    k, l = ol.select_kernel(rows, nnz, mx, em, 1)
+    assert (info["kernel"], info["vector_lanes"]) == (k, l)
+
+
+def test_coo_index_out_of_range_is_refused(eng):
+    from hispmv_b200.capi import HispmvError
+    with pytest.raises(HispmvError):
+        eng.create_sparse_handle(np.array([0, 5], np.int32), np.array([0, 1], np.int32), np.ones(2, np.float32), 4, 4)
+
+
+@pytest.mark.parametrize("tile", [128 * 7, 256 * 7, 256 * 11, 512 * 7])
+def test_merge_plan_bit_exact(eng, tile, monkeypatch):
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_MERGE_TILE", str(tile))
+    rng = np.random.default_rng(tile)
+    rows, cols = 20000, 20000
+    lens = np.minimum(rng.zipf(1.7, rows), 30000)
+    lens[rng.integers(0, rows, 3)] = 15000
+    lens[rng.integers(0, rows, 2000)] = 0
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_MERGE)
+    info = eng.matrix_info(idx)
+    assert info["kernel"] == capi.KERNEL_MERGE and info["tile_items"] == tile
+    rp, ci, vv = eng.plan_csr(idx)
+    tr, tn = eng.plan_tiles(idx)
+    tr2, tn2 = ol.merge_tiles(rp, tile)
+    assert np.array_equal(tr, tr2) and np.array_equal(tn, tn2)
+    sp = eng.plan_split_rows(idx)
+    sp2 = ol.split_rows(rp, tr2, tn2)
+    assert np.array_equal(sp, sp2)
+    assert info["num_split_rows"] == sp2.size
+    _check_run(eng, idx, rp, ci, vv, rows, cols, rng)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 8])
+def test_shard_bounds_bit_exact(eng, parts):
+    from hispmv_b200 import shard_bounds
+    rng = np.random.default_rng(parts)
+    lens = np.minimum(rng.zipf(1.6, 5000), 4000)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    assert np.array_equal(shard_bounds(rp, parts), ol.shard_bounds(rp, parts))
+
+
+# ---------------------------------------------------------------------------------------------------
+# floating point: every kernel strategy against the float64 restatement
+# ---------------------------------------------------------------------------------------------------
+def _matrix(rng, kind, rows, cols):
+    if kind == "powerlaw":
+        lens = np.minimum(rng.zipf(1.8, rows), cols)
+        lens[rng.integers(0, rows, 4)] = min(cols, 25000)
+    elif kind == "regular":
+        lens = np.full(rows, 27)
+    elif kind == "short":
+        lens = rng.integers(0, 3, rows)
+    elif kind == "hollow":
+        lens = np.where(rng.random(rows) < 0.8, 0, rng.integers(1, 40, rows))
+    else:
+        raise ValueError(kind)
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    return r, c, v
+
+
+@pytest.mark.parametrize("kind", ["powerlaw", "regular", "short", "hollow"])
+@pytest.mark.parametrize("kernel,lanes", [(1, 0), (2, 2), (2, 8), (2, 32), (3, 0), (0, 0)])
+def test_spmv_kernels_within_tolerance(eng, kind, kernel, lanes):
+    rng = np.random.default_rng(sum(map(ord, kind)) * 131 + kernel * 17 + lanes)
+    rows, cols = 30011, 40009
+    r, c, v = _matrix(rng, kind, rows, cols)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    if kernel:
+        eng.force_kernel(idx, kernel, lanes)
+    rp, ci, vv = eng.plan_csr(idx)
+    _check_run(eng, idx, rp, ci, vv, rows, cols, rng)
+    _check_run(eng, idx, rp, ci, vv, rows, cols, rng, alpha=1.0, beta=0.0)
+
+
+def test_run_is_deterministic(eng):
+    rng = np.random.default_rng(11)
+    rows, cols = 20000, 20000
+    r, c, v = _matrix(rng, "powerlaw", rows, cols)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    rp, ci, vv = eng.plan_csr(idx)
+    x = rng.standard_normal(cols).astype(np.float32)
+    b = rng.standard_normal(rows).astype(np.float32)
+    eng.select_matrix(idx)
+    ys = []
+    for _ in range(3):
+        y = np.zeros(rows, np.float32)
+        eng.run_kernel(x, b, y, 0.55, -2.05)
+        ys.append(y.copy())
+    assert np.array_equal(ys[0].view(np.uint32), ys[1].view(np.uint32))
+    assert np.array_equal(ys[0].view(np.uint32), ys[2].view(np.uint32))
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (3, 5), (257, 1031), (1024, 4096), (1000, 10000), (64, 50000), (5, 70001)])
+def test_gemv_within_tolerance(eng, rows, cols):
+    rng = np.random.default_rng(rows * 7 + cols)
+    a = rng.standard_normal((rows, cols)).astype(np.float32)
+    x = rng.standard_normal(cols).astype(np.float32)
+    b = rng.standard_normal(rows).astype(np.float32)
+    idx = eng.create_dense_handle(a.reshape(-1), rows, cols)
+    assert eng.matrix_info(idx)["kernel_name"] == "gemv"
+    eng.select_matrix(idx)
+    y = np.full(rows, np.nan, np.float32)
+    eng.run_kernel(x, b, y, float(ALPHA), float(BETA))
+    y64, scale = ol.gemv_f64(a, rows, cols, x, b, ALPHA, BETA)
+    err, at = ol.max_scaled_error(y, y64, scale)
+    assert err <= TOL, (err, at)
+
+
+def test_reference_closed_form_inputs_vs_mkl(eng):
+    """The reference's own self-check protocol (cpu/src/main.cpp:147-148,173-178) on a C1-shaped matrix; our
+    result and the reference's mkl_sparse_s_mv result are both held to the 1e-5 bar against float64."""
+    from hispmv_b200.synth import c1_imbalanced_coo, reference_vectors
+    r, c, v, n, _ = c1_imbalanced_coo(n=8192, target_nnz=110000, dense_rows=4, dense_len=3000)
+    idx = eng.create_sparse_handle(r, c, v, n, n)
+    rp, ci, vv = eng.plan_csr(idx)
+    x, y0 = reference_vectors(n, n)
+    y = np.zeros(n, np.float32)
+    eng.select_matrix(idx)
+    eng.run_kernel(x, y0, y, float(ALPHA), float(BETA))
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, y0, ALPHA, BETA)
+    err, _ = ol.max_scaled_error(y, y64, scale)
+    assert err <= TOL
+    if ol.have_ref():
+        y_mkl = y0.copy()
+        ol.ref_cpu().ref_mkl_spmv(rp, ci, vv, n, n, ci.size, x, y_mkl, ALPHA, BETA, 1)
+        err_mkl, _ = ol.max_scaled_error(y_mkl, y64, scale)
+        assert err_mkl <= TOL
+        # ours vs MKL directly, same normaliser
+        d = np.abs(y.astype(np.float64) - y_mkl.astype(np.float64))
+        assert np.all(d <= 2 * TOL * np.maximum(scale, 1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------
+# the plugin surface (pyhispmv), mirroring apps/general_test.py:22-116
+# ---------------------------------------------------------------------------------------------------
+def test_pyhispmv_general_test_flow():
+    import pyhispmv
+    fpga = pyhispmv.FpgaHandle("unused.xclbin", 0, 24, 1, 1, 2, 5, True, False, True)
+    rng = np.random.default_rng(0)
+    rows, cols = 5000, 1000
+    dense = rng.random((rows, cols), dtype=np.float32)
+    x = rng.random(cols, dtype=np.float32)
+    bias = rng.random(rows, dtype=np.float32)
+    nnz = 100000
+    cr = rng.integers(0, rows, nnz).astype(np.int32)
+    cc = rng.integers(0, cols, nnz).astype(np.int32)
+    cv = rng.random(nnz, dtype=np.float32)
+    di = fpga.create_dense_handle(dense.flatten(), rows, cols)
+    si = fpga.create_sparse_handle(cr, cc, cv, rows, cols)
+    assert (di, si) == (0, 1)
+    fpga.load_matrices()
+    fpga.load_matrices()  # idempotent here
+    y_d = np.zeros(rows, np.float32)
+    y_s = np.zeros(rows, np.float32)
+    fpga.select_matrix(di)
+    fpga.run_kernel(x, bias, y_d, 1.0, 1.0)
+    fpga.select_matrix(si)
+    fpga.run_kernel(x, bias, y_s, 1.0, 1.0)
+    from scipy.sparse import coo_matrix
+    exp_d = dense.astype(np.float64) @ x + bias
+    exp_s = coo_matrix((cv.astype(np.float64), (cr, cc)), shape=(rows, cols)).dot(x.astype(np.float64)) + bias
+    assert np.allclose(y_d, exp_d, rtol=1e-3)   # the reference's own bar (general_test.py:106,113)
+    assert np.allclose(y_s, exp_s, rtol=1e-3)
+    assert np.max(np.abs(y_d - exp_d) / np.abs(exp_d)) < 1e-5
+    assert np.max(np.abs(y_s - exp_s) / np.abs(exp_s)) < 1e-5
+    # linear(): alpha = beta = 1, several vectors, new array back
+    xs = rng.random((3, cols), dtype=np.float32)
+    out = fpga.linear(si, xs.reshape(-1), bias)
+    assert out.shape == (3 * rows,) and out.dtype == np.float32
+    for k in range(3):
+        e = coo_matrix((cv.astype(np.float64), (cr, cc)), shape=(rows, cols)).dot(xs[k].astype(np.float64)) + bias
+        assert np.allclose(out[k * rows:(k + 1) * rows], e, rtol=1e-4, atol=1e-5)
+    with pytest.raises(IndexError):
+        fpga.select_matrix(7)
+    with pytest.raises(TypeError):
+        fpga.run_kernel(x, bias, np.zeros(rows, np.float64), 1.0, 1.0)  # y must be float32, written in place
+
+
+def test_pyhispmv_misuse_errors():
+    import pyhispmv
+    fpga = pyhispmv.FpgaHandle("x", 0, 24, 1, 1, 2, 5, False, False, True)  # dense_overlay off
+    with pytest.raises(RuntimeError):
+        fpga.create_dense_handle(np.zeros(4, np.float32), 2, 2)
+    with pytest.raises(RuntimeError):
+        fpga.run_kernel(np.zeros(2, np.float32), np.zeros(2, np.float32), np.zeros(2, np.float32), 1.0, 1.0)
+    with pytest.raises(RuntimeError):
+        pyhispmv.FpgaHandle("x", 99, 24, 1, 1, 2, 5, True, False, True)  # no such device: error, not exit()
+
+
+def test_memory_full_returns_minus_one():
+    from hispmv_b200 import Engine
+    e = Engine(0, memory_limit=1 << 20)
+    rng = np.random.default_rng(0)
+    assert e.create_dense_handle(np.zeros(16, np.float32), 4, 4) == 0
+    assert e.create_dense_handle(rng.random(1 << 20, dtype=np.float32), 1024, 1024) == -1   # 4 MiB > 1 MiB cap
+    r, c, v = _rand_coo(rng, 1000, 1000, 400000)
+    assert e.create_sparse_handle(r, c, v, 1000, 1000) == -1
+    assert e.num_matrices() == 1
+    e.close()
+
+
+def test_load_mtx_on_device(eng, tmp_path):
+    from hispmv_b200.synth import c1_imbalanced_coo, write_mtx
+    r, c, v, n, _ = c1_imbalanced_coo(n=2048, target_nnz=20000, dense_rows=2, dense_len=1500)
+    p = tmp_path / "m.mtx"
+    write_mtx(str(p), r, c, v, n, n)
+    idx = eng.load_mtx(str(p))
+    rp, ci, vv = eng.plan_csr(idx)
+    r2, c2, v2, nr, nc = ol.load_mtx(str(p))
+    rp2, ci2, vv2 = ol.coo_to_csr(nr, r2, c2, v2)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and np.array_equal(vv, vv2)
+    sym = tmp_path / "s.mtx"
+    sym.write_text("%%MatrixMarket matrix coordinate real symmetric\n4 4 4\n1 1 1\n3 1 2.5\n4 2 -1\n4 4 3\n")
+    idx = eng.load_mtx(str(sym))
+    rp, ci, vv = eng.plan_csr(idx)
+    r2, c2, v2, nr, nc = ol.load_mtx(str(sym))
+    rp2, ci2, vv2 = ol.coo_to_csr(nr, r2, c2, v2)
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and np.array_equal(vv, vv2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic generators: device output bit-exact against the CPU restatement
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("which", ["c2", "c4", "c5"])
+def test_synth_generators_bit_exact(eng, which):
+    from hispmv_b200 import synth
+    spec = {"c2": synth.c2_powerlaw(0.002), "c4": synth.c4_stencil(0.0004), "c5": synth.c5_uniform(0.0002)}[which]
+    d = synth.DeviceCSR(spec)
+    idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
+    rp, ci, vv = eng.plan_csr(idx)
+    rp2, ci2, vv2 = ol.synth_csr(spec.kind, spec.seed, spec.cols, spec.params, 0, spec.rows)
+    assert d.nnz == ci2.size
+    assert np.array_equal(rp, rp2) and np.array_equal(ci, ci2) and np.array_equal(vv.view(np.uint32), vv2.view(np.uint32))
+    # columns sorted inside each row
+    row_of = np.repeat(np.arange(spec.rows), np.diff(rp2))
+    same_row = row_of[1:] == row_of[:-1]
+    assert np.all(ci2[1:][same_row] >= ci2[:-1][same_row])
+    rng = np.random.default_rng(1)
+    _check_run(eng, idx, rp2, ci2, vv2, spec.rows, spec.cols, rng)
+    # a row block generated on its own equals the slice of the whole
+    b0, b1 = spec.rows // 3, 2 * spec.rows // 3
+    blk = synth.DeviceCSR(spec, b0, b1)
+    assert blk.nnz == rp2[b1] - rp2[b0]
+    bounds, total = synth.synth_shard_bounds(spec, 4)
+    assert total == ci2.size and np.array_equal(bounds, ol.shard_bounds(rp2, 4))
+    d.close()
+    blk.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident calls and sharding inside one process
+# ---------------------------------------------------------------------------------------------------
+def test_run_dev_and_linear_dev_relu(eng):
+    import torch
+    rng = np.random.default_rng(5)
+    rows, cols = 20000, 9000
+    r, c, v = _matrix(rng, "powerlaw", rows, cols)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    rp, ci, vv = eng.plan_csr(idx)
+    x = rng.standard_normal(cols).astype(np.float32)
+    b = rng.standard_normal(rows).astype(np.float32)
+    xd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(b).cuda()
+    yd = torch.empty(rows, dtype=torch.float32, device="cuda")
+    for kernel in (0, 1, 2, 3):
+        eng.force_kernel(idx, kernel)
+        stream = torch.cuda.current_stream().cuda_stream
+        eng.linear_dev(idx, xd, bd, yd, relu=True, stream=stream)
+        torch.cuda.synchronize()
+        y64, scale = ol.spmv_f64(rp, ci, vv, x, b, 1.0, 1.0)
+        y = yd.cpu().numpy()
+        assert np.all(y >= 0)
+        pos = y64 > 1e-4 * np.maximum(scale, 1e-30)
+        err, _ = ol.max_scaled_error(y[pos], y64[pos], scale[pos])
+        assert err <= TOL
+        neg = y64 < -1e-4 * np.maximum(scale, 1e-30)
+        assert np.all(y[neg] == 0)
+
+
+@pytest.mark.parametrize("parts", [2, 3])
+def test_row_block_shards_reassemble(parts):
+    """Each shard context keeps only its nnz-balanced row block; concatenated y equals the unsharded y."""
+    from hispmv_b200 import Engine
+    rng = np.random.default_rng(parts)
+    rows, cols = 30000, 12000
+    r, c, v = _matrix(rng, "powerlaw", rows, cols)
+    x = rng.standard_normal(cols).astype(np.float32)
+    b = rng.standard_normal(rows).astype(np.float32)
+    full = Engine(0)
+    fi = full.create_sparse_handle(r, c, v, rows, cols)
+    rp, ci, vv = full.plan_csr(fi)
+    bounds = ol.shard_bounds(rp, parts)
+    pieces = []
+    for p in range(parts):
+        e = Engine(0, shard=(p, parts))
+        i = e.create_sparse_handle(r, c, v, rows, cols)
+        info = e.matrix_info(i)
+        assert (info["row_begin"], info["row_end"]) == (bounds[p], bounds[p + 1])
+        y = np.zeros(info["row_end"] - info["row_begin"], np.float32)
+        e.select_matrix(i)
+        e.run_kernel(x, b[info["row_begin"]:info["row_end"]], y, 0.55, -2.05)
+        pieces.append(y)
+        e.close()
+    y = np.concatenate(pieces)
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, b, 0.55, -2.05)
+    err, _ = ol.max_scaled_error(y, y64, scale)
+    assert err <= TOL
+    full.close()

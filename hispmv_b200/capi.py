@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libhispmv_cuda.so")
 HIST_BINS = 33
 
 OK, FULL, ERR_ARG, ERR_INDEX, ERR_CUDA, ERR_STATE, ERR_IO = 0, -1, -2, -3, -4, -5, -6
-KERNEL_AUTO, KERNEL_CSR_SCALAR, KERNEL_CSR_VECTOR, KERNEL_MERGE, KERNEL_GEMV, KERNEL_EMPTY = 0, 1, 2, 3, 4, 5
-KERNEL_NAMES = {0: "auto", 1: "csr_scalar", 2: "csr_vector", 3: "merge", 4: "gemv", 5: "empty"}
+KERNEL_AUTO, KERNEL_CSR_SCALAR, KERNEL_CSR_VECTOR, KERNEL_MERGE, KERNEL_GEMV, KERNEL_EMPTY, KERNEL_ADAPTIVE = 0, 1, 2, 3, 4, 5, 6
+KERNEL_NAMES = {0: "auto", 1: "csr_scalar", 2: "csr_vector", 3: "merge", 4: "gemv", 5: "empty", 6: "adaptive"}
 FLAG_DENSE_OVERLAY, FLAG_ROW_DIST_NET = 1, 2
 SYNTH_POWERLAW, SYNTH_UNIFORM, SYNTH_STENCIL27 = 1, 2, 3
 
@@ -68,11 +68,13 @@ def _load() -> C.CDLL:
         "hispmv_run_dev": (C.c_int, [p, C.c_int, p, p, p, f32, f32, p]),
         "hispmv_linear_dev": (C.c_int, [p, C.c_int, p, p, p, C.c_int, p]),
         "hispmv_sync": (C.c_int, [p]),
+        "hispmv_stream": (C.c_void_p, [p]),
         "hispmv_launches_per_run": (C.c_int, [p, C.c_int]),
         "hispmv_matrix_info_get": (C.c_int, [p, C.c_int, C.POINTER(MatrixInfo)]),
         "hispmv_plan_csr": (C.c_int, [p, C.c_int, p, p, p]),
         "hispmv_plan_tiles": (C.c_int, [p, C.c_int, p, p]),
         "hispmv_plan_split_rows": (C.c_int, [p, C.c_int, p]),
+        "hispmv_plan_tile_chunks": (C.c_int, [p, C.c_int, p]),
         "hispmv_load_mtx": (C.c_int, [p, C.c_char_p]),
         "hispmv_synth_count": (C.c_int, [C.c_int, u64, i32, i32, p, i32, i32, C.POINTER(i64)]),
         "hispmv_synth_shard_bounds": (C.c_int, [C.c_int, u64, i32, i32, p, C.c_int, p, C.POINTER(i64)]),
@@ -92,8 +94,8 @@ EXPORTED = [
     "hispmv_shard_bounds", "hispmv_set_memory_limit", "hispmv_add_sparse_coo", "hispmv_add_sparse_csr",
     "hispmv_add_dense", "hispmv_add_sparse_coo_dev", "hispmv_add_sparse_csr_dev", "hispmv_add_dense_dev",
     "hispmv_commit", "hispmv_num_matrices", "hispmv_select", "hispmv_force_kernel", "hispmv_run",
-    "hispmv_linear", "hispmv_run_dev", "hispmv_linear_dev", "hispmv_sync", "hispmv_launches_per_run",
-    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_load_mtx",
+    "hispmv_linear", "hispmv_run_dev", "hispmv_linear_dev", "hispmv_sync", "hispmv_stream", "hispmv_launches_per_run",
+    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_load_mtx",
     "hispmv_synth_count", "hispmv_synth_shard_bounds", "hispmv_synth_csr", "hispmv_synth_free",
 ]
 

@@ -7,6 +7,7 @@
 #include <fstream>
 #include <sstream>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "internal.h"
@@ -45,6 +46,9 @@ struct Matrix {
   float* d_carry = nullptr;
   int32_t* d_split_rows = nullptr;
   int64_t num_split = 0;
+  int32_t* d_tile_chunk = nullptr;      // ADAPTIVE
+  unsigned int* d_counter = nullptr;    // ADAPTIVE (two lanes, like d_carry)
+  int32_t long_threshold = 0, chunk_nnz = 0;
   // dense
   float* d_a = nullptr;
   int64_t ld = 0;
@@ -55,6 +59,10 @@ struct Matrix {
     cudaFree(d_tile_nnz);
     cudaFree(d_carry);
     cudaFree(d_split_rows);
+    cudaFree(d_tile_chunk);
+    cudaFree(d_counter);
+    d_tile_chunk = nullptr;
+    d_counter = nullptr;
     d_tile_row = nullptr;
     d_tile_nnz = nullptr;
     d_carry = nullptr;
@@ -66,7 +74,7 @@ struct Matrix {
   int64_t device_bytes() const {
     if (dense) return (int64_t)local_rows() * ld * 4;
     int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
-    if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 4 + num_split * 4;
+    if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4;
     return b;
   }
   ~Matrix() {
@@ -168,10 +176,23 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     st = merge_tiles_device(m->d_row_ptr, m->local_rows(), m->nnz, m->tile_items, &m->num_tiles, &m->d_tile_row,
                             &m->d_tile_nnz, c->stream);
     if (st != HISPMV_OK) return st;
-    HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, (size_t)m->num_tiles * sizeof(float)));
+    HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, (size_t)m->num_tiles * 2 * sizeof(float)));
     st = split_rows_device(m->d_row_ptr, m->local_rows(), m->d_tile_row, m->d_tile_nnz, m->num_tiles,
                            &m->d_split_rows, &m->num_split, c->stream);
     if (st != HISPMV_OK) return st;
+  }
+  if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
+    m->tile_items = kAdaptiveStreamItems;
+    m->long_threshold = kAdaptiveLongThreshold;
+    m->chunk_nnz = kAdaptiveChunkNnz;
+    st = adaptive_tiles_device(m->d_row_ptr, m->local_rows(), m->tile_items, m->long_threshold, m->chunk_nnz,
+                               &m->num_tiles, &m->d_tile_row, &m->d_tile_chunk, &m->d_split_rows, &m->num_split,
+                               c->stream);
+    if (st != HISPMV_OK) return st;
+    const size_t n = (size_t)std::max<int64_t>(m->num_tiles, 1) * 2;
+    HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, n * sizeof(float)));
+    HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, n * sizeof(unsigned int)));
+    HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, n * sizeof(unsigned int), c->stream));
   }
   HISPMV_CUDA(cudaStreamSynchronize(c->stream));
   return HISPMV_OK;
@@ -343,8 +364,10 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
   return (int)c->mats.size() - 1;
 }
 
+// `lane` selects one of the two carry / counter sets so that linear()'s two stream lanes never share them.
+// Device-pointer callers get lane 0: one run in flight per matrix handle, as with the reference's xrt::run.
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
-               int relu, cudaStream_t s) {
+               int relu, cudaStream_t s, int lane = 0) {
   Epilogue ep{alpha, beta, d_bias, relu};
   if (beta != 0.0f && !d_bias) {
     set_error("run: bias is required when beta != 0");
@@ -375,8 +398,20 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.num_tiles = m->num_tiles;
       P.tile_row = m->d_tile_row;
       P.tile_nnz = m->d_tile_nnz;
-      P.carry = m->d_carry;
+      P.carry = m->d_carry + (size_t)lane * m->num_tiles;
       return launch_merge(A, P, d_x, d_y, ep, s);
+    }
+    case HISPMV_KERNEL_ADAPTIVE: {
+      AdaptivePlan P;
+      P.stream_items = m->tile_items;
+      P.long_threshold = m->long_threshold;
+      P.chunk_nnz = m->chunk_nnz;
+      P.num_tiles = m->num_tiles;
+      P.tile_row = m->d_tile_row;
+      P.tile_chunk = m->d_tile_chunk;
+      P.carry = m->d_carry + (size_t)lane * m->num_tiles;
+      P.counter = m->d_counter + (size_t)lane * m->num_tiles;
+      return launch_adaptive(A, P, d_x, d_y, ep, s);
     }
     default: set_error("run: matrix has no plan"); return HISPMV_ERR_STATE;
   }
@@ -530,7 +565,7 @@ int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
     return HISPMV_ERR_ARG;
   }
   if (kernel != HISPMV_KERNEL_AUTO && kernel != HISPMV_KERNEL_CSR_SCALAR && kernel != HISPMV_KERNEL_CSR_VECTOR &&
-      kernel != HISPMV_KERNEL_MERGE) {
+      kernel != HISPMV_KERNEL_MERGE && kernel != HISPMV_KERNEL_ADAPTIVE) {
     set_error("force_kernel: unknown kernel");
     return HISPMV_ERR_ARG;
   }
@@ -550,7 +585,7 @@ int hispmv_run_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);
-  return run_matrix(c, m, d_x, d_bias, d_y, alpha, beta, 0, stream ? (cudaStream_t)stream : c->stream);
+  return run_matrix(c, m, d_x, d_bias, d_y, alpha, beta, 0, (cudaStream_t)stream);
 }
 
 int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
@@ -558,8 +593,10 @@ int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_b
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);
-  return run_matrix(c, m, d_x, d_bias, d_y, 1.0f, d_bias ? 1.0f : 0.0f, relu, stream ? (cudaStream_t)stream : c->stream);
+  return run_matrix(c, m, d_x, d_bias, d_y, 1.0f, d_bias ? 1.0f : 0.0f, relu, (cudaStream_t)stream);
 }
+
+void* hispmv_stream(hispmv_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int hispmv_sync(hispmv_ctx* c) {
   if (!c) return HISPMV_ERR_ARG;
@@ -627,7 +664,7 @@ int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const f
   for (int64_t v = 0; v < num_vecs; ++v) {
     const int l = (int)(v & 1);
     HISPMV_CUDA(cudaMemcpyAsync(c->d_x[l], x + v * m->cols, (size_t)m->cols * 4, cudaMemcpyHostToDevice, lanes[l]));
-    st = run_matrix(c, m, c->d_x[l], c->d_bias, c->d_y[l], 1.0f, 1.0f, 0, lanes[l]);
+    st = run_matrix(c, m, c->d_x[l], c->d_bias, c->d_y[l], 1.0f, 1.0f, 0, lanes[l], l);
     if (st != HISPMV_OK) return st;
     if (n_y > 0)
       HISPMV_CUDA(cudaMemcpyAsync(y_out + v * n_y, c->d_y[l], (size_t)n_y * 4, cudaMemcpyDeviceToHost, lanes[l]));
@@ -679,12 +716,38 @@ int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_n
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (!m->d_tile_row) {
-    set_error("plan_tiles: matrix is not planned for the merge kernel");
+    set_error("plan_tiles: matrix is not planned for a tiled kernel");
     return HISPMV_ERR_STATE;
   }
   DeviceGuard g(c->device);
   if (tile_row) HISPMV_CUDA(cudaMemcpy(tile_row, m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
-  if (tile_nnz) HISPMV_CUDA(cudaMemcpy(tile_nnz, m->d_tile_nnz, (size_t)(m->num_tiles + 1) * 8, cudaMemcpyDeviceToHost));
+  if (tile_nnz && m->kernel == HISPMV_KERNEL_MERGE)
+    HISPMV_CUDA(cudaMemcpy(tile_nnz, m->d_tile_nnz, (size_t)(m->num_tiles + 1) * 8, cudaMemcpyDeviceToHost));
+  if (tile_nnz && m->kernel == HISPMV_KERNEL_ADAPTIVE) {
+    // offset of each tile's first nonzero: row_ptr[tile_row] (+ chunk * chunk_nnz for LONG tiles)
+    std::vector<int32_t> tr((size_t)m->num_tiles + 1), tc((size_t)std::max<int64_t>(m->num_tiles, 1));
+    HISPMV_CUDA(cudaMemcpy(tr.data(), m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
+    if (m->num_tiles)
+      HISPMV_CUDA(cudaMemcpy(tc.data(), m->d_tile_chunk, (size_t)m->num_tiles * 4, cudaMemcpyDeviceToHost));
+    for (int64_t t = 0; t <= m->num_tiles; ++t) {
+      int32_t rp = 0;
+      HISPMV_CUDA(cudaMemcpy(&rp, m->d_row_ptr + tr[(size_t)t], 4, cudaMemcpyDeviceToHost));
+      tile_nnz[t] = (int64_t)rp + (t < m->num_tiles && tc[(size_t)t] > 0 ? (int64_t)tc[(size_t)t] * m->chunk_nnz : 0);
+    }
+  }
+  return HISPMV_OK;
+}
+
+int hispmv_plan_tile_chunks(hispmv_ctx* c, int idx, int32_t* chunk_out) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (m->kernel != HISPMV_KERNEL_ADAPTIVE || !m->d_tile_chunk) {
+    set_error("plan_tile_chunks: matrix is not planned for the adaptive kernel");
+    return HISPMV_ERR_STATE;
+  }
+  DeviceGuard g(c->device);
+  if (chunk_out && m->num_tiles)
+    HISPMV_CUDA(cudaMemcpy(chunk_out, m->d_tile_chunk, (size_t)m->num_tiles * 4, cudaMemcpyDeviceToHost));
   return HISPMV_OK;
 }
 

@@ -39,6 +39,20 @@ struct MergePlan {
   float* carry = nullptr;              // num_tiles: partial sum of the row left open at each tile's end
 };
 
+// Row-aligned adaptive tiling (the default for imbalanced matrices):
+//   STREAM tile  consecutive rows, each shorter than long_threshold, together about stream_items merge items
+//                (row ends + nonzeros; never more than stream_items + long_threshold)
+//   LONG tile    one chunk of at most chunk_nnz nonzeros of a row with >= long_threshold nonzeros; a row
+//                with several chunks is "split": its partial sums meet in carry[] (one slot per tile)
+struct AdaptivePlan {
+  int32_t stream_items = 0, long_threshold = 0, chunk_nnz = 0;
+  int64_t num_tiles = 0;
+  const int32_t* tile_row = nullptr;    // num_tiles+1: first row of every tile, then `rows`
+  const int32_t* tile_chunk = nullptr;  // num_tiles: -1 for STREAM tiles, chunk index for LONG tiles
+  float* carry = nullptr;               // num_tiles partial sums (LONG tiles of split rows)
+  unsigned int* counter = nullptr;      // num_tiles arrival counters, indexed by a split row's first tile
+};
+
 struct RowStats {
   int64_t hist[HISPMV_HIST_BINS];
   int64_t nnz;
@@ -72,6 +86,11 @@ int alloc_padded_nnz_arrays(const int32_t* src_col, const float* src_val, int64_
 int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int n_parts, int32_t* h_bounds,
                         cudaStream_t stream);
 
+// Adaptive tiles; arrays cudaMalloc'ed by the callee.  d_split_rows: rows with more than one LONG chunk.
+int adaptive_tiles_device(const int32_t* d_row_ptr, int32_t rows, int32_t stream_items, int32_t long_threshold,
+                          int32_t chunk_nnz, int64_t* num_tiles, int32_t** d_tile_row, int32_t** d_tile_chunk,
+                          int32_t** d_split_rows, int64_t* num_split, cudaStream_t stream);
+
 // The runtime selector (pure host integer arithmetic over RowStats; restated in oracle/).
 void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* kernel, int* lanes);
 // tile_items the merge kernel instantiation uses for a matrix with these stats
@@ -86,6 +105,8 @@ struct Epilogue {
 int launch_csr_scalar(const CsrDev& A, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_csr_vector(const CsrDev& A, int lanes, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_merge(const CsrDev& A, const MergePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
+int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
+constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdaptiveChunkNnz = 4096;
 int launch_empty(int32_t rows, float* y, Epilogue ep, cudaStream_t s);
 bool merge_tile_items_supported(int tile_items);
 

@@ -427,6 +427,127 @@ int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adaptive, row-aligned tiling (see AdaptivePlan in internal.h; restated in oracle_adaptive_tiles).
+//   w_r = 0 for long rows (len >= T), 1 + len otherwise;  S = exclusive prefix sum of w
+//   a short row r opens a STREAM tile when r == 0, when row r-1 is long, or when S_r / B != S_{r-1} / B
+//   a long row r contributes ceil(len / CH) LONG tiles (chunk 0, 1, ...)
+// Tiles are numbered in row order, so a STREAM tile's rows end where the next tile's first row begins.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct ShortWork {
+  const int32_t* rp;
+  int32_t T;
+  __host__ __device__ int64_t operator()(int64_t r) const {
+    const int32_t len = rp[r + 1] - rp[r];
+    return len >= T ? 0 : 1 + (int64_t)len;
+  }
+};
+
+__global__ void adaptive_count_kernel(const int32_t* __restrict__ rp, const int64_t* __restrict__ S, int32_t rows,
+                                      int32_t B, int32_t T, int32_t CH, int32_t* __restrict__ cnt,
+                                      int32_t* __restrict__ split_flag) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int32_t len = rp[r + 1] - rp[r];
+  int32_t c;
+  if (len >= T) {
+    c = (len + CH - 1) / CH;
+  } else if (r == 0) {
+    c = 1;
+  } else {
+    const bool prev_long = (rp[r] - rp[r - 1]) >= T;
+    c = (prev_long || (S[r] / B != S[r - 1] / B)) ? 1 : 0;
+  }
+  cnt[r] = c;
+  split_flag[r] = (len >= T && c >= 2) ? 1 : 0;
+}
+
+__global__ void adaptive_scatter_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ cnt,
+                                        const int32_t* __restrict__ first, const int32_t* __restrict__ split_flag,
+                                        const int32_t* __restrict__ split_pos, int32_t rows, int32_t T,
+                                        int32_t* __restrict__ tile_row, int32_t* __restrict__ tile_chunk,
+                                        int32_t* __restrict__ split_rows) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int32_t c = cnt[r];
+  if (c > 0) {
+    const bool is_long = (rp[r + 1] - rp[r]) >= T;
+    const int32_t t0 = first[r];
+    for (int32_t k = 0; k < c; ++k) {
+      tile_row[t0 + k] = (int32_t)r;
+      tile_chunk[t0 + k] = is_long ? k : -1;
+    }
+  }
+  if (split_flag[r]) split_rows[split_pos[r]] = (int32_t)r;
+}
+
+}  // namespace
+
+int adaptive_tiles_device(const int32_t* d_row_ptr, int32_t rows, int32_t stream_items, int32_t long_threshold,
+                          int32_t chunk_nnz, int64_t* num_tiles, int32_t** d_tile_row, int32_t** d_tile_chunk,
+                          int32_t** d_split_rows, int64_t* num_split, cudaStream_t stream) {
+  *num_tiles = 0;
+  *num_split = 0;
+  *d_tile_row = nullptr;
+  *d_tile_chunk = nullptr;
+  *d_split_rows = nullptr;
+  if (rows <= 0) {
+    HISPMV_CUDA(cudaMalloc((void**)d_tile_row, sizeof(int32_t)));
+    HISPMV_CUDA(cudaMemsetAsync(*d_tile_row, 0, sizeof(int32_t), stream));
+    return HISPMV_OK;
+  }
+  DevBuf S, cnt, first, sflag, spos, tmp;
+  int st;
+  if ((st = S.alloc((size_t)rows * 8)) || (st = cnt.alloc((size_t)rows * 4)) || (st = first.alloc((size_t)rows * 4)) ||
+      (st = sflag.alloc((size_t)rows * 4)) || (st = spos.alloc((size_t)rows * 4)))
+    return st;
+  cub::CountingInputIterator<int64_t> counting(0);
+  cub::TransformInputIterator<int64_t, ShortWork, cub::CountingInputIterator<int64_t>> work(
+      counting, ShortWork{d_row_ptr, long_threshold});
+  size_t tb = 0, tb2 = 0;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, work, S.as<int64_t>(), rows, stream));
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, cnt.as<int32_t>(), first.as<int32_t>(), rows, stream));
+  if ((st = tmp.alloc(std::max(tb, tb2)))) return st;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, work, S.as<int64_t>(), rows, stream));
+  adaptive_count_kernel<<<blocks_for(rows, 256), 256, 0, stream>>>(d_row_ptr, S.as<int64_t>(), rows, stream_items,
+                                                                   long_threshold, chunk_nnz, cnt.as<int32_t>(),
+                                                                   sflag.as<int32_t>());
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, cnt.as<int32_t>(), first.as<int32_t>(), rows, stream));
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, sflag.as<int32_t>(), spos.as<int32_t>(), rows, stream));
+  int32_t h[4];
+  HISPMV_CUDA(cudaMemcpyAsync(&h[0], cnt.as<int32_t>() + (rows - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h[1], first.as<int32_t>() + (rows - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h[2], sflag.as<int32_t>() + (rows - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h[3], spos.as<int32_t>() + (rows - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  const int64_t nt = (int64_t)h[0] + h[1];
+  const int64_t ns = (int64_t)h[2] + h[3];
+  HISPMV_CUDA(cudaMalloc((void**)d_tile_row, (size_t)(nt + 1) * 4));
+  st = check_cuda(cudaMalloc((void**)d_tile_chunk, (size_t)std::max<int64_t>(nt, 1) * 4), "cudaMalloc", __FILE__, __LINE__);
+  if (st == HISPMV_OK && ns > 0)
+    st = check_cuda(cudaMalloc((void**)d_split_rows, (size_t)ns * 4), "cudaMalloc", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    cudaFree(*d_tile_row);
+    cudaFree(*d_tile_chunk);
+    *d_tile_row = nullptr;
+    *d_tile_chunk = nullptr;
+    return st;
+  }
+  adaptive_scatter_kernel<<<blocks_for(rows, 256), 256, 0, stream>>>(d_row_ptr, cnt.as<int32_t>(), first.as<int32_t>(),
+                                                                     sflag.as<int32_t>(), spos.as<int32_t>(), rows,
+                                                                     long_threshold, *d_tile_row, *d_tile_chunk,
+                                                                     *d_split_rows);
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaMemcpyAsync(*d_tile_row + nt, &rows, 4, cudaMemcpyHostToDevice, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  *num_tiles = nt;
+  *num_split = ns;
+  return HISPMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Runtime selector.  Pure integer arithmetic on the row-length histogram so that the CPU restatement
 // (oracle/oracle.c: oracle_select_kernel) reproduces the decision bit for bit.
 //
@@ -434,7 +555,7 @@ int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int
 // collapses on a GPU to one question: is the row-length distribution regular enough that a fixed number
 // of lanes per row keeps every lane busy, or must work be balanced by nonzeros with heavy rows split?
 //   mean  = ceil(nnz / rows);  lanes = largest power of two <= mean, clamped to [2, 32]
-//   MERGE       if row splitting is allowed and any of
+//   ADAPTIVE    if row splitting is allowed and any of
 //                 heavy       max row  > 32 * max(mean, 4)      (one row would serialise a sub-warp)
 //                 hollow      more than half of the rows are empty
 //                 underfilled rows * lanes < 148 SMs * 1024 threads (too few rows to fill the GPU)
@@ -455,7 +576,7 @@ void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* 
   const bool hollow = (int64_t)st.empty_rows * 2 > (int64_t)st.rows;
   const bool underfilled = (int64_t)st.rows * l < 148LL * 1024;
   if (allow_split_rows && (heavy || hollow || underfilled)) {
-    *kernel = HISPMV_KERNEL_MERGE;
+    *kernel = HISPMV_KERNEL_ADAPTIVE;
     return;
   }
   if (mean <= 2) {

@@ -122,14 +122,18 @@ class Engine:
         check(lib.hispmv_force_kernel(self._ctx, matrix_idx, kernel, lanes), "force_kernel")
 
     def run_dev(self, matrix_idx: int, x, bias, y, alpha: float = 1.0, beta: float = 0.0, stream: int = 0) -> None:
-        """y = alpha*A@x + beta*bias on torch CUDA tensors, asynchronous on `stream` (a cudaStream_t int;
-        0 = the engine's own stream)."""
+        """y = alpha*A@x + beta*bias on torch CUDA tensors, asynchronous on `stream` (a cudaStream_t as int;
+        0 is the CUDA default stream, `self.stream` the engine's own)."""
         check(lib.hispmv_run_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), alpha, beta,
                                  C.c_void_p(stream)), "run_dev")
 
     def linear_dev(self, matrix_idx: int, x, bias, y, relu: bool = False, stream: int = 0) -> None:
         check(lib.hispmv_linear_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), int(relu),
                                     C.c_void_p(stream)), "linear_dev")
+
+    @property
+    def stream(self) -> int:
+        return int(lib.hispmv_stream(self._ctx) or 0)
 
     def sync(self) -> None:
         check(lib.hispmv_sync(self._ctx), "sync")
@@ -164,6 +168,12 @@ class Engine:
         tn = np.empty(info["num_tiles"] + 1, np.int64)
         check(lib.hispmv_plan_tiles(self._ctx, matrix_idx, _ptr(tr), _ptr(tn)), "plan_tiles")
         return tr, tn
+
+    def plan_tile_chunks(self, matrix_idx: int) -> np.ndarray:
+        info = self.matrix_info(matrix_idx)
+        out = np.empty(info["num_tiles"], np.int32)
+        check(lib.hispmv_plan_tile_chunks(self._ctx, matrix_idx, _ptr(out)), "plan_tile_chunks")
+        return out
 
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:
         info = self.matrix_info(matrix_idx)

@@ -30,9 +30,9 @@ class SynthSpec:
         return np.asarray(self.params, dtype=np.int64)
 
 
-# P(len >= L) = (K / 2^32) / L.  K/2^32 = 0.66 gives mean ~10 nnz/row when clipped at 1M (alpha = 2 tail);
-# about 6-7 rows in 10M reach the 1M clip, 34% of the rows are empty.
-_K_C2 = int(round(0.66 * 2 ** 32))
+# P(len >= L) = (K / 2^32) / L.  K/2^32 = 0.6912 gives 10.0 nnz/row on average (100.0M nnz in 10M rows) when clipped at 1M (alpha = 2 tail);
+# 5 rows in 10M sit at the 1M clip, 31% of the rows are empty.
+_K_C2 = int(round(0.6912 * 2 ** 32))
 
 
 def c2_powerlaw(scale: float = 1.0) -> SynthSpec:

@@ -63,7 +63,9 @@ enum {
   HISPMV_KERNEL_CSR_VECTOR = 2,  /* a sub-warp of 2..32 lanes per row: regular rows */
   HISPMV_KERNEL_MERGE = 3,       /* merge-path tiles, heavy rows split across CTAs, carry-out fix-up */
   HISPMV_KERNEL_GEMV = 4,        /* dense overlay: streaming row-major GeMV */
-  HISPMV_KERNEL_EMPTY = 5        /* nnz == 0: y = beta * bias */
+  HISPMV_KERNEL_EMPTY = 5,       /* nnz == 0: y = beta * bias */
+  HISPMV_KERNEL_ADAPTIVE = 6     /* row-aligned nnz-balanced tiles: short rows streamed through shared memory,
+                                    long rows chunked across CTAs with carry-out (default for imbalanced rows) */
 };
 
 /* ctor flags: the reference's hardware switches that still mean something on a GPU */
@@ -81,7 +83,7 @@ typedef struct hispmv_matrix_info {
   int32_t is_dense;
   int32_t kernel;           /* HISPMV_KERNEL_* actually planned */
   int32_t vector_lanes;     /* sub-warp width when kernel == CSR_VECTOR */
-  int32_t tile_items;       /* merge items (row ends + nonzeros) per CTA when kernel == MERGE */
+  int32_t tile_items;       /* merge items (row ends + nonzeros) per CTA: MERGE tile size / ADAPTIVE stream budget */
   int64_t num_tiles;        /* merge tiles (CTAs) */
   int64_t num_split_rows;   /* rows whose nonzeros span more than one tile (the "shared rows") */
   int32_t max_row_nnz;
@@ -133,7 +135,9 @@ int hispmv_force_kernel(hispmv_ctx* ctx, int idx, int kernel, int lanes);
 int hispmv_run(hispmv_ctx* ctx, const float* x, const float* bias, float* y, float alpha, float beta);
 int hispmv_linear(hispmv_ctx* ctx, int idx, const float* x, int64_t x_len, const float* bias, float* y_out);
 
-/* ---- device-buffer calls (asynchronous on `stream`, a cudaStream_t; NULL = the context's stream) ---- */
+/* ---- device-buffer calls: asynchronous on `stream`, a cudaStream_t.  As everywhere in CUDA, NULL is the
+ *      default stream; hispmv_stream() returns the context's own non-blocking stream. ---- */
+void* hispmv_stream(hispmv_ctx* ctx);
 int hispmv_run_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha,
                    float beta, void* stream);
 /* y = relu?(A x + bias) for chained layers that stay on the device. */
@@ -148,10 +152,13 @@ int hispmv_matrix_info_get(hispmv_ctx* ctx, int idx, hispmv_matrix_info* out);
 /* Copy the device CSR of the local row block back to the host (row_ptr rebased to 0).  Any pointer may be
  * NULL to skip that array.  Sizes: local_rows+1, nnz, nnz. */
 int hispmv_plan_csr(hispmv_ctx* ctx, int idx, int32_t* row_ptr, int32_t* col_idx, float* vals);
-/* Merge-path tile start coordinates: num_tiles+1 entries each (last = (local_rows, nnz)). */
+/* Tile start coordinates, num_tiles+1 entries each (last = (local_rows, nnz)).
+ * MERGE: merge-path coordinates.  ADAPTIVE: first row of the tile and the offset of its first nonzero. */
 int hispmv_plan_tiles(hispmv_ctx* ctx, int idx, int32_t* tile_row, int64_t* tile_nnz);
 /* Sorted ids of the rows split across tiles (num_split_rows entries). */
 int hispmv_plan_split_rows(hispmv_ctx* ctx, int idx, int32_t* rows_out);
+/* ADAPTIVE only: per tile, -1 for a STREAM tile or the chunk index of a LONG tile (num_tiles entries). */
+int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
 
 /* ---- Matrix Market ingest: real/integer/pattern x general/symmetric/skew-symmetric ---- */
 int hispmv_load_mtx(hispmv_ctx* ctx, const char* path);

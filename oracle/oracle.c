@@ -204,7 +204,7 @@ void oracle_row_stats(int rows, const int* row_ptr, int64_t* hist, int* max_row_
 }
 
 /* kernel ids as in include/hispmv.h */
-enum { K_SCALAR = 1, K_VECTOR = 2, K_MERGE = 3, K_EMPTY = 5 };
+enum { K_SCALAR = 1, K_VECTOR = 2, K_MERGE = 3, K_EMPTY = 5, K_ADAPTIVE = 6 };
 
 void oracle_select_kernel(int rows, int64_t nnz, int max_row_nnz, int empty_rows, int allow_split_rows, int* kernel,
                           int* lanes) {
@@ -223,7 +223,7 @@ void oracle_select_kernel(int rows, int64_t nnz, int max_row_nnz, int empty_rows
     const int hollow = (int64_t)empty_rows * 2 > (int64_t)rows;
     const int underfilled = (int64_t)rows * l < 148LL * 1024;
     if (allow_split_rows && (heavy || hollow || underfilled)) {
-      *kernel = K_MERGE;
+      *kernel = K_ADAPTIVE;
       return;
     }
   }
@@ -277,6 +277,59 @@ int64_t oracle_split_rows(int rows, const int* row_ptr, int64_t num_tiles, const
       if (out) out[n] = r;
       ++n;
       last = r;
+    }
+  }
+  return n;
+}
+
+/* Adaptive row-aligned tiles (hispmv_b200/csrc/partition.cu: adaptive_tiles_device).  Short rows
+ * (len < T) are packed, in order, into STREAM tiles of about B merge items (1 + len each); a tile is cut
+ * where the running item count crosses a multiple of B, and around every long row.  A long row becomes
+ * ceil(len / CH) LONG tiles.  tile_row gets num_tiles+1 entries (last = rows), tile_chunk num_tiles entries
+ * (-1 for STREAM, chunk index for LONG).  Call with tile_row == NULL to count. */
+int64_t oracle_adaptive_tiles(int rows, const int* row_ptr, int B, int T, int CH, int* tile_row, int* tile_chunk) {
+  int64_t nt = 0, S = 0, S_prev = 0;
+  int r, prev_long = 0;
+  for (r = 0; r < rows; ++r) {
+    const int len = row_ptr[r + 1] - row_ptr[r];
+    if (len >= T) {
+      const int c = (len + CH - 1) / CH;
+      int k;
+      for (k = 0; k < c; ++k) {
+        if (tile_row) {
+          tile_row[nt] = r;
+          tile_chunk[nt] = k;
+        }
+        ++nt;
+      }
+      prev_long = 1;
+      S_prev = S; /* w_r = 0 */
+    } else {
+      if (r == 0 || prev_long || (S / B != S_prev / B)) {
+        if (tile_row) {
+          tile_row[nt] = r;
+          tile_chunk[nt] = -1;
+        }
+        ++nt;
+      }
+      prev_long = 0;
+      S_prev = S;
+      S += 1 + (int64_t)len;
+    }
+  }
+  if (tile_row) tile_row[nt] = rows;
+  return nt;
+}
+
+/* rows split across several LONG tiles (len >= T and more than one chunk), ascending */
+int64_t oracle_adaptive_split_rows(int rows, const int* row_ptr, int T, int CH, int* out) {
+  int64_t n = 0;
+  int r;
+  for (r = 0; r < rows; ++r) {
+    const int len = row_ptr[r + 1] - row_ptr[r];
+    if (len >= T && (len + CH - 1) / CH >= 2) {
+      if (out) out[n] = r;
+      ++n;
     }
   }
   return n;

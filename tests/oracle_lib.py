@@ -66,6 +66,10 @@ def oracle() -> C.CDLL:
     lib.oracle_split_rows.argtypes = [i, _i32p, i64, _i32p, _i64p, vp]
     lib.oracle_split_rows.restype = i64
     lib.oracle_shard_bounds.argtypes = [i, _i32p, i, _i32p]
+    lib.oracle_adaptive_tiles.argtypes = [i, _i32p, i, i, i, vp, vp]
+    lib.oracle_adaptive_tiles.restype = i64
+    lib.oracle_adaptive_split_rows.argtypes = [i, _i32p, i, i, vp]
+    lib.oracle_adaptive_split_rows.restype = i64
     lib.oracle_synth_row_len.argtypes = [i, C.c_uint64, _i64p, i64]
     lib.oracle_synth_row_len.restype = i
     lib.oracle_synth_csr.argtypes = [i, C.c_uint64, i, _i64p, i, i, vp, vp, vp]
@@ -188,6 +192,22 @@ def split_rows(rp, tr, tn):
     if n:
         oracle().oracle_split_rows(rows, rp, nt, tr, tn, out.ctypes.data)
     return out
+
+
+def adaptive_tiles(rp, B=2048, T=1024, CH=4096):
+    rp = np.ascontiguousarray(rp, np.int32)
+    rows = rp.size - 1
+    nt = oracle().oracle_adaptive_tiles(rows, rp, B, T, CH, None, None)
+    tr = np.zeros(nt + 1, np.int32)
+    tc = np.zeros(max(nt, 1), np.int32)
+    oracle().oracle_adaptive_tiles(rows, rp, B, T, CH, tr.ctypes.data, tc.ctypes.data)
+    tc = tc[:nt]
+    tn = rp[tr].astype(np.int64)
+    tn[:nt] += np.maximum(tc, 0).astype(np.int64) * CH
+    ns = oracle().oracle_adaptive_split_rows(rows, rp, T, CH, None)
+    sp = np.zeros(max(ns, 1), np.int32)
+    oracle().oracle_adaptive_split_rows(rows, rp, T, CH, sp.ctypes.data)
+    return tr, tc, tn, sp[:ns]
 
 
 def row_stats(rp):

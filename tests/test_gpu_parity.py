@@ -105,6 +105,40 @@ def test_merge_plan_bit_exact(eng, tile, monkeypatch):
     _check_run(eng, idx, rp, ci, vv, rows, cols, rng)
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_adaptive_plan_bit_exact(eng, seed):
+    """Tile descriptors (first row, first-nonzero offset, chunk index) and the split-row list of the adaptive
+    kernel against the sequential restatement; includes heavy rows, runs of empty rows and long rows back to back."""
+    from hispmv_b200 import capi
+    rng = np.random.default_rng(seed)
+    rows, cols = 30000, 50000
+    lens = np.minimum(rng.zipf(1.6, rows), 40000)
+    heavy = rng.integers(1, rows - 2, 6)
+    lens[heavy] = rng.integers(1024, 20000, 6)
+    lens[heavy[0] + 1] = 5000           # two long rows in a row
+    lens[0] = 9000 if seed == 1 else lens[0]
+    lens[rows - 1] = 4096 if seed == 2 else lens[rows - 1]
+    lens[rng.integers(0, rows, 3000)] = 0
+    lens[1000:4500] = 0                 # > stream_items empty rows in a row
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_ADAPTIVE)
+    info = eng.matrix_info(idx)
+    assert info["kernel"] == capi.KERNEL_ADAPTIVE
+    rp, ci, vv = eng.plan_csr(idx)
+    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, info["tile_items"])
+    assert info["num_tiles"] == tc2.size and info["num_split_rows"] == sp2.size
+    tr, tn = eng.plan_tiles(idx)
+    assert np.array_equal(tr, tr2) and np.array_equal(tn, tn2)
+    assert np.array_equal(eng.plan_tile_chunks(idx), tc2)
+    assert np.array_equal(eng.plan_split_rows(idx), sp2)
+    y1 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
+    y2 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))   # counters reset themselves
+    assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
+
+
 @pytest.mark.parametrize("parts", [2, 3, 8])
 def test_shard_bounds_bit_exact(eng, parts):
     from hispmv_b200 import shard_bounds
@@ -136,7 +170,7 @@ def _matrix(rng, kind, rows, cols):
 
 
 @pytest.mark.parametrize("kind", ["powerlaw", "regular", "short", "hollow"])
-@pytest.mark.parametrize("kernel,lanes", [(1, 0), (2, 2), (2, 8), (2, 32), (3, 0), (0, 0)])
+@pytest.mark.parametrize("kernel,lanes", [(1, 0), (2, 2), (2, 8), (2, 32), (3, 0), (6, 0), (0, 0)])
 def test_spmv_kernels_within_tolerance(eng, kind, kernel, lanes):
     rng = np.random.default_rng(sum(map(ord, kind)) * 131 + kernel * 17 + lanes)
     rows, cols = 30011, 40009
@@ -338,7 +372,7 @@ def test_run_dev_and_linear_dev_relu(eng):
     b = rng.standard_normal(rows).astype(np.float32)
     xd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(b).cuda()
     yd = torch.empty(rows, dtype=torch.float32, device="cuda")
-    for kernel in (0, 1, 2, 3):
+    for kernel in (0, 1, 2, 3, 6):
         eng.force_kernel(idx, kernel)
         stream = torch.cuda.current_stream().cuda_stream
         eng.linear_dev(idx, xd, bd, yd, relu=True, stream=stream)

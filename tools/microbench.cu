@@ -151,7 +151,7 @@ int main() {
     const int64_t n = 1ll << 28;  // 268M gathers, 1 GiB of indices
     int32_t* idx;
     CK(cudaMalloc(&idx, n * 4));
-    const int64_t tables[] = {1ll << 18, 1ll << 20, 10000000ll, 40000000ll, 100000000ll};  // elements
+    const int64_t tables[] = {1ll << 13, 1ll << 14, 1ll << 15, 1ll << 16, 1ll << 18, 10000000ll, 100000000ll};  // elements
     const char* names[] = {"uniform", "zipf0.8", "sequential", "runs-of-8", "zipf0.8-scattered"};
     for (int64_t table : tables) {
       float* t;

@@ -91,11 +91,12 @@ def main():
         x = torch.rand(spec.cols, device="cuda", generator=g) + 0.5
         b = torch.rand(spec.rows, device="cuda", generator=g)
         y = torch.empty(spec.rows, device="cuda")
-        variants = [("merge", capi.KERNEL_MERGE, 0, t) for t in args.tiles.split(",")]
+        variants = [("adapt", capi.KERNEL_ADAPTIVE, 0, "")]
+        variants += [("merge", capi.KERNEL_MERGE, 0, t) for t in args.tiles.split(",") if t]
         variants += [("vector", capi.KERNEL_CSR_VECTOR, l, "") for l in (2, 4, 8, 16, 32)]
         variants += [("scalar", capi.KERNEL_CSR_SCALAR, 0, "")]
         for kname, k, lanes, tile in variants:
-            if kname != "merge" and info["max_row_nnz"] > 50000 and lanes != 32:
+            if kname in ("vector", "scalar") and info["max_row_nnz"] > 50000 and lanes != 32:
                 continue  # a 1M-nnz row on one thread / a narrow sub-warp would run for seconds
             if tile:
                 os.environ["HISPMV_MERGE_TILE"] = tile

@@ -185,6 +185,14 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     m->tile_items = kAdaptiveStreamItems;
     m->long_threshold = kAdaptiveLongThreshold;
     m->chunk_nnz = kAdaptiveChunkNnz;
+    if (const char* e = getenv("HISPMV_ADAPTIVE")) {  // "B,T,CH" (development sweeps)
+      int b = 0, t = 0, ch = 0;
+      if (sscanf(e, "%d,%d,%d", &b, &t, &ch) == 3 && b >= 256 && t >= 16 && b + t <= 4096 && ch >= 1024) {
+        m->tile_items = b;
+        m->long_threshold = t;
+        m->chunk_nnz = ch;
+      }
+    }
     st = adaptive_tiles_device(m->d_row_ptr, m->local_rows(), m->tile_items, m->long_threshold, m->chunk_nnz,
                                &m->num_tiles, &m->d_tile_row, &m->d_tile_chunk, &m->d_split_rows, &m->num_split,
                                c->stream);

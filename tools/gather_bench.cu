@@ -1,0 +1,140 @@
+// What bounds x gathers that miss L1?  (development microbenchmark; results recorded in DESIGN.md)
+//   A. rate vs. number of SMs used                 -> per-SM limit or L2-side limit?
+//   B. 4-byte vs 16-byte payload per random index  -> request-limited or byte-limited?
+//   C. L1 allocate / no_allocate / .cg              -> does skipping L1 allocation change the miss path rate?
+//   D. mix of shared-memory hits and global misses  -> do the two paths overlap?
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o build/gather_bench tools/gather_bench.cu
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+__global__ void make_idx(int32_t* idx, int64_t n, int64_t table) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) idx[i] = (int32_t)(mix64(i * 77 + 5) % (uint64_t)table);
+}
+
+__global__ void make_hot(int32_t* idx, int64_t n, int hot, int pct) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint64_t h = mix64(i * 31 + 9);
+    if ((int)(h % 100) < pct) idx[i] = (int32_t)((h >> 20) % (uint64_t)hot);
+  }
+}
+
+// MODE 0: ld.global.nc (L1 allocate)   1: ld.global.nc.L1::no_allocate   2: ld.global.cg
+// MODE 3: float4 payload (index rounded to 4)   4: hot fraction from shared memory (idx < hot -> smem)
+template <int MODE>
+__global__ void __launch_bounds__(1024) gather(const int32_t* __restrict__ idx, int64_t n4, const float* __restrict__ tab, int hot,
+                                               float* out) {
+  extern __shared__ float s_hot[];
+  if (MODE == 4) {
+    for (int i = threadIdx.x; i < hot; i += blockDim.x) s_hot[i] = tab[i];
+    __syncthreads();
+  }
+  float acc = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+#pragma unroll 2
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    int4 c;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(idx + 4 * i));
+    const int cs[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float v;
+      if (MODE == 0) {
+        asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
+      } else if (MODE == 1) {
+        asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
+      } else if (MODE == 2) {
+        asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
+      } else if (MODE == 3) {
+        float4 q;
+        asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(tab + (cs[k] & ~3)));
+        v = q.x + q.y + q.z + q.w;
+      } else {
+        if (cs[k] < hot) v = s_hot[cs[k]];
+        else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
+      }
+      acc += v;
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
+template <int MODE>
+float run(int grid, int threads, const int32_t* idx, int64_t n, const float* tab, int hot, float* out) {
+  auto kern = gather<MODE>;
+  const size_t smem = MODE == 4 ? (size_t)hot * 4 : 0;
+  if (smem) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int it = 0; it < 4; ++it) {
+    CK(cudaEventRecord(e0));
+    kern<<<grid, threads, smem>>>(idx, n / 4, tab, hot, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaGetLastError());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (it > 0 && ms < best) best = ms;
+  }
+  return best;
+}
+
+int main() {
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, 0));
+  const int sms = p.multiProcessorCount;
+  const int64_t n = 1ll << 27;
+  const int64_t table = 10 * 1000 * 1000;  // 40 MB: L2-resident, far larger than L1
+  int32_t* idx;
+  float *tab, *out;
+  CK(cudaMalloc(&idx, n * 4));
+  CK(cudaMalloc(&tab, table * 4 + 64));
+  CK(cudaMalloc(&out, 16));
+  CK(cudaMemset(tab, 0, table * 4 + 64));
+  make_idx<<<(int)((n + 255) / 256), 256>>>(idx, n, table);
+  CK(cudaDeviceSynchronize());
+  printf("A/B/C: uniform random gathers from a 40 MB table, %lld gathers\n", (long long)n);
+  for (int frac : {4, 2, 1}) {
+    const int use = sms / frac;
+    for (int threads : {512, 1024}) {
+      const int grid = use * (2048 / threads);
+      const float m0 = run<0>(grid, threads, idx, n, tab, 0, out);
+      const float m1 = run<1>(grid, threads, idx, n, tab, 0, out);
+      const float m2 = run<2>(grid, threads, idx, n, tab, 0, out);
+      const float m3 = run<3>(grid, threads, idx, n, tab, 0, out);
+      printf("SMs=%3d threads=%4d : nc %7.2f G/s | nc.no_allocate %7.2f G/s | cg %7.2f G/s | nc.v4(16B) %7.2f G/s  [per SM per clk @1.965GHz: %.3f %.3f %.3f %.3f]\n",
+             use, threads, n / m0 / 1e6, n / m1 / 1e6, n / m2 / 1e6, n / m3 / 1e6, n / m0 / 1e6 / use / 1.965,
+             n / m1 / 1e6 / use / 1.965, n / m2 / 1e6 / use / 1.965, n / m3 / 1e6 / use / 1.965);
+    }
+  }
+  printf("D: fraction of gathers served from a shared-memory hot window (1 CTA of 1024 threads per SM)\n");
+  for (int hot_words : {8192, 32768, 49152}) {
+    for (int pct : {0, 25, 50, 75}) {
+      // indices < hot_words with probability pct%, else uniform over the table
+      make_idx<<<(int)((n + 255) / 256), 256>>>(idx, n, table);
+      CK(cudaDeviceSynchronize());
+      // rewrite in place on the device: cheap second kernel
+      make_hot<<<(int)((n + 255) / 256), 256>>>(idx, n, hot_words, pct);
+      CK(cudaDeviceSynchronize());
+      const float m4 = run<4>(sms, 1024, idx, n, tab, hot_words, out);
+      const float m1 = run<1>(sms * 2, 1024, idx, n, tab, 0, out);
+      printf("hot=%6d words (%3d KB) hit=%2d%% : smem+global %7.2f G/s | all-global(no_allocate) %7.2f G/s\n", hot_words,
+             hot_words * 4 / 1024, pct, n / m4 / 1e6, n / m1 / 1e6);
+    }
+  }
+  return 0;
+}

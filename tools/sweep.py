@@ -66,6 +66,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/sweep.json")
     ap.add_argument("--tiles", default="896,1792,2816,3584")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--adaptive", default="2048,1024,4096", help="';'-separated B,T,CH triples")
     args = ap.parse_args()
     torch.cuda.init()
     peak = peak_gbs()
@@ -91,14 +92,16 @@ def main():
         x = torch.rand(spec.cols, device="cuda", generator=g) + 0.5
         b = torch.rand(spec.rows, device="cuda", generator=g)
         y = torch.empty(spec.rows, device="cuda")
-        variants = [("adapt", capi.KERNEL_ADAPTIVE, 0, "")]
+        variants = [("adapt", capi.KERNEL_ADAPTIVE, 0, "A" + a) for a in args.adaptive.split(";") if a]
         variants += [("merge", capi.KERNEL_MERGE, 0, t) for t in args.tiles.split(",") if t]
         variants += [("vector", capi.KERNEL_CSR_VECTOR, l, "") for l in (2, 4, 8, 16, 32)]
         variants += [("scalar", capi.KERNEL_CSR_SCALAR, 0, "")]
         for kname, k, lanes, tile in variants:
             if kname in ("vector", "scalar") and info["max_row_nnz"] > 50000 and lanes != 32:
                 continue  # a 1M-nnz row on one thread / a narrow sub-warp would run for seconds
-            if tile:
+            if tile.startswith("A"):
+                os.environ["HISPMV_ADAPTIVE"] = tile[1:]
+            elif tile:
                 os.environ["HISPMV_MERGE_TILE"] = tile
             try:
                 eng.force_kernel(idx, k, lanes)
@@ -111,7 +114,7 @@ def main():
             rec = dict(config=spec.name, kernel=kname, lanes=lanes, tile=tile, ms_med=med, ms_min=mn, gbs=gbs,
                        frac=gbs / peak, gflops=2 * (info["nnz"] + spec.rows) / (med * 1e-3) / 1e9, err=err)
             results.append(rec)
-            print(f"{spec.name:14s} {kname:6s} lanes={lanes:2d} tile={tile:5s} med={med:8.4f}ms min={mn:8.4f}ms "
+            print(f"{spec.name:14s} {kname:6s} lanes={lanes:2d} tile={tile:16s} med={med:8.4f}ms min={mn:8.4f}ms "
                   f"{gbs:8.1f} GB/s frac={gbs/peak:5.3f} err={err:.2e}", flush=True)
         eng.close()
         os.environ.pop("HISPMV_MERGE_TILE", None)

@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libhispmv_cuda.so")
 HIST_BINS = 33
 
 OK, FULL, ERR_ARG, ERR_INDEX, ERR_CUDA, ERR_STATE, ERR_IO = 0, -1, -2, -3, -4, -5, -6
-KERNEL_AUTO, KERNEL_CSR_SCALAR, KERNEL_CSR_VECTOR, KERNEL_MERGE, KERNEL_GEMV, KERNEL_EMPTY, KERNEL_ADAPTIVE = 0, 1, 2, 3, 4, 5, 6
-KERNEL_NAMES = {0: "auto", 1: "csr_scalar", 2: "csr_vector", 3: "merge", 4: "gemv", 5: "empty", 6: "adaptive"}
+KERNEL_AUTO, KERNEL_CSR_SCALAR, KERNEL_CSR_VECTOR, KERNEL_MERGE, KERNEL_GEMV, KERNEL_EMPTY, KERNEL_ADAPTIVE, KERNEL_ROWSTAGE = 0, 1, 2, 3, 4, 5, 6, 7
+KERNEL_NAMES = {0: "auto", 1: "csr_scalar", 2: "csr_vector", 3: "merge", 4: "gemv", 5: "empty", 6: "adaptive", 7: "rowstage"}
 FLAG_DENSE_OVERLAY, FLAG_ROW_DIST_NET = 1, 2
 SYNTH_POWERLAW, SYNTH_UNIFORM, SYNTH_STENCIL27 = 1, 2, 3
 
@@ -27,7 +27,8 @@ class MatrixInfo(C.Structure):
         ("nnz", C.c_int64), ("is_dense", C.c_int32), ("kernel", C.c_int32), ("vector_lanes", C.c_int32),
         ("tile_items", C.c_int32), ("num_tiles", C.c_int64), ("num_split_rows", C.c_int64),
         ("max_row_nnz", C.c_int32), ("empty_rows", C.c_int32), ("hist", C.c_int64 * HIST_BINS),
-        ("device_bytes", C.c_int64),
+        ("device_bytes", C.c_int64), ("probe_near", C.c_int64), ("probe_cmp", C.c_int64),
+        ("x_window_cols", C.c_int32), ("long_threshold", C.c_int32), ("chunk_nnz", C.c_int32),
     ]
 
 

@@ -1,0 +1,553 @@
+// Tile kernels for sm_100a: y = alpha * A x + beta * bias over the row-aligned, nnz-balanced tiles of an
+// AdaptivePlan (partition.cu: adaptive_tiles_device).  What they replace in the reference (semantics only):
+//   ComputeAB / PreAccumulator   val * x[col], adder chain          automation_tool/assets/base_functions.cpp:228-327
+//   ADD / SWB / SSW              shared-row partial sums + routing   base_functions.cpp:356-436
+//   AccumBuffer / Compute_C      y_Ax[row] += ..., alpha/beta        base_functions.cpp:475-488, 535
+//   balanceWorkload / prepareTile (the balanced schedule)            common/src/spmv-helper.cpp:265-347, 517-638
+//
+// Two measured facts shape them (tools/gather_bench.cu, tools/dsmem_bench.cu):
+//   * an SM can send only ~0.95 L1-miss requests per clock to L2, whatever their size (4 or 16 bytes), whether or not
+//     they allocate in L1; a gather instruction costs one request per distinct line its 32 lanes touch.  On
+//     gather-heavy matrices this, not HBM, is the ceiling, so lanes are mapped to nonzeros in the order that makes them
+//     share lines, and everything that can be served on-chip is;
+//   * shared-memory hits are nearly free next to that (275 G gathers/s become 275 / (1 - hit rate)), while
+//     distributed shared memory across a cluster is slower than L2 for 4-byte gathers (51-184 G/s) and is not used.
+//
+// Tiles (TileDesc, 32 bytes, built once per plan so that a tile costs one metadata load instead of a chain of four):
+//   STREAM  consecutive rows, each shorter than the long threshold, about stream_items row ends + nonzeros
+//   LONG    one chunk (<= chunk_nnz nonzeros) of a row at or above the threshold; a row with several chunks is
+//           "split": every chunk drops its partial sum in carry[tile], the chunk that arrives last at the row's
+//           counter adds the partials in chunk order and writes y -- one launch, no atomics on y, bit-reproducible.
+//
+// Kernels:
+//   spmv_adaptive_kernel             nnz-major, one CTA per tile (small matrices, no usable x window)
+//   spmv_adaptive_persistent_kernel  nnz-major, one or two resident CTAs per SM, x[0, hot) in shared memory,
+//                                    tiles pulled from a global counter with metadata / L2 prefetch one tile ahead
+//   spmv_rowstage_kernel             row-major behind a TMA-staged col/val stream (banded / stencil / FEM rows)
+// nnz-major: lane l of a warp takes nonzero base+l -- 128-byte coalesced col/val loads, and the 32 gathers of one
+//   instruction cover consecutive nonzeros, which are column-sorted inside a row and therefore share lines; products
+//   go to shared memory and each warp then reduces a slice of the tile's rows (one lane per short row, 8 lanes or the
+//   whole warp for longer ones).
+// row-major: LANES lanes walk each row, so the gathers of one instruction cover the same position of 32/LANES
+//   consecutive rows -- on banded matrices consecutive columns, i.e. one or two lines instead of up to 32.
+#include <limits.h>
+
+#include <algorithm>
+
+#include "device_utils.cuh"
+#include "internal.h"
+
+namespace hispmv {
+
+namespace {
+
+constexpr int kGroup = 256;  // threads that cooperate on one tile
+constexpr int kGroupWarps = kGroup / 32;
+constexpr int kSerialRow = 8;   // rows up to this many nonzeros are summed by one lane, longer ones by the warp
+
+// ---- x gathers ------------------------------------------------------------------------------------------------
+template <bool SPLIT>
+struct GatherL1 {  // SPLIT: columns below `hot` are pinned in L1 and the rest skips L1 allocation; else keep every line
+  const float* x;
+  int hot;
+  uint64_t pk;
+  __device__ __forceinline__ float operator()(int c) const {
+#ifdef HISPMV_DIAG
+    if (hot == -1) return 1.0f;                                    // diagnostics: no gathers at all
+    if (hot <= -2) return c < -hot ? 1.0f : ld_x_keep(x + c, pk);  // diagnostics: no gathers below -hot
+#endif
+    if (SPLIT) return ld_x_split(x, c, hot, pk);
+    return ld_x_keep(x + c, pk);
+  }
+};
+struct GatherWindow {  // columns below `hot` live in shared memory
+  const float* x;
+  const float* s_x;
+  int hot;
+  uint64_t pk;
+  __device__ __forceinline__ float operator()(int c) const { return c < hot ? s_x[c] : ld_x_bypass(x + c, pk); }
+};
+
+// ---- products of the nonzeros [n0, n1): lane-consecutive, four independent (col, val, x) triples per thread ----
+// OUT(i, p) receives product p of nonzero i.  Threads whose four slots are all inside [n0, n1) take a path without
+// per-slot predicates (instruction issue, not memory, was the floor of the first version of this loop).
+template <class G, class OUT>
+__device__ __forceinline__ void stream_products(const CsrDev& A, const G& gx, int n0, int n1, int gt, uint64_t ps,
+                                                OUT out) {
+  for (int i0 = (n0 & ~31) + gt; i0 < n1; i0 += 4 * kGroup) {  // every warp load is one aligned 128-byte line
+    const int32_t* pc = A.col + i0;
+    const float* pv = A.val + i0;
+    if (i0 >= n0 && i0 + 3 * kGroup < n1) {
+      int c[4];
+      float v[4], xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        c[u] = ld_stream_i1(pc + u * kGroup, ps);
+        v[u] = ld_stream_f1(pv + u * kGroup, ps);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) xv[u] = gx(c[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) out(i0 + u * kGroup, v[u] * xv[u]);
+    } else {  // first / last slots of the tile: same three phases, predicated per slot
+      int c[4];
+      float v[4], xv[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * kGroup;
+        ok[u] = (i >= n0) & (i < n1);
+        c[u] = 0;
+        v[u] = 0.0f;
+        if (ok[u]) {
+          c[u] = ld_stream_i1(pc + u * kGroup, ps);
+          v[u] = ld_stream_f1(pv + u * kGroup, ps);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        xv[u] = 0.0f;
+        if (ok[u]) xv[u] = gx(c[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) out(i0 + u * kGroup, v[u] * xv[u]);
+    }
+  }
+}
+
+// ---- rows of a STREAM tile out of the product buffer: warp gw owns rows [beg, end) of the tile -------------------
+// (b0, e0) are the extents of row beg+lane relative to s_prod[0], loaded by the caller before the barrier that
+// publishes the products.  One lane sums a row of up to kSerialRow products; longer rows are taken one at a time by
+// the whole warp.
+__device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int n0, int beg, int end, int b0, int e0,
+                                                   const float* s_prod, int lane, float* __restrict__ y,
+                                                   const Epilogue& ep) {
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    int b = b0, e = e0;
+    if (base != beg) {
+      b = e = 0;
+      if (i < end) {
+        b = A.row_ptr[r0 + i] - n0;
+        e = A.row_ptr[r0 + i + 1] - n0;
+      }
+    }
+    const int len = e - b;
+    float s = 0.0f;
+    if (len <= kSerialRow) {
+#pragma unroll
+      for (int k = 0; k < kSerialRow; ++k)
+        if (k < len) s += s_prod[b + k];
+    }
+    unsigned big = __ballot_sync(kFullMask, len > kSerialRow);
+    while (big) {
+      const int j = __ffs(big) - 1;
+      big &= big - 1;
+      const int bj = __shfl_sync(kFullMask, b, j), ej = __shfl_sync(kFullMask, e, j);
+      float p = 0.0f;
+      for (int k = bj + lane; k < ej; k += 32) p += s_prod[k];
+      p = warp_sum(p);
+      if (lane == j) s = p;
+    }
+    if (i < end) y[r0 + i] = finish(s, ep.alpha, ep.beta, ep.bias, r0 + i, ep.relu);
+  }
+}
+
+// ---- the end of a LONG tile: warp 0 of the group holds the chunk's total in every lane ---------------------------
+__device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDesc& d, int64_t t, float total, int lane,
+                                             float* __restrict__ y, const Epilogue& ep) {
+  if (d.nchunks == 1) {
+    if (lane == 0) y[d.r0] = finish(total, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu);
+    return;
+  }
+  const int64_t first = t - d.chunk;  // tile id of this row's chunk 0
+  int last = 0;
+  if (lane == 0) {
+    P.carry[t] = total;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&P.counter[first], 1u);
+    last = (prev == (unsigned int)(d.nchunks - 1));
+  }
+  last = __shfl_sync(kFullMask, last, 0);
+  if (!last) return;
+  __threadfence();
+  float s = 0.0f;
+  for (int k = lane; k < d.nchunks; k += 32) s += __ldcg(P.carry + first + k);
+  s = warp_sum(s);
+  if (lane == 0) {
+    y[d.r0] = finish(s, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu);
+    P.counter[first] = 0;  // ready for the next run / graph replay
+  }
+}
+
+// Wait for the tile's bulk copies: one thread polls the mbarrier (try_wait suspends it in hardware), the rest of the
+// CTA parks on the hardware barrier.  256 threads polling the same mbarrier flood the MIO queue (measured: the
+// kernel ran 1.6x slower with mio_throttle as its top stall).
+__device__ __forceinline__ void tile_staged(uint64_t* bar, int cnt) {
+  if (threadIdx.x == 0 && cnt > 0) mbar_wait(bar, 0);
+  __syncthreads();
+}
+
+__device__ __forceinline__ TileDesc load_desc(const TileDesc* p) {
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
+  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  TileDesc d;
+  d.r0 = a.x;
+  d.r1 = a.y;
+  d.n0 = a.z;
+  d.n1 = a.w;
+  d.chunk = b.x;
+  d.nchunks = b.y;
+  d.tile = b.z;
+  d.pad = b.w;
+  return d;
+}
+
+// ================================================================================================================
+// one CTA per tile
+// ================================================================================================================
+template <int CAP, bool SPLIT>  // CAP >= stream_items + long_threshold: products a STREAM tile may hold
+__global__ void __launch_bounds__(kGroup, 8)
+    spmv_adaptive_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
+  __shared__ float s_prod[CAP];
+  __shared__ float s_red[kGroupWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t = blockIdx.x;
+  const TileDesc d = load_desc(P.desc + t);
+  const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
+  const GatherL1<SPLIT> gx{x, P.hot_cols, pk};
+  if (d.chunk >= 0) {
+    float acc = 0.0f;
+    stream_products(A, gx, d.n0, d.n1, tid, ps, [&](int, float p) { acc += p; });
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (warp != 0) return;
+    float total = lane < kGroupWarps ? s_red[lane] : 0.0f;
+    total = warp_sum(total);
+    finish_chunk(P, d, t, total, lane, y, ep);
+    return;
+  }
+  const int n0 = d.n0;
+  // the extents of this lane's first row are requested before the stream so that their DRAM round trip overlaps it
+  const int trows = d.r1 - d.r0;
+  const int rpw = (trows + kGroupWarps - 1) / kGroupWarps;
+  const int beg = warp * rpw, end = min(trows, beg + rpw);
+  int b0 = 0, e0 = 0;
+  if (beg + lane < end) {
+    b0 = A.row_ptr[d.r0 + beg + lane];
+    e0 = A.row_ptr[d.r0 + beg + lane + 1];
+  }
+  stream_products(A, gx, n0, d.n1, tid, ps, [&](int i, float p) { s_prod[i - n0] = p; });
+  __syncthreads();
+  rows_from_products(A, d.r0, n0, beg, end, b0 - n0, e0 - n0, s_prod, lane, y, ep);
+}
+
+// ================================================================================================================
+// persistent, x window in shared memory
+// ================================================================================================================
+constexpr int kPsGroups = 4;
+
+template <int CAP>
+struct PsGroupSmem {
+  float prod[CAP];
+  float red[kGroupWarps];
+  __align__(16) TileDesc ring[3];  // descriptors of the current tile and the two after it
+};
+
+// named barrier g+1 over the kGroup threads of group g; immediate ids so that ptxas reserves only 5 of the SM's 16
+// hardware barriers per CTA (a register id makes it reserve all 16, which caps residency at one CTA per SM)
+__device__ __forceinline__ void group_sync(int g) {
+  switch (g) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(kGroup) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(kGroup) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"n"(kGroup) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"n"(kGroup) : "memory"); break;
+  }
+}
+static_assert(kPsGroups == 4, "group_sync names four barriers");
+
+__device__ __forceinline__ void prefetch_l2(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// descriptor of tile t -> shared memory, asynchronously (two 16-byte cp.async); past the end: an end marker
+__device__ __forceinline__ void desc_async(const AdaptivePlan& P, unsigned int t, TileDesc* dst) {
+  if ((int64_t)t < P.num_tiles) {
+    const uint32_t d = smem_u32(dst);
+    const TileDesc* src = P.desc + t;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d + 16), "l"(reinterpret_cast<const char*>(src) + 16)
+                 : "memory");
+  } else {
+    dst->tile = -1;
+    dst->chunk = -1;
+    dst->n0 = dst->n1 = 0;
+  }
+}
+__device__ __forceinline__ void desc_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int CAP, int MINBLOCKS>
+__global__ void __launch_bounds__(kGroup* kPsGroups, MINBLOCKS)
+    spmv_adaptive_persistent_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y,
+                                    Epilogue ep, int total_groups) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_x = reinterpret_cast<float*>(s_raw);
+  const int hot = P.hot_cols;
+  const int tid = threadIdx.x, g = tid / kGroup, gt = tid % kGroup, lane = tid & 31, gw = gt >> 5;
+  PsGroupSmem<CAP>* gs = reinterpret_cast<PsGroupSmem<CAP>*>(s_raw + (((size_t)hot * 4 + 15) & ~(size_t)15)) + g;
+  const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
+  const GatherWindow gx{x, s_x, hot, pk};
+
+  // Thread 0 of each group runs the tile pipeline, one step per processed tile k:
+  //   tile index k+3   atomicAdd on the global counter (result used one step later)
+  //   descriptor k+2   cp.async into the group's ring (lands during tile k)
+  //   stream of k+1    cp.async.bulk.prefetch.L2 of its col/val range, so the loads of the next tile hit L2
+  unsigned int t_ahead = 0;
+  if (gt == 0) {
+    const unsigned int t0 = atomicAdd(P.sched, 1u);
+    const unsigned int t1 = atomicAdd(P.sched, 1u);
+    t_ahead = atomicAdd(P.sched, 1u);
+    desc_async(P, t0, &gs->ring[0]);
+    desc_async(P, t1, &gs->ring[1]);
+  }
+  for (int i = tid; i < hot; i += kGroup * kPsGroups) s_x[i] = ld_x_bypass(x + i, pk);
+  __syncthreads();
+
+  for (int k = 0;; ++k) {
+    if (gt == 0) desc_wait();
+    group_sync(g);
+    const TileDesc d = gs->ring[k % 3];
+    if (d.tile < 0) break;
+    if (gt == 0) {
+      const TileDesc* dn = &gs->ring[(k + 1) % 3];
+      if (dn->tile >= 0 && dn->n1 > dn->n0) {
+        const int a0 = dn->n0 & ~3;
+        const uint32_t bytes = (uint32_t)(((dn->n1 + 3) & ~3) - a0) * 4u;
+        prefetch_l2(A.col + a0, bytes);
+        prefetch_l2(A.val + a0, bytes);
+      }
+      desc_async(P, t_ahead, &gs->ring[(k + 2) % 3]);
+      t_ahead = atomicAdd(P.sched, 1u);
+    }
+    const int64_t t = d.tile;
+    if (d.chunk >= 0) {
+      float acc = 0.0f;
+      stream_products(A, gx, d.n0, d.n1, gt, ps, [&](int, float p) { acc += p; });
+      acc = warp_sum(acc);
+      if (lane == 0) gs->red[gw] = acc;
+      group_sync(g);
+      if (gw == 0) {
+        float total = lane < kGroupWarps ? gs->red[lane] : 0.0f;
+        total = warp_sum(total);
+        finish_chunk(P, d, t, total, lane, y, ep);
+      }
+      continue;
+    }
+    const int n0 = d.n0;
+    float* s_prod = gs->prod;
+    stream_products(A, gx, n0, d.n1, gt, ps, [&](int i, float p) { s_prod[i - n0] = p; });
+    const int trows = d.r1 - d.r0;
+    const int rpw = (trows + kGroupWarps - 1) / kGroupWarps;
+    const int beg = gw * rpw, end = min(trows, beg + rpw);
+    int b0 = 0, e0 = 0;
+    if (beg + lane < end) {
+      b0 = A.row_ptr[d.r0 + beg + lane] - n0;
+      e0 = A.row_ptr[d.r0 + beg + lane + 1] - n0;
+    }
+    group_sync(g);
+    rows_from_products(A, d.r0, n0, beg, end, b0, e0, s_prod, lane, y, ep);
+  }
+  // the last group to run dry re-arms the tile counter for the next launch / graph replay
+  if (gt == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(P.sched + 1, 1u + (t_ahead == 0xffffffffu));  // t_ahead has landed
+    if (prev == (unsigned int)(total_groups - 1)) {
+      P.sched[0] = 0;
+      P.sched[1] = 0;
+    }
+  }
+}
+
+// ================================================================================================================
+// row-major behind a TMA-staged stream.  Dynamic shared memory: col[CAP + 8] | val[CAP + 8].
+// ================================================================================================================
+template <int CAP, int LANES>
+__global__ void __launch_bounds__(kGroup)
+    spmv_rowstage_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  int* s_col = reinterpret_cast<int*>(s_raw);
+  float* s_val = reinterpret_cast<float*>(s_raw) + (CAP + 8);
+  __shared__ float s_red[kGroupWarps];
+  __shared__ __align__(8) uint64_t s_bar;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t = blockIdx.x;
+  const TileDesc d = load_desc(P.desc + t);
+  const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
+  const GatherL1<false> gx{x, P.hot_cols, pk};  // banded matrices reuse every gathered line a few rows later
+  if (d.chunk >= 0) {
+    float acc = 0.0f;
+    stream_products(A, gx, d.n0, d.n1, tid, ps, [&](int, float p) { acc += p; });
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (warp != 0) return;
+    float total = lane < kGroupWarps ? s_red[lane] : 0.0f;
+    total = warp_sum(total);
+    finish_chunk(P, d, t, total, lane, y, ep);
+    return;
+  }
+  const int r0 = d.r0, trows = d.r1 - d.r0;
+  const int a0 = d.n0 & ~3;                 // 16-byte aligned window [a0, a1) around the tile's nonzeros;
+  const int cnt = ((d.n1 + 3) & ~3) - a0;   // col/val are zero-padded past nnz, so the tail is readable
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (tid == 0 && cnt > 0) {
+    mbar_expect_tx(&s_bar, (uint32_t)cnt * 8u);
+    bulk_g2s_hint(s_col, A.col + a0, (uint32_t)cnt * 4u, &s_bar, ps);
+    bulk_g2s_hint(s_val, A.val + a0, (uint32_t)cnt * 4u, &s_bar, ps);
+  }
+  constexpr int R = kGroup / LANES;  // rows per pass
+  const int sub = tid % LANES, g = tid / LANES;
+  // row extents of the first pass are fetched while the bulk copies fly
+  int b = 0, e = 0;
+  if (g < trows) {
+    b = A.row_ptr[r0 + g] - a0;
+    e = A.row_ptr[r0 + g + 1] - a0;
+  }
+  tile_staged(&s_bar, cnt);
+  for (int rb = 0; rb < trows; rb += R) {
+    const int i = rb + g;
+    if (rb > 0) {
+      b = e = 0;
+      if (i < trows) {
+        b = A.row_ptr[r0 + i] - a0;
+        e = A.row_ptr[r0 + i + 1] - a0;
+      }
+    }
+    float acc0 = 0.0f, acc1 = 0.0f;
+    int k = b + sub;
+    for (; k + LANES < e; k += 2 * LANES) {
+      const int ca = s_col[k], cb = s_col[k + LANES];
+      const float xa = gx(ca), xb = gx(cb);
+      acc0 = fmaf(s_val[k], xa, acc0);
+      acc1 = fmaf(s_val[k + LANES], xb, acc1);
+    }
+    if (k < e) acc0 = fmaf(s_val[k], gx(s_col[k]), acc0);
+    const float acc = subwarp_sum<LANES>(acc0 + acc1);
+    if (sub == 0 && i < trows) y[r0 + i] = finish(acc, ep.alpha, ep.beta, ep.bias, r0 + i, ep.relu);
+  }
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------------------------
+template <int CAP, int MINBLOCKS>
+int launch_persistent_inst(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
+                           size_t smem, cudaStream_t s) {
+  auto k = spmv_adaptive_persistent_kernel<CAP, MINBLOCKS>;
+  HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t grid = (P.num_tiles + kPsGroups - 1) / kPsGroups;
+  if (grid > (int64_t)sm_count * MINBLOCKS) grid = (int64_t)sm_count * MINBLOCKS;
+  k<<<(int)grid, kGroup * kPsGroups, smem, s>>>(A, P, x, y, ep, (int)grid * kPsGroups);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+template <int CAP>
+int launch_persistent_cap(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
+                          cudaStream_t s) {
+  const size_t smem = (((size_t)P.hot_cols * 4 + 15) & ~(size_t)15) + sizeof(PsGroupSmem<CAP>) * kPsGroups;
+  // small windows leave room for two resident CTAs per SM (eight tile groups instead of four)
+  if (smem * 2 <= (size_t)225 * 1024) return launch_persistent_inst<CAP, 2>(A, P, x, y, ep, sm_count, smem, s);
+  if (smem <= (size_t)226 * 1024) return launch_persistent_inst<CAP, 1>(A, P, x, y, ep, sm_count, smem, s);
+  set_error("adaptive_persistent: x window does not fit in shared memory");
+  return HISPMV_ERR_ARG;
+}
+
+template <int CAP, int LANES>
+int launch_rowstage_inst(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
+                         cudaStream_t s) {
+  auto k = spmv_rowstage_kernel<CAP, LANES>;
+  constexpr int smem = (CAP + 8) * 8;
+  HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  k<<<(int)P.num_tiles, kGroup, smem, s>>>(A, P, x, y, ep);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+template <int CAP>
+int launch_rowstage_cap(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
+                        cudaStream_t s) {
+  switch (lanes) {
+    case 1: return launch_rowstage_inst<CAP, 1>(A, P, x, y, ep, s);
+    case 2: return launch_rowstage_inst<CAP, 2>(A, P, x, y, ep, s);
+    case 4: return launch_rowstage_inst<CAP, 4>(A, P, x, y, ep, s);
+    case 8: return launch_rowstage_inst<CAP, 8>(A, P, x, y, ep, s);
+    case 16: return launch_rowstage_inst<CAP, 16>(A, P, x, y, ep, s);
+    case 32: return launch_rowstage_inst<CAP, 32>(A, P, x, y, ep, s);
+  }
+  set_error("rowstage: lanes must be 1,2,4,8,16 or 32");
+  return HISPMV_ERR_ARG;
+}
+
+int check_plan(const AdaptivePlan& P, int max_cap, const char* who) {
+  if (P.num_tiles > INT_MAX) {
+    set_error(std::string(who) + ": too many tiles");
+    return HISPMV_ERR_ARG;
+  }
+  if (P.stream_items + P.long_threshold > max_cap || P.chunk_nnz <= 0 || !P.desc) {
+    set_error(std::string(who) + ": plan exceeds the compiled shared-memory capacity");
+    return HISPMV_ERR_ARG;
+  }
+  return HISPMV_OK;
+}
+
+}  // namespace
+
+int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s) {
+  if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
+  int st = check_plan(P, 4096, "adaptive");
+  if (st != HISPMV_OK) return st;
+  const int need = P.stream_items + P.long_threshold;
+  const int grid = (int)P.num_tiles;
+  const bool split = P.hot_cols != 0x7fffffff;
+  if (need <= 2048) {
+    if (split) spmv_adaptive_kernel<2048, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    else spmv_adaptive_kernel<2048, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+  } else if (need <= 3072) {
+    if (split) spmv_adaptive_kernel<3072, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    else spmv_adaptive_kernel<3072, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+  } else {
+    if (split) spmv_adaptive_kernel<4096, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    else spmv_adaptive_kernel<4096, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+  }
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
+                               int sm_count, cudaStream_t s) {
+  if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
+  int st = check_plan(P, 4096, "adaptive_persistent");
+  if (st != HISPMV_OK) return st;
+  if (P.hot_cols < 0 || P.hot_cols > A.cols || !P.sched) {
+    set_error("adaptive_persistent: bad x window");
+    return HISPMV_ERR_ARG;
+  }
+  const int need = P.stream_items + P.long_threshold;
+  if (need <= 2048) return launch_persistent_cap<2048>(A, P, x, y, ep, sm_count, s);
+  if (need <= 3072) return launch_persistent_cap<3072>(A, P, x, y, ep, sm_count, s);
+  return launch_persistent_cap<4096>(A, P, x, y, ep, sm_count, s);
+}
+
+int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
+                    cudaStream_t s) {
+  if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
+  int st = check_plan(P, kRowstageMaxCap, "rowstage");
+  if (st != HISPMV_OK) return st;
+  const int need = P.stream_items + P.long_threshold;
+  if (need <= 2048) return launch_rowstage_cap<2048>(A, P, lanes, x, y, ep, s);
+  if (need <= 4096) return launch_rowstage_cap<4096>(A, P, lanes, x, y, ep, s);
+  if (need <= 6144) return launch_rowstage_cap<6144>(A, P, lanes, x, y, ep, s);
+  return launch_rowstage_cap<8192>(A, P, lanes, x, y, ep, s);
+}
+
+}  // namespace hispmv

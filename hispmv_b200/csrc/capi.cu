@@ -48,7 +48,11 @@ struct Matrix {
   int64_t num_split = 0;
   int32_t* d_tile_chunk = nullptr;      // ADAPTIVE
   unsigned int* d_counter = nullptr;    // ADAPTIVE (two lanes, like d_carry)
+  TileDesc* d_desc = nullptr;           // ADAPTIVE / ROWSTAGE: resolved tile records
   int32_t long_threshold = 0, chunk_nnz = 0;
+  int32_t hot_cols = 0x7fffffff;        // ADAPTIVE / ROWSTAGE: split L1 policy threshold for x gathers
+  bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
+  ColProbe probe{};                     // column-locality probe (selector input)
   // dense
   float* d_a = nullptr;
   int64_t ld = 0;
@@ -61,6 +65,8 @@ struct Matrix {
     cudaFree(d_split_rows);
     cudaFree(d_tile_chunk);
     cudaFree(d_counter);
+    cudaFree(d_desc);
+    d_desc = nullptr;
     d_tile_chunk = nullptr;
     d_counter = nullptr;
     d_tile_row = nullptr;
@@ -74,7 +80,7 @@ struct Matrix {
   int64_t device_bytes() const {
     if (dense) return (int64_t)local_rows() * ld * 4;
     int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
-    if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4;
+    if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
     return b;
   }
   ~Matrix() {
@@ -157,14 +163,16 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
   m->free_plan();
   int st = row_stats_device(m->d_row_ptr, m->local_rows(), &m->stats, c->stream);
   if (st != HISPMV_OK) return st;
+  st = col_probe_device(m->d_row_ptr, m->d_col, m->local_rows(), &m->probe, c->stream);
+  if (st != HISPMV_OK) return st;
   if (!m->forced) {
-    select_kernel(m->stats, m->cols, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0, &m->kernel, &m->lanes);
+    select_kernel(m->stats, m->probe, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0, &m->kernel, &m->lanes);
   } else if (m->nnz == 0 || m->local_rows() == 0) {
     m->kernel = HISPMV_KERNEL_EMPTY;
   }
-  if (m->kernel == HISPMV_KERNEL_CSR_VECTOR && m->lanes == 0) {
+  if (m->kernel == HISPMV_KERNEL_CSR_VECTOR && m->lanes < 2) {
     int k, l;
-    select_kernel(m->stats, m->cols, 0, &k, &l);
+    select_kernel(m->stats, m->probe, 0, &k, &l);
     m->lanes = l ? l : 2;
   }
   if (m->kernel == HISPMV_KERNEL_MERGE) {
@@ -181,26 +189,59 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
                            &m->d_split_rows, &m->num_split, c->stream);
     if (st != HISPMV_OK) return st;
   }
-  if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
-    m->tile_items = kAdaptiveStreamItems;
-    m->long_threshold = kAdaptiveLongThreshold;
-    m->chunk_nnz = kAdaptiveChunkNnz;
-    if (const char* e = getenv("HISPMV_ADAPTIVE")) {  // "B,T,CH" (development sweeps)
-      int b = 0, t = 0, ch = 0;
-      if (sscanf(e, "%d,%d,%d", &b, &t, &ch) == 3 && b >= 256 && t >= 16 && b + t <= 4096 && ch >= 1024) {
-        m->tile_items = b;
-        m->long_threshold = t;
-        m->chunk_nnz = ch;
+  if (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) {
+    if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
+      m->tile_items = kAdaptiveStreamItems;
+      m->long_threshold = kAdaptiveLongThreshold;
+      m->chunk_nnz = kAdaptiveChunkNnz;
+      if (const char* e = getenv("HISPMV_ADAPTIVE")) {  // "B,T,CH" (development sweeps)
+        int b = 0, t = 0, ch = 0;
+        if (sscanf(e, "%d,%d,%d", &b, &t, &ch) == 3 && b >= 256 && t >= 16 && b + t <= 4096 && ch >= 1024 &&
+            ch <= 4096) {
+          m->tile_items = b;
+          m->long_threshold = t;
+          m->chunk_nnz = ch;
+        }
       }
+    } else {
+      rowstage_params(m->stats, m->lanes, &m->lanes, &m->tile_items, &m->long_threshold, &m->chunk_nnz);
+      if (const char* e = getenv("HISPMV_ROWSTAGE")) {  // "LANES,B,T,CH" (development sweeps)
+        int l = 0, b = 0, t = 0, ch = 0;
+        if (sscanf(e, "%d,%d,%d,%d", &l, &b, &t, &ch) == 4 && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && b >= 256 &&
+            t >= 16 && b + t <= kRowstageMaxCap && ch >= 1024) {
+          m->lanes = l;
+          m->tile_items = b;
+          m->long_threshold = t;
+          m->chunk_nnz = ch;
+        }
+      }
+    }
+    m->hot_cols = 0x7fffffff;
+    m->persistent = false;
+    if (const char* e = getenv("HISPMV_PERSIST")) {  // research switch: the persistent x-window variant (never auto)
+      const int h = atoi(e);
+      if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
+        m->persistent = h > 0;
+        if (h > 0) m->hot_cols = std::min(std::min(h, m->cols), kPersistentMaxHot);
+        else if (m->hot_cols <= kPersistentMaxHot) m->hot_cols = 0x7fffffff;
+      }
+    }
+    if (const char* e = getenv("HISPMV_HOT")) {  // development sweeps: L1 split threshold of the non-persistent kernels
+      const int h = atoi(e);
+      if (h != 0 && !m->persistent) m->hot_cols = h;  // negative values: diagnostics (builds with -DHISPMV_DIAG)
     }
     st = adaptive_tiles_device(m->d_row_ptr, m->local_rows(), m->tile_items, m->long_threshold, m->chunk_nnz,
                                &m->num_tiles, &m->d_tile_row, &m->d_tile_chunk, &m->d_split_rows, &m->num_split,
                                c->stream);
     if (st != HISPMV_OK) return st;
+    st = tile_desc_device(m->d_row_ptr, m->d_tile_row, m->d_tile_chunk, m->num_tiles, m->chunk_nnz, &m->d_desc,
+                          c->stream);
+    if (st != HISPMV_OK) return st;
     const size_t n = (size_t)std::max<int64_t>(m->num_tiles, 1) * 2;
     HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, n * sizeof(float)));
-    HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, n * sizeof(unsigned int)));
-    HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, n * sizeof(unsigned int), c->stream));
+    // two lanes of arrival counters, then two lanes of 4 scheduler words for the persistent kernel
+    HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, (n + 8) * sizeof(unsigned int)));
+    HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, (n + 8) * sizeof(unsigned int), c->stream));
   }
   HISPMV_CUDA(cudaStreamSynchronize(c->stream));
   return HISPMV_OK;
@@ -409,7 +450,8 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.carry = m->d_carry + (size_t)lane * m->num_tiles;
       return launch_merge(A, P, d_x, d_y, ep, s);
     }
-    case HISPMV_KERNEL_ADAPTIVE: {
+    case HISPMV_KERNEL_ADAPTIVE:
+    case HISPMV_KERNEL_ROWSTAGE: {
       AdaptivePlan P;
       P.stream_items = m->tile_items;
       P.long_threshold = m->long_threshold;
@@ -417,8 +459,13 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.num_tiles = m->num_tiles;
       P.tile_row = m->d_tile_row;
       P.tile_chunk = m->d_tile_chunk;
+      P.desc = m->d_desc;
       P.carry = m->d_carry + (size_t)lane * m->num_tiles;
       P.counter = m->d_counter + (size_t)lane * m->num_tiles;
+      P.hot_cols = m->hot_cols;
+      P.sched = m->d_counter + (size_t)std::max<int64_t>(m->num_tiles, 1) * 2 + 4 * (size_t)lane;
+      if (m->kernel == HISPMV_KERNEL_ROWSTAGE) return launch_rowstage(A, P, m->lanes, d_x, d_y, ep, s);
+      if (m->persistent) return launch_adaptive_persistent(A, P, d_x, d_y, ep, c->sm_count, s);
       return launch_adaptive(A, P, d_x, d_y, ep, s);
     }
     default: set_error("run: matrix has no plan"); return HISPMV_ERR_STATE;
@@ -573,12 +620,12 @@ int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
     return HISPMV_ERR_ARG;
   }
   if (kernel != HISPMV_KERNEL_AUTO && kernel != HISPMV_KERNEL_CSR_SCALAR && kernel != HISPMV_KERNEL_CSR_VECTOR &&
-      kernel != HISPMV_KERNEL_MERGE && kernel != HISPMV_KERNEL_ADAPTIVE) {
+      kernel != HISPMV_KERNEL_MERGE && kernel != HISPMV_KERNEL_ADAPTIVE && kernel != HISPMV_KERNEL_ROWSTAGE) {
     set_error("force_kernel: unknown kernel");
     return HISPMV_ERR_ARG;
   }
-  if (lanes != 0 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) {
-    set_error("force_kernel: lanes must be 0,2,4,8,16,32");
+  if (lanes != 0 && lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) {
+    set_error("force_kernel: lanes must be 0,1,2,4,8,16,32");
     return HISPMV_ERR_ARG;
   }
   DeviceGuard g(c->device);
@@ -703,6 +750,11 @@ int hispmv_matrix_info_get(hispmv_ctx* c, int idx, hispmv_matrix_info* out) {
   if (!m->dense)
     for (int i = 0; i < HISPMV_HIST_BINS; ++i) out->hist[i] = m->stats.hist[i];
   out->device_bytes = m->device_bytes();
+  out->x_window_cols = (!m->dense && m->persistent) ? m->hot_cols : 0;
+  out->probe_near = m->dense ? 0 : m->probe.near;
+  out->probe_cmp = m->dense ? 0 : m->probe.cmp;
+  out->long_threshold = m->dense ? 0 : m->long_threshold;
+  out->chunk_nnz = m->dense ? 0 : m->chunk_nnz;
   return HISPMV_OK;
 }
 
@@ -731,7 +783,7 @@ int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_n
   if (tile_row) HISPMV_CUDA(cudaMemcpy(tile_row, m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
   if (tile_nnz && m->kernel == HISPMV_KERNEL_MERGE)
     HISPMV_CUDA(cudaMemcpy(tile_nnz, m->d_tile_nnz, (size_t)(m->num_tiles + 1) * 8, cudaMemcpyDeviceToHost));
-  if (tile_nnz && m->kernel == HISPMV_KERNEL_ADAPTIVE) {
+  if (tile_nnz && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE)) {
     // offset of each tile's first nonzero: row_ptr[tile_row] (+ chunk * chunk_nnz for LONG tiles)
     std::vector<int32_t> tr((size_t)m->num_tiles + 1), tc((size_t)std::max<int64_t>(m->num_tiles, 1));
     HISPMV_CUDA(cudaMemcpy(tr.data(), m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
@@ -749,7 +801,7 @@ int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_n
 int hispmv_plan_tile_chunks(hispmv_ctx* c, int idx, int32_t* chunk_out) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
-  if (m->kernel != HISPMV_KERNEL_ADAPTIVE || !m->d_tile_chunk) {
+  if ((m->kernel != HISPMV_KERNEL_ADAPTIVE && m->kernel != HISPMV_KERNEL_ROWSTAGE) || !m->d_tile_chunk) {
     set_error("plan_tile_chunks: matrix is not planned for the adaptive kernel");
     return HISPMV_ERR_STATE;
   }

@@ -44,13 +44,27 @@ struct MergePlan {
 //                (row ends + nonzeros; never more than stream_items + long_threshold)
 //   LONG tile    one chunk of at most chunk_nnz nonzeros of a row with >= long_threshold nonzeros; a row
 //                with several chunks is "split": its partial sums meet in carry[] (one slot per tile)
+// One tile of an AdaptivePlan, 32 bytes (two 128-bit loads).
+struct TileDesc {
+  int32_t r0, r1;      // rows [r0, r1) (LONG: the one row r0)
+  int32_t n0, n1;      // nonzeros [n0, n1) (LONG: the chunk)
+  int32_t chunk;       // -1 for a STREAM tile, else the chunk index of a LONG tile
+  int32_t nchunks;     // LONG: number of chunks of the row
+  int32_t tile;        // the tile's own index
+  int32_t pad;
+};
+
 struct AdaptivePlan {
   int32_t stream_items = 0, long_threshold = 0, chunk_nnz = 0;
   int64_t num_tiles = 0;
   const int32_t* tile_row = nullptr;    // num_tiles+1: first row of every tile, then `rows`
   const int32_t* tile_chunk = nullptr;  // num_tiles: -1 for STREAM tiles, chunk index for LONG tiles
+  const TileDesc* desc = nullptr;       // num_tiles: the same facts resolved against row_ptr, one record per tile
   float* carry = nullptr;               // num_tiles partial sums (LONG tiles of split rows)
   unsigned int* counter = nullptr;      // num_tiles arrival counters, indexed by a split row's first tile
+  int32_t hot_cols = 0x7fffffff;        // x[c] with c < hot_cols is kept in L1 (persistent kernel: in shared
+                                        // memory), the rest bypasses L1 allocation
+  unsigned int* sched = nullptr;        // persistent kernel: [0] next tile, [1] groups that ran dry
 };
 
 struct RowStats {
@@ -91,10 +105,26 @@ int adaptive_tiles_device(const int32_t* d_row_ptr, int32_t rows, int32_t stream
                           int32_t chunk_nnz, int64_t* num_tiles, int32_t** d_tile_row, int32_t** d_tile_chunk,
                           int32_t** d_split_rows, int64_t* num_split, cudaStream_t stream);
 
+// Column-locality probe: for up to kProbeSamples evenly spaced rows r, the first min(len(r), len(r-1), 32) entries of
+// rows r and r-1 are compared position by position; `near` counts pairs whose columns differ by at most 32 (same or
+// adjacent 128-byte line of x), `cmp` the pairs compared.  Banded / stencil / FEM matrices score near 1.
+struct ColProbe {
+  int64_t near = 0, cmp = 0;
+};
+constexpr int32_t kProbeSamples = 8192;
+int col_probe_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, ColProbe* out, cudaStream_t stream);
+
+// TileDesc records from tile_row / tile_chunk / row_ptr (one thread per tile); d_desc cudaMalloc'ed by the callee.
+int tile_desc_device(const int32_t* d_row_ptr, const int32_t* d_tile_row, const int32_t* d_tile_chunk,
+                     int64_t num_tiles, int32_t chunk_nnz, TileDesc** d_desc, cudaStream_t stream);
+
 // The runtime selector (pure host integer arithmetic over RowStats; restated in oracle/).
-void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* kernel, int* lanes);
+void select_kernel(const RowStats& st, const ColProbe& probe, int allow_split_rows, int* kernel, int* lanes);
 // tile_items the merge kernel instantiation uses for a matrix with these stats
 int merge_tile_items_for(const RowStats& st);
+// ROWSTAGE plan parameters from the row statistics (lanes_in = 0: choose lanes); restated in oracle/.
+void rowstage_params(const RowStats& st, int lanes_in, int* lanes, int32_t* stream_items, int32_t* long_threshold,
+                     int32_t* chunk_nnz);
 
 // ---- spmv.cu --------------------------------------------------------------------------------
 struct Epilogue {
@@ -106,7 +136,15 @@ int launch_csr_scalar(const CsrDev& A, const float* x, float* y, Epilogue ep, cu
 int launch_csr_vector(const CsrDev& A, int lanes, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_merge(const CsrDev& A, const MergePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
-constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdaptiveChunkNnz = 4096;
+constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdaptiveChunkNnz = 3072;
+// Persistent nnz-major kernel: one CTA per SM, x[0, hot_cols) held in shared memory, tiles pulled from P.sched.
+int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
+                               int sm_count, cudaStream_t s);
+constexpr int kPersistentMaxHot = 40960;  // floats of x the window may hold next to the four group buffers
+// Row-major STREAM tiles behind a TMA-staged stream (regular rows with column locality); `lanes` lanes per row.
+int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
+                    cudaStream_t s);
+constexpr int kRowstageMaxCap = 8192;
 int launch_empty(int32_t rows, float* y, Epilogue ep, cudaStream_t s);
 bool merge_tile_items_supported(int tile_items);
 

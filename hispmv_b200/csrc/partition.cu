@@ -192,6 +192,32 @@ __global__ void shard_bounds_kernel(const int32_t* __restrict__ row_ptr, int32_t
   bounds[k] = (int32_t)lo;
 }
 
+__global__ void col_probe_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ col, int32_t rows,
+                                 int32_t samples, unsigned long long* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned int near = 0, cmp = 0;
+  if (j < samples) {
+    const int64_t r = 1 + ((int64_t)j * (rows - 1)) / samples;
+    const int32_t a0 = rp[r - 1], a1 = rp[r], a2 = rp[r + 1];
+    int n = min(a1 - a0, a2 - a1);
+    n = min(n, 32);
+    for (int k = 0; k < n; ++k) {
+      const int32_t d = col[a1 + k] - col[a0 + k];
+      near += (d <= 32 && d >= -32);
+    }
+    cmp = n > 0 ? n : 0;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    near += __shfl_xor_sync(0xffffffffu, near, d);
+    cmp += __shfl_xor_sync(0xffffffffu, cmp, d);
+  }
+  if ((threadIdx.x & 31) == 0 && cmp) {
+    atomicAdd(out, (unsigned long long)near);
+    atomicAdd(out + 1, (unsigned long long)cmp);
+  }
+}
+
 inline int64_t padded_nnz(int64_t nnz) { return ((nnz + 3) & ~(int64_t)3) + 4; }
 
 }  // namespace
@@ -307,6 +333,25 @@ int coo_to_csr_device(const int32_t* d_rows, const int32_t* d_cols, const float*
                                                                                  *d_row_ptr);
   HISPMV_CUDA(cudaGetLastError());
   HISPMV_CUDA(cudaStreamSynchronize(stream));  // scratch buffers die at scope exit
+  return HISPMV_OK;
+}
+
+int col_probe_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, ColProbe* out, cudaStream_t stream) {
+  out->near = out->cmp = 0;
+  if (rows < 2) return HISPMV_OK;
+  const int32_t samples = std::min<int32_t>(rows - 1, kProbeSamples);
+  DevBuf buf;
+  int st;
+  if ((st = buf.alloc(2 * sizeof(unsigned long long)))) return st;
+  HISPMV_CUDA(cudaMemsetAsync(buf.p, 0, 2 * sizeof(unsigned long long), stream));
+  col_probe_kernel<<<blocks_for(samples, 128), 128, 0, stream>>>(d_row_ptr, d_col, rows, samples,
+                                                                 buf.as<unsigned long long>());
+  HISPMV_CUDA(cudaGetLastError());
+  unsigned long long h[2] = {0, 0};
+  HISPMV_CUDA(cudaMemcpyAsync(h, buf.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  out->near = (int64_t)h[0];
+  out->cmp = (int64_t)h[1];
   return HISPMV_OK;
 }
 
@@ -547,23 +592,63 @@ int adaptive_tiles_device(const int32_t* d_row_ptr, int32_t rows, int32_t stream
   return HISPMV_OK;
 }
 
+namespace {
+__global__ void tile_desc_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ tile_row,
+                                 const int32_t* __restrict__ tile_chunk, int64_t num_tiles, int32_t CH,
+                                 TileDesc* __restrict__ desc) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_tiles) return;
+  TileDesc d;
+  d.r0 = tile_row[t];
+  d.chunk = tile_chunk[t];
+  d.tile = (int32_t)t;
+  d.pad = 0;
+  if (d.chunk >= 0) {
+    const int32_t rb = rp[d.r0], re = rp[d.r0 + 1];
+    d.r1 = d.r0 + 1;
+    d.nchunks = (re - rb + CH - 1) / CH;
+    d.n0 = rb + d.chunk * CH;
+    d.n1 = min(re, d.n0 + CH);
+  } else {
+    d.r1 = tile_row[t + 1];
+    d.nchunks = 0;
+    d.n0 = rp[d.r0];
+    d.n1 = rp[d.r1];
+  }
+  desc[t] = d;
+}
+}  // namespace
+
+int tile_desc_device(const int32_t* d_row_ptr, const int32_t* d_tile_row, const int32_t* d_tile_chunk,
+                     int64_t num_tiles, int32_t chunk_nnz, TileDesc** d_desc, cudaStream_t stream) {
+  *d_desc = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)d_desc, (size_t)std::max<int64_t>(num_tiles, 1) * sizeof(TileDesc)));
+  if (num_tiles > 0) {
+    tile_desc_kernel<<<blocks_for(num_tiles, 256), 256, 0, stream>>>(d_row_ptr, d_tile_row, d_tile_chunk, num_tiles,
+                                                                     chunk_nnz, *d_desc);
+    HISPMV_CUDA(cudaGetLastError());
+  }
+  return HISPMV_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Runtime selector.  Pure integer arithmetic on the row-length histogram so that the CPU restatement
-// (oracle/oracle.c: oracle_select_kernel) reproduces the decision bit for bit.
+// Runtime selector.  Pure integer arithmetic on the row-length histogram and the column-locality probe, so that the
+// CPU restatement (oracle/oracle.c: oracle_select_kernel) reproduces the decision bit for bit.
 //
-// The FPGA design space (channels A:B:C, pre-accumulator, row-distribution network; dse.py:23-95)
-// collapses on a GPU to one question: is the row-length distribution regular enough that a fixed number
-// of lanes per row keeps every lane busy, or must work be balanced by nonzeros with heavy rows split?
-//   mean  = ceil(nnz / rows);  lanes = largest power of two <= mean, clamped to [2, 32]
-//   ADAPTIVE    if row splitting is allowed and any of
-//                 heavy       max row  > 32 * max(mean, 4)      (one row would serialise a sub-warp)
-//                 hollow      more than half of the rows are empty
-//                 underfilled rows * lanes < 148 SMs * 1024 threads (too few rows to fill the GPU)
-//   CSR_SCALAR  else if mean <= 2
-//   CSR_VECTOR  else, with `lanes` lanes per row
+// The FPGA design space (channels A:B:C, pre-accumulator, row-distribution network; dse.py:23-95) collapses on a GPU
+// to two questions: may rows be split across CTAs at all (row_dist_net), and in which order should lanes walk the
+// nonzeros so that the x gathers of one instruction share cache lines (the measured ceiling on gather-heavy matrices
+// is the ~0.95 L1-miss requests per clock an SM can issue)?
+//   mean    = ceil(nnz / rows);  lanes = largest power of two <= mean, clamped to [2, 32]
+//   regular = rows of >= 4*mean nonzeros hold < 1/8 of all nonzeros (estimated from the power-of-two histogram:
+//             a row in bin k, 2^(k-1) <= len < 2^k, counts 3 * 2^(k-2) nonzeros, 1 for k = 1)
+//   banded  = the probe compared >= 64 entry pairs and >= 3/4 of them were within 32 columns of the row above
+//   EMPTY       no nonzeros
+//   CSR_SCALAR / CSR_VECTOR(lanes)   row splitting not allowed (row_dist_net off): mean <= 2 / otherwise
+//   ROWSTAGE    regular and banded: row-major walk behind a TMA-staged stream
+//   ADAPTIVE    everything else: nnz-major tiles, heavy rows chunked across CTAs
 // ------------------------------------------------------------------------------------------------
-void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* kernel, int* lanes) {
-  (void)cols;
+void select_kernel(const RowStats& st, const ColProbe& probe, int allow_split_rows, int* kernel, int* lanes) {
   *lanes = 0;
   if (st.rows <= 0 || st.nnz <= 0) {
     *kernel = HISPMV_KERNEL_EMPTY;
@@ -572,19 +657,44 @@ void select_kernel(const RowStats& st, int32_t cols, int allow_split_rows, int* 
   const int64_t mean = (st.nnz + st.rows - 1) / st.rows;
   int l = 2;
   while (l < 32 && (int64_t)l * 2 <= mean) l *= 2;
-  const bool heavy = (int64_t)st.max_row_nnz > 32 * std::max<int64_t>(mean, 4);
-  const bool hollow = (int64_t)st.empty_rows * 2 > (int64_t)st.rows;
-  const bool underfilled = (int64_t)st.rows * l < 148LL * 1024;
-  if (allow_split_rows && (heavy || hollow || underfilled)) {
-    *kernel = HISPMV_KERNEL_ADAPTIVE;
+  if (!allow_split_rows) {
+    if (mean <= 2) {
+      *kernel = HISPMV_KERNEL_CSR_SCALAR;
+    } else {
+      *kernel = HISPMV_KERNEL_CSR_VECTOR;
+      *lanes = l;
+    }
     return;
   }
-  if (mean <= 2) {
-    *kernel = HISPMV_KERNEL_CSR_SCALAR;
-    return;
+  int64_t heavy_nnz = 0;
+  for (int k = 1; k < HISPMV_HIST_BINS; ++k) {
+    const int64_t lo = (int64_t)1 << (k - 1);
+    if (lo >= 4 * mean) heavy_nnz += st.hist[k] * (k == 1 ? 1 : 3 * ((int64_t)1 << (k - 2)));
   }
-  *kernel = HISPMV_KERNEL_CSR_VECTOR;
+  const bool regular = heavy_nnz * 8 < st.nnz;
+  const bool banded = probe.cmp >= 64 && probe.near * 4 >= probe.cmp * 3;
+  *kernel = (regular && banded) ? HISPMV_KERNEL_ROWSTAGE : HISPMV_KERNEL_ADAPTIVE;
+}
+
+// ROWSTAGE: `lanes` lanes per row, R = 256 / lanes rows per pass; the STREAM budget is R rows of average
+// length (row ends count as items), so a regular matrix gets tiles of about R rows and every thread has a row.
+//   items = ceil((nnz + rows) / rows);  lanes = smallest power of two with (256 / lanes) * items <= 4096
+//   B = max(256, (256 / lanes) * items);  T = 512 (longer rows become LONG tiles);  CH = 4096
+void rowstage_params(const RowStats& st, int lanes_in, int* lanes, int32_t* stream_items, int32_t* long_threshold,
+                     int32_t* chunk_nnz) {
+  const int64_t rows = std::max<int64_t>(st.rows, 1);
+  const int64_t items = (st.nnz + rows + rows - 1) / rows;
+  int l = lanes_in;
+  if (l <= 0) {
+    l = 1;
+    while (l < 32 && (256 / l) * items > 4096) l *= 2;
+  }
+  int64_t b = (256 / l) * items;
+  b = std::max<int64_t>(256, std::min<int64_t>(b, kRowstageMaxCap - 512));
   *lanes = l;
+  *stream_items = (int32_t)b;
+  *long_threshold = 512;
+  *chunk_nnz = 4096;
 }
 
 int merge_tile_items_for(const RowStats& st) {

@@ -10,6 +10,7 @@
 // Three strategies, chosen per matrix by the runtime selector (partition.cu: select_kernel):
 //   csr_scalar  one thread per row            -- very short regular rows
 //   csr_vector  LANES-wide sub-warp per row    -- regular rows, shuffle reduction
+//   (adaptive.cu holds the tile kernels -- adaptive, adaptive_persistent, rowstage -- the selector prefers)
 //   merge       merge-path tiles of row-ends+nonzeros: every CTA gets the same amount of work no
 //               matter how skewed the row lengths are; heavy rows are split across threads, warps
 //               and CTAs.  Partial sums meet through a warp-shuffle segmented scan inside the CTA and
@@ -231,185 +232,6 @@ __global__ void __launch_bounds__(256) spmv_merge_fixup_kernel(MergePlan P, int3
   y[row] = v;
 }
 
-// ------------------------------------------------------------------------------------------------
-// adaptive kernel: row-aligned, nnz-balanced tiles (AdaptivePlan); one CTA per tile, one launch.
-// ------------------------------------------------------------------------------------------------
-// STREAM tile (consecutive rows, each shorter than the long threshold):
-//   1. the tile's val/col stream is read once with aligned 128-bit evict-first loads, x is gathered, and the
-//      products land in shared memory -- the only shared-memory buffer, so most of the SM's 256 KB stays L1
-//      for the x gathers;
-//   2. rows are reduced out of shared memory by the narrowest group that keeps lanes busy: one thread for rows
-//      of <= kThreadRow nonzeros, an 8-lane group up to kGroupRow, a full warp above (in-tile binning through
-//      two small shared lists); y = alpha*sum + beta*bias is written straight from the reducing lane.
-// LONG tile (one chunk of a heavy row): the CTA streams the chunk with the same loads, reduces through
-//   warp shuffles + one shared exchange, and either finishes the row (single chunk) or drops its partial in
-//   carry[tile].  The CTA that arrives last at the row's counter sums the partials in chunk order and
-//   finishes the row, so split rows need no second launch, no atomics on y, and are bit-reproducible.
-constexpr int kAdThreads = 256;
-constexpr int kThreadRow = 4;
-constexpr int kGroupRow = 64;
-
-template <int CAP>  // CAP >= stream_items + long_threshold: products a STREAM tile may hold
-__global__ void __launch_bounds__(kAdThreads, 8)
-    spmv_adaptive_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
-  constexpr int WARPS = kAdThreads / 32;
-  constexpr int LIST = CAP / (kThreadRow + 1) + 1;
-  __shared__ float s_prod[CAP];
-  __shared__ unsigned short s_list8[LIST];
-  __shared__ unsigned short s_list32[CAP / (kGroupRow + 1) + 1];
-  __shared__ int s_n8, s_n32;
-  __shared__ float s_red[WARPS];
-  __shared__ int s_last;
-
-  const uint64_t ps = policy_evict_first(), pk = policy_evict_last(), pn = policy_evict_normal();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t t = blockIdx.x;
-  const int r0 = P.tile_row[t];
-  const int chunk = P.tile_chunk[t];
-
-  if (chunk < 0) {
-    // ------------------------------------------------------------------ STREAM tile
-    const int r1 = P.tile_row[t + 1];
-    const int trows = r1 - r0;
-    const int n0 = A.row_ptr[r0], n1 = A.row_ptr[r1];
-    const int tnnz = n1 - n0;
-    if (tid == 0) {
-      s_n8 = 0;
-      s_n32 = 0;
-    }
-    {
-      // One vector (4 nonzeros, 4 gathers) per thread and iteration: 32 registers keep 8 CTAs (2048 threads)
-      // resident per SM, which measured faster than fewer threads with deeper per-thread unrolling.
-      const int base = n0 & ~3;
-      for (int i = base + 4 * tid; i < n1; i += 4 * kAdThreads) {
-        const int4 c = ld_stream_i4(A.col + i, ps);
-        const float4 v = ld_stream_f4(A.val + i, ps);
-        const int k = i - n0;  // -3..-1 possible for the first vector
-        const bool p0 = (k >= 0) & (k < tnnz), p1 = (k + 1 >= 0) & (k + 1 < tnnz);
-        const bool p2 = (k + 2 >= 0) & (k + 2 < tnnz), p3 = (k + 3 < tnnz);
-        float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
-        if (p0) x0 = ld_x(x + c.x, pk);
-        if (p1) x1 = ld_x(x + c.y, pk);
-        if (p2) x2 = ld_x(x + c.z, pk);
-        if (p3) x3 = ld_x(x + c.w, pk);
-        if (p0) s_prod[k] = v.x * x0;
-        if (p1) s_prod[k + 1] = v.y * x1;
-        if (p2) s_prod[k + 2] = v.z * x2;
-        if (p3) s_prod[k + 3] = v.w * x3;
-      }
-    }
-    __syncthreads();
-    // rows: thread-per-row pass, longer rows are binned for the group / warp passes
-    for (int i = tid; i < trows; i += kAdThreads) {
-      const int r = r0 + i;
-      const int b = ld_stream_i1(A.row_ptr + r, pn) - n0, e = ld_stream_i1(A.row_ptr + r + 1, pn) - n0;
-      const int len = e - b;
-      if (len <= kThreadRow) {
-        float s = 0.0f;
-#pragma unroll
-        for (int k = 0; k < kThreadRow; ++k)
-          if (k < len) s += s_prod[b + k];
-        y[r] = finish(s, ep.alpha, ep.beta, ep.bias, r, ep.relu);
-      } else if (len <= kGroupRow) {
-        s_list8[atomicAdd(&s_n8, 1)] = (unsigned short)i;
-      } else {
-        s_list32[atomicAdd(&s_n32, 1)] = (unsigned short)i;
-      }
-    }
-    __syncthreads();
-    const int n8 = s_n8, n32 = s_n32;
-    {
-      const int gl = lane & 7, gi = lane >> 3;  // 4 groups of 8 lanes per warp
-      for (int qb = warp * 4; qb < n8; qb += WARPS * 4) {
-        const int q = qb + gi;
-        float s = 0.0f;
-        int r = 0;
-        if (q < n8) {
-          r = r0 + s_list8[q];
-          const int b = A.row_ptr[r] - n0, e = A.row_ptr[r + 1] - n0;
-          for (int k = b + gl; k < e; k += 8) s += s_prod[k];
-        }
-        s += __shfl_down_sync(kFullMask, s, 4, 8);
-        s += __shfl_down_sync(kFullMask, s, 2, 8);
-        s += __shfl_down_sync(kFullMask, s, 1, 8);
-        if (gl == 0 && q < n8) y[r] = finish(s, ep.alpha, ep.beta, ep.bias, r, ep.relu);
-      }
-    }
-    for (int q = warp; q < n32; q += WARPS) {
-      const int r = r0 + s_list32[q];
-      const int b = A.row_ptr[r] - n0, e = A.row_ptr[r + 1] - n0;
-      float s = 0.0f;
-      for (int k = b + lane; k < e; k += 32) s += s_prod[k];
-      s = warp_sum(s);
-      if (lane == 0) y[r] = finish(s, ep.alpha, ep.beta, ep.bias, r, ep.relu);
-    }
-    return;
-  }
-
-  // -------------------------------------------------------------------- LONG tile: chunk `chunk` of row r0
-  const int rb = A.row_ptr[r0], re = A.row_ptr[r0 + 1];
-  const int len = re - rb;
-  const int nchunks = (len + P.chunk_nnz - 1) / P.chunk_nnz;
-  const int c0 = rb + chunk * P.chunk_nnz;
-  const int c1 = min(re, c0 + P.chunk_nnz);
-  float acc = 0.0f;
-  {
-    // two vectors (8 nonzeros, 8 gathers) in flight per thread and iteration
-    const int base = (c0 & ~3) + 4 * tid;
-    for (int i = base; i < c1; i += 8 * kAdThreads) {
-      const int i2 = i + 4 * kAdThreads;
-      const bool second = i2 < c1;
-      const int4 ca = ld_stream_i4(A.col + i, ps);
-      const float4 va = ld_stream_f4(A.val + i, ps);
-      int4 cb = make_int4(0, 0, 0, 0);
-      float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (second) {
-        cb = ld_stream_i4(A.col + i2, ps);
-        vb = ld_stream_f4(A.val + i2, ps);
-      }
-      // entries outside [c0, c1) are valid matrix entries of a neighbouring chunk / zero padding: gather, then mask
-      const float xa0 = ld_x(x + ca.x, pk), xa1 = ld_x(x + ca.y, pk), xa2 = ld_x(x + ca.z, pk), xa3 = ld_x(x + ca.w, pk);
-      const float xb0 = ld_x(x + cb.x, pk), xb1 = ld_x(x + cb.y, pk), xb2 = ld_x(x + cb.z, pk), xb3 = ld_x(x + cb.w, pk);
-      if (i >= c0) acc = fmaf(va.x, xa0, acc);
-      if (i + 1 >= c0 && i + 1 < c1) acc = fmaf(va.y, xa1, acc);
-      if (i + 2 >= c0 && i + 2 < c1) acc = fmaf(va.z, xa2, acc);
-      if (i + 3 < c1) acc = fmaf(va.w, xa3, acc);
-      if (second) acc = fmaf(vb.x, xb0, acc);
-      if (second && i2 + 1 < c1) acc = fmaf(vb.y, xb1, acc);
-      if (second && i2 + 2 < c1) acc = fmaf(vb.z, xb2, acc);
-      if (second && i2 + 3 < c1) acc = fmaf(vb.w, xb3, acc);
-    }
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) s_red[warp] = acc;
-  __syncthreads();
-  if (warp != 0) return;
-  float total = lane < WARPS ? s_red[lane] : 0.0f;
-  total = warp_sum(total);
-  if (nchunks == 1) {
-    if (lane == 0) y[r0] = finish(total, ep.alpha, ep.beta, ep.bias, r0, ep.relu);
-    return;
-  }
-  const int64_t first = t - chunk;  // tile id of this row's chunk 0
-  int last = 0;
-  if (lane == 0) {
-    P.carry[t] = total;
-    __threadfence();
-    const unsigned int prev = atomicAdd(&P.counter[first], 1u);
-    last = (prev == (unsigned int)(nchunks - 1));
-  }
-  last = __shfl_sync(kFullMask, last, 0);
-  if (!last) return;
-  __threadfence();
-  float s = 0.0f;
-  for (int k = lane; k < nchunks; k += 32) s += __ldcg(P.carry + first + k);
-  s = warp_sum(s);
-  if (lane == 0) {
-    y[r0] = finish(s, ep.alpha, ep.beta, ep.bias, r0, ep.relu);
-    P.counter[first] = 0;  // ready for the next run / graph replay
-  }
-}
-
 __global__ void __launch_bounds__(256) spmv_empty_kernel(int32_t rows, float* __restrict__ y, Epilogue ep) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < rows) y[r] = finish(0.0f, ep.alpha, ep.beta, ep.bias, r, ep.relu);
@@ -450,28 +272,6 @@ int launch_csr_vector(const CsrDev& A, int lanes, const float* x, float* y, Epil
     case 16: spmv_csr_vector_kernel<16><<<grid, 256, 0, s>>>(A, x, y, ep); break;
     case 32: spmv_csr_vector_kernel<32><<<grid, 256, 0, s>>>(A, x, y, ep); break;
     default: set_error("csr_vector: lanes must be 2,4,8,16 or 32"); return HISPMV_ERR_ARG;
-  }
-  HISPMV_CUDA(cudaGetLastError());
-  return HISPMV_OK;
-}
-
-int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s) {
-  if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
-  if (P.num_tiles > INT_MAX) {
-    set_error("adaptive: too many tiles");
-    return HISPMV_ERR_ARG;
-  }
-  const int need = P.stream_items + P.long_threshold;
-  if (need > 4096 || P.chunk_nnz <= 0) {
-    set_error("adaptive: plan exceeds the compiled shared-memory capacity");
-    return HISPMV_ERR_ARG;
-  }
-  if (need <= 2048) {
-    spmv_adaptive_kernel<2048><<<(int)P.num_tiles, kAdThreads, 0, s>>>(A, P, x, y, ep);
-  } else if (need <= 3072) {
-    spmv_adaptive_kernel<3072><<<(int)P.num_tiles, kAdThreads, 0, s>>>(A, P, x, y, ep);
-  } else {
-    spmv_adaptive_kernel<4096><<<(int)P.num_tiles, kAdThreads, 0, s>>>(A, P, x, y, ep);
   }
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;

@@ -64,8 +64,11 @@ enum {
   HISPMV_KERNEL_MERGE = 3,       /* merge-path tiles, heavy rows split across CTAs, carry-out fix-up */
   HISPMV_KERNEL_GEMV = 4,        /* dense overlay: streaming row-major GeMV */
   HISPMV_KERNEL_EMPTY = 5,       /* nnz == 0: y = beta * bias */
-  HISPMV_KERNEL_ADAPTIVE = 6     /* row-aligned nnz-balanced tiles: short rows streamed through shared memory,
+  HISPMV_KERNEL_ADAPTIVE = 6,    /* row-aligned nnz-balanced tiles: short rows streamed through shared memory,
                                     long rows chunked across CTAs with carry-out (default for imbalanced rows) */
+  HISPMV_KERNEL_ROWSTAGE = 7     /* the same tiles with the col/val stream staged in shared memory by TMA bulk copies
+                                    and rows walked by 1..32 lanes each: regular rows with column locality
+                                    (banded / stencil / FEM) */
 };
 
 /* ctor flags: the reference's hardware switches that still mean something on a GPU */
@@ -82,7 +85,7 @@ typedef struct hispmv_matrix_info {
   int64_t nnz;              /* nonzeros held locally (dense: local_rows*cols) */
   int32_t is_dense;
   int32_t kernel;           /* HISPMV_KERNEL_* actually planned */
-  int32_t vector_lanes;     /* sub-warp width when kernel == CSR_VECTOR */
+  int32_t vector_lanes;     /* lanes per row when kernel == CSR_VECTOR or ROWSTAGE */
   int32_t tile_items;       /* merge items (row ends + nonzeros) per CTA: MERGE tile size / ADAPTIVE stream budget */
   int64_t num_tiles;        /* merge tiles (CTAs) */
   int64_t num_split_rows;   /* rows whose nonzeros span more than one tile (the "shared rows") */
@@ -90,6 +93,11 @@ typedef struct hispmv_matrix_info {
   int32_t empty_rows;
   int64_t hist[HISPMV_HIST_BINS]; /* hist[0]: empty rows; hist[k]: rows with 2^(k-1) <= nnz < 2^k */
   int64_t device_bytes;     /* HBM held by this matrix, incl. plan metadata */
+  int64_t probe_near;       /* column-locality probe: sampled entry pairs within 32 columns of the row above ... */
+  int64_t probe_cmp;        /* ... out of this many compared (selector input: banded when near/cmp >= 3/4) */
+  int32_t x_window_cols;    /* > 0 only under the HISPMV_PERSIST research switch (persistent x-window kernel) */
+  int32_t long_threshold;   /* ADAPTIVE / ROWSTAGE: rows with at least this many nonzeros become LONG tiles */
+  int32_t chunk_nnz;        /* ADAPTIVE / ROWSTAGE: nonzeros per LONG tile (chunk of a heavy row) */
 } hispmv_matrix_info;
 
 const char* hispmv_last_error(void);

@@ -204,12 +204,36 @@ void oracle_row_stats(int rows, const int* row_ptr, int64_t* hist, int* max_row_
 }
 
 /* kernel ids as in include/hispmv.h */
-enum { K_SCALAR = 1, K_VECTOR = 2, K_MERGE = 3, K_EMPTY = 5, K_ADAPTIVE = 6 };
+enum { K_SCALAR = 1, K_VECTOR = 2, K_MERGE = 3, K_EMPTY = 5, K_ADAPTIVE = 6, K_ROWSTAGE = 7 };
 
-void oracle_select_kernel(int rows, int64_t nnz, int max_row_nnz, int empty_rows, int allow_split_rows, int* kernel,
-                          int* lanes) {
-  int64_t mean, m4;
-  int l = 2;
+/* Column-locality probe (partition.cu: col_probe_kernel): up to 8192 evenly spaced rows r >= 1, entries of rows r and
+ * r-1 compared position by position over the first min(len(r), len(r-1), 32) positions. */
+void oracle_col_probe(int rows, const int* rp, const int* col, int64_t* near, int64_t* cmp) {
+  int64_t nr = 0, cp = 0;
+  if (rows >= 2) {
+    const int samples = rows - 1 < 8192 ? rows - 1 : 8192;
+    int j, k;
+    for (j = 0; j < samples; ++j) {
+      const int64_t r = 1 + ((int64_t)j * (rows - 1)) / samples;
+      const int a0 = rp[r - 1], a1 = rp[r], a2 = rp[r + 1];
+      int n = a1 - a0 < a2 - a1 ? a1 - a0 : a2 - a1;
+      if (n > 32) n = 32;
+      for (k = 0; k < n; ++k) {
+        const int d = col[a1 + k] - col[a0 + k];
+        nr += (d <= 32 && d >= -32);
+      }
+      if (n > 0) cp += n;
+    }
+  }
+  *near = nr;
+  *cmp = cp;
+}
+
+/* partition.cu: select_kernel.  hist: 33 power-of-two bins as produced by oracle_row_stats. */
+void oracle_select_kernel(int rows, int64_t nnz, const int64_t* hist, int64_t probe_near, int64_t probe_cmp,
+                          int allow_split_rows, int* kernel, int* lanes) {
+  int64_t mean, heavy_nnz = 0;
+  int l = 2, k;
   *lanes = 0;
   if (rows <= 0 || nnz <= 0) {
     *kernel = K_EMPTY;
@@ -217,28 +241,51 @@ void oracle_select_kernel(int rows, int64_t nnz, int max_row_nnz, int empty_rows
   }
   mean = (nnz + rows - 1) / rows;
   while (l < 32 && (int64_t)l * 2 <= mean) l *= 2;
-  m4 = mean > 4 ? mean : 4;
-  {
-    const int heavy = (int64_t)max_row_nnz > 32 * m4;
-    const int hollow = (int64_t)empty_rows * 2 > (int64_t)rows;
-    const int underfilled = (int64_t)rows * l < 148LL * 1024;
-    if (allow_split_rows && (heavy || hollow || underfilled)) {
-      *kernel = K_ADAPTIVE;
-      return;
+  if (!allow_split_rows) {
+    if (mean <= 2) {
+      *kernel = K_SCALAR;
+    } else {
+      *kernel = K_VECTOR;
+      *lanes = l;
     }
-  }
-  if (mean <= 2) {
-    *kernel = K_SCALAR;
     return;
   }
-  *kernel = K_VECTOR;
-  *lanes = l;
+  for (k = 1; k < 33; ++k) {
+    const int64_t lo = (int64_t)1 << (k - 1);
+    if (lo >= 4 * mean) heavy_nnz += hist[k] * (k == 1 ? 1 : 3 * ((int64_t)1 << (k - 2)));
+  }
+  {
+    const int regular = heavy_nnz * 8 < nnz;
+    const int banded = probe_cmp >= 64 && probe_near * 4 >= probe_cmp * 3;
+    *kernel = (regular && banded) ? K_ROWSTAGE : K_ADAPTIVE;
+  }
 }
 
 int oracle_merge_tile_items(int rows, int64_t nnz) {
   const int64_t total = (int64_t)rows + nnz;
   if (total < 148LL * 4 * 1792) return 128 * 7;
   return 256 * 7;
+}
+
+/* ROWSTAGE plan parameters (partition.cu: rowstage_params): lanes per row, STREAM budget B, long threshold T,
+ * chunk size CH.  lanes_in = 0 lets the rule choose lanes. */
+void oracle_rowstage_params(int rows, int64_t nnz, int lanes_in, int* lanes, int* stream_items, int* long_threshold,
+                            int* chunk_nnz) {
+  const int64_t rws = rows > 1 ? rows : 1;
+  const int64_t items = (nnz + rws + rws - 1) / rws;
+  int l = lanes_in;
+  int64_t b;
+  if (l <= 0) {
+    l = 1;
+    while (l < 32 && (256 / l) * items > 4096) l *= 2;
+  }
+  b = (256 / l) * items;
+  if (b > 8192 - 512) b = 8192 - 512;
+  if (b < 256) b = 256;
+  *lanes = l;
+  *stream_items = (int)b;
+  *long_threshold = 512;
+  *chunk_nnz = 4096;
 }
 
 /* Merge-path tile start coordinates: tile t starts at diagonal min(t*tile_items, rows+nnz) of the merge

@@ -58,7 +58,9 @@ def oracle() -> C.CDLL:
     lib.oracle_max_scaled_error.argtypes = [i, _f32p, _f64p, _f64p, C.POINTER(i)]
     lib.oracle_max_scaled_error.restype = d
     lib.oracle_row_stats.argtypes = [i, _i32p, _i64p, C.POINTER(i), C.POINTER(i)]
-    lib.oracle_select_kernel.argtypes = [i, i64, i, i, i, C.POINTER(i), C.POINTER(i)]
+    lib.oracle_select_kernel.argtypes = [i, i64, _i64p, i64, i64, i, C.POINTER(i), C.POINTER(i)]
+    lib.oracle_col_probe.argtypes = [i, _i32p, _i32p, C.POINTER(i64), C.POINTER(i64)]
+    lib.oracle_rowstage_params.argtypes = [i, i64, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.oracle_merge_tile_items.argtypes = [i, i64]
     lib.oracle_merge_tile_items.restype = i
     lib.oracle_merge_tiles.argtypes = [i, _i32p, i, vp, vp]
@@ -194,7 +196,7 @@ def split_rows(rp, tr, tn):
     return out
 
 
-def adaptive_tiles(rp, B=2048, T=1024, CH=4096):
+def adaptive_tiles(rp, B=2048, T=1024, CH=3072):
     rp = np.ascontiguousarray(rp, np.int32)
     rows = rp.size - 1
     nt = oracle().oracle_adaptive_tiles(rows, rp, B, T, CH, None, None)
@@ -218,10 +220,29 @@ def row_stats(rp):
     return hist, mx.value, em.value
 
 
-def select_kernel(rows, nnz, max_row, empty_rows, allow_split=1):
+def col_probe(rp, ci):
+    rp, ci = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32)
+    if ci.size == 0:
+        ci = np.zeros(1, np.int32)
+    near, cmp_ = C.c_int64(), C.c_int64()
+    oracle().oracle_col_probe(rp.size - 1, rp, ci, C.byref(near), C.byref(cmp_))
+    return near.value, cmp_.value
+
+
+def select_kernel(rp, ci, allow_split=1):
+    """(kernel, lanes, probe_near, probe_cmp) the selector must choose for this CSR."""
+    rp = np.ascontiguousarray(rp, np.int32)
+    hist, mx, em = row_stats(rp)
+    near, cmp_ = col_probe(rp, ci)
     k, l = C.c_int(), C.c_int()
-    oracle().oracle_select_kernel(rows, nnz, max_row, empty_rows, allow_split, C.byref(k), C.byref(l))
-    return k.value, l.value
+    oracle().oracle_select_kernel(rp.size - 1, int(rp[-1]), hist, near, cmp_, allow_split, C.byref(k), C.byref(l))
+    return k.value, l.value, near, cmp_
+
+
+def rowstage_params(rows, nnz, lanes_in=0):
+    l, b, t, ch = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    oracle().oracle_rowstage_params(rows, nnz, lanes_in, C.byref(l), C.byref(b), C.byref(t), C.byref(ch))
+    return l.value, b.value, t.value, ch.value
 
 
 def shard_bounds(rp, n_parts):

@@ -68,8 +68,8 @@ def test_coo_to_csr_bit_exact(eng, rows, cols, nnz, dup):
     info = eng.matrix_info(idx)
     hist, mx, em = ol.row_stats(rp2)
     assert info["hist"] == hist.tolist() and info["max_row_nnz"] == mx and info["empty_rows"] == em
-    k, l = ol.select_kernel(rows, nnz, mx, em, 1)
-    assert (info["kernel"], info["vector_lanes"]) == (k, l)
+    k, l, near, cmp_ = ol.select_kernel(rp2, ci2, 1)
+    assert (info["kernel"], info["probe_near"], info["probe_cmp"]) == (k, near, cmp_)
 
 
 def test_coo_index_out_of_range_is_refused(eng):
@@ -128,7 +128,7 @@ def test_adaptive_plan_bit_exact(eng, seed):
     info = eng.matrix_info(idx)
     assert info["kernel"] == capi.KERNEL_ADAPTIVE
     rp, ci, vv = eng.plan_csr(idx)
-    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, info["tile_items"])
+    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, info["tile_items"], info["long_threshold"], info["chunk_nnz"])
     assert info["num_tiles"] == tc2.size and info["num_split_rows"] == sp2.size
     tr, tn = eng.plan_tiles(idx)
     assert np.array_equal(tr, tr2) and np.array_equal(tn, tn2)
@@ -137,6 +137,122 @@ def test_adaptive_plan_bit_exact(eng, seed):
     y1 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
     y2 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))   # counters reset themselves
     assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
+
+
+@pytest.mark.parametrize("lanes", [0, 1, 4, 32])
+def test_rowstage_plan_bit_exact(eng, lanes):
+    """The TMA-staged row-major kernel shares the adaptive tiling; its plan parameters (lanes, B, T, CH) and the
+    resulting tile descriptors must equal the sequential restatement."""
+    from hispmv_b200 import capi
+    rng = np.random.default_rng(100 + lanes)
+    rows, cols = 40000, 40000
+    lens = rng.integers(20, 34, rows)
+    lens[rng.integers(0, rows, 5)] = rng.integers(512, 9000, 5)     # a few LONG rows, some split
+    lens[rng.integers(0, rows, 500)] = 0
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = np.clip(r + rng.integers(-40, 41, r.size), 0, cols - 1).astype(np.int32)   # banded
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_ROWSTAGE, lanes)
+    info = eng.matrix_info(idx)
+    assert info["kernel"] == capi.KERNEL_ROWSTAGE
+    l, B, T, CH = ol.rowstage_params(rows, r.size, lanes)
+    assert (info["vector_lanes"], info["tile_items"], info["long_threshold"], info["chunk_nnz"]) == (l, B, T, CH)
+    rp, ci, vv = eng.plan_csr(idx)
+    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, B, T, CH)
+    assert info["num_tiles"] == tc2.size and info["num_split_rows"] == sp2.size
+    tr, tn = eng.plan_tiles(idx)
+    assert np.array_equal(tr, tr2) and np.array_equal(tn, tn2)
+    assert np.array_equal(eng.plan_tile_chunks(idx), tc2)
+    assert np.array_equal(eng.plan_split_rows(idx), sp2)
+    y1 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
+    y2 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
+    assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
+
+
+@pytest.mark.parametrize("window", [1, 777, 16000, 40960])
+def test_persistent_window_kernel(eng, window, monkeypatch):
+    """The persistent ADAPTIVE kernel (x[0, window) in shared memory, tiles pulled from a global counter): same
+    plan artefacts as the one-tile-per-CTA kernel, results within tolerance, bit-identical from run to run even
+    though the tile-to-group assignment is dynamic."""
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_PERSIST", str(window))
+    rng = np.random.default_rng(window)
+    rows, cols = 30000, 16000 if window == 16000 else 50000
+    lens = np.minimum(rng.zipf(1.6, rows), 40000)
+    heavy = rng.integers(1, rows - 2, 6)
+    lens[heavy] = rng.integers(1024, 20000, 6)
+    lens[rng.integers(0, rows, 3000)] = 0
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = (rng.random(r.size) ** 4 * cols).astype(np.int32)            # head-heavy columns
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_ADAPTIVE)
+    info = eng.matrix_info(idx)
+    assert info["kernel"] == capi.KERNEL_ADAPTIVE and info["x_window_cols"] == min(window, cols)
+    rp, ci, vv = eng.plan_csr(idx)
+    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, info["tile_items"], info["long_threshold"], info["chunk_nnz"])
+    assert np.array_equal(eng.plan_tile_chunks(idx), tc2) and np.array_equal(eng.plan_split_rows(idx), sp2)
+    ys = [_check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7)) for _ in range(3)]
+    assert np.array_equal(ys[0].view(np.uint32), ys[1].view(np.uint32))
+    assert np.array_equal(ys[0].view(np.uint32), ys[2].view(np.uint32))
+    monkeypatch.setenv("HISPMV_PERSIST", "0")
+    eng.force_kernel(idx, capi.KERNEL_ADAPTIVE)
+    assert eng.matrix_info(idx)["x_window_cols"] == 0
+    _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
+
+
+@pytest.mark.parametrize("kind,expect", [("banded", "rowstage"), ("banded_heavy", "adaptive"), ("random", "adaptive"),
+                                         ("stencil", "rowstage")])
+def test_selector_bit_exact(eng, kind, expect):
+    """The runtime selector (row-length histogram + column-locality probe) against the oracle's restatement, on
+    matrices built to land on either side of both rules."""
+    rng = np.random.default_rng(sum(map(ord, kind)))
+    rows = cols = 60000
+    if kind == "stencil":
+        from hispmv_b200 import synth
+        spec = synth.c4_stencil(0.003)
+        rp, ci, vv = ol.synth_csr(spec.kind, spec.seed, spec.cols, spec.params, 0, spec.rows)
+        rows = cols = spec.rows
+        idx = eng.create_sparse_handle_csr(rp, ci, vv, rows, cols)
+    else:
+        lens = rng.integers(8, 24, rows)
+        if kind == "banded_heavy":
+            lens[rng.integers(0, rows, 300)] = 1500                   # > 1/8 of the nonzeros in rows >= 4 * mean
+        r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+        if kind == "random":
+            c = rng.integers(0, cols, r.size).astype(np.int32)
+        else:
+            c = np.clip(r + rng.integers(-30, 31, r.size), 0, cols - 1).astype(np.int32)
+        v = rng.standard_normal(r.size).astype(np.float32)
+        idx = eng.create_sparse_handle(r, c, v, rows, cols)
+        rp, ci, vv = eng.plan_csr(idx)
+    info = eng.matrix_info(idx)
+    k, l, near, cmp_ = ol.select_kernel(rp, ci, 1)
+    assert (info["kernel"], info["probe_near"], info["probe_cmp"]) == (k, near, cmp_)
+    assert info["kernel_name"] == expect
+    _check_run(eng, idx, rp, ci, vv, rows, cols, rng)
+
+
+def test_selector_without_row_dist_net():
+    """row_dist_net=False (the reference's switch for its shared-row network) forbids splitting rows across CTAs:
+    the selector must stay on the one-row-per-lane-group kernels."""
+    from hispmv_b200 import Engine
+    e = Engine(0, row_dist_net=False)
+    rng = np.random.default_rng(5)
+    rows, cols = 20000, 20000
+    for mean, want in ((1, "csr_scalar"), (12, "csr_vector")):
+        lens = rng.integers(0, 2 * mean + 1, rows)
+        r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+        c = rng.integers(0, cols, r.size).astype(np.int32)
+        v = rng.standard_normal(r.size).astype(np.float32)
+        idx = e.create_sparse_handle(r, c, v, rows, cols)
+        rp, ci, vv = e.plan_csr(idx)
+        info = e.matrix_info(idx)
+        k, l, _, _ = ol.select_kernel(rp, ci, 0)
+        assert (info["kernel"], info["vector_lanes"]) == (k, l) and info["kernel_name"] == want
+        _check_run(e, idx, rp, ci, vv, rows, cols, rng)
+    e.close()
 
 
 @pytest.mark.parametrize("parts", [2, 3, 8])
@@ -170,7 +286,8 @@ def _matrix(rng, kind, rows, cols):
 
 
 @pytest.mark.parametrize("kind", ["powerlaw", "regular", "short", "hollow"])
-@pytest.mark.parametrize("kernel,lanes", [(1, 0), (2, 2), (2, 8), (2, 32), (3, 0), (6, 0), (0, 0)])
+@pytest.mark.parametrize("kernel,lanes", [(1, 0), (2, 2), (2, 8), (2, 32), (3, 0), (6, 0), (7, 0), (7, 1), (7, 2), (7, 8),
+                                          (0, 0)])
 def test_spmv_kernels_within_tolerance(eng, kind, kernel, lanes):
     rng = np.random.default_rng(sum(map(ord, kind)) * 131 + kernel * 17 + lanes)
     rows, cols = 30011, 40009

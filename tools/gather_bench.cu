@@ -72,9 +72,10 @@ __global__ void __launch_bounds__(1024) gather(const int32_t* __restrict__ idx, 
 }
 
 template <int MODE>
-float run(int grid, int threads, const int32_t* idx, int64_t n, const float* tab, int hot, float* out) {
+float run(int grid, int threads, const int32_t* idx, int64_t n, const float* tab, int hot, float* out,
+          size_t extra_smem = 0) {
   auto kern = gather<MODE>;
-  const size_t smem = MODE == 4 ? (size_t)hot * 4 : 0;
+  const size_t smem = MODE == 4 ? (size_t)hot * 4 : extra_smem;
   if (smem) CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -120,6 +121,13 @@ int main() {
              use, threads, n / m0 / 1e6, n / m1 / 1e6, n / m2 / 1e6, n / m3 / 1e6, n / m0 / 1e6 / use / 1.965,
              n / m1 / 1e6 / use / 1.965, n / m2 / 1e6 / use / 1.965, n / m3 / 1e6 / use / 1.965);
     }
+  }
+  printf("E: does the shared-memory carve-out (i.e. a smaller L1) throttle L1-miss gathers?  2 CTAs x 1024 threads per SM\n");
+  for (int kb : {0, 16, 32, 48, 64, 80, 96, 110}) {
+    const float m0 = run<0>(sms * 2, 1024, idx, n, tab, 0, out, (size_t)kb * 1024);
+    const float m1 = run<1>(sms * 2, 1024, idx, n, tab, 0, out, (size_t)kb * 1024);
+    printf("dynamic smem %3d KB per CTA (%3d KB per SM): nc %7.2f G/s | nc.no_allocate %7.2f G/s\n", kb, 2 * kb, n / m0 / 1e6,
+           n / m1 / 1e6);
   }
   printf("D: fraction of gathers served from a shared-memory hot window (1 CTA of 1024 threads per SM)\n");
   for (int hot_words : {8192, 32768, 49152}) {

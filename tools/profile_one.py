@@ -19,7 +19,7 @@ from hispmv_b200 import Engine, capi, synth  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "adaptive", "merge", "vector", "scalar", "gemv"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "adaptive", "rowstage", "merge", "vector", "scalar", "gemv"])
     ap.add_argument("--tile", default="")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--scale", type=float, default=1.0)
@@ -39,7 +39,7 @@ def main():
         d = synth.DeviceCSR(spec)
         idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
         d.close()
-        k = {"auto": capi.KERNEL_AUTO, "adaptive": capi.KERNEL_ADAPTIVE, "merge": capi.KERNEL_MERGE, "vector": capi.KERNEL_CSR_VECTOR,
+        k = {"auto": capi.KERNEL_AUTO, "adaptive": capi.KERNEL_ADAPTIVE, "rowstage": capi.KERNEL_ROWSTAGE, "merge": capi.KERNEL_MERGE, "vector": capi.KERNEL_CSR_VECTOR,
              "scalar": capi.KERNEL_CSR_SCALAR}[args.kernel]
         eng.force_kernel(idx, k, args.lanes)
         rows, cols = spec.rows, spec.cols

@@ -1,0 +1,108 @@
+"""One process per GPU: nnz-balanced row blocks, x replicated by broadcast, y blocks all-gathered.
+
+The reference is single-device (one xrt::device, pyhispmv/src/fpga_handle.cpp:55); this module is the multi-GPU
+design the north star adds.  Rows are independent, so the SpMV itself needs no collective: rank r owns the
+contiguous row block [bounds[r], bounds[r+1]) of every matrix (split points = lower_bound(row_ptr, k*nnz/G), rows are
+never split across GPUs; dense matrices use equal row blocks) and a full copy of x.  Two exchange steps exist:
+  * broadcast_x   x produced on one rank -> all ranks (NCCL broadcast over NVLink)
+  * allgather_rows  chained layers: every rank's y block -> the next layer's replicated x.  Blocks have unequal
+                    row counts, so they travel padded to the largest block and are compacted by one gather.
+torch.distributed supplies the process group (NCCL on GPUs; the same code runs over gloo on CPU tensors, which is how
+tests/test_sharded_cpu.py covers the bookkeeping).  All arithmetic stays in libhispmv_cuda.so.
+"""
+from __future__ import annotations
+
+from typing import Dict, Hashable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class RowBlockComm:
+    """Collective plumbing for row-block sharded vectors."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised (launch with torchrun)")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self._plans: Dict[Hashable, dict] = {}
+
+    def set_blocks(self, key: Hashable, row_begin: int, row_end: int, device) -> np.ndarray:
+        """Register this rank's block of vector `key`; returns the bounds of all ranks (world+1 entries)."""
+        mine = torch.tensor([row_begin, row_end], dtype=torch.int64, device=device)
+        allb = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allb, mine, group=self.group)
+        pairs = torch.stack(allb).cpu().numpy()
+        bounds = np.concatenate([pairs[:, 0], pairs[-1:, 1]])
+        if not (np.all(pairs[1:, 0] == pairs[:-1, 1]) and bounds[0] == 0):
+            raise ValueError(f"row blocks do not tile the vector: {pairs.tolist()}")
+        counts = np.diff(bounds)
+        pad = int(counts.max()) if counts.size else 0
+        # position of row i inside the padded (world x pad) receive buffer
+        index = np.concatenate([r * pad + np.arange(counts[r]) for r in range(self.world)]) if pad else np.zeros(0)
+        self._plans[key] = {
+            "bounds": bounds, "pad": pad,
+            "index": torch.from_numpy(index.astype(np.int64)).to(device),
+            "send": torch.zeros(max(pad, 1), dtype=torch.float32, device=device),
+            "recv": torch.zeros(max(pad, 1) * self.world, dtype=torch.float32, device=device),
+        }
+        return bounds
+
+    def bounds(self, key: Hashable) -> np.ndarray:
+        return self._plans[key]["bounds"]
+
+    def allgather_rows(self, idx_layer: Hashable, y_local: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+        """out[bounds[r]:bounds[r+1]] = rank r's y_local, on every rank."""
+        p = self._plans[idx_layer]
+        n = y_local.numel()
+        p["send"][:n].copy_(y_local)
+        chunks = list(p["recv"].view(self.world, -1).unbind(0))
+        dist.all_gather(chunks, p["send"], group=self.group)
+        torch.index_select(p["recv"], 0, p["index"], out=out)
+        return out
+
+    def broadcast_x(self, x: torch.Tensor, src: int = 0) -> torch.Tensor:
+        dist.broadcast(x, src=src, group=self.group)
+        return x
+
+
+class ShardedEngine:
+    """An Engine that keeps row block `rank` of `world` of every matrix, plus the collectives around it."""
+
+    def __init__(self, local_device: int, group=None, **engine_kwargs):
+        from .engine import Engine
+        self.comm = RowBlockComm(group)
+        self.engine = Engine(local_device, shard=(self.comm.rank, self.comm.world), **engine_kwargs)
+        self.device = torch.device("cuda", local_device)
+        self._y: Dict[int, torch.Tensor] = {}
+
+    def add(self, idx: int) -> int:
+        """Register matrix idx (already created on self.engine) for gathers of its y."""
+        info = self.engine.matrix_info(idx)
+        self.comm.set_blocks(idx, info["row_begin"], info["row_end"], self.device)
+        self._y[idx] = torch.empty(info["row_end"] - info["row_begin"], device=self.device)
+        return idx
+
+    def spmv(self, idx: int, x: torch.Tensor, bias_local: Optional[torch.Tensor], alpha: float = 1.0,
+             beta: float = 0.0, x_root: Optional[int] = None, gather: bool = False, stream: int = 0):
+        """y_block = alpha * A_block x + beta * bias_block.  x_root: rank whose x is broadcast first (None: x is
+        already replicated).  gather=True returns the full y on every rank, else this rank's block."""
+        if x_root is not None:
+            self.comm.broadcast_x(x, x_root)
+        y = self._y[idx]
+        self.engine.run_dev(idx, x, bias_local, y, alpha, beta, stream or torch.cuda.current_stream().cuda_stream)
+        if not gather:
+            return y
+        rows = int(self.comm.bounds(idx)[-1])
+        return self.comm.allgather_rows(idx, y, torch.empty(rows, device=self.device))
+
+    def close(self):
+        self.engine.close()
+
+
+def reassemble(blocks: Sequence[np.ndarray]) -> np.ndarray:
+    """Host-side concatenation of per-rank y blocks (tests / debugging)."""
+    return np.concatenate(list(blocks)) if len(blocks) else np.zeros(0, np.float32)

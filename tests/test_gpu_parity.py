@@ -533,3 +533,52 @@ def test_row_block_shards_reassemble(parts):
     err, _ = ol.max_scaled_error(y, y64, scale)
     assert err <= TOL
     full.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# the DNN-layer callers: apps/model_test.py flow (host plugin path) and the device-resident chain
+# ---------------------------------------------------------------------------------------------------
+def _mlp(seed=0, sizes=(512, 1024, 1024, 256)):
+    import torch
+    from hispmv_b200.layers import ThreeLayerFCModel, ThreeLayerFCModelConfig
+    torch.manual_seed(seed)
+    cfg = ThreeLayerFCModelConfig(sizes[0], sizes[1], sizes[2], sizes[3], 0.1, 0.25)
+    m = ThreeLayerFCModel(cfg).eval()
+    for p in m.parameters():
+        p.requires_grad = False
+    return m
+
+
+def test_model_test_flow_through_plugin():
+    """apps/model_test.py:53-90: replace_layers(cpu_model, fpga), one forward of a random input, compare with the
+    CPU model.  Tolerance as apps/general_test.py:106 (rtol 1e-3), plus the north-star bar per layer output."""
+    import torch
+    import pyhispmv
+    from hispmv_b200.layers import FpgaLayerManager
+    cpu_model = _mlp()
+    fpga = pyhispmv.FpgaHandle("unused.xclbin", 0, 24, 1, 1, 2, 5, True, False, True)
+    fpga_model = FpgaLayerManager().replace_layers(cpu_model, fpga)
+    x = torch.randn((1, 512))
+    with torch.no_grad():
+        ref = cpu_model(x).numpy()
+        out = fpga_model(x).numpy()
+    assert out.shape == ref.shape == (1, 256)
+    assert np.allclose(out, ref, rtol=1e-3, atol=1e-4)
+    # batch > 1 goes through linear()'s vector loop (fpga_handle.cpp:336, 366-379)
+    xb = torch.randn((3, 512))
+    with torch.no_grad():
+        assert np.allclose(fpga_model(xb).numpy(), cpu_model(xb).numpy(), rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_device_chain_matches_cpu_model(eng, graph):
+    import torch
+    from hispmv_b200.layers import DeviceChain
+    cpu_model = _mlp(1)
+    chain = DeviceChain(eng, [cpu_model.dense, cpu_model.sparse1, cpu_model.sparse2], relu=[True, True, True], graph=graph)
+    for _ in range(3):   # replays must not depend on leftover state
+        x = torch.randn(512)
+        with torch.no_grad():
+            ref = cpu_model(x.view(1, -1)).numpy().reshape(-1)
+        out = chain.forward(x.cuda()).cpu().numpy()
+        assert np.allclose(out, ref, rtol=1e-3, atol=1e-4)

@@ -277,7 +277,8 @@ def run_ours(args):
         achieved = bytes_alg_local / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("c2_merge_bytes_per_launch")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "c2_" + info["kernel_name"] + "_dram_bytes_per_launch")
         except Exception:
             pass
         line = {
@@ -295,7 +296,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": bytes_alg_local,
-                         "note": "rank 0's row block; merge kernel + carry fix-up timed together per step"},
+                         "launches_per_step": int(eng.launches_per_run(idx)),
+                         "note": "rank 0's row block, one launch per step; traffic = ncu dram read+write of the same "
+                                 "kernel on the N=1 matrix (profiles/); the binding limit on this matrix is the SM's "
+                                 "L1-miss request rate for the x gathers, not HBM (DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * spec.cols + 4 * n_local) * world,
                     "d2h_bytes_per_step": int(4 * spec.rows), "ms_per_step": e2e_ms,
                     "api": "hispmv_run (host x, bias -> host y), pinned host memory"},

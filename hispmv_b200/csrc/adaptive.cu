@@ -117,11 +117,11 @@ __device__ __forceinline__ void stream_products(const CsrDev& A, const G& gx, in
 }
 
 // ---- rows of a STREAM tile out of the product buffer: warp gw owns rows [beg, end) of the tile -------------------
-// (b0, e0) are the extents of row beg+lane relative to s_prod[0], loaded by the caller before the barrier that
-// publishes the products.  One lane sums a row of up to kSerialRow products; longer rows are taken one at a time by
+// (b0, e0) are the extents of row beg+lane relative to s_prod[0] and bias0 its bias value, loaded by the caller
+// before the barrier that publishes the products (their DRAM round trips overlap the stream).  One lane sums a row of up to kSerialRow products; longer rows are taken one at a time by
 // the whole warp.
 __device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int n0, int beg, int end, int b0, int e0,
-                                                   const float* s_prod, int lane, float* __restrict__ y,
+                                                   float bias0, const float* s_prod, int lane, float* __restrict__ y,
                                                    const Epilogue& ep) {
   for (int base = beg; base < end; base += 32) {
     const int i = base + lane;
@@ -150,7 +150,12 @@ __device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int 
       p = warp_sum(p);
       if (lane == j) s = p;
     }
-    if (i < end) y[r0 + i] = finish(s, ep.alpha, ep.beta, ep.bias, r0 + i, ep.relu);
+    if (i < end) {
+      float v = ep.alpha * s;
+      if (ep.beta != 0.0f) v = fmaf(ep.beta, base == beg ? bias0 : ep.bias[r0 + i], v);
+      if (ep.relu) v = fmaxf(v, 0.0f);
+      y[r0 + i] = v;
+    }
   }
 }
 
@@ -165,13 +170,16 @@ __device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDe
   int last = 0;
   if (lane == 0) {
     P.carry[t] = total;
-    __threadfence();
-    const unsigned int prev = atomicAdd(&P.counter[first], 1u);
+    // Release-ordered arrival (MEMBAR.ALL.GPU + ATOM): publishes carry[t] without the CCTL.IVALL that __threadfence()
+    // carries on sm_100.  That instruction invalidates the SM's whole L1 -- with ~10^4 chunks per SpMV the x lines the
+    // other CTAs of the SM had cached were being thrown away every few microseconds.
+    unsigned int prev;
+    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(P.counter + first) : "memory");
     last = (prev == (unsigned int)(d.nchunks - 1));
   }
   last = __shfl_sync(kFullMask, last, 0);
   if (!last) return;
-  __threadfence();
+  __threadfence();  // acquire side, once per split row: the carries below are also read past L1 (__ldcg)
   float s = 0.0f;
   for (int k = lane; k < d.nchunks; k += 32) s += __ldcg(P.carry + first + k);
   s = warp_sum(s);
@@ -235,13 +243,15 @@ __global__ void __launch_bounds__(kGroup, 8)
   const int rpw = (trows + kGroupWarps - 1) / kGroupWarps;
   const int beg = warp * rpw, end = min(trows, beg + rpw);
   int b0 = 0, e0 = 0;
+  float bias0 = 0.0f;
   if (beg + lane < end) {
     b0 = A.row_ptr[d.r0 + beg + lane];
     e0 = A.row_ptr[d.r0 + beg + lane + 1];
+    if (ep.beta != 0.0f) bias0 = ep.bias[d.r0 + beg + lane];
   }
   stream_products(A, gx, n0, d.n1, tid, ps, [&](int i, float p) { s_prod[i - n0] = p; });
   __syncthreads();
-  rows_from_products(A, d.r0, n0, beg, end, b0 - n0, e0 - n0, s_prod, lane, y, ep);
+  rows_from_products(A, d.r0, n0, beg, end, b0 - n0, e0 - n0, bias0, s_prod, lane, y, ep);
 }
 
 // ================================================================================================================
@@ -351,12 +361,14 @@ __global__ void __launch_bounds__(kGroup* kPsGroups, MINBLOCKS)
     const int rpw = (trows + kGroupWarps - 1) / kGroupWarps;
     const int beg = gw * rpw, end = min(trows, beg + rpw);
     int b0 = 0, e0 = 0;
+    float bias0 = 0.0f;
     if (beg + lane < end) {
       b0 = A.row_ptr[d.r0 + beg + lane] - n0;
       e0 = A.row_ptr[d.r0 + beg + lane + 1] - n0;
+      if (ep.beta != 0.0f) bias0 = ep.bias[d.r0 + beg + lane];
     }
     group_sync(g);
-    rows_from_products(A, d.r0, n0, beg, end, b0, e0, s_prod, lane, y, ep);
+    rows_from_products(A, d.r0, n0, beg, end, b0, e0, bias0, s_prod, lane, y, ep);
   }
   // the last group to run dry re-arms the tile counter for the next launch / graph replay
   if (gt == 0) {

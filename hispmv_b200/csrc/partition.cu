@@ -645,7 +645,8 @@ int tile_desc_device(const int32_t* d_row_ptr, const int32_t* d_tile_row, const 
 //   banded  = the probe compared >= 64 entry pairs and >= 3/4 of them were within 32 columns of the row above
 //   EMPTY       no nonzeros
 //   CSR_SCALAR / CSR_VECTOR(lanes)   row splitting not allowed (row_dist_net off): mean <= 2 / otherwise
-//   ROWSTAGE    regular and banded: row-major walk behind a TMA-staged stream
+//   ROWSTAGE    regular, banded and mean <= 64: row-major walk behind a TMA-staged stream (longer rows already
+//               give a nnz-major warp 32 column-sorted neighbours of one row, and would all be LONG tiles here)
 //   ADAPTIVE    everything else: nnz-major tiles, heavy rows chunked across CTAs
 // ------------------------------------------------------------------------------------------------
 void select_kernel(const RowStats& st, const ColProbe& probe, int allow_split_rows, int* kernel, int* lanes) {
@@ -673,7 +674,7 @@ void select_kernel(const RowStats& st, const ColProbe& probe, int allow_split_ro
   }
   const bool regular = heavy_nnz * 8 < st.nnz;
   const bool banded = probe.cmp >= 64 && probe.near * 4 >= probe.cmp * 3;
-  *kernel = (regular && banded) ? HISPMV_KERNEL_ROWSTAGE : HISPMV_KERNEL_ADAPTIVE;
+  *kernel = (regular && banded && mean <= 64) ? HISPMV_KERNEL_ROWSTAGE : HISPMV_KERNEL_ADAPTIVE;
 }
 
 // ROWSTAGE: `lanes` lanes per row, R = 256 / lanes rows per pass; the STREAM budget is R rows of average

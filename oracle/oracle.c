@@ -257,7 +257,7 @@ void oracle_select_kernel(int rows, int64_t nnz, const int64_t* hist, int64_t pr
   {
     const int regular = heavy_nnz * 8 < nnz;
     const int banded = probe_cmp >= 64 && probe_near * 4 >= probe_cmp * 3;
-    *kernel = (regular && banded) ? K_ROWSTAGE : K_ADAPTIVE;
+    *kernel = (regular && banded && mean <= 64) ? K_ROWSTAGE : K_ADAPTIVE;
   }
 }
 

@@ -196,7 +196,7 @@ def split_rows(rp, tr, tn):
     return out
 
 
-def adaptive_tiles(rp, B=2048, T=1024, CH=3072):
+def adaptive_tiles(rp, B=2048, T=1024, CH=4096):
     rp = np.ascontiguousarray(rp, np.int32)
     rows = rp.size - 1
     nt = oracle().oracle_adaptive_tiles(rows, rp, B, T, CH, None, None)

@@ -74,6 +74,7 @@ def main():
     ap.add_argument("--rowstage", default="", help="';'-separated LANES,B,T,CH quadruples ('auto' = planner default)")
     ap.add_argument("--hot", default="0", help="','-separated hot-column thresholds for the split L1 policy (0 = keep all)")
     ap.add_argument("--persist", default="", help="','-separated x-window sizes for the persistent adaptive kernel")
+    ap.add_argument("--only-auto", action="store_true", help="time only what the selector picks")
     ap.add_argument("--skip", default="", help="','-separated variant names to skip (adapt,rows,merge,vector,scalar)")
     args = ap.parse_args()
     torch.cuda.init()
@@ -86,6 +87,28 @@ def main():
         host_csr = None
         t0 = time.time()
         eng = Engine(0)
+        if name in ("g8192", "g3a", "gtall"):
+            # dense overlay: 8192^2 (cpu/run_gemv.sh shape), the MLP's dense layer, general_test.py's 50000 x 10000
+            nr, nc = {"g8192": (8192, 8192), "g3a": (8192, 4096), "gtall": (50000, 10000)}[name]
+            a = torch.rand(nr, nc, device="cuda") - 0.5
+            idx = eng.create_dense_handle_dev(a, nr, nc)
+            bytes_alg = 4 * nr * nc + 4 * nc + 4 * nr
+            x = torch.rand(nc, device="cuda") + 0.5
+            b = torch.rand(nr, device="cuda")
+            y = torch.empty(nr, device="cuda")
+            med, mn = time_runs(eng, idx, x, b, y, args.iters, flush)
+            ref = 0.85 * (a.double() @ x.double()) - 2.06 * b.double()
+            scale = 0.85 * (a.double().abs() @ x.double().abs()) + 2.06 * b.double().abs()
+            err = float(((y.double() - ref).abs() / scale).max())
+            gbs = bytes_alg / (med * 1e-3) / 1e9
+            results.append(dict(config=name, kernel="gemv", lanes=0, tile="", ms_med=med, ms_min=mn, gbs=gbs, frac=gbs / peak,
+                                gflops=(2 * nr * nc + nr) / (med * 1e-3) / 1e9, err=err, rows=nr, cols=nc, nnz=nr * nc))
+            print(f"## {name}: dense {nr}x{nc} bytes_alg={bytes_alg/1e6:.1f}MB", flush=True)
+            print(f"{name:14s} gemv   lanes= 0 tile={'':26s} med={med:8.4f}ms min={mn:8.4f}ms {gbs:8.1f} GB/s "
+                  f"frac={gbs/peak:5.3f} err={err:.2e}", flush=True)
+            del a
+            eng.close()
+            continue
         if name in ("c2", "c4", "c5"):
             spec = {"c2": synth.c2_powerlaw, "c4": synth.c4_stencil, "c5": synth.c5_uniform}[name](args.scale)
             d = synth.DeviceCSR(spec)
@@ -132,6 +155,8 @@ def main():
         variants += [("vector", capi.KERNEL_CSR_VECTOR, l, "") for l in (2, 4, 8, 16, 32)]
         variants += [("scalar", capi.KERNEL_CSR_SCALAR, 0, "")]
         skip = set(args.skip.split(","))
+        if args.only_auto:
+            variants = [("auto", capi.KERNEL_AUTO, 0, "")]
         for kname, k, lanes, tile in variants:
             if kname in skip:
                 continue
@@ -161,8 +186,11 @@ def main():
                 print(f"{spec.name} {kname}{lanes or ''}{('/' + tile) if tile else ''}: FAILED {ex}", flush=True)
                 continue
             gbs = bytes_alg / (med * 1e-3) / 1e9
+            chosen = eng.matrix_info(idx)
             rec = dict(config=spec.name, kernel=kname, lanes=lanes, tile=tile, ms_med=med, ms_min=mn, gbs=gbs,
-                       frac=gbs / peak, gflops=2 * (info["nnz"] + spec.rows) / (med * 1e-3) / 1e9, err=err)
+                       frac=gbs / peak, gflops=2 * (info["nnz"] + spec.rows) / (med * 1e-3) / 1e9, err=err,
+                       rows=spec.rows, cols=spec.cols, nnz=info["nnz"], planned=chosen["kernel_name"],
+                       planned_lanes=chosen["vector_lanes"], tile_items=chosen["tile_items"])
             results.append(rec)
             print(f"{spec.name:14s} {kname:6s} lanes={lanes:2d} tile={tile:26s} med={med:8.4f}ms min={mn:8.4f}ms "
                   f"{gbs:8.1f} GB/s frac={gbs/peak:5.3f} err={err:.2e}", flush=True)

@@ -160,6 +160,12 @@ __device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int 
 }
 
 // ---- the end of a LONG tile: warp 0 of the group holds the chunk's total in every lane ---------------------------
+// Split rows meet without a fence on the arrival path: carry[] slots hold a sentinel (a NaN payload no arithmetic
+// produces) until their chunk writes its partial; the chunk that arrives last at the row's counter reads the slots in
+// chunk order past L1, waiting out any slot whose write is still in flight, adds them in that order and re-arms slots
+// and counter for the next launch.  (The first version published carry[] with __threadfence(): on sm_100 that is
+// MEMBAR.SC + CCTL.IVALL -- a ~2 k-cycle stall and an L1 flush per chunk.)
+constexpr unsigned int kCarryEmpty = kCarryEmptyBits;
 __device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDesc& d, int64_t t, float total, int lane,
                                              float* __restrict__ y, const Epilogue& ep) {
   if (d.nchunks == 1) {
@@ -169,19 +175,25 @@ __device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDe
   const int64_t first = t - d.chunk;  // tile id of this row's chunk 0
   int last = 0;
   if (lane == 0) {
-    P.carry[t] = total;
-    // Release-ordered arrival (MEMBAR.ALL.GPU + ATOM): publishes carry[t] without the CCTL.IVALL that __threadfence()
-    // carries on sm_100.  That instruction invalidates the SM's whole L1 -- with ~10^4 chunks per SpMV the x lines the
-    // other CTAs of the SM had cached were being thrown away every few microseconds.
-    unsigned int prev;
-    asm volatile("atom.release.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(P.counter + first) : "memory");
+    unsigned int bits = __float_as_uint(total);
+    if (bits == kCarryEmpty) bits = 0x7fffffffu;  // a NaN is a NaN
+    __stcg(reinterpret_cast<unsigned int*>(P.carry) + t, bits);
+    const unsigned int prev = atomicAdd(&P.counter[first], 1u);
     last = (prev == (unsigned int)(d.nchunks - 1));
   }
   last = __shfl_sync(kFullMask, last, 0);
   if (!last) return;
-  __threadfence();  // acquire side, once per split row: the carries below are also read past L1 (__ldcg)
+  unsigned int* slots = reinterpret_cast<unsigned int*>(P.carry) + first;
   float s = 0.0f;
-  for (int k = lane; k < d.nchunks; k += 32) s += __ldcg(P.carry + first + k);
+  for (int k = lane; k < d.nchunks; k += 32) {
+    unsigned int bits = __ldcg(slots + k);
+    while (bits == kCarryEmpty) {
+      __nanosleep(40);
+      bits = __ldcg(slots + k);
+    }
+    s += __uint_as_float(bits);
+    __stcg(slots + k, kCarryEmpty);
+  }
   s = warp_sum(s);
   if (lane == 0) {
     y[d.r0] = finish(s, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu);
@@ -452,6 +464,263 @@ __global__ void __launch_bounds__(kGroup)
   }
 }
 
+// ================================================================================================================
+// warp-specialised persistent pipeline (one CTA of 992 threads per SM)
+// ================================================================================================================
+// The one-CTA-per-tile kernel serialises, inside every CTA, a DRAM round trip (col/val), an L2 round trip (gathers),
+// a barrier and the row reduction (with two more DRAM round trips for row extents and bias); its ncu profile shows
+// the SM's L1-miss request path -- the real ceiling on gather-heavy matrices -- busy only ~65-70 % of the time.
+// Here a producer warp keeps a ring of tile-sized stages full by TMA, so that everything a tile needs is already in
+// shared memory when a team of warps picks it up:
+//   warp 30         producer.  CTA b owns tiles b, b+G, b+2G, ... (strided: statistically balanced, deterministic,
+//                   no atomics).  Its 32 lanes fetch 32 descriptors at a time; lane 0 then waits for a free stage and
+//                   fills it with up to four bulk copies: col, val, the tile's row_ptr slice and its bias slice.
+//   teams           kPipeTeams x kPipeTeamWarps warps; a team takes every kPipeTeams-th stage: columns from shared
+//                   memory, U gathers in flight per thread, product written over val; a named barrier over the team;
+//                   then each warp reduces a slice of the tile's rows out of shared memory (LONG chunks: per-warp
+//                   partials, warp 0 finishes the chunk) and the stage goes back to the producer.  While one team
+//                   reduces, the others gather, so the miss path always has a burst in flight.
+// (A first version with separate reduce warps was reduce-bound: 7 warps need ~3 k cycles for a tile of short rows.)
+// full[s]  (1 arrival + TMA bytes)  producer -> team          empty[s] (team warps)  team -> producer
+constexpr int kPipeTeams = 3;
+constexpr int kPipeTeamWarps = 10;
+constexpr int kPipeTeamThreads = kPipeTeamWarps * 32;
+constexpr int kPipeProducerWarp = kPipeTeams * kPipeTeamWarps;  // warp 30: the arbiter favours high warp ids
+constexpr int kPipeThreads = (kPipeProducerWarp + 1) * 32;
+
+#ifdef HISPMV_DIAG
+__device__ long long g_pipe_dbg[8 * 512];  // [event][tile k] clock64 stamps of CTA 0
+#define PIPE_STAMP(ev, k) do { if (blockIdx.x == 0 && (k) < 512) g_pipe_dbg[(ev) * 512 + (k)] = clock64(); } while (0)
+#else
+#define PIPE_STAMP(ev, k) do { } while (0)
+#endif
+
+template <int CAP, int RCAP>
+struct PipeStage {
+  __align__(128) int col[CAP + 8];
+  __align__(16) float val[CAP + 8];
+  __align__(16) int rp[RCAP + 8];      // row_ptr[r0 & ~3 ...]
+  __align__(16) float bias[RCAP + 8];  // bias[r0 & ~3 ...]
+  __align__(16) TileDesc desc;
+  float partial[kPipeTeamWarps];
+};
+template <int STAGES>
+struct PipeBars {
+  uint64_t full[STAGES], empty[STAGES];
+};
+
+// one lane polls, the warp follows: keeps hundreds of threads from hammering the same mbarrier
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int lane) {
+  if (lane == 0) mbar_wait_backoff(bar, parity);
+  __syncwarp();
+}
+__device__ __forceinline__ void team_sync(int team) {
+  switch (team) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"n"(kPipeTeamThreads) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"n"(kPipeTeamThreads) : "memory"); break;
+    default: asm volatile("bar.sync 3, %0;" ::"n"(kPipeTeamThreads) : "memory"); break;
+  }
+}
+static_assert(kPipeTeams == 3, "team_sync names three barriers");
+
+__device__ __forceinline__ TileDesc desc_or_end(const AdaptivePlan& P, int64_t t) {
+  TileDesc d;
+  if (t < P.num_tiles) {
+    d = load_desc(P.desc + t);
+  } else {
+    d.r0 = d.r1 = d.n0 = d.n1 = d.nchunks = d.pad = 0;
+    d.chunk = -1;
+    d.tile = -1;  // end marker
+  }
+  return d;
+}
+__device__ __forceinline__ TileDesc shfl_desc(const TileDesc& d, int src) {
+  TileDesc o;
+  o.r0 = __shfl_sync(kFullMask, d.r0, src);
+  o.r1 = __shfl_sync(kFullMask, d.r1, src);
+  o.n0 = __shfl_sync(kFullMask, d.n0, src);
+  o.n1 = __shfl_sync(kFullMask, d.n1, src);
+  o.chunk = __shfl_sync(kFullMask, d.chunk, src);
+  o.nchunks = __shfl_sync(kFullMask, d.nchunks, src);
+  o.tile = __shfl_sync(kFullMask, d.tile, src);
+  o.pad = 0;
+  return o;
+}
+
+template <int CAP, int RCAP, int STAGES, bool SPLIT>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+    spmv_pipeline_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
+  using Stage = PipeStage<CAP, RCAP>;
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  Stage* stages = reinterpret_cast<Stage*>(s_raw);
+  PipeBars<STAGES>* bars = reinterpret_cast<PipeBars<STAGES>*>(s_raw + sizeof(Stage) * STAGES);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // bias travels by TMA when it is 16-byte aligned (always, for cudaMalloc'ed vectors); only whole 4-float groups
+  // inside the vector are copied, a ragged last group is read directly
+  const bool use_bias = ep.beta != 0.0f;
+  const bool bias_tma = use_bias && (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0;
+  const int bias_full = A.rows & ~3;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], kPipeTeamWarps);
+    }
+  }
+  __syncthreads();
+
+  if (warp == kPipeProducerWarp) {
+    // ------------------------------------------------------------------------------------------- producer
+    const uint64_t ps = policy_evict_first(), pn = policy_evict_normal();
+    int k = 0, ends = 0;
+    for (int64_t kb = 0; ends < kPipeTeams; kb += 32) {
+      const TileDesc mine = desc_or_end(P, (int64_t)blockIdx.x + (kb + lane) * (int64_t)gridDim.x);
+      for (int j = 0; j < 32 && ends < kPipeTeams; ++j, ++k) {
+        const TileDesc d = shfl_desc(mine, j);
+        const int s = k % STAGES, u = k / STAGES;
+        Stage& st = stages[s];
+        // lane 0 owns the barriers; the four copies of a tile are issued by four different lanes (issuing one
+        // cp.async.bulk costs the issuing thread several hundred cycles: one lane doing all four was the bottleneck)
+        if (lane == 0) {
+          PIPE_STAMP(0, k);
+          if (u > 0) mbar_wait(&bars->empty[s], (u - 1) & 1);
+          PIPE_STAMP(1, k);
+          st.desc = d;
+        }
+        if (d.tile < 0) {  // one end marker per team
+          if (lane == 0) mbar_arrive(&bars->full[s]);
+          ++ends;
+          continue;
+        }
+        const int a0 = d.n0 & ~3;
+        const int cnt = ((d.n1 + 3) & ~3) - a0;
+        uint32_t bytes = (uint32_t)cnt * 8u;
+        int ra = 0, rcnt = 0, bcnt = 0;
+        if (d.chunk < 0) {
+          ra = d.r0 & ~3;
+          rcnt = ((d.r1 + 1 + 3) & ~3) - ra;  // row_ptr[ra, ra + rcnt): the allocation is padded by 4 entries
+          bytes += (uint32_t)rcnt * 4u;
+          if (bias_tma) {
+            bcnt = min((d.r1 + 3) & ~3, bias_full) - ra;
+            if (bcnt < 0) bcnt = 0;
+            bytes += (uint32_t)bcnt * 4u;
+          }
+        }
+        if (lane == 0) {
+          if (bytes > 0) mbar_expect_tx(&bars->full[s], bytes);
+          else mbar_arrive(&bars->full[s]);
+        }
+        __syncwarp();
+        if (lane == 0 && cnt > 0) bulk_g2s_hint(st.col, A.col + a0, (uint32_t)cnt * 4u, &bars->full[s], ps);
+        if (lane == 1 && cnt > 0) bulk_g2s_hint(st.val, A.val + a0, (uint32_t)cnt * 4u, &bars->full[s], ps);
+        if (lane == 2 && rcnt > 0) bulk_g2s_hint(st.rp, A.row_ptr + ra, (uint32_t)rcnt * 4u, &bars->full[s], pn);
+        if (lane == 3 && bcnt > 0) bulk_g2s_hint(st.bias, ep.bias + ra, (uint32_t)bcnt * 4u, &bars->full[s], pn);
+      }
+    }
+    return;
+  }
+
+  // ----------------------------------------------------------------------------------------------- teams
+  const uint64_t pk = policy_evict_last();
+  const GatherL1<SPLIT> gx{x, P.hot_cols, pk};
+  const int team = warp / kPipeTeamWarps, tw = warp % kPipeTeamWarps;
+  const int tt = tw * 32 + lane;
+  constexpr int U = CAP / kPipeTeamThreads;  // gathers in flight per thread
+  static_assert(CAP % kPipeTeamThreads == 0, "tile capacity must be a multiple of the team size");
+  for (int k = team;; k += kPipeTeams) {
+    const int s = k % STAGES, u = k / STAGES;
+    Stage& st = stages[s];
+    warp_wait(&bars->full[s], u & 1, lane);
+    if (tw == 0 && lane == 0) PIPE_STAMP(2, k);
+    const TileDesc d = st.desc;
+    if (d.tile < 0) break;
+    const int a0 = d.n0 & ~3;
+    const int k0 = d.n0 - a0, k1 = k0 + (d.n1 - d.n0);
+    int c[U];
+    float xv[U];
+#pragma unroll
+    for (int q = 0; q < U; ++q) {
+      const int i = k0 + tt + q * kPipeTeamThreads;
+      c[q] = i < k1 ? st.col[i] : -1;
+    }
+#pragma unroll
+    for (int q = 0; q < U; ++q) xv[q] = c[q] >= 0 ? gx(c[q]) : 0.0f;
+    if (d.chunk >= 0) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        if (c[q] >= 0) acc = fmaf(st.val[k0 + tt + q * kPipeTeamThreads], xv[q], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) st.partial[tw] = acc;
+      team_sync(team);
+      if (tw == 0) {
+        float total = lane < kPipeTeamWarps ? st.partial[lane] : 0.0f;
+        total = warp_sum(total);
+        finish_chunk(P, d, d.tile, total, lane, y, ep);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < U; ++q)
+        if (c[q] >= 0) st.val[k0 + tt + q * kPipeTeamThreads] *= xv[q];
+      team_sync(team);
+      if (tw == 0 && lane == 0) PIPE_STAMP(3, k);
+      const int ra = d.r0 & ~3;
+      const int trows = d.r1 - d.r0;
+      const int rpw = (trows + kPipeTeamWarps - 1) / kPipeTeamWarps;
+      const int beg = tw * rpw, end = min(trows, beg + rpw);
+      const int* rp = st.rp + (d.r0 - ra);      // rp[i] = row_ptr[r0 + i]
+      const float* bs = st.bias + (d.r0 - ra);  // bs[i] = bias[r0 + i] (where copied)
+      const float* prod = st.val;               // product of nonzero n at prod[n - a0]
+      for (int base = beg; base < end; base += 32) {
+        const int i = base + lane;
+        int b = 0, e = 0;
+        if (i < end) {
+          b = rp[i] - a0;
+          e = rp[i + 1] - a0;
+        }
+        const int len = e - b;
+        float sum = 0.0f;
+        if (len <= kSerialRow) {
+#pragma unroll
+          for (int q = 0; q < kSerialRow; ++q)
+            if (q < len) sum += prod[b + q];
+        }
+        unsigned big = __ballot_sync(kFullMask, len > kSerialRow);
+        while (big) {
+          const int j = __ffs(big) - 1;
+          big &= big - 1;
+          const int bj = __shfl_sync(kFullMask, b, j), ej = __shfl_sync(kFullMask, e, j);
+          float p = 0.0f;
+          for (int q = bj + lane; q < ej; q += 32) p += prod[q];
+          p = warp_sum(p);
+          if (lane == j) sum = p;
+        }
+        if (i < end) {
+          float v = ep.alpha * sum;
+          if (use_bias) {
+            const int r = d.r0 + i;
+            v = fmaf(ep.beta, (bias_tma && r < bias_full) ? bs[i] : ep.bias[r], v);
+          }
+          if (ep.relu) v = fmaxf(v, 0.0f);
+          y[d.r0 + i] = v;
+        }
+      }
+    }
+    __syncwarp();
+    if (tw == 0 && lane == 0) PIPE_STAMP(5, k);
+    if (lane == 0) mbar_arrive(&bars->empty[s]);
+  }
+}
+
+#ifdef HISPMV_DIAG
+}  // namespace
+}  // namespace hispmv
+extern "C" int hispmv_debug_pipe(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, hispmv::g_pipe_dbg, sizeof(long long) * 8 * 512);
+}
+namespace hispmv {
+namespace {
+#endif
+
 // ---- launch helpers ----------------------------------------------------------------------------------------------
 template <int CAP, int MINBLOCKS>
 int launch_persistent_inst(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
@@ -548,6 +817,36 @@ int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const flo
   if (need <= 2048) return launch_persistent_cap<2048>(A, P, x, y, ep, sm_count, s);
   if (need <= 3072) return launch_persistent_cap<3072>(A, P, x, y, ep, sm_count, s);
   return launch_persistent_cap<4096>(A, P, x, y, ep, sm_count, s);
+}
+
+namespace {
+template <int CAP, int RCAP, int STAGES, bool SPLIT>
+int launch_pipeline_inst(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
+                         cudaStream_t s) {
+  auto k = spmv_pipeline_kernel<CAP, RCAP, STAGES, SPLIT>;
+  const size_t smem = sizeof(PipeStage<CAP, RCAP>) * STAGES + sizeof(PipeBars<STAGES>);
+  HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = (int)std::min<int64_t>(P.num_tiles, sm_count);
+  k<<<grid, kPipeThreads, smem, s>>>(A, P, x, y, ep);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+}  // namespace
+
+int launch_pipeline(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
+                    cudaStream_t s) {
+  if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
+  int st = check_plan(P, kPipelineCap, "pipeline");
+  if (st != HISPMV_OK) return st;
+  if (P.chunk_nnz > kPipelineCap || P.stream_items > kPipelineRows) {
+    set_error("pipeline: tiles must fit a stage (chunk_nnz <= 2048, stream_items <= 1536)");
+    return HISPMV_ERR_ARG;
+  }
+  // CAP nonzeros + RCAP row extents per stage: 26.6 KB, five stages = 133 KB (shared memory beyond ~190 KB per SM
+  // throttles the L1-miss path)
+  if (P.hot_cols != 0x7fffffff)
+    return launch_pipeline_inst<kPipelineCap, kPipelineRows + 8, 5, true>(A, P, x, y, ep, sm_count, s);
+  return launch_pipeline_inst<kPipelineCap, kPipelineRows + 8, 5, false>(A, P, x, y, ep, sm_count, s);
 }
 
 int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,

@@ -52,6 +52,7 @@ struct Matrix {
   int32_t long_threshold = 0, chunk_nnz = 0;
   int32_t hot_cols = 0x7fffffff;        // ADAPTIVE / ROWSTAGE: split L1 policy threshold for x gathers
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
+  bool pipeline = false;                // ADAPTIVE: warp-specialised persistent pipeline (TMA ring)
   ColProbe probe{};                     // column-locality probe (selector input)
   // dense
   float* d_a = nullptr;
@@ -218,6 +219,15 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     }
     m->hot_cols = 0x7fffffff;
     m->persistent = false;
+    m->pipeline = false;
+    if (const char* e = getenv("HISPMV_PIPELINE")) {
+      if (atoi(e) > 0 && m->kernel == HISPMV_KERNEL_ADAPTIVE) {
+        m->pipeline = true;
+        m->tile_items = std::min(m->tile_items, kPipelineRows);
+        m->long_threshold = std::min(m->long_threshold, kPipelineCap - m->tile_items);
+        m->chunk_nnz = std::min(m->chunk_nnz, kPipelineCap);
+      }
+    }
     if (const char* e = getenv("HISPMV_PERSIST")) {  // research switch: the persistent x-window variant (never auto)
       const int h = atoi(e);
       if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
@@ -239,6 +249,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     if (st != HISPMV_OK) return st;
     const size_t n = (size_t)std::max<int64_t>(m->num_tiles, 1) * 2;
     HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, n * sizeof(float)));
+    HISPMV_CUDA(fill_u32_device(reinterpret_cast<uint32_t*>(m->d_carry), kCarryEmptyBits, n, c->stream));
     // two lanes of arrival counters, then two lanes of 4 scheduler words for the persistent kernel
     HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, (n + 8) * sizeof(unsigned int)));
     HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, (n + 8) * sizeof(unsigned int), c->stream));
@@ -359,7 +370,7 @@ int add_csr_common(hispmv_ctx* c, const int32_t* row_ptr, const int32_t* col, co
   int st = check_capacity(c, nnz * 8 + ((int64_t)rows + 1) * 4);
   if (st != HISPMV_OK) return st;
   int32_t* rp = nullptr;
-  HISPMV_CUDA(cudaMalloc((void**)&rp, ((size_t)rows + 1) * 4));
+  HISPMV_CUDA(cudaMalloc((void**)&rp, ((size_t)rows + 1 + 4) * 4));  // +4: 16-byte TMA windows may overrun the end
   st = check_cuda(cudaMemcpyAsync(rp, row_ptr, ((size_t)rows + 1) * 4, kind, c->stream), "copy row_ptr", __FILE__, __LINE__);
   int32_t* cl = nullptr;
   float* vl = nullptr;
@@ -465,6 +476,7 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.hot_cols = m->hot_cols;
       P.sched = m->d_counter + (size_t)std::max<int64_t>(m->num_tiles, 1) * 2 + 4 * (size_t)lane;
       if (m->kernel == HISPMV_KERNEL_ROWSTAGE) return launch_rowstage(A, P, m->lanes, d_x, d_y, ep, s);
+      if (m->pipeline) return launch_pipeline(A, P, d_x, d_y, ep, c->sm_count, s);
       if (m->persistent) return launch_adaptive_persistent(A, P, d_x, d_y, ep, c->sm_count, s);
       return launch_adaptive(A, P, d_x, d_y, ep, s);
     }

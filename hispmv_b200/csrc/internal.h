@@ -114,6 +114,9 @@ struct ColProbe {
 constexpr int32_t kProbeSamples = 8192;
 int col_probe_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, ColProbe* out, cudaStream_t stream);
 
+// carry[] slots of split rows hold this NaN payload until their chunk has written its partial (adaptive.cu)
+constexpr uint32_t kCarryEmptyBits = 0x7fc0dead;
+cudaError_t fill_u32_device(uint32_t* p, uint32_t value, size_t n, cudaStream_t stream);
 // TileDesc records from tile_row / tile_chunk / row_ptr (one thread per tile); d_desc cudaMalloc'ed by the callee.
 int tile_desc_device(const int32_t* d_row_ptr, const int32_t* d_tile_row, const int32_t* d_tile_chunk,
                      int64_t num_tiles, int32_t chunk_nnz, TileDesc** d_desc, cudaStream_t stream);
@@ -141,6 +144,11 @@ constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdapt
 int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
                                int sm_count, cudaStream_t s);
 constexpr int kPersistentMaxHot = 40960;  // floats of x the window may hold next to the four group buffers
+// Warp-specialised persistent pipeline (TMA producer / gather teams / reduce warps).  A stage holds one tile:
+// stream_items + long_threshold <= kPipelineCap, chunk_nnz <= kPipelineCap, stream_items <= kPipelineRows.
+constexpr int kPipelineCap = 1920, kPipelineRows = 1408;  // CAP = 6 gathers x 320 team threads
+int launch_pipeline(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
+                    cudaStream_t s);
 // Row-major STREAM tiles behind a TMA-staged stream (regular rows with column locality); `lanes` lanes per row.
 int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
                     cudaStream_t s);

@@ -317,7 +317,7 @@ int coo_to_csr_device(const int32_t* d_rows, const int32_t* d_cols, const float*
     }
   }
 
-  HISPMV_CUDA(cudaMalloc((void**)d_row_ptr, ((size_t)rows + 1) * sizeof(int32_t)));
+  HISPMV_CUDA(cudaMalloc((void**)d_row_ptr, ((size_t)rows + 1 + 4) * sizeof(int32_t)));  // +4: TMA windows
   st = check_cuda(cudaMalloc((void**)d_col, pad * sizeof(int32_t)), "cudaMalloc(col)", __FILE__, __LINE__);
   if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)d_val, pad * sizeof(float)), "cudaMalloc(val)", __FILE__, __LINE__);
   if (st != HISPMV_OK) {
@@ -446,7 +446,7 @@ int csr_slice_device(const int32_t* d_row_ptr, const int32_t* d_col, const float
   const int32_t n_rows = row_end - row_begin;
   *o_nnz = nnz;
   *o_row_ptr = nullptr;
-  HISPMV_CUDA(cudaMalloc((void**)o_row_ptr, ((size_t)n_rows + 1) * sizeof(int32_t)));
+  HISPMV_CUDA(cudaMalloc((void**)o_row_ptr, ((size_t)n_rows + 1 + 4) * sizeof(int32_t)));  // +4: TMA windows
   rebase_row_ptr_kernel<<<blocks_for((int64_t)n_rows + 1, 256), 256, 0, stream>>>(d_row_ptr, row_begin, n_rows,
                                                                                   *o_row_ptr);
   int st = alloc_padded_nnz_arrays(d_col + h[0], d_val + h[0], nnz, cudaMemcpyDeviceToDevice, o_col, o_val, stream);
@@ -618,6 +618,17 @@ __global__ void tile_desc_kernel(const int32_t* __restrict__ rp, const int32_t* 
   desc[t] = d;
 }
 }  // namespace
+
+namespace {
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+}  // namespace
+cudaError_t fill_u32_device(uint32_t* p, uint32_t value, size_t n, cudaStream_t stream) {
+  if (n) fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(p, value, n);
+  return cudaGetLastError();
+}
 
 int tile_desc_device(const int32_t* d_row_ptr, const int32_t* d_tile_row, const int32_t* d_tile_chunk,
                      int64_t num_tiles, int32_t chunk_nnz, TileDesc** d_desc, cudaStream_t stream) {

@@ -202,6 +202,38 @@ def test_persistent_window_kernel(eng, window, monkeypatch):
     _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_pipeline_kernel(eng, seed, monkeypatch):
+    """The warp-specialised persistent pipeline (TMA producer / gather teams / reduce warps over an mbarrier ring):
+    same tiles as the one-CTA-per-tile kernel, results within tolerance and bit-identical from run to run."""
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_PIPELINE", "1")
+    rng = np.random.default_rng(50 + seed)
+    rows, cols = 40000, 60000
+    lens = np.minimum(rng.zipf(1.6, rows), 40000)
+    heavy = rng.integers(1, rows - 2, 8)
+    lens[heavy] = rng.integers(1024, 30000, 8)
+    lens[rng.integers(0, rows, 3000)] = 0
+    lens[5000:9000] = 0                         # tiles made of empty rows only (no bytes to stage)
+    if seed == 1:
+        lens[:] = np.minimum(lens, 3)           # very short rows: many rows per tile
+        lens[17] = 20000
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = (rng.random(r.size) ** 3 * cols).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_ADAPTIVE)
+    info = eng.matrix_info(idx)
+    assert info["chunk_nnz"] <= 3072
+    rp, ci, vv = eng.plan_csr(idx)
+    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, info["tile_items"], info["long_threshold"], info["chunk_nnz"])
+    assert np.array_equal(eng.plan_tile_chunks(idx), tc2) and np.array_equal(eng.plan_split_rows(idx), sp2)
+    ys = [_check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7)) for _ in range(3)]
+    assert np.array_equal(ys[0].view(np.uint32), ys[1].view(np.uint32))
+    assert np.array_equal(ys[0].view(np.uint32), ys[2].view(np.uint32))
+    _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(8), alpha=1.0, beta=0.0)
+
+
 @pytest.mark.parametrize("kind,expect", [("banded", "rowstage"), ("banded_heavy", "adaptive"), ("random", "adaptive"),
                                          ("stencil", "rowstage")])
 def test_selector_bit_exact(eng, kind, expect):

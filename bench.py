@@ -226,7 +226,9 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(comp)
+    t_host = time.perf_counter()
     steps_device(args.steps)
+    host_enqueue_ms = (time.perf_counter() - t_host) * 1e3 / args.steps   # CPU time to enqueue one step
     comm.synchronize()
     e1.record(comp)
     barrier()
@@ -317,6 +319,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(4 * spec.rows), "ms_per_step": e2e_ms,
                     "api": "hispmv_run (host x, bias -> host y), pinned host memory"},
             "phases": {"spmv_ms_max_over_ranks": kernel_ms_max, "x_broadcast_ms": bcast_ms,
+                       "host_enqueue_ms_per_step": host_enqueue_ms,
                        "spmv_only_gflops": flops_step / (kernel_ms_max * 1e-3) / 1e9,
                        "note": "value includes the per-step x broadcast (pipelined under the previous SpMV); "
                                "spmv_only is the same step with x already resident"},

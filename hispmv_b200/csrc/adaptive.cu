@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(kGroup, 8)
   __shared__ float s_prod[CAP];
   __shared__ float s_red[kGroupWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t t = blockIdx.x;
+  const int64_t t = P.tile_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
   const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
   const GatherL1<SPLIT> gx{x, P.hot_cols, pk};
@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kGroup)
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t t = blockIdx.x;
+  const int64_t t = P.tile_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
   const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
   const GatherL1<false> gx{x, P.hot_cols, pk};  // banded matrices reuse every gathered line a few rows later
@@ -750,7 +750,9 @@ int launch_rowstage_inst(const CsrDev& A, const AdaptivePlan& P, const float* x,
   auto k = spmv_rowstage_kernel<CAP, LANES>;
   constexpr int smem = (CAP + 8) * 8;
   HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  k<<<(int)P.num_tiles, kGroup, smem, s>>>(A, P, x, y, ep);
+  const int grid = (int)(P.tile_count >= 0 ? P.tile_count : P.num_tiles);
+  if (grid <= 0) return HISPMV_OK;
+  k<<<grid, kGroup, smem, s>>>(A, P, x, y, ep);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }
@@ -788,7 +790,8 @@ int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, floa
   int st = check_plan(P, 4096, "adaptive");
   if (st != HISPMV_OK) return st;
   const int need = P.stream_items + P.long_threshold;
-  const int grid = (int)P.num_tiles;
+  const int grid = (int)(P.tile_count >= 0 ? P.tile_count : P.num_tiles);
+  if (grid <= 0) return HISPMV_OK;
   const bool split = P.hot_cols != 0x7fffffff;
   if (need <= 2048) {
     if (split) spmv_adaptive_kernel<2048, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);

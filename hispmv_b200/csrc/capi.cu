@@ -49,6 +49,7 @@ struct Matrix {
   int32_t* d_tile_chunk = nullptr;      // ADAPTIVE
   unsigned int* d_counter = nullptr;    // ADAPTIVE (two lanes, like d_carry)
   TileDesc* d_desc = nullptr;           // ADAPTIVE / ROWSTAGE: resolved tile records
+  std::vector<int32_t> h_tile_row, h_tile_chunk;  // host copies: row ranges for the pipelined host-buffer call
   int32_t long_threshold = 0, chunk_nnz = 0;
   int32_t hot_cols = 0x7fffffff;        // ADAPTIVE / ROWSTAGE: split L1 policy threshold for x gathers
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
@@ -102,7 +103,9 @@ struct hispmv_ctx {
   int flags = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;  // second lane for pipelined linear()
+  cudaStream_t stream2 = nullptr;  // second lane for pipelined linear(); H2D lane of the pipelined run()
+  cudaStream_t stream3 = nullptr;  // D2H lane of the pipelined run()
+  cudaEvent_t ev_pipe[2 * 8 + 1] = {};  // x ready, bias chunk ready x8, kernel chunk done x8
   cudaEvent_t ev_bias = nullptr;
   int shard_part = 0, shard_parts = 1;
   int64_t mem_limit = 0;
@@ -247,6 +250,13 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     st = tile_desc_device(m->d_row_ptr, m->d_tile_row, m->d_tile_chunk, m->num_tiles, m->chunk_nnz, &m->d_desc,
                           c->stream);
     if (st != HISPMV_OK) return st;
+    m->h_tile_row.assign((size_t)m->num_tiles + 1, 0);
+    m->h_tile_chunk.assign((size_t)std::max<int64_t>(m->num_tiles, 1), -1);
+    HISPMV_CUDA(cudaMemcpyAsync(m->h_tile_row.data(), m->d_tile_row, (size_t)(m->num_tiles + 1) * 4,
+                                cudaMemcpyDeviceToHost, c->stream));
+    if (m->num_tiles)
+      HISPMV_CUDA(cudaMemcpyAsync(m->h_tile_chunk.data(), m->d_tile_chunk, (size_t)m->num_tiles * 4,
+                                  cudaMemcpyDeviceToHost, c->stream));
     const size_t n = (size_t)std::max<int64_t>(m->num_tiles, 1) * 2;
     HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, n * sizeof(float)));
     HISPMV_CUDA(fill_u32_device(reinterpret_cast<uint32_t*>(m->d_carry), kCarryEmptyBits, n, c->stream));
@@ -427,7 +437,7 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
 // `lane` selects one of the two carry / counter sets so that linear()'s two stream lanes never share them.
 // Device-pointer callers get lane 0: one run in flight per matrix handle, as with the reference's xrt::run.
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
-               int relu, cudaStream_t s, int lane = 0) {
+               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1) {
   Epilogue ep{alpha, beta, d_bias, relu};
   if (beta != 0.0f && !d_bias) {
     set_error("run: bias is required when beta != 0");
@@ -474,6 +484,8 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.carry = m->d_carry + (size_t)lane * m->num_tiles;
       P.counter = m->d_counter + (size_t)lane * m->num_tiles;
       P.hot_cols = m->hot_cols;
+      P.tile_begin = tile_begin;
+      P.tile_count = tile_count;
       P.sched = m->d_counter + (size_t)std::max<int64_t>(m->num_tiles, 1) * 2 + 4 * (size_t)lane;
       if (m->kernel == HISPMV_KERNEL_ROWSTAGE) return launch_rowstage(A, P, m->lanes, d_x, d_y, ep, s);
       if (m->pipeline) return launch_pipeline(A, P, d_x, d_y, ep, c->sm_count, s);
@@ -527,6 +539,9 @@ int hispmv_create(hispmv_ctx** out, int device_id, int flags) {
   int st = check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
   if (st == HISPMV_OK) st = check_cuda(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
   if (st == HISPMV_OK) st = check_cuda(cudaEventCreateWithFlags(&c->ev_bias, cudaEventDisableTiming), "event", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamCreateWithFlags(&c->stream3, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
+  for (auto& e : c->ev_pipe)
+    if (st == HISPMV_OK) st = check_cuda(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "event", __FILE__, __LINE__);
   if (st != HISPMV_OK) {
     delete c;
     return st;
@@ -549,6 +564,9 @@ void hispmv_destroy(hispmv_ctx* c) {
   cudaEventDestroy(c->ev_bias);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->stream2);
+  if (c->stream3) cudaStreamDestroy(c->stream3);
+  for (auto& e : c->ev_pipe)
+    if (e) cudaEventDestroy(e);
   delete c;
 }
 
@@ -670,6 +688,7 @@ int hispmv_sync(hispmv_ctx* c) {
   DeviceGuard g(c->device);
   HISPMV_CUDA(cudaStreamSynchronize(c->stream));
   HISPMV_CUDA(cudaStreamSynchronize(c->stream2));
+  HISPMV_CUDA(cudaStreamSynchronize(c->stream3));
   return HISPMV_OK;
 }
 
@@ -697,12 +716,56 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
   int st = ensure_staging(c, m->cols, n_y);
   if (st != HISPMV_OK) return st;
   cudaStream_t s = c->stream;
-  if (m->cols > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s));
-  if (bias && n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, s));
-  st = run_matrix(c, m, c->d_x[0], bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s);
-  if (st != HISPMV_OK) return st;
-  if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(y, c->d_y[0], (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
+  // Large tiled matrices: the rows are cut into up to 8 ranges at tile boundaries and the ranges are pipelined over
+  // three streams -- bias range i+1 goes up and y range i-1 comes down (PCIe is full duplex) while range i computes.
+  // The reference overlaps its host-side fill with the running kernel the same way (fpga_handle.cpp:366-379).
+  const bool tiled = !m->dense && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) &&
+                     !m->pipeline && !m->persistent;
+  int chunks = 1;
+  if (tiled && n_y >= (1 << 20) && m->num_tiles >= 64) chunks = n_y >= (1 << 22) ? 8 : 4;
+  if (chunks == 1) {
+    if (m->cols > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s));
+    if (bias && n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, s));
+    st = run_matrix(c, m, c->d_x[0], bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s);
+    if (st != HISPMV_OK) return st;
+    if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(y, c->d_y[0], (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
+    HISPMV_CUDA(cudaStreamSynchronize(s));
+    return HISPMV_OK;
+  }
+  // range boundaries: tile indices where a new row starts (never between two chunks of a split row)
+  int64_t tb[9];
+  tb[0] = 0;
+  tb[chunks] = m->num_tiles;
+  for (int i = 1; i < chunks; ++i) {
+    int64_t t = (m->num_tiles * i) / chunks;
+    t = std::max(t, tb[i - 1]);
+    while (t < m->num_tiles && m->h_tile_chunk[(size_t)t] > 0) ++t;
+    tb[i] = t;
+  }
+  cudaStream_t s_up = c->stream2, s_down = c->stream3;
+  cudaEvent_t ev_x = c->ev_pipe[0];
+  HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s_up));
+  HISPMV_CUDA(cudaEventRecord(ev_x, s_up));
+  HISPMV_CUDA(cudaStreamWaitEvent(s, ev_x, 0));
+  for (int i = 0; i < chunks; ++i) {
+    const int64_t r0 = m->h_tile_row[(size_t)tb[i]], r1 = m->h_tile_row[(size_t)tb[i + 1]];
+    cudaEvent_t ev_b = c->ev_pipe[1 + i], ev_k = c->ev_pipe[9 + i];
+    if (bias && r1 > r0) {
+      HISPMV_CUDA(cudaMemcpyAsync(c->d_bias + r0, bias + r0, (size_t)(r1 - r0) * 4, cudaMemcpyHostToDevice, s_up));
+      HISPMV_CUDA(cudaEventRecord(ev_b, s_up));
+      HISPMV_CUDA(cudaStreamWaitEvent(s, ev_b, 0));
+    }
+    st = run_matrix(c, m, c->d_x[0], bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, tb[i],
+                    tb[i + 1] - tb[i]);
+    if (st != HISPMV_OK) return st;
+    HISPMV_CUDA(cudaEventRecord(ev_k, s));
+    HISPMV_CUDA(cudaStreamWaitEvent(s_down, ev_k, 0));
+    if (r1 > r0)
+      HISPMV_CUDA(cudaMemcpyAsync(y + r0, c->d_y[0] + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, s_down));
+  }
+  HISPMV_CUDA(cudaStreamSynchronize(s_down));
   HISPMV_CUDA(cudaStreamSynchronize(s));
+  HISPMV_CUDA(cudaStreamSynchronize(s_up));
   return HISPMV_OK;
 }
 

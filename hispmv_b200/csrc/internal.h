@@ -65,6 +65,8 @@ struct AdaptivePlan {
   int32_t hot_cols = 0x7fffffff;        // x[c] with c < hot_cols is kept in L1 (persistent kernel: in shared
                                         // memory), the rest bypasses L1 allocation
   unsigned int* sched = nullptr;        // persistent kernel: [0] next tile, [1] groups that ran dry
+  int64_t tile_begin = 0;               // one-CTA-per-tile kernels: launch only tiles [tile_begin, tile_begin + tile_count)
+  int64_t tile_count = -1;              // (-1: all) -- the host-buffer call pipelines row ranges against PCIe copies
 };
 
 struct RowStats {

@@ -614,3 +614,30 @@ def test_device_chain_matches_cpu_model(eng, graph):
             ref = cpu_model(x.view(1, -1)).numpy().reshape(-1)
         out = chain.forward(x.cuda()).cpu().numpy()
         assert np.allclose(out, ref, rtol=1e-3, atol=1e-4)
+
+
+def test_host_run_pipelines_row_ranges(eng):
+    """hispmv_run on a matrix with > 2^20 rows cuts the rows into ranges at tile boundaries and overlaps bias upload,
+    kernel and y download of different ranges: same result as the device-resident single launch, bit for bit."""
+    import torch
+    from hispmv_b200 import synth
+    spec = synth.c2_powerlaw(0.13)                       # 1.3 M rows, ~13 M nnz, rows of up to 520 k nonzeros
+    d = synth.DeviceCSR(spec)
+    idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
+    d.close()
+    info = eng.matrix_info(idx)
+    assert info["kernel_name"] == "adaptive" and info["num_split_rows"] > 0 and info["num_tiles"] >= 64
+    x, y0 = synth.reference_vectors(spec.rows, spec.cols)
+    y = np.full(spec.rows, np.nan, np.float32)
+    eng.select_matrix(idx)
+    eng.run_kernel(x, y0, y, float(ALPHA), float(BETA))
+    yd = torch.empty(spec.rows, device="cuda")
+    eng.run_dev(idx, torch.from_numpy(x).cuda(), torch.from_numpy(y0).cuda(), yd, float(ALPHA), float(BETA),
+                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(y.view(np.uint32), yd.cpu().numpy().view(np.uint32))
+    n = 300000
+    rp, ci, vv = ol.synth_csr(spec.kind, spec.seed, spec.cols, spec.params, 0, n)
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, y0[:n], ALPHA, BETA)
+    err, at = ol.max_scaled_error(y[:n], y64, scale)
+    assert err <= TOL, (err, at)

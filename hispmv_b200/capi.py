@@ -29,6 +29,7 @@ class MatrixInfo(C.Structure):
         ("max_row_nnz", C.c_int32), ("empty_rows", C.c_int32), ("hist", C.c_int64 * HIST_BINS),
         ("device_bytes", C.c_int64), ("probe_near", C.c_int64), ("probe_cmp", C.c_int64),
         ("x_window_cols", C.c_int32), ("long_threshold", C.c_int32), ("chunk_nnz", C.c_int32),
+        ("num_slabs", C.c_int32), ("slab_cols", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -76,6 +77,8 @@ def _load() -> C.CDLL:
         "hispmv_plan_tiles": (C.c_int, [p, C.c_int, p, p]),
         "hispmv_plan_split_rows": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_tile_chunks": (C.c_int, [p, C.c_int, p]),
+        "hispmv_plan_slab_nnz": (i64, [p, C.c_int, C.c_int]),
+        "hispmv_plan_slab_csr": (C.c_int, [p, C.c_int, C.c_int, p, p, p]),
         "hispmv_load_mtx": (C.c_int, [p, C.c_char_p]),
         "hispmv_synth_count": (C.c_int, [C.c_int, u64, i32, i32, p, i32, i32, C.POINTER(i64)]),
         "hispmv_synth_shard_bounds": (C.c_int, [C.c_int, u64, i32, i32, p, C.c_int, p, C.POINTER(i64)]),
@@ -96,7 +99,7 @@ EXPORTED = [
     "hispmv_add_dense", "hispmv_add_sparse_coo_dev", "hispmv_add_sparse_csr_dev", "hispmv_add_dense_dev",
     "hispmv_commit", "hispmv_num_matrices", "hispmv_select", "hispmv_force_kernel", "hispmv_run",
     "hispmv_linear", "hispmv_run_dev", "hispmv_linear_dev", "hispmv_sync", "hispmv_stream", "hispmv_launches_per_run",
-    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_load_mtx",
+    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_plan_slab_nnz", "hispmv_plan_slab_csr", "hispmv_load_mtx",
     "hispmv_synth_count", "hispmv_synth_shard_bounds", "hispmv_synth_csr", "hispmv_synth_free",
 ]
 

@@ -50,6 +50,10 @@ struct Matrix {
   unsigned int* d_counter = nullptr;    // ADAPTIVE (two lanes, like d_carry)
   TileDesc* d_desc = nullptr;           // ADAPTIVE / ROWSTAGE: resolved tile records
   std::vector<int32_t> h_tile_row, h_tile_chunk;  // host copies: row ranges for the pipelined host-buffer call
+  // column slabs (x larger than L2): each slab is a CSR over the same rows with its own plan; y accumulates over them
+  std::vector<Matrix*> slabs;
+  int32_t slab_cols = 0;
+  bool is_slab = false;
   int32_t long_threshold = 0, chunk_nnz = 0;
   int32_t hot_cols = 0x7fffffff;        // ADAPTIVE / ROWSTAGE: split L1 policy threshold for x gathers
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
@@ -83,9 +87,11 @@ struct Matrix {
     if (dense) return (int64_t)local_rows() * ld * 4;
     int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
+    for (auto* sm : slabs) b += sm->device_bytes();
     return b;
   }
   ~Matrix() {
+    for (auto* sm : slabs) delete sm;
     free_plan();
     cudaFree(d_row_ptr);
     cudaFree(d_col);
@@ -173,6 +179,33 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     select_kernel(m->stats, m->probe, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0, &m->kernel, &m->lanes);
   } else if (m->nnz == 0 || m->local_rows() == 0) {
     m->kernel = HISPMV_KERNEL_EMPTY;
+  }
+  for (auto* sm : m->slabs) delete sm;
+  m->slabs.clear();
+  m->slab_cols = 0;
+  if (m->kernel == HISPMV_KERNEL_ADAPTIVE && !m->is_slab) {
+    int32_t w = select_slab_cols(m->cols, m->nnz, m->probe);
+    if (const char* e = getenv("HISPMV_SLAB_COLS")) w = std::max(0, atoi(e));  // tests / sweeps
+    if (w > 0 && w < m->cols) {
+      m->slab_cols = w;
+      for (int64_t lo = 0; lo < m->cols; lo += w) {
+        Matrix* sm = new Matrix();
+        sm->is_slab = true;
+        sm->forced = true;
+        sm->kernel = HISPMV_KERNEL_ADAPTIVE;
+        sm->rows = m->rows;
+        sm->cols = m->cols;
+        sm->row_begin = m->row_begin;
+        sm->row_end = m->row_end;
+        m->slabs.push_back(sm);
+        st = csr_column_slab_device(m->d_row_ptr, m->d_col, m->d_val, m->local_rows(), (int32_t)lo,
+                                    (int32_t)std::min<int64_t>(lo + w, m->cols), &sm->d_row_ptr, &sm->d_col, &sm->d_val,
+                                    &sm->nnz, c->stream);
+        if (st == HISPMV_OK) st = plan_sparse(c, sm);
+        if (st != HISPMV_OK) return st;
+      }
+      return HISPMV_OK;  // the parent keeps its CSR for introspection; the slabs carry the plans
+    }
   }
   if (m->kernel == HISPMV_KERNEL_CSR_VECTOR && m->lanes < 2) {
     int k, l;
@@ -451,6 +484,17 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
     D.a = m->d_a;
     return launch_gemv(D, d_x, d_y, ep, c->sm_count, s);
   }
+  if (!m->slabs.empty()) {
+    // y = alpha*A_0 x + beta*bias, then y += alpha*A_s x for the other slabs (the kernels read bias[r] and write y[r]
+    // from the same thread, so y can be its own bias); ReLU only after the last slab
+    for (size_t k = 0; k < m->slabs.size(); ++k) {
+      const bool first = k == 0, last = k + 1 == m->slabs.size();
+      int st = run_matrix(c, m->slabs[k], d_x, first ? d_bias : d_y, d_y, alpha, first ? beta : 1.0f, last ? relu : 0, s,
+                          lane);
+      if (st != HISPMV_OK) return st;
+    }
+    return HISPMV_OK;
+  }
   CsrDev A;
   A.rows = m->local_rows();
   A.cols = m->cols;
@@ -697,6 +741,7 @@ int hispmv_launches_per_run(hispmv_ctx* c, int idx) {
   if (!m) return HISPMV_ERR_INDEX;
   if (m->local_rows() <= 0) return 0;
   if (!m->dense && m->kernel == HISPMV_KERNEL_MERGE) return m->num_tiles > 1 ? 2 : 1;
+  if (!m->slabs.empty()) return (int)m->slabs.size();
   return 1;
 }
 
@@ -720,7 +765,7 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
   // three streams -- bias range i+1 goes up and y range i-1 comes down (PCIe is full duplex) while range i computes.
   // The reference overlaps its host-side fill with the running kernel the same way (fpga_handle.cpp:366-379).
   const bool tiled = !m->dense && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) &&
-                     !m->pipeline && !m->persistent;
+                     !m->pipeline && !m->persistent && m->slabs.empty();
   int chunks = 1;
   if (tiled && n_y >= (1 << 20) && m->num_tiles >= 64) chunks = n_y >= (1 << 22) ? 8 : 4;
   if (chunks == 1) {
@@ -826,6 +871,19 @@ int hispmv_matrix_info_get(hispmv_ctx* c, int idx, hispmv_matrix_info* out) {
     for (int i = 0; i < HISPMV_HIST_BINS; ++i) out->hist[i] = m->stats.hist[i];
   out->device_bytes = m->device_bytes();
   out->x_window_cols = (!m->dense && m->persistent) ? m->hot_cols : 0;
+  out->num_slabs = (int32_t)m->slabs.size();
+  out->slab_cols = m->slab_cols;
+  if (!m->slabs.empty()) {  // the slabs carry the plans: report their totals
+    out->num_tiles = 0;
+    out->num_split_rows = 0;
+    for (auto* sm : m->slabs) {
+      out->num_tiles += sm->num_tiles;
+      out->num_split_rows += sm->num_split;
+    }
+    out->tile_items = m->slabs[0]->tile_items;
+    out->long_threshold = m->slabs[0]->long_threshold;
+    out->chunk_nnz = m->slabs[0]->chunk_nnz;
+  }
   out->probe_near = m->dense ? 0 : m->probe.near;
   out->probe_cmp = m->dense ? 0 : m->probe.cmp;
   out->long_threshold = m->dense ? 0 : m->long_threshold;
@@ -870,6 +928,31 @@ int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_n
       tile_nnz[t] = (int64_t)rp + (t < m->num_tiles && tc[(size_t)t] > 0 ? (int64_t)tc[(size_t)t] * m->chunk_nnz : 0);
     }
   }
+  return HISPMV_OK;
+}
+
+int64_t hispmv_plan_slab_nnz(hispmv_ctx* c, int idx, int slab) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (slab < 0 || slab >= (int)m->slabs.size()) {
+    set_error("plan_slab: no such slab");
+    return HISPMV_ERR_ARG;
+  }
+  return m->slabs[(size_t)slab]->nnz;
+}
+
+int hispmv_plan_slab_csr(hispmv_ctx* c, int idx, int slab, int32_t* row_ptr, int32_t* col_idx, float* vals) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (slab < 0 || slab >= (int)m->slabs.size()) {
+    set_error("plan_slab: no such slab");
+    return HISPMV_ERR_ARG;
+  }
+  Matrix* sm = m->slabs[(size_t)slab];
+  DeviceGuard g(c->device);
+  if (row_ptr) HISPMV_CUDA(cudaMemcpy(row_ptr, sm->d_row_ptr, ((size_t)sm->local_rows() + 1) * 4, cudaMemcpyDeviceToHost));
+  if (col_idx && sm->nnz) HISPMV_CUDA(cudaMemcpy(col_idx, sm->d_col, (size_t)sm->nnz * 4, cudaMemcpyDeviceToHost));
+  if (vals && sm->nnz) HISPMV_CUDA(cudaMemcpy(vals, sm->d_val, (size_t)sm->nnz * 4, cudaMemcpyDeviceToHost));
   return HISPMV_OK;
 }
 

@@ -116,6 +116,14 @@ struct ColProbe {
 constexpr int32_t kProbeSamples = 8192;
 int col_probe_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, ColProbe* out, cudaStream_t stream);
 
+// Column slab [lo_col, hi_col) of a device CSR as a CSR over the same rows (arrays cudaMalloc'ed by the callee, padded).
+int csr_column_slab_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows,
+                           int32_t lo_col, int32_t hi_col, int32_t** o_row_ptr, int32_t** o_col, float** o_val,
+                           int64_t* o_nnz, cudaStream_t stream);
+constexpr int64_t kSlabMinBytes = 64ll << 20;   // x up to 64 MB is left whole
+constexpr int32_t kSlabMaxCols = 12500000;      // 50 MB of x per slab (C5 sweep: 10 M 8.1 ms, 12.5 M 7.5, 20 M 7.9, 25 M 9.0)
+// 0 = no slabs, else the slab width in columns (restated in oracle/: oracle_select_slab_cols)
+int32_t select_slab_cols(int32_t cols, int64_t nnz, const ColProbe& probe);
 // carry[] slots of split rows hold this NaN payload until their chunk has written its partial (adaptive.cu)
 constexpr uint32_t kCarryEmptyBits = 0x7fc0dead;
 cudaError_t fill_u32_device(uint32_t* p, uint32_t value, size_t n, cudaStream_t stream);

@@ -630,6 +630,113 @@ cudaError_t fill_u32_device(uint32_t* p, uint32_t value, size_t n, cudaStream_t 
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Column slabs (x larger than L2): slab s keeps the nonzeros with bounds[s] <= col < bounds[s+1] of every row, as a
+// CSR of its own over the same rows.  Columns are sorted inside a row, so a row's share of a slab is one contiguous
+// segment found by two binary searches.
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void slab_count_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ col, int32_t rows,
+                                  int32_t lo_col, int32_t hi_col, int32_t* __restrict__ first,
+                                  int32_t* __restrict__ len) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > rows) return;
+  if (r == rows) {
+    len[r] = 0;  // slot for the exclusive scan's total
+    return;
+  }
+  const int32_t b = rp[r], e = rp[r + 1];
+  int32_t lo = b, hi = e;  // first entry with col >= lo_col
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (col[mid] < lo_col) lo = mid + 1; else hi = mid;
+  }
+  const int32_t f = lo;
+  hi = e;  // first entry with col >= hi_col
+  while (lo < hi) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (col[mid] < hi_col) lo = mid + 1; else hi = mid;
+  }
+  first[r] = f;
+  len[r] = lo - f;
+}
+__global__ void slab_copy_kernel(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                 const int32_t* __restrict__ first, const int32_t* __restrict__ srp, int32_t rows,
+                                 int64_t nnz, int64_t padded, int32_t* __restrict__ ocol, float* __restrict__ oval) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= padded) return;
+  if (j >= nnz) {
+    ocol[j] = 0;
+    oval[j] = 0.0f;
+    return;
+  }
+  int32_t lo = 0, hi = rows;  // row of output entry j: last r with srp[r] <= j
+  while (hi - lo > 1) {
+    const int32_t mid = (lo + hi) >> 1;
+    if ((int64_t)srp[mid] <= j) lo = mid; else hi = mid;
+  }
+  const int64_t src = (int64_t)first[lo] + (j - srp[lo]);
+  ocol[j] = col[src];
+  oval[j] = val[src];
+}
+}  // namespace
+
+int csr_column_slab_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows,
+                           int32_t lo_col, int32_t hi_col, int32_t** o_row_ptr, int32_t** o_col, float** o_val,
+                           int64_t* o_nnz, cudaStream_t stream) {
+  *o_row_ptr = nullptr;
+  *o_col = nullptr;
+  *o_val = nullptr;
+  *o_nnz = 0;
+  DevBuf first, len, tmp;
+  int st;
+  if ((st = first.alloc(((size_t)rows + 1) * 4)) || (st = len.alloc(((size_t)rows + 1) * 4))) return st;
+  HISPMV_CUDA(cudaMalloc((void**)o_row_ptr, ((size_t)rows + 1 + 4) * sizeof(int32_t)));
+  slab_count_kernel<<<blocks_for((int64_t)rows + 1, 256), 256, 0, stream>>>(d_row_ptr, d_col, rows, lo_col, hi_col,
+                                                                           first.as<int32_t>(), len.as<int32_t>());
+  size_t tb = 0;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, len.as<int32_t>(), *o_row_ptr, (int64_t)rows + 1, stream));
+  st = tmp.alloc(tb);
+  if (st == HISPMV_OK)
+    st = check_cuda(cub::DeviceScan::ExclusiveSum(tmp.p, tb, len.as<int32_t>(), *o_row_ptr, (int64_t)rows + 1, stream),
+                    "scan", __FILE__, __LINE__);
+  int32_t total = 0;
+  if (st == HISPMV_OK)
+    st = check_cuda(cudaMemcpyAsync(&total, *o_row_ptr + rows, 4, cudaMemcpyDeviceToHost, stream), "D2H", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamSynchronize(stream), "sync", __FILE__, __LINE__);
+  const int64_t pad = padded_nnz(total);
+  if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)o_col, pad * 4), "cudaMalloc(slab col)", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)o_val, pad * 4), "cudaMalloc(slab val)", __FILE__, __LINE__);
+  if (st == HISPMV_OK) {
+    slab_copy_kernel<<<blocks_for(pad, 256), 256, 0, stream>>>(d_col, d_val, first.as<int32_t>(), *o_row_ptr, rows,
+                                                               total, pad, *o_col, *o_val);
+    st = check_cuda(cudaGetLastError(), "slab_copy", __FILE__, __LINE__);
+  }
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamSynchronize(stream), "sync", __FILE__, __LINE__);
+  if (st != HISPMV_OK) {
+    cudaFree(*o_row_ptr);
+    cudaFree(*o_col);
+    cudaFree(*o_val);
+    *o_row_ptr = nullptr;
+    *o_col = nullptr;
+    *o_val = nullptr;
+    return st;
+  }
+  *o_nnz = total;
+  return HISPMV_OK;
+}
+
+// Slab width: x beyond kSlabMinBytes does not stay in L2 under random gathers (measured: 275 G gathers/s for a 40 MB
+// table, 101 G/s at 160 MB, 60 G/s at 400 MB), so the columns are cut into equal slabs of at most kSlabMaxCols.
+// C5 on one GPU (100 M columns): 17.5 ms whole, 7.5 ms as 8 slabs -- each pass pays row_ptr + y read + y write again.
+int32_t select_slab_cols(int32_t cols, int64_t nnz, const ColProbe& probe) {
+  const bool banded = probe.cmp >= 64 && probe.near * 4 >= probe.cmp * 3;
+  if (banded || (int64_t)cols * 4 <= kSlabMinBytes || nnz < 4000000) return 0;
+  const int64_t n = ((int64_t)cols + kSlabMaxCols - 1) / kSlabMaxCols;
+  const int64_t w = ((int64_t)cols + n - 1) / n;
+  return (int32_t)((w + 31) & ~(int64_t)31);
+}
+
 int tile_desc_device(const int32_t* d_row_ptr, const int32_t* d_tile_row, const int32_t* d_tile_chunk,
                      int64_t num_tiles, int32_t chunk_nnz, TileDesc** d_desc, cudaStream_t stream) {
   *d_desc = nullptr;

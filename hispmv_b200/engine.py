@@ -175,6 +175,14 @@ class Engine:
         check(lib.hispmv_plan_tile_chunks(self._ctx, matrix_idx, _ptr(out)), "plan_tile_chunks")
         return out
 
+    def plan_slab_csr(self, matrix_idx: int, slab: int):
+        info = self.matrix_info(matrix_idx)
+        n = info["row_end"] - info["row_begin"]
+        nnz = check(lib.hispmv_plan_slab_nnz(self._ctx, matrix_idx, slab), "plan_slab_nnz")
+        rp, ci, v = np.empty(n + 1, np.int32), np.empty(nnz, np.int32), np.empty(nnz, np.float32)
+        check(lib.hispmv_plan_slab_csr(self._ctx, matrix_idx, slab, _ptr(rp), _ptr(ci), _ptr(v)), "plan_slab_csr")
+        return rp, ci, v
+
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:
         info = self.matrix_info(matrix_idx)
         out = np.empty(info["num_split_rows"], np.int32)

@@ -98,6 +98,9 @@ typedef struct hispmv_matrix_info {
   int32_t x_window_cols;    /* > 0 only under the HISPMV_PERSIST research switch (persistent x-window kernel) */
   int32_t long_threshold;   /* ADAPTIVE / ROWSTAGE: rows with at least this many nonzeros become LONG tiles */
   int32_t chunk_nnz;        /* ADAPTIVE / ROWSTAGE: nonzeros per LONG tile (chunk of a heavy row) */
+  int32_t num_slabs;        /* > 0: x is larger than L2 and the matrix runs as this many column slabs, one launch each */
+  int32_t slab_cols;        /* columns per slab */
+  int32_t reserved_;
 } hispmv_matrix_info;
 
 const char* hispmv_last_error(void);
@@ -165,6 +168,10 @@ int hispmv_plan_csr(hispmv_ctx* ctx, int idx, int32_t* row_ptr, int32_t* col_idx
 int hispmv_plan_tiles(hispmv_ctx* ctx, int idx, int32_t* tile_row, int64_t* tile_nnz);
 /* Sorted ids of the rows split across tiles (num_split_rows entries). */
 int hispmv_plan_split_rows(hispmv_ctx* ctx, int idx, int32_t* rows_out);
+/* Column slab `slab` of matrix idx as CSR over the local rows (sizes: local_rows+1, and the slab's nnz, which
+ * hispmv_plan_slab_nnz returns).  Any pointer may be NULL. */
+int64_t hispmv_plan_slab_nnz(hispmv_ctx* ctx, int idx, int slab);
+int hispmv_plan_slab_csr(hispmv_ctx* ctx, int idx, int slab, int32_t* row_ptr, int32_t* col_idx, float* vals);
 /* ADAPTIVE only: per tile, -1 for a STREAM tile or the chunk index of a LONG tile (num_tiles entries). */
 int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
 

@@ -267,6 +267,16 @@ int oracle_merge_tile_items(int rows, int64_t nnz) {
   return 256 * 7;
 }
 
+/* Column slab width (partition.cu: select_slab_cols); 0 = no slabs. */
+int oracle_select_slab_cols(int cols, int64_t nnz, int64_t probe_near, int64_t probe_cmp) {
+  const int banded = probe_cmp >= 64 && probe_near * 4 >= probe_cmp * 3;
+  int64_t n, w;
+  if (banded || (int64_t)cols * 4 <= (64ll << 20) || nnz < 4000000) return 0;
+  n = ((int64_t)cols + 12500000 - 1) / 12500000;
+  w = ((int64_t)cols + n - 1) / n;
+  return (int)((w + 31) & ~(int64_t)31);
+}
+
 /* ROWSTAGE plan parameters (partition.cu: rowstage_params): lanes per row, STREAM budget B, long threshold T,
  * chunk size CH.  lanes_in = 0 lets the rule choose lanes. */
 void oracle_rowstage_params(int rows, int64_t nnz, int lanes_in, int* lanes, int* stream_items, int* long_threshold,

@@ -60,6 +60,8 @@ def oracle() -> C.CDLL:
     lib.oracle_row_stats.argtypes = [i, _i32p, _i64p, C.POINTER(i), C.POINTER(i)]
     lib.oracle_select_kernel.argtypes = [i, i64, _i64p, i64, i64, i, C.POINTER(i), C.POINTER(i)]
     lib.oracle_col_probe.argtypes = [i, _i32p, _i32p, C.POINTER(i64), C.POINTER(i64)]
+    lib.oracle_select_slab_cols.argtypes = [i, i64, i64, i64]
+    lib.oracle_select_slab_cols.restype = i
     lib.oracle_rowstage_params.argtypes = [i, i64, i, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     lib.oracle_merge_tile_items.argtypes = [i, i64]
     lib.oracle_merge_tile_items.restype = i
@@ -237,6 +239,20 @@ def select_kernel(rp, ci, allow_split=1):
     k, l = C.c_int(), C.c_int()
     oracle().oracle_select_kernel(rp.size - 1, int(rp[-1]), hist, near, cmp_, allow_split, C.byref(k), C.byref(l))
     return k.value, l.value, near, cmp_
+
+
+def select_slab_cols(cols, nnz, near, cmp_):
+    return oracle().oracle_select_slab_cols(cols, nnz, near, cmp_)
+
+
+def column_slab(rp, ci, vv, lo, hi):
+    """CSR of the entries with lo <= col < hi, same rows (numpy restatement of csr_column_slab_device)."""
+    keep = (ci >= lo) & (ci < hi)
+    rows = rp.size - 1
+    row_of = np.repeat(np.arange(rows), np.diff(rp))
+    cnt = np.bincount(row_of[keep], minlength=rows)
+    srp = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    return srp, ci[keep], vv[keep]
 
 
 def rowstage_params(rows, nnz, lanes_in=0):

@@ -641,3 +641,71 @@ def test_host_run_pipelines_row_ranges(eng):
     y64, scale = ol.spmv_f64(rp, ci, vv, x, y0[:n], ALPHA, BETA)
     err, at = ol.max_scaled_error(y[:n], y64, scale)
     assert err <= TOL, (err, at)
+
+
+def test_column_slabs_bit_exact_and_within_tolerance(eng, monkeypatch):
+    """x larger than L2: the matrix is cut into column slabs (CSR over the same rows, bit-exact against a numpy
+    restatement), one launch per slab, y accumulating across them; bias / ReLU applied exactly once."""
+    import torch
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_SLAB_COLS", "30016")
+    rng = np.random.default_rng(77)
+    rows, cols = 50000, 100003
+    lens = np.minimum(rng.zipf(1.7, rows), 30000)
+    lens[rng.integers(0, rows, 4)] = 9000
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_ADAPTIVE)
+    info = eng.matrix_info(idx)
+    assert (info["num_slabs"], info["slab_cols"]) == (4, 30016)
+    rp, ci, vv = eng.plan_csr(idx)
+    total = 0
+    for sidx in range(4):
+        srp, sci, svv = eng.plan_slab_csr(idx, sidx)
+        srp2, sci2, svv2 = ol.column_slab(rp, ci, vv, sidx * 30016, min((sidx + 1) * 30016, cols))
+        assert np.array_equal(srp, srp2) and np.array_equal(sci, sci2)
+        assert np.array_equal(svv.view(np.uint32), svv2.view(np.uint32))
+        total += sci.size
+    assert total == ci.size
+    y1 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(3))
+    y2 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(3))
+    assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
+    _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(4), alpha=1.0, beta=0.0)
+    # fused ReLU only after the last slab
+    x = rng.standard_normal(cols).astype(np.float32)
+    b = rng.standard_normal(rows).astype(np.float32)
+    yd = torch.empty(rows, device="cuda")
+    eng.linear_dev(idx, torch.from_numpy(x).cuda(), torch.from_numpy(b).cuda(), yd, relu=True,
+                   stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, b, 1.0, 1.0)
+    y = yd.cpu().numpy()
+    pos = y64 > 1e-4 * np.maximum(scale, 1e-30)
+    err, _ = ol.max_scaled_error(y[pos], y64[pos], scale[pos])
+    assert err <= TOL and np.all(y >= 0) and np.all(y[y64 < -1e-4 * np.maximum(scale, 1e-30)] == 0)
+    # linear() through the host path
+    out = eng.linear(idx, x, b)
+    err, _ = ol.max_scaled_error(out, y64, scale)
+    assert err <= TOL
+
+
+def test_slab_selector_bit_exact(eng):
+    """select_slab_cols: x of 80 MB with random columns -> two slabs of 10 M columns; the same matrix with 16 M
+    columns (64 MB) stays whole."""
+    rng = np.random.default_rng(9)
+    rows, nnz = 300000, 4200000
+    for cols, want in ((20000000, 2), (16000000, 0)):
+        r = rng.integers(0, rows, nnz).astype(np.int32)
+        r[:50000] = 11                                              # a heavy row
+        c = rng.integers(0, cols, nnz).astype(np.int32)
+        v = rng.standard_normal(nnz).astype(np.float32)
+        idx = eng.create_sparse_handle(r, c, v, rows, cols)
+        info = eng.matrix_info(idx)
+        w = ol.select_slab_cols(cols, nnz, info["probe_near"], info["probe_cmp"])
+        assert info["kernel_name"] == "adaptive" and info["slab_cols"] == w and info["num_slabs"] == want
+        if want:
+            assert w == 10000000 and (info["num_slabs"] - 1) * w < cols <= info["num_slabs"] * w
+        rp, ci, vv = eng.plan_csr(idx)
+        _check_run(eng, idx, rp, ci, vv, rows, cols, rng)

@@ -44,8 +44,12 @@ def measured_peak():
 
 
 def workload_name(spec, n_gpus):
-    return (f"C2 power-law CSR {spec.rows}x{spec.cols} fp32, row len ~ min(1M, 0.6912/u), cols ~ Zipf(0.8), seed {spec.seed}"
-            + (f", {n_gpus} nnz-balanced row blocks" if n_gpus > 1 else ""))
+    if spec.name.startswith("C5"):
+        base = f"C5 uniform-random CSR {spec.rows}x{spec.cols} fp32, 6 + popcount(8 bits) nnz per row, seed {spec.seed}"
+    else:
+        base = (f"C2 power-law CSR {spec.rows}x{spec.cols} fp32, row len ~ min(1M, 0.6912/u), cols ~ Zipf(0.8), "
+                f"seed {spec.seed}")
+    return base + (f", {n_gpus} nnz-balanced row blocks" if n_gpus > 1 else "")
 
 
 class ClockSampler:
@@ -117,7 +121,7 @@ def run_reference(args):
     import oracle_lib as ol
     from hispmv_b200 import synth
     ol.build()
-    spec = synth.c2_powerlaw(args.scale)
+    spec = synth.c5_uniform(args.scale) if args.workload == "c5" else synth.c2_powerlaw(args.scale)
     threads = os.cpu_count() or 1
     t0 = time.time()
     rp, ci, vv = host_matrix(spec, 0, spec.rows)
@@ -170,8 +174,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    base = synth.c2_powerlaw(args.scale)
-    spec = synth.SynthSpec(base.name, base.kind, base.seed, base.rows * world, base.cols, base.params)
+    if args.workload == "c5":   # BASELINE configs[4]: one 100M x 100M, 1B-nnz matrix split over the ranks (strong scaling)
+        spec = synth.c5_uniform(args.scale)
+    else:                       # BASELINE configs[1] per GPU (weak scaling)
+        base = synth.c2_powerlaw(args.scale)
+        spec = synth.SynthSpec(base.name, base.kind, base.seed, base.rows * world, base.cols, base.params)
     if world > 1:
         bounds, total_nnz = synth.synth_shard_bounds(spec, world)
         rb, re = int(bounds[rank]), int(bounds[rank + 1])
@@ -293,18 +300,20 @@ def run_ours(args):
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "c2_" + info["kernel_name"] + "_dram_bytes_per_launch")
+                args.workload + "_" + info["kernel_name"] + "_dram_bytes_per_launch") if world == 1 else None
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c5" else "weak",
+            "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(spec, world), "rows": spec.rows, "cols": spec.cols, "nnz": int(total_nnz),
                        "alpha": ALPHA, "beta": BETA, "kernel": info["kernel_name"], "tile_items": info["tile_items"],
+                       "column_slabs": info.get("num_slabs", 0),
                        "split_rows": info["num_split_rows"],
                        "l2": f"matrix stream is {8 * local_nnz / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2; "
-                             "x (40 MB) is the only operand that can stay L2-resident",
+                             f"x ({4 * spec.cols / 1e6:.0f} MB) is the only operand that can stay L2-resident",
                        "x_exchange": "none (N=1)" if world == 1 else "NCCL broadcast of x from rank 0 each step, "
                                      "double-buffered under the previous step's SpMV"},
             "gb_per_s": (8 * total_nnz + 4 * spec.cols + 4 * spec.rows) / (ms_step * 1e-3) / 1e9,
@@ -368,6 +377,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 (default, the headline: configs[1], weak scaling) or c5 (configs[4], strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,7 +43,7 @@ namespace {
 
 constexpr int kGroup = 256;  // threads that cooperate on one tile
 constexpr int kGroupWarps = kGroup / 32;
-constexpr int kSerialRow = 8;   // rows up to this many nonzeros are summed by one lane, longer ones by the warp
+constexpr int kSerialRow = 16;  // rows up to this many nonzeros are summed by one lane, longer ones by the warp
 
 // ---- x gathers ------------------------------------------------------------------------------------------------
 template <bool SPLIT>
@@ -71,9 +71,10 @@ struct GatherWindow {  // columns below `hot` live in shared memory
 // ---- products of the nonzeros [n0, n1): lane-consecutive, four independent (col, val, x) triples per thread ----
 // OUT(i, p) receives product p of nonzero i.  Threads whose four slots are all inside [n0, n1) take a path without
 // per-slot predicates (instruction issue, not memory, was the floor of the first version of this loop).
-template <class G, class OUT>
+template <int STRIDE = kGroup, class G, class OUT>
 __device__ __forceinline__ void stream_products(const CsrDev& A, const G& gx, int n0, int n1, int gt, uint64_t ps,
                                                 OUT out) {
+  constexpr int kGroup = STRIDE;  // threads sharing the range (a CTA group, or one warp)
   for (int i0 = (n0 & ~31) + gt; i0 < n1; i0 += 4 * kGroup) {  // every warp load is one aligned 128-byte line
     const int32_t* pc = A.col + i0;
     const float* pv = A.val + i0;
@@ -135,11 +136,13 @@ __device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int 
     }
     const int len = e - b;
     float s = 0.0f;
-    if (len <= kSerialRow) {
-#pragma unroll
-      for (int k = 0; k < kSerialRow; ++k)
-        if (k < len) s += s_prod[b + k];
-    }
+    // one lane per row up to kSerialRow products; the trip count is the longest such row of this pass, so a pass over
+    // 10-nnz rows costs 10 steps and a pass over 1-nnz rows one
+    const int mine = len <= kSerialRow ? len : 0;
+    const int steps = __reduce_max_sync(kFullMask, mine);
+#pragma unroll 4
+    for (int k = 0; k < steps; ++k)
+      if (k < mine) s += s_prod[b + k];
     unsigned big = __ballot_sync(kFullMask, len > kSerialRow);
     while (big) {
       const int j = __ffs(big) - 1;
@@ -264,6 +267,45 @@ __global__ void __launch_bounds__(kGroup, 8)
   stream_products(A, gx, n0, d.n1, tid, ps, [&](int i, float p) { s_prod[i - n0] = p; });
   __syncthreads();
   rows_from_products(A, d.r0, n0, beg, end, b0 - n0, e0 - n0, bias0, s_prod, lane, y, ep);
+}
+
+// ================================================================================================================
+// one WARP per tile
+// ================================================================================================================
+// The same tiles at warp granularity (a few hundred items): a warp loads its tile's col/val, gathers, keeps the
+// products in its own slice of shared memory and reduces its rows -- no CTA-wide barrier anywhere, so no warp ever
+// waits for another warp's gathers, and an SM has 64 independent latency chains in flight instead of 8.
+template <int WCAP, bool SPLIT>  // WCAP >= stream_items + long_threshold and >= chunk_nnz
+__global__ void __launch_bounds__(kGroup, 8)
+    spmv_warptile_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
+  __shared__ float s_prod_all[kGroupWarps][WCAP];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t t = P.tile_begin + (int64_t)blockIdx.x * kGroupWarps + warp;
+  const int64_t t_end = P.tile_begin + (P.tile_count >= 0 ? P.tile_count : P.num_tiles);
+  if (t >= t_end) return;
+  float* s_prod = s_prod_all[warp];
+  const TileDesc d = load_desc(P.desc + t);
+  const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
+  const GatherL1<SPLIT> gx{x, P.hot_cols, pk};
+  if (d.chunk >= 0) {
+    float acc = 0.0f;
+    stream_products<32>(A, gx, d.n0, d.n1, lane, ps, [&](int, float p) { acc += p; });
+    acc = warp_sum(acc);
+    finish_chunk(P, d, t, acc, lane, y, ep);
+    return;
+  }
+  const int n0 = d.n0;
+  const int trows = d.r1 - d.r0;
+  int b0 = 0, e0 = 0;
+  float bias0 = 0.0f;
+  if (lane < trows) {
+    b0 = A.row_ptr[d.r0 + lane];
+    e0 = A.row_ptr[d.r0 + lane + 1];
+    if (ep.beta != 0.0f) bias0 = ep.bias[d.r0 + lane];
+  }
+  stream_products<32>(A, gx, n0, d.n1, lane, ps, [&](int i, float p) { s_prod[i - n0] = p; });
+  __syncwarp();
+  rows_from_products(A, d.r0, n0, 0, trows, b0 - n0, e0 - n0, bias0, s_prod, lane, y, ep);
 }
 
 // ================================================================================================================
@@ -679,11 +721,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
         }
         const int len = e - b;
         float sum = 0.0f;
-        if (len <= kSerialRow) {
-#pragma unroll
-          for (int q = 0; q < kSerialRow; ++q)
-            if (q < len) sum += prod[b + q];
-        }
+        const int mine = len <= kSerialRow ? len : 0;
+        const int steps = __reduce_max_sync(kFullMask, mine);
+#pragma unroll 4
+        for (int q = 0; q < steps; ++q)
+          if (q < mine) sum += prod[b + q];
         unsigned big = __ballot_sync(kFullMask, len > kSerialRow);
         while (big) {
           const int j = __ffs(big) - 1;
@@ -803,6 +845,23 @@ int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, floa
     if (split) spmv_adaptive_kernel<4096, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
     else spmv_adaptive_kernel<4096, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
   }
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int launch_warptile(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s) {
+  if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
+  int st = check_plan(P, kWarpTileCap, "warptile");
+  if (st != HISPMV_OK) return st;
+  if (P.chunk_nnz > 65536) {
+    set_error("warptile: chunk_nnz too large");
+    return HISPMV_ERR_ARG;
+  }
+  const int64_t tiles = P.tile_count >= 0 ? P.tile_count : P.num_tiles;
+  const int grid = (int)((tiles + kGroupWarps - 1) / kGroupWarps);
+  if (grid <= 0) return HISPMV_OK;
+  if (P.hot_cols != 0x7fffffff) spmv_warptile_kernel<kWarpTileCap, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+  else spmv_warptile_kernel<kWarpTileCap, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }

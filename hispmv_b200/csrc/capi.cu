@@ -58,6 +58,7 @@ struct Matrix {
   int32_t hot_cols = 0x7fffffff;        // ADAPTIVE / ROWSTAGE: split L1 policy threshold for x gathers
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
   bool pipeline = false;                // ADAPTIVE: warp-specialised persistent pipeline (TMA ring)
+  bool warptile = false;                // ADAPTIVE: one warp per (small) tile, no CTA barrier
   ColProbe probe{};                     // column-locality probe (selector input)
   // dense
   float* d_a = nullptr;
@@ -256,6 +257,17 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     m->hot_cols = 0x7fffffff;
     m->persistent = false;
     m->pipeline = false;
+    m->warptile = false;
+    if (const char* e = getenv("HISPMV_WARPTILE")) {  // "B,T,CH"
+      int b = 0, t = 0, ch = 0;
+      if (m->kernel == HISPMV_KERNEL_ADAPTIVE && sscanf(e, "%d,%d,%d", &b, &t, &ch) == 3 && b >= 32 && t >= 16 &&
+          b + t <= kWarpTileCap && ch >= 64) {
+        m->warptile = true;
+        m->tile_items = b;
+        m->long_threshold = t;
+        m->chunk_nnz = ch;
+      }
+    }
     if (const char* e = getenv("HISPMV_PIPELINE")) {
       if (atoi(e) > 0 && m->kernel == HISPMV_KERNEL_ADAPTIVE) {
         m->pipeline = true;
@@ -532,6 +544,7 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.tile_count = tile_count;
       P.sched = m->d_counter + (size_t)std::max<int64_t>(m->num_tiles, 1) * 2 + 4 * (size_t)lane;
       if (m->kernel == HISPMV_KERNEL_ROWSTAGE) return launch_rowstage(A, P, m->lanes, d_x, d_y, ep, s);
+      if (m->warptile) return launch_warptile(A, P, d_x, d_y, ep, s);
       if (m->pipeline) return launch_pipeline(A, P, d_x, d_y, ep, c->sm_count, s);
       if (m->persistent) return launch_adaptive_persistent(A, P, d_x, d_y, ep, c->sm_count, s);
       return launch_adaptive(A, P, d_x, d_y, ep, s);
@@ -765,7 +778,7 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
   // three streams -- bias range i+1 goes up and y range i-1 comes down (PCIe is full duplex) while range i computes.
   // The reference overlaps its host-side fill with the running kernel the same way (fpga_handle.cpp:366-379).
   const bool tiled = !m->dense && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) &&
-                     !m->pipeline && !m->persistent && m->slabs.empty();
+                     !m->pipeline && !m->persistent && !m->warptile && m->slabs.empty();
   int chunks = 1;
   if (tiled && n_y >= (1 << 20) && m->num_tiles >= 64) chunks = n_y >= (1 << 22) ? 8 : 4;
   if (chunks == 1) {

@@ -154,6 +154,9 @@ constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdapt
 int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
                                int sm_count, cudaStream_t s);
 constexpr int kPersistentMaxHot = 40960;  // floats of x the window may hold next to the four group buffers
+// One warp per tile (tiles of a few hundred items): stream_items + long_threshold <= kWarpTileCap.
+int launch_warptile(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
+constexpr int kWarpTileCap = 512;
 // Warp-specialised persistent pipeline (TMA producer / gather teams / reduce warps).  A stage holds one tile:
 // stream_items + long_threshold <= kPipelineCap, chunk_nnz <= kPipelineCap, stream_items <= kPipelineRows.
 constexpr int kPipelineCap = 1920, kPipelineRows = 1408;  // CAP = 6 gathers x 320 team threads

@@ -61,8 +61,11 @@ __global__ void __launch_bounds__(1024) gather(const int32_t* __restrict__ idx, 
         float4 q;
         asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "l"(tab + (cs[k] & ~3)));
         v = q.x + q.y + q.z + q.w;
-      } else {
+      } else if (MODE == 4) {
         if (cs[k] < hot) v = s_hot[cs[k]];
+        else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
+      } else {  // MODE 5: L1 split policy -- head pinned (evict_last), tail bypasses allocation
+        if (cs[k] < hot) asm volatile("ld.global.nc.L1::evict_last.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
         else asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(tab + cs[k]));
       }
       acc += v;
@@ -140,8 +143,10 @@ int main() {
       CK(cudaDeviceSynchronize());
       const float m4 = run<4>(sms, 1024, idx, n, tab, hot_words, out);
       const float m1 = run<1>(sms * 2, 1024, idx, n, tab, 0, out);
-      printf("hot=%6d words (%3d KB) hit=%2d%% : smem+global %7.2f G/s | all-global(no_allocate) %7.2f G/s\n", hot_words,
-             hot_words * 4 / 1024, pct, n / m4 / 1e6, n / m1 / 1e6);
+      const float m5 = run<5>(sms * 2, 1024, idx, n, tab, hot_words, out);
+      const float m0 = run<0>(sms * 2, 1024, idx, n, tab, 0, out);
+      printf("hot=%6d words (%3d KB) hit=%2d%% : smem+global %7.2f G/s | all-global(no_allocate) %7.2f G/s | L1 split policy %7.2f G/s | plain nc %7.2f G/s\n", hot_words,
+             hot_words * 4 / 1024, pct, n / m4 / 1e6, n / m1 / 1e6, n / m5 / 1e6, n / m0 / 1e6);
     }
   }
   return 0;

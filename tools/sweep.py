@@ -75,6 +75,7 @@ def main():
     ap.add_argument("--hot", default="0", help="','-separated hot-column thresholds for the split L1 policy (0 = keep all)")
     ap.add_argument("--persist", default="", help="','-separated x-window sizes for the persistent adaptive kernel")
     ap.add_argument("--pipeline", default="", help="';'-separated B,T,CH triples for the warp-specialised pipeline kernel")
+    ap.add_argument("--warptile", default="", help="';'-separated B,T,CH triples for the warp-per-tile kernel")
     ap.add_argument("--only-auto", action="store_true", help="time only what the selector picks")
     ap.add_argument("--skip", default="", help="','-separated variant names to skip (adapt,rows,merge,vector,scalar)")
     args = ap.parse_args()
@@ -152,6 +153,7 @@ def main():
         variants += [("persist", capi.KERNEL_ADAPTIVE, 0, "A" + a + "P" + w) for a in args.adaptive.split(";") if a
                      for w in args.persist.split(",") if w]
         variants += [("pipe", capi.KERNEL_ADAPTIVE, 0, "A" + a + "Q") for a in args.pipeline.split(";") if a]
+        variants += [("warpt", capi.KERNEL_ADAPTIVE, 0, "W" + a) for a in args.warptile.split(";") if a]
         variants += [("auto", capi.KERNEL_AUTO, 0, "")]
         variants += [("merge", capi.KERNEL_MERGE, 0, t) for t in args.tiles.split(",") if t]
         variants += [("vector", capi.KERNEL_CSR_VECTOR, l, "") for l in (2, 4, 8, 16, 32)]
@@ -165,9 +167,12 @@ def main():
             if kname in ("vector", "scalar") and info["max_row_nnz"] > 50000 and lanes != 32:
                 continue  # a 1M-nnz row on one thread / a narrow sub-warp would run for seconds
             for var in ("HISPMV_ADAPTIVE", "HISPMV_ROWSTAGE", "HISPMV_HOT", "HISPMV_MERGE_TILE", "HISPMV_PERSIST",
-                        "HISPMV_PIPELINE"):
+                        "HISPMV_PIPELINE", "HISPMV_WARPTILE"):
                 os.environ.pop(var, None)
             spec_s = tile
+            if spec_s.startswith("W"):
+                os.environ["HISPMV_WARPTILE"] = spec_s[1:]
+                spec_s = ""
             if spec_s.endswith("Q"):
                 spec_s = spec_s[:-1]
                 os.environ["HISPMV_PIPELINE"] = "1"

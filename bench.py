@@ -297,12 +297,22 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         bytes_alg_local = 8 * local_nnz + 4 * spec.cols + 4 * n_local      # nnz*(val+idx) + x + y
         achieved = bytes_alg_local / (kernel_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, sectors = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                args.workload + "_" + info["kernel_name"] + "_dram_bytes_per_launch") if world == 1 else None
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if world == 1 and args.scale == 1.0:
+                traffic = tj.get(args.workload + "_" + info["kernel_name"] + "_dram_bytes_per_launch")
+                sectors = tj.get(args.workload + "_" + info["kernel_name"] + "_l1_miss_sectors_per_launch")
         except Exception:
             pass
+        # second roofline: an SM takes in ~0.95 L1-miss sectors per clock (tools/gather_bench.cu); a
+        # scattered x gather costs a whole 32-byte sector.  sectors = ncu count for this kernel on this matrix.
+        gather_roofline = None
+        if sectors and clocks and clocks.get("sm_mhz"):
+            min_ms = sectors / (148 * 0.95 * clocks["sm_mhz"] * 1e6) * 1e3
+            gather_roofline = {"bound": "sm_l1_miss_sectors", "sectors_per_launch": sectors,
+                               "peak_sectors_per_clk_per_sm": 0.95, "min_ms": min_ms, "frac": min_ms / kernel_ms,
+                               "source": "ncu l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum (profiles/)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.workload == "c5" else "weak",
@@ -327,6 +337,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * spec.cols + 4 * n_local) * world,
                     "d2h_bytes_per_step": int(4 * spec.rows), "ms_per_step": e2e_ms,
                     "api": "hispmv_run (host x, bias -> host y), pinned host memory"},
+            "gather_roofline": gather_roofline,
             "phases": {"spmv_ms_max_over_ranks": kernel_ms_max, "x_broadcast_ms": bcast_ms,
                        "host_enqueue_ms_per_step": host_enqueue_ms,
                        "spmv_only_gflops": flops_step / (kernel_ms_max * 1e-3) / 1e9,

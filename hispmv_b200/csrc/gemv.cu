@@ -6,16 +6,31 @@
 // stream, so no tensor cores.  Design:
 //   * A is stored with a leading dimension padded to 4 floats, so every row starts 16-byte aligned and
 //     the stream is nothing but 128-bit evict-first loads (each element is read exactly once).
-//   * x is staged once per CTA in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier), then
-//     re-read from shared memory for every row the CTA owns.
+//   * x is read with 128-bit read-only loads and lives in L1 for all the rows a CTA owns (staging it in shared
+//     memory by a TMA bulk copy is implemented too, but measured slower: see launch_gemv).
 //   * A CTA owns a contiguous block of rows and all its threads sweep the columns of R rows at a time
 //     (R*unroll independent 16-byte loads in flight per thread); a shuffle + shared-memory reduction
 //     finishes each group of R rows.  Row blocks are sized so the grid is one wave of
 //     sm_count * CTAS_PER_SM CTAs.
+#include <cstdio>
+#include <cstdlib>
+
 #include "device_utils.cuh"
 #include "internal.h"
 
 namespace hispmv {
+
+// four consecutive entries of x (zero past the end): one 128-bit read-only load when x is 16-byte aligned, which it is
+// for cudaMalloc'ed vectors; x is tiny next to A and stays in L1 for all the rows a CTA owns
+__device__ __forceinline__ float4 load_x4(const float* __restrict__ x, int c, int cols, bool x_vec) {
+  if (x_vec && c + 3 < cols) return __ldg(reinterpret_cast<const float4*>(x + c));
+  float4 v;
+  v.x = c < cols ? __ldg(x + c) : 0.f;
+  v.y = c + 1 < cols ? __ldg(x + c + 1) : 0.f;
+  v.z = c + 2 < cols ? __ldg(x + c + 2) : 0.f;
+  v.w = c + 3 < cols ? __ldg(x + c + 3) : 0.f;
+  return v;
+}
 
 template <int THREADS, int R, bool STAGE_X>
 __global__ void __launch_bounds__(THREADS)
@@ -29,6 +44,7 @@ __global__ void __launch_bounds__(THREADS)
   const uint64_t ps = policy_evict_first();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ncol4 = (int)(A.ld >> 2);
+  const bool x_vec = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
 
   if (STAGE_X) {
     const bool bulk_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -63,16 +79,7 @@ __global__ void __launch_bounds__(THREADS)
         float4 a[R];
 #pragma unroll
         for (int q = 0; q < R; ++q) a[q] = ld_stream_f4(arow + (int64_t)q * A.ld + 4 * c4, ps);
-        float4 xv;
-        if (STAGE_X) {
-          xv = reinterpret_cast<const float4*>(s_x)[c4];
-        } else {
-          const int c = 4 * c4;
-          xv.x = c < A.cols ? __ldg(x + c) : 0.f;
-          xv.y = c + 1 < A.cols ? __ldg(x + c + 1) : 0.f;
-          xv.z = c + 2 < A.cols ? __ldg(x + c + 2) : 0.f;
-          xv.w = c + 3 < A.cols ? __ldg(x + c + 3) : 0.f;
-        }
+        const float4 xv = STAGE_X ? reinterpret_cast<const float4*>(s_x)[c4] : load_x4(x, 4 * c4, A.cols, x_vec);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
           acc[q] = fmaf(a[q].x, xv.x, acc[q]);
@@ -83,16 +90,7 @@ __global__ void __launch_bounds__(THREADS)
       }
     } else {
       for (int c4 = tid; c4 < ncol4; c4 += THREADS) {
-        float4 xv;
-        if (STAGE_X) {
-          xv = reinterpret_cast<const float4*>(s_x)[c4];
-        } else {
-          const int c = 4 * c4;
-          xv.x = c < A.cols ? __ldg(x + c) : 0.f;
-          xv.y = c + 1 < A.cols ? __ldg(x + c + 1) : 0.f;
-          xv.z = c + 2 < A.cols ? __ldg(x + c + 2) : 0.f;
-          xv.w = c + 3 < A.cols ? __ldg(x + c + 3) : 0.f;
-        }
+        const float4 xv = STAGE_X ? reinterpret_cast<const float4*>(s_x)[c4] : load_x4(x, 4 * c4, A.cols, x_vec);
 #pragma unroll
         for (int q = 0; q < R; ++q) {
           if (q < nr) {
@@ -122,12 +120,40 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
+namespace {
+template <int R, bool STAGE>
+int launch_gemv_inst(const DenseDev& A, const float* x, float* y, Epilogue ep, int64_t grid, int rows_per_cta,
+                     size_t x_bytes, cudaStream_t s) {
+  constexpr int THREADS = 256;
+  auto k = gemv_rowblock_kernel<THREADS, R, STAGE>;
+  if (STAGE) {
+    HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    k<<<(int)grid, THREADS, x_bytes, s>>>(A, x, y, ep, rows_per_cta);
+  } else {
+    k<<<(int)grid, THREADS, 0, s>>>(A, x, y, ep, rows_per_cta);
+  }
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+}  // namespace
+
 int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm_count, cudaStream_t s) {
   if (A.rows <= 0) return HISPMV_OK;
-  constexpr int THREADS = 256, R = 4;
   const size_t x_bytes = (size_t)A.ld * sizeof(float);
-  const bool stage = x_bytes <= 160 * 1024;
-  int ctas_per_sm = 4;
+  // x is read through L1 by default: staging it in shared memory (TMA bulk copy + mbarrier, kept as an option:
+  // HISPMV_GEMV=c,r,1) costs a start-up barrier per CTA and measured slower on every shape (50000 x 10000: 0.381 ms
+  // staged, 0.316 ms through L1).  Five CTAs of 256 threads per SM, four rows per group: 0.98 of the measured HBM
+  // peak on that shape; 8192^2 0.77-0.85, 8192 x 4096 0.69-0.72 (launch + ramp are a third of a 30 us kernel).
+  bool stage = false;
+  int ctas_per_sm = 5, r = 4;
+  if (const char* e = getenv("HISPMV_GEMV")) {  // "CTAS_PER_SM,R,STAGE" (development sweeps)
+    int c = 0, rr = 0, st = 0;
+    if (sscanf(e, "%d,%d,%d", &c, &rr, &st) == 3 && c >= 1 && c <= 8 && (rr == 2 || rr == 4 || rr == 8)) {
+      ctas_per_sm = c;
+      r = rr;
+      stage = st != 0 && x_bytes <= 160 * 1024;
+    }
+  }
   if (stage) {
     while (ctas_per_sm > 1 && (x_bytes + 1024) * ctas_per_sm > 200 * 1024) --ctas_per_sm;
   }
@@ -136,18 +162,13 @@ int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm
   const int rows_per_cta = (int)((A.rows + grid - 1) / grid);
   grid = (A.rows + rows_per_cta - 1) / rows_per_cta;
   if (stage) {
-    auto k = gemv_rowblock_kernel<THREADS, R, true>;
-    static bool attr_set = false;
-    if (!attr_set) {
-      HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      attr_set = true;
-    }
-    k<<<(int)grid, THREADS, x_bytes, s>>>(A, x, y, ep, rows_per_cta);
-  } else {
-    gemv_rowblock_kernel<THREADS, R, false><<<(int)grid, THREADS, 0, s>>>(A, x, y, ep, rows_per_cta);
+    if (r == 2) return launch_gemv_inst<2, true>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
+    if (r == 8) return launch_gemv_inst<8, true>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
+    return launch_gemv_inst<4, true>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
   }
-  HISPMV_CUDA(cudaGetLastError());
-  return HISPMV_OK;
+  if (r == 2) return launch_gemv_inst<2, false>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
+  if (r == 8) return launch_gemv_inst<8, false>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
+  return launch_gemv_inst<4, false>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
 }
 
 }  // namespace hispmv

@@ -61,7 +61,10 @@ def full(rep, tag, rnd):
             def get(m):
                 i = h.index(m)
                 return float(vals[i].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
-            traffic[tag] = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
+            traffic[tag + "_dram_bytes_per_launch"] = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
+            m = "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum"
+            if m in h:
+                traffic[tag + "_l1_miss_sectors_per_launch"] = float(vals[h.index(m)].replace(",", ""))
     return traffic
 
 
@@ -78,8 +81,7 @@ def main():
     tj = json.load(open(tpath)) if os.path.exists(tpath) else {}
     for spec in a.full:
         rep, tag = spec.rsplit(":", 1)
-        for k, v in full(rep, tag, a.round).items():
-            tj[k + "_dram_bytes_per_launch"] = v
+        tj.update(full(rep, tag, a.round))
     json.dump(tj, open(tpath, "w"), indent=1, sort_keys=True)
 
 

@@ -438,13 +438,13 @@ __global__ void __launch_bounds__(kGroup* kPsGroups, MINBLOCKS)
 // ================================================================================================================
 // row-major behind a TMA-staged stream.  Dynamic shared memory: col[CAP + 8] | val[CAP + 8].
 // ================================================================================================================
-template <int CAP, int LANES>
-__global__ void __launch_bounds__(kGroup)
+template <int CAP, int LANES, int THREADS>
+__global__ void __launch_bounds__(THREADS)
     spmv_rowstage_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(128) unsigned char s_raw[];
   int* s_col = reinterpret_cast<int*>(s_raw);
   float* s_val = reinterpret_cast<float*>(s_raw) + (CAP + 8);
-  __shared__ float s_red[kGroupWarps];
+  __shared__ float s_red[THREADS / 32];
   __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -454,12 +454,12 @@ __global__ void __launch_bounds__(kGroup)
   const GatherL1<false> gx{x, P.hot_cols, pk};  // banded matrices reuse every gathered line a few rows later
   if (d.chunk >= 0) {
     float acc = 0.0f;
-    stream_products(A, gx, d.n0, d.n1, tid, ps, [&](int, float p) { acc += p; });
+    stream_products<THREADS>(A, gx, d.n0, d.n1, tid, ps, [&](int, float p) { acc += p; });
     acc = warp_sum(acc);
     if (lane == 0) s_red[warp] = acc;
     __syncthreads();
     if (warp != 0) return;
-    float total = lane < kGroupWarps ? s_red[lane] : 0.0f;
+    float total = lane < THREADS / 32 ? s_red[lane] : 0.0f;
     total = warp_sum(total);
     finish_chunk(P, d, t, total, lane, y, ep);
     return;
@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(kGroup)
     bulk_g2s_hint(s_col, A.col + a0, (uint32_t)cnt * 4u, &s_bar, ps);
     bulk_g2s_hint(s_val, A.val + a0, (uint32_t)cnt * 4u, &s_bar, ps);
   }
-  constexpr int R = kGroup / LANES;  // rows per pass
+  constexpr int R = THREADS / LANES;  // rows per pass
   const int sub = tid % LANES, g = tid / LANES;
   // row extents of the first pass are fetched while the bulk copies fly
   int b = 0, e = 0;
@@ -786,28 +786,28 @@ int launch_persistent_cap(const CsrDev& A, const AdaptivePlan& P, const float* x
   return HISPMV_ERR_ARG;
 }
 
-template <int CAP, int LANES>
+template <int CAP, int LANES, int THREADS>
 int launch_rowstage_inst(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
                          cudaStream_t s) {
-  auto k = spmv_rowstage_kernel<CAP, LANES>;
+  auto k = spmv_rowstage_kernel<CAP, LANES, THREADS>;
   constexpr int smem = (CAP + 8) * 8;
   HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = (int)(P.tile_count >= 0 ? P.tile_count : P.num_tiles);
   if (grid <= 0) return HISPMV_OK;
-  k<<<grid, kGroup, smem, s>>>(A, P, x, y, ep);
+  k<<<grid, THREADS, smem, s>>>(A, P, x, y, ep);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }
-template <int CAP>
+template <int CAP, int THREADS>
 int launch_rowstage_cap(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
                         cudaStream_t s) {
   switch (lanes) {
-    case 1: return launch_rowstage_inst<CAP, 1>(A, P, x, y, ep, s);
-    case 2: return launch_rowstage_inst<CAP, 2>(A, P, x, y, ep, s);
-    case 4: return launch_rowstage_inst<CAP, 4>(A, P, x, y, ep, s);
-    case 8: return launch_rowstage_inst<CAP, 8>(A, P, x, y, ep, s);
-    case 16: return launch_rowstage_inst<CAP, 16>(A, P, x, y, ep, s);
-    case 32: return launch_rowstage_inst<CAP, 32>(A, P, x, y, ep, s);
+    case 1: return launch_rowstage_inst<CAP, 1, THREADS>(A, P, x, y, ep, s);
+    case 2: return launch_rowstage_inst<CAP, 2, THREADS>(A, P, x, y, ep, s);
+    case 4: return launch_rowstage_inst<CAP, 4, THREADS>(A, P, x, y, ep, s);
+    case 8: return launch_rowstage_inst<CAP, 8, THREADS>(A, P, x, y, ep, s);
+    case 16: return launch_rowstage_inst<CAP, 16, THREADS>(A, P, x, y, ep, s);
+    case 32: return launch_rowstage_inst<CAP, 32, THREADS>(A, P, x, y, ep, s);
   }
   set_error("rowstage: lanes must be 1,2,4,8,16 or 32");
   return HISPMV_ERR_ARG;
@@ -911,16 +911,20 @@ int launch_pipeline(const CsrDev& A, const AdaptivePlan& P, const float* x, floa
   return launch_pipeline_inst<kPipelineCap, kPipelineRows + 8, 5, false>(A, P, x, y, ep, sm_count, s);
 }
 
-int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
-                    cudaStream_t s) {
+int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, int threads, const float* x, float* y,
+                    Epilogue ep, cudaStream_t s) {
   if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
   int st = check_plan(P, kRowstageMaxCap, "rowstage");
   if (st != HISPMV_OK) return st;
   const int need = P.stream_items + P.long_threshold;
-  if (need <= 2048) return launch_rowstage_cap<2048>(A, P, lanes, x, y, ep, s);
-  if (need <= 4096) return launch_rowstage_cap<4096>(A, P, lanes, x, y, ep, s);
-  if (need <= 6144) return launch_rowstage_cap<6144>(A, P, lanes, x, y, ep, s);
-  return launch_rowstage_cap<8192>(A, P, lanes, x, y, ep, s);
+  if (threads == 128) {  // small tiles, up to 16 CTAs per SM: more independent load -> gather -> reduce chains in flight
+    if (need <= 2048) return launch_rowstage_cap<2048, 128>(A, P, lanes, x, y, ep, s);
+    return launch_rowstage_cap<4096, 128>(A, P, lanes, x, y, ep, s);
+  }
+  if (need <= 2048) return launch_rowstage_cap<2048, 256>(A, P, lanes, x, y, ep, s);
+  if (need <= 4096) return launch_rowstage_cap<4096, 256>(A, P, lanes, x, y, ep, s);
+  if (need <= 6144) return launch_rowstage_cap<6144, 256>(A, P, lanes, x, y, ep, s);
+  return launch_rowstage_cap<8192, 256>(A, P, lanes, x, y, ep, s);
 }
 
 }  // namespace hispmv

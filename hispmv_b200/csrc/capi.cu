@@ -59,6 +59,7 @@ struct Matrix {
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
   bool pipeline = false;                // ADAPTIVE: warp-specialised persistent pipeline (TMA ring)
   bool warptile = false;                // ADAPTIVE: one warp per (small) tile, no CTA barrier
+  int rowstage_threads = 128;           // ROWSTAGE: threads per CTA (128; 256 through the development switch)
   ColProbe probe{};                     // column-locality probe (selector input)
   // dense
   float* d_a = nullptr;
@@ -243,14 +244,16 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
       }
     } else {
       rowstage_params(m->stats, m->lanes, &m->lanes, &m->tile_items, &m->long_threshold, &m->chunk_nnz);
-      if (const char* e = getenv("HISPMV_ROWSTAGE")) {  // "LANES,B,T,CH" (development sweeps)
-        int l = 0, b = 0, t = 0, ch = 0;
-        if (sscanf(e, "%d,%d,%d,%d", &l, &b, &t, &ch) == 4 && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && b >= 256 &&
+      m->rowstage_threads = 128;
+      if (const char* e = getenv("HISPMV_ROWSTAGE")) {  // "LANES,B,T,CH[,THREADS]" (development sweeps)
+        int l = 0, b = 0, t = 0, ch = 0, th = 256;
+        if (sscanf(e, "%d,%d,%d,%d,%d", &l, &b, &t, &ch, &th) >= 4 && (th == 128 || th == 256) && l >= 1 && l <= 32 && (l & (l - 1)) == 0 && b >= 128 &&
             t >= 16 && b + t <= kRowstageMaxCap && ch >= 1024) {
           m->lanes = l;
           m->tile_items = b;
           m->long_threshold = t;
           m->chunk_nnz = ch;
+          m->rowstage_threads = th;
         }
       }
     }
@@ -543,7 +546,8 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.tile_begin = tile_begin;
       P.tile_count = tile_count;
       P.sched = m->d_counter + (size_t)std::max<int64_t>(m->num_tiles, 1) * 2 + 4 * (size_t)lane;
-      if (m->kernel == HISPMV_KERNEL_ROWSTAGE) return launch_rowstage(A, P, m->lanes, d_x, d_y, ep, s);
+      if (m->kernel == HISPMV_KERNEL_ROWSTAGE)
+        return launch_rowstage(A, P, m->lanes, m->rowstage_threads, d_x, d_y, ep, s);
       if (m->warptile) return launch_warptile(A, P, d_x, d_y, ep, s);
       if (m->pipeline) return launch_pipeline(A, P, d_x, d_y, ep, c->sm_count, s);
       if (m->persistent) return launch_adaptive_persistent(A, P, d_x, d_y, ep, c->sm_count, s);

@@ -163,8 +163,8 @@ constexpr int kPipelineCap = 1920, kPipelineRows = 1408;  // CAP = 6 gathers x 3
 int launch_pipeline(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, int sm_count,
                     cudaStream_t s);
 // Row-major STREAM tiles behind a TMA-staged stream (regular rows with column locality); `lanes` lanes per row.
-int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, const float* x, float* y, Epilogue ep,
-                    cudaStream_t s);
+int launch_rowstage(const CsrDev& A, const AdaptivePlan& P, int lanes, int threads, const float* x, float* y,
+                    Epilogue ep, cudaStream_t s);
 constexpr int kRowstageMaxCap = 8192;
 int launch_empty(int32_t rows, float* y, Epilogue ep, cudaStream_t s);
 bool merge_tile_items_supported(int tile_items);

@@ -287,14 +287,14 @@ void oracle_rowstage_params(int rows, int64_t nnz, int lanes_in, int* lanes, int
   int64_t b;
   if (l <= 0) {
     l = 1;
-    while (l < 32 && (256 / l) * items > 4096) l *= 2;
+    while (l < 32 && (128 / l) * items > 1792) l *= 2;
   }
-  b = (256 / l) * items;
-  if (b > 8192 - 512) b = 8192 - 512;
-  if (b < 256) b = 256;
+  b = (128 / l) * items;
+  if (b > 8192 - 256) b = 8192 - 256;
+  if (b < 128) b = 128;
   *lanes = l;
   *stream_items = (int)b;
-  *long_threshold = 512;
+  *long_threshold = 256;
   *chunk_nnz = 4096;
 }
 

@@ -121,10 +121,19 @@ def run_reference(args):
     import oracle_lib as ol
     from hispmv_b200 import synth
     ol.build()
-    spec = synth.c5_uniform(args.scale) if args.workload == "c5" else synth.c2_powerlaw(args.scale)
+    world = max(1, int(os.environ.get("WORLD_SIZE", str(args.gpus))))
+    if args.workload == "c5":
+        full = synth.c5_uniform(args.scale)
+        # bounded sample: the first tenth of the rows (rows are independent; 100 M nnz, about 30 ms per MKL call)
+        sample_rows = max(1, full.rows // 10)
+    else:
+        base = synth.c2_powerlaw(args.scale)
+        full = synth.SynthSpec(base.name, base.kind, base.seed, base.rows * world, base.cols, base.params)
+        sample_rows = base.rows   # bounded sample: the first 10 M rows = exactly the N=1 matrix (rows are hash-generated)
+    spec = synth.SynthSpec(full.name, full.kind, full.seed, sample_rows, full.cols, full.params)
     threads = os.cpu_count() or 1
     t0 = time.time()
-    rp, ci, vv = host_matrix(spec, 0, spec.rows)
+    rp, ci, vv = host_matrix(full, 0, sample_rows)
     t_gen = time.time() - t0
     x, _ = synth.reference_vectors(spec.rows, spec.cols)
     kind = "reference" if ol.have_ref() else "port"
@@ -139,12 +148,14 @@ def run_reference(args):
         ns = (time.time() - t0) / args.steps * 1e9
     nnz = int(ci.size)
     gflops = 2.0 * (nnz + spec.rows) / ns
-    sample = f"full matrix ({nnz} nnz), {args.steps} calls after {args.warmup} warm-up, host-generated in {t_gen:.1f}s"
+    sample = (f"rows [0, {sample_rows}) of the {full.rows}-row workload ({nnz} nnz; rows are independent and "
+              f"hash-generated, so this is the N=1 matrix), {args.steps} mkl_sparse_s_mv calls after {args.warmup} "
+              f"warm-up, host-generated in {t_gen:.1f}s")
     line = {
         "impl": "reference", "metric": METRIC, "value": gflops, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ns * 1e-6, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(spec, 1), "rows": spec.rows, "cols": spec.cols, "nnz": nnz,
+        "config": {"workload": workload_name(full, world), "rows": full.rows, "cols": full.cols, "sample_nnz": nnz,
                    "what": "mkl_sparse_s_mv via the reference's mkl_spmv (cpu/src/main.cpp:26-49), libtorch's MKL"
                            if kind == "reference" else "oracle port of cpu_spmv"},
         "cpu_baseline": {"value": gflops, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},

@@ -5,29 +5,31 @@
 //   AccumBuffer / Compute_C      y_Ax[row] += ..., alpha/beta        base_functions.cpp:475-488, 535
 //   balanceWorkload / prepareTile (the balanced schedule)            common/src/spmv-helper.cpp:265-347, 517-638
 //
-// Two measured facts shape them (tools/gather_bench.cu, tools/dsmem_bench.cu):
-//   * an SM can send only ~0.95 L1-miss requests per clock to L2, whatever their size (4 or 16 bytes), whether or not
-//     they allocate in L1; a gather instruction costs one request per distinct line its 32 lanes touch.  On
-//     gather-heavy matrices this, not HBM, is the ceiling, so lanes are mapped to nonzeros in the order that makes them
-//     share lines, and everything that can be served on-chip is;
-//   * shared-memory hits are nearly free next to that (275 G gathers/s become 275 / (1 - hit rate)), while
-//     distributed shared memory across a cluster is slower than L2 for 4-byte gathers (51-184 G/s) and is not used.
+// Measured facts that shape them (tools/gather_bench.cu, tools/dsmem_bench.cu):
+//   * an SM takes in only ~0.95 L1-miss sectors per clock, whatever their payload (4 or 16 bytes) and whether or not
+//     they allocate in L1; a scattered x gather costs a whole 32-byte sector.  On gather-heavy matrices this, not
+//     HBM, is the ceiling (C2: 107 M sectors per SpMV = 0.387 ms, the kernel takes 0.38), so lanes are mapped to
+//     nonzeros in the order that makes them share sectors, and per-tile latency chains are kept short and numerous;
+//   * hits served on-chip are nearly free next to that, distributed shared memory is slower than L2 for 4-byte
+//     gathers, more than ~190 KB of shared memory per SM throttles the miss path, __threadfence() flushes L1.
 //
 // Tiles (TileDesc, 32 bytes, built once per plan so that a tile costs one metadata load instead of a chain of four):
 //   STREAM  consecutive rows, each shorter than the long threshold, about stream_items row ends + nonzeros
 //   LONG    one chunk (<= chunk_nnz nonzeros) of a row at or above the threshold; a row with several chunks is
-//           "split": every chunk drops its partial sum in carry[tile], the chunk that arrives last at the row's
-//           counter adds the partials in chunk order and writes y -- one launch, no atomics on y, bit-reproducible.
+//           "split": every chunk drops its partial sum in carry[tile] (a data flag, see finish_chunk), the chunk that
+//           arrives last at the row's counter adds the partials in chunk order and writes y -- one launch, no atomics
+//           on y, no fence, bit-reproducible.
 //
 // Kernels:
-//   spmv_adaptive_kernel             nnz-major, one CTA per tile (small matrices, no usable x window)
-//   spmv_adaptive_persistent_kernel  nnz-major, one or two resident CTAs per SM, x[0, hot) in shared memory,
-//                                    tiles pulled from a global counter with metadata / L2 prefetch one tile ahead
-//   spmv_rowstage_kernel             row-major behind a TMA-staged col/val stream (banded / stencil / FEM rows)
+//   spmv_adaptive_kernel   nnz-major, one CTA per tile (the default for irregular rows)
+//   spmv_rowstage_kernel   row-major behind a TMA-staged col/val stream (banded / stencil / FEM rows)
+//   research switches, tested but never auto-selected: spmv_warptile_kernel (one warp per tile),
+//   spmv_adaptive_persistent_kernel (resident CTAs, x window in shared memory), spmv_pipeline_kernel
+//   (warp-specialised TMA producer -> mbarrier ring -> gather/reduce teams)
 // nnz-major: lane l of a warp takes nonzero base+l -- 128-byte coalesced col/val loads, and the 32 gathers of one
-//   instruction cover consecutive nonzeros, which are column-sorted inside a row and therefore share lines; products
-//   go to shared memory and each warp then reduces a slice of the tile's rows (one lane per short row, 8 lanes or the
-//   whole warp for longer ones).
+//   instruction cover consecutive nonzeros, which are column-sorted inside a row and therefore share sectors; products
+//   go to shared memory and each warp then reduces a slice of the tile's rows (one lane per row of up to 16 products,
+//   the whole warp for longer ones).
 // row-major: LANES lanes walk each row, so the gathers of one instruction cover the same position of 32/LANES
 //   consecutive rows -- on banded matrices consecutive columns, i.e. one or two lines instead of up to 32.
 #include <limits.h>
@@ -230,11 +232,12 @@ __device__ __forceinline__ TileDesc load_desc(const TileDesc* p) {
 // ================================================================================================================
 // one CTA per tile
 // ================================================================================================================
-template <int CAP, bool SPLIT>  // CAP >= stream_items + long_threshold: products a STREAM tile may hold
-__global__ void __launch_bounds__(kGroup, 8)
+template <int CAP, bool SPLIT, int THREADS>  // CAP >= stream_items + long_threshold: products of a STREAM tile
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS)
     spmv_adaptive_kernel(CsrDev A, AdaptivePlan P, const float* __restrict__ x, float* __restrict__ y, Epilogue ep) {
   __shared__ float s_prod[CAP];
-  __shared__ float s_red[kGroupWarps];
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_red[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t = P.tile_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
@@ -242,12 +245,12 @@ __global__ void __launch_bounds__(kGroup, 8)
   const GatherL1<SPLIT> gx{x, P.hot_cols, pk};
   if (d.chunk >= 0) {
     float acc = 0.0f;
-    stream_products(A, gx, d.n0, d.n1, tid, ps, [&](int, float p) { acc += p; });
+    stream_products<THREADS>(A, gx, d.n0, d.n1, tid, ps, [&](int, float p) { acc += p; });
     acc = warp_sum(acc);
     if (lane == 0) s_red[warp] = acc;
     __syncthreads();
     if (warp != 0) return;
-    float total = lane < kGroupWarps ? s_red[lane] : 0.0f;
+    float total = lane < WARPS ? s_red[lane] : 0.0f;
     total = warp_sum(total);
     finish_chunk(P, d, t, total, lane, y, ep);
     return;
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(kGroup, 8)
   const int n0 = d.n0;
   // the extents of this lane's first row are requested before the stream so that their DRAM round trip overlaps it
   const int trows = d.r1 - d.r0;
-  const int rpw = (trows + kGroupWarps - 1) / kGroupWarps;
+  const int rpw = (trows + WARPS - 1) / WARPS;
   const int beg = warp * rpw, end = min(trows, beg + rpw);
   int b0 = 0, e0 = 0;
   float bias0 = 0.0f;
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(kGroup, 8)
     e0 = A.row_ptr[d.r0 + beg + lane + 1];
     if (ep.beta != 0.0f) bias0 = ep.bias[d.r0 + beg + lane];
   }
-  stream_products(A, gx, n0, d.n1, tid, ps, [&](int i, float p) { s_prod[i - n0] = p; });
+  stream_products<THREADS>(A, gx, n0, d.n1, tid, ps, [&](int i, float p) { s_prod[i - n0] = p; });
   __syncthreads();
   rows_from_products(A, d.r0, n0, beg, end, b0 - n0, e0 - n0, bias0, s_prod, lane, y, ep);
 }
@@ -827,7 +830,8 @@ int check_plan(const AdaptivePlan& P, int max_cap, const char* who) {
 
 }  // namespace
 
-int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s) {
+int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, int threads, const float* x, float* y, Epilogue ep,
+                    cudaStream_t s) {
   if (A.rows <= 0 || P.num_tiles <= 0) return HISPMV_OK;
   int st = check_plan(P, 4096, "adaptive");
   if (st != HISPMV_OK) return st;
@@ -835,15 +839,23 @@ int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, floa
   const int grid = (int)(P.tile_count >= 0 ? P.tile_count : P.num_tiles);
   if (grid <= 0) return HISPMV_OK;
   const bool split = P.hot_cols != 0x7fffffff;
-  if (need <= 2048) {
-    if (split) spmv_adaptive_kernel<2048, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
-    else spmv_adaptive_kernel<2048, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+  if (threads == 128 && need <= 2048) {
+    if (need <= 1024) {
+      if (split) spmv_adaptive_kernel<1024, true, 128><<<grid, 128, 0, s>>>(A, P, x, y, ep);
+      else spmv_adaptive_kernel<1024, false, 128><<<grid, 128, 0, s>>>(A, P, x, y, ep);
+    } else {
+      if (split) spmv_adaptive_kernel<2048, true, 128><<<grid, 128, 0, s>>>(A, P, x, y, ep);
+      else spmv_adaptive_kernel<2048, false, 128><<<grid, 128, 0, s>>>(A, P, x, y, ep);
+    }
+  } else if (need <= 2048) {
+    if (split) spmv_adaptive_kernel<2048, true, kGroup><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    else spmv_adaptive_kernel<2048, false, kGroup><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
   } else if (need <= 3072) {
-    if (split) spmv_adaptive_kernel<3072, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
-    else spmv_adaptive_kernel<3072, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    if (split) spmv_adaptive_kernel<3072, true, kGroup><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    else spmv_adaptive_kernel<3072, false, kGroup><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
   } else {
-    if (split) spmv_adaptive_kernel<4096, true><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
-    else spmv_adaptive_kernel<4096, false><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    if (split) spmv_adaptive_kernel<4096, true, kGroup><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
+    else spmv_adaptive_kernel<4096, false, kGroup><<<grid, kGroup, 0, s>>>(A, P, x, y, ep);
   }
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;

@@ -59,6 +59,7 @@ struct Matrix {
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
   bool pipeline = false;                // ADAPTIVE: warp-specialised persistent pipeline (TMA ring)
   bool warptile = false;                // ADAPTIVE: one warp per (small) tile, no CTA barrier
+  int adaptive_threads = 256;           // ADAPTIVE: threads per CTA (256; 128 through the development switch)
   int rowstage_threads = 128;           // ROWSTAGE: threads per CTA (128; 256 through the development switch)
   ColProbe probe{};                     // column-locality probe (selector input)
   // dense
@@ -233,13 +234,15 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
       m->tile_items = kAdaptiveStreamItems;
       m->long_threshold = kAdaptiveLongThreshold;
       m->chunk_nnz = kAdaptiveChunkNnz;
-      if (const char* e = getenv("HISPMV_ADAPTIVE")) {  // "B,T,CH" (development sweeps)
-        int b = 0, t = 0, ch = 0;
-        if (sscanf(e, "%d,%d,%d", &b, &t, &ch) == 3 && b >= 256 && t >= 16 && b + t <= 4096 && ch >= 1024 &&
-            ch <= 4096) {
+      m->adaptive_threads = 256;
+      if (const char* e = getenv("HISPMV_ADAPTIVE")) {  // "B,T,CH[,THREADS]" (development sweeps)
+        int b = 0, t = 0, ch = 0, th = 256;
+        if (sscanf(e, "%d,%d,%d,%d", &b, &t, &ch, &th) >= 3 && b >= 128 && t >= 16 && b + t <= 4096 && ch >= 512 &&
+            ch <= 65536 && (th == 128 || th == 256)) {
           m->tile_items = b;
           m->long_threshold = t;
           m->chunk_nnz = ch;
+          m->adaptive_threads = th;
         }
       }
     } else {
@@ -551,7 +554,7 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       if (m->warptile) return launch_warptile(A, P, d_x, d_y, ep, s);
       if (m->pipeline) return launch_pipeline(A, P, d_x, d_y, ep, c->sm_count, s);
       if (m->persistent) return launch_adaptive_persistent(A, P, d_x, d_y, ep, c->sm_count, s);
-      return launch_adaptive(A, P, d_x, d_y, ep, s);
+      return launch_adaptive(A, P, m->adaptive_threads, d_x, d_y, ep, s);
     }
     default: set_error("run: matrix has no plan"); return HISPMV_ERR_STATE;
   }

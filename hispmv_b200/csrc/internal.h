@@ -148,7 +148,8 @@ struct Epilogue {
 int launch_csr_scalar(const CsrDev& A, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_csr_vector(const CsrDev& A, int lanes, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_merge(const CsrDev& A, const MergePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
-int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
+int launch_adaptive(const CsrDev& A, const AdaptivePlan& P, int threads, const float* x, float* y, Epilogue ep,
+                    cudaStream_t s);
 constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdaptiveChunkNnz = 4096;
 // Persistent nnz-major kernel: one CTA per SM, x[0, hot_cols) held in shared memory, tiles pulled from P.sched.
 int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,

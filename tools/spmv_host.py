@@ -1,0 +1,130 @@
+#!/usr/bin/env python
+"""spmv-host for the GPU engine: the reference's stand-alone self-checking host program (common/src/spmv-host.cpp:41-191)
+with the same protocol and the same log lines, so that builds/collect_data.py:8-23 scrapes its output unchanged.
+
+    python tools/spmv_host.py <matrix.mtx>            [--exec_ms 1000] [--device 0]
+    python tools/spmv_host.py <dense rows> <dense cols> [--exec_ms 1000]
+
+Protocol (spmv-host.cpp:17-23,43-44,92-100,181-189): x = c_in = (i+2)/(i+1), alpha = 0.55, beta = -2.05; a CPU result
+(scipy CSR product in fp32 here; the reference uses its own cpuSequential) is compared with the accelerator's through
+the relative-error histogram of printErrorStats (common/src/spmv-helper.cpp:835-895); GFLOPS = 2 (nnz + rows) / time.
+The accelerator time is the mean of as many back-to-back device-resident runs as fit in --exec_ms ("rp_time").
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def generate_vector(n: int) -> np.ndarray:
+    i = np.arange(n, dtype=np.float32)
+    return ((i + np.float32(2.0)) / (i + np.float32(1.0))).astype(np.float32)   # spmv-host.cpp:17-23
+
+
+def print_error_stats(cpu_ref: np.ndarray, out: np.ndarray) -> None:
+    a, b = np.abs(out.astype(np.float64)), np.abs(cpu_ref.astype(np.float64))
+    ref = np.maximum(b, np.finfo(np.float64).tiny)
+    rel = np.abs(a - ref) / ref
+    rel = rel[rel != 0]
+    if rel.size == 0:
+        print("No mismatch found")
+        return
+    if rel.size <= 10:
+        print("Found atmost 10 mismatches, Relative Errors:")
+        for e in rel:
+            print(f"\t{e}")
+        return
+    lo, hi = rel.min(), rel.max()
+    counts, edges = np.histogram(rel, bins=10, range=(lo, hi))
+    print("Relative Error Range:\tCount")
+    for k in range(10):
+        print(f"[{edges[k]:.3e}, {edges[k + 1]:.3e}):\t{counts[k]}")
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("args", nargs="+", help="<matrix.mtx>  |  <dense rows> <dense cols>")
+    ap.add_argument("--exec_ms", type=float, default=1000.0, help="time budget for the repeated runs (reference: --exec_ms)")
+    ap.add_argument("--device", type=int, default=0)
+    a = ap.parse_args()
+    import scipy.sparse as sp
+    import torch
+    from hispmv_b200 import Engine
+
+    alpha, beta = 0.55, -2.05                                   # spmv-host.cpp:43-44
+    eng = Engine(a.device)
+    print("\nPreparing A Mtx...")
+    t0 = time.perf_counter()
+    if len(a.args) == 1:
+        idx = eng.load_mtx(a.args[0])
+        dense = None
+    elif len(a.args) == 2:
+        rows, cols = int(a.args[0]), int(a.args[1])
+        dense = generate_vector(rows * cols).reshape(rows, cols)  # spmv-host.cpp:71-79
+        idx = eng.create_dense_handle(dense.reshape(-1), rows, cols)
+    else:
+        print(f"Sparse Mode Usage: {sys.argv[0]} <sparse mtx>\nDense Mode Usage: {sys.argv[0]} <rows> <cols>", file=sys.stderr)
+        return 1
+    eng.load_matrices()
+    print(f"Pre-processing Time: {time.perf_counter() - t0:.6f} secs")
+    info = eng.matrix_info(idx)
+    rows, cols, nnz = info["rows"], info["cols"], info["nnz"]
+    print(f"Matrix A Length: {nnz}")
+    print(f"Kernel: {info['kernel_name']} lanes={info['vector_lanes']} tiles={info['num_tiles']} "
+          f"split rows={info['num_split_rows']} column slabs={info.get('num_slabs', 0)}")
+    x, c_in = generate_vector(cols), generate_vector(rows)
+
+    print("\nComputing on CPU... ")
+    if dense is None:
+        rp, ci, vv = eng.plan_csr(idx)
+        m = sp.csr_matrix((vv, ci, rp), shape=(rows, cols))
+    t0 = time.perf_counter()
+    ax = (m @ x) if dense is None else (dense @ x)
+    cpu = (np.float32(alpha) * ax.astype(np.float32) + np.float32(beta) * c_in).astype(np.float32)
+    t_cpu = time.perf_counter() - t0
+    print(f"CPU TIME: {t_cpu * 1e3:.6f} ms")
+    print(f"CPU GFLOPS: {2.0 * (nnz + rows) / (t_cpu * 1e9):.6f}")
+
+    print("\nComputing on GPU... ")
+    xd, cd = torch.from_numpy(x).cuda(a.device), torch.from_numpy(c_in).cuda(a.device)
+    yd = torch.empty(rows, device=xd.device)
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
+    e1.record()
+    e1.synchronize()
+    rp_time = max(1, min(100000, int(a.exec_ms / max(e0.elapsed_time(e1), 1e-3))))
+    print(f"Using Repeat Time: {rp_time}")
+    e0.record()
+    for _ in range(rp_time):
+        eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
+    e1.record()
+    e1.synchronize()
+    total_ms = e0.elapsed_time(e1)
+    t_us = total_ms * 1e3 / rp_time
+    print(f"Total Kernel Runtime: {total_ms:.6f}ms")
+    print(f"FPGA TIME: {t_us:.6f}us")                              # key names kept for builds/collect_data.py
+    print(f"FPGA GFLOPS: {2.0 * (nnz + rows) / (t_us * 1e3):.6f}")
+    # the host-buffer call the plugin makes (copies inside)
+    y = np.zeros(rows, np.float32)
+    eng.select_matrix(idx)
+    eng.run_kernel(x, c_in, y, alpha, beta)
+    print()
+    print_error_stats(cpu, y)
+    eng.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,41 @@
+// x replication over NVSwitch multicast (NVLS): the rank that owns x stores it once to a multicast address and the
+// switch delivers the stores to every GPU of the group -- no SM on the receiving side runs anything, and the sender's
+// NVLink egress carries x once instead of once per peer.  The multicast mapping itself comes from
+// torch.distributed._symmetric_memory (device memory + rendezvous are plumbing); the store kernel is ours.
+#include "device_utils.cuh"
+#include "internal.h"
+
+namespace hispmv {
+namespace {
+
+__global__ void __launch_bounds__(512) multicast_copy_kernel(float* __restrict__ mc_dst, const float* __restrict__ src,
+                                                             int64_t n4, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + 4 * i), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+  }
+  // tail (n not a multiple of 4)
+  const int64_t t = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(mc_dst + t), "f"(src[t]) : "memory");
+  __threadfence_system();
+}
+
+}  // namespace
+}  // namespace hispmv
+
+using namespace hispmv;
+
+extern "C" int hispmv_multicast_copy(void* mc_dst, const float* d_src, int64_t n, int sm_budget, void* stream) {
+  if (!mc_dst || !d_src || n < 0 || (reinterpret_cast<uintptr_t>(mc_dst) & 15) || (reinterpret_cast<uintptr_t>(d_src) & 15)) {
+    set_error("multicast_copy: pointers must be 16-byte aligned");
+    return HISPMV_ERR_ARG;
+  }
+  if (n == 0) return HISPMV_OK;
+  const int grid = sm_budget > 0 ? sm_budget : 16;  // a few CTAs saturate one GPU's NVLink egress
+  multicast_copy_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(static_cast<float*>(mc_dst), d_src, n / 4, n);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}

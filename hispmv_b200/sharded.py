@@ -69,6 +69,63 @@ class RowBlockComm:
         return x
 
 
+class XReplicator:
+    """x produced on one rank -> a replica on every rank, double-buffered so that the exchange of step k+1 runs under
+    the SpMV of step k.
+
+    mode "multicast": the replicas live in symmetric memory (torch.distributed._symmetric_memory: allocation and
+    rendezvous only) and the root stores x ONCE to the NVSwitch multicast address with hispmv_multicast_copy
+    (multimem.st): the switch delivers it to every GPU, no SM on the receivers runs anything, and the root's NVLink
+    egress carries x once instead of once per peer.  Two small device-side barriers per exchange order it against the
+    readers.  mode "nccl": dist.broadcast.  "auto" tries multicast and falls back to NCCL."""
+
+    def __init__(self, n: int, device, group=None, mode: str = "auto", root: int = 0):
+        self.n, self.device, self.group, self.root = n, device, group, root
+        self.rank = dist.get_rank(group)
+        self.npad = (n + 3) & ~3
+        self.mode = "nccl"
+        self._hdl = None
+        if mode in ("auto", "multicast"):
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(2 * self.npad, dtype=torch.float32, device=device)
+                hdl = symm_mem.rendezvous(buf, group=group if group is not None else dist.group.WORLD)
+                if not hdl.multicast_ptr:
+                    raise RuntimeError("no multicast mapping (NVLS unavailable)")
+                self._hdl, self._buf, self.mode = hdl, buf, "multicast"
+            except Exception as ex:  # noqa: BLE001
+                if mode == "multicast":
+                    raise
+                self._why = f"{type(ex).__name__}: {ex}"
+        if self.mode == "nccl":
+            self._buf = torch.empty(2 * self.npad, dtype=torch.float32, device=device)
+        self._buf.zero_()
+
+    def buffer(self, k: int) -> torch.Tensor:
+        """This rank's replica k (k & 1): what the SpMV of step k reads."""
+        o = (k & 1) * self.npad
+        return self._buf[o:o + self.n]
+
+    def replicate(self, k: int, src_on_root: Optional[torch.Tensor], stream: torch.cuda.Stream) -> None:
+        """Enqueue on `stream` the exchange that fills replica k on every rank from `src_on_root` (root only)."""
+        with torch.cuda.stream(stream):
+            if self.mode == "nccl":
+                b = self.buffer(k)
+                if self.rank == self.root and src_on_root is not None and src_on_root.data_ptr() != b.data_ptr():
+                    b.copy_(src_on_root)
+                dist.broadcast(b, src=self.root, group=self.group)
+                return
+            import ctypes as C
+            from .capi import lib, check
+            cur = k & 1
+            self._hdl.barrier(channel=cur)          # every rank is done reading replica `cur`
+            if self.rank == self.root:
+                mc = self._hdl.multicast_ptr + cur * self.npad * 4
+                check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(src_on_root.data_ptr()), self.n, 16,
+                                                C.c_void_p(stream.cuda_stream)), "multicast_copy")
+            self._hdl.barrier(channel=2 + cur)      # the stores have landed everywhere
+
+
 class ShardedEngine:
     """An Engine that keeps row block `rank` of `world` of every matrix, plus the collectives around it."""
 

@@ -549,3 +549,138 @@ int64_t oracle_load_mtx(const char* path, int* rows, int* cols, int* coo_r, int*
   fclose(f);
   return n;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Packed PEG stream decoder / emulator.  The reference host library packs a matrix into
+ * num_ch_A streams of 64-bit words, pes_per_ch PEs interleaved per channel
+ *     word = rowEnd[63] row15[62:48] tileEnd[47] shared[46] col14[45:32] val32[31:0]
+ * (encode, common/include/spmv-helper.h:45-60; layout written by prepareTile, common/src/spmv-helper.cpp:517-638:
+ * word k of PE p of tile t sits at channel p / pes_per_ch, address tile_offset + k * pes_per_ch + p % pes_per_ch).
+ * The accelerator consumes it as restated here:
+ *   ComputeAB       (automation_tool/assets/base_functions.cpp:228-241)  product = val * x_window[col14]; the flags
+ *                   of a PE pair come from the EVEN PE's word
+ *   PreAccumulator  (:295-305,330)  shared pair: destination bank = row field of the even PE (low bits), row16 = row
+ *                   field of the odd PE; a word is a dummy when its rowEnd bit is clear (every real entry has it set)
+ *   ADD / SWB / SSW (:356-436)      partials of one shared row from all PEs are tree-added, then routed to the bank
+ *                   (restated as a pairwise tree over adjacent PEs; the exact stage order is the crossbar
+ *                   generator's, so the emulation is held to the tolerance, not to the bit)
+ *   AccumBuffer     (:483-485)      BUFF_C[row16] += val in stream order, one buffer per PE, dumped per row tile
+ *   Compute_C       (:535)          y = beta * c_in + alpha * acc
+ * `stream` is num_ch * words_per_ch words, channel-major.  Local row of a private word of PE p: row15 * num_pes + p;
+ * of a shared pair: row15(odd) * num_pes + rowfield(even) (prepareTile :560-563,612); global = tile index * tile size.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int valid, shared, row, col;
+  float val;
+} peg_item_t;
+
+static inline uint64_t peg_word(const uint64_t* stream, int64_t words_per_ch, int pes_per_ch, int pe, int64_t slot) {
+  return stream[(int64_t)(pe / pes_per_ch) * words_per_ch + slot * pes_per_ch + pe % pes_per_ch];
+}
+
+/* Decodes slot `slot` of PE pair g into items[0..1]; returns the pair's tileEnd flag. */
+static int peg_decode_pair(const uint64_t* stream, int64_t words_per_ch, int pes_per_ch, int num_pes, int g,
+                           int64_t slot, int row_base, int col_base, peg_item_t* items) {
+  int log2pes = 0;
+  while ((1 << log2pes) < num_pes) ++log2pes;
+  const uint64_t w0 = peg_word(stream, words_per_ch, pes_per_ch, 2 * g, slot);
+  const uint64_t w1 = peg_word(stream, words_per_ch, pes_per_ch, 2 * g + 1, slot);
+  const int shared = (int)((w0 >> 46) & 1), tile_end = (int)((w0 >> 47) & 1);
+  const uint64_t w[2] = {w0, w1};
+  const int rf0 = (int)((w0 >> 48) & 0xFFFF), rf1 = (int)((w1 >> 48) & 0xFFFF);
+  for (int p = 0; p < 2; ++p) {
+    const uint32_t bits = (uint32_t)(w[p] & 0xFFFFFFFFu);
+    const int rf = (int)((w[p] >> 48) & 0xFFFF);
+    peg_item_t* it = &items[p];
+    memcpy(&it->val, &bits, 4);
+    it->col = col_base + (int)((w[p] >> 32) & 0x3FFF);
+    it->shared = shared;
+    if (shared) {
+      it->valid = (rf1 >> 15) & 1;
+      it->row = row_base + (rf1 & 0x7FFF) * num_pes + (rf0 & ((1 << log2pes) - 1));
+    } else {
+      it->valid = (rf >> 15) & 1;
+      it->row = row_base + (rf & 0x7FFF) * num_pes + (2 * g + p);
+    }
+  }
+  return tile_end;
+}
+
+/* Every real (non-dummy) word as (global row, global col, value, shared flag), in slot-major / PE-minor order.
+ * Returns the count (arrays may be NULL to count only), -2 if the PE pairs disagree on a tile boundary. */
+int64_t oracle_peg_decode(const uint64_t* stream, int num_ch, int pes_per_ch, int64_t words_per_ch, int tile_rows,
+                          int tile_cols, int col_tiles, int32_t* row, int32_t* col, float* val, uint8_t* shared) {
+  const int num_pes = num_ch * pes_per_ch;
+  const int64_t slots = words_per_ch / pes_per_ch;
+  int64_t n = 0;
+  int tile = 0;
+  for (int64_t s = 0; s < slots; ++s) {
+    int ends = 0;
+    for (int g = 0; g < num_pes / 2; ++g) {
+      peg_item_t it[2];
+      ends += peg_decode_pair(stream, words_per_ch, pes_per_ch, num_pes, g, s, (tile / col_tiles) * tile_rows,
+                              (tile % col_tiles) * tile_cols, it);
+      for (int p = 0; p < 2; ++p) {
+        if (!it[p].valid) continue;
+        if (row) { row[n] = it[p].row; col[n] = it[p].col; val[n] = it[p].val; shared[n] = (uint8_t)it[p].shared; }
+        ++n;
+      }
+    }
+    if (ends != 0 && ends != num_pes / 2) return -2;
+    if (ends) ++tile;
+  }
+  return n;
+}
+
+/* y = beta * c_in + alpha * (A x) computed the way the accelerator walks the stream (fp32, -ffp-contract=off).
+ * Returns the number of tiles seen, or -2 / -3 on a malformed stream (tile flags disagree / row out of range). */
+int oracle_peg_spmv(const uint64_t* stream, int num_ch, int pes_per_ch, int64_t words_per_ch, int tile_rows,
+                    int tile_cols, int col_tiles, int rows, int cols, const float* x, const float* c_in, float alpha,
+                    float beta, float* y) {
+  const int num_pes = num_ch * pes_per_ch;
+  const int64_t slots = words_per_ch / pes_per_ch;
+  float* acc = (float*)calloc((size_t)(rows > 0 ? rows : 1), sizeof(float));
+  float* part = (float*)malloc(sizeof(float) * (size_t)num_pes);
+  int* prow = (int*)malloc(sizeof(int) * (size_t)num_pes);
+  int tile = 0, status = 0;
+  for (int64_t s = 0; s < slots && status == 0; ++s) {
+    int ends = 0;
+    for (int pe = 0; pe < num_pes; ++pe) prow[pe] = -1;
+    for (int g = 0; g < num_pes / 2; ++g) {
+      peg_item_t it[2];
+      ends += peg_decode_pair(stream, words_per_ch, pes_per_ch, num_pes, g, s, (tile / col_tiles) * tile_rows,
+                              (tile % col_tiles) * tile_cols, it);
+      for (int p = 0; p < 2; ++p) {
+        if (!it[p].valid) continue;
+        if (it[p].row < 0 || it[p].row >= rows || it[p].col < 0 || it[p].col >= cols) {
+          if (it[p].val == 0.0f) continue; /* zero fill of a shared row's last stripe / padded rows */
+          status = -3;
+          break;
+        }
+        const float prod = it[p].val * x[it[p].col];                     /* ComputeAB */
+        if (it[p].shared) {
+          part[2 * g + p] = prod;                                        /* goes through the ADD tree below */
+          prow[2 * g + p] = it[p].row;
+        } else {
+          acc[it[p].row] = prod + acc[it[p].row];                        /* AccumBuffer: val + BUFF_C[row] */
+        }
+      }
+    }
+    for (int stride = 1; stride < num_pes; stride *= 2)                  /* ADD stages: adjacent partners */
+      for (int a = 0; a + stride < num_pes; a += 2 * stride)
+        if (prow[a] >= 0 && prow[a + stride] == prow[a]) {
+          part[a] = part[a] + part[a + stride];
+          prow[a + stride] = -1;
+        }
+    for (int pe = 0; pe < num_pes; ++pe)
+      if (prow[pe] >= 0) acc[prow[pe]] = part[pe] + acc[prow[pe]];
+    if (ends != 0 && ends != num_pes / 2) status = -2;
+    if (ends) ++tile;
+  }
+  if (status == 0)
+    for (int i = 0; i < rows; ++i) y[i] = (beta * c_in[i]) + (alpha * acc[i]);   /* Compute_C :535 */
+  free(acc);
+  free(part);
+  free(prow);
+  return status ? status : tile;
+}

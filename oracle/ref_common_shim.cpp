@@ -5,6 +5,7 @@
 //   HiSpmvHandle::tileAndPad(COO)           common/src/spmv-helper.cpp:139-227   (private)
 //   HiSpmvHandle::prepareSparseMtxForFPGA   common/src/spmv-helper.cpp:648-715   (shared-row list)
 //   HiSpmvHandle::loadMtx                   common/src/spmv-helper.cpp:34-136    (private)
+//   HiSpmvHandle::getPreparedMtx            the packed 64-bit PEG streams (computeTileSize / prepareTile :429-638)
 // The private members are reached by re-declaring access for this translation unit only; the reference
 // sources themselves are compiled untouched.
 #include <cstdint>
@@ -132,5 +133,35 @@ void ref_common_load_mtx_fetch(int* r, int* c, float* v) {
   std::memcpy(c, g_coo.cols.data(), sizeof(int) * g_coo.cols.size());
   std::memcpy(v, g_coo.values.data(), sizeof(float) * g_coo.values.size());
   g_coo = COOMatrix_t();
+}
+
+// The packed PEG streams of a COO matrix for one hardware configuration (prepareSparseMtxForFPGA -> prepareTile).
+// meta = {num_pes, pes_per_ch, tile_rows, tile_cols, row_tiles, col_tiles, words_per_channel, shared rows};
+// returns the number of channels.  ref_common_pack_fetch copies channel-major words and the shared-row ids.
+static std::vector<uint64_t> g_stream;
+static std::vector<int> g_shared;
+int ref_common_pack(int num_ch_a, int urams, int fp_acc_latency, int pre_acc, int rows, int cols, int64_t nnz,
+                    const int* r, const int* c, const float* v, int64_t* meta) {
+  Quiet q;
+  HiSpmvHandle* h = make_handle(num_ch_a, 1, 1, urams, fp_acc_latency, 1, pre_acc, 1);
+  std::vector<int> rv(r, r + nnz), cv(c, c + nnz);
+  std::vector<float> vv(v, v + nnz);
+  h->prepareSparseMtxForFPGA(rows, cols, rv, cv, vv);
+  const auto& prep = h->prep_mtx;
+  const int64_t words = prep.empty() ? 0 : (int64_t)prep[0].size();
+  g_stream.resize((size_t)(words * (int64_t)prep.size()));
+  for (size_t ch = 0; ch < prep.size(); ++ch) std::memcpy(g_stream.data() + ch * words, prep[ch].data(), sizeof(uint64_t) * words);
+  g_shared.assign(h->shared_row_indices.begin(), h->shared_row_indices.end());
+  meta[0] = h->num_pes; meta[1] = h->pes_per_ch; meta[2] = h->tile_rows; meta[3] = h->tile_cols;
+  meta[4] = h->row_tiles; meta[5] = h->col_tiles; meta[6] = words; meta[7] = (int64_t)g_shared.size();
+  const int n_ch = (int)prep.size();
+  delete h;
+  return n_ch;
+}
+void ref_common_pack_fetch(uint64_t* stream, int* shared_rows) {
+  std::memcpy(stream, g_stream.data(), sizeof(uint64_t) * g_stream.size());
+  if (shared_rows && !g_shared.empty()) std::memcpy(shared_rows, g_shared.data(), sizeof(int) * g_shared.size());
+  g_stream = std::vector<uint64_t>();
+  g_shared = std::vector<int>();
 }
 }

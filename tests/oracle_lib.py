@@ -80,6 +80,11 @@ def oracle() -> C.CDLL:
     lib.oracle_synth_csr.restype = i64
     lib.oracle_load_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), vp, vp, vp]
     lib.oracle_load_mtx.restype = i64
+    _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+    lib.oracle_peg_decode.argtypes = [_u64p, i, i, i64, i, i, i, vp, vp, vp, vp]
+    lib.oracle_peg_decode.restype = i64
+    lib.oracle_peg_spmv.argtypes = [_u64p, i, i, i64, i, i, i, i, i, _f32p, _f32p, f, f, _f32p]
+    lib.oracle_peg_spmv.restype = i
     _cache["oracle"] = lib
     return lib
 
@@ -135,6 +140,9 @@ def ref_common() -> C.CDLL:
     lib.ref_common_shared_rows.restype = i
     lib.ref_common_load_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64)]
     lib.ref_common_load_mtx_fetch.argtypes = [_i32p, _i32p, _f32p]
+    lib.ref_common_pack.argtypes = [i, i, i, i, i, i, i64, _i32p, _i32p, _f32p, _i64p]
+    lib.ref_common_pack.restype = i
+    lib.ref_common_pack_fetch.argtypes = [np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_void_p]
     return lib
 
 
@@ -277,6 +285,47 @@ def synth_csr(kind, seed, cols, params, row_begin, row_end):
     v = np.zeros(max(nnz, 1), np.float32)
     oracle().oracle_synth_csr(kind, seed, cols, p, row_begin, row_end, rp.ctypes.data, ci.ctypes.data, v.ctypes.data)
     return rp, ci[:nnz], v[:nnz]
+
+
+PEG_META = ("num_pes", "pes_per_ch", "tile_rows", "tile_cols", "row_tiles", "col_tiles", "words_per_ch", "n_shared")
+
+
+def ref_pack(num_ch_a, urams, fp_acc_latency, pre_acc, rows, cols, r, c, v):
+    """The reference's packed PEG streams (channel-major uint64), its layout numbers and its shared-row ids."""
+    r, c, v = (np.ascontiguousarray(r, np.int32), np.ascontiguousarray(c, np.int32), np.ascontiguousarray(v, np.float32))
+    meta = np.zeros(8, np.int64)
+    n_ch = ref_common().ref_common_pack(num_ch_a, urams, fp_acc_latency, int(pre_acc), rows, cols, r.size, r, c, v, meta)
+    m = dict(zip(PEG_META, (int(t) for t in meta)))
+    m["num_ch"] = n_ch
+    stream = np.zeros(max(1, n_ch * m["words_per_ch"]), np.uint64)
+    shared = np.zeros(max(1, m["n_shared"]), np.int32)
+    ref_common().ref_common_pack_fetch(stream, shared.ctypes.data)
+    return stream[:n_ch * m["words_per_ch"]], m, shared[:m["n_shared"]]
+
+
+def peg_decode(stream, m):
+    """(row, col, val, shared) of every real word of a packed PEG stream (oracle_peg_decode)."""
+    stream = np.ascontiguousarray(stream, np.uint64)
+    args = (stream, m["num_ch"], m["pes_per_ch"], m["words_per_ch"], m["tile_rows"], m["tile_cols"], m["col_tiles"])
+    n = oracle().oracle_peg_decode(*args, None, None, None, None)
+    if n < 0:
+        raise ValueError(f"oracle_peg_decode: malformed stream ({n})")
+    row, col = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32)
+    val, sh = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.uint8)
+    oracle().oracle_peg_decode(*args, row.ctypes.data, col.ctypes.data, val.ctypes.data, sh.ctypes.data)
+    return row[:n], col[:n], val[:n], sh[:n]
+
+
+def peg_spmv(stream, m, rows, cols, x, c_in, alpha, beta):
+    """y = beta*c_in + alpha*A x walked the way the accelerator consumes the stream (oracle_peg_spmv)."""
+    y = np.zeros(rows, np.float32)
+    st = oracle().oracle_peg_spmv(np.ascontiguousarray(stream, np.uint64), m["num_ch"], m["pes_per_ch"],
+                                  m["words_per_ch"], m["tile_rows"], m["tile_cols"], m["col_tiles"], rows, cols,
+                                  np.ascontiguousarray(x, np.float32), np.ascontiguousarray(c_in, np.float32),
+                                  alpha, beta, y)
+    if st < 0:
+        raise ValueError(f"oracle_peg_spmv: malformed stream ({st})")
+    return y, st
 
 
 def load_mtx(path):

@@ -2,13 +2,16 @@
 """spmv-host for the GPU engine: the reference's stand-alone self-checking host program (common/src/spmv-host.cpp:41-191)
 with the same protocol and the same log lines, so that builds/collect_data.py:8-23 scrapes its output unchanged.
 
-    python tools/spmv_host.py <matrix.mtx>            [--exec_ms 1000] [--device 0]
+    python tools/spmv_host.py <matrix.mtx>            [--exec_ms 1000] [--power_s 0] [--device 0]
     python tools/spmv_host.py <dense rows> <dense cols> [--exec_ms 1000]
 
 Protocol (spmv-host.cpp:17-23,43-44,92-100,181-189): x = c_in = (i+2)/(i+1), alpha = 0.55, beta = -2.05; a CPU result
 (scipy CSR product in fp32 here; the reference uses its own cpuSequential) is compared with the accelerator's through
 the relative-error histogram of printErrorStats (common/src/spmv-helper.cpp:835-895); GFLOPS = 2 (nnz + rows) / time.
 The accelerator time is the mean of as many back-to-back device-resident runs as fit in --exec_ms ("rp_time").
+--power_s S keeps the kernel running for S seconds while the board power is sampled (spmv-host.cpp:138-147,
+common/src/spmv-helper.cpp:1027-1049) and prints the reference's Average Power / Max Power / Number of Samples lines,
+plus one watt value per line in ./power_logs/<matrix>.log as the V100 benchmark does (gpu/src/nvmlPower.cpp:51-91).
 """
 from __future__ import annotations
 
@@ -52,6 +55,7 @@ def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("args", nargs="+", help="<matrix.mtx>  |  <dense rows> <dense cols>")
     ap.add_argument("--exec_ms", type=float, default=1000.0, help="time budget for the repeated runs (reference: --exec_ms)")
+    ap.add_argument("--power_s", type=float, default=0.0, help="seconds of sampled execution (reference: --power_s)")
     ap.add_argument("--device", type=int, default=0)
     a = ap.parse_args()
     import scipy.sparse as sp
@@ -104,18 +108,37 @@ def main() -> int:
     eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
     e1.record()
     e1.synchronize()
-    rp_time = max(1, min(100000, int(a.exec_ms / max(e0.elapsed_time(e1), 1e-3))))
+    one_ms = max(e0.elapsed_time(e1), 1e-3)
+    rp_time = max(1, min(100000, int(a.exec_ms / one_ms)))
+    if a.power_s > 0:                                              # spmv-host.cpp:146-147: run for power_s seconds
+        rp_time = max(rp_time, int(a.power_s * 1000.0 / one_ms))
     print(f"Using Repeat Time: {rp_time}")
+    monitor = None
+    if a.power_s > 0:
+        from hispmv_b200.power import GpuPowerMonitor, report
+        name = os.path.splitext(os.path.basename(a.args[0]))[0] if len(a.args) == 1 else f"dense_{a.args[0]}x{a.args[1]}"
+        monitor = GpuPowerMonitor(period_s=min(1.0, max(0.05, a.power_s / 10)))
+        monitor.start_monitoring(a.device, log_path=os.path.join("power_logs", name + ".log"))
+    print("Kernel Launched")
     e0.record()
-    for _ in range(rp_time):
+    for k in range(rp_time):
         eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
+        if monitor is not None and (k & 1023) == 1023:
+            torch.cuda.current_stream().synchronize()            # keep the launch queue bounded on long power runs
     e1.record()
     e1.synchronize()
+    print("Kernel Finished")
+    if monitor is not None:
+        monitor.stop_monitoring()
+        print(report(monitor))
     total_ms = e0.elapsed_time(e1)
     t_us = total_ms * 1e3 / rp_time
     print(f"Total Kernel Runtime: {total_ms:.6f}ms")
     print(f"FPGA TIME: {t_us:.6f}us")                              # key names kept for builds/collect_data.py
     print(f"FPGA GFLOPS: {2.0 * (nnz + rows) / (t_us * 1e3):.6f}")
+    if monitor is not None and monitor.get_average_power()[1]:
+        avg_w = monitor.get_average_power()[0]
+        print(f"GFLOPS per Watt: {2.0 * (nnz + rows) / (t_us * 1e3) / avg_w:.6f}")
     # the host-buffer call the plugin makes (copies inside)
     y = np.zeros(rows, np.float32)
     eng.select_matrix(idx)

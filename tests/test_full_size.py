@@ -22,7 +22,7 @@ import oracle_lib as ol
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-ALPHA, BETA = 0.85, -2.06
+ALPHA, BETA = float(np.float32(0.85)), float(np.float32(-2.06))   # what the C-ABI's float arguments hold
 CHUNK = 1 << 27          # nonzeros per torch reference chunk (keeps the float64 temporaries near 4 GB)
 SAMPLE_ROWS = 100_000    # rows the C oracle re-generates and re-computes on the CPU
 

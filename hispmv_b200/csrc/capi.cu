@@ -765,13 +765,18 @@ int hispmv_launches_per_run(hispmv_ctx* c, int idx) {
   return 1;
 }
 
-int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float alpha, float beta) {
+}  // extern "C"
+
+// The host-buffer step behind hispmv_run / hispmv_run_xdev.  x comes either from host memory (x_host) or is already
+// in HBM (d_x_ext, complete once the work queued on x_stream so far has run); bias and y are host buffers.
+static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ext, cudaStream_t x_stream,
+                         const float* bias, float* y, float alpha, float beta) {
   if (!c) return HISPMV_ERR_ARG;
   if (c->selected < 0) {
     set_error("Run Kernel called before selecting a matrix");  // reference: assert, fpga_handle.cpp:292
     return HISPMV_ERR_STATE;
   }
-  if (!x || !y || (beta != 0.0f && !bias)) {
+  if ((!x_host && !d_x_ext) || !y || (beta != 0.0f && !bias)) {
     set_error("run: null vector");
     return HISPMV_ERR_ARG;
   }
@@ -781,6 +786,11 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
   int st = ensure_staging(c, m->cols, n_y);
   if (st != HISPMV_OK) return st;
   cudaStream_t s = c->stream;
+  const float* d_x = d_x_ext ? d_x_ext : c->d_x[0];
+  if (d_x_ext) {  // order the compute stream after whatever produces x
+    HISPMV_CUDA(cudaEventRecord(c->ev_pipe[0], x_stream));
+    HISPMV_CUDA(cudaStreamWaitEvent(s, c->ev_pipe[0], 0));
+  }
   // Large tiled matrices: the rows are cut into up to 8 ranges at tile boundaries and the ranges are pipelined over
   // three streams -- bias range i+1 goes up and y range i-1 comes down (PCIe is full duplex) while range i computes.
   // The reference overlaps its host-side fill with the running kernel the same way (fpga_handle.cpp:366-379).
@@ -789,9 +799,10 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
   int chunks = 1;
   if (tiled && n_y >= (1 << 20) && m->num_tiles >= 64) chunks = n_y >= (1 << 22) ? 8 : 4;
   if (chunks == 1) {
-    if (m->cols > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s));
+    if (x_host && m->cols > 0)
+      HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s));
     if (bias && n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, s));
-    st = run_matrix(c, m, c->d_x[0], bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s);
+    st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s);
     if (st != HISPMV_OK) return st;
     if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(y, c->d_y[0], (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
     HISPMV_CUDA(cudaStreamSynchronize(s));
@@ -808,10 +819,12 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
     tb[i] = t;
   }
   cudaStream_t s_up = c->stream2, s_down = c->stream3;
-  cudaEvent_t ev_x = c->ev_pipe[0];
-  HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s_up));
-  HISPMV_CUDA(cudaEventRecord(ev_x, s_up));
-  HISPMV_CUDA(cudaStreamWaitEvent(s, ev_x, 0));
+  if (x_host) {
+    cudaEvent_t ev_x = c->ev_pipe[0];
+    HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s_up));
+    HISPMV_CUDA(cudaEventRecord(ev_x, s_up));
+    HISPMV_CUDA(cudaStreamWaitEvent(s, ev_x, 0));
+  }
   for (int i = 0; i < chunks; ++i) {
     const int64_t r0 = m->h_tile_row[(size_t)tb[i]], r1 = m->h_tile_row[(size_t)tb[i + 1]];
     cudaEvent_t ev_b = c->ev_pipe[1 + i], ev_k = c->ev_pipe[9 + i];
@@ -820,7 +833,7 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
       HISPMV_CUDA(cudaEventRecord(ev_b, s_up));
       HISPMV_CUDA(cudaStreamWaitEvent(s, ev_b, 0));
     }
-    st = run_matrix(c, m, c->d_x[0], bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, tb[i],
+    st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, tb[i],
                     tb[i + 1] - tb[i]);
     if (st != HISPMV_OK) return st;
     HISPMV_CUDA(cudaEventRecord(ev_k, s));
@@ -832,6 +845,21 @@ int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float
   HISPMV_CUDA(cudaStreamSynchronize(s));
   HISPMV_CUDA(cudaStreamSynchronize(s_up));
   return HISPMV_OK;
+}
+
+extern "C" {
+
+int hispmv_run(hispmv_ctx* c, const float* x, const float* bias, float* y, float alpha, float beta) {
+  return run_host_step(c, x, nullptr, nullptr, bias, y, alpha, beta);
+}
+
+int hispmv_run_xdev(hispmv_ctx* c, const float* d_x, void* x_stream, const float* bias, float* y, float alpha,
+                    float beta) {
+  if (!d_x) {
+    set_error("run_xdev: null x");
+    return HISPMV_ERR_ARG;
+  }
+  return run_host_step(c, nullptr, d_x, (cudaStream_t)x_stream, bias, y, alpha, beta);
 }
 
 int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const float* bias, float* y_out) {

@@ -106,9 +106,15 @@ class XReplicator:
         o = (k & 1) * self.npad
         return self._buf[o:o + self.n]
 
-    def replicate(self, k: int, src_on_root: Optional[torch.Tensor], stream: torch.cuda.Stream) -> None:
-        """Enqueue on `stream` the exchange that fills replica k on every rank from `src_on_root` (root only)."""
-        with torch.cuda.stream(stream):
+    @staticmethod
+    def _on(stream):
+        import contextlib
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def replicate(self, k: int, src_on_root: Optional[torch.Tensor], stream: Optional[torch.cuda.Stream]) -> None:
+        """Enqueue on `stream` the exchange that fills replica k on every rank from `src_on_root` (root only).
+        stream=None: current stream / CPU tensors over gloo (tests)."""
+        with self._on(stream):
             if self.mode == "nccl":
                 b = self.buffer(k)
                 if self.rank == self.root and src_on_root is not None and src_on_root.data_ptr() != b.data_ptr():
@@ -124,6 +130,44 @@ class XReplicator:
                 check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(src_on_root.data_ptr()), self.n, 16,
                                                 C.c_void_p(stream.cuda_stream)), "multicast_copy")
             self._hdl.barrier(channel=2 + cur)      # the stores have landed everywhere
+
+    # ---- host-resident x: every rank holds the same x in (pinned) host memory --------------------------------
+    def slice_bounds(self, rank: Optional[int] = None):
+        """[lo, hi) of x that `rank` carries across PCIe: equal 16-byte-aligned slices."""
+        world = dist.get_world_size(self.group)
+        per = (((self.n + world - 1) // world) + 3) & ~3
+        r = self.rank if rank is None else rank
+        return min(self.n, r * per), min(self.n, (r + 1) * per)
+
+    def gather_from_host(self, k: int, x_host: torch.Tensor, stream: Optional[torch.cuda.Stream]) -> int:
+        """Enqueue on `stream`: this rank copies ONLY its slice of the (pinned) host x to the GPU and the slices meet
+        in replica k of every rank over NVLink -- one multimem.st store per rank to the multicast address (mode
+        "multicast") or an NCCL all-gather.  x crosses PCIe once per node instead of once per GPU.  Returns the bytes
+        this rank sent host -> device."""
+        lo, hi = self.slice_bounds()
+        cur = k & 1
+        world = dist.get_world_size(self.group)
+        if not hasattr(self, "_stage"):
+            per = self.slice_bounds(0)[1]
+            self._stage = torch.empty(max(per, 4), dtype=torch.float32, device=self.device)
+            if self.mode == "nccl":
+                self._gath = torch.empty(world * max(per, 4), dtype=torch.float32, device=self.device)
+        with self._on(stream):
+            if hi > lo:
+                self._stage[:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+            if self.mode == "nccl":
+                dist.all_gather_into_tensor(self._gath, self._stage, group=self.group)
+                self.buffer(k).copy_(self._gath[:self.n])
+                return (hi - lo) * 4
+            import ctypes as C
+            from .capi import lib, check
+            self._hdl.barrier(channel=cur)          # every rank is done reading replica `cur`
+            if hi > lo:
+                mc = self._hdl.multicast_ptr + (cur * self.npad + lo) * 4
+                check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(self._stage.data_ptr()), hi - lo, 16,
+                                                C.c_void_p(stream.cuda_stream)), "multicast_copy")
+            self._hdl.barrier(channel=2 + cur)      # every slice has landed everywhere
+        return (hi - lo) * 4
 
 
 class ShardedEngine:

@@ -145,6 +145,11 @@ int hispmv_force_kernel(hispmv_ctx* ctx, int idx, int kernel, int lanes);
 /* ---- host-buffer calls (synchronous; copies inside, like the reference's BO syncs) ---- */
 int hispmv_run(hispmv_ctx* ctx, const float* x, const float* bias, float* y, float alpha, float beta);
 int hispmv_linear(hispmv_ctx* ctx, int idx, const float* x, int64_t x_len, const float* bias, float* y_out);
+/* hispmv_run with x already in HBM (d_x is complete once the work queued on x_stream -- a cudaStream_t -- so far has
+ * run); bias and y are host buffers, copied and pipelined as in hispmv_run.  The multi-GPU host path uses it: each
+ * rank sends only its slice of x across PCIe and the slices meet over NVLink (hispmv_multicast_copy). */
+int hispmv_run_xdev(hispmv_ctx* ctx, const float* d_x, void* x_stream, const float* bias, float* y, float alpha,
+                    float beta);
 
 /* ---- device-buffer calls: asynchronous on `stream`, a cudaStream_t.  As everywhere in CUDA, NULL is the
  *      default stream; hispmv_stream() returns the context's own non-blocking stream. ---- */

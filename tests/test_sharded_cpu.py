@@ -58,6 +58,23 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
             comm.set_blocks("z", b2[rank], b2[rank + 1], torch.device("cpu"))
             z = comm.allgather_rows("z", torch.arange(b2[rank], b2[rank + 1], dtype=torch.float32), torch.empty(11))
             assert torch.equal(z, torch.arange(11, dtype=torch.float32))
+        # x exchange: replication from the root, and the sliced host upload (every rank carries 1/world of x)
+        from hispmv_b200.sharded import XReplicator
+        n = 1003                                            # not a multiple of 4 * world: ragged last slice
+        rep = XReplicator(n, torch.device("cpu"), mode="nccl")
+        assert rep.mode == "nccl" and rep.buffer(0).numel() == n and rep.buffer(1).data_ptr() != rep.buffer(0).data_ptr()
+        cuts = [rep.slice_bounds(q) for q in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        assert all(lo % 4 == 0 for lo, _ in cuts)
+        xs = torch.arange(n, dtype=torch.float32) * 0.5 - 7
+        rep.replicate(0, xs if rank == 0 else None, None)
+        assert torch.equal(rep.buffer(0), xs)
+        poisoned = xs.clone()
+        lo, hi = rep.slice_bounds()
+        poisoned[:lo] = float("nan")                        # a rank may only read its own slice of the host vector
+        poisoned[hi:] = float("nan")
+        sent = rep.gather_from_host(1, poisoned, None)
+        assert sent == 4 * (hi - lo) and torch.equal(rep.buffer(1), xs)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

@@ -229,6 +229,17 @@ __device__ __forceinline__ TileDesc load_desc(const TileDesc* p) {
   return d;
 }
 
+// L2 prefetch of the col/val range of tile `ta` (two bulk-prefetch instructions from one thread).  A matrix of a few
+// waves of tiles is otherwise latency-bound: every wave pays descriptor + stream round trips to DRAM back to back
+// while HBM idles (C3b: 33 % DRAM utilisation, long_scoreboard the top stall).
+__device__ __forceinline__ void prefetch_tile_l2(const CsrDev& A, const TileDesc& da) {
+  const int a = da.n0 & ~3;
+  const uint32_t bytes = (uint32_t)((((da.n1 + 3) & ~3) - a) * 4);
+  if (bytes == 0) return;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.col + a), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(A.val + a), "r"(bytes) : "memory");
+}
+
 // ================================================================================================================
 // one CTA per tile
 // ================================================================================================================
@@ -240,7 +251,12 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
   __shared__ float s_red[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t = P.tile_begin + blockIdx.x;
+  const bool look_ahead = P.ahead > 0 && tid == THREADS - 1 && blockIdx.x + (int64_t)P.ahead < (int64_t)gridDim.x;
+  TileDesc da;
+  if (look_ahead) da = load_desc(P.desc + t + P.ahead);  // in flight together with this tile's own descriptor
   const TileDesc d = load_desc(P.desc + t);
+  if (look_ahead && (da.chunk >= 0 || P.ahead_all)) prefetch_tile_l2(A, da);
+  if (P.ahead < 0 && tid == THREADS - 1) prefetch_tile_l2(A, d);  // own tile: later loop iterations hit L2
   const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
   const GatherL1<SPLIT> gx{x, P.hot_cols, pk};
   if (d.chunk >= 0) {

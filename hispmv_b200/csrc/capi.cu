@@ -56,6 +56,8 @@ struct Matrix {
   bool is_slab = false;
   int32_t long_threshold = 0, chunk_nnz = 0;
   int32_t hot_cols = 0x7fffffff;        // ADAPTIVE / ROWSTAGE: split L1 policy threshold for x gathers
+  int32_t ahead = 0;                    // ADAPTIVE: L2 prefetch distance in tiles (0 = off), see AdaptivePlan::ahead
+  int32_t ahead_all = 0;                // look ahead for STREAM tiles too (development sweeps)
   bool persistent = false;              // ADAPTIVE: one resident CTA per SM with x[0, hot_cols) in shared memory
   bool pipeline = false;                // ADAPTIVE: warp-specialised persistent pipeline (TMA ring)
   bool warptile = false;                // ADAPTIVE: one warp per (small) tile, no CTA barrier
@@ -298,6 +300,27 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
                                &m->num_tiles, &m->d_tile_row, &m->d_tile_chunk, &m->d_split_rows, &m->num_split,
                                c->stream);
     if (st != HISPMV_OK) return st;
+    // L2 look-ahead (AdaptivePlan::ahead): thread THREADS-1 of every CTA asks L2 for the col/val range of the LONG
+    // tile one CTA-per-SM ahead.  A LONG tile is four dependent load -> gather rounds per thread; with its stream
+    // already in L2 each round is ~500 cycles shorter (C2: 0.384 -> 0.374 ms).  STREAM tiles are gather-bound and
+    // lose 2 % when prefetched (C5/10: 0.432 -> 0.442 ms), so they are left alone, and matrices without long rows
+    // never look ahead.
+    m->ahead = 0;
+    m->ahead_all = 0;
+    if (m->kernel == HISPMV_KERNEL_ADAPTIVE && !m->warptile && !m->pipeline && !m->persistent) {
+      if (m->stats.max_row_nnz >= m->long_threshold) m->ahead = c->sm_count;
+      if (const char* e = getenv("HISPMV_AHEAD")) {  // development sweeps: "-1" off, "-2" own tile, "N[,all]"
+        int a = 0;
+        char all[8] = {0};
+        const int got = sscanf(e, "%d,%7s", &a, all);
+        if (got >= 1) {
+          if (a == -1) m->ahead = 0;
+          else if (a == -2) m->ahead = -1;
+          else if (a > 0) m->ahead = a;
+          m->ahead_all = got == 2 && all[0] == 'a';
+        }
+      }
+    }
     st = tile_desc_device(m->d_row_ptr, m->d_tile_row, m->d_tile_chunk, m->num_tiles, m->chunk_nnz, &m->d_desc,
                           c->stream);
     if (st != HISPMV_OK) return st;
@@ -548,6 +571,8 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.hot_cols = m->hot_cols;
       P.tile_begin = tile_begin;
       P.tile_count = tile_count;
+      P.ahead = m->ahead;
+      P.ahead_all = m->ahead_all;
       P.sched = m->d_counter + (size_t)std::max<int64_t>(m->num_tiles, 1) * 2 + 4 * (size_t)lane;
       if (m->kernel == HISPMV_KERNEL_ROWSTAGE)
         return launch_rowstage(A, P, m->lanes, m->rowstage_threads, d_x, d_y, ep, s);

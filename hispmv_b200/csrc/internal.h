@@ -67,6 +67,11 @@ struct AdaptivePlan {
   unsigned int* sched = nullptr;        // persistent kernel: [0] next tile, [1] groups that ran dry
   int64_t tile_begin = 0;               // one-CTA-per-tile kernels: launch only tiles [tile_begin, tile_begin + tile_count)
   int64_t tile_count = -1;              // (-1: all) -- the host-buffer call pipelines row ranges against PCIe copies
+  int32_t ahead = 0;                    // > 0: every CTA asks L2 to fetch the col/val range of tile t + ahead (the tile
+                                        // the next wave runs in its place), so DRAM keeps streaming while this wave
+                                        // gathers and reduces; 0 = off; < 0: every CTA prefetches its own tile
+  int32_t ahead_all = 0;                // 0: look ahead only for LONG tiles (chunks of long rows: four dependent
+                                        // load -> gather rounds per thread, the part that is DRAM-latency-bound)
 };
 
 struct RowStats {

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--runs", type=int, default=3)
     ap.add_argument("--rows", type=int, default=8192)
     ap.add_argument("--cols", type=int, default=8192)
+    ap.add_argument("--flush", action="store_true", help="write a 256 MB buffer between runs (cold L2)")
     args = ap.parse_args()
     if args.tile:
         os.environ["HISPMV_MERGE_TILE"] = args.tile
@@ -34,6 +35,20 @@ def main():
         a = torch.rand(args.rows, args.cols, device="cuda")
         idx = eng.create_dense_handle_dev(a, args.rows, args.cols)
         rows, cols = args.rows, args.cols
+    elif args.config in ("c1", "c3b", "c3c"):   # the small host-built configs (as tools/sweep.py builds them)
+        import numpy as np
+        if args.config == "c1":
+            r, c, v, rows, cols = synth.c1_imbalanced_coo()
+        else:
+            rows, cols, dens = {"c3b": (8192, 8192, 0.1), "c3c": (1024, 8192, 0.25)}[args.config]
+            g0 = torch.Generator().manual_seed(0)
+            w = torch.randn(rows, cols, generator=g0) * (torch.rand(rows, cols, generator=g0) < dens)
+            nzr, nzc = torch.nonzero(w, as_tuple=True)
+            r, c, v = nzr.numpy().astype(np.int32), nzc.numpy().astype(np.int32), w[nzr, nzc].numpy()
+        idx = eng.create_sparse_handle(r, c, v, rows, cols)
+        k = {"auto": capi.KERNEL_AUTO, "adaptive": capi.KERNEL_ADAPTIVE, "rowstage": capi.KERNEL_ROWSTAGE, "merge": capi.KERNEL_MERGE,
+             "vector": capi.KERNEL_CSR_VECTOR, "scalar": capi.KERNEL_CSR_SCALAR}[args.kernel]
+        eng.force_kernel(idx, k, args.lanes)
     else:
         spec = {"c2": synth.c2_powerlaw, "c4": synth.c4_stencil, "c5": synth.c5_uniform}[args.config](args.scale)
         d = synth.DeviceCSR(spec)
@@ -47,7 +62,10 @@ def main():
     b = torch.rand(rows, device="cuda")
     y = torch.empty(rows, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda") if args.flush else None
     for _ in range(args.runs):
+        if flush is not None:
+            flush.add_(1.0)          # cold L2 for the next run
         eng.run_dev(idx, x, b, y, 0.85, -2.06, st)
     torch.cuda.synchronize()
     print(eng.matrix_info(idx)["kernel_name"], float(y.sum()))

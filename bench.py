@@ -33,6 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 ALPHA, BETA = 0.85, -2.06  # cpu/src/main.cpp:147-148
 METRIC, UNIT = "spmv_gflops", "GFLOP/s"
+L2_SECTOR_RATE = 276.9e9  # measured: 32-byte sector requests per second the L2 serves, chip-wide
 
 
 def measured_peak():
@@ -332,13 +333,15 @@ def run_ours(args):
                 sectors = tj.get(args.workload + "_" + info["kernel_name"] + "_l1_miss_sectors_per_launch")
         except Exception:
             pass
-        # second roofline: an SM takes in ~0.95 L1-miss sectors per clock (tools/gather_bench.cu); a
-        # scattered x gather costs a whole 32-byte sector.  sectors = ncu count for this kernel on this matrix.
+        # second roofline: the L2 slices answer ~277 G sector requests per second chip-wide, however many
+        # SMs ask (tools/gather_bench.cu: 276-277 G/s with 37, 74 or 148 SMs busy; 4- or 16-byte payloads alike), and a
+        # scattered x gather costs a whole 32-byte sector.  sectors = ncu's L1-miss count for this kernel on this matrix.
         gather_roofline = None
-        if sectors and clocks and clocks.get("sm_mhz"):
-            min_ms = sectors / (148 * 0.95 * clocks["sm_mhz"] * 1e6) * 1e3
-            gather_roofline = {"bound": "sm_l1_miss_sectors", "sectors_per_launch": sectors,
-                               "peak_sectors_per_clk_per_sm": 0.95, "min_ms": min_ms, "frac": min_ms / kernel_ms,
+        if sectors:
+            min_ms = sectors / L2_SECTOR_RATE * 1e3
+            gather_roofline = {"bound": "l2_sector_requests", "sectors_per_launch": sectors,
+                               "peak_sectors_per_s": L2_SECTOR_RATE, "min_ms": min_ms, "frac": min_ms / kernel_ms,
+                               "peak_source": "tools/gather_bench.cu on B200 (profiles/r1_microbench_stream_gather.txt)",
                                "source": "ncu l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum (profiles/)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -362,8 +365,8 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": bytes_alg_local,
                          "launches_per_step": int(eng.launches_per_run(idx)),
                          "note": "rank 0's row block, one launch per step; traffic = ncu dram read+write of the same "
-                                 "kernel on the N=1 matrix (profiles/); the binding limit on this matrix is the SM's "
-                                 "L1-miss request rate for the x gathers, not HBM (DESIGN.md)"},
+                                 "kernel on the N=1 matrix (profiles/); the binding limit on this matrix is the L2's "
+                                 "sector request rate (every scattered x gather costs a 32-byte sector), not HBM (DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * spec.cols + 4 * spec.rows),
                     "d2h_bytes_per_step": int(4 * spec.rows), "ms_per_step": e2e_ms,
                     "bit_identical_to_device_path": e2e_bad == 0.0,

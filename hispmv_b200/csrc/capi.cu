@@ -27,6 +27,8 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
   return e == cudaErrorMemoryAllocation ? HISPMV_FULL : HISPMV_ERR_CUDA;
 }
 
+constexpr int kMaxRunChunks = 16;  // row ranges the host-buffer call pipelines against PCIe copies
+
 struct Matrix {
   bool dense = false;
   int32_t rows = 0, cols = 0;          // global shape
@@ -116,7 +118,7 @@ struct hispmv_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second lane for pipelined linear(); H2D lane of the pipelined run()
   cudaStream_t stream3 = nullptr;  // D2H lane of the pipelined run()
-  cudaEvent_t ev_pipe[2 * 8 + 1] = {};  // x ready, bias chunk ready x8, kernel chunk done x8
+  cudaEvent_t ev_pipe[2 * kMaxRunChunks + 1] = {};  // x ready, bias range ready x16, kernel range done x16
   cudaEvent_t ev_bias = nullptr;
   int shard_part = 0, shard_parts = 1;
   int64_t mem_limit = 0;
@@ -834,41 +836,95 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
     return HISPMV_OK;
   }
   // range boundaries: tile indices where a new row starts (never between two chunks of a split row)
-  int64_t tb[9];
+  // Ranges are sized by ROWS (what the copies move), equal shares.  Measured on C2 (profiles/r1_e2e_shares.txt):
+  // 8 to 16 equal ranges all take 1.92-1.95 ms; shares that shrink towards the end, or fewer and larger ranges, are
+  // 2-8 % slower because the first y copy starts later.  With both directions busy the link moves ~37 GB/s each way
+  // (HISPMV_RUN_TRACE=1 prints the timeline), against 55 GB/s one way: that, not the kernel, is the floor here.
+  double share[kMaxRunChunks];
+  for (int i = 0; i < chunks; ++i) share[i] = 1.0 / chunks;
+  if (const char* e = getenv("HISPMV_RUN_SHARES")) {  // development sweeps: "f0,f1,...": 2..8 positive shares
+    double f[kMaxRunChunks];
+    int n = 0;
+    const char* q = e;
+    while (n < kMaxRunChunks) {
+      char* end = nullptr;
+      const double v = strtod(q, &end);
+      if (end == q || !(v > 0)) break;
+      f[n++] = v;
+      if (*end != ',') break;
+      q = end + 1;
+    }
+    if (n >= 2) {
+      double sum = 0;
+      for (int i = 0; i < n; ++i) sum += f[i];
+      chunks = n;
+      for (int i = 0; i < n; ++i) share[i] = f[i] / sum;
+    }
+  }
+  int64_t tb[kMaxRunChunks + 1];
   tb[0] = 0;
   tb[chunks] = m->num_tiles;
+  double cum = 0;
   for (int i = 1; i < chunks; ++i) {
-    int64_t t = (m->num_tiles * i) / chunks;
+    cum += share[i - 1];
+    const int32_t want = (int32_t)std::min<double>((double)n_y, cum * (double)n_y);
+    int64_t t = std::lower_bound(m->h_tile_row.begin(), m->h_tile_row.begin() + m->num_tiles, want) -
+                m->h_tile_row.begin();
     t = std::max(t, tb[i - 1]);
     while (t < m->num_tiles && m->h_tile_chunk[(size_t)t] > 0) ++t;
     tb[i] = t;
   }
   cudaStream_t s_up = c->stream2, s_down = c->stream3;
+  // HISPMV_RUN_TRACE=1: device-side timeline of one call (development; events are created per call)
+  static const bool trace = getenv("HISPMV_RUN_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;
+  std::vector<std::string> tname;
+  auto mark = [&](cudaStream_t on, const std::string& what) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, on);
+    tev.push_back(e);
+    tname.push_back(what);
+  };
+  mark(s_up, "start");
   if (x_host) {
     cudaEvent_t ev_x = c->ev_pipe[0];
     HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s_up));
     HISPMV_CUDA(cudaEventRecord(ev_x, s_up));
     HISPMV_CUDA(cudaStreamWaitEvent(s, ev_x, 0));
+    mark(s_up, "x up");
   }
   for (int i = 0; i < chunks; ++i) {
     const int64_t r0 = m->h_tile_row[(size_t)tb[i]], r1 = m->h_tile_row[(size_t)tb[i + 1]];
-    cudaEvent_t ev_b = c->ev_pipe[1 + i], ev_k = c->ev_pipe[9 + i];
+    cudaEvent_t ev_b = c->ev_pipe[1 + i], ev_k = c->ev_pipe[1 + kMaxRunChunks + i];
     if (bias && r1 > r0) {
       HISPMV_CUDA(cudaMemcpyAsync(c->d_bias + r0, bias + r0, (size_t)(r1 - r0) * 4, cudaMemcpyHostToDevice, s_up));
       HISPMV_CUDA(cudaEventRecord(ev_b, s_up));
       HISPMV_CUDA(cudaStreamWaitEvent(s, ev_b, 0));
+      mark(s_up, "bias up " + std::to_string(i));
     }
     st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, tb[i],
                     tb[i + 1] - tb[i]);
     if (st != HISPMV_OK) return st;
     HISPMV_CUDA(cudaEventRecord(ev_k, s));
     HISPMV_CUDA(cudaStreamWaitEvent(s_down, ev_k, 0));
+    mark(s, "kernel " + std::to_string(i));
     if (r1 > r0)
       HISPMV_CUDA(cudaMemcpyAsync(y + r0, c->d_y[0] + r0, (size_t)(r1 - r0) * 4, cudaMemcpyDeviceToHost, s_down));
+    mark(s_down, "y down " + std::to_string(i) + " (" + std::to_string((r1 - r0) * 4 / 1000) + " KB)");
   }
   HISPMV_CUDA(cudaStreamSynchronize(s_down));
   HISPMV_CUDA(cudaStreamSynchronize(s));
   HISPMV_CUDA(cudaStreamSynchronize(s_up));
+  if (trace) {
+    for (size_t i = 1; i < tev.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, tev[0], tev[i]);
+      fprintf(stderr, "[hispmv_run] %-24s done at %.3f ms\n", tname[i].c_str(), ms);
+    }
+    for (auto e : tev) cudaEventDestroy(e);
+  }
   return HISPMV_OK;
 }
 

@@ -355,8 +355,9 @@ def run_ours(args):
                        "l2": f"matrix stream is {8 * local_nnz / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2; "
                              f"x ({4 * spec.cols / 1e6:.0f} MB) is the only operand that can stay L2-resident",
                        "x_exchange": "none (N=1)" if world == 1 else (
-                           ("one multimem.st store of x from rank 0 to the NVSwitch multicast address each step "
-                            "(hispmv_multicast_copy, symmetric-memory replicas, two device barriers)"
+                           ("one store of x from rank 0 to the NVSwitch multicast address each step "
+                            f"(hispmv_multicast_copy, {'copy engine' if xrep.mc_ctas < 0 else str(xrep.mc_ctas or 32) + ' CTAs of multimem.st'}, "
+                            "symmetric-memory replicas, two device barriers)"
                             if xrep.mode == "multicast" else "NCCL broadcast of x from rank 0 each step")
                            + ", double-buffered under the previous step's SpMV")},
             "gb_per_s": (8 * total_nnz + 4 * spec.cols + 4 * spec.rows) / (ms_step * 1e-3) / 1e9,

@@ -8,15 +8,24 @@
 namespace hispmv {
 namespace {
 
+__device__ __forceinline__ void mc_store4(float* dst, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(512) multicast_copy_kernel(float* __restrict__ mc_dst, const float* __restrict__ src,
                                                              int64_t n4, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
-    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_dst + 4 * i), "f"(v.x), "f"(v.y),
-                 "f"(v.z), "f"(v.w)
-                 : "memory");
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16-byte loads in flight per thread
+    const float4 a = __ldg(s4 + i), b = __ldg(s4 + i + stride), c = __ldg(s4 + i + 2 * stride), d = __ldg(s4 + i + 3 * stride);
+    mc_store4(mc_dst + 4 * i, a);
+    mc_store4(mc_dst + 4 * (i + stride), b);
+    mc_store4(mc_dst + 4 * (i + 2 * stride), c);
+    mc_store4(mc_dst + 4 * (i + 3 * stride), d);
   }
+  for (; i < n4; i += stride) mc_store4(mc_dst + 4 * i, __ldg(s4 + i));
   // tail (n not a multiple of 4)
   const int64_t t = 4 * n4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(mc_dst + t), "f"(src[t]) : "memory");
@@ -34,7 +43,11 @@ extern "C" int hispmv_multicast_copy(void* mc_dst, const float* d_src, int64_t n
     return HISPMV_ERR_ARG;
   }
   if (n == 0) return HISPMV_OK;
-  const int grid = sm_budget > 0 ? sm_budget : 16;  // a few CTAs saturate one GPU's NVLink egress
+  if (sm_budget < 0) {  // copy engine writing to the multicast address: no SM at all
+    HISPMV_CUDA(cudaMemcpyAsync(mc_dst, d_src, (size_t)n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return HISPMV_OK;
+  }
+  const int grid = sm_budget > 0 ? sm_budget : 32;
   multicast_copy_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(static_cast<float*>(mc_dst), d_src, n / 4, n);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;

@@ -77,14 +77,27 @@ class XReplicator:
     rendezvous only) and the root stores x ONCE to the NVSwitch multicast address with hispmv_multicast_copy
     (multimem.st): the switch delivers it to every GPU, no SM on the receivers runs anything, and the root's NVLink
     egress carries x once instead of once per peer.  Two small device-side barriers per exchange order it against the
-    readers.  mode "nccl": dist.broadcast.  "auto" tries multicast and falls back to NCCL."""
+    readers.  mode "nccl": dist.broadcast.  "auto": multicast for x up to AUTO_MULTICAST_BYTES, NCCL above or when
+    the multicast mapping is unavailable.
 
-    def __init__(self, n: int, device, group=None, mode: str = "auto", root: int = 0):
+    Measured on 8 B200 (profiles/r1_exchange_probe.txt): one root reaches ~330-400 GB/s through the multicast address
+    (copy engine or 32+ CTAs alike; 560 GB/s with one peer), NCCL's broadcast 400-630 GB/s.  For C2's 40 MB x the
+    multicast store still gives the faster step (4233 vs 3992 GFLOP/s: it takes no SM and no receiver-side kernel away
+    from the SpMV it overlaps); for C5's 400 MB x the transfer itself dominates and NCCL wins (0.64 vs 1.0 ms)."""
+
+    AUTO_MULTICAST_BYTES = 64 << 20
+
+    def __init__(self, n: int, device, group=None, mode: str = "auto", root: int = 0, mc_ctas: Optional[int] = None):
+        import os
         self.n, self.device, self.group, self.root = n, device, group, root
         self.rank = dist.get_rank(group)
         self.npad = (n + 3) & ~3
         self.mode = "nccl"
         self._hdl = None
+        # who issues the multicast stores: -1 = a copy engine (no SM at all), N > 0 = N CTAs of multimem.st
+        self.mc_ctas = int(os.environ.get("HISPMV_MC_CTAS", "-1")) if mc_ctas is None else mc_ctas
+        if mode == "auto" and 4 * n > self.AUTO_MULTICAST_BYTES:
+            mode = "nccl"
         if mode in ("auto", "multicast"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -127,7 +140,7 @@ class XReplicator:
             self._hdl.barrier(channel=cur)          # every rank is done reading replica `cur`
             if self.rank == self.root:
                 mc = self._hdl.multicast_ptr + cur * self.npad * 4
-                check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(src_on_root.data_ptr()), self.n, 16,
+                check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(src_on_root.data_ptr()), self.n, self.mc_ctas,
                                                 C.c_void_p(stream.cuda_stream)), "multicast_copy")
             self._hdl.barrier(channel=2 + cur)      # the stores have landed everywhere
 
@@ -164,8 +177,8 @@ class XReplicator:
             self._hdl.barrier(channel=cur)          # every rank is done reading replica `cur`
             if hi > lo:
                 mc = self._hdl.multicast_ptr + (cur * self.npad + lo) * 4
-                check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(self._stage.data_ptr()), hi - lo, 16,
-                                                C.c_void_p(stream.cuda_stream)), "multicast_copy")
+                check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(self._stage.data_ptr()), hi - lo,
+                                                self.mc_ctas, C.c_void_p(stream.cuda_stream)), "multicast_copy")
             self._hdl.barrier(channel=2 + cur)      # every slice has landed everywhere
         return (hi - lo) * 4
 

@@ -181,8 +181,9 @@ int hispmv_plan_slab_csr(hispmv_ctx* ctx, int idx, int slab, int32_t* row_ptr, i
 int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
 
 /* ---- x exchange over NVSwitch multicast: store n floats from d_src to a multicast address (every GPU of the
- *      multicast group receives them).  mc_dst comes from a symmetric-memory rendezvous; sm_budget = CTAs to use
- *      (0 = 16).  Asynchronous on `stream`; peers need a barrier on the same group before they read. ---- */
+ *      multicast group receives them).  mc_dst comes from a symmetric-memory rendezvous; sm_budget > 0 = that many
+ *      CTAs of multimem.st stores, 0 = 32 CTAs, < 0 = a copy engine writes to the multicast address (no SM used).
+ *      Asynchronous on `stream`; peers need a barrier on the same group before they read. ---- */
 int hispmv_multicast_copy(void* mc_dst, const float* d_src, int64_t n, int sm_budget, void* stream);
 
 /* ---- Matrix Market ingest: real/integer/pattern x general/symmetric/skew-symmetric ---- */

@@ -37,7 +37,7 @@ def main():
     src = torch.arange(n, device="cuda", dtype=torch.float32) + 1 if rank == 0 else torch.zeros(n, device="cuda")
     xs = symm_mem.empty(n, dtype=torch.float32, device=torch.device("cuda", local))
     hdl = symm_mem.rendezvous(xs, group=dist.group.WORLD)
-    mc = hdl.has_multicast_support
+    mc = bool(hdl.multicast_ptr)
     if rank == 0:
         print(f"world={world} n={n} multicast_support={mc} mc_ptr={hex(hdl.multicast_ptr) if mc else None}", flush=True)
     st = torch.cuda.current_stream()
@@ -64,13 +64,19 @@ def main():
         torch.cuda.synchronize()
         dist.barrier()
 
-        def mcast():
-            hdl.barrier(channel=1)              # everyone is done reading the previous x
-            if rank == 0:
-                check(lib.hispmv_multicast_copy(C.c_void_p(hdl.multicast_ptr), C.c_void_p(src.data_ptr()), n, 16,
-                                                C.c_void_p(st.cuda_stream)), "multicast_copy")
-            hdl.barrier(channel=2)              # x has landed everywhere
-        t_mc = timed(mcast)
+        t_by_ctas = {}
+        for ctas in (-1, 16, 32, 64):
+            def mcast():
+                hdl.barrier(channel=1)              # everyone is done reading the previous x
+                if rank == 0:
+                    check(lib.hispmv_multicast_copy(C.c_void_p(hdl.multicast_ptr), C.c_void_p(src.data_ptr()), n, ctas,
+                                                    C.c_void_p(st.cuda_stream)), "multicast_copy")
+                hdl.barrier(channel=2)              # x has landed everywhere
+            t_by_ctas[ctas] = timed(mcast)
+        if rank == 0:
+            print("multicast(+2 barriers) by CTAs: " + "  ".join(f"{c}: {t:.4f} ms ({4 * n / t / 1e6:.0f} GB/s)"
+                                                                for c, t in t_by_ctas.items()), flush=True)
+        t_mc = min(t_by_ctas.values())
         ok_mc = bool(torch.equal(xs, torch.arange(n, device="cuda", dtype=torch.float32) + 1))
     flags = torch.tensor([int(ok_pull), int(ok_mc) if ok_mc is not None else 1], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)

@@ -94,8 +94,10 @@ class XReplicator:
         self.npad = (n + 3) & ~3
         self.mode = "nccl"
         self._hdl = None
-        # who issues the multicast stores: -1 = a copy engine (no SM at all), N > 0 = N CTAs of multimem.st
-        self.mc_ctas = int(os.environ.get("HISPMV_MC_CTAS", "-1")) if mc_ctas is None else mc_ctas
+        # who issues the multicast stores: N > 0 = N CTAs of multimem.st, -1 = a copy engine.  Inside the pipelined
+        # step 16 CTAs are the best measured (N=2, C2: 1086 GFLOP/s; 32 CTAs 1082, 8 CTAs 1074, copy engine 984 --
+        # its transfer is as fast in isolation but overlaps the SpMV worse; profiles/r1_exchange_probe.txt)
+        self.mc_ctas = int(os.environ.get("HISPMV_MC_CTAS", "16")) if mc_ctas is None else mc_ctas
         if mode == "auto" and 4 * n > self.AUTO_MULTICAST_BYTES:
             mode = "nccl"
         if mode in ("auto", "multicast"):

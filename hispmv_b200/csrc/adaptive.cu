@@ -159,7 +159,7 @@ __device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int 
       float v = ep.alpha * s;
       if (ep.beta != 0.0f) v = fmaf(ep.beta, base == beg ? bias0 : ep.bias[r0 + i], v);
       if (ep.relu) v = fmaxf(v, 0.0f);
-      y[r0 + i] = v;
+      store_y(y, r0 + i, v, ep.y_mc);
     }
   }
 }
@@ -174,7 +174,7 @@ constexpr unsigned int kCarryEmpty = kCarryEmptyBits;
 __device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDesc& d, int64_t t, float total, int lane,
                                              float* __restrict__ y, const Epilogue& ep) {
   if (d.nchunks == 1) {
-    if (lane == 0) y[d.r0] = finish(total, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu);
+    if (lane == 0) store_y(y, d.r0, finish(total, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu), ep.y_mc);
     return;
   }
   const int64_t first = t - d.chunk;  // tile id of this row's chunk 0
@@ -201,7 +201,7 @@ __device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDe
   }
   s = warp_sum(s);
   if (lane == 0) {
-    y[d.r0] = finish(s, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu);
+    store_y(y, d.r0, finish(s, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu), ep.y_mc);
     P.counter[first] = 0;  // ready for the next run / graph replay
   }
 }
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(THREADS)
     }
     if (k < e) acc0 = fmaf(s_val[k], gx(s_col[k]), acc0);
     const float acc = subwarp_sum<LANES>(acc0 + acc1);
-    if (sub == 0 && i < trows) y[r0 + i] = finish(acc, ep.alpha, ep.beta, ep.bias, r0 + i, ep.relu);
+    if (sub == 0 && i < trows) store_y(y, r0 + i, finish(acc, ep.alpha, ep.beta, ep.bias, r0 + i, ep.relu), ep.y_mc);
   }
 }
 

@@ -513,8 +513,14 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
 // `lane` selects one of the two carry / counter sets so that linear()'s two stream lanes never share them.
 // Device-pointer callers get lane 0: one run in flight per matrix handle, as with the reference's xrt::run.
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
-               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1) {
+               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1, int y_mc = 0) {
   Epilogue ep{alpha, beta, d_bias, relu};
+  ep.y_mc = y_mc;
+  if (y_mc && !m->dense && (m->kernel == HISPMV_KERNEL_MERGE || !m->slabs.empty() || m->pipeline)) {
+    // these read y back (carry fix-up, slab accumulation) or keep their own store path: a multicast address is write-only
+    set_error("run: this matrix's strategy cannot write y through a multicast address");
+    return HISPMV_ERR_STATE;
+  }
   if (beta != 0.0f && !d_bias) {
     set_error("run: bias is required when beta != 0");
     return HISPMV_ERR_ARG;
@@ -770,6 +776,18 @@ int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_b
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);
   return run_matrix(c, m, d_x, d_bias, d_y, 1.0f, d_bias ? 1.0f : 0.0f, relu, (cudaStream_t)stream);
+}
+
+int hispmv_run_dev_mc(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* mc_y, float alpha,
+                      float beta, int relu, void* stream) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (!mc_y) {
+    set_error("run_dev_mc: null multicast address");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  return run_matrix(c, m, d_x, d_bias, mc_y, alpha, beta, relu, (cudaStream_t)stream, 0, 0, -1, 1);
 }
 
 void* hispmv_stream(hispmv_ctx* c) { return c ? (void*)c->stream : nullptr; }

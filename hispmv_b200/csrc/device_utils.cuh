@@ -167,4 +167,12 @@ __device__ __forceinline__ float finish(float ax, float alpha, float beta, const
   return v;
 }
 
+// y[i] = v, or -- when y is the NVSwitch multicast view of a vector replicated on every GPU (Epilogue::y_mc) -- one
+// multimem.st that the switch delivers to all replicas: the all-gather of a chained layer's y, fused into the kernel
+// that produces it.
+__device__ __forceinline__ void store_y(float* y, int64_t i, float v, int y_mc) {
+  if (y_mc) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(y + i), "f"(v) : "memory");
+  else y[i] = v;
+}
+
 }  // namespace hispmv

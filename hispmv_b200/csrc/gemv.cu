@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(THREADS)
       float s = 0.0f;
 #pragma unroll
       for (int w = 0; w < WARPS; ++w) s += s_red[buf][w][tid];
-      y[r + tid] = finish(s, ep.alpha, ep.beta, ep.bias, r + tid, ep.relu);
+      store_y(y, r + tid, finish(s, ep.alpha, ep.beta, ep.bias, r + tid, ep.relu), ep.y_mc);
     }
     buf ^= 1;  // the next group writes the other buffer, so one barrier per group is enough
   }

@@ -149,6 +149,7 @@ struct Epilogue {
   float alpha, beta;
   const float* bias;  // may be null when beta == 0
   int relu;           // fused max(.,0) (device-resident chained layers only)
+  int y_mc = 0;       // y is a multicast address: results are stored with multimem.st and land on every GPU of the group
 };
 int launch_csr_scalar(const CsrDev& A, const float* x, float* y, Epilogue ep, cudaStream_t s);
 int launch_csr_vector(const CsrDev& A, int lanes, const float* x, float* y, Epilogue ep, cudaStream_t s);

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(256) spmv_csr_scalar_kernel(CsrDev A, const fl
     float acc = 0.0f;
     for (int j = b; j < e; ++j)
       acc = fmaf(ld_stream_f1(A.val + j, ps), ld_x(x + ld_stream_i1(A.col + j, ps), pk), acc);
-    y[r] = finish(acc, ep.alpha, ep.beta, ep.bias, r, ep.relu);
+    store_y(y, r, finish(acc, ep.alpha, ep.beta, ep.bias, r, ep.relu), ep.y_mc);
   }
 }
 
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) spmv_csr_vector_kernel(CsrDev A, const fl
       if (j < e) acc = fmaf(ld_stream_f1(A.val + j, ps), ld_x(x + ld_stream_i1(A.col + j, ps), pk), acc);
     }
     acc = subwarp_sum<LANES>(acc);
-    if (lane == 0 && r < A.rows) y[r] = finish(acc, ep.alpha, ep.beta, ep.bias, r, ep.relu);
+    if (lane == 0 && r < A.rows) store_y(y, r, finish(acc, ep.alpha, ep.beta, ep.bias, r, ep.relu), ep.y_mc);
   }
 }
 
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) spmv_merge_fixup_kernel(MergePlan P, int3
 
 __global__ void __launch_bounds__(256) spmv_empty_kernel(int32_t rows, float* __restrict__ y, Epilogue ep) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < rows) y[r] = finish(0.0f, ep.alpha, ep.beta, ep.bias, r, ep.relu);
+  if (r < rows) store_y(y, r, finish(0.0f, ep.alpha, ep.beta, ep.bias, r, ep.relu), ep.y_mc);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -131,6 +131,14 @@ class Engine:
         check(lib.hispmv_linear_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), int(relu),
                                     C.c_void_p(stream)), "linear_dev")
 
+    def run_dev_mc(self, matrix_idx: int, x, bias, mc_y: int, alpha: float = 1.0, beta: float = 0.0,
+                   relu: bool = False, stream: int = 0) -> None:
+        """As run_dev, but y goes through `mc_y`, the NVSwitch multicast address of this rank's first row inside a
+        vector replicated on every GPU: the results land on all ranks (the all-gather of a chained layer fused into
+        the producing kernel, hispmv_run_dev_mc).  Peers need a barrier before they read."""
+        check(lib.hispmv_run_dev_mc(self._ctx, matrix_idx, _dptr(x), _dptr(bias), C.c_void_p(mc_y), alpha, beta,
+                                    int(relu), C.c_void_p(stream)), "run_dev_mc")
+
     @property
     def stream(self) -> int:
         return int(lib.hispmv_stream(self._ctx) or 0)

@@ -140,9 +140,15 @@ class DeviceChain:
     """Chained layers that never leave HBM: y_k = relu(A_k x_k + b_k) with bias and ReLU fused into the kernel
     epilogue (hispmv_linear_dev).  With `shards` (a hispmv_b200.sharded.RowBlocks per layer) every rank holds a row
     block of each layer and the blocks of y are all-gathered into the next layer's replicated x.  `graph=True`
-    captures the launches of one forward pass in a CUDA graph and replays it."""
+    captures the launches of one forward pass in a CUDA graph and replays it.
 
-    def __init__(self, engine, layers: Sequence[nn.Module], relu: Sequence[bool], comm=None, graph: bool = False):
+    `fused=True` (sharded chains on NVSwitch boxes): the activations live in symmetric memory and every layer's kernel
+    stores its y block straight to the multicast address of the next layer's x (Engine.run_dev_mc, multimem.st), so
+    the all-gather disappears into the producing kernel; one device-side barrier per layer orders it against the
+    readers.  Falls back to the NCCL all-gather when no multicast mapping can be made."""
+
+    def __init__(self, engine, layers: Sequence[nn.Module], relu: Sequence[bool], comm=None, graph: bool = False,
+                 fused: bool = False):
         self.engine, self.comm = engine, comm
         self.idx: List[int] = []
         self.bias: List[torch.Tensor] = []
@@ -162,7 +168,27 @@ class DeviceChain:
                 comm.set_blocks(("chain", id(self), len(self.blocks) - 1), rb, re, torch.device("cuda", engine.device_id))
         engine.load_matrices()
         dev = torch.device("cuda", engine.device_id)
-        self._x = [torch.empty(c, device=dev) for _, c in self.shapes] + [torch.empty(self.shapes[-1][0], device=dev)]
+        sizes = [c for _, c in self.shapes] + [self.shapes[-1][0]]
+        self.fused, self._hdl, self._mc = False, None, []
+        if fused and comm is not None:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                import torch.distributed as dist
+                offs = [0]
+                for n in sizes:
+                    offs.append(offs[-1] + ((n + 3) & ~3))          # 16-byte aligned activations in one allocation
+                buf = symm_mem.empty(offs[-1], dtype=torch.float32, device=dev)
+                hdl = symm_mem.rendezvous(buf, group=comm.group if comm.group is not None else dist.group.WORLD)
+                if not hdl.multicast_ptr:
+                    raise RuntimeError("no multicast mapping (NVLS unavailable)")
+                buf.zero_()
+                self._x = [buf[offs[k]:offs[k] + n] for k, n in enumerate(sizes)]
+                self._mc = [hdl.multicast_ptr + 4 * o for o in offs[:-1]]   # multicast view of activation k
+                self._hdl, self._symm, self.fused = hdl, buf, True
+            except Exception as ex:  # noqa: BLE001
+                self.fused_unavailable = f"{type(ex).__name__}: {ex}"
+        if not self.fused:
+            self._x = [torch.empty(n, device=dev) for n in sizes]
         self._y_local = [torch.empty(re - rb, device=dev) for rb, re in self.blocks]
         self._graph = None
         self._want_graph = graph and comm is None
@@ -171,6 +197,12 @@ class DeviceChain:
         for k, idx in enumerate(self.idx):
             rb, re = self.blocks[k]
             whole = (re - rb) == self.shapes[k][0]
+            if self.fused:
+                # y block -> every rank's copy of the next activation, by the kernel's own stores
+                self.engine.run_dev_mc(idx, self._x[k], self.bias[k], self._mc[k + 1] + 4 * rb, 1.0, 1.0,
+                                       relu=self.relu[k], stream=stream)
+                self._hdl.barrier(channel=k)
+                continue
             y = self._x[k + 1] if whole else self._y_local[k]
             self.engine.linear_dev(idx, self._x[k], self.bias[k], y, relu=self.relu[k], stream=stream)
             if not whole:

@@ -159,6 +159,16 @@ int hispmv_run_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bi
 /* y = relu?(A x + bias) for chained layers that stay on the device. */
 int hispmv_linear_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
                       void* stream);
+
+/* The all-gather of a chained layer fused into the kernel that produces y: mc_y is the NVSwitch MULTICAST address of
+ * this rank's first row inside a vector replicated on every GPU of a multicast group (symmetric-memory rendezvous), and
+ * every result is stored with multimem.st, so the switch delivers this rank's y block to all replicas -- the next
+ * layer's x -- with no separate collective (reference: the host-side copy of y into the next layer's input,
+ * apps/fpga_layer_manager.py:58-67).  y = relu?(alpha*A x + beta*bias).  Peers need a barrier on the group before
+ * they read.  Strategies that read y back (MERGE, column slabs) refuse with HISPMV_ERR_STATE. */
+int hispmv_run_dev_mc(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* mc_y, float alpha,
+                      float beta, int relu, void* stream);
+
 int hispmv_sync(hispmv_ctx* ctx);
 /* number of kernels one hispmv_run_dev of matrix idx launches (for bench.py's gpu_launches) */
 int hispmv_launches_per_run(hispmv_ctx* ctx, int idx);

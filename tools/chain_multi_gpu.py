@@ -30,31 +30,47 @@ def main():
         p.requires_grad = False
     eng = Engine(local, shard=(rank, world))
     comm = RowBlockComm()
-    chain = DeviceChain(eng, [model.dense, model.sparse1, model.sparse2], relu=[True, True, True], comm=comm)
-    ok = True
-    for trial in range(3):
+    layers = [model.dense, model.sparse1, model.sparse2]
+    chain = DeviceChain(eng, layers, relu=[True, True, True], comm=comm)
+    fused = DeviceChain(eng, layers, relu=[True, True, True], comm=comm, fused=True)
+    ok, same = True, True
+    for trial in range(20):
         x = torch.randn(4096)
         with torch.no_grad():
             ref = model(x.view(1, -1)).numpy().reshape(-1)
         out = chain.forward(x.cuda()).cpu().numpy()
-        ok = ok and bool(np.allclose(out, ref, rtol=1e-3, atol=1e-4))
+        # three un-normalised randn layers: outputs are O(1e3) sums of cancelling terms, so the bar is relative to
+        # the largest output (general_test.py's own check is rtol=1e-3 on such sums, apps/general_test.py:106)
+        ok = ok and bool(np.abs(out - ref).max() <= 1e-4 * np.abs(ref).max())
+        out_f = fused.forward(x.cuda()).cpu().numpy()
+        same = same and bool(np.array_equal(out.view(np.uint32), out_f.view(np.uint32)))   # same kernels, same bits
     xd = torch.randn(4096, device="cuda")
-    for _ in range(5):
-        chain.forward(xd)
-    torch.cuda.synchronize()
-    dist.barrier()
-    t0 = time.perf_counter()
-    iters = 200
-    for _ in range(iters):
-        chain.forward(xd)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / iters * 1e6
-    flag = torch.tensor([1 if ok else 0], device="cuda")
+    times = {}
+    for name, ch in (("nccl all-gather", chain), ("fused multicast store" if fused.fused else "fused(unavailable)", fused)):
+        for _ in range(5):
+            ch.forward(xd)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 200
+        e0.record()
+        for _ in range(iters):
+            ch.forward(xd)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times[name] = float(t)
+    flag = torch.tensor([1 if ok else 0, 1 if same else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         blocks = [(b[1] - b[0]) for b in chain.blocks]
-        print(f"chain_multi_gpu: world={world} parity={'ok' if int(flag) else 'FAILED'} rows per rank {blocks} "
-              f"{dt:.1f} us per forward pass (3 layers + {sum(1 for b, s in zip(chain.blocks, chain.shapes) if b[1]-b[0] != s[0])} all-gathers)")
+        print(f"chain_multi_gpu: world={world} parity={'ok' if int(flag[0]) else 'FAILED'} "
+              f"fused==allgather bit-for-bit={'yes' if int(flag[1]) else 'NO'} (fused path active: {fused.fused}"
+              f"{'' if fused.fused else ' -- ' + getattr(fused, 'fused_unavailable', '')}) rows per rank {blocks}")
+        for name, us in times.items():
+            print(f"  {name:24s} {us:8.1f} us per forward pass (3 layers, device time, max over ranks)")
+    flag = flag.min().reshape(1)
     eng.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag) else 1)

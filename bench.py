@@ -8,11 +8,13 @@ A step is one pass y = alpha*A*x + beta*y0 over the whole matrix.
   N = 1   the C2 matrix on one B200.
   N > 1   weak scaling: the matrix has N x 10M rows (same generator, same 10M columns), split into
           nnz-balanced contiguous row blocks, one per rank (one process per GPU, torchrun).  x is produced on
-          rank 0 and replicated by an NCCL broadcast every step; the broadcast of step k+1 runs on a second
-          stream under the SpMV of step k (the reference pipelines consecutive vectors the same way,
-          pyhispmv/src/fpga_handle.cpp:366-379).
+          rank 0 and replicated every step -- one multimem.st store stream to the NVSwitch multicast address
+          (hispmv_multicast_copy; NCCL broadcast when no multicast mapping exists or x is larger than 64 MB); the
+          exchange of step k+1 runs on a second stream under the SpMV of step k (the reference pipelines
+          consecutive vectors the same way, pyhispmv/src/fpga_handle.cpp:366-379).
 `value` is device-resident whole-job throughput (CUDA events, max over ranks).  `e2e` is the same metric through
-the plugin's host-buffer call (hispmv_run: x and bias from pinned host memory, y back to the host, every step).
+the plugin's host-buffer call (hispmv_run: x and bias from pinned host memory, y back to the host, every step; at
+N > 1 every rank sends 1/N of x across PCIe and the slices meet over NVLink, then hispmv_run_xdev).
 `--impl reference` times the reference's own CPU path (mkl_sparse_s_mv exactly as cpu/src/main.cpp:26-49 calls
 it, compiled unmodified into oracle/_ref) on the host cores, on the same matrix.
 """
@@ -217,7 +219,7 @@ def run_ours(args):
         xbuf = [xrep.buffer(0), xrep.buffer(1)]
     else:
         xrep = None
-        xbuf = [x_src.clone() for _ in range(2)]
+        xbuf = [x_src, x_src]                 # no exchange at N=1: one resident x
     bias = b_host.cuda()
     y = torch.empty(n_local, device="cuda")
     comp = torch.cuda.Stream()

@@ -643,6 +643,65 @@ def test_host_run_pipelines_row_ranges(eng):
     assert err <= TOL, (err, at)
 
 
+def test_run_xdev_matches_run_and_respects_the_x_stream(eng, monkeypatch):
+    """hispmv_run_xdev: x already in HBM, produced on another stream; host bias and y.  Same bits as hispmv_run, also
+    with uneven row-range shares (HISPMV_RUN_SHARES) and when x is still being written when the call is made."""
+    import ctypes as C
+    import torch
+    from hispmv_b200 import synth
+    from hispmv_b200.capi import lib, check
+    spec = synth.c2_powerlaw(0.11)
+    d = synth.DeviceCSR(spec)
+    idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
+    d.close()
+    x, y0 = synth.reference_vectors(spec.rows, spec.cols)
+    y_ref = np.full(spec.rows, np.nan, np.float32)
+    eng.select_matrix(idx)
+    eng.run_kernel(x, y0, y_ref, float(ALPHA), float(BETA))
+    side = torch.cuda.Stream()
+    xh = torch.from_numpy(x).pin_memory()
+    bh = torch.from_numpy(y0).pin_memory()
+    for shares in (None, "5,1,1,3,1,1,1,1,1,2,1"):
+        if shares:
+            monkeypatch.setenv("HISPMV_RUN_SHARES", shares)
+        xd = torch.zeros(spec.cols, device="cuda")
+        yh = torch.full((spec.rows,), float("nan")).pin_memory()
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(20_000_000)                 # x arrives late: the call must wait for the side stream
+            xd.copy_(xh, non_blocking=True)
+        check(lib.hispmv_run_xdev(eng._ctx, C.c_void_p(xd.data_ptr()), C.c_void_p(side.cuda_stream),
+                                  C.c_void_p(bh.data_ptr()), C.c_void_p(yh.data_ptr()), float(ALPHA), float(BETA)),
+              "run_xdev")
+        assert np.array_equal(yh.numpy().view(np.uint32), y_ref.view(np.uint32)), shares
+    monkeypatch.delenv("HISPMV_RUN_SHARES", raising=False)
+    st = lib.hispmv_run_xdev(eng._ctx, C.c_void_p(0), C.c_void_p(0), C.c_void_p(bh.data_ptr()),
+                             C.c_void_p(yh.data_ptr()), 1.0, 0.0)
+    assert st != 0                                         # null x is refused
+
+
+def test_multicast_y_is_refused_where_y_is_read_back(eng):
+    """hispmv_run_dev_mc: strategies that read y back (merge-path fix-up) cannot write through a write-only multicast
+    address and must say so before launching anything.  (The store path itself needs two GPUs: test_multi_gpu.py.)"""
+    import ctypes as C
+    import torch
+    from hispmv_b200 import capi
+    from hispmv_b200.capi import lib
+    rng = np.random.default_rng(2)
+    r, c, v = _rand_coo(rng, 3000, 2000, 40000)
+    idx = eng.create_sparse_handle(r, c, v, 3000, 2000)
+    eng.force_kernel(idx, capi.KERNEL_MERGE)
+    x = torch.zeros(2000, device="cuda")
+    y = torch.full((3000,), 7.0, device="cuda")
+    st = lib.hispmv_run_dev_mc(eng._ctx, idx, C.c_void_p(x.data_ptr()), C.c_void_p(0), C.c_void_p(y.data_ptr()), 1.0,
+                               0.0, 0, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert st == -5 and b"multicast" in lib.hispmv_last_error()           # HISPMV_ERR_STATE, nothing launched
+    assert bool((y == 7.0).all())
+    st = lib.hispmv_run_dev_mc(eng._ctx, idx, C.c_void_p(x.data_ptr()), C.c_void_p(0), C.c_void_p(0), 1.0, 0.0, 0,
+                               C.c_void_p(0))
+    assert st != 0                                                         # null multicast address
+
+
 def test_column_slabs_bit_exact_and_within_tolerance(eng, monkeypatch):
     """x larger than L2: the matrix is cut into column slabs (CSR over the same rows, bit-exact against a numpy
     restatement), one launch per slab, y accumulating across them; bias / ReLU applied exactly once."""

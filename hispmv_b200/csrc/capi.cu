@@ -115,6 +115,8 @@ struct hispmv_ctx {
   int device = 0;
   int flags = 0;
   int sm_count = 148;
+  int64_t l2_persist_max = 0, l2_window_max = 0;  // device limits for persisting L2 lines / access-policy windows
+  bool l2_persist_on = false;                     // the persisting carve-out has been set aside (column slabs)
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second lane for pipelined linear(); H2D lane of the pipelined run()
   cudaStream_t stream3 = nullptr;  // D2H lane of the pipelined run()
@@ -536,11 +538,35 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
   if (!m->slabs.empty()) {
     // y = alpha*A_0 x + beta*bias, then y += alpha*A_s x for the other slabs (the kernels read bias[r] and write y[r]
     // from the same thread, so y can be its own bias); ReLU only after the last slab
+    // HISPMV_L2_PERSIST=1: mark the x slab a pass gathers from as persisting in L2 and everything else on the stream as
+    // streaming (cudaStreamAttributeAccessPolicyWindow), so the 8-bytes-per-nonzero stream cannot push the slab out
+    static const int want_persist = getenv("HISPMV_L2_PERSIST") ? atoi(getenv("HISPMV_L2_PERSIST")) : 0;
+    const bool persist = want_persist > 0 && c->l2_persist_max > 0 && c->l2_window_max > 0;
+    if (persist && !c->l2_persist_on) {
+      HISPMV_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)c->l2_persist_max));
+      c->l2_persist_on = true;
+    }
     for (size_t k = 0; k < m->slabs.size(); ++k) {
       const bool first = k == 0, last = k + 1 == m->slabs.size();
+      if (persist) {
+        const int64_t lo = (int64_t)k * m->slab_cols;
+        const int64_t bytes = std::min<int64_t>(std::min<int64_t>(m->slab_cols, m->cols - lo) * 4, c->l2_window_max);
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = const_cast<float*>(d_x + lo);
+        av.accessPolicyWindow.num_bytes = (size_t)bytes;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)c->l2_persist_max / (double)bytes);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        HISPMV_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+      }
       int st = run_matrix(c, m->slabs[k], d_x, first ? d_bias : d_y, d_y, alpha, first ? beta : 1.0f, last ? relu : 0, s,
                           lane);
       if (st != HISPMV_OK) return st;
+    }
+    if (persist) {
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.num_bytes = 0;
+      HISPMV_CUDA(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
     }
     return HISPMV_OK;
   }
@@ -633,6 +659,8 @@ int hispmv_create(hispmv_ctx** out, int device_id, int flags) {
   c->device = device_id;
   c->flags = flags;
   c->sm_count = prop.multiProcessorCount;
+  c->l2_persist_max = prop.persistingL2CacheMaxSize;
+  c->l2_window_max = prop.accessPolicyMaxWindowSize;
   int st = check_cuda(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
   if (st == HISPMV_OK) st = check_cuda(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking), "stream", __FILE__, __LINE__);
   if (st == HISPMV_OK) st = check_cuda(cudaEventCreateWithFlags(&c->ev_bias, cudaEventDisableTiming), "event", __FILE__, __LINE__);

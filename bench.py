@@ -185,8 +185,12 @@ def run_ours(args):
             raise SystemExit("launch N>1 with torchrun (one rank per GPU)")
         args.gpus = world
     torch.cuda.set_device(local)
+    affinity = "not requested"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not args.no_numa_bind:
+            from hispmv_b200.sharded import bind_to_gpu_numa
+            affinity = bind_to_gpu_numa(local)      # before any pinned allocation
 
     if args.workload == "c5":   # BASELINE configs[4]: one 100M x 100M, 1B-nnz matrix split over the ranks (strong scaling)
         spec = synth.c5_uniform(args.scale)
@@ -372,7 +376,7 @@ def run_ours(args):
                                  "sector request rate (every scattered x gather costs a 32-byte sector), not HBM (DESIGN.md)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * spec.cols + 4 * spec.rows),
                     "d2h_bytes_per_step": int(4 * spec.rows), "ms_per_step": e2e_ms,
-                    "bit_identical_to_device_path": e2e_bad == 0.0,
+                    "bit_identical_to_device_path": e2e_bad == 0.0, "cpu_affinity_rank0": affinity,
                     "api": "hispmv_run (host x, bias -> host y), pinned host memory" if world == 1 else
                            "per rank: 1/N of the host x up + slices exchanged over NVLink (XReplicator.gather_from_host, "
                            f"{xrep.mode}), then hispmv_run_xdev (host bias block -> host y block), pinned host memory"},
@@ -427,6 +431,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's local CPUs")
     ap.add_argument("--x-exchange", default="auto", choices=["auto", "multicast", "nccl"],
                     help="N>1: how x reaches every rank each step (auto = NVSwitch multicast if available, else NCCL)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],

@@ -69,6 +69,28 @@ class RowBlockComm:
         return x
 
 
+def bind_to_gpu_numa(device_index: int) -> str:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index`, so that pinned host buffers
+    allocated afterwards (first touch) sit on the GPU's NUMA node and host <-> device copies do not cross sockets.
+    One process per GPU makes this the natural place.  Returns a short description; never raises."""
+    try:
+        import os
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return f"unchanged ({len(allowed)} cpus, no narrower GPU-local set)"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to {len(cpus)} GPU-local cpus ({min(cpus)}-{max(cpus)})"
+    except Exception as ex:  # noqa: BLE001
+        return f"unchanged ({type(ex).__name__}: {ex})"
+
+
 class XReplicator:
     """x produced on one rank -> a replica on every rank, double-buffered so that the exchange of step k+1 runs under
     the SpMV of step k.

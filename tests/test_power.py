@@ -65,3 +65,16 @@ def test_nvml_reader_on_the_box():
     mon.stop_monitoring()
     avg, n = mon.get_average_power()
     assert n >= 3 and 30.0 < avg < 1500.0 and mon.get_max_power() >= avg
+
+
+def test_numa_binding_helper_never_raises():
+    """sharded.bind_to_gpu_numa: without NVML (this container) or without a narrower GPU-local CPU set it reports
+    'unchanged' and leaves the affinity mask alone."""
+    import os
+    from hispmv_b200.sharded import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    msg = bind_to_gpu_numa(0)
+    assert isinstance(msg, str) and (msg.startswith("unchanged") or msg.startswith("bound to"))
+    if msg.startswith("unchanged"):
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)

@@ -8,6 +8,7 @@
 #include <sstream>
 #include <string>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -1157,8 +1158,13 @@ int hispmv_plan_split_rows(hispmv_ctx* c, int idx, int32_t* rows_out) {
 // banner "%%MatrixMarket matrix coordinate {real|integer|pattern} {general|symmetric|skew-symmetric}",
 // comment lines skipped, 1-based indices, pattern entries get 1.0, explicit zeros are dropped, symmetric
 // and skew-symmetric files are expanded with (c, r, +-v) for off-diagonal entries.
-int hispmv_load_mtx(hispmv_ctx* c, const char* path) {
-  if (!c || !path) return HISPMV_ERR_ARG;
+int hispmv_parse_mtx(const char* path, int32_t* rows_out, int32_t* cols_out, int64_t* nnz_out, int32_t** r_out,
+                     int32_t** c_out, float** v_out) {
+  if (!path || !rows_out || !cols_out || !nnz_out || !r_out || !c_out || !v_out) return HISPMV_ERR_ARG;
+  *r_out = nullptr;
+  *c_out = nullptr;
+  *v_out = nullptr;
+  *nnz_out = 0;
   FILE* f = fopen(path, "rb");
   if (!f) {
     set_error(std::string("Error: Unable to open file ") + path);
@@ -1227,40 +1233,122 @@ int hispmv_load_mtx(hispmv_ctx* c, const char* path) {
     set_error("Error: bad size line");
     return HISPMV_ERR_IO;
   }
-  std::vector<int32_t> R, C;
-  std::vector<float> V;
-  const size_t reserve = (size_t)nnz_decl * ((symm || skew) ? 2 : 1);
-  R.reserve(reserve);
-  C.reserve(reserve);
-  V.reserve(reserve);
-  while (p < end) {
-    char* q;
-    while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
-    if (p >= end) break;
-    const long r = strtol(p, &q, 10);
-    if (q == p) break;
-    p = q;
-    const long cc = strtol(p, &q, 10);
-    if (q == p) break;
-    p = q;
-    float v = 1.0f;
-    if (!pattern) {
-      v = strtof(p, &q);
-      if (q == p) break;
-      p = q;
-    }
-    while (p < end && *p != '\n') ++p;  // rest of the line
-    if (v == 0) continue;
-    R.push_back((int32_t)(r - 1));
-    C.push_back((int32_t)(cc - 1));
-    V.push_back(v);
-    if ((symm || skew) && r != cc) {
-      R.push_back((int32_t)(cc - 1));
-      C.push_back((int32_t)(r - 1));
-      V.push_back(skew ? -v : v);
-    }
+  // The entry lines are cut into one chunk per thread at line boundaries; every thread parses its chunk into its own
+  // arrays and the chunks are concatenated in file order, so the COO comes out exactly as a serial reader produces it.
+  struct Chunk {
+    std::vector<int32_t> r, c;
+    std::vector<float> v;
+    bool stopped = false;  // a line that does not parse ends the file (as in the reference readers)
+  };
+  const size_t body = (size_t)(end - p);
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::max(1u, std::min(nt ? nt : 1u, 16u));
+  nt = (unsigned)std::max<size_t>(1, std::min<size_t>(nt, body / (1u << 20) + 1));
+  if (const char* e = getenv("HISPMV_MTX_THREADS")) nt = (unsigned)std::max(1, std::min(64, atoi(e)));
+  std::vector<const char*> cut(nt + 1);
+  cut[0] = p;
+  cut[nt] = end;
+  for (unsigned i = 1; i < nt; ++i) {
+    const char* q = p + body * i / nt;
+    q = std::max(q, cut[i - 1]);
+    const char* nl = q < end ? (const char*)memchr(q, '\n', end - q) : nullptr;
+    cut[i] = nl ? nl + 1 : end;
   }
-  return hispmv_add_sparse_coo(c, R.data(), C.data(), V.data(), (int64_t)R.size(), (int32_t)rows, (int32_t)cols);
+  std::vector<Chunk> chunks(nt);
+  auto parse = [&](unsigned i) {
+    Chunk& ck = chunks[i];
+    const char* s = cut[i];
+    const char* e = cut[i + 1];
+    const size_t guess = (size_t)(e - s) / 12 + 16;
+    ck.r.reserve(guess);
+    ck.c.reserve(guess);
+    ck.v.reserve(guess);
+    while (s < e) {
+      char* q;
+      while (s < e && (*s == ' ' || *s == '\t' || *s == '\r' || *s == '\n')) ++s;
+      if (s >= e) break;
+      const long r = strtol(s, &q, 10);
+      if (q == s) { ck.stopped = true; break; }
+      s = q;
+      const long cc = strtol(s, &q, 10);
+      if (q == s) { ck.stopped = true; break; }
+      s = q;
+      float v = 1.0f;
+      if (!pattern) {
+        v = strtof(s, &q);
+        if (q == s) { ck.stopped = true; break; }
+        s = q;
+      }
+      while (s < e && *s != '\n') ++s;  // rest of the line
+      if (v == 0) continue;
+      ck.r.push_back((int32_t)(r - 1));
+      ck.c.push_back((int32_t)(cc - 1));
+      ck.v.push_back(v);
+      if ((symm || skew) && r != cc) {
+        ck.r.push_back((int32_t)(cc - 1));
+        ck.c.push_back((int32_t)(r - 1));
+        ck.v.push_back(skew ? -v : v);
+      }
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (unsigned i = 1; i < nt; ++i) pool.emplace_back(parse, i);
+    parse(0);
+    for (auto& t : pool) t.join();
+  }
+  size_t total = 0;
+  unsigned used = 0;
+  for (; used < nt; ++used) {
+    total += chunks[used].r.size();
+    if (chunks[used].stopped) { ++used; break; }
+  }
+  int32_t* R = (int32_t*)malloc(std::max<size_t>(total, 1) * sizeof(int32_t));
+  int32_t* Cc = (int32_t*)malloc(std::max<size_t>(total, 1) * sizeof(int32_t));
+  float* V = (float*)malloc(std::max<size_t>(total, 1) * sizeof(float));
+  if (!R || !Cc || !V) {
+    free(R);
+    free(Cc);
+    free(V);
+    set_error("Error: out of host memory");
+    return HISPMV_ERR_IO;
+  }
+  size_t off = 0;
+  for (unsigned i = 0; i < used; ++i) {
+    const size_t n = chunks[i].r.size();
+    if (n) {
+      memcpy(R + off, chunks[i].r.data(), n * sizeof(int32_t));
+      memcpy(Cc + off, chunks[i].c.data(), n * sizeof(int32_t));
+      memcpy(V + off, chunks[i].v.data(), n * sizeof(float));
+    }
+    off += n;
+  }
+  *rows_out = (int32_t)rows;
+  *cols_out = (int32_t)cols;
+  *nnz_out = (int64_t)total;
+  *r_out = R;
+  *c_out = Cc;
+  *v_out = V;
+  return HISPMV_OK;
+}
+
+void hispmv_parse_mtx_free(int32_t* r, int32_t* c, float* v) {
+  free(r);
+  free(c);
+  free(v);
+}
+
+int hispmv_load_mtx(hispmv_ctx* c, const char* path) {
+  if (!c || !path) return HISPMV_ERR_ARG;
+  int32_t rows = 0, cols = 0;
+  int64_t nnz = 0;
+  int32_t *R = nullptr, *Cc = nullptr;
+  float* V = nullptr;
+  int st = hispmv_parse_mtx(path, &rows, &cols, &nnz, &R, &Cc, &V);
+  if (st != HISPMV_OK) return st;
+  st = hispmv_add_sparse_coo(c, R, Cc, V, nnz, rows, cols);
+  hispmv_parse_mtx_free(R, Cc, V);
+  return st;
 }
 
 }  // extern "C"

@@ -198,6 +198,24 @@ class Engine:
         return out
 
 
+def parse_mtx(path: str):
+    """Matrix Market file -> (rows_i32, cols_i32, vals_f32, n_rows, n_cols): the multithreaded host parser behind
+    load_mtx (hispmv_parse_mtx), 0-based COO in file order with loadMtx's rules (common/src/spmv-helper.cpp:34-136).
+    Needs no GPU."""
+    nr, nc, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+    r, c_, v = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    check(lib.hispmv_parse_mtx(path.encode(), C.byref(nr), C.byref(nc), C.byref(nnz), C.byref(r), C.byref(c_),
+                               C.byref(v)), "parse_mtx")
+    try:
+        n = nnz.value
+        rows = np.ctypeslib.as_array(C.cast(r, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n].copy()
+        cols = np.ctypeslib.as_array(C.cast(c_, C.POINTER(C.c_int32)), shape=(max(n, 1),))[:n].copy()
+        vals = np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_float)), shape=(max(n, 1),))[:n].copy()
+    finally:
+        lib.hispmv_parse_mtx_free(r, c_, v)
+    return rows, cols, vals, nr.value, nc.value
+
+
 def shard_bounds(row_ptr, n_parts: int) -> np.ndarray:
     rp = _np(row_ptr, np.int32)
     out = np.empty(n_parts + 1, np.int32)

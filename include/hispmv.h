@@ -198,6 +198,13 @@ int hispmv_multicast_copy(void* mc_dst, const float* d_src, int64_t n, int sm_bu
 
 /* ---- Matrix Market ingest: real/integer/pattern x general/symmetric/skew-symmetric ---- */
 int hispmv_load_mtx(hispmv_ctx* ctx, const char* path);
+/* The parser behind hispmv_load_mtx on its own (host only, no GPU needed): the entry lines are parsed by one thread per
+ * ~1 MB chunk and come out as 0-based COO in file order, exactly what loadMtx (common/src/spmv-helper.cpp:34-136) and
+ * its two twins (gpu/src/spmvHelper.cpp:4-115, cpu/src/helper_functions.cpp:91-210) return.  Arrays are malloc'ed by the
+ * callee; release them with hispmv_parse_mtx_free. */
+int hispmv_parse_mtx(const char* path, int32_t* rows, int32_t* cols, int64_t* nnz, int32_t** coo_rows,
+                     int32_t** coo_cols, float** coo_vals);
+void hispmv_parse_mtx_free(int32_t* coo_rows, int32_t* coo_cols, float* coo_vals);
 
 #ifdef __cplusplus
 }

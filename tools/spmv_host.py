@@ -109,28 +109,37 @@ def main() -> int:
     e1.record()
     e1.synchronize()
     one_ms = max(e0.elapsed_time(e1), 1e-3)
-    rp_time = max(1, min(100000, int(a.exec_ms / one_ms)))
-    if a.power_s > 0:                                              # spmv-host.cpp:146-147: run for power_s seconds
-        rp_time = max(rp_time, int(a.power_s * 1000.0 / one_ms))
+    clock_mhz = getattr(torch.cuda.get_device_properties(a.device), "clock_rate", 1965000) / 1e3
+    print(f"Approx. Clock Cycles: {int(one_ms * 1e3 * clock_mhz)}")   # SM cycles of one product (reference: FPGA cycles)
+    # spmv-host.cpp:120-150: rp_time fills exec_ms and is capped at 2^15 (a uint16 kernel argument there); what does
+    # not fit becomes whole repeats of the batch ("Num samples"), scaled up to power_s seconds for a power run
+    rp_wanted = max(1.0, a.exec_ms / one_ms)
+    rp_time = int(min(rp_wanted, 1 << 15))
+    num_samples = rp_wanted / rp_time if int(rp_wanted) != rp_time else 1.0
+    if a.power_s > 0:
+        num_samples *= a.power_s * 1000.0 / a.exec_ms
+    num_samples = max(1, int(num_samples))
     print(f"Using Repeat Time: {rp_time}")
+    print(f"Using Num samples: {num_samples}")
     monitor = None
     if a.power_s > 0:
         from hispmv_b200.power import GpuPowerMonitor, report
         name = os.path.splitext(os.path.basename(a.args[0]))[0] if len(a.args) == 1 else f"dense_{a.args[0]}x{a.args[1]}"
         monitor = GpuPowerMonitor(period_s=min(1.0, max(0.05, a.power_s / 10)))
-        monitor.start_monitoring(a.device, log_path=os.path.join("power_logs", name + ".log"))
+        monitor.start_monitoring(a.device, debug=True, log_path=os.path.join("power_logs", name + ".log"))
     print("Kernel Launched")
     e0.record()
-    for k in range(rp_time):
-        eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
-        if monitor is not None and (k & 1023) == 1023:
-            torch.cuda.current_stream().synchronize()            # keep the launch queue bounded on long power runs
+    for _ in range(num_samples):
+        for _ in range(rp_time):
+            eng.run_dev(idx, xd, cd, yd, alpha, beta, st)
+        torch.cuda.current_stream().synchronize()                # one batch in flight at a time, as run.wait() there
     e1.record()
     e1.synchronize()
     print("Kernel Finished")
     if monitor is not None:
         monitor.stop_monitoring()
         print(report(monitor))
+    rp_time *= num_samples
     total_ms = e0.elapsed_time(e1)
     t_us = total_ms * 1e3 / rp_time
     print(f"Total Kernel Runtime: {total_ms:.6f}ms")

@@ -4,9 +4,13 @@ The reference is single-device (one xrt::device, pyhispmv/src/fpga_handle.cpp:55
 design the north star adds.  Rows are independent, so the SpMV itself needs no collective: rank r owns the
 contiguous row block [bounds[r], bounds[r+1]) of every matrix (split points = lower_bound(row_ptr, k*nnz/G), rows are
 never split across GPUs; dense matrices use equal row blocks) and a full copy of x.  Two exchange steps exist:
-  * broadcast_x   x produced on one rank -> all ranks (NCCL broadcast over NVLink)
+  * x replication   x produced on one rank (or held by every rank in host memory) -> all ranks: XReplicator, one
+                    multimem.st store stream to the NVSwitch multicast address (hispmv_multicast_copy), NCCL
+                    broadcast / all-gather as the fallback and for x above 64 MB
   * allgather_rows  chained layers: every rank's y block -> the next layer's replicated x.  Blocks have unequal
                     row counts, so they travel padded to the largest block and are compacted by one gather.
+                    layers.DeviceChain(fused=True) removes this step: the kernel stores y through the multicast
+                    address of the next layer's x (hispmv_run_dev_mc).
 torch.distributed supplies the process group (NCCL on GPUs; the same code runs over gloo on CPU tensors, which is how
 tests/test_sharded_cpu.py covers the bookkeeping).  All arithmetic stays in libhispmv_cuda.so.
 """

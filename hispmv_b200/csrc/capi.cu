@@ -116,6 +116,11 @@ struct hispmv_ctx {
   int device = 0;
   int flags = 0;
   int sm_count = 148;
+  // batches (several right-hand sides per pass): interleaved x per stream lane, and host-path staging for a group
+  float* d_xi[2] = {nullptr, nullptr};
+  int64_t cap_xi = 0;
+  float *d_xb = nullptr, *d_yb = nullptr;
+  int64_t cap_xb = 0, cap_yb = 0;
   int64_t l2_persist_max = 0, l2_window_max = 0;  // device limits for persisting L2 lines / access-policy windows
   bool l2_persist_on = false;                     // the persisting carve-out has been set aside (column slabs)
   cudaStream_t stream = nullptr;
@@ -171,6 +176,10 @@ int ensure_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
       HISPMV_CUDA(cudaMalloc((void**)&c->d_y[l], (size_t)n_y * 4));
     }
     cudaFree(c->d_bias);
+  cudaFree(c->d_xi[0]);
+  cudaFree(c->d_xi[1]);
+  cudaFree(c->d_xb);
+  cudaFree(c->d_yb);
     c->d_bias = nullptr;
     HISPMV_CUDA(cudaMalloc((void**)&c->d_bias, (size_t)n_y * 4));
     c->cap_y = n_y;
@@ -620,6 +629,108 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
   }
 }
 
+constexpr int kBatchMax = 8;              // vectors per pass (batch.cu)
+constexpr int kBatchMaxRowNnz = 1 << 16;  // a sub-warp walks a whole row: keep the longest row bounded
+
+int ensure_batch_xi(hispmv_ctx* c, int64_t n) {
+  if (n > c->cap_xi) {
+    for (int l = 0; l < 2; ++l) {
+      cudaFree(c->d_xi[l]);
+      c->d_xi[l] = nullptr;
+      HISPMV_CUDA(cudaMalloc((void**)&c->d_xi[l], (size_t)n * 4));
+    }
+    c->cap_xi = n;
+  }
+  return HISPMV_OK;
+}
+
+int ensure_batch_host_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
+  if (n_x > c->cap_xb) {
+    cudaFree(c->d_xb);
+    c->d_xb = nullptr;
+    HISPMV_CUDA(cudaMalloc((void**)&c->d_xb, (size_t)n_x * 4));
+    c->cap_xb = n_x;
+  }
+  if (n_y > c->cap_yb) {
+    cudaFree(c->d_yb);
+    c->d_yb = nullptr;
+    HISPMV_CUDA(cudaMalloc((void**)&c->d_yb, (size_t)n_y * 4));
+    c->cap_yb = n_y;
+  }
+  return HISPMV_OK;
+}
+
+// Dense matrices, and sparse ones whose longest row a sub-warp can walk, take several vectors per pass;
+// HISPMV_BATCH=0 turns it off.
+bool batch_eligible(const Matrix* m) {
+  static const bool off = getenv("HISPMV_BATCH") && atoi(getenv("HISPMV_BATCH")) == 0;
+  if (!off && m->dense) return m->local_rows() > 0 && m->cols > 0;
+  return !off && !m->dense && m->slabs.empty() && m->kernel != HISPMV_KERNEL_EMPTY && m->nnz > 0 &&
+         m->local_rows() > 0 && m->stats.max_row_nnz <= kBatchMaxRowNnz;
+}
+
+// y [nv][rows] = alpha * A x_k + beta * bias for the nv vectors x [nv][cols] (both row-major in HBM), in passes of up to
+// eight vectors where the matrix allows it, vector by vector otherwise.  `lane` picks the context's scratch set.
+int run_matrix_batch(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, int64_t nv, float alpha,
+                     float beta, int relu, cudaStream_t s, int lane = 0) {
+  const int64_t rows = m->local_rows();
+  if (nv <= 0) return HISPMV_OK;
+  if (nv == 1 || !batch_eligible(m)) {
+    for (int64_t v = 0; v < nv; ++v) {
+      int st = run_matrix(c, m, d_x + v * m->cols, d_bias, d_y + v * rows, alpha, beta, relu, s, lane);
+      if (st != HISPMV_OK) return st;
+    }
+    return HISPMV_OK;
+  }
+  if (beta != 0.0f && !d_bias) {
+    set_error("run: bias is required when beta != 0");
+    return HISPMV_ERR_ARG;
+  }
+  const int64_t x_rows = m->dense ? m->ld : (int64_t)m->cols;  // rows of the interleaved x (dense: padded like A)
+  int st = ensure_batch_xi(c, (int64_t)kBatchMax * x_rows);
+  if (st != HISPMV_OK) return st;
+  if (m->dense) {
+    DenseDev D;
+    D.rows = (int32_t)rows;
+    D.cols = m->cols;
+    D.ld = m->ld;
+    D.a = m->d_a;
+    Epilogue epd{alpha, beta, d_bias, relu};
+    for (int64_t v0 = 0; v0 < nv; v0 += kBatchMax) {
+      const int g = (int)std::min<int64_t>(kBatchMax, nv - v0);
+      if (g == 1) {
+        st = run_matrix(c, m, d_x + v0 * m->cols, d_bias, d_y + v0 * rows, alpha, beta, relu, s, lane);
+      } else {
+        st = launch_interleave(d_x + v0 * m->cols, g, m->cols, x_rows, c->d_xi[lane], s);
+        if (st == HISPMV_OK) st = launch_gemm_lite(D, c->d_xi[lane], d_y + v0 * rows, g, epd, s);
+      }
+      if (st != HISPMV_OK) return st;
+    }
+    return HISPMV_OK;
+  }
+  const double mean = (double)m->nnz / (double)rows;
+  const int lanes = mean >= 64 ? 32 : mean >= 32 ? 16 : mean >= 16 ? 8 : mean >= 8 ? 4 : 2;
+  CsrDev A;
+  A.rows = (int32_t)rows;
+  A.cols = m->cols;
+  A.nnz = m->nnz;
+  A.row_ptr = m->d_row_ptr;
+  A.col = m->d_col;
+  A.val = m->d_val;
+  Epilogue ep{alpha, beta, d_bias, relu};
+  for (int64_t v0 = 0; v0 < nv; v0 += kBatchMax) {
+    const int g = (int)std::min<int64_t>(kBatchMax, nv - v0);
+    if (g == 1) {
+      st = run_matrix(c, m, d_x + v0 * m->cols, d_bias, d_y + v0 * rows, alpha, beta, relu, s, lane);
+    } else {
+      st = launch_interleave(d_x + v0 * m->cols, g, m->cols, m->cols, c->d_xi[lane], s);
+      if (st == HISPMV_OK) st = launch_spmm_csr(A, lanes, c->d_xi[lane], d_y + v0 * rows, g, ep, s);
+    }
+    if (st != HISPMV_OK) return st;
+  }
+  return HISPMV_OK;
+}
+
 Matrix* get_matrix(hispmv_ctx* c, int64_t idx) {
   if (!c) {
     set_error("null context");
@@ -819,6 +930,18 @@ int hispmv_run_dev_mc(hispmv_ctx* c, int idx, const float* d_x, const float* d_b
   return run_matrix(c, m, d_x, d_bias, mc_y, alpha, beta, relu, (cudaStream_t)stream, 0, 0, -1, 1);
 }
 
+int hispmv_run_dev_batch(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, int64_t num_vecs,
+                         float alpha, float beta, int relu, void* stream) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (num_vecs < 0 || (num_vecs > 0 && (!d_x || !d_y))) {
+    set_error("run_dev_batch: bad arguments");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  return run_matrix_batch(c, m, d_x, d_bias, d_y, num_vecs, alpha, beta, relu, (cudaStream_t)stream);
+}
+
 void* hispmv_stream(hispmv_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int hispmv_sync(hispmv_ctx* c) {
@@ -1010,6 +1133,26 @@ int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const f
   if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, lanes[0]));
   HISPMV_CUDA(cudaEventRecord(c->ev_bias, lanes[0]));
   HISPMV_CUDA(cudaStreamWaitEvent(lanes[1], c->ev_bias, 0));
+  if (num_vecs >= 2 && batch_eligible(m)) {
+    // Several vectors: groups of up to eight share one pass over the matrix (batch.cu).  Groups alternate between the two
+    // stream lanes, each with its own half of the staging, so the copies of one group overlap the pass of the other.
+    st = ensure_batch_host_staging(c, 2 * (int64_t)kBatchMax * m->cols, 2 * (int64_t)kBatchMax * n_y);
+    if (st != HISPMV_OK) return st;
+    int l = 0;
+    for (int64_t v0 = 0; v0 < num_vecs; v0 += kBatchMax, l ^= 1) {
+      const int64_t g = std::min<int64_t>(kBatchMax, num_vecs - v0);
+      float* xb = c->d_xb + (int64_t)l * kBatchMax * m->cols;
+      float* yb = c->d_yb + (int64_t)l * kBatchMax * n_y;
+      HISPMV_CUDA(cudaMemcpyAsync(xb, x + v0 * m->cols, (size_t)(g * m->cols) * 4, cudaMemcpyHostToDevice, lanes[l]));
+      st = run_matrix_batch(c, m, xb, c->d_bias, yb, g, 1.0f, 1.0f, 0, lanes[l], l);
+      if (st != HISPMV_OK) return st;
+      if (n_y > 0)
+        HISPMV_CUDA(cudaMemcpyAsync(y_out + v0 * n_y, yb, (size_t)(g * n_y) * 4, cudaMemcpyDeviceToHost, lanes[l]));
+    }
+    HISPMV_CUDA(cudaStreamSynchronize(lanes[0]));
+    HISPMV_CUDA(cudaStreamSynchronize(lanes[1]));
+    return HISPMV_OK;
+  }
   // Vectors alternate between two stream lanes so the copy of vector v+1 overlaps the kernel of vector v
   // (the reference overlaps host fill with the FPGA run the same way, fpga_handle.cpp:366-379).
   for (int64_t v = 0; v < num_vecs; ++v) {

@@ -176,6 +176,13 @@ constexpr int kRowstageMaxCap = 8192;
 int launch_empty(int32_t rows, float* y, Epilogue ep, cudaStream_t s);
 bool merge_tile_items_supported(int tile_items);
 
+// ---- batch.cu: several right-hand sides in one pass over A (x interleaved as xi[c * K + k], K = batch_width(nv)) ----
+int batch_width(int nv);  // 2, 4 or 8
+// x [nv][n] -> xi [n_pad][K] (rows n..n_pad-1 and vectors nv..K-1 zero)
+int launch_interleave(const float* x, int nv, int64_t n, int64_t n_pad, float* xi, cudaStream_t s);
+// y [nv][rows] = alpha * A x_k + beta * bias (+ReLU); `lanes` lanes walk each row
+int launch_spmm_csr(const CsrDev& A, int lanes, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s);
+
 // ---- gemv.cu --------------------------------------------------------------------------------
 struct DenseDev {
   int32_t rows = 0, cols = 0;
@@ -183,5 +190,7 @@ struct DenseDev {
   const float* a = nullptr;
 };
 int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm_count, cudaStream_t s);
+// batch.cu: y [nv][rows] for nv <= 8 vectors interleaved as xi [ld][K]
+int launch_gemm_lite(const DenseDev& A, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s);
 
 }  // namespace hispmv

@@ -139,6 +139,15 @@ class Engine:
         check(lib.hispmv_run_dev_mc(self._ctx, matrix_idx, _dptr(x), _dptr(bias), C.c_void_p(mc_y), alpha, beta,
                                     int(relu), C.c_void_p(stream)), "run_dev_mc")
 
+    def run_dev_batch(self, matrix_idx: int, x, bias, y, alpha: float = 1.0, beta: float = 0.0, relu: bool = False,
+                      stream: int = 0) -> None:
+        """Several right-hand sides in one pass over the matrix: x is (num_vecs, cols), y (num_vecs, local rows), both
+        contiguous CUDA tensors (hispmv_run_dev_batch)."""
+        if x.dim() != 2 or y.dim() != 2 or x.shape[0] != y.shape[0]:
+            raise ValueError("expected x (num_vecs, cols) and y (num_vecs, rows)")
+        check(lib.hispmv_run_dev_batch(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), int(x.shape[0]), alpha,
+                                       beta, int(relu), C.c_void_p(stream)), "run_dev_batch")
+
     @property
     def stream(self) -> int:
         return int(lib.hispmv_stream(self._ctx) or 0)

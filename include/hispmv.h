@@ -169,6 +169,15 @@ int hispmv_linear_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d
 int hispmv_run_dev_mc(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* mc_y, float alpha,
                       float beta, int relu, void* stream);
 
+/* Several right-hand sides in one pass ("SpMM-lite"): d_x is [num_vecs][cols], d_y [num_vecs][local rows], both
+ * row-major in HBM; y_k = relu?(alpha*A x_k + beta*bias).  The reference runs a batch vector by vector (runLinear's
+ * loop, pyhispmv/src/fpga_handle.cpp:336,366-379); here up to eight vectors are interleaved so that col/val are read
+ * once and one 32-byte sector gather serves all of them.  Dense matrices and sparse matrices whose longest row has at
+ * most 65536 nonzeros take this path, everything else falls back to one launch per vector (same results contract).
+ * hispmv_linear uses it for num_vecs >= 2. */
+int hispmv_run_dev_batch(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, int64_t num_vecs,
+                         float alpha, float beta, int relu, void* stream);
+
 int hispmv_sync(hispmv_ctx* ctx);
 /* number of kernels one hispmv_run_dev of matrix idx launches (for bench.py's gpu_launches) */
 int hispmv_launches_per_run(hispmv_ctx* ctx, int idx);

@@ -702,6 +702,99 @@ def test_multicast_y_is_refused_where_y_is_read_back(eng):
     assert st != 0                                                         # null multicast address
 
 
+@pytest.mark.parametrize("shape", ["dnn", "short_rows", "with_empty_rows"])
+def test_batched_vectors_one_pass(eng, shape):
+    """Several right-hand sides per pass (hispmv_run_dev_batch, and linear() with num_vecs >= 2): every vector within
+    the north_star bar of the float64 oracle, for 1..11 vectors (groups of 8 / 4 / 2 and a single left over), with
+    alpha/beta and the fused ReLU on the device call."""
+    import torch
+    rng = np.random.default_rng({"dnn": 1, "short_rows": 2, "with_empty_rows": 3}[shape])
+    if shape == "dnn":
+        rows, cols = 2048, 1536
+        w = rng.standard_normal((rows, cols)).astype(np.float32) * (rng.random((rows, cols)) < 0.1)
+        r, c = np.nonzero(w)
+        v = w[r, c]
+    elif shape == "short_rows":
+        rows, cols = 30000, 5000
+        r, c, v = _rand_coo(rng, rows, cols, 90000, dup=0.02)
+    else:
+        rows, cols = 5000, 7000
+        lens = np.minimum(rng.zipf(1.6, rows), 4000)
+        lens[rng.integers(0, rows, 1500)] = 0
+        r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+        c = rng.integers(0, cols, r.size).astype(np.int32)
+        v = rng.standard_normal(r.size).astype(np.float32)
+    r, c, v = r.astype(np.int32), c.astype(np.int32), v.astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    rp, ci, vv = eng.plan_csr(idx)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    for nv in (1, 2, 3, 5, 8, 11):
+        X = rng.standard_normal((nv, cols)).astype(np.float32)
+        # host path: linear() = alpha = beta = 1 (fpga_handle.cpp:351-352), returns num_vecs * rows values
+        Y = eng.linear(idx, X.reshape(-1), bias).reshape(nv, rows)
+        for k in range(nv):
+            y64, scale = ol.spmv_f64(rp, ci, vv, X[k], bias, 1.0, 1.0)
+            err, at = ol.max_scaled_error(Y[k], y64, scale)
+            assert err <= TOL, (shape, nv, k, err, at)
+        # device path with alpha / beta / ReLU
+        Xd, bd = torch.from_numpy(X).cuda(), torch.from_numpy(bias).cuda()
+        Yd = torch.full((nv, rows), float("nan"), device="cuda")
+        eng.run_dev_batch(idx, Xd, bd, Yd, float(ALPHA), float(BETA), relu=True,
+                          stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        Yh = Yd.cpu().numpy()
+        for k in range(nv):
+            y64, scale = ol.spmv_f64(rp, ci, vv, X[k], bias, ALPHA, BETA)
+            pos = y64 > 1e-4 * np.maximum(scale, 1e-30)
+            err, _ = ol.max_scaled_error(Yh[k][pos], y64[pos], scale[pos])
+            assert err <= TOL and np.all(Yh[k] >= 0)
+            assert np.all(Yh[k][y64 < -1e-4 * np.maximum(scale, 1e-30)] == 0)
+
+
+@pytest.mark.parametrize("rows,cols", [(1, 1), (257, 1031), (1024, 4096), (37, 70001)])
+def test_batched_vectors_dense_one_pass(eng, rows, cols):
+    """The dense overlay with several vectors (gemm_lite_kernel): every vector within the bar of the float64 oracle,
+    ragged shapes (cols not a multiple of 4, odd row counts), host and device calls."""
+    import torch
+    rng = np.random.default_rng(rows * 7 + cols)
+    a = rng.standard_normal((rows, cols)).astype(np.float32)
+    idx = eng.create_dense_handle(a.reshape(-1), rows, cols)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    for nv in (2, 3, 8, 9):
+        X = rng.standard_normal((nv, cols)).astype(np.float32)
+        Y = eng.linear(idx, X.reshape(-1), bias).reshape(nv, rows)
+        Xd, bd = torch.from_numpy(X).cuda(), torch.from_numpy(bias).cuda()
+        Yd = torch.full((nv, rows), float("nan"), device="cuda")
+        eng.run_dev_batch(idx, Xd, bd, Yd, float(ALPHA), float(BETA), stream=torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        Yh = Yd.cpu().numpy()
+        for k in range(nv):
+            y64, scale = ol.gemv_f64(a, rows, cols, X[k], bias, 1.0, 1.0)
+            assert ol.max_scaled_error(Y[k], y64, scale)[0] <= TOL, (nv, k)
+            y64, scale = ol.gemv_f64(a, rows, cols, X[k], bias, ALPHA, BETA)
+            assert ol.max_scaled_error(Yh[k], y64, scale)[0] <= TOL, (nv, k)
+
+
+def test_batch_falls_back_for_rows_a_sub_warp_cannot_walk(eng):
+    """A row above 65536 nonzeros keeps the batch on the one-launch-per-vector path: same contract."""
+    rng = np.random.default_rng(9)
+    rows, cols = 300, 200000
+    lens = np.full(rows, 50)
+    lens[7] = 70000
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    assert eng.matrix_info(idx)["max_row_nnz"] == 70000
+    rp, ci, vv = eng.plan_csr(idx)
+    bias = rng.standard_normal(rows).astype(np.float32)
+    X = rng.standard_normal((3, cols)).astype(np.float32)
+    Y = eng.linear(idx, X.reshape(-1), bias).reshape(3, rows)
+    for k in range(3):
+        y64, scale = ol.spmv_f64(rp, ci, vv, X[k], bias, 1.0, 1.0)
+        assert ol.max_scaled_error(Y[k], y64, scale)[0] <= TOL
+
+
 def test_column_slabs_bit_exact_and_within_tolerance(eng, monkeypatch):
     """x larger than L2: the matrix is cut into column slabs (CSR over the same rows, bit-exact against a numpy
     restatement), one launch per slab, y accumulating across them; bias / ReLU applied exactly once."""

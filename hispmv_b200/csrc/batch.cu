@@ -8,7 +8,7 @@
 //     single-vector gather fetches for 4 useful bytes (the L2 sector rate is what binds).
 // Sparse rows are walked by sub-warps of LANES lanes (the csr_vector shape), so the path is offered for matrices whose
 // longest row a sub-warp can walk (DNN layers); others keep running vector by vector.  The dense overlay has the same
-// treatment (gemm_lite_kernel): A is streamed once for up to eight vectors.
+// treatment (gemm_lite_kernel): A is streamed once for up to eight vectors, x panels staged in shared memory.
 #include "device_utils.cuh"
 #include "internal.h"
 
@@ -93,17 +93,37 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(CsrDev A, const float* __
   }
 }
 
-// Dense overlay with several vectors ("GeMM-lite"): a warp owns R consecutive rows and sweeps the columns four at a
-// time; the 4K interleaved x values of those columns come through L1 once and feed all R rows and K vectors.
-template <int K, int R>
-__global__ void __launch_bounds__(256) gemm_lite_kernel(DenseDev A, const float* __restrict__ xi, float* __restrict__ y,
+// Dense overlay with several vectors ("GeMM-lite").  Columns are cut into panels of kPanel4 * 4 = 512; the x values of
+// a panel for all K vectors (16 KB at K = 8) are staged in shared memory once per CTA and reused by every row the CTA
+// owns -- through L1 alone the 128-256 KB of interleaved x does not stay resident next to the stream of A, and the
+// first version of this kernel ran at the speed of its L2 x reads (profiles/r1_batch_probe.txt).  x comes in the layout
+// xp[panel][j * K + k][c4] (column 4 * (panel * kPanel4 + c4) + j, vector k): staging is a straight coalesced copy
+// and the compute loop's shared-memory reads are conflict-free (consecutive lanes, consecutive c4).
+constexpr int kPanel4 = 128;
+
+template <int K>
+__global__ void __launch_bounds__(256) interleave_panel_kernel(const float* __restrict__ x, int nv, int64_t n,
+                                                               int64_t total, float* __restrict__ xp) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+    const int c4l = (int)(o % kPanel4);
+    const int64_t t = o / kPanel4;
+    const int jk = (int)(t % (4 * K));
+    const int64_t p = t / (4 * K);
+    const int j = jk / K, k = jk % K;
+    const int64_t c = 4 * (p * kPanel4 + c4l) + j;
+    xp[o] = (k < nv && c < n) ? x[(int64_t)k * n + c] : 0.0f;
+  }
+}
+
+template <int K, int R>  // a warp owns R consecutive rows, a CTA 8 * R
+__global__ void __launch_bounds__(256) gemm_lite_kernel(DenseDev A, const float* __restrict__ xp, float* __restrict__ y,
                                                         int nv, Epilogue ep) {
+  __shared__ __align__(16) float xs[4 * K][kPanel4];
   const uint64_t ps = policy_evict_first();
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t r0 = warp * R;
-  if (r0 >= A.rows) return;
-  const int nr = (int)min((int64_t)R, (int64_t)A.rows - r0);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * R;
+  const int nr = (int)max((int64_t)0, min((int64_t)R, (int64_t)A.rows - r0));
   const int ncol4 = (int)(A.ld >> 2);
   float acc[R][K];
 #pragma unroll
@@ -111,23 +131,40 @@ __global__ void __launch_bounds__(256) gemm_lite_kernel(DenseDev A, const float*
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[q][k] = 0.0f;
   const float* arow = A.a + r0 * A.ld;
-  for (int c4 = lane; c4 < ncol4; c4 += 32) {
-    float4 a[R];
+  constexpr int T = kPanel4 / 32;  // column groups per lane and panel
+  for (int p0 = 0, p = 0; p0 < ncol4; p0 += kPanel4, ++p) {
+    // this panel's rows of A are requested first: their DRAM round trip overlaps the staging of x
+    float4 a[T][R];
 #pragma unroll
-    for (int q = 0; q < R; ++q)
-      a[q] = q < nr ? ld_stream_f4(arow + (int64_t)q * A.ld + 4 * c4, ps) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float xv[4][K];
+    for (int t = 0; t < T; ++t)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) load_xk<K>(xi, 4 * c4 + j, xv[j]);
+      for (int q = 0; q < R; ++q) {
+        const int c4 = p0 + lane + 32 * t;
+        a[t][q] = (c4 < ncol4 && q < nr) ? ld_stream_f4(arow + (int64_t)q * A.ld + 4 * c4, ps)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    __syncthreads();  // every warp is done with the previous panel
+    {
+      const float4* src = reinterpret_cast<const float4*>(xp + (int64_t)p * (4 * K * kPanel4));
+      float4* dst = reinterpret_cast<float4*>(&xs[0][0]);
+      for (int i = tid; i < K * kPanel4; i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
 #pragma unroll
-    for (int q = 0; q < R; ++q)
+    for (int t = 0; t < T; ++t) {
+      const int c4l = lane + 32 * t;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        acc[q][k] = fmaf(a[q].x, xv[0][k], acc[q][k]);
-        acc[q][k] = fmaf(a[q].y, xv[1][k], acc[q][k]);
-        acc[q][k] = fmaf(a[q].z, xv[2][k], acc[q][k]);
-        acc[q][k] = fmaf(a[q].w, xv[3][k], acc[q][k]);
+        const float x0 = xs[0 * K + k][c4l], x1 = xs[1 * K + k][c4l], x2 = xs[2 * K + k][c4l], x3 = xs[3 * K + k][c4l];
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+          acc[q][k] = fmaf(a[t][q].x, x0, acc[q][k]);
+          acc[q][k] = fmaf(a[t][q].y, x1, acc[q][k]);
+          acc[q][k] = fmaf(a[t][q].z, x2, acc[q][k]);
+          acc[q][k] = fmaf(a[t][q].w, x3, acc[q][k]);
+        }
       }
+    }
   }
 #pragma unroll
   for (int q = 0; q < R; ++q)
@@ -144,17 +181,76 @@ __global__ void __launch_bounds__(256) gemm_lite_kernel(DenseDev A, const float*
 }
 
 template <int K>
-int launch_gemm_lite_k(const DenseDev& A, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s) {
-  constexpr int R = 2;
-  const int64_t warps = (A.rows + R - 1) / R;
-  const int grid = (int)((warps + 7) / 8);
-  gemm_lite_kernel<K, R><<<grid, 256, 0, s>>>(A, xi, y, nv, ep);
+int launch_gemm_lite_k(const DenseDev& A, const float* xp, float* y, int nv, Epilogue ep, cudaStream_t s) {
+  // rows per warp: more rows share every staged panel, fewer keep small matrices spread over the SMs
+  if (A.rows >= 148 * 32) {
+    gemm_lite_kernel<K, 4><<<(int)(((int64_t)A.rows + 31) / 32), 256, 0, s>>>(A, xp, y, nv, ep);
+  } else if (A.rows >= 148 * 16) {
+    gemm_lite_kernel<K, 2><<<(int)(((int64_t)A.rows + 15) / 16), 256, 0, s>>>(A, xp, y, nv, ep);
+  } else {
+    gemm_lite_kernel<K, 1><<<(int)(((int64_t)A.rows + 7) / 8), 256, 0, s>>>(A, xp, y, nv, ep);
+  }
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }
 
+// Few, long rows (a 1024 x 8192 layer at density 0.25 has 1024 rows of ~2048 nonzeros): one CTA per row keeps all SMs
+// busy where one warp per row would leave most of them idle.
+template <int K>
+__global__ void __launch_bounds__(256) spmm_csr_cta_kernel(CsrDev A, const float* __restrict__ xi, float* __restrict__ y,
+                                                           int nv, Epilogue ep) {
+  __shared__ float s_red[8][K];
+  const uint64_t ps = policy_evict_first();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t r = blockIdx.x; r < A.rows; r += gridDim.x) {
+    const int b = A.row_ptr[r], e = A.row_ptr[r + 1];
+    float acc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = 0.0f;
+    int j = b + tid;
+    for (; j + 256 < e; j += 512) {
+      const int c0 = ld_stream_i1(A.col + j, ps), c1 = ld_stream_i1(A.col + j + 256, ps);
+      const float v0 = ld_stream_f1(A.val + j, ps), v1 = ld_stream_f1(A.val + j + 256, ps);
+      float x0[K], x1[K];
+      load_xk<K>(xi, c0, x0);
+      load_xk<K>(xi, c1, x1);
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(v0, x0[k], acc[k]);
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(v1, x1[k], acc[k]);
+    }
+    if (j < e) {
+      const int c0 = ld_stream_i1(A.col + j, ps);
+      const float v0 = ld_stream_f1(A.val + j, ps);
+      float x0[K];
+      load_xk<K>(xi, c0, x0);
+#pragma unroll
+      for (int k = 0; k < K; ++k) acc[k] = fmaf(v0, x0[k], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = warp_sum(acc[k]);
+    __syncthreads();  // the previous row's s_red has been read
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) s_red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < K && tid < nv) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += s_red[w][tid];
+      y[(int64_t)tid * A.rows + r] = finish(t, ep.alpha, ep.beta, ep.bias, r, ep.relu);
+    }
+  }
+}
+
 template <int K>
 int launch_spmm_k(const CsrDev& A, int lanes, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s) {
+  if (lanes > 32) {  // one CTA per row
+    spmm_csr_cta_kernel<K><<<(int)std::min<int64_t>(A.rows, 148 * 16), 256, 0, s>>>(A, xi, y, nv, ep);
+    HISPMV_CUDA(cudaGetLastError());
+    return HISPMV_OK;
+  }
   const int64_t threads = (int64_t)A.rows * lanes;
   const int grid = (int)std::min<int64_t>((threads + 255) / 256, 148 * 64);
   switch (lanes) {
@@ -180,6 +276,26 @@ int launch_interleave(const float* x, int nv, int64_t n, int64_t n_pad, float* x
     case 8: interleave_kernel<8><<<grid, 256, 0, s>>>(x, nv, n, n_pad, xi); break;
     case 4: interleave_kernel<4><<<grid, 256, 0, s>>>(x, nv, n, n_pad, xi); break;
     default: interleave_kernel<2><<<grid, 256, 0, s>>>(x, nv, n, n_pad, xi); break;
+  }
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int64_t panel_floats(int64_t ld) {  // floats of the panel layout for kBatchMax = 8 vectors
+  const int64_t panels = ((ld >> 2) + kPanel4 - 1) / kPanel4;
+  return std::max<int64_t>(panels, 1) * 4 * 8 * kPanel4;
+}
+
+int launch_interleave_panels(const float* x, int nv, int64_t n, int64_t ld, float* xp, cudaStream_t s) {
+  const int K = batch_width(nv);
+  const int64_t panels = ((ld >> 2) + kPanel4 - 1) / kPanel4;
+  const int64_t total = panels * 4 * K * kPanel4;
+  if (total <= 0) return HISPMV_OK;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  switch (K) {
+    case 8: interleave_panel_kernel<8><<<grid, 256, 0, s>>>(x, nv, n, total, xp); break;
+    case 4: interleave_panel_kernel<4><<<grid, 256, 0, s>>>(x, nv, n, total, xp); break;
+    default: interleave_panel_kernel<2><<<grid, 256, 0, s>>>(x, nv, n, total, xp); break;
   }
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;

@@ -176,10 +176,6 @@ int ensure_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
       HISPMV_CUDA(cudaMalloc((void**)&c->d_y[l], (size_t)n_y * 4));
     }
     cudaFree(c->d_bias);
-  cudaFree(c->d_xi[0]);
-  cudaFree(c->d_xi[1]);
-  cudaFree(c->d_xb);
-  cudaFree(c->d_yb);
     c->d_bias = nullptr;
     HISPMV_CUDA(cudaMalloc((void**)&c->d_bias, (size_t)n_y * 4));
     c->cap_y = n_y;
@@ -635,7 +631,7 @@ constexpr int kBatchMaxRowNnz = 1 << 16;  // a sub-warp walks a whole row: keep 
 int ensure_batch_xi(hispmv_ctx* c, int64_t n) {
   if (n > c->cap_xi) {
     for (int l = 0; l < 2; ++l) {
-      cudaFree(c->d_xi[l]);
+      HISPMV_CUDA(cudaFree(c->d_xi[l]));
       c->d_xi[l] = nullptr;
       HISPMV_CUDA(cudaMalloc((void**)&c->d_xi[l], (size_t)n * 4));
     }
@@ -646,13 +642,13 @@ int ensure_batch_xi(hispmv_ctx* c, int64_t n) {
 
 int ensure_batch_host_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
   if (n_x > c->cap_xb) {
-    cudaFree(c->d_xb);
+    HISPMV_CUDA(cudaFree(c->d_xb));
     c->d_xb = nullptr;
     HISPMV_CUDA(cudaMalloc((void**)&c->d_xb, (size_t)n_x * 4));
     c->cap_xb = n_x;
   }
   if (n_y > c->cap_yb) {
-    cudaFree(c->d_yb);
+    HISPMV_CUDA(cudaFree(c->d_yb));
     c->d_yb = nullptr;
     HISPMV_CUDA(cudaMalloc((void**)&c->d_yb, (size_t)n_y * 4));
     c->cap_yb = n_y;
@@ -675,6 +671,7 @@ int run_matrix_batch(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_
                      float beta, int relu, cudaStream_t s, int lane = 0) {
   const int64_t rows = m->local_rows();
   if (nv <= 0) return HISPMV_OK;
+  HISPMV_CUDA(cudaPeekAtLastError());  // a stale error must not be blamed on the launches below
   if (nv == 1 || !batch_eligible(m)) {
     for (int64_t v = 0; v < nv; ++v) {
       int st = run_matrix(c, m, d_x + v * m->cols, d_bias, d_y + v * rows, alpha, beta, relu, s, lane);
@@ -686,8 +683,7 @@ int run_matrix_batch(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_
     set_error("run: bias is required when beta != 0");
     return HISPMV_ERR_ARG;
   }
-  const int64_t x_rows = m->dense ? m->ld : (int64_t)m->cols;  // rows of the interleaved x (dense: padded like A)
-  int st = ensure_batch_xi(c, (int64_t)kBatchMax * x_rows);
+  int st = ensure_batch_xi(c, m->dense ? panel_floats(m->ld) : (int64_t)kBatchMax * m->cols);
   if (st != HISPMV_OK) return st;
   if (m->dense) {
     DenseDev D;
@@ -701,7 +697,7 @@ int run_matrix_batch(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_
       if (g == 1) {
         st = run_matrix(c, m, d_x + v0 * m->cols, d_bias, d_y + v0 * rows, alpha, beta, relu, s, lane);
       } else {
-        st = launch_interleave(d_x + v0 * m->cols, g, m->cols, x_rows, c->d_xi[lane], s);
+        st = launch_interleave_panels(d_x + v0 * m->cols, g, m->cols, m->ld, c->d_xi[lane], s);
         if (st == HISPMV_OK) st = launch_gemm_lite(D, c->d_xi[lane], d_y + v0 * rows, g, epd, s);
       }
       if (st != HISPMV_OK) return st;
@@ -709,7 +705,9 @@ int run_matrix_batch(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_
     return HISPMV_OK;
   }
   const double mean = (double)m->nnz / (double)rows;
-  const int lanes = mean >= 64 ? 32 : mean >= 32 ? 16 : mean >= 16 ? 8 : mean >= 8 ? 4 : 2;
+  // lanes per row follow the mean row length; few long rows (one warp each would not fill the SMs) get a CTA each
+  int lanes = mean >= 64 ? 32 : mean >= 32 ? 16 : mean >= 16 ? 8 : mean >= 8 ? 4 : 2;
+  if (mean >= 512 && rows * 32 < (int64_t)c->sm_count * 1024) lanes = 256;
   CsrDev A;
   A.rows = (int32_t)rows;
   A.cols = m->cols;
@@ -798,6 +796,10 @@ void hispmv_destroy(hispmv_ctx* c) {
     cudaFree(c->d_y[l]);
   }
   cudaFree(c->d_bias);
+  cudaFree(c->d_xi[0]);
+  cudaFree(c->d_xi[1]);
+  cudaFree(c->d_xb);
+  cudaFree(c->d_yb);
   cudaEventDestroy(c->ev_bias);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->stream2);
@@ -1133,6 +1135,7 @@ int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const f
   if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, lanes[0]));
   HISPMV_CUDA(cudaEventRecord(c->ev_bias, lanes[0]));
   HISPMV_CUDA(cudaStreamWaitEvent(lanes[1], c->ev_bias, 0));
+  HISPMV_CUDA(cudaPeekAtLastError());
   if (num_vecs >= 2 && batch_eligible(m)) {
     // Several vectors: groups of up to eight share one pass over the matrix (batch.cu).  Groups alternate between the two
     // stream lanes, each with its own half of the staging, so the copies of one group overlap the pass of the other.

@@ -190,7 +190,9 @@ struct DenseDev {
   const float* a = nullptr;
 };
 int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm_count, cudaStream_t s);
-// batch.cu: y [nv][rows] for nv <= 8 vectors interleaved as xi [ld][K]
-int launch_gemm_lite(const DenseDev& A, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s);
+// batch.cu: y [nv][rows] for nv <= 8 vectors in the panel layout written by launch_interleave_panels
+int64_t panel_floats(int64_t ld);  // buffer size of that layout for eight vectors
+int launch_interleave_panels(const float* x, int nv, int64_t n, int64_t ld, float* xp, cudaStream_t s);
+int launch_gemm_lite(const DenseDev& A, const float* xp, float* y, int nv, Epilogue ep, cudaStream_t s);
 
 }  // namespace hispmv

@@ -702,18 +702,25 @@ def test_multicast_y_is_refused_where_y_is_read_back(eng):
     assert st != 0                                                         # null multicast address
 
 
-@pytest.mark.parametrize("shape", ["dnn", "short_rows", "with_empty_rows"])
+@pytest.mark.parametrize("shape", ["dnn", "short_rows", "with_empty_rows", "few_long_rows"])
 def test_batched_vectors_one_pass(eng, shape):
     """Several right-hand sides per pass (hispmv_run_dev_batch, and linear() with num_vecs >= 2): every vector within
     the north_star bar of the float64 oracle, for 1..11 vectors (groups of 8 / 4 / 2 and a single left over), with
     alpha/beta and the fused ReLU on the device call."""
     import torch
-    rng = np.random.default_rng({"dnn": 1, "short_rows": 2, "with_empty_rows": 3}[shape])
+    rng = np.random.default_rng({"dnn": 1, "short_rows": 2, "with_empty_rows": 3, "few_long_rows": 4}[shape])
     if shape == "dnn":
         rows, cols = 2048, 1536
         w = rng.standard_normal((rows, cols)).astype(np.float32) * (rng.random((rows, cols)) < 0.1)
         r, c = np.nonzero(w)
         v = w[r, c]
+    elif shape == "few_long_rows":                       # one CTA per row (spmm_csr_cta_kernel)
+        rows, cols = 300, 9000
+        lens = rng.integers(2500, 3500, rows)
+        lens[5] = 0
+        r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+        c = rng.integers(0, cols, r.size).astype(np.int32)
+        v = rng.standard_normal(r.size).astype(np.float32)
     elif shape == "short_rows":
         rows, cols = 30000, 5000
         r, c, v = _rand_coo(rng, rows, cols, 90000, dup=0.02)

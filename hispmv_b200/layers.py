@@ -208,6 +208,22 @@ class DeviceChain:
             if not whole:
                 self.comm.allgather_rows(("chain", id(self), k), y, self._x[k + 1])
 
+    def forward_batch(self, x: torch.Tensor) -> torch.Tensor:
+        """x: (batch, in_features) CUDA tensor -> (batch, out_features).  Every layer takes the whole batch in passes of
+        up to eight vectors over its matrix (Engine.run_dev_batch: col/val or the dense rows are read once per pass),
+        bias and ReLU fused, activations stay in HBM.  Single-GPU chains only (the sharded hand-over is per vector)."""
+        if self.comm is not None:
+            raise NotImplementedError("forward_batch is for unsharded chains")
+        if x.dim() != 2 or x.shape[1] != self.shapes[0][1]:
+            raise ValueError(f"expected (batch, {self.shapes[0][1]})")
+        stream = torch.cuda.current_stream().cuda_stream
+        act = x.contiguous().float()
+        for k, idx in enumerate(self.idx):
+            out = torch.empty((act.shape[0], self.shapes[k][0]), device=act.device, dtype=torch.float32)
+            self.engine.run_dev_batch(idx, act, self.bias[k], out, 1.0, 1.0, relu=self.relu[k], stream=stream)
+            act = out
+        return act
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """x: (in_features,) CUDA tensor.  Returns the (out_features,) result, replicated on every rank."""
         self._x[0].copy_(x.reshape(-1))

@@ -616,6 +616,24 @@ def test_device_chain_matches_cpu_model(eng, graph):
         assert np.allclose(out, ref, rtol=1e-3, atol=1e-4)
 
 
+def test_device_chain_batched_forward(eng):
+    """DeviceChain.forward_batch: a (batch, in) block through the three layers, eight vectors per pass over each matrix,
+    against the CPU model and against the vector-by-vector chain."""
+    import torch
+    from hispmv_b200.layers import DeviceChain
+    model = _mlp()
+    chain = DeviceChain(eng, [model.dense, model.sparse1, model.sparse2], relu=[True, True, True])
+    for batch in (1, 3, 8, 13):
+        xb = torch.randn((batch, 512))
+        with torch.no_grad():
+            ref = model(xb).numpy()
+        out = chain.forward_batch(xb.cuda()).cpu().numpy()
+        assert out.shape == ref.shape
+        assert np.abs(out - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+        one = np.stack([chain.forward(xb[i].cuda()).cpu().numpy() for i in range(batch)])
+        assert np.abs(out - one).max() <= 1e-4 * max(1.0, np.abs(one).max())
+
+
 def test_host_run_pipelines_row_ranges(eng):
     """hispmv_run on a matrix with > 2^20 rows cuts the rows into ranges at tile boundaries and overlaps bias upload,
     kernel and y download of different ranges: same result as the device-resident single launch, bit for bit."""

@@ -46,6 +46,19 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         out[name] = e0.elapsed_time(e1) / iters * 1e3
+    ch = DeviceChain(eng, layers, relu=[True, True, True])
+    for batch in (8, 64):
+        xb = torch.randn(batch, 4096, device="cuda")
+        for _ in range(5):
+            ch.forward_batch(xb)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100):
+            ch.forward_batch(xb)
+        e1.record()
+        torch.cuda.synchronize()
+        out[f"device chain, batch {batch} (us per vector)"] = e0.elapsed_time(e1) / 100 * 1e3 / batch
     # the plugin path: host numpy in, host numpy out, per layer (apps/fpga_layer_manager.py:58-67)
     import pyhispmv
     from hispmv_b200.layers import FpgaLayerManager

@@ -102,3 +102,38 @@ def test_errors_carry_the_reference_messages(tmp_path):
         p.write_text(text)
         with pytest.raises(HispmvError, match=msg):
             parse_mtx(str(p))
+
+
+def test_random_well_formed_files_match_the_oracle(tmp_path, monkeypatch):
+    """Property check: any well-formed coordinate file -- random type / symmetry, separators (spaces, tabs), number
+    formats (fixed, exponent, signed, integers), comment block, trailing blanks -- parses to the oracle's COO, for any
+    thread count."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    fmt = st.sampled_from(["{:.9g}", "{:e}", "{:+.6f}", "{:.3E}"])
+    sep = st.sampled_from([" ", "  ", "\t", " \t "])
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(kind=st.sampled_from(["real", "integer", "pattern"]), sym=st.sampled_from(["general", "symmetric", "skew-symmetric"]),
+           n=st.integers(1, 60), m=st.integers(0, 400), seed=st.integers(0, 2 ** 31), f=fmt, s1=sep, s2=sep,
+           threads=st.sampled_from(["1", "2", "7"]), comments=st.integers(0, 3))
+    def run(kind, sym, n, m, seed, f, s1, s2, threads, comments):
+        rng = np.random.default_rng(seed)
+        r = rng.integers(1, n + 1, m)
+        c = rng.integers(1, n + 1, m)
+        if sym != "general":
+            r, c = np.maximum(r, c), np.minimum(r, c)
+        lines = [f"%%MatrixMarket matrix coordinate {kind} {sym}"] + ["% note"] * comments + [f"{n} {n} {m}"]
+        for k in range(m):
+            if kind == "pattern":
+                lines.append(f"{r[k]}{s1}{c[k]}")
+            elif kind == "integer":
+                lines.append(f"{r[k]}{s1}{c[k]}{s2}{int(rng.integers(-9, 10))}")
+            else:
+                lines.append(f"{r[k]}{s1}{c[k]}{s2}" + f.format(float(rng.standard_normal()) * (rng.random() > 0.1)))
+        p = tmp_path / "h.mtx"
+        p.write_text("\n".join(lines) + "\n" + "\n" * int(rng.integers(0, 3)))
+        monkeypatch.setenv("HISPMV_MTX_THREADS", threads)
+        assert _same(parse_mtx(str(p)), ol.load_mtx(str(p)))
+
+    run()

@@ -6,8 +6,10 @@
 //   HiSpmvHandle::prepareSparseMtxForFPGA   common/src/spmv-helper.cpp:648-715   (shared-row list)
 //   HiSpmvHandle::loadMtx                   common/src/spmv-helper.cpp:34-136    (private)
 //   HiSpmvHandle::getPreparedMtx            the packed 64-bit PEG streams (computeTileSize / prepareTile :429-638)
+//   HiSpmvHandle::printErrorStats           common/src/spmv-helper.cpp:835-895   (the host program's error report)
 // The private members are reached by re-declaring access for this translation unit only; the reference
 // sources themselves are compiled untouched.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <iostream>
@@ -163,5 +165,31 @@ void ref_common_pack_fetch(uint64_t* stream, int* shared_rows) {
   if (shared_rows && !g_shared.empty()) std::memcpy(shared_rows, g_shared.data(), sizeof(int) * g_shared.size());
   g_stream = std::vector<uint64_t>();
   g_shared = std::vector<int>();
+}
+
+// The text HiSpmvHandle::printErrorStats prints for (cpu_ref, fpga_out); returns its length (truncated to cap - 1).
+int ref_common_error_stats(int n, const float* cpu_ref, const float* out, char* buf, int cap) {
+  std::ostringstream sink;
+  std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+  std::cout.unsetf(std::ios::floatfield);  // the reference leaves std::scientific set after a histogram: start clean
+  std::cout.precision(6);
+  HiSpmvHandle* h = nullptr;
+  {
+    std::ostringstream banner;  // the constructor prints the configuration
+    std::streambuf* keep = std::cout.rdbuf(banner.rdbuf());
+    h = make_handle(24, 1, 1, 2, 5, 1, 0, 1);
+    std::cout.rdbuf(keep);
+  }
+  std::vector<float> a(cpu_ref, cpu_ref + n), b(out, out + n);
+  h->printErrorStats(a, b);
+  delete h;
+  std::cout.rdbuf(old);
+  const std::string text = sink.str();
+  const int len = (int)std::min<size_t>(text.size(), (size_t)std::max(cap - 1, 0));
+  if (cap > 0) {
+    std::memcpy(buf, text.data(), (size_t)len);
+    buf[len] = 0;
+  }
+  return len;
 }
 }

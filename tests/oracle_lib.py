@@ -140,6 +140,8 @@ def ref_common() -> C.CDLL:
     lib.ref_common_shared_rows.restype = i
     lib.ref_common_load_mtx.argtypes = [C.c_char_p, C.POINTER(i), C.POINTER(i), C.POINTER(i64)]
     lib.ref_common_load_mtx_fetch.argtypes = [_i32p, _i32p, _f32p]
+    lib.ref_common_error_stats.argtypes = [i, _f32p, _f32p, C.c_char_p, i]
+    lib.ref_common_error_stats.restype = i
     lib.ref_common_pack.argtypes = [i, i, i, i, i, i, i64, _i32p, _i32p, _f32p, _i64p]
     lib.ref_common_pack.restype = i
     lib.ref_common_pack_fetch.argtypes = [np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), C.c_void_p]

@@ -32,23 +32,30 @@ def generate_vector(n: int) -> np.ndarray:
 
 
 def print_error_stats(cpu_ref: np.ndarray, out: np.ndarray) -> None:
-    a, b = np.abs(out.astype(np.float64)), np.abs(cpu_ref.astype(np.float64))
-    ref = np.maximum(b, np.finfo(np.float64).tiny)
-    rel = np.abs(a - ref) / ref
-    rel = rel[rel != 0]
+    """HiSpmvHandle::printErrorStats (common/src/spmv-helper.cpp:835-895), line for line: relative error of the
+    magnitudes against the CPU result (no floor under the reference value: its `epsilon` is numeric_limits::lowest(),
+    i.e. negative), exact matches dropped, at most ten mismatches listed, otherwise ten equal-width bins between the
+    smallest and the largest error with the last bin closed."""
+    a, b = np.abs(out.astype(np.float32)).astype(np.float64), np.abs(cpu_ref.astype(np.float32)).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(a - b) / b
+    rel = rel[rel != 0]                                   # NaN != 0 holds, as in the C++ test
     if rel.size == 0:
         print("No mismatch found")
         return
     if rel.size <= 10:
         print("Found atmost 10 mismatches, Relative Errors:")
         for e in rel:
-            print(f"\t{e}")
+            print(f"\t{e:g}")
         return
     lo, hi = rel.min(), rel.max()
-    counts, edges = np.histogram(rel, bins=10, range=(lo, hi))
+    width = (hi - lo) / 10
+    idx = np.minimum(((rel - lo) / width).astype(np.int64), 9)
+    counts = np.bincount(idx, minlength=10)
     print("Relative Error Range:\tCount")
     for k in range(10):
-        print(f"[{edges[k]:.3e}, {edges[k + 1]:.3e}):\t{counts[k]}")
+        start = lo + k * width
+        print(f"[{start:.3e}, {start + width:.3e}):\t{counts[k]}")
 
 
 def main() -> int:

@@ -135,3 +135,44 @@ def test_replaced_model_makes_the_same_calls_and_results():
         assert torch.equal(ya, yb)
         assert torch.allclose(yb, y0, rtol=1e-4, atol=1e-4)
     _same_calls(a.calls, b.calls)
+
+
+def _reference_model_module():
+    """apps/model.py with sparse_dot_mkl (absent here) replaced by scipy's CSR product -- same arithmetic, MKL aside."""
+    stub = types.ModuleType("sparse_dot_mkl")
+    stub.dot_product_mkl = lambda a, b: np.asarray(a @ b, dtype=np.float32)
+    saved = sys.modules.get("sparse_dot_mkl")
+    sys.modules["sparse_dot_mkl"] = stub
+    try:
+        spec = importlib.util.spec_from_file_location("ref_apps_model", "/root/reference/apps/model.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        if saved is None:
+            sys.modules.pop("sparse_dot_mkl", None)
+        else:
+            sys.modules["sparse_dot_mkl"] = saved
+    return mod
+
+
+def test_model_classes_draw_the_same_weights_and_compute_the_same_outputs():
+    """layers.SparseLinear / ThreeLayerFCModel against apps/model.py:10-80: under the same torch seed the layers hold
+    the same weights (same order of random draws, same mask rule) and the forward pass gives the same activations."""
+    ref = _reference_model_module()
+    sizes = (40, 72, 56, 20, 0.1, 0.25)
+    with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(11)
+        a = ref.ThreeLayerFCModel(ref.ThreeLayerFCModelConfig(*sizes), rp_time=1).eval()
+    torch.manual_seed(11)
+    b = L.ThreeLayerFCModel(L.ThreeLayerFCModelConfig(*sizes)).eval()
+    assert torch.equal(a.dense.weight, b.dense.weight) and torch.equal(a.dense.bias, b.dense.bias)
+    for name in ("sparse1", "sparse2"):
+        wa, wb = getattr(a, name).weight.coalesce(), getattr(b, name).weight.coalesce()
+        assert wa.shape == wb.shape and torch.equal(wa.indices(), wb.indices()) and torch.equal(wa.values(), wb.values())
+        assert torch.equal(getattr(a, name).bias, getattr(b, name).bias)
+    x = torch.randn(3, 40)
+    with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+        ya = a(x)
+        yb = b(x)
+    assert ya.shape == yb.shape == (3, 20)
+    assert torch.allclose(ya, yb, rtol=1e-5, atol=1e-5)

@@ -64,6 +64,30 @@ class ThreeLayerFCModel(nn.Module):
         return self.activation(self.sparse2(x))
 
 
+def compare_model_outputs(ref_output: torch.Tensor, cmp_output: torch.Tensor) -> None:
+    """The report model_test prints after the two forward passes (apps/model.py:82-142): absolute and relative error
+    (|ref - cmp| / (ref + 1e-8), signed denominator as there) histograms over ten shared bins from 0 to the larger of the
+    two maxima, then the maxima with the values at their positions."""
+    ref, cmp_ = ref_output.flatten(), cmp_output.flatten()
+    abs_err = torch.abs(ref - cmp_)
+    rel_err = torch.abs((ref - cmp_) / (ref + 1e-8))
+    a, r = abs_err.cpu().numpy(), rel_err.cpu().numpy()
+    bins = np.linspace(0, max(np.max(a), np.max(r)), 11)
+    for title, err in (("Absolute", a), ("Relative", r)):
+        hist, edges = np.histogram(err, bins=bins)
+        print(f"\n{title} Error Histogram:")
+        for i in range(len(hist)):
+            print(f"Range: ({edges[i]:.4f}, {edges[i + 1]:.4f}), Count: {hist[i]}")
+    ia, ir = torch.argmax(abs_err), torch.argmax(rel_err)
+    print("\n")
+    print(f"Max Absolute Error: {torch.max(abs_err).item()}")
+    print(f"Max Relative Error: {torch.max(rel_err).item()}")
+    print(f"Values at Max Absolute Error (index {ia.item()}):")
+    print(f"Ref Output: {ref[ia].item()}, Actual Output: {cmp_[ia].item()}")
+    print(f"Values at Max Relative Error (index {ir.item()}):")
+    print(f"Ref Output: {ref[ir].item()}, Actual Output: {cmp_[ir].item()}")
+
+
 def layer_arrays(layer) -> Tuple[str, tuple, np.ndarray]:
     """What process_weights extracts from a layer (apps/fpga_layer_manager.py:15-52):
     ("sparse", (rows_i32, cols_i32, vals_f32, out, in), bias) or ("dense", (flat_f32, out, in), bias).

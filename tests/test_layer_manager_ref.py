@@ -176,3 +176,18 @@ def test_model_classes_draw_the_same_weights_and_compute_the_same_outputs():
         yb = b(x)
     assert ya.shape == yb.shape == (3, 20)
     assert torch.allclose(ya, yb, rtol=1e-5, atol=1e-5)
+
+
+def test_compare_model_outputs_prints_the_same_report():
+    ref = _reference_model_module()
+    torch.manual_seed(5)
+    a = torch.randn(4, 300) * 50
+    b = a * (1 + 1e-4 * torch.randn(4, 300))
+    b[0, 7] += 0.5
+    texts = []
+    for fn in (ref.compare_model_outputs, L.compare_model_outputs):
+        s = io.StringIO()
+        with contextlib.redirect_stdout(s):
+            fn(a, b)
+        texts.append(s.getvalue())
+    assert texts[0] == texts[1] and "Max Relative Error" in texts[1]

@@ -8,14 +8,14 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -Ihispm
 PKG       := hispmv_b200
 CSRC      := $(PKG)/csrc
 OBJDIR    := build/obj
-OBJS      := $(OBJDIR)/capi.o $(OBJDIR)/spmv.o $(OBJDIR)/adaptive.o $(OBJDIR)/gemv.o $(OBJDIR)/partition.o $(OBJDIR)/synth.o $(OBJDIR)/exchange.o $(OBJDIR)/batch.o
+OBJS      := $(OBJDIR)/capi.o $(OBJDIR)/spmv.o $(OBJDIR)/adaptive.o $(OBJDIR)/gemv.o $(OBJDIR)/partition.o $(OBJDIR)/synth.o $(OBJDIR)/exchange.o $(OBJDIR)/batch.o $(OBJDIR)/blocked.o
 LIB       := $(PKG)/libhispmv_cuda.so
 PYEXT     := $(PKG)/pyhispmv$(shell $(PY) -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
 PYINC     := $(shell $(PY) -c "import sysconfig,pybind11;print('-I'+sysconfig.get_paths()['include'],'-I'+pybind11.get_include())")
 
 all: $(LIB) $(PYEXT) oracle
 
-$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh include/hispmv.h
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh $(CSRC)/tile_device.cuh include/hispmv.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 

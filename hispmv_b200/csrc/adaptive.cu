@@ -38,6 +38,7 @@
 
 #include "device_utils.cuh"
 #include "internal.h"
+#include "tile_device.cuh"
 
 namespace hispmv {
 
@@ -164,69 +165,12 @@ __device__ __forceinline__ void rows_from_products(const CsrDev& A, int r0, int 
   }
 }
 
-// ---- the end of a LONG tile: warp 0 of the group holds the chunk's total in every lane ---------------------------
-// Split rows meet without a fence on the arrival path: carry[] slots hold a sentinel (a NaN payload no arithmetic
-// produces) until their chunk writes its partial; the chunk that arrives last at the row's counter reads the slots in
-// chunk order past L1, waiting out any slot whose write is still in flight, adds them in that order and re-arms slots
-// and counter for the next launch.  (The first version published carry[] with __threadfence(): on sm_100 that is
-// MEMBAR.SC + CCTL.IVALL -- a ~2 k-cycle stall and an L1 flush per chunk.)
-constexpr unsigned int kCarryEmpty = kCarryEmptyBits;
-__device__ __forceinline__ void finish_chunk(const AdaptivePlan& P, const TileDesc& d, int64_t t, float total, int lane,
-                                             float* __restrict__ y, const Epilogue& ep) {
-  if (d.nchunks == 1) {
-    if (lane == 0) store_y(y, d.r0, finish(total, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu), ep.y_mc);
-    return;
-  }
-  const int64_t first = t - d.chunk;  // tile id of this row's chunk 0
-  int last = 0;
-  if (lane == 0) {
-    unsigned int bits = __float_as_uint(total);
-    if (bits == kCarryEmpty) bits = 0x7fffffffu;  // a NaN is a NaN
-    __stcg(reinterpret_cast<unsigned int*>(P.carry) + t, bits);
-    const unsigned int prev = atomicAdd(&P.counter[first], 1u);
-    last = (prev == (unsigned int)(d.nchunks - 1));
-  }
-  last = __shfl_sync(kFullMask, last, 0);
-  if (!last) return;
-  unsigned int* slots = reinterpret_cast<unsigned int*>(P.carry) + first;
-  float s = 0.0f;
-  for (int k = lane; k < d.nchunks; k += 32) {
-    unsigned int bits = __ldcg(slots + k);
-    while (bits == kCarryEmpty) {
-      __nanosleep(40);
-      bits = __ldcg(slots + k);
-    }
-    s += __uint_as_float(bits);
-    __stcg(slots + k, kCarryEmpty);
-  }
-  s = warp_sum(s);
-  if (lane == 0) {
-    store_y(y, d.r0, finish(s, ep.alpha, ep.beta, ep.bias, d.r0, ep.relu), ep.y_mc);
-    P.counter[first] = 0;  // ready for the next run / graph replay
-  }
-}
-
 // Wait for the tile's bulk copies: one thread polls the mbarrier (try_wait suspends it in hardware), the rest of the
 // CTA parks on the hardware barrier.  256 threads polling the same mbarrier flood the MIO queue (measured: the
 // kernel ran 1.6x slower with mio_throttle as its top stall).
 __device__ __forceinline__ void tile_staged(uint64_t* bar, int cnt) {
   if (threadIdx.x == 0 && cnt > 0) mbar_wait(bar, 0);
   __syncthreads();
-}
-
-__device__ __forceinline__ TileDesc load_desc(const TileDesc* p) {
-  const int4 a = __ldg(reinterpret_cast<const int4*>(p));
-  const int4 b = __ldg(reinterpret_cast<const int4*>(p) + 1);
-  TileDesc d;
-  d.r0 = a.x;
-  d.r1 = a.y;
-  d.n0 = a.z;
-  d.n1 = a.w;
-  d.chunk = b.x;
-  d.nchunks = b.y;
-  d.tile = b.z;
-  d.pad = b.w;
-  return d;
 }
 
 // L2 prefetch of the col/val range of tile `ta` (two bulk-prefetch instructions from one thread).  A matrix of a few
@@ -268,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS)
     if (warp != 0) return;
     float total = lane < WARPS ? s_red[lane] : 0.0f;
     total = warp_sum(total);
-    finish_chunk(P, d, t, total, lane, y, ep);
+    finish_chunk(P.carry, P.counter, d, t, total, lane, y, ep);
     return;
   }
   const int n0 = d.n0;
@@ -310,7 +254,7 @@ __global__ void __launch_bounds__(kGroup, 8)
     float acc = 0.0f;
     stream_products<32>(A, gx, d.n0, d.n1, lane, ps, [&](int, float p) { acc += p; });
     acc = warp_sum(acc);
-    finish_chunk(P, d, t, acc, lane, y, ep);
+    finish_chunk(P.carry, P.counter, d, t, acc, lane, y, ep);
     return;
   }
   const int n0 = d.n0;
@@ -423,7 +367,7 @@ __global__ void __launch_bounds__(kGroup* kPsGroups, MINBLOCKS)
       if (gw == 0) {
         float total = lane < kGroupWarps ? gs->red[lane] : 0.0f;
         total = warp_sum(total);
-        finish_chunk(P, d, t, total, lane, y, ep);
+        finish_chunk(P.carry, P.counter, d, t, total, lane, y, ep);
       }
       continue;
     }
@@ -480,7 +424,7 @@ __global__ void __launch_bounds__(THREADS)
     if (warp != 0) return;
     float total = lane < THREADS / 32 ? s_red[lane] : 0.0f;
     total = warp_sum(total);
-    finish_chunk(P, d, t, total, lane, y, ep);
+    finish_chunk(P.carry, P.counter, d, t, total, lane, y, ep);
     return;
   }
   const int r0 = d.r0, trows = d.r1 - d.r0;
@@ -716,7 +660,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1)
       if (tw == 0) {
         float total = lane < kPipeTeamWarps ? st.partial[lane] : 0.0f;
         total = warp_sum(total);
-        finish_chunk(P, d, d.tile, total, lane, y, ep);
+        finish_chunk(P.carry, P.counter, d, d.tile, total, lane, y, ep);
       }
     } else {
 #pragma unroll

@@ -1,0 +1,656 @@
+// The blocked (two-pass, column-slab x row-panel) SpMV strategy for sm_100a: x gathers are served from shared memory
+// instead of L2.  See PbPlan in internal.h for the layout; DESIGN.md section 5 for the measurements behind it.
+//
+// What it replaces in the reference (semantics only -- the reference's stream is an FPGA format):
+//   tileAndPad's column tiles (a tile covers (num_fp32s_b/2)*1024 columns so that its piece of x fits the
+//   on-chip B buffers)                                                     common/src/spmv-helper.cpp:139-227
+//   ComputeAB reading x from the on-chip buffer, one product per cycle     automation_tool/assets/base_functions.cpp:158-254
+//   AccumBuffer / Compute_C per row tile                                   base_functions.cpp:439-540
+// The reference streams every column tile's nonzeros past an x slice held in BRAM/URAM and accumulates y_Ax per row
+// tile on chip; here the slab's slice of x lives in the SM's shared memory (pass 1, pb_expand_kernel) and the per-row
+// accumulation happens one row panel at a time in shared memory (pass 2, pb_reduce_kernel), with the products crossing
+// HBM once in between.
+//
+// Integer artefacts (slab starts, the blocked order, 16-bit local columns, 16-bit CSR positions, the (panel, slab)
+// segment table) are bit-exact against oracle/oracle.c: oracle_pb_plan.
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "tile_device.cuh"
+
+namespace hispmv {
+
+namespace {
+
+struct DevBuf {  // RAII for scratch allocations inside one call
+  void* p = nullptr;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  int alloc(size_t bytes) {
+    if (p) cudaFree(p);
+    p = nullptr;
+    if (bytes == 0) bytes = 16;
+    return check_cuda(cudaMalloc(&p, bytes), "cudaMalloc(scratch)", __FILE__, __LINE__);
+  }
+  template <typename T>
+  T* as() {
+    return static_cast<T*>(p);
+  }
+};
+
+inline int blocks_for(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
+
+// ================================================================================================================
+// plan
+// ================================================================================================================
+__global__ void pb_key_kernel(const int32_t* __restrict__ col, int64_t nnz, int32_t W, uint16_t* __restrict__ key,
+                              uint32_t* __restrict__ idx) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) {
+    key[j] = (uint16_t)(col[j] / W);
+    idx[j] = (uint32_t)j;
+  }
+}
+
+__global__ void pb_iota_kernel(uint32_t* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+// ustart[s] = number of sorted entries whose slab is < s, for s = 0 .. S
+__global__ void pb_slab_bounds_kernel(const uint16_t* __restrict__ key, int64_t nnz, int32_t S,
+                                      int32_t* __restrict__ ustart) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s > S) return;
+  int64_t lo = 0, hi = nnz;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int32_t)key[mid] < s) lo = mid + 1; else hi = mid;
+  }
+  ustart[s] = (int32_t)lo;
+}
+
+// the panel that holds CSR position j: the first t with desc[t].n1 > j (panels cover [0, nnz) in order)
+__device__ __forceinline__ int32_t pb_panel_of(const TileDesc* __restrict__ desc, int64_t np, int32_t j) {
+  int64_t lo = 0, hi = np - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(&desc[mid].n1) <= j) lo = mid + 1; else hi = mid;
+  }
+  return (int32_t)lo;
+}
+
+__global__ void pb_scatter_kernel(const uint16_t* __restrict__ key, const uint32_t* __restrict__ idx, int64_t nnz,
+                                  const int32_t* __restrict__ col, const float* __restrict__ val,
+                                  const TileDesc* __restrict__ desc, int64_t np, int32_t W,
+                                  const int32_t* __restrict__ ustart, const int32_t* __restrict__ pstart,
+                                  float* __restrict__ o_val, uint16_t* __restrict__ o_lcol,
+                                  uint16_t* __restrict__ o_perm, int32_t* __restrict__ pan) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int32_t s = key[k];
+  const int32_t j = (int32_t)idx[k];
+  const int64_t dst = (int64_t)pstart[s] + (k - ustart[s]);
+  const int32_t p = pb_panel_of(desc, np, j);
+  o_val[dst] = val[j];
+  o_lcol[dst] = (uint16_t)(col[j] - s * W);
+  o_perm[dst] = (uint16_t)(j - __ldg(&desc[p].n0));
+  pan[k] = p;
+}
+
+__global__ void pb_head_kernel(const uint16_t* __restrict__ key, const int32_t* __restrict__ pan, int64_t nnz,
+                               int32_t* __restrict__ head) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  head[k] = (k == 0 || key[k] != key[k - 1] || pan[k] != pan[k - 1]) ? 1 : 0;
+}
+
+__global__ void pb_seg_emit_kernel(const uint16_t* __restrict__ key, const int32_t* __restrict__ pan,
+                                   const int32_t* __restrict__ head, const int32_t* __restrict__ segidx, int64_t nnz,
+                                   const int32_t* __restrict__ ustart, const int32_t* __restrict__ pstart, int32_t S,
+                                   int32_t* __restrict__ seg_dst, uint64_t* __restrict__ seg_key,
+                                   int32_t* __restrict__ seg_k) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz || !head[k]) return;
+  const int32_t i = segidx[k];
+  const int32_t s = key[k];
+  seg_dst[i] = (int32_t)((int64_t)pstart[s] + (k - ustart[s]));
+  seg_key[i] = (uint64_t)pan[k] * (uint64_t)S + (uint64_t)s;
+  seg_k[i] = (int32_t)k;
+}
+
+// length of segment order[q] (segments are contiguous in k: the next head in slab-major order ends it)
+__global__ void pb_seg_len_kernel(const uint32_t* __restrict__ order, const int32_t* __restrict__ seg_k, int64_t nseg,
+                                  int64_t nnz, int32_t* __restrict__ len_sorted) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nseg) return;
+  const int64_t i = order[q];
+  const int64_t end = i + 1 < nseg ? seg_k[i + 1] : nnz;
+  len_sorted[q] = (int32_t)(end - seg_k[i]);
+}
+
+__global__ void pb_seg_final_kernel(const uint64_t* __restrict__ seg_key_sorted, const uint32_t* __restrict__ order,
+                                    const int32_t* __restrict__ seg_dst, const int32_t* __restrict__ G,
+                                    const TileDesc* __restrict__ desc, int32_t S, int64_t nseg,
+                                    PbSeg* __restrict__ out) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nseg) return;
+  const int64_t p = (int64_t)(seg_key_sorted[q] / (uint64_t)S);
+  PbSeg sg;
+  sg.start = seg_dst[order[q]];
+  sg.off = G[q] - __ldg(&desc[p].n0);  // entries of earlier panels add up to the panel's first CSR position
+  out[q] = sg;
+}
+
+// panel_seg[p] = number of segments whose panel is < p, p = 0 .. np
+__global__ void pb_panel_seg_kernel(const uint64_t* __restrict__ seg_key_sorted, int64_t nseg, int64_t np, int32_t S,
+                                    int32_t* __restrict__ panel_seg) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > np) return;
+  const uint64_t target = (uint64_t)p * (uint64_t)S;
+  int64_t lo = 0, hi = nseg;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (seg_key_sorted[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  panel_seg[p] = (int32_t)lo;
+}
+
+__global__ void pb_max_segs_kernel(const int32_t* __restrict__ panel_seg, int64_t np, int* __restrict__ out) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = 0;
+  if (p < np) v = panel_seg[p + 1] - panel_seg[p];
+  v = __reduce_max_sync(kFullMask, v);
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+}  // namespace
+
+void pb_free(PbArrays* a) {
+  cudaFree(a->d_slab_ptr);
+  cudaFree(a->d_val);
+  cudaFree(a->d_lcol);
+  cudaFree(a->d_perm);
+  cudaFree(a->d_panel_seg);
+  cudaFree(a->d_seg);
+  cudaFree(a->d_work);
+  cudaFree(a->d_prod[0]);
+  cudaFree(a->d_prod[1]);
+  delete[] a->h_slab_ptr;
+  *a = PbArrays();
+}
+
+int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
+                    int64_t nnz, const TileDesc* d_desc, int64_t num_panels, int32_t slab_cols, PbArrays* out,
+                    cudaStream_t stream) {
+  (void)d_row_ptr;
+  (void)rows;
+  pb_free(out);
+  if (slab_cols < 4 || slab_cols > kPbMaxSlabCols || (slab_cols & 3) || cols <= 0 || nnz <= 0 || num_panels <= 0) {
+    set_error("blocked plan: bad slab width or empty matrix");
+    return HISPMV_ERR_ARG;
+  }
+  const int32_t W = slab_cols;
+  const int64_t S64 = ((int64_t)cols + W - 1) / W;
+  if (S64 > 65535) {
+    set_error("blocked plan: more than 65535 column slabs");
+    return HISPMV_ERR_ARG;
+  }
+  const int32_t S = (int32_t)S64;
+  const int B = 256;
+  int st;
+  int sbits = 1;
+  while ((1 << sbits) < S) ++sbits;
+
+  // ---- stable sort of the CSR positions by slab: slab-major, CSR order inside a slab -----------------------------
+  DevBuf key_a, key_b, idx_a, idx_b, tmp, ustart, pstart;
+  if ((st = key_a.alloc((size_t)nnz * 2)) || (st = key_b.alloc((size_t)nnz * 2)) || (st = idx_a.alloc((size_t)nnz * 4)) ||
+      (st = idx_b.alloc((size_t)nnz * 4)) || (st = ustart.alloc(((size_t)S + 1) * 4)) ||
+      (st = pstart.alloc(((size_t)S + 1) * 4)))
+    return st;
+  cub::DoubleBuffer<uint16_t> keys(key_a.as<uint16_t>(), key_b.as<uint16_t>());
+  cub::DoubleBuffer<uint32_t> idx(idx_a.as<uint32_t>(), idx_b.as<uint32_t>());
+  pb_key_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(d_col, nnz, W, keys.Current(), idx.Current());
+  HISPMV_CUDA(cudaGetLastError());
+  size_t tb = 0;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, idx, nnz, 0, sbits, stream));
+  if ((st = tmp.alloc(tb))) return st;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys, idx, nnz, 0, sbits, stream));
+  pb_slab_bounds_kernel<<<blocks_for((int64_t)S + 1, 128), 128, 0, stream>>>(keys.Current(), nnz, S,
+                                                                            ustart.as<int32_t>());
+  HISPMV_CUDA(cudaGetLastError());
+  std::vector<int32_t> h_ustart((size_t)S + 1);
+  HISPMV_CUDA(cudaMemcpyAsync(h_ustart.data(), ustart.p, ((size_t)S + 1) * 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  // every slab starts at a multiple of kPbAlign in the blocked arrays (128-bit loads never straddle two slabs)
+  out->h_slab_ptr = new int32_t[(size_t)S + 1];
+  int64_t pos = 0;
+  for (int32_t s = 0; s < S; ++s) {
+    out->h_slab_ptr[s] = (int32_t)pos;
+    pos += (int64_t)h_ustart[(size_t)s + 1] - h_ustart[(size_t)s];
+    pos = (pos + kPbAlign - 1) / kPbAlign * kPbAlign;
+    if (pos >= (int64_t)INT32_MAX - kPbAlign) {
+      set_error("blocked plan: more than 2^31 entries");
+      return HISPMV_ERR_ARG;
+    }
+  }
+  out->h_slab_ptr[S] = (int32_t)pos;
+  const int64_t padded = pos;
+  HISPMV_CUDA(cudaMemcpyAsync(pstart.p, out->h_slab_ptr, ((size_t)S + 1) * 4, cudaMemcpyHostToDevice, stream));
+
+  // ---- the blocked copy ------------------------------------------------------------------------------------------
+  const size_t slack = 64;  // vector loads of the last group may look past the end
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_val, ((size_t)padded + slack) * 4));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_lcol, ((size_t)padded + slack) * 2));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_perm, ((size_t)padded + slack) * 2));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_slab_ptr, ((size_t)S + 1) * 4));
+  HISPMV_CUDA(cudaMemsetAsync(out->d_val, 0, ((size_t)padded + slack) * 4, stream));
+  HISPMV_CUDA(cudaMemsetAsync(out->d_lcol, 0, ((size_t)padded + slack) * 2, stream));
+  HISPMV_CUDA(cudaMemsetAsync(out->d_perm, 0, ((size_t)padded + slack) * 2, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(out->d_slab_ptr, pstart.p, ((size_t)S + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+  DevBuf pan, head, segidx;
+  if ((st = pan.alloc((size_t)nnz * 4))) return st;
+  pb_scatter_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), idx.Current(), nnz, d_col, d_val, d_desc,
+                                                          num_panels, W, ustart.as<int32_t>(), pstart.as<int32_t>(),
+                                                          out->d_val, out->d_lcol, out->d_perm, pan.as<int32_t>());
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  idx_a.alloc(0);  // the CSR positions are no longer needed
+  idx_b.alloc(0);
+
+  // ---- (panel, slab) segments: heads in slab-major order, then ordered by (panel, slab) ---------------------------
+  if ((st = head.alloc((size_t)nnz * 4)) || (st = segidx.alloc((size_t)nnz * 4))) return st;
+  pb_head_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), pan.as<int32_t>(), nnz, head.as<int32_t>());
+  size_t tb2 = 0;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, head.as<int32_t>(), segidx.as<int32_t>(), nnz, stream));
+  if (tb2 > tb) {
+    if ((st = tmp.alloc(tb2))) return st;
+    tb = tb2;
+  }
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, head.as<int32_t>(), segidx.as<int32_t>(), nnz, stream));
+  int32_t h_last[2] = {0, 0};
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last[0], head.as<int32_t>() + (nnz - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last[1], segidx.as<int32_t>() + (nnz - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  const int64_t nseg = (int64_t)h_last[0] + h_last[1];
+  DevBuf seg_dst, seg_k, skey_a, skey_b, ord_a, ord_b, len_sorted, G;
+  if ((st = seg_dst.alloc((size_t)nseg * 4)) || (st = seg_k.alloc((size_t)nseg * 4)) ||
+      (st = skey_a.alloc((size_t)nseg * 8)) || (st = skey_b.alloc((size_t)nseg * 8)) ||
+      (st = ord_a.alloc((size_t)nseg * 4)) || (st = ord_b.alloc((size_t)nseg * 4)) ||
+      (st = len_sorted.alloc((size_t)nseg * 4)) || (st = G.alloc((size_t)nseg * 4)))
+    return st;
+  pb_seg_emit_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), pan.as<int32_t>(), head.as<int32_t>(),
+                                                           segidx.as<int32_t>(), nnz, ustart.as<int32_t>(),
+                                                           pstart.as<int32_t>(), S, seg_dst.as<int32_t>(),
+                                                           skey_a.as<uint64_t>(), seg_k.as<int32_t>());
+  HISPMV_CUDA(cudaGetLastError());
+  cub::DoubleBuffer<uint64_t> skeys(skey_a.as<uint64_t>(), skey_b.as<uint64_t>());
+  cub::DoubleBuffer<uint32_t> ords(ord_a.as<uint32_t>(), ord_b.as<uint32_t>());
+  pb_iota_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(ords.Current(), nseg);
+  HISPMV_CUDA(cudaGetLastError());
+  int kbits = 1;
+  {
+    const uint64_t top = (uint64_t)num_panels * (uint64_t)S;
+    while (kbits < 64 && ((uint64_t)1 << kbits) < top) ++kbits;
+  }
+  size_t tb4 = 0;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb4, skeys, ords, nseg, 0, kbits, stream));
+  if (tb4 > tb) {
+    if ((st = tmp.alloc(tb4))) return st;
+    tb = tb4;
+  }
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb4, skeys, ords, nseg, 0, kbits, stream));
+  pb_seg_len_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(ords.Current(), seg_k.as<int32_t>(), nseg, nnz,
+                                                           len_sorted.as<int32_t>());
+  size_t tb5 = 0;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb5, len_sorted.as<int32_t>(), G.as<int32_t>(), nseg, stream));
+  if (tb5 > tb) {
+    if ((st = tmp.alloc(tb5))) return st;
+    tb = tb5;
+  }
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb5, len_sorted.as<int32_t>(), G.as<int32_t>(), nseg, stream));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_seg, ((size_t)nseg + 1) * sizeof(PbSeg)));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_panel_seg, ((size_t)num_panels + 1) * 4));
+  pb_seg_final_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(skeys.Current(), ords.Current(), seg_dst.as<int32_t>(),
+                                                             G.as<int32_t>(), d_desc, S, nseg, out->d_seg);
+  pb_panel_seg_kernel<<<blocks_for(num_panels + 1, B), B, 0, stream>>>(skeys.Current(), nseg, num_panels, S,
+                                                                      out->d_panel_seg);
+  DevBuf mx;
+  if ((st = mx.alloc(sizeof(int)))) return st;
+  HISPMV_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
+  pb_max_segs_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(out->d_panel_seg, num_panels, mx.as<int>());
+  HISPMV_CUDA(cudaGetLastError());
+  int h_mx = 0;
+  HISPMV_CUDA(cudaMemcpyAsync(&h_mx, mx.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  out->slab_cols = W;
+  out->num_slabs = S;
+  out->padded_nnz = padded;
+  out->num_seg = nseg;
+  out->max_panel_segs = h_mx;
+  return HISPMV_OK;
+}
+
+// Pass-1 work ranges: n_cta contiguous pieces of the blocked order, balanced by entries + slab_cost per slab a CTA
+// has to stage (a CTA that walks many thin slabs of the column tail spends its time loading x, not streaming).
+int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream) {
+  cudaFree(a->d_work);
+  a->d_work = nullptr;
+  a->num_work = 0;
+  if (n_cta < 1) n_cta = 1;
+  const int32_t S = a->num_slabs;
+  const int32_t* sp = a->h_slab_ptr;
+  int64_t slabs_used = 0;
+  for (int32_t s = 0; s < S; ++s) slabs_used += sp[s + 1] > sp[s];
+  int64_t remaining = a->padded_nnz + slab_cost * slabs_used;
+  std::vector<int2> work((size_t)n_cta);
+  int64_t k = 0;
+  int32_t s = 0;
+  for (int b = 0; b < n_cta; ++b) {
+    const int64_t k0 = k;
+    int64_t budget = (remaining + (n_cta - b) - 1) / (n_cta - b);
+    int64_t spent = 0;
+    bool fresh = true;  // the CTA has to stage the slab it starts in, even when the previous CTA already paid for it
+    while (k < a->padded_nnz && (budget > 0 || b == n_cta - 1)) {
+      while (s < S && sp[s + 1] <= k) {
+        ++s;
+        fresh = true;
+      }
+      if (s >= S) break;
+      if (fresh) {
+        if (k == sp[s]) {  // first CTA on this slab: the cost is part of `remaining`
+          budget -= slab_cost;
+          spent += slab_cost;
+        }
+        fresh = false;
+        if (budget <= 0 && k > k0 && b != n_cta - 1) break;
+      }
+      int64_t take = (int64_t)sp[s + 1] - k;
+      if (b != n_cta - 1) take = std::min<int64_t>(take, std::max<int64_t>(kPbAlign, (budget + kPbAlign - 1) / kPbAlign * kPbAlign));
+      k += take;
+      budget -= take;
+      spent += take;
+    }
+    if (b == n_cta - 1) k = a->padded_nnz;
+    work[(size_t)b] = make_int2((int)k0, (int)k);
+    remaining -= spent;
+    if (remaining < 0) remaining = 0;
+  }
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_work, (size_t)n_cta * sizeof(int2)));
+  HISPMV_CUDA(cudaMemcpyAsync(a->d_work, work.data(), (size_t)n_cta * sizeof(int2), cudaMemcpyHostToDevice, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  a->num_work = n_cta;
+  return HISPMV_OK;
+}
+
+// ================================================================================================================
+// pass 1: prod[k] = val[k] * x[slab(k) * W + lcol[k]], the slab's piece of x staged in shared memory by TMA bulk copies
+// ================================================================================================================
+namespace {
+
+constexpr int kExpandThreads = 1024;
+constexpr int kBulkPiece = 4096;  // floats per cp.async.bulk (one copy costs its issuing thread ~650 cycles: 12 lanes
+                                  // issue the 12 pieces of a 48 K-column slab side by side)
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
+    pb_expand_kernel(PbPlan P, const float* __restrict__ x, int32_t cols) {
+  extern __shared__ __align__(128) unsigned char s_raw[];
+  float* s_x = reinterpret_cast<float*>(s_raw);
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int2 w = P.work[blockIdx.x];
+  if (w.x >= w.y) return;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  int s;
+  {  // the slab that holds entry w.x: the first s with slab_ptr[s + 1] > w.x
+    int lo = 0, hi = P.num_slabs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(P.slab_ptr + mid + 1) <= w.x) lo = mid + 1; else hi = mid;
+    }
+    s = lo;
+  }
+  const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
+  const bool x_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  uint32_t parity = 0;
+  int k = w.x;
+  while (k < w.y) {
+    const int kend = min(w.y, __ldg(P.slab_ptr + s + 1));
+    if (kend > k) {
+      const int c0 = s * P.slab_cols;
+      const int n = min(P.slab_cols, cols - c0);
+      const int nb = x_aligned ? (n & ~3) : 0;  // floats that travel by bulk copy (c0 is a multiple of 4)
+      if (nb > 0 && tid < 32) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous slab was read through the generic proxy
+        if (tid == 0) mbar_expect_tx(&bar, (uint32_t)nb * 4u);
+        __syncwarp();
+        for (int p = tid * kBulkPiece; p < nb; p += 32 * kBulkPiece)
+          bulk_g2s_hint(s_x + p, x + c0 + p, (uint32_t)min(kBulkPiece, nb - p) * 4u, &bar, pk);
+      }
+      for (int i = nb + tid; i < n; i += THREADS) s_x[i] = ld_x_keep(x + c0 + i, pk);
+      if (nb > 0) {
+        if (tid == 0) mbar_wait(&bar, parity);
+        parity ^= 1u;
+      }
+      __syncthreads();
+      constexpr int U = 4;
+      for (int base = k + tid * 4; base < kend; base += THREADS * 4 * U) {
+        float4 v[U];
+        uint2 c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * THREADS * 4;
+          if (i < kend) {
+            v[u] = ld_stream_f4(P.val + i, ps);
+            c[u] = ld_stream_u2(P.lcol + i, ps);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int i = base + u * THREADS * 4;
+          if (i < kend) {
+            float4 p;
+            p.x = v[u].x * s_x[c[u].x & 0xffffu];
+            p.y = v[u].y * s_x[c[u].x >> 16];
+            p.z = v[u].z * s_x[c[u].y & 0xffffu];
+            p.w = v[u].w * s_x[c[u].y >> 16];
+            *reinterpret_cast<float4*>(P.prod + i) = p;
+          }
+        }
+      }
+      __syncthreads();  // every gather from this slab has been issued before the next one overwrites it
+    }
+    k = kend;
+    ++s;
+  }
+}
+
+// ================================================================================================================
+// pass 2: one CTA per panel
+// ================================================================================================================
+constexpr int kReduceThreads = 512;
+constexpr int kSerialRowPb = 16;
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
+    pb_reduce_kernel(CsrDev A, PbPlan P, float* __restrict__ y, Epilogue ep) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's products, then its row extents
+  PbSeg* s_seg = reinterpret_cast<PbSeg*>(s_raw + (size_t)P.cap_words * 4);  // [max_panel_segs + 1]
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_red[WARPS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t t = P.panel_begin + blockIdx.x;
+  const TileDesc d = load_desc(P.desc + t);
+  const int sp0 = __ldg(P.panel_seg + t);
+  const int nseg = __ldg(P.panel_seg + t + 1) - sp0;
+  const int n = d.n1 - d.n0;
+  const bool is_long = d.chunk >= 0;
+  const int trows = d.r1 - d.r0;
+  const uint64_t ps = policy_evict_first();
+  for (int i = tid; i < nseg; i += THREADS) {
+    const int2 v = __ldg(reinterpret_cast<const int2*>(P.seg) + sp0 + i);
+    s_seg[i].start = v.x;
+    s_seg[i].off = v.y;
+  }
+  if (tid == 0) {
+    s_seg[nseg].start = 0;
+    s_seg[nseg].off = n;
+  }
+  int* s_rp = reinterpret_cast<int*>(s_prod + n);
+  if (!is_long)
+    for (int i = tid; i <= trows; i += THREADS) s_rp[i] = A.row_ptr[d.r0 + i] - d.n0;
+  __syncthreads();
+
+  // ---- walk the panel's segments: warp w takes the flat range [f0, f1) of the panel's entries in (slab, CSR) order --
+  constexpr int U = 8;
+  const int per = (((n + WARPS - 1) / WARPS) + 31) & ~31;
+  const int f0 = min(n, warp * per), f1 = min(n, f0 + per);
+  int cur = 0;
+  if (f0 < f1) {  // the last segment that starts at or before f0
+    int lo = 0, hi = nseg - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_seg[mid].off <= f0) lo = mid; else hi = mid - 1;
+    }
+    cur = lo;
+  }
+  float acc = 0.0f;
+  for (int base = f0; base < f1; base += 32 * U) {
+    int addr[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * 32 + lane;
+      int sg = cur;
+      addr[u] = -1;
+      if (i < f1) {
+        while (i >= s_seg[sg + 1].off) ++sg;
+        addr[u] = s_seg[sg].start + (i - s_seg[sg].off);
+      }
+      cur = __shfl_sync(kFullMask, sg, 31);
+    }
+    float p[U];
+    uint32_t q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      p[u] = 0.0f;
+      q[u] = 0;
+      if (addr[u] >= 0) {
+        p[u] = ld_stream_f1(P.prod + addr[u], ps);
+        if (!is_long) q[u] = ld_stream_u16(P.perm + addr[u], ps);
+      }
+    }
+    if (is_long) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc += p[u];
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (addr[u] >= 0) s_prod[q[u]] = p[u];
+    }
+  }
+  if (is_long) {
+    acc = warp_sum(acc);
+    if (lane == 0) s_red[warp] = acc;
+    __syncthreads();
+    if (warp != 0) return;
+    float total = lane < WARPS ? s_red[lane] : 0.0f;
+    total = warp_sum(total);
+    finish_chunk(P.carry, P.counter, d, t, total, lane, y, ep);
+    return;
+  }
+  __syncthreads();
+
+  // ---- rows out of the product buffer, in CSR order: warp w owns rows [beg, end) of the panel ----------------------
+  const int rpw = (trows + WARPS - 1) / WARPS;
+  const int beg = warp * rpw, end = min(trows, beg + rpw);
+  for (int base = beg; base < end; base += 32) {
+    const int i = base + lane;
+    int b = 0, e = 0;
+    float bias = 0.0f;
+    if (i < end) {
+      b = s_rp[i];
+      e = s_rp[i + 1];
+      if (ep.beta != 0.0f) bias = ep.bias[d.r0 + i];
+    }
+    const int len = e - b;
+    float s = 0.0f;
+    const int mine = len <= kSerialRowPb ? len : 0;
+    const int steps = __reduce_max_sync(kFullMask, mine);
+#pragma unroll 4
+    for (int k = 0; k < steps; ++k)
+      if (k < mine) s += s_prod[b + k];
+    unsigned big = __ballot_sync(kFullMask, len > kSerialRowPb);
+    while (big) {
+      const int j = __ffs(big) - 1;
+      big &= big - 1;
+      const int bj = __shfl_sync(kFullMask, b, j), ej = __shfl_sync(kFullMask, e, j);
+      float pp = 0.0f;
+      for (int k = bj + lane; k < ej; k += 32) pp += s_prod[k];
+      pp = warp_sum(pp);
+      if (lane == j) s = pp;
+    }
+    if (i < end) {
+      float v = ep.alpha * s;
+      if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
+      if (ep.relu) v = fmaxf(v, 0.0f);
+      store_y(y, d.r0 + i, v, ep.y_mc);
+    }
+  }
+}
+
+}  // namespace
+
+int pb_expand_ctas_per_sm(int32_t slab_cols) { return ((size_t)slab_cols * 4 + 1024) * 2 <= 227 * 1024 ? 2 : 1; }
+
+int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s) {
+  if (P.num_work <= 0) return HISPMV_OK;
+  const size_t smem = (size_t)P.slab_cols * 4;
+  static size_t configured = 0;
+  if (smem > configured) {
+    HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<kExpandThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    configured = smem;
+  }
+  pb_expand_kernel<kExpandThreads><<<P.num_work, kExpandThreads, smem, s>>>(P, x, cols);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s) {
+  const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
+  if (count <= 0) return HISPMV_OK;
+  const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.max_panel_segs + 1) * sizeof(PbSeg);
+  if (smem > 227 * 1024) {
+    set_error("blocked plan: a panel does not fit shared memory");
+    return HISPMV_ERR_STATE;
+  }
+  static size_t configured = 0;
+  if (smem > configured) {
+    HISPMV_CUDA(cudaFuncSetAttribute(pb_reduce_kernel<kReduceThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    configured = smem;
+  }
+  pb_reduce_kernel<kReduceThreads><<<(unsigned)count, kReduceThreads, smem, s>>>(A, P, y, ep);
+  HISPMV_CUDA(cudaGetLastError());
+  return HISPMV_OK;
+}
+
+// The blocked strategy pays 16 bytes of streaming per nonzero instead of 8 plus a 32-byte L2 sector per scattered
+// gather, so it wins when the gathers are scattered (not banded), x is far larger than an SM's L1 (otherwise the
+// gathers hit on chip anyway) and the matrix is large enough to fill two launches.  Integer rule, restated in
+// oracle/oracle.c (oracle_select_blocked).
+int select_blocked(int32_t rows, int32_t cols, int64_t nnz, const ColProbe& probe, int allow_split_rows) {
+  const bool banded = probe.cmp >= 64 && probe.near * 4 >= probe.cmp * 3;
+  if (!allow_split_rows || banded || rows <= 0) return 0;
+  if ((int64_t)cols < 1000000 || nnz < 16000000) return 0;
+  if (((int64_t)cols + kPbSlabCols - 1) / kPbSlabCols > 4096) return 0;
+  return 1;
+}
+
+}  // namespace hispmv

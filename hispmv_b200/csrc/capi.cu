@@ -67,6 +67,8 @@ struct Matrix {
   int adaptive_threads = 256;           // ADAPTIVE: threads per CTA (256; 128 through the development switch)
   int rowstage_threads = 128;           // ROWSTAGE: threads per CTA (128; 256 through the development switch)
   ColProbe probe{};                     // column-locality probe (selector input)
+  PbArrays pb;                          // BLOCKED: the slab-major copy, segment table, pass-1 work ranges, products
+  int64_t pb_slab_cost = 0;             // BLOCKED: entries one slab load is worth when pass-1 ranges are balanced
   // dense
   float* d_a = nullptr;
   int64_t ld = 0;
@@ -80,6 +82,7 @@ struct Matrix {
     cudaFree(d_tile_chunk);
     cudaFree(d_counter);
     cudaFree(d_desc);
+    pb_free(&pb);
     d_desc = nullptr;
     d_tile_chunk = nullptr;
     d_counter = nullptr;
@@ -95,6 +98,8 @@ struct Matrix {
     if (dense) return (int64_t)local_rows() * ld * 4;
     int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
+    if (pb.d_val)  // val + lcol + perm + one product buffer per stream lane in use + segment table
+      b += pb.padded_nnz * (8 + 4 * (pb.d_prod[1] ? 2 : 1)) + pb.num_seg * 8 + (num_tiles + 1) * 4 + (pb.num_slabs + 1) * 4;
     for (auto* sm : slabs) b += sm->device_bytes();
     return b;
   }
@@ -198,6 +203,12 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
   for (auto* sm : m->slabs) delete sm;
   m->slabs.clear();
   m->slab_cols = 0;
+  if (!m->forced && m->kernel == HISPMV_KERNEL_ADAPTIVE && !m->is_slab) {
+    // scattered gathers over a large x: two streaming passes with x served from shared memory (blocked.cu)
+    int want = select_blocked(m->local_rows(), m->cols, m->nnz, m->probe, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0);
+    if (const char* e = getenv("HISPMV_BLOCKED_AUTO")) want = want && atoi(e) != 0;  // "0": keep the one-pass kernels
+    if (want) m->kernel = HISPMV_KERNEL_BLOCKED;
+  }
   if (m->kernel == HISPMV_KERNEL_ADAPTIVE && !m->is_slab) {
     int32_t w = select_slab_cols(m->cols, m->nnz, m->probe);
     if (const char* e = getenv("HISPMV_SLAB_COLS")) w = std::max(0, atoi(e));  // tests / sweeps
@@ -240,6 +251,52 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     st = split_rows_device(m->d_row_ptr, m->local_rows(), m->d_tile_row, m->d_tile_nnz, m->num_tiles,
                            &m->d_split_rows, &m->num_split, c->stream);
     if (st != HISPMV_OK) return st;
+  }
+  if (m->kernel == HISPMV_KERNEL_BLOCKED) {
+    int32_t W = kPbSlabCols;
+    m->tile_items = kPbPanelItems;
+    m->long_threshold = kPbLongThreshold;
+    m->chunk_nnz = kPbChunkNnz;
+    m->pb_slab_cost = 32768;
+    if (const char* e = getenv("HISPMV_BLOCKED")) {  // "W,B,T,CH[,SLABCOST]" (development sweeps)
+      int w = 0, b = 0, t = 0, ch = 0, sc = -1;
+      if (sscanf(e, "%d,%d,%d,%d,%d", &w, &b, &t, &ch, &sc) >= 4 && w >= 1024 && w <= kPbMaxSlabCols && (w & 3) == 0 &&
+          b >= 256 && t >= 16 && b + t <= 56000 && ch >= 512 && ch <= 65535) {
+        W = w;
+        m->tile_items = b;
+        m->long_threshold = t;
+        m->chunk_nnz = ch;
+        if (sc >= 0) m->pb_slab_cost = sc;
+      }
+    }
+    if (m->nnz <= 0 || m->local_rows() <= 0) {
+      m->kernel = HISPMV_KERNEL_EMPTY;
+    } else {
+      st = adaptive_tiles_device(m->d_row_ptr, m->local_rows(), m->tile_items, m->long_threshold, m->chunk_nnz,
+                                 &m->num_tiles, &m->d_tile_row, &m->d_tile_chunk, &m->d_split_rows, &m->num_split,
+                                 c->stream);
+      if (st != HISPMV_OK) return st;
+      st = tile_desc_device(m->d_row_ptr, m->d_tile_row, m->d_tile_chunk, m->num_tiles, m->chunk_nnz, &m->d_desc,
+                            c->stream);
+      if (st != HISPMV_OK) return st;
+      m->h_tile_row.assign((size_t)m->num_tiles + 1, 0);
+      m->h_tile_chunk.assign((size_t)std::max<int64_t>(m->num_tiles, 1), -1);
+      HISPMV_CUDA(cudaMemcpyAsync(m->h_tile_row.data(), m->d_tile_row, (size_t)(m->num_tiles + 1) * 4,
+                                  cudaMemcpyDeviceToHost, c->stream));
+      HISPMV_CUDA(cudaMemcpyAsync(m->h_tile_chunk.data(), m->d_tile_chunk, (size_t)m->num_tiles * 4,
+                                  cudaMemcpyDeviceToHost, c->stream));
+      const size_t n = (size_t)std::max<int64_t>(m->num_tiles, 1) * 2;
+      HISPMV_CUDA(cudaMalloc((void**)&m->d_carry, n * sizeof(float)));
+      HISPMV_CUDA(fill_u32_device(reinterpret_cast<uint32_t*>(m->d_carry), kCarryEmptyBits, n, c->stream));
+      HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, (n + 8) * sizeof(unsigned int)));
+      HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, (n + 8) * sizeof(unsigned int), c->stream));
+      st = pb_build_device(m->d_row_ptr, m->d_col, m->d_val, m->local_rows(), m->cols, m->nnz, m->d_desc, m->num_tiles,
+                           W, &m->pb, c->stream);
+      if (st != HISPMV_OK) return st;
+      st = pb_make_work(&m->pb, c->sm_count * pb_expand_ctas_per_sm(W), m->pb_slab_cost, c->stream);
+      if (st != HISPMV_OK) return st;
+      HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_prod[0], ((size_t)m->pb.padded_nnz + 64) * 4));
+    }
   }
   if (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) {
     if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
@@ -520,8 +577,10 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
 
 // `lane` selects one of the two carry / counter sets so that linear()'s two stream lanes never share them.
 // Device-pointer callers get lane 0: one run in flight per matrix handle, as with the reference's xrt::run.
+// `phases`: BLOCKED only -- bit 0 runs pass 1 (products of the whole matrix), bit 1 pass 2 over the given panels.
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
-               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1, int y_mc = 0) {
+               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1, int y_mc = 0,
+               int phases = 3) {
   Epilogue ep{alpha, beta, d_bias, relu};
   ep.y_mc = y_mc;
   if (y_mc && !m->dense && (m->kernel == HISPMV_KERNEL_MERGE || !m->slabs.empty() || m->pipeline)) {
@@ -620,6 +679,38 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       if (m->pipeline) return launch_pipeline(A, P, d_x, d_y, ep, c->sm_count, s);
       if (m->persistent) return launch_adaptive_persistent(A, P, d_x, d_y, ep, c->sm_count, s);
       return launch_adaptive(A, P, m->adaptive_threads, d_x, d_y, ep, s);
+    }
+    case HISPMV_KERNEL_BLOCKED: {
+      if (!m->pb.d_prod[lane]) {  // the second stream lane of linear() gets its own product buffer on first use
+        HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_prod[lane], ((size_t)m->pb.padded_nnz + 64) * 4));
+      }
+      PbPlan P;
+      P.slab_cols = m->pb.slab_cols;
+      P.num_slabs = m->pb.num_slabs;
+      P.padded_nnz = m->pb.padded_nnz;
+      P.slab_ptr = m->pb.d_slab_ptr;
+      P.val = m->pb.d_val;
+      P.lcol = m->pb.d_lcol;
+      P.perm = m->pb.d_perm;
+      P.prod = m->pb.d_prod[lane];
+      P.num_panels = m->num_tiles;
+      P.desc = m->d_desc;
+      P.panel_seg = m->pb.d_panel_seg;
+      P.seg = m->pb.d_seg;
+      P.max_panel_segs = m->pb.max_panel_segs;
+      P.work = m->pb.d_work;
+      P.num_work = m->pb.num_work;
+      P.cap_words = (m->tile_items + m->long_threshold + 8 + 1) & ~1;  // even: the segment table behind it is 8-byte aligned
+      P.panel_begin = tile_begin;
+      P.panel_count = tile_count;
+      P.carry = m->d_carry + (size_t)lane * m->num_tiles;
+      P.counter = m->d_counter + (size_t)lane * m->num_tiles;
+      if (phases & 1) {
+        int st = launch_pb_expand(P, m->cols, d_x, s);
+        if (st != HISPMV_OK) return st;
+      }
+      if (phases & 2) return launch_pb_reduce(A, P, d_y, ep, s);
+      return HISPMV_OK;
     }
     default: set_error("run: matrix has no plan"); return HISPMV_ERR_STATE;
   }
@@ -889,7 +980,8 @@ int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
     return HISPMV_ERR_ARG;
   }
   if (kernel != HISPMV_KERNEL_AUTO && kernel != HISPMV_KERNEL_CSR_SCALAR && kernel != HISPMV_KERNEL_CSR_VECTOR &&
-      kernel != HISPMV_KERNEL_MERGE && kernel != HISPMV_KERNEL_ADAPTIVE && kernel != HISPMV_KERNEL_ROWSTAGE) {
+      kernel != HISPMV_KERNEL_MERGE && kernel != HISPMV_KERNEL_ADAPTIVE && kernel != HISPMV_KERNEL_ROWSTAGE &&
+      kernel != HISPMV_KERNEL_BLOCKED) {
     set_error("force_kernel: unknown kernel");
     return HISPMV_ERR_ARG;
   }
@@ -961,6 +1053,7 @@ int hispmv_launches_per_run(hispmv_ctx* c, int idx) {
   if (m->local_rows() <= 0) return 0;
   if (!m->dense && m->kernel == HISPMV_KERNEL_MERGE) return m->num_tiles > 1 ? 2 : 1;
   if (!m->slabs.empty()) return (int)m->slabs.size();
+  if (!m->dense && m->kernel == HISPMV_KERNEL_BLOCKED) return 2;
   return 1;
 }
 
@@ -993,7 +1086,8 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
   // Large tiled matrices: the rows are cut into up to 8 ranges at tile boundaries and the ranges are pipelined over
   // three streams -- bias range i+1 goes up and y range i-1 comes down (PCIe is full duplex) while range i computes.
   // The reference overlaps its host-side fill with the running kernel the same way (fpga_handle.cpp:366-379).
-  const bool tiled = !m->dense && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) &&
+  const bool tiled = !m->dense && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE ||
+                                   m->kernel == HISPMV_KERNEL_BLOCKED) &&
                      !m->pipeline && !m->persistent && !m->warptile && m->slabs.empty();
   int chunks = 1;
   if (tiled && n_y >= (1 << 20) && m->num_tiles >= 64) chunks = n_y >= (1 << 22) ? 8 : 4;
@@ -1076,8 +1170,9 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
       HISPMV_CUDA(cudaStreamWaitEvent(s, ev_b, 0));
       mark(s_up, "bias up " + std::to_string(i));
     }
+    // BLOCKED: pass 1 needs only x and runs once, ahead of the first range; pass 2 follows range by range
     st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, tb[i],
-                    tb[i + 1] - tb[i]);
+                    tb[i + 1] - tb[i], 0, i == 0 ? 3 : 2);
     if (st != HISPMV_OK) return st;
     HISPMV_CUDA(cudaEventRecord(ev_k, s));
     HISPMV_CUDA(cudaStreamWaitEvent(s_down, ev_k, 0));
@@ -1238,7 +1333,8 @@ int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_n
   if (tile_row) HISPMV_CUDA(cudaMemcpy(tile_row, m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
   if (tile_nnz && m->kernel == HISPMV_KERNEL_MERGE)
     HISPMV_CUDA(cudaMemcpy(tile_nnz, m->d_tile_nnz, (size_t)(m->num_tiles + 1) * 8, cudaMemcpyDeviceToHost));
-  if (tile_nnz && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE)) {
+  if (tile_nnz && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE ||
+                   m->kernel == HISPMV_KERNEL_BLOCKED)) {
     // offset of each tile's first nonzero: row_ptr[tile_row] (+ chunk * chunk_nnz for LONG tiles)
     std::vector<int32_t> tr((size_t)m->num_tiles + 1), tc((size_t)std::max<int64_t>(m->num_tiles, 1));
     HISPMV_CUDA(cudaMemcpy(tr.data(), m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
@@ -1281,13 +1377,54 @@ int hispmv_plan_slab_csr(hispmv_ctx* c, int idx, int slab, int32_t* row_ptr, int
 int hispmv_plan_tile_chunks(hispmv_ctx* c, int idx, int32_t* chunk_out) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
-  if ((m->kernel != HISPMV_KERNEL_ADAPTIVE && m->kernel != HISPMV_KERNEL_ROWSTAGE) || !m->d_tile_chunk) {
+  if ((m->kernel != HISPMV_KERNEL_ADAPTIVE && m->kernel != HISPMV_KERNEL_ROWSTAGE &&
+       m->kernel != HISPMV_KERNEL_BLOCKED) || !m->d_tile_chunk) {
     set_error("plan_tile_chunks: matrix is not planned for the adaptive kernel");
     return HISPMV_ERR_STATE;
   }
   DeviceGuard g(c->device);
   if (chunk_out && m->num_tiles)
     HISPMV_CUDA(cudaMemcpy(chunk_out, m->d_tile_chunk, (size_t)m->num_tiles * 4, cudaMemcpyDeviceToHost));
+  return HISPMV_OK;
+}
+
+int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (!out8) return HISPMV_ERR_ARG;
+  if (m->dense || m->kernel != HISPMV_KERNEL_BLOCKED) {
+    set_error("plan_blocked: matrix is not planned for the blocked strategy");
+    return HISPMV_ERR_STATE;
+  }
+  out8[0] = m->pb.slab_cols;
+  out8[1] = m->pb.num_slabs;
+  out8[2] = m->pb.padded_nnz;
+  out8[3] = m->pb.num_seg;
+  out8[4] = m->pb.max_panel_segs;
+  out8[5] = m->pb.num_work;
+  out8[6] = m->num_tiles;
+  out8[7] = m->pb_slab_cost;
+  return HISPMV_OK;
+}
+
+int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* perm,
+                        int32_t* panel_seg, int32_t* seg_start_off, int32_t* work) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (m->dense || m->kernel != HISPMV_KERNEL_BLOCKED) {
+    set_error("plan_blocked: matrix is not planned for the blocked strategy");
+    return HISPMV_ERR_STATE;
+  }
+  DeviceGuard g(c->device);
+  const PbArrays& a = m->pb;
+  const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+  if (slab_ptr) HISPMV_CUDA(cudaMemcpy(slab_ptr, a.d_slab_ptr, ((size_t)a.num_slabs + 1) * 4, k));
+  if (vals) HISPMV_CUDA(cudaMemcpy(vals, a.d_val, (size_t)a.padded_nnz * 4, k));
+  if (lcol) HISPMV_CUDA(cudaMemcpy(lcol, a.d_lcol, (size_t)a.padded_nnz * 2, k));
+  if (perm) HISPMV_CUDA(cudaMemcpy(perm, a.d_perm, (size_t)a.padded_nnz * 2, k));
+  if (panel_seg) HISPMV_CUDA(cudaMemcpy(panel_seg, a.d_panel_seg, ((size_t)m->num_tiles + 1) * 4, k));
+  if (seg_start_off) HISPMV_CUDA(cudaMemcpy(seg_start_off, a.d_seg, (size_t)a.num_seg * 8, k));
+  if (work) HISPMV_CUDA(cudaMemcpy(work, a.d_work, (size_t)a.num_work * 8, k));
   return HISPMV_OK;
 }
 

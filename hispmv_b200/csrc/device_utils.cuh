@@ -50,6 +50,18 @@ __device__ __forceinline__ float ld_stream_f1(const float* p, uint64_t pol) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(p), "l"(pol));
   return r;
 }
+__device__ __forceinline__ uint2 ld_stream_u2(const void* p, uint64_t pol) {  // 8 bytes (four 16-bit local columns)
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_stream_u16(const uint16_t* p, uint64_t pol) {
+  uint16_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(r) : "l"(p), "l"(pol));
+  return r;
+}
 // 256-bit streaming load (sm_100+): 8 consecutive 32-bit words from a 32-byte aligned address.
 struct alignas(32) Words8 {
   uint32_t w[8];

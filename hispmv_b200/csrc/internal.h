@@ -176,6 +176,76 @@ constexpr int kRowstageMaxCap = 8192;
 int launch_empty(int32_t rows, float* y, Epilogue ep, cudaStream_t s);
 bool merge_tile_items_supported(int tile_items);
 
+// ---- blocked.cu: column-blocked two-pass SpMV (x gathers served from shared memory) --------------------------------
+// For matrices whose x gathers have no locality (power-law / uniform columns, x far larger than L1) a scattered 4-byte
+// gather costs a whole 32-byte L2 sector, and the L2's sector rate -- not HBM -- bounds the one-pass kernels (DESIGN.md
+// section 4).  The blocked strategy removes the gathers from L2 altogether:
+//   expand  (pass 1)  the nonzeros are stored a second time in SLAB-MAJOR order (slab = slab_cols consecutive columns,
+//                     inside a slab in CSR order); a CTA keeps the slab's piece of x in shared memory (one TMA bulk load)
+//                     and streams val / 16-bit local column -> prod[k] = val[k] * x_slab[lcol[k]], all coalesced.
+//   reduce  (pass 2)  rows are cut into PANELS (the adaptive tiles with a larger budget: STREAM panels of short rows,
+//                     LONG panels = chunks of long rows); a panel's products are the (panel, slab) SEGMENTS -- contiguous
+//                     runs of prod[] -- which a CTA walks in slab order, dropping each product at its CSR position inside
+//                     the panel (16-bit perm) in shared memory, then sums the rows in CSR order (deterministic, the same
+//                     order as a sequential CSR SpMV) and applies alpha / beta / ReLU.  LONG panels just add up their
+//                     segments and meet through the split-row carries of the adaptive kernel.
+// Traffic: 4 + 2 + 4 bytes per nonzero in pass 1, 4 + 2 in pass 2 (16 B against the 8 B of CSR) -- all of it streaming.
+struct PbSeg {
+  int32_t start;  // first entry of the segment in slab-major (blocked) order
+  int32_t off;    // number of entries of the same panel in earlier slabs (the segment's offset in the panel's walk)
+};
+struct PbPlan {
+  int32_t slab_cols = 0, num_slabs = 0;
+  int64_t padded_nnz = 0;              // length of the blocked arrays: every slab starts at a multiple of kPbAlign
+  const int32_t* slab_ptr = nullptr;   // num_slabs+1 starts in blocked order (device)
+  const float* val = nullptr;          // blocked order; padding entries are 0
+  const uint16_t* lcol = nullptr;      // column - slab * slab_cols
+  const uint16_t* perm = nullptr;      // STREAM panels: CSR position - the panel's first CSR position
+  float* prod = nullptr;               // pass 1 output / pass 2 input
+  int64_t num_panels = 0;
+  const TileDesc* desc = nullptr;      // the panels (adaptive tiles)
+  const int32_t* panel_seg = nullptr;  // num_panels+1 offsets into seg[]
+  const PbSeg* seg = nullptr;          // non-empty (panel, slab) segments, panel-major then slab
+  int32_t max_panel_segs = 0;
+  const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
+  int32_t num_work = 0;
+  int32_t cap_words = 0;               // shared-memory words a STREAM panel needs (products + row extents)
+  int64_t panel_begin = 0, panel_count = -1;  // pass 2: launch only these panels (host-buffer pipeline)
+  float* carry = nullptr;              // split LONG rows: as in AdaptivePlan
+  unsigned int* counter = nullptr;
+};
+constexpr int32_t kPbAlign = 128;
+constexpr int32_t kPbMaxSlabCols = 57344;  // 224 KB of x: the largest slab one CTA's shared memory can hold
+// owned device arrays of a blocked plan (built by pb_build_device, freed by pb_free)
+struct PbArrays {
+  int32_t slab_cols = 0, num_slabs = 0;
+  int64_t padded_nnz = 0, num_seg = 0;
+  int32_t max_panel_segs = 0;
+  int32_t* d_slab_ptr = nullptr;
+  float* d_val = nullptr;
+  uint16_t* d_lcol = nullptr;
+  uint16_t* d_perm = nullptr;
+  int32_t* d_panel_seg = nullptr;
+  PbSeg* d_seg = nullptr;
+  int2* d_work = nullptr;
+  int32_t num_work = 0;
+  float* d_prod[2] = {nullptr, nullptr};  // one per stream lane, the second allocated on first use
+  int32_t* h_slab_ptr = nullptr;          // host copy (num_slabs+1), new[]
+};
+void pb_free(PbArrays* a);
+// Build the blocked copy of a device CSR whose panels are `d_desc` (adaptive tiles).  Restated in oracle/ (oracle_pb_plan).
+int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
+                    int64_t nnz, const TileDesc* d_desc, int64_t num_panels, int32_t slab_cols, PbArrays* out,
+                    cudaStream_t stream);
+// pass-1 work ranges for `n_cta` resident CTAs: contiguous, balanced by entries + slab_cost per slab (re)load
+int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream);
+int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);
+int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
+int pb_expand_ctas_per_sm(int32_t slab_cols);
+// Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
+constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 16384, kPbLongThreshold = 1024, kPbChunkNnz = 32768;
+int select_blocked(int32_t rows, int32_t cols, int64_t nnz, const ColProbe& probe, int allow_split_rows);
+
 // ---- batch.cu: several right-hand sides in one pass over A (x interleaved as xi[c * K + k], K = batch_width(nv)) ----
 int batch_width(int nv);  // 2, 4 or 8
 // x [nv][n] -> xi [n_pad][K] (rows n..n_pad-1 and vectors nv..K-1 zero)

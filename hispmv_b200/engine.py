@@ -200,6 +200,25 @@ class Engine:
         check(lib.hispmv_plan_slab_csr(self._ctx, matrix_idx, slab, _ptr(rp), _ptr(ci), _ptr(v)), "plan_slab_csr")
         return rp, ci, v
 
+    def plan_blocked(self, matrix_idx: int, arrays: bool = True) -> dict:
+        """The blocked strategy's plan (hispmv_plan_blocked_info / hispmv_plan_blocked) as host arrays."""
+        o = np.zeros(8, np.int64)
+        check(lib.hispmv_plan_blocked_info(self._ctx, matrix_idx, _ptr(o)), "plan_blocked_info")
+        d = {"slab_cols": int(o[0]), "num_slabs": int(o[1]), "padded_nnz": int(o[2]), "num_seg": int(o[3]),
+             "max_panel_segs": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "slab_cost": int(o[7])}
+        if arrays:
+            d["slab_ptr"] = np.empty(d["num_slabs"] + 1, np.int32)
+            d["val"] = np.empty(d["padded_nnz"], np.float32)
+            d["lcol"] = np.empty(d["padded_nnz"], np.uint16)
+            d["perm"] = np.empty(d["padded_nnz"], np.uint16)
+            d["panel_seg"] = np.empty(d["num_panels"] + 1, np.int32)
+            d["seg"] = np.empty((d["num_seg"], 2), np.int32)
+            d["work"] = np.empty((d["num_work"], 2), np.int32)
+            check(lib.hispmv_plan_blocked(self._ctx, matrix_idx, _ptr(d["slab_ptr"]), _ptr(d["val"]), _ptr(d["lcol"]),
+                                          _ptr(d["perm"]), _ptr(d["panel_seg"]), _ptr(d["seg"]), _ptr(d["work"])),
+                  "plan_blocked")
+        return d
+
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:
         info = self.matrix_info(matrix_idx)
         out = np.empty(info["num_split_rows"], np.int32)

@@ -66,9 +66,13 @@ enum {
   HISPMV_KERNEL_EMPTY = 5,       /* nnz == 0: y = beta * bias */
   HISPMV_KERNEL_ADAPTIVE = 6,    /* row-aligned nnz-balanced tiles: short rows streamed through shared memory,
                                     long rows chunked across CTAs with carry-out (default for imbalanced rows) */
-  HISPMV_KERNEL_ROWSTAGE = 7     /* the same tiles with the col/val stream staged in shared memory by TMA bulk copies
+  HISPMV_KERNEL_ROWSTAGE = 7,    /* the same tiles with the col/val stream staged in shared memory by TMA bulk copies
                                     and rows walked by 1..32 lanes each: regular rows with column locality
                                     (banded / stencil / FEM) */
+  HISPMV_KERNEL_BLOCKED = 8      /* two streaming passes for scattered columns over a large x: the nonzeros are kept a
+                                    second time in column-slab-major order, pass 1 multiplies them with the slab's piece
+                                    of x held in shared memory (the reference's column tiles and on-chip x buffers,
+                                    common/src/spmv-helper.cpp:139-227), pass 2 sums the products per row panel */
 };
 
 /* ctor flags: the reference's hardware switches that still mean something on a GPU */
@@ -196,8 +200,19 @@ int hispmv_plan_split_rows(hispmv_ctx* ctx, int idx, int32_t* rows_out);
  * hispmv_plan_slab_nnz returns).  Any pointer may be NULL. */
 int64_t hispmv_plan_slab_nnz(hispmv_ctx* ctx, int idx, int slab);
 int hispmv_plan_slab_csr(hispmv_ctx* ctx, int idx, int slab, int32_t* row_ptr, int32_t* col_idx, float* vals);
-/* ADAPTIVE only: per tile, -1 for a STREAM tile or the chunk index of a LONG tile (num_tiles entries). */
+/* ADAPTIVE / BLOCKED: per tile (panel), -1 for a STREAM tile or the chunk index of a LONG tile (num_tiles entries). */
 int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
+/* BLOCKED only (the column tiling of tileAndPad, common/src/spmv-helper.cpp:139-227, as this engine lays it out).
+ * out8 = { slab_cols, num_slabs, padded_nnz, num_segments, max segments of a panel, pass-1 work ranges, panels,
+ *          slab cost used to balance the ranges }.
+ * hispmv_plan_blocked copies the plan to the host (any pointer may be NULL): slab_ptr[num_slabs+1] (slab starts in
+ * the slab-major order, multiples of 128), vals / lcol / perm [padded_nnz] (value, column - slab*slab_cols, CSR position
+ * - first CSR position of the entry's panel; padding entries are zero), panel_seg[panels+1], seg_start_off
+ * [2*num_segments] ((start in slab-major order, entries of the same panel in earlier slabs) per non-empty (panel, slab)
+ * segment, panel-major), work[2*ranges] (pass-1 [begin, end) per resident CTA). */
+int hispmv_plan_blocked_info(hispmv_ctx* ctx, int idx, int64_t* out8);
+int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* perm,
+                        int32_t* panel_seg, int32_t* seg_start_off, int32_t* work);
 
 /* ---- x exchange over NVSwitch multicast: store n floats from d_src to a multicast address (every GPU of the
  *      multicast group receives them).  mc_dst comes from a symmetric-memory rendezvous; sm_budget > 0 = that many

@@ -392,6 +392,159 @@ int64_t oracle_adaptive_split_rows(int rows, const int* row_ptr, int T, int CH, 
   return n;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Blocked (column-slab x row-panel) plan, restating hispmv_b200/csrc/blocked.cu: pb_build_device,
+ * pb_make_work and select_blocked.  The reference's own column tiling is tileAndPad
+ * (common/src/spmv-helper.cpp:139-227: a tile covers as many columns as the on-chip x buffers hold);
+ * this is the same idea with the GPU engine's sizes, single-threaded.
+ *   slab s      = columns [s*W, (s+1)*W)
+ *   panels      = the adaptive tiles (oracle_adaptive_tiles) given by tile_row / tile_chunk / CH
+ *   blocked order: slab-major, CSR order inside a slab; every slab starts at a multiple of `align`,
+ *                  the gaps are padding (val 0, lcol 0, perm 0)
+ *   per entry   : val, lcol = col - s*W, perm = CSR position - first CSR position of the entry's panel
+ *   segments    : the non-empty (panel, slab) runs, listed panel-major then by slab, as
+ *                 (start in blocked order, number of the panel's entries in earlier slabs)
+ * Returns the padded length; *num_seg gets the segment count.  Call with o_val == NULL to size.
+ * ---------------------------------------------------------------------------------------------- */
+static void pb_panel_extent(const int* row_ptr, const int* tile_row, const int* tile_chunk, int CH, int64_t t,
+                            int* n0, int* n1) {
+  if (tile_chunk[t] >= 0) {
+    const int r = tile_row[t];
+    const int b = row_ptr[r] + tile_chunk[t] * CH;
+    const int e = row_ptr[r + 1];
+    *n0 = b;
+    *n1 = b + CH < e ? b + CH : e;
+  } else {
+    *n0 = row_ptr[tile_row[t]];
+    *n1 = row_ptr[tile_row[t + 1]];
+  }
+}
+
+static int cmp_int(const void* a, const void* b) {
+  const int x = *(const int*)a, y = *(const int*)b;
+  return (x > y) - (x < y);
+}
+
+int64_t oracle_pb_plan(int rows, int cols, const int* row_ptr, const int* col, const float* val, int64_t num_panels,
+                       const int* tile_row, const int* tile_chunk, int CH, int W, int align, int* slab_ptr,
+                       float* o_val, uint16_t* o_lcol, uint16_t* o_perm, int* panel_seg, int* seg,
+                       int64_t* num_seg) {
+  const int64_t nnz = row_ptr[rows];
+  const int S = (int)(((int64_t)cols + W - 1) / W);
+  int64_t* cnt = (int64_t*)calloc((size_t)S + 1, sizeof(int64_t));
+  int64_t* start = (int64_t*)calloc((size_t)S + 1, sizeof(int64_t));
+  int* first = (int*)malloc(sizeof(int) * ((size_t)S + 1));
+  int* pcnt = (int*)calloc((size_t)S + 1, sizeof(int));
+  int* touched = (int*)malloc(sizeof(int) * ((size_t)S + 1));
+  int64_t j, pos = 0, nseg = 0, t;
+  int s;
+  for (j = 0; j < nnz; ++j) cnt[col[j] / W]++;
+  for (s = 0; s < S; ++s) {
+    start[s] = pos;
+    if (slab_ptr) slab_ptr[s] = (int)pos;
+    pos += cnt[s];
+    pos = (pos + align - 1) / align * align;
+    cnt[s] = 0; /* becomes the fill counter */
+  }
+  if (slab_ptr) slab_ptr[S] = (int)pos;
+  if (o_val) {
+    memset(o_val, 0, sizeof(float) * (size_t)pos);
+    memset(o_lcol, 0, sizeof(uint16_t) * (size_t)pos);
+    memset(o_perm, 0, sizeof(uint16_t) * (size_t)pos);
+  }
+  for (t = 0; t < num_panels; ++t) {
+    int n0, n1, nt = 0, i, off = 0;
+    pb_panel_extent(row_ptr, tile_row, tile_chunk, CH, t, &n0, &n1);
+    if (panel_seg) panel_seg[t] = (int)nseg;
+    for (j = n0; j < n1; ++j) {
+      const int sl = col[j] / W;
+      const int64_t dst = start[sl] + cnt[sl]++;
+      if (pcnt[sl]++ == 0) {
+        first[sl] = (int)dst;
+        touched[nt++] = sl;
+      }
+      if (o_val) {
+        o_val[dst] = val[j];
+        o_lcol[dst] = (uint16_t)(col[j] - sl * W);
+        o_perm[dst] = (uint16_t)(j - n0);
+      }
+    }
+    qsort(touched, (size_t)nt, sizeof(int), cmp_int);
+    for (i = 0; i < nt; ++i) {
+      const int sl = touched[i];
+      if (seg) {
+        seg[2 * nseg] = first[sl];
+        seg[2 * nseg + 1] = off;
+      }
+      off += pcnt[sl];
+      pcnt[sl] = 0;
+      ++nseg;
+    }
+  }
+  if (panel_seg) panel_seg[num_panels] = (int)nseg;
+  if (num_seg) *num_seg = nseg;
+  free(cnt);
+  free(start);
+  free(first);
+  free(pcnt);
+  free(touched);
+  return pos;
+}
+
+/* Pass-1 work ranges (blocked.cu: pb_make_work): n_cta contiguous pieces of the blocked order, balanced by entries
+ * plus slab_cost for every slab a piece is the first to touch.  work gets 2*n_cta ints. */
+void oracle_pb_work(int S, const int* slab_ptr, int align, int n_cta, int64_t slab_cost, int* work) {
+  const int64_t total = slab_ptr[S];
+  int64_t used = 0, remaining, k = 0;
+  int s = 0, b;
+  for (b = 0; b < S; ++b) used += slab_ptr[b + 1] > slab_ptr[b];
+  remaining = total + slab_cost * used;
+  for (b = 0; b < n_cta; ++b) {
+    const int64_t k0 = k;
+    int64_t budget = (remaining + (n_cta - b) - 1) / (n_cta - b), spent = 0;
+    int fresh = 1;
+    while (k < total && (budget > 0 || b == n_cta - 1)) {
+      int64_t take;
+      while (s < S && slab_ptr[s + 1] <= k) {
+        ++s;
+        fresh = 1;
+      }
+      if (s >= S) break;
+      if (fresh) {
+        if (k == slab_ptr[s]) {
+          budget -= slab_cost;
+          spent += slab_cost;
+        }
+        fresh = 0;
+        if (budget <= 0 && k > k0 && b != n_cta - 1) break;
+      }
+      take = (int64_t)slab_ptr[s + 1] - k;
+      if (b != n_cta - 1) {
+        int64_t cap = (budget + align - 1) / align * align;
+        if (cap < align) cap = align;
+        if (take > cap) take = cap;
+      }
+      k += take;
+      budget -= take;
+      spent += take;
+    }
+    if (b == n_cta - 1) k = total;
+    work[2 * b] = (int)k0;
+    work[2 * b + 1] = (int)k;
+    remaining -= spent;
+    if (remaining < 0) remaining = 0;
+  }
+}
+
+/* blocked.cu: select_blocked -- scattered columns over a large x on a matrix big enough for two launches */
+int oracle_select_blocked(int rows, int cols, int64_t nnz, int64_t probe_near, int64_t probe_cmp, int allow_split_rows) {
+  const int banded = probe_cmp >= 64 && probe_near * 4 >= probe_cmp * 3;
+  if (!allow_split_rows || banded || rows <= 0) return 0;
+  if ((int64_t)cols < 1000000 || nnz < 16000000) return 0;
+  if (((int64_t)cols + 49152 - 1) / 49152 > 4096) return 0;
+  return 1;
+}
+
 /* nnz-balanced contiguous row blocks: bounds[k] = first row r with row_ptr[r] >= k*nnz/n_parts. */
 void oracle_shard_bounds(int rows, const int* row_ptr, int n_parts, int* bounds) {
   const int64_t nnz = row_ptr[rows];

@@ -74,6 +74,12 @@ def oracle() -> C.CDLL:
     lib.oracle_adaptive_tiles.restype = i64
     lib.oracle_adaptive_split_rows.argtypes = [i, _i32p, i, i, vp]
     lib.oracle_adaptive_split_rows.restype = i64
+    lib.oracle_pb_plan.argtypes = [i, i, _i32p, _i32p, _f32p, i64, _i32p, _i32p, i, i, i, vp, vp, vp, vp, vp, vp,
+                                   C.POINTER(i64)]
+    lib.oracle_pb_plan.restype = i64
+    lib.oracle_pb_work.argtypes = [i, _i32p, i, i, i64, _i32p]
+    lib.oracle_select_blocked.argtypes = [i, i, i64, i64, i64, i]
+    lib.oracle_select_blocked.restype = i
     lib.oracle_synth_row_len.argtypes = [i, C.c_uint64, _i64p, i64]
     lib.oracle_synth_row_len.restype = i
     lib.oracle_synth_csr.argtypes = [i, C.c_uint64, i, _i64p, i, i, vp, vp, vp]
@@ -253,6 +259,40 @@ def select_kernel(rp, ci, allow_split=1):
 
 def select_slab_cols(cols, nnz, near, cmp_):
     return oracle().oracle_select_slab_cols(cols, nnz, near, cmp_)
+
+
+def select_blocked(rows, cols, nnz, near, cmp_, allow_split=1):
+    return oracle().oracle_select_blocked(rows, cols, nnz, near, cmp_, allow_split)
+
+
+def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=128, n_cta=0, slab_cost=0):
+    """The blocked strategy's plan for this CSR (oracle_pb_plan / oracle_pb_work) as a dict of numpy arrays."""
+    rp, ci = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32)
+    vv = np.ascontiguousarray(vv, np.float32)
+    rows = rp.size - 1
+    tr, tc, _, _ = adaptive_tiles(rp, B, T, CH)
+    tc = np.ascontiguousarray(tc if tc.size else np.zeros(1, np.int32), np.int32)
+    npan = tr.size - 1
+    S = (cols + W - 1) // W
+    nseg = C.c_int64()
+    slab_ptr = np.zeros(S + 1, np.int32)
+    padded = oracle().oracle_pb_plan(rows, cols, rp, ci, vv, npan, tr, tc, CH, W, align, slab_ptr.ctypes.data, None,
+                                     None, None, None, None, C.byref(nseg))
+    val = np.zeros(padded, np.float32)
+    lcol = np.zeros(padded, np.uint16)
+    perm = np.zeros(padded, np.uint16)
+    panel_seg = np.zeros(npan + 1, np.int32)
+    seg = np.zeros((max(nseg.value, 1), 2), np.int32)
+    oracle().oracle_pb_plan(rows, cols, rp, ci, vv, npan, tr, tc, CH, W, align, slab_ptr.ctypes.data, val.ctypes.data,
+                            lcol.ctypes.data, perm.ctypes.data, panel_seg.ctypes.data, seg.ctypes.data, C.byref(nseg))
+    d = {"slab_cols": W, "num_slabs": S, "padded_nnz": int(padded), "num_seg": int(nseg.value), "num_panels": npan,
+         "slab_ptr": slab_ptr, "val": val, "lcol": lcol, "perm": perm, "panel_seg": panel_seg,
+         "seg": seg[:nseg.value], "max_panel_segs": int(np.diff(panel_seg).max()) if npan else 0}
+    if n_cta:
+        work = np.zeros((n_cta, 2), np.int32)
+        oracle().oracle_pb_work(S, slab_ptr, align, n_cta, slab_cost, work.reshape(-1))
+        d["work"] = work
+    return d
 
 
 def column_slab(rp, ci, vv, lo, hi):

@@ -1,0 +1,266 @@
+"""The blocked (column-slab x row-panel, two-pass) strategy: plan bit-exact against the oracle's sequential
+restatement, results within the north_star tolerance of the float64 restatement, bit-reproducible runs, the
+host-buffer pipeline and the selector rule.  CPU part: the oracle's plan, walked the way the two passes walk it,
+reproduces the CSR product (so the restatement itself is pinned to the CSR semantics the other tests pin)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+TOL = 1e-5
+ALPHA, BETA = np.float32(0.85), np.float32(-2.06)
+
+
+def _powerlaw(rng, rows, cols, heavy=3, max_len=20000):
+    lens = np.minimum(rng.zipf(1.6, rows), max_len)
+    if heavy:
+        lens[rng.integers(0, rows, heavy)] = rng.integers(max_len // 4, max_len, heavy)
+    lens[rng.integers(0, rows, rows // 10)] = 0
+    lens[rows // 3: rows // 3 + 3000] = 0        # more empty rows in a row than a panel's item budget
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    # power-law columns (a hot head and a thin tail, as in C2) so that slabs differ in size by orders of magnitude
+    c = np.minimum((rng.random(r.size) ** 5 * cols).astype(np.int32), cols - 1)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    return r, c, v
+
+
+def _walk_plan(d, rp, tr, tc, tn, CH, W, cols, x):
+    """numpy emulation of pass 1 + pass 2 over a plan dict: returns A x in float64."""
+    rows = rp.size - 1
+    slab_of = np.zeros(d["padded_nnz"], np.int64)
+    for s in range(d["num_slabs"]):
+        slab_of[d["slab_ptr"][s]:d["slab_ptr"][s + 1]] = s
+    prod = d["val"].astype(np.float64) * x[np.minimum(slab_of * W + d["lcol"], cols - 1)]
+    y = np.zeros(rows)
+    for p in range(d["num_panels"]):
+        n0 = int(tn[p])
+        n1 = min(int(rp[tr[p] + 1]), n0 + CH) if tc[p] >= 0 else int(rp[tr[p + 1]])
+        n = n1 - n0
+        buf = np.full(n, np.nan)
+        segs = d["seg"][d["panel_seg"][p]:d["panel_seg"][p + 1]]
+        offs = list(segs[:, 1]) + [n]
+        for i, (st, off) in enumerate(segs):
+            ln = offs[i + 1] - off
+            assert ln > 0
+            buf[d["perm"][st:st + ln]] = prod[st:st + ln]
+        assert not np.isnan(buf).any()           # every CSR position of the panel is covered exactly once
+        if tc[p] >= 0:
+            y[tr[p]] += buf.sum()
+        else:
+            for rr in range(tr[p], tr[p + 1]):
+                y[rr] = buf[rp[rr] - n0:rp[rr + 1] - n0].sum()
+    return y
+
+
+@pytest.mark.parametrize("seed,W,B,T,CH", [(0, 1024, 2048, 256, 512), (1, 4096, 512, 64, 1024), (2, 20000, 4096, 1024, 4096)])
+def test_oracle_blocked_plan_reproduces_the_csr_product(seed, W, B, T, CH):
+    rng = np.random.default_rng(seed)
+    rows, cols = 4000, 20000 + seed
+    r, c, v = _powerlaw(rng, rows, cols, max_len=6000)
+    rp, ci, vv = ol.coo_to_csr(rows, r, c, v)
+    d = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=7, slab_cost=300)
+    tr, tc, tn, _ = ol.adaptive_tiles(rp, B, T, CH)
+    x = rng.standard_normal(cols).astype(np.float32)
+    y = _walk_plan(d, rp, tr, tc, tn, CH, W, cols, x)
+    y64, scale = ol.spmv_f64(rp, ci, vv, x)
+    assert np.max(np.abs(y - y64) / np.maximum(scale, 1e-30)) < 1e-12
+    # layout facts: slab starts aligned, ascending; lcol inside the slab; work ranges tile the blocked order
+    assert np.all(d["slab_ptr"] % 128 == 0) and np.all(np.diff(d["slab_ptr"]) >= 0)
+    assert d["lcol"].max() < W
+    w = d["work"]
+    assert w[0, 0] == 0 and w[-1, 1] == d["padded_nnz"] and np.array_equal(w[1:, 0], w[:-1, 1])
+    assert np.all(w % 128 == 0)
+
+
+def test_oracle_select_blocked_rule():
+    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 10, 1000) == 1      # C2
+    assert ol.select_blocked(100_000_000, 100_000_000, 1_000_000_000, 0, 1000) == 1   # C5
+    assert ol.select_blocked(20_000_000, 20_000_000, 540_000_000, 990, 1000) == 0     # C4: banded
+    assert ol.select_blocked(65536, 65536, 1_000_000, 10, 1000) == 0                  # C1: small
+    assert ol.select_blocked(8192, 8192, 6_700_000, 10, 1000) == 0                    # C3b: x fits L1
+    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 10, 1000, 0) == 0   # rows may not be split
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def eng():
+    from hispmv_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def _check_run(eng, idx, rp, ci, vv, rows, cols, rng, alpha=ALPHA, beta=BETA):
+    x = rng.standard_normal(cols).astype(np.float32)
+    y0 = rng.standard_normal(rows).astype(np.float32)
+    y = np.full(rows, np.nan, np.float32)
+    eng.select_matrix(idx)
+    eng.run_kernel(x, y0, y, float(alpha), float(beta))
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, y0, alpha, beta)
+    err, at = ol.max_scaled_error(y, y64, scale)
+    assert err <= TOL, (err, at, eng.matrix_info(idx)["kernel_name"])
+    return y
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,params", [(0, "1024,2048,256,512,300"), (1, "4096,512,64,1024,0"),
+                                         (2, "20000,4096,1024,4096,5000"), (3, "49152,16384,1024,32768,32768")])
+def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
+    """Every integer artefact of the blocked plan (slab starts, blocked order through val / lcol / perm, segment table,
+    pass-1 work ranges) equals the sequential restatement; then the run is within tolerance and bit-reproducible."""
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_BLOCKED", params)
+    W, B, T, CH, cost = (int(t) for t in params.split(","))
+    rng = np.random.default_rng(seed)
+    rows, cols = 30000, 200003 + seed
+    r, c, v = _powerlaw(rng, rows, cols)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_BLOCKED)
+    info = eng.matrix_info(idx)
+    assert info["kernel_name"] == "blocked" and (info["tile_items"], info["long_threshold"], info["chunk_nnz"]) == (B, T, CH)
+    rp, ci, vv = eng.plan_csr(idx)
+    got = eng.plan_blocked(idx)
+    want = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=got["num_work"], slab_cost=cost)
+    for k in ("slab_cols", "num_slabs", "padded_nnz", "num_seg", "num_panels", "max_panel_segs"):
+        assert got[k] == want[k], k
+    for k in ("slab_ptr", "lcol", "perm", "panel_seg", "seg", "work"):
+        assert np.array_equal(got[k], want[k]), k
+    assert np.array_equal(got["val"].view(np.uint32), want["val"].view(np.uint32))
+    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, B, T, CH)
+    tr, tn = eng.plan_tiles(idx)
+    assert np.array_equal(tr, tr2) and np.array_equal(tn, tn2) and np.array_equal(eng.plan_tile_chunks(idx), tc2)
+    assert np.array_equal(eng.plan_split_rows(idx), sp2)
+    assert eng.launches_per_run(idx) == 2
+    y1 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
+    y2 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
+    assert np.array_equal(y1.view(np.uint32), y2.view(np.uint32))
+    _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(8), alpha=1.0, beta=0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["powerlaw", "regular", "short", "hollow", "one_row", "one_col"])
+def test_blocked_within_tolerance(eng, kind, monkeypatch):
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_BLOCKED", "8192,4096,512,2048")
+    rng = np.random.default_rng(sum(map(ord, kind)))
+    rows, cols = 30011, 100003
+    if kind == "powerlaw":
+        r, c, v = _powerlaw(rng, rows, cols)
+    else:
+        if kind == "regular":
+            lens = np.full(rows, 27)
+        elif kind == "short":
+            lens = rng.integers(0, 3, rows)
+        elif kind == "hollow":
+            lens = np.where(rng.random(rows) < 0.8, 0, rng.integers(1, 40, rows))
+        elif kind == "one_row":
+            rows = 1
+            lens = np.array([70000])
+        else:
+            cols = 1
+            lens = rng.integers(0, 2, rows)
+        r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+        c = rng.integers(0, cols, r.size).astype(np.int32)
+        v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_BLOCKED)
+    assert eng.matrix_info(idx)["kernel_name"] == "blocked"
+    rp, ci, vv = eng.plan_csr(idx)
+    _check_run(eng, idx, rp, ci, vv, rows, cols, rng)
+    _check_run(eng, idx, rp, ci, vv, rows, cols, rng, alpha=1.0, beta=0.0)
+
+
+@pytest.mark.gpu
+def test_blocked_device_calls_relu_linear_and_unaligned_x(eng, monkeypatch):
+    """run_dev / linear_dev(+ReLU) / linear() on a blocked matrix; x at an address that is not 16-byte aligned takes
+    the plain-load staging path and gives the same bits."""
+    import torch
+    from hispmv_b200 import capi
+    monkeypatch.setenv("HISPMV_BLOCKED", "16384,8192,1024,4096")
+    rng = np.random.default_rng(5)
+    rows, cols = 40000, 150001
+    r, c, v = _powerlaw(rng, rows, cols)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_BLOCKED)
+    rp, ci, vv = eng.plan_csr(idx)
+    x = rng.standard_normal(cols).astype(np.float32)
+    b = rng.standard_normal(rows).astype(np.float32)
+    s = torch.cuda.current_stream().cuda_stream
+    xd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(b).cuda()
+    y = torch.empty(rows, device="cuda")
+    eng.run_dev(idx, xd, bd, y, float(ALPHA), float(BETA), s)
+    torch.cuda.synchronize()
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, b, ALPHA, BETA)
+    assert ol.max_scaled_error(y.cpu().numpy(), y64, scale)[0] <= TOL
+    big = torch.empty(cols + 1, device="cuda")
+    big[1:].copy_(xd)
+    y_un = torch.empty(rows, device="cuda")
+    eng.run_dev(idx, big[1:], bd, y_un, float(ALPHA), float(BETA), s)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int32), y_un.view(torch.int32))
+    yr = torch.empty(rows, device="cuda")
+    eng.linear_dev(idx, xd, bd, yr, relu=True, stream=s)
+    torch.cuda.synchronize()
+    y64, scale = ol.spmv_f64(rp, ci, vv, x, b, 1.0, 1.0)
+    yh = yr.cpu().numpy()
+    pos = y64 > 1e-4 * np.maximum(scale, 1e-30)
+    assert ol.max_scaled_error(yh[pos], y64[pos], scale[pos])[0] <= TOL
+    assert np.all(yh >= 0) and np.all(yh[y64 < -1e-4 * np.maximum(scale, 1e-30)] == 0)
+    xs = np.concatenate([x, x[::-1].copy(), 2 * x])          # three vectors: both stream lanes of linear()
+    out = eng.linear(idx, xs, b).reshape(3, rows)
+    for k, xv in enumerate((x, x[::-1].copy(), 2 * x)):
+        y64, scale = ol.spmv_f64(rp, ci, vv, xv, b, 1.0, 1.0)
+        assert ol.max_scaled_error(out[k], y64, scale)[0] <= TOL
+
+
+@pytest.mark.gpu
+def test_blocked_host_run_pipelines_panel_ranges(eng):
+    """> 1 M rows: hispmv_run cuts the panels into row ranges (pass 1 once, pass 2 range by range around the bias / y
+    copies); the result is bit-identical to the device-resident call."""
+    import torch
+    from hispmv_b200 import capi
+    rng = np.random.default_rng(21)
+    rows, cols = 1_300_000, 1_100_000
+    lens = rng.integers(0, 7, rows)
+    lens[[5, 700_000]] = [40000, 3000]
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    eng.force_kernel(idx, capi.KERNEL_BLOCKED)
+    info = eng.matrix_info(idx)
+    assert info["kernel_name"] == "blocked" and info["num_tiles"] >= 64
+    rp, ci, vv = eng.plan_csr(idx)
+    y_host = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(3))
+    g = np.random.default_rng(3)
+    x = g.standard_normal(cols).astype(np.float32)
+    y0 = g.standard_normal(rows).astype(np.float32)
+    yd = torch.empty(rows, device="cuda")
+    eng.run_dev(idx, torch.from_numpy(x).cuda(), torch.from_numpy(y0).cuda(), yd, float(ALPHA), float(BETA),
+                torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(yd.cpu().numpy().view(np.uint32), y_host.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_blocked_selector_bit_exact(eng):
+    """The selector sends a scattered-column matrix with >= 1 M columns and >= 16 M nonzeros to the blocked strategy
+    and leaves smaller / narrower ones on the one-pass kernels, exactly as oracle_select_blocked says."""
+    import torch
+    for rows, cols, nnz in ((2_000_000, 1_500_000, 16_500_000), (2_000_000, 900_000, 16_500_000),
+                            (1_000_000, 1_500_000, 8_000_000)):
+        g = torch.Generator(device="cuda").manual_seed(rows + cols)
+        r = torch.randint(0, rows, (nnz,), device="cuda", generator=g, dtype=torch.int32)
+        c = torch.randint(0, cols, (nnz,), device="cuda", generator=g, dtype=torch.int32)
+        v = torch.randn(nnz, device="cuda", generator=g)
+        idx = eng.create_sparse_handle_coo_dev(r, c, v, rows, cols)
+        info = eng.matrix_info(idx)
+        want = ol.select_blocked(rows, cols, nnz, info["probe_near"], info["probe_cmp"])
+        assert (info["kernel_name"] == "blocked") == bool(want), (rows, cols, nnz, info["kernel_name"])
+        if want:
+            pb = eng.plan_blocked(idx, arrays=False)
+            assert pb["slab_cols"] == 49152 and pb["num_slabs"] == (cols + 49151) // 49152
+        rp, ci, vv = eng.plan_csr(idx)
+        _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(1))

@@ -68,6 +68,7 @@ def _load() -> C.CDLL:
         "hispmv_run": (C.c_int, [p, p, p, p, f32, f32]),
         "hispmv_linear": (C.c_int, [p, C.c_int, p, i64, p, p]),
         "hispmv_run_dev": (C.c_int, [p, C.c_int, p, p, p, f32, f32, p]),
+        "hispmv_run_dev_phase": (C.c_int, [p, C.c_int, p, p, p, f32, f32, C.c_int, p]),
         "hispmv_linear_dev": (C.c_int, [p, C.c_int, p, p, p, C.c_int, p]),
         "hispmv_sync": (C.c_int, [p]),
         "hispmv_stream": (C.c_void_p, [p]),
@@ -78,7 +79,7 @@ def _load() -> C.CDLL:
         "hispmv_plan_split_rows": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_tile_chunks": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_blocked_info": (C.c_int, [p, C.c_int, p]),
-        "hispmv_plan_blocked": (C.c_int, [p, C.c_int, p, p, p, p, p, p, p]),
+        "hispmv_plan_blocked": (C.c_int, [p, C.c_int, p, p, p, p, p, p, p, p, p, p]),
         "hispmv_plan_slab_nnz": (i64, [p, C.c_int, C.c_int]),
         "hispmv_plan_slab_csr": (C.c_int, [p, C.c_int, C.c_int, p, p, p]),
         "hispmv_load_mtx": (C.c_int, [p, C.c_char_p]),
@@ -106,7 +107,7 @@ EXPORTED = [
     "hispmv_shard_bounds", "hispmv_set_memory_limit", "hispmv_add_sparse_coo", "hispmv_add_sparse_csr",
     "hispmv_add_dense", "hispmv_add_sparse_coo_dev", "hispmv_add_sparse_csr_dev", "hispmv_add_dense_dev",
     "hispmv_commit", "hispmv_num_matrices", "hispmv_select", "hispmv_force_kernel", "hispmv_run",
-    "hispmv_linear", "hispmv_run_dev", "hispmv_linear_dev", "hispmv_sync", "hispmv_stream", "hispmv_launches_per_run",
+    "hispmv_linear", "hispmv_run_dev", "hispmv_run_dev_phase", "hispmv_linear_dev", "hispmv_sync", "hispmv_stream", "hispmv_launches_per_run",
     "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_plan_blocked_info", "hispmv_plan_blocked", "hispmv_plan_slab_nnz", "hispmv_plan_slab_csr", "hispmv_load_mtx", "hispmv_parse_mtx", "hispmv_parse_mtx_free", "hispmv_multicast_copy", "hispmv_run_xdev", "hispmv_run_dev_mc", "hispmv_run_dev_batch",
     "hispmv_synth_count", "hispmv_synth_shard_bounds", "hispmv_synth_csr", "hispmv_synth_free",
 ]
@@ -117,9 +118,18 @@ def last_error() -> str:
 
 
 def check(status: int, where: str) -> int:
-    """Raise on negative status other than FULL (-1), which callers handle like the reference does."""
-    if status < FULL:
+    """Raise on any negative status (IndexError for a bad matrix index, as the plugin does)."""
+    if status < 0:
         if status == ERR_INDEX:
             raise IndexError(f"{where}: {last_error()}")
         raise HispmvError(status, where, last_error())
     return status
+
+
+def check_handle(status: int, where: str) -> int:
+    """For the calls that hand out a matrix handle (create_*_handle, load_mtx): -1 = "device memory is full" is a
+    return value there, exactly as in the reference (pyhispmv/src/fpga_handle.cpp:192-195,235-238); every other
+    negative status raises."""
+    if status == FULL:
+        return status
+    return check(status, where)

@@ -73,76 +73,137 @@ __global__ void pb_slab_bounds_kernel(const uint16_t* __restrict__ key, int64_t 
   ustart[s] = (int32_t)lo;
 }
 
-// the panel that holds CSR position j: the first t with desc[t].n1 > j (panels cover [0, nnz) in order)
-__device__ __forceinline__ int32_t pb_panel_of(const TileDesc* __restrict__ desc, int64_t np, int32_t j) {
-  int64_t lo = 0, hi = np - 1;
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (__ldg(&desc[mid].n1) <= j) lo = mid + 1; else hi = mid;
-  }
-  return (int32_t)lo;
-}
-
+// blocked copy of entry k of the slab-sorted order; brow[dst] = its row (padding positions keep -1)
 __global__ void pb_scatter_kernel(const uint16_t* __restrict__ key, const uint32_t* __restrict__ idx, int64_t nnz,
-                                  const int32_t* __restrict__ col, const float* __restrict__ val,
-                                  const TileDesc* __restrict__ desc, int64_t np, int32_t W,
-                                  const int32_t* __restrict__ ustart, const int32_t* __restrict__ pstart,
-                                  float* __restrict__ o_val, uint16_t* __restrict__ o_lcol,
-                                  uint16_t* __restrict__ o_perm, int32_t* __restrict__ pan) {
+                                  const int32_t* __restrict__ row_ptr, int32_t rows, const int32_t* __restrict__ col,
+                                  const float* __restrict__ val, int32_t W, const int32_t* __restrict__ ustart,
+                                  const int32_t* __restrict__ pstart, float* __restrict__ o_val,
+                                  uint16_t* __restrict__ o_lcol, int32_t* __restrict__ brow) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= nnz) return;
   const int32_t s = key[k];
   const int32_t j = (int32_t)idx[k];
   const int64_t dst = (int64_t)pstart[s] + (k - ustart[s]);
-  const int32_t p = pb_panel_of(desc, np, j);
+  int32_t lo = 0, hi = rows;  // the row of CSR position j: last r with row_ptr[r] <= j
+  while (hi - lo > 1) {
+    const int32_t mid = (int32_t)(((int64_t)lo + hi) >> 1);
+    if (__ldg(row_ptr + mid) <= j) lo = mid; else hi = mid;
+  }
   o_val[dst] = val[j];
   o_lcol[dst] = (uint16_t)(col[j] - s * W);
-  o_perm[dst] = (uint16_t)(j - __ldg(&desc[p].n0));
-  pan[k] = p;
+  brow[dst] = lo;
 }
 
-__global__ void pb_head_kernel(const uint16_t* __restrict__ key, const int32_t* __restrict__ pan, int64_t nnz,
-                               int32_t* __restrict__ head) {
+// an entry ends a piece when the next blocked position holds another row, is padding, or opens the next group
+__global__ void pb_end_kernel(const int32_t* __restrict__ brow, int64_t padded, int32_t* __restrict__ end) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nnz) return;
-  head[k] = (k == 0 || key[k] != key[k - 1] || pan[k] != pan[k - 1]) ? 1 : 0;
+  if (k >= padded) return;
+  const int32_t r = brow[k];
+  end[k] = (r >= 0 && (((k + 1) % kPbGroup) == 0 || brow[k + 1] != r)) ? 1 : 0;
 }
 
-__global__ void pb_seg_emit_kernel(const uint16_t* __restrict__ key, const int32_t* __restrict__ pan,
-                                   const int32_t* __restrict__ head, const int32_t* __restrict__ segidx, int64_t nnz,
-                                   const int32_t* __restrict__ ustart, const int32_t* __restrict__ pstart, int32_t S,
-                                   int32_t* __restrict__ seg_dst, uint64_t* __restrict__ seg_key,
-                                   int32_t* __restrict__ seg_k) {
+__global__ void pb_pack_kernel(const int32_t* __restrict__ end, const int32_t* __restrict__ pid, int64_t padded,
+                               uint8_t* __restrict__ flags, int32_t* __restrict__ group_base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one byte = four entries
+  if (i * 4 >= padded) return;
+  const int4 e = *reinterpret_cast<const int4*>(end + i * 4);
+  flags[i] = (uint8_t)(e.x | (e.y << 1) | (e.z << 2) | (e.w << 3));
+  if ((i * 4) % kPbGroup == 0) group_base[(i * 4) / kPbGroup] = pid[i * 4];
+}
+
+__global__ void pb_piece_emit_kernel(const int32_t* __restrict__ brow, const int32_t* __restrict__ end,
+                                     const int32_t* __restrict__ pid, int64_t padded,
+                                     const int32_t* __restrict__ pstart, int32_t S, int32_t* __restrict__ piece_row,
+                                     int32_t* __restrict__ piece_slab) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nnz || !head[k]) return;
-  const int32_t i = segidx[k];
-  const int32_t s = key[k];
-  seg_dst[i] = (int32_t)((int64_t)pstart[s] + (k - ustart[s]));
-  seg_key[i] = (uint64_t)pan[k] * (uint64_t)S + (uint64_t)s;
-  seg_k[i] = (int32_t)k;
+  if (k >= padded || !end[k]) return;
+  const int32_t q = pid[k];
+  int32_t lo = 0, hi = S;  // the slab of blocked position k: last s with pstart[s] <= k
+  while (hi - lo > 1) {
+    const int32_t mid = (lo + hi) >> 1;
+    if (__ldg(pstart + mid) <= k) lo = mid; else hi = mid;
+  }
+  piece_row[q] = brow[k];
+  piece_slab[q] = lo;
 }
 
-// length of segment order[q] (segments are contiguous in k: the next head in slab-major order ends it)
-__global__ void pb_seg_len_kernel(const uint32_t* __restrict__ order, const int32_t* __restrict__ seg_k, int64_t nseg,
-                                  int64_t nnz, int32_t* __restrict__ len_sorted) {
+// pieces sorted by row (stable, so a row's pieces stay in slab order): position i of that order belongs to piece order[i]
+__global__ void pb_pcsr_kernel(const uint32_t* __restrict__ order, int64_t np, int32_t* __restrict__ piece_pcsr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < np) piece_pcsr[order[i]] = (int32_t)i;
+}
+
+// prow_ptr[r] = number of pieces whose row is < r
+__global__ void pb_prow_ptr_kernel(const uint32_t* __restrict__ row_sorted, int64_t np, int32_t rows,
+                                   int32_t* __restrict__ prow_ptr) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > rows) return;
+  int64_t lo = 0, hi = np;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)row_sorted[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  prow_ptr[r] = (int32_t)lo;
+}
+
+// the panel that holds position i of the per-row piece order: the first t with desc[t].n1 > i
+__device__ __forceinline__ int32_t pb_panel_of(const TileDesc* __restrict__ desc, int64_t np, int32_t i) {
+  int64_t lo = 0, hi = np - 1;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(&desc[mid].n1) <= i) lo = mid + 1; else hi = mid;
+  }
+  return (int32_t)lo;
+}
+
+__global__ void pb_perm_kernel(const int32_t* __restrict__ piece_pcsr, int64_t np, const TileDesc* __restrict__ desc,
+                               int64_t npan, uint16_t* __restrict__ perm, int32_t* __restrict__ pan) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nseg) return;
-  const int64_t i = order[q];
-  const int64_t end = i + 1 < nseg ? seg_k[i + 1] : nnz;
-  len_sorted[q] = (int32_t)(end - seg_k[i]);
+  if (q >= np) return;
+  const int32_t i = piece_pcsr[q];
+  const int32_t p = pb_panel_of(desc, npan, i);
+  perm[q] = (uint16_t)(i - __ldg(&desc[p].n0));
+  pan[q] = p;
+}
+
+__global__ void pb_head_kernel(const int32_t* __restrict__ slab, const int32_t* __restrict__ pan, int64_t np,
+                               int32_t* __restrict__ head) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= np) return;
+  head[q] = (q == 0 || slab[q] != slab[q - 1] || pan[q] != pan[q - 1]) ? 1 : 0;
+}
+
+__global__ void pb_seg_emit_kernel(const int32_t* __restrict__ slab, const int32_t* __restrict__ pan,
+                                   const int32_t* __restrict__ head, const int32_t* __restrict__ segidx, int64_t np,
+                                   int32_t S, uint64_t* __restrict__ seg_key, int32_t* __restrict__ seg_q) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= np || !head[q]) return;
+  const int32_t i = segidx[q];
+  seg_key[i] = (uint64_t)pan[q] * (uint64_t)S + (uint64_t)slab[q];
+  seg_q[i] = (int32_t)q;
+}
+
+// length of segment order[i] (segments are contiguous in piece ids: the next head ends it)
+__global__ void pb_seg_len_kernel(const uint32_t* __restrict__ order, const int32_t* __restrict__ seg_q, int64_t nseg,
+                                  int64_t np, int32_t* __restrict__ len_sorted) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseg) return;
+  const int64_t o = order[i];
+  const int64_t end = o + 1 < nseg ? seg_q[o + 1] : np;
+  len_sorted[i] = (int32_t)(end - seg_q[o]);
 }
 
 __global__ void pb_seg_final_kernel(const uint64_t* __restrict__ seg_key_sorted, const uint32_t* __restrict__ order,
-                                    const int32_t* __restrict__ seg_dst, const int32_t* __restrict__ G,
+                                    const int32_t* __restrict__ seg_q, const int32_t* __restrict__ G,
                                     const TileDesc* __restrict__ desc, int32_t S, int64_t nseg,
                                     PbSeg* __restrict__ out) {
-  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= nseg) return;
-  const int64_t p = (int64_t)(seg_key_sorted[q] / (uint64_t)S);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseg) return;
+  const int64_t p = (int64_t)(seg_key_sorted[i] / (uint64_t)S);
   PbSeg sg;
-  sg.start = seg_dst[order[q]];
-  sg.off = G[q] - __ldg(&desc[p].n0);  // entries of earlier panels add up to the panel's first CSR position
-  out[q] = sg;
+  sg.start = seg_q[order[i]];
+  sg.off = G[i] - __ldg(&desc[p].n0);  // pieces of earlier panels add up to the panel's first position
+  out[i] = sg;
 }
 
 // panel_seg[p] = number of segments whose panel is < p, p = 0 .. np
@@ -167,29 +228,37 @@ __global__ void pb_max_segs_kernel(const int32_t* __restrict__ panel_seg, int64_
   if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
+int grow(DevBuf& tmp, size_t& have, size_t want) {
+  if (want <= have) return HISPMV_OK;
+  have = want;
+  return tmp.alloc(want);
+}
+
 }  // namespace
 
 void pb_free(PbArrays* a) {
   cudaFree(a->d_slab_ptr);
   cudaFree(a->d_val);
   cudaFree(a->d_lcol);
+  cudaFree(a->d_flags);
+  cudaFree(a->d_group_base);
+  cudaFree(a->d_prow_ptr);
   cudaFree(a->d_perm);
   cudaFree(a->d_panel_seg);
   cudaFree(a->d_seg);
   cudaFree(a->d_work);
-  cudaFree(a->d_prod[0]);
-  cudaFree(a->d_prod[1]);
+  cudaFree(a->d_part[0]);
+  cudaFree(a->d_part[1]);
+  cudaFree(a->d_piece_pcsr);
+  cudaFree(a->d_piece_slab);
   delete[] a->h_slab_ptr;
   *a = PbArrays();
 }
 
-int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
-                    int64_t nnz, const TileDesc* d_desc, int64_t num_panels, int32_t slab_cols, PbArrays* out,
-                    cudaStream_t stream) {
-  (void)d_row_ptr;
-  (void)rows;
+int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
+                    int64_t nnz, int32_t slab_cols, PbArrays* out, cudaStream_t stream) {
   pb_free(out);
-  if (slab_cols < 4 || slab_cols > kPbMaxSlabCols || (slab_cols & 3) || cols <= 0 || nnz <= 0 || num_panels <= 0) {
+  if (slab_cols < 4 || slab_cols > kPbMaxSlabCols || (slab_cols & 3) || cols <= 0 || nnz <= 0 || rows <= 0) {
     set_error("blocked plan: bad slab width or empty matrix");
     return HISPMV_ERR_ARG;
   }
@@ -207,6 +276,7 @@ int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
 
   // ---- stable sort of the CSR positions by slab: slab-major, CSR order inside a slab -----------------------------
   DevBuf key_a, key_b, idx_a, idx_b, tmp, ustart, pstart;
+  size_t tb = 0;
   if ((st = key_a.alloc((size_t)nnz * 2)) || (st = key_b.alloc((size_t)nnz * 2)) || (st = idx_a.alloc((size_t)nnz * 4)) ||
       (st = idx_b.alloc((size_t)nnz * 4)) || (st = ustart.alloc(((size_t)S + 1) * 4)) ||
       (st = pstart.alloc(((size_t)S + 1) * 4)))
@@ -215,24 +285,24 @@ int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
   cub::DoubleBuffer<uint32_t> idx(idx_a.as<uint32_t>(), idx_b.as<uint32_t>());
   pb_key_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(d_col, nnz, W, keys.Current(), idx.Current());
   HISPMV_CUDA(cudaGetLastError());
-  size_t tb = 0;
-  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, idx, nnz, 0, sbits, stream));
-  if ((st = tmp.alloc(tb))) return st;
-  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys, idx, nnz, 0, sbits, stream));
+  size_t need = 0;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, keys, idx, nnz, 0, sbits, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, need, keys, idx, nnz, 0, sbits, stream));
   pb_slab_bounds_kernel<<<blocks_for((int64_t)S + 1, 128), 128, 0, stream>>>(keys.Current(), nnz, S,
                                                                             ustart.as<int32_t>());
   HISPMV_CUDA(cudaGetLastError());
   std::vector<int32_t> h_ustart((size_t)S + 1);
   HISPMV_CUDA(cudaMemcpyAsync(h_ustart.data(), ustart.p, ((size_t)S + 1) * 4, cudaMemcpyDeviceToHost, stream));
   HISPMV_CUDA(cudaStreamSynchronize(stream));
-  // every slab starts at a multiple of kPbAlign in the blocked arrays (128-bit loads never straddle two slabs)
+  // every slab starts at a multiple of kPbGroup in the blocked arrays (a warp's group never straddles two slabs)
   out->h_slab_ptr = new int32_t[(size_t)S + 1];
   int64_t pos = 0;
   for (int32_t s = 0; s < S; ++s) {
     out->h_slab_ptr[s] = (int32_t)pos;
     pos += (int64_t)h_ustart[(size_t)s + 1] - h_ustart[(size_t)s];
-    pos = (pos + kPbAlign - 1) / kPbAlign * kPbAlign;
-    if (pos >= (int64_t)INT32_MAX - kPbAlign) {
+    pos = (pos + kPbGroup - 1) / kPbGroup * kPbGroup;
+    if (pos >= (int64_t)INT32_MAX - kPbGroup) {
       set_error("blocked plan: more than 2^31 entries");
       return HISPMV_ERR_ARG;
     }
@@ -243,49 +313,113 @@ int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
 
   // ---- the blocked copy ------------------------------------------------------------------------------------------
   const size_t slack = 64;  // vector loads of the last group may look past the end
+  const int64_t ngroups = padded / kPbGroup;
   HISPMV_CUDA(cudaMalloc((void**)&out->d_val, ((size_t)padded + slack) * 4));
   HISPMV_CUDA(cudaMalloc((void**)&out->d_lcol, ((size_t)padded + slack) * 2));
-  HISPMV_CUDA(cudaMalloc((void**)&out->d_perm, ((size_t)padded + slack) * 2));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_flags, (size_t)padded / 4 + slack));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_group_base, ((size_t)ngroups + 1) * 4));
   HISPMV_CUDA(cudaMalloc((void**)&out->d_slab_ptr, ((size_t)S + 1) * 4));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_prow_ptr, ((size_t)rows + 1 + 4) * 4));
   HISPMV_CUDA(cudaMemsetAsync(out->d_val, 0, ((size_t)padded + slack) * 4, stream));
   HISPMV_CUDA(cudaMemsetAsync(out->d_lcol, 0, ((size_t)padded + slack) * 2, stream));
-  HISPMV_CUDA(cudaMemsetAsync(out->d_perm, 0, ((size_t)padded + slack) * 2, stream));
+  HISPMV_CUDA(cudaMemsetAsync(out->d_flags, 0, (size_t)padded / 4 + slack, stream));
   HISPMV_CUDA(cudaMemcpyAsync(out->d_slab_ptr, pstart.p, ((size_t)S + 1) * 4, cudaMemcpyDeviceToDevice, stream));
-  DevBuf pan, head, segidx;
-  if ((st = pan.alloc((size_t)nnz * 4))) return st;
-  pb_scatter_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), idx.Current(), nnz, d_col, d_val, d_desc,
-                                                          num_panels, W, ustart.as<int32_t>(), pstart.as<int32_t>(),
-                                                          out->d_val, out->d_lcol, out->d_perm, pan.as<int32_t>());
+  DevBuf brow, end, pid;
+  if ((st = brow.alloc(((size_t)padded + 4) * 4))) return st;
+  HISPMV_CUDA(cudaMemsetAsync(brow.p, 0xff, ((size_t)padded + 4) * 4, stream));  // -1: padding
+  pb_scatter_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), idx.Current(), nnz, d_row_ptr, rows, d_col,
+                                                          d_val, W, ustart.as<int32_t>(), pstart.as<int32_t>(),
+                                                          out->d_val, out->d_lcol, brow.as<int32_t>());
   HISPMV_CUDA(cudaGetLastError());
   HISPMV_CUDA(cudaStreamSynchronize(stream));
-  idx_a.alloc(0);  // the CSR positions are no longer needed
+  key_a.alloc(0);  // the sort buffers are no longer needed
+  key_b.alloc(0);
+  idx_a.alloc(0);
   idx_b.alloc(0);
 
-  // ---- (panel, slab) segments: heads in slab-major order, then ordered by (panel, slab) ---------------------------
-  if ((st = head.alloc((size_t)nnz * 4)) || (st = segidx.alloc((size_t)nnz * 4))) return st;
-  pb_head_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), pan.as<int32_t>(), nnz, head.as<int32_t>());
-  size_t tb2 = 0;
-  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb2, head.as<int32_t>(), segidx.as<int32_t>(), nnz, stream));
-  if (tb2 > tb) {
-    if ((st = tmp.alloc(tb2))) return st;
-    tb = tb2;
-  }
-  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb2, head.as<int32_t>(), segidx.as<int32_t>(), nnz, stream));
+  // ---- pieces ----------------------------------------------------------------------------------------------------
+  if ((st = end.alloc(((size_t)padded + 4) * 4)) || (st = pid.alloc(((size_t)padded + 4) * 4))) return st;
+  pb_end_kernel<<<blocks_for(padded, B), B, 0, stream>>>(brow.as<int32_t>(), padded, end.as<int32_t>());
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, end.as<int32_t>(), pid.as<int32_t>(), padded, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, end.as<int32_t>(), pid.as<int32_t>(), padded, stream));
   int32_t h_last[2] = {0, 0};
-  HISPMV_CUDA(cudaMemcpyAsync(&h_last[0], head.as<int32_t>() + (nnz - 1), 4, cudaMemcpyDeviceToHost, stream));
-  HISPMV_CUDA(cudaMemcpyAsync(&h_last[1], segidx.as<int32_t>() + (nnz - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last[0], end.as<int32_t>() + (padded - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last[1], pid.as<int32_t>() + (padded - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  const int64_t np = (int64_t)h_last[0] + h_last[1];
+  pb_pack_kernel<<<blocks_for(padded / 4, B), B, 0, stream>>>(end.as<int32_t>(), pid.as<int32_t>(), padded, out->d_flags,
+                                                              out->d_group_base);
+  const int32_t np32 = (int32_t)np;
+  HISPMV_CUDA(cudaMemcpyAsync(out->d_group_base + ngroups, &np32, 4, cudaMemcpyHostToDevice, stream));
+  DevBuf prow_a, prow_b, ord_a, ord_b;
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_piece_pcsr, (size_t)std::max<int64_t>(np, 1) * 4));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_piece_slab, (size_t)std::max<int64_t>(np, 1) * 4));
+  if ((st = prow_a.alloc((size_t)np * 4)) || (st = prow_b.alloc((size_t)np * 4)) || (st = ord_a.alloc((size_t)np * 4)) ||
+      (st = ord_b.alloc((size_t)np * 4)))
+    return st;
+  pb_piece_emit_kernel<<<blocks_for(padded, B), B, 0, stream>>>(brow.as<int32_t>(), end.as<int32_t>(), pid.as<int32_t>(),
+                                                                padded, pstart.as<int32_t>(), S, prow_a.as<int32_t>(),
+                                                                out->d_piece_slab);
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  brow.alloc(0);
+  end.alloc(0);
+  pid.alloc(0);
+  // a row's pieces in slab order: stable sort of the piece ids by row
+  cub::DoubleBuffer<uint32_t> prow(prow_a.as<uint32_t>(), prow_b.as<uint32_t>());
+  cub::DoubleBuffer<uint32_t> ord(ord_a.as<uint32_t>(), ord_b.as<uint32_t>());
+  pb_iota_kernel<<<blocks_for(np, B), B, 0, stream>>>(ord.Current(), np);
+  int rbits = 1;
+  while (rbits < 32 && ((int64_t)1 << rbits) < (int64_t)rows) ++rbits;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, prow, ord, np, 0, rbits, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, need, prow, ord, np, 0, rbits, stream));
+  pb_pcsr_kernel<<<blocks_for(np, B), B, 0, stream>>>(ord.Current(), np, out->d_piece_pcsr);
+  pb_prow_ptr_kernel<<<blocks_for((int64_t)rows + 1, B), B, 0, stream>>>(prow.Current(), np, rows, out->d_prow_ptr);
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  out->slab_cols = W;
+  out->num_slabs = S;
+  out->padded_nnz = padded;
+  out->num_pieces = np;
+  return HISPMV_OK;
+}
+
+int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, cudaStream_t stream) {
+  const int64_t np = a->num_pieces;
+  const int32_t S = a->num_slabs;
+  const int B = 256;
+  int st;
+  if (np <= 0 || num_panels <= 0 || !a->d_piece_pcsr) {
+    set_error("blocked plan: no pieces");
+    return HISPMV_ERR_STATE;
+  }
+  DevBuf pan, head, segidx, tmp;
+  size_t tb = 0, need = 0;
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_perm, ((size_t)np + 64) * 2));
+  if ((st = pan.alloc((size_t)np * 4)) || (st = head.alloc((size_t)np * 4)) || (st = segidx.alloc((size_t)np * 4)))
+    return st;
+  pb_perm_kernel<<<blocks_for(np, B), B, 0, stream>>>(a->d_piece_pcsr, np, d_desc, num_panels, a->d_perm,
+                                                      pan.as<int32_t>());
+  pb_head_kernel<<<blocks_for(np, B), B, 0, stream>>>(a->d_piece_slab, pan.as<int32_t>(), np, head.as<int32_t>());
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, head.as<int32_t>(), segidx.as<int32_t>(), np, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, head.as<int32_t>(), segidx.as<int32_t>(), np, stream));
+  int32_t h_last[2] = {0, 0};
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last[0], head.as<int32_t>() + (np - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_last[1], segidx.as<int32_t>() + (np - 1), 4, cudaMemcpyDeviceToHost, stream));
   HISPMV_CUDA(cudaStreamSynchronize(stream));
   const int64_t nseg = (int64_t)h_last[0] + h_last[1];
-  DevBuf seg_dst, seg_k, skey_a, skey_b, ord_a, ord_b, len_sorted, G;
-  if ((st = seg_dst.alloc((size_t)nseg * 4)) || (st = seg_k.alloc((size_t)nseg * 4)) ||
-      (st = skey_a.alloc((size_t)nseg * 8)) || (st = skey_b.alloc((size_t)nseg * 8)) ||
-      (st = ord_a.alloc((size_t)nseg * 4)) || (st = ord_b.alloc((size_t)nseg * 4)) ||
-      (st = len_sorted.alloc((size_t)nseg * 4)) || (st = G.alloc((size_t)nseg * 4)))
+  DevBuf seg_q, skey_a, skey_b, ord_a, ord_b, len_sorted, G;
+  if ((st = seg_q.alloc((size_t)nseg * 4)) || (st = skey_a.alloc((size_t)nseg * 8)) ||
+      (st = skey_b.alloc((size_t)nseg * 8)) || (st = ord_a.alloc((size_t)nseg * 4)) ||
+      (st = ord_b.alloc((size_t)nseg * 4)) || (st = len_sorted.alloc((size_t)nseg * 4)) || (st = G.alloc((size_t)nseg * 4)))
     return st;
-  pb_seg_emit_kernel<<<blocks_for(nnz, B), B, 0, stream>>>(keys.Current(), pan.as<int32_t>(), head.as<int32_t>(),
-                                                           segidx.as<int32_t>(), nnz, ustart.as<int32_t>(),
-                                                           pstart.as<int32_t>(), S, seg_dst.as<int32_t>(),
-                                                           skey_a.as<uint64_t>(), seg_k.as<int32_t>());
+  pb_seg_emit_kernel<<<blocks_for(np, B), B, 0, stream>>>(a->d_piece_slab, pan.as<int32_t>(), head.as<int32_t>(),
+                                                          segidx.as<int32_t>(), np, S, skey_a.as<uint64_t>(),
+                                                          seg_q.as<int32_t>());
   HISPMV_CUDA(cudaGetLastError());
   cub::DoubleBuffer<uint64_t> skeys(skey_a.as<uint64_t>(), skey_b.as<uint64_t>());
   cub::DoubleBuffer<uint32_t> ords(ord_a.as<uint32_t>(), ord_b.as<uint32_t>());
@@ -296,41 +430,34 @@ int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
     const uint64_t top = (uint64_t)num_panels * (uint64_t)S;
     while (kbits < 64 && ((uint64_t)1 << kbits) < top) ++kbits;
   }
-  size_t tb4 = 0;
-  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb4, skeys, ords, nseg, 0, kbits, stream));
-  if (tb4 > tb) {
-    if ((st = tmp.alloc(tb4))) return st;
-    tb = tb4;
-  }
-  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb4, skeys, ords, nseg, 0, kbits, stream));
-  pb_seg_len_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(ords.Current(), seg_k.as<int32_t>(), nseg, nnz,
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, skeys, ords, nseg, 0, kbits, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, need, skeys, ords, nseg, 0, kbits, stream));
+  pb_seg_len_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(ords.Current(), seg_q.as<int32_t>(), nseg, np,
                                                            len_sorted.as<int32_t>());
-  size_t tb5 = 0;
-  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb5, len_sorted.as<int32_t>(), G.as<int32_t>(), nseg, stream));
-  if (tb5 > tb) {
-    if ((st = tmp.alloc(tb5))) return st;
-    tb = tb5;
-  }
-  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb5, len_sorted.as<int32_t>(), G.as<int32_t>(), nseg, stream));
-  HISPMV_CUDA(cudaMalloc((void**)&out->d_seg, ((size_t)nseg + 1) * sizeof(PbSeg)));
-  HISPMV_CUDA(cudaMalloc((void**)&out->d_panel_seg, ((size_t)num_panels + 1) * 4));
-  pb_seg_final_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(skeys.Current(), ords.Current(), seg_dst.as<int32_t>(),
-                                                             G.as<int32_t>(), d_desc, S, nseg, out->d_seg);
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, len_sorted.as<int32_t>(), G.as<int32_t>(), nseg, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, len_sorted.as<int32_t>(), G.as<int32_t>(), nseg, stream));
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_seg, ((size_t)nseg + 1) * sizeof(PbSeg)));
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_panel_seg, ((size_t)num_panels + 1) * 4));
+  pb_seg_final_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(skeys.Current(), ords.Current(), seg_q.as<int32_t>(),
+                                                             G.as<int32_t>(), d_desc, S, nseg, a->d_seg);
   pb_panel_seg_kernel<<<blocks_for(num_panels + 1, B), B, 0, stream>>>(skeys.Current(), nseg, num_panels, S,
-                                                                      out->d_panel_seg);
+                                                                      a->d_panel_seg);
   DevBuf mx;
   if ((st = mx.alloc(sizeof(int)))) return st;
   HISPMV_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
-  pb_max_segs_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(out->d_panel_seg, num_panels, mx.as<int>());
+  pb_max_segs_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(a->d_panel_seg, num_panels, mx.as<int>());
   HISPMV_CUDA(cudaGetLastError());
   int h_mx = 0;
   HISPMV_CUDA(cudaMemcpyAsync(&h_mx, mx.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
   HISPMV_CUDA(cudaStreamSynchronize(stream));
-  out->slab_cols = W;
-  out->num_slabs = S;
-  out->padded_nnz = padded;
-  out->num_seg = nseg;
-  out->max_panel_segs = h_mx;
+  a->num_seg = nseg;
+  a->max_panel_segs = h_mx;
+  cudaFree(a->d_piece_pcsr);
+  cudaFree(a->d_piece_slab);
+  a->d_piece_pcsr = nullptr;
+  a->d_piece_slab = nullptr;
   return HISPMV_OK;
 }
 
@@ -369,7 +496,7 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
         if (budget <= 0 && k > k0 && b != n_cta - 1) break;
       }
       int64_t take = (int64_t)sp[s + 1] - k;
-      if (b != n_cta - 1) take = std::min<int64_t>(take, std::max<int64_t>(kPbAlign, (budget + kPbAlign - 1) / kPbAlign * kPbAlign));
+      if (b != n_cta - 1) take = std::min<int64_t>(take, std::max<int64_t>(kPbGroup, (budget + kPbGroup - 1) / kPbGroup * kPbGroup));
       k += take;
       budget -= take;
       spent += take;
@@ -387,21 +514,71 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
 }
 
 // ================================================================================================================
-// pass 1: prod[k] = val[k] * x[slab(k) * W + lcol[k]], the slab's piece of x staged in shared memory by TMA bulk copies
+// pass 1: one partial sum per piece, the slab's piece of x staged in shared memory by TMA bulk copies
 // ================================================================================================================
 namespace {
 
 constexpr int kExpandThreads = 1024;
+constexpr int kExpandWarps = kExpandThreads / 32;
 constexpr int kBulkPiece = 4096;  // floats per cp.async.bulk (one copy costs its issuing thread ~650 cycles: 12 lanes
                                   // issue the 12 pieces of a 48 K-column slab side by side)
+
+// One warp, one group of 128 consecutive entries (lane l holds entries 4l .. 4l+3: products p[], end flags f).
+// Every piece's total goes to stage[rank of the piece inside the group]; returns the number of pieces.
+// Fixed shuffle tree, so the sums are bit-reproducible.
+__device__ __forceinline__ int group_pieces(const float (&p)[4], uint32_t f, int lane, float* __restrict__ stage) {
+  const unsigned b0 = __ballot_sync(kFullMask, f & 1u), b1 = __ballot_sync(kFullMask, f & 2u);
+  const unsigned b2 = __ballot_sync(kFullMask, f & 4u), b3 = __ballot_sync(kFullMask, f & 8u);
+  const int count = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+  if (count == kPbGroup) {  // every entry is its own piece (hypersparse rows): the products are the partials
+    *reinterpret_cast<float4*>(stage + 4 * lane) = make_float4(p[0], p[1], p[2], p[3]);
+    return count;
+  }
+  // inside the lane: totals of the pieces that end here; `run` = what follows the last end (or all four entries)
+  float out[4];
+  float run = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    run += p[j];
+    out[j] = run;
+    if (f & (1u << j)) run = 0.0f;
+  }
+  // inclusive segmented scan over the lanes of (run, has-an-end): what an open piece has collected up to this lane
+  float sv = run;
+  unsigned sf = f != 0;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const float uv = __shfl_up_sync(kFullMask, sv, d);
+    const unsigned uf = __shfl_up_sync(kFullMask, sf, d);
+    if (lane >= d) {
+      if (!sf) sv += uv;
+      sf |= uf;
+    }
+  }
+  float carry = __shfl_up_sync(kFullMask, sv, 1);  // the open piece's sum over the lanes before this one
+  if (lane == 0) carry = 0.0f;                     // pieces never cross a group
+  const unsigned lt = (1u << lane) - 1u;
+  int rank = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
+  bool first = true;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (f & (1u << j)) {
+      stage[rank++] = first ? carry + out[j] : out[j];
+      first = false;
+    }
+  }
+  return count;
+}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
     pb_expand_kernel(PbPlan P, const float* __restrict__ x, int32_t cols) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  float* s_x = reinterpret_cast<float*>(s_raw);
+  float* s_x = reinterpret_cast<float*>(s_raw);                        // [slab_cols]
+  float* s_stage = s_x + P.slab_cols + (threadIdx.x >> 5) * kPbGroup;  // this warp's 128 partials
   __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int WARPS = THREADS / 32;
   const int2 w = P.work[blockIdx.x];
   if (w.x >= w.y) return;
   if (tid == 0) mbar_init(&bar, 1);
@@ -438,28 +615,38 @@ __global__ void __launch_bounds__(THREADS, 1)
         parity ^= 1u;
       }
       __syncthreads();
+      // groups of this slab's range: warp w takes group g0 + w, g0 + w + WARPS, ...; U groups' loads are in flight at once
       constexpr int U = 4;
-      for (int base = k + tid * 4; base < kend; base += THREADS * 4 * U) {
+      const int g_end = kend / kPbGroup;
+      for (int g = k / kPbGroup + warp; g < g_end; g += WARPS * U) {
         float4 v[U];
         uint2 c[U];
+        uint32_t f[U];
+        int base[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int i = base + u * THREADS * 4;
-          if (i < kend) {
+          const int gu = g + u * WARPS;
+          if (gu < g_end) {
+            const int i = gu * kPbGroup + lane * 4;
             v[u] = ld_stream_f4(P.val + i, ps);
             c[u] = ld_stream_u2(P.lcol + i, ps);
+            f[u] = __ldg(P.flags + (i >> 2));
+            base[u] = __ldg(P.group_base + gu);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int i = base + u * THREADS * 4;
-          if (i < kend) {
-            float4 p;
-            p.x = v[u].x * s_x[c[u].x & 0xffffu];
-            p.y = v[u].y * s_x[c[u].x >> 16];
-            p.z = v[u].z * s_x[c[u].y & 0xffffu];
-            p.w = v[u].w * s_x[c[u].y >> 16];
-            *reinterpret_cast<float4*>(P.prod + i) = p;
+          const int gu = g + u * WARPS;
+          if (gu < g_end) {  // warp-uniform
+            float p[4];
+            p[0] = v[u].x * s_x[c[u].x & 0xffffu];
+            p[1] = v[u].y * s_x[c[u].x >> 16];
+            p[2] = v[u].z * s_x[c[u].y & 0xffffu];
+            p[3] = v[u].w * s_x[c[u].y >> 16];
+            const int count = group_pieces(p, f[u], lane, s_stage);
+            __syncwarp();
+            for (int i = lane; i < count; i += 32) P.part[base[u] + i] = s_stage[i];
+            __syncwarp();
           }
         }
       }
@@ -473,14 +660,15 @@ __global__ void __launch_bounds__(THREADS, 1)
 // ================================================================================================================
 // pass 2: one CTA per panel
 // ================================================================================================================
-constexpr int kReduceThreads = 512;
+constexpr int kReduceThreads = 256;
 constexpr int kSerialRowPb = 16;
+constexpr int kBiasAhead = 4;  // bias values per lane requested before the walk (rows of the warp's first passes)
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
-    pb_reduce_kernel(CsrDev A, PbPlan P, float* __restrict__ y, Epilogue ep) {
+__global__ void __launch_bounds__(THREADS, 4)
+    pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's products, then its row extents
+  float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's partials, then its row extents
   PbSeg* s_seg = reinterpret_cast<PbSeg*>(s_raw + (size_t)P.cap_words * 4);  // [max_panel_segs + 1]
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
@@ -503,11 +691,21 @@ __global__ void __launch_bounds__(THREADS, 2)
     s_seg[nseg].off = n;
   }
   int* s_rp = reinterpret_cast<int*>(s_prod + n);
-  if (!is_long)
-    for (int i = tid; i <= trows; i += THREADS) s_rp[i] = A.row_ptr[d.r0 + i] - d.n0;
+  // rows of the panel are dealt to the warps in blocks: warp w owns rows [beg, end)
+  const int rpw = (trows + WARPS - 1) / WARPS;
+  const int beg = warp * rpw, end = min(trows, beg + rpw);
+  float bias_pre[kBiasAhead];
+  if (!is_long) {
+    for (int i = tid; i <= trows; i += THREADS) s_rp[i] = __ldg(P.prow_ptr + d.r0 + i) - d.n0;
+#pragma unroll
+    for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap the walk
+      const int i = beg + a * 32 + lane;
+      bias_pre[a] = (ep.beta != 0.0f && i < end) ? ep.bias[d.r0 + i] : 0.0f;
+    }
+  }
   __syncthreads();
 
-  // ---- walk the panel's segments: warp w takes the flat range [f0, f1) of the panel's entries in (slab, CSR) order --
+  // ---- walk the panel's segments: warp w takes the flat range [f0, f1) of the panel's pieces in (slab, row) order --
   constexpr int U = 8;
   const int per = (((n + WARPS - 1) / WARPS) + 31) & ~31;
   const int f0 = min(n, warp * per), f1 = min(n, f0 + per);
@@ -541,7 +739,7 @@ __global__ void __launch_bounds__(THREADS, 2)
       p[u] = 0.0f;
       q[u] = 0;
       if (addr[u] >= 0) {
-        p[u] = ld_stream_f1(P.prod + addr[u], ps);
+        p[u] = ld_stream_f1(P.part + addr[u], ps);
         if (!is_long) q[u] = ld_stream_u16(P.perm + addr[u], ps);
       }
     }
@@ -566,17 +764,22 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
   __syncthreads();
 
-  // ---- rows out of the product buffer, in CSR order: warp w owns rows [beg, end) of the panel ----------------------
-  const int rpw = (trows + WARPS - 1) / WARPS;
-  const int beg = warp * rpw, end = min(trows, beg + rpw);
-  for (int base = beg; base < end; base += 32) {
+  // ---- rows out of the buffer, every row's pieces in slab order -----------------------------------------------------
+  int pass = 0;
+  for (int base = beg; base < end; base += 32, ++pass) {
     const int i = base + lane;
     int b = 0, e = 0;
     float bias = 0.0f;
     if (i < end) {
       b = s_rp[i];
       e = s_rp[i + 1];
-      if (ep.beta != 0.0f) bias = ep.bias[d.r0 + i];
+    }
+    if (pass < kBiasAhead) {
+#pragma unroll
+      for (int a = 0; a < kBiasAhead; ++a)
+        if (a == pass) bias = bias_pre[a];
+    } else if (i < end && ep.beta != 0.0f) {
+      bias = ep.bias[d.r0 + i];
     }
     const int len = e - b;
     float s = 0.0f;
@@ -606,11 +809,9 @@ __global__ void __launch_bounds__(THREADS, 2)
 
 }  // namespace
 
-int pb_expand_ctas_per_sm(int32_t slab_cols) { return ((size_t)slab_cols * 4 + 1024) * 2 <= 227 * 1024 ? 2 : 1; }
-
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s) {
   if (P.num_work <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.slab_cols * 4;
+  const size_t smem = (size_t)P.slab_cols * 4 + (size_t)kExpandWarps * kPbGroup * 4;
   static size_t configured = 0;
   if (smem > configured) {
     HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<kExpandThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -623,6 +824,7 @@ int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t
 }
 
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s) {
+  (void)A;
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
   const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.max_panel_segs + 1) * sizeof(PbSeg);
@@ -636,12 +838,12 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
                                      (int)smem));
     configured = smem;
   }
-  pb_reduce_kernel<kReduceThreads><<<(unsigned)count, kReduceThreads, smem, s>>>(A, P, y, ep);
+  pb_reduce_kernel<kReduceThreads><<<(unsigned)count, kReduceThreads, smem, s>>>(P, y, ep);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }
 
-// The blocked strategy pays 16 bytes of streaming per nonzero instead of 8 plus a 32-byte L2 sector per scattered
+// The blocked strategy pays up to 16 bytes of streaming per nonzero instead of 8 plus a 32-byte L2 sector per scattered
 // gather, so it wins when the gathers are scattered (not banded), x is far larger than an SM's L1 (otherwise the
 // gathers hit on chip anyway) and the matrix is large enough to fill two launches.  Integer rule, restated in
 // oracle/oracle.c (oracle_select_blocked).

@@ -98,8 +98,9 @@ struct Matrix {
     if (dense) return (int64_t)local_rows() * ld * 4;
     int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
-    if (pb.d_val)  // val + lcol + perm + one product buffer per stream lane in use + segment table
-      b += pb.padded_nnz * (8 + 4 * (pb.d_prod[1] ? 2 : 1)) + pb.num_seg * 8 + (num_tiles + 1) * 4 + (pb.num_slabs + 1) * 4;
+    if (pb.d_val)  // val + lcol + flags per entry; perm + one partial per stream lane in use per piece; tables
+      b += pb.padded_nnz * 6 + pb.padded_nnz / 4 + pb.padded_nnz / kPbGroup * 4 + pb.num_pieces * (2 + 4 * (pb.d_part[1] ? 2 : 1)) +
+           pb.num_seg * 8 + (num_tiles + 1) * 4 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
     for (auto* sm : slabs) b += sm->device_bytes();
     return b;
   }
@@ -166,23 +167,35 @@ struct DeviceGuard {
 };
 
 int ensure_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
+  // the capacity is dropped to 0 before the old buffers go, so a failed grow can never leave a stale capacity behind
+  // null (or mixed-size) buffers; scratch failures in run paths are CUDA errors, not the "matrix memory full" sentinel
+  auto scratch = [](int st) { return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st; };
   if (n_x > c->cap_x) {
+    c->cap_x = 0;
     for (int l = 0; l < 2; ++l) {
       cudaFree(c->d_x[l]);
       c->d_x[l] = nullptr;
-      HISPMV_CUDA(cudaMalloc((void**)&c->d_x[l], (size_t)n_x * 4));
+    }
+    for (int l = 0; l < 2; ++l) {
+      int st = check_cuda(cudaMalloc((void**)&c->d_x[l], (size_t)n_x * 4), "cudaMalloc(x staging)", __FILE__, __LINE__);
+      if (st != HISPMV_OK) return scratch(st);
     }
     c->cap_x = n_x;
   }
   if (n_y > c->cap_y) {
+    c->cap_y = 0;
     for (int l = 0; l < 2; ++l) {
       cudaFree(c->d_y[l]);
       c->d_y[l] = nullptr;
-      HISPMV_CUDA(cudaMalloc((void**)&c->d_y[l], (size_t)n_y * 4));
     }
     cudaFree(c->d_bias);
     c->d_bias = nullptr;
-    HISPMV_CUDA(cudaMalloc((void**)&c->d_bias, (size_t)n_y * 4));
+    for (int l = 0; l < 2; ++l) {
+      int st = check_cuda(cudaMalloc((void**)&c->d_y[l], (size_t)n_y * 4), "cudaMalloc(y staging)", __FILE__, __LINE__);
+      if (st != HISPMV_OK) return scratch(st);
+    }
+    int st = check_cuda(cudaMalloc((void**)&c->d_bias, (size_t)n_y * 4), "cudaMalloc(bias staging)", __FILE__, __LINE__);
+    if (st != HISPMV_OK) return scratch(st);
     c->cap_y = n_y;
   }
   return HISPMV_OK;
@@ -257,11 +270,11 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     m->tile_items = kPbPanelItems;
     m->long_threshold = kPbLongThreshold;
     m->chunk_nnz = kPbChunkNnz;
-    m->pb_slab_cost = 32768;
+    m->pb_slab_cost = 0;
     if (const char* e = getenv("HISPMV_BLOCKED")) {  // "W,B,T,CH[,SLABCOST]" (development sweeps)
       int w = 0, b = 0, t = 0, ch = 0, sc = -1;
       if (sscanf(e, "%d,%d,%d,%d,%d", &w, &b, &t, &ch, &sc) >= 4 && w >= 1024 && w <= kPbMaxSlabCols && (w & 3) == 0 &&
-          b >= 256 && t >= 16 && b + t <= 56000 && ch >= 512 && ch <= 65535) {
+          b >= 256 && t >= 16 && b + t <= 56000 && ch >= 128 && ch <= 65535) {
         W = w;
         m->tile_items = b;
         m->long_threshold = t;
@@ -272,11 +285,14 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     if (m->nnz <= 0 || m->local_rows() <= 0) {
       m->kernel = HISPMV_KERNEL_EMPTY;
     } else {
-      st = adaptive_tiles_device(m->d_row_ptr, m->local_rows(), m->tile_items, m->long_threshold, m->chunk_nnz,
+      // slab-major copy and its pieces first: the panels are cut over the per-row PIECE counts (prow_ptr), not nonzeros
+      st = pb_order_device(m->d_row_ptr, m->d_col, m->d_val, m->local_rows(), m->cols, m->nnz, W, &m->pb, c->stream);
+      if (st != HISPMV_OK) return st;
+      st = adaptive_tiles_device(m->pb.d_prow_ptr, m->local_rows(), m->tile_items, m->long_threshold, m->chunk_nnz,
                                  &m->num_tiles, &m->d_tile_row, &m->d_tile_chunk, &m->d_split_rows, &m->num_split,
                                  c->stream);
       if (st != HISPMV_OK) return st;
-      st = tile_desc_device(m->d_row_ptr, m->d_tile_row, m->d_tile_chunk, m->num_tiles, m->chunk_nnz, &m->d_desc,
+      st = tile_desc_device(m->pb.d_prow_ptr, m->d_tile_row, m->d_tile_chunk, m->num_tiles, m->chunk_nnz, &m->d_desc,
                             c->stream);
       if (st != HISPMV_OK) return st;
       m->h_tile_row.assign((size_t)m->num_tiles + 1, 0);
@@ -290,12 +306,11 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
       HISPMV_CUDA(fill_u32_device(reinterpret_cast<uint32_t*>(m->d_carry), kCarryEmptyBits, n, c->stream));
       HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, (n + 8) * sizeof(unsigned int)));
       HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, (n + 8) * sizeof(unsigned int), c->stream));
-      st = pb_build_device(m->d_row_ptr, m->d_col, m->d_val, m->local_rows(), m->cols, m->nnz, m->d_desc, m->num_tiles,
-                           W, &m->pb, c->stream);
+      st = pb_segments_device(&m->pb, m->d_desc, m->num_tiles, c->stream);
       if (st != HISPMV_OK) return st;
-      st = pb_make_work(&m->pb, c->sm_count * pb_expand_ctas_per_sm(W), m->pb_slab_cost, c->stream);
+      st = pb_make_work(&m->pb, c->sm_count, m->pb_slab_cost, c->stream);
       if (st != HISPMV_OK) return st;
-      HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_prod[0], ((size_t)m->pb.padded_nnz + 64) * 4));
+      HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_part[0], ((size_t)m->pb.num_pieces + 64) * 4));
     }
   }
   if (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE) {
@@ -527,6 +542,33 @@ int add_csr_common(hispmv_ctx* c, const int32_t* row_ptr, const int32_t* col, co
   float* vl = nullptr;
   if (st == HISPMV_OK) st = alloc_padded_nnz_arrays(col, val, nnz, kind, &cl, &vl, c->stream);
   if (st == HISPMV_OK) st = check_cuda(cudaStreamSynchronize(c->stream), "sync", __FILE__, __LINE__);
+  // the contract of include/hispmv.h: row_ptr non-decreasing from 0 to nnz and every column inside [0, cols) -- refused
+  // otherwise (the COO path refuses bad indices the same way); rows whose columns are out of order are re-sorted by
+  // (column, value) exactly as the COO path orders them, because the column-slab and blocked plans cut rows by column
+  int flags[3] = {0, 0, 0};
+  if (st == HISPMV_OK) st = csr_validate_device(rp, cl, rows, cols, nnz, flags, c->stream);
+  if (st == HISPMV_OK && (flags[0] || flags[1])) {
+    set_error(flags[0] ? "add_sparse_csr: row_ptr must start at 0, be non-decreasing and end at nnz"
+                       : "add_sparse_csr: a column index is outside [0,cols)");
+    st = HISPMV_ERR_ARG;
+  }
+  if (st == HISPMV_OK && flags[2]) {
+    int32_t* d_rows = nullptr;
+    st = check_cuda(cudaMalloc((void**)&d_rows, (size_t)std::max<int64_t>(nnz, 1) * 4), "cudaMalloc(rows)", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = csr_expand_rows_device(rp, rows, nnz, d_rows, c->stream);
+    int32_t *rp2 = nullptr, *cl2 = nullptr;
+    float* vl2 = nullptr;
+    if (st == HISPMV_OK) st = coo_to_csr_device(d_rows, cl, vl, nnz, rows, cols, &rp2, &cl2, &vl2, c->stream);
+    cudaFree(d_rows);
+    if (st == HISPMV_OK) {
+      cudaFree(rp);
+      cudaFree(cl);
+      cudaFree(vl);
+      rp = rp2;
+      cl = cl2;
+      vl = vl2;
+    }
+  }
   if (st != HISPMV_OK) {
     cudaFree(rp);
     cudaFree(cl);
@@ -681,8 +723,8 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       return launch_adaptive(A, P, m->adaptive_threads, d_x, d_y, ep, s);
     }
     case HISPMV_KERNEL_BLOCKED: {
-      if (!m->pb.d_prod[lane]) {  // the second stream lane of linear() gets its own product buffer on first use
-        HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_prod[lane], ((size_t)m->pb.padded_nnz + 64) * 4));
+      if (!m->pb.d_part[lane]) {  // the second stream lane of linear() gets its own partial-sum buffer on first use
+        HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_part[lane], ((size_t)m->pb.num_pieces + 64) * 4));
       }
       PbPlan P;
       P.slab_cols = m->pb.slab_cols;
@@ -691,8 +733,12 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.slab_ptr = m->pb.d_slab_ptr;
       P.val = m->pb.d_val;
       P.lcol = m->pb.d_lcol;
+      P.flags = m->pb.d_flags;
+      P.group_base = m->pb.d_group_base;
       P.perm = m->pb.d_perm;
-      P.prod = m->pb.d_prod[lane];
+      P.prow_ptr = m->pb.d_prow_ptr;
+      P.part = m->pb.d_part[lane];
+      P.num_pieces = m->pb.num_pieces;
       P.num_panels = m->num_tiles;
       P.desc = m->d_desc;
       P.panel_seg = m->pb.d_panel_seg;
@@ -721,10 +767,14 @@ constexpr int kBatchMaxRowNnz = 1 << 16;  // a sub-warp walks a whole row: keep 
 
 int ensure_batch_xi(hispmv_ctx* c, int64_t n) {
   if (n > c->cap_xi) {
+    c->cap_xi = 0;
     for (int l = 0; l < 2; ++l) {
-      HISPMV_CUDA(cudaFree(c->d_xi[l]));
+      cudaFree(c->d_xi[l]);
       c->d_xi[l] = nullptr;
-      HISPMV_CUDA(cudaMalloc((void**)&c->d_xi[l], (size_t)n * 4));
+    }
+    for (int l = 0; l < 2; ++l) {
+      int st = check_cuda(cudaMalloc((void**)&c->d_xi[l], (size_t)n * 4), "cudaMalloc(batch x)", __FILE__, __LINE__);
+      if (st != HISPMV_OK) return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st;
     }
     c->cap_xi = n;
   }
@@ -733,15 +783,19 @@ int ensure_batch_xi(hispmv_ctx* c, int64_t n) {
 
 int ensure_batch_host_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
   if (n_x > c->cap_xb) {
-    HISPMV_CUDA(cudaFree(c->d_xb));
+    c->cap_xb = 0;
+    cudaFree(c->d_xb);
     c->d_xb = nullptr;
-    HISPMV_CUDA(cudaMalloc((void**)&c->d_xb, (size_t)n_x * 4));
+    int st = check_cuda(cudaMalloc((void**)&c->d_xb, (size_t)n_x * 4), "cudaMalloc(batch x staging)", __FILE__, __LINE__);
+    if (st != HISPMV_OK) return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st;
     c->cap_xb = n_x;
   }
   if (n_y > c->cap_yb) {
-    HISPMV_CUDA(cudaFree(c->d_yb));
+    c->cap_yb = 0;
+    cudaFree(c->d_yb);
     c->d_yb = nullptr;
-    HISPMV_CUDA(cudaMalloc((void**)&c->d_yb, (size_t)n_y * 4));
+    int st = check_cuda(cudaMalloc((void**)&c->d_yb, (size_t)n_y * 4), "cudaMalloc(batch y staging)", __FILE__, __LINE__);
+    if (st != HISPMV_OK) return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st;
     c->cap_yb = n_y;
   }
   return HISPMV_OK;
@@ -1002,6 +1056,20 @@ int hispmv_run_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);
   return run_matrix(c, m, d_x, d_bias, d_y, alpha, beta, 0, (cudaStream_t)stream);
+}
+
+int hispmv_run_dev_phase(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha,
+                         float beta, int phases, void* stream) {
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (phases < 1 || phases > 3) {
+    set_error("run_dev_phase: phases must be 1 (products), 2 (row sums) or 3 (both)");
+    return HISPMV_ERR_ARG;
+  }
+  DeviceGuard g(c->device);
+  const bool two_pass = !m->dense && m->kernel == HISPMV_KERNEL_BLOCKED;
+  if (!two_pass && !(phases & 2)) return HISPMV_OK;  // one-pass strategies do all their work in the second phase
+  return run_matrix(c, m, d_x, d_bias, d_y, alpha, beta, 0, (cudaStream_t)stream, 0, 0, -1, 0, two_pass ? phases : 3);
 }
 
 int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
@@ -1340,9 +1408,10 @@ int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_n
     HISPMV_CUDA(cudaMemcpy(tr.data(), m->d_tile_row, (size_t)(m->num_tiles + 1) * 4, cudaMemcpyDeviceToHost));
     if (m->num_tiles)
       HISPMV_CUDA(cudaMemcpy(tc.data(), m->d_tile_chunk, (size_t)m->num_tiles * 4, cudaMemcpyDeviceToHost));
+    const int32_t* offsets = m->kernel == HISPMV_KERNEL_BLOCKED ? m->pb.d_prow_ptr : m->d_row_ptr;  // pieces / nonzeros
     for (int64_t t = 0; t <= m->num_tiles; ++t) {
       int32_t rp = 0;
-      HISPMV_CUDA(cudaMemcpy(&rp, m->d_row_ptr + tr[(size_t)t], 4, cudaMemcpyDeviceToHost));
+      HISPMV_CUDA(cudaMemcpy(&rp, offsets + tr[(size_t)t], 4, cudaMemcpyDeviceToHost));
       tile_nnz[t] = (int64_t)rp + (t < m->num_tiles && tc[(size_t)t] > 0 ? (int64_t)tc[(size_t)t] * m->chunk_nnz : 0);
     }
   }
@@ -1403,12 +1472,13 @@ int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
   out8[4] = m->pb.max_panel_segs;
   out8[5] = m->pb.num_work;
   out8[6] = m->num_tiles;
-  out8[7] = m->pb_slab_cost;
+  out8[7] = m->pb.num_pieces;
   return HISPMV_OK;
 }
 
-int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* perm,
-                        int32_t* panel_seg, int32_t* seg_start_off, int32_t* work) {
+int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint8_t* flags,
+                        int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
+                        int32_t* seg_start_off, int32_t* work) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (m->dense || m->kernel != HISPMV_KERNEL_BLOCKED) {
@@ -1421,7 +1491,10 @@ int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, 
   if (slab_ptr) HISPMV_CUDA(cudaMemcpy(slab_ptr, a.d_slab_ptr, ((size_t)a.num_slabs + 1) * 4, k));
   if (vals) HISPMV_CUDA(cudaMemcpy(vals, a.d_val, (size_t)a.padded_nnz * 4, k));
   if (lcol) HISPMV_CUDA(cudaMemcpy(lcol, a.d_lcol, (size_t)a.padded_nnz * 2, k));
-  if (perm) HISPMV_CUDA(cudaMemcpy(perm, a.d_perm, (size_t)a.padded_nnz * 2, k));
+  if (flags) HISPMV_CUDA(cudaMemcpy(flags, a.d_flags, (size_t)a.padded_nnz / 4, k));
+  if (group_base) HISPMV_CUDA(cudaMemcpy(group_base, a.d_group_base, ((size_t)a.padded_nnz / kPbGroup + 1) * 4, k));
+  if (prow_ptr) HISPMV_CUDA(cudaMemcpy(prow_ptr, a.d_prow_ptr, ((size_t)m->local_rows() + 1) * 4, k));
+  if (perm) HISPMV_CUDA(cudaMemcpy(perm, a.d_perm, (size_t)a.num_pieces * 2, k));
   if (panel_seg) HISPMV_CUDA(cudaMemcpy(panel_seg, a.d_panel_seg, ((size_t)m->num_tiles + 1) * 4, k));
   if (seg_start_off) HISPMV_CUDA(cudaMemcpy(seg_start_off, a.d_seg, (size_t)a.num_seg * 8, k));
   if (work) HISPMV_CUDA(cudaMemcpy(work, a.d_work, (size_t)a.num_work * 8, k));

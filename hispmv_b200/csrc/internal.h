@@ -107,6 +107,13 @@ int alloc_padded_nnz_arrays(const int32_t* src_col, const float* src_val, int64_
 int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int n_parts, int32_t* h_bounds,
                         cudaStream_t stream);
 
+// Caller-supplied CSR: h_flags3 = { row_ptr not monotone within [0, nnz], a column outside [0, cols), a row whose columns
+// are not non-decreasing }.  csr_expand_rows_device writes the row index of every entry (for the re-sort).
+int csr_validate_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, int32_t cols, int64_t nnz,
+                        int* h_flags3, cudaStream_t stream);
+int csr_expand_rows_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int32_t* d_rows_out,
+                           cudaStream_t stream);
+
 // Adaptive tiles; arrays cudaMalloc'ed by the callee.  d_split_rows: rows with more than one LONG chunk.
 int adaptive_tiles_device(const int32_t* d_row_ptr, int32_t rows, int32_t stream_items, int32_t long_threshold,
                           int32_t chunk_nnz, int64_t* num_tiles, int32_t** d_tile_row, int32_t** d_tile_chunk,
@@ -179,71 +186,83 @@ bool merge_tile_items_supported(int tile_items);
 // ---- blocked.cu: column-blocked two-pass SpMV (x gathers served from shared memory) --------------------------------
 // For matrices whose x gathers have no locality (power-law / uniform columns, x far larger than L1) a scattered 4-byte
 // gather costs a whole 32-byte L2 sector, and the L2's sector rate -- not HBM -- bounds the one-pass kernels (DESIGN.md
-// section 4).  The blocked strategy removes the gathers from L2 altogether:
+// section 4; cuSPARSE sits on the same ceiling).  The blocked strategy takes the gathers out of L2 altogether:
 //   expand  (pass 1)  the nonzeros are stored a second time in SLAB-MAJOR order (slab = slab_cols consecutive columns,
-//                     inside a slab in CSR order); a CTA keeps the slab's piece of x in shared memory (one TMA bulk load)
-//                     and streams val / 16-bit local column -> prod[k] = val[k] * x_slab[lcol[k]], all coalesced.
-//   reduce  (pass 2)  rows are cut into PANELS (the adaptive tiles with a larger budget: STREAM panels of short rows,
-//                     LONG panels = chunks of long rows); a panel's products are the (panel, slab) SEGMENTS -- contiguous
-//                     runs of prod[] -- which a CTA walks in slab order, dropping each product at its CSR position inside
-//                     the panel (16-bit perm) in shared memory, then sums the rows in CSR order (deterministic, the same
-//                     order as a sequential CSR SpMV) and applies alpha / beta / ReLU.  LONG panels just add up their
-//                     segments and meet through the split-row carries of the adaptive kernel.
-// Traffic: 4 + 2 + 4 bytes per nonzero in pass 1, 4 + 2 in pass 2 (16 B against the 8 B of CSR) -- all of it streaming.
+//                     inside a slab in CSR order, every slab padded to a multiple of kPbGroup entries); a CTA keeps the
+//                     slab's piece of x in shared memory (TMA bulk loads) and streams val / 16-bit local column.
+//                     Consecutive entries of one row inside one 128-entry group form a PIECE; a warp multiplies a group,
+//                     adds up every piece with a segmented shuffle scan and writes one partial sum per piece --
+//                     a long row costs one partial per slab and group, a hypersparse row one per nonzero.
+//   reduce  (pass 2)  rows are cut into PANELS (the adaptive tiles over the per-row piece counts: STREAM panels of rows
+//                     with few pieces, LONG panels = chunks of a row with very many); a panel's partials are the
+//                     (panel, slab) SEGMENTS -- runs of consecutive piece ids -- which a CTA walks in slab order,
+//                     dropping each partial at its place in the panel's per-row order (16-bit perm) in shared memory,
+//                     then sums the rows in that order (deterministic) and applies alpha / beta / ReLU.
+// Traffic: 4 + 2 + 0.25 bytes per nonzero plus 4 per piece in pass 1, 4 + 2 per piece in pass 2 -- all of it streaming.
 struct PbSeg {
-  int32_t start;  // first entry of the segment in slab-major (blocked) order
-  int32_t off;    // number of entries of the same panel in earlier slabs (the segment's offset in the panel's walk)
+  int32_t start;  // first piece id of the segment (piece ids follow the slab-major order)
+  int32_t off;    // number of pieces of the same panel in earlier slabs (the segment's offset in the panel's walk)
 };
 struct PbPlan {
   int32_t slab_cols = 0, num_slabs = 0;
-  int64_t padded_nnz = 0;              // length of the blocked arrays: every slab starts at a multiple of kPbAlign
+  int64_t padded_nnz = 0;              // length of the blocked arrays: every slab starts at a multiple of kPbGroup
   const int32_t* slab_ptr = nullptr;   // num_slabs+1 starts in blocked order (device)
   const float* val = nullptr;          // blocked order; padding entries are 0
   const uint16_t* lcol = nullptr;      // column - slab * slab_cols
-  const uint16_t* perm = nullptr;      // STREAM panels: CSR position - the panel's first CSR position
-  float* prod = nullptr;               // pass 1 output / pass 2 input
+  const uint8_t* flags = nullptr;      // padded_nnz/4: bit j of byte i = entry 4i+j ends a piece
+  const int32_t* group_base = nullptr; // padded_nnz/kPbGroup + 1: pieces that end before each group
+  const uint16_t* perm = nullptr;      // per piece: position in its row's piece order - the panel's first position
+  const int32_t* prow_ptr = nullptr;   // rows+1: CSR-style offsets of the pieces of every row
+  float* part = nullptr;               // one partial sum per piece: pass 1 output / pass 2 input
+  int64_t num_pieces = 0;
   int64_t num_panels = 0;
-  const TileDesc* desc = nullptr;      // the panels (adaptive tiles)
+  const TileDesc* desc = nullptr;      // the panels (adaptive tiles over prow_ptr)
   const int32_t* panel_seg = nullptr;  // num_panels+1 offsets into seg[]
   const PbSeg* seg = nullptr;          // non-empty (panel, slab) segments, panel-major then slab
   int32_t max_panel_segs = 0;
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
   int32_t num_work = 0;
-  int32_t cap_words = 0;               // shared-memory words a STREAM panel needs (products + row extents)
+  int32_t cap_words = 0;               // shared-memory words a STREAM panel needs (partials + row extents)
   int64_t panel_begin = 0, panel_count = -1;  // pass 2: launch only these panels (host-buffer pipeline)
   float* carry = nullptr;              // split LONG rows: as in AdaptivePlan
   unsigned int* counter = nullptr;
 };
-constexpr int32_t kPbAlign = 128;
-constexpr int32_t kPbMaxSlabCols = 57344;  // 224 KB of x: the largest slab one CTA's shared memory can hold
-// owned device arrays of a blocked plan (built by pb_build_device, freed by pb_free)
+constexpr int32_t kPbGroup = 128;          // entries a warp handles per step: 4 per lane
+constexpr int32_t kPbMaxSlabCols = 53248;  // 208 KB of x: the largest slab next to the per-warp staging of pass 1
+// owned device arrays of a blocked plan (built by pb_order_device + pb_segments_device, freed by pb_free)
 struct PbArrays {
   int32_t slab_cols = 0, num_slabs = 0;
-  int64_t padded_nnz = 0, num_seg = 0;
+  int64_t padded_nnz = 0, num_pieces = 0, num_seg = 0;
   int32_t max_panel_segs = 0;
   int32_t* d_slab_ptr = nullptr;
   float* d_val = nullptr;
   uint16_t* d_lcol = nullptr;
+  uint8_t* d_flags = nullptr;
+  int32_t* d_group_base = nullptr;
+  int32_t* d_prow_ptr = nullptr;
   uint16_t* d_perm = nullptr;
   int32_t* d_panel_seg = nullptr;
   PbSeg* d_seg = nullptr;
   int2* d_work = nullptr;
   int32_t num_work = 0;
-  float* d_prod[2] = {nullptr, nullptr};  // one per stream lane, the second allocated on first use
+  float* d_part[2] = {nullptr, nullptr};  // one per stream lane, the second allocated on first use
   int32_t* h_slab_ptr = nullptr;          // host copy (num_slabs+1), new[]
+  int32_t* d_piece_pcsr = nullptr;        // between the two build stages only
+  int32_t* d_piece_slab = nullptr;
 };
 void pb_free(PbArrays* a);
-// Build the blocked copy of a device CSR whose panels are `d_desc` (adaptive tiles).  Restated in oracle/ (oracle_pb_plan).
-int pb_build_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
-                    int64_t nnz, const TileDesc* d_desc, int64_t num_panels, int32_t slab_cols, PbArrays* out,
-                    cudaStream_t stream);
+// Stage 1: the blocked copy of a device CSR, its pieces and prow_ptr.  Stage 2 (after the panels have been cut over
+// prow_ptr with adaptive_tiles_device / tile_desc_device): perm and the segment table.  Restated in oracle/
+// (oracle_pb_order, oracle_pb_segments).
+int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
+                    int64_t nnz, int32_t slab_cols, PbArrays* out, cudaStream_t stream);
+int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, cudaStream_t stream);
 // pass-1 work ranges for `n_cta` resident CTAs: contiguous, balanced by entries + slab_cost per slab (re)load
 int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream);
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
-int pb_expand_ctas_per_sm(int32_t slab_cols);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
-constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 16384, kPbLongThreshold = 1024, kPbChunkNnz = 32768;
+constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 8192, kPbLongThreshold = 4096, kPbChunkNnz = 8192;
 int select_blocked(int32_t rows, int32_t cols, int64_t nnz, const ColProbe& probe, int allow_split_rows);
 
 // ---- batch.cu: several right-hand sides in one pass over A (x interleaved as xi[c * K + k], K = batch_width(nv)) ----

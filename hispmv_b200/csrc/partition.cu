@@ -472,6 +472,69 @@ int shard_bounds_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// CSR handed in by the caller (hispmv_add_sparse_csr[_dev]): the kernels assume row_ptr non-decreasing from 0 to nnz,
+// 0 <= col < cols, and columns non-decreasing inside a row (the column-slab and blocked plans cut rows by column).
+// One warp per row checks all three; flags: [0] row_ptr broken, [1] column out of range, [2] a row's columns out of
+// order (the caller then re-sorts through the COO path, which orders entries like the reference's std::sort).
+// ------------------------------------------------------------------------------------------------
+namespace {
+__global__ void csr_validate_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ col, int32_t rows,
+                                    int32_t cols, int64_t nnz, int* __restrict__ flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const int64_t b = rp[r], e = rp[r + 1];
+    if (b > e || b < 0 || e > nnz) {
+      if (lane == 0) flags[0] = 1;
+      continue;
+    }
+    for (int64_t j = b + lane; j < e; j += 32) {
+      const int32_t c = col[j];
+      if (c < 0 || c >= cols) flags[1] = 1;
+      if (j + 1 < e && col[j + 1] < c) flags[2] = 1;
+    }
+  }
+}
+__global__ void csr_expand_rows_kernel(const int32_t* __restrict__ rp, int32_t rows, int64_t nnz,
+                                       int32_t* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  int64_t lo = 0, hi = rows;  // the row of entry j: last r with rp[r] <= j
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)rp[mid] <= j) lo = mid; else hi = mid;
+  }
+  out[j] = (int32_t)lo;
+}
+}  // namespace
+
+int csr_validate_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, int32_t cols, int64_t nnz,
+                        int* h_flags3, cudaStream_t stream) {
+  h_flags3[0] = h_flags3[1] = h_flags3[2] = 0;
+  if (rows <= 0) return HISPMV_OK;
+  DevBuf f;
+  int st;
+  if ((st = f.alloc(3 * sizeof(int)))) return st;
+  HISPMV_CUDA(cudaMemsetAsync(f.p, 0, 3 * sizeof(int), stream));
+  const int grid = (int)std::min<int64_t>(blocks_for((int64_t)rows * 32, 256), 148 * 32);
+  csr_validate_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_col, rows, cols, nnz, f.as<int>());
+  HISPMV_CUDA(cudaGetLastError());
+  HISPMV_CUDA(cudaMemcpyAsync(h_flags3, f.p, 3 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  return HISPMV_OK;
+}
+
+int csr_expand_rows_device(const int32_t* d_row_ptr, int32_t rows, int64_t nnz, int32_t* d_rows_out,
+                           cudaStream_t stream) {
+  if (nnz > 0) {
+    csr_expand_rows_kernel<<<blocks_for(nnz, 256), 256, 0, stream>>>(d_row_ptr, rows, nnz, d_rows_out);
+    HISPMV_CUDA(cudaGetLastError());
+  }
+  return HISPMV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Adaptive, row-aligned tiling (see AdaptivePlan in internal.h; restated in oracle_adaptive_tiles).
 //   w_r = 0 for long rows (len >= T), 1 + len otherwise;  S = exclusive prefix sum of w
 //   a short row r opens a STREAM tile when r == 0, when row r-1 is long, or when S_r / B != S_{r-1} / B

@@ -14,7 +14,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import capi
-from .capi import lib, check
+from .capi import lib, check, check_handle
 
 
 def _np(a, dtype) -> np.ndarray:
@@ -25,12 +25,19 @@ def _ptr(a: np.ndarray) -> C.c_void_p:
     return C.c_void_p(a.ctypes.data)
 
 
-def _dptr(t) -> C.c_void_p:
-    """Device pointer of a torch CUDA tensor (None -> NULL)."""
+def _dptr(t, n: int = -1, what: str = "tensor", f32: bool = False, device: int = -1) -> C.c_void_p:
+    """Device pointer of a torch CUDA tensor (None -> NULL); n >= 0 also checks the element count, f32 the dtype and
+    device >= 0 the GPU it lives on -- a short vector would otherwise be an out-of-bounds access inside the kernel."""
     if t is None:
         return C.c_void_p(0)
     if not t.is_cuda or not t.is_contiguous():
-        raise ValueError("expected a contiguous CUDA tensor")
+        raise ValueError(f"{what}: expected a contiguous CUDA tensor")
+    if f32 and str(t.dtype) != "torch.float32":
+        raise TypeError(f"{what}: expected float32, got {t.dtype}")
+    if device >= 0 and t.device.index != device:
+        raise ValueError(f"{what}: lives on cuda:{t.device.index}, the engine on cuda:{device}")
+    if n >= 0 and t.numel() < n:
+        raise ValueError(f"{what}: {t.numel()} elements, the matrix needs {n}")
     return C.c_void_p(t.data_ptr())
 
 
@@ -65,14 +72,30 @@ class Engine:
         a = _np(flattened_dense_values, np.float32).reshape(-1)
         if a.size < rows * cols:
             raise ValueError("flattened_dense_values is shorter than rows*cols")
-        return check(lib.hispmv_add_dense(self._ctx, _ptr(a), rows, cols), "create_dense_handle")
+        return check_handle(lib.hispmv_add_dense(self._ctx, _ptr(a), rows, cols), "create_dense_handle")
 
     def create_sparse_handle(self, coo_rows, coo_cols, coo_values, rows: int, cols: int) -> int:
         r, c, v = _np(coo_rows, np.int32), _np(coo_cols, np.int32), _np(coo_values, np.float32)
         if not (r.size == c.size == v.size):
             raise ValueError("coo_rows, coo_cols and coo_values differ in length")
-        return check(lib.hispmv_add_sparse_coo(self._ctx, _ptr(r), _ptr(c), _ptr(v), r.size, rows, cols),
+        return check_handle(lib.hispmv_add_sparse_coo(self._ctx, _ptr(r), _ptr(c), _ptr(v), r.size, rows, cols),
                      "create_sparse_handle")
+
+    def _shape(self, matrix_idx: int):
+        """(cols, local rows) of a matrix, cached (shapes never change after creation)."""
+        cache = self.__dict__.setdefault("_shapes", {})
+        if matrix_idx not in cache:
+            info = self.matrix_info(matrix_idx)
+            cache[matrix_idx] = (info["cols"], info["row_end"] - info["row_begin"])
+        return cache[matrix_idx]
+
+    def _vecs(self, matrix_idx: int, x, bias, y, beta=1.0):
+        """Device pointers of x / bias / y after checking them against the matrix's shape."""
+        cols, n_y = self._shape(matrix_idx)
+        dev = self.device_id
+        if bias is None and beta != 0.0:
+            raise ValueError("bias is required when beta != 0")
+        return (_dptr(x, cols, "x", True, dev), _dptr(bias, n_y, "bias", True, dev), _dptr(y, n_y, "y", True, dev))
 
     def load_matrices(self) -> None:
         check(lib.hispmv_commit(self._ctx), "load_matrices")
@@ -87,13 +110,22 @@ class Engine:
         if not (isinstance(y, np.ndarray) and y.dtype == np.float32 and y.flags.c_contiguous):
             raise TypeError("y must be a C-contiguous float32 numpy array (it is written in place)")
         xs, bs = _np(x, np.float32), _np(bias, np.float32)
+        sel = getattr(self, "_selected", None)
+        if sel is not None:
+            cols, n_y = self._shape(sel)
+            if xs.size < cols or bs.size < n_y or y.size < n_y:
+                raise ValueError(f"run_kernel: the selected matrix needs x[{cols}], bias[{n_y}], y[{n_y}]; got "
+                                 f"{xs.size}, {bs.size}, {y.size}")
         check(lib.hispmv_run(self._ctx, _ptr(xs), _ptr(bs), _ptr(y), alpha, beta), "run_kernel")
 
     def linear(self, matrix_idx: int, x, bias) -> np.ndarray:
-        info = self.matrix_info(matrix_idx)
+        cols, n_y = self._shape(matrix_idx)
         xs, bs = _np(x, np.float32).reshape(-1), _np(bias, np.float32)
-        n_y = info["row_end"] - info["row_begin"]
-        num_vecs = xs.size // info["cols"]
+        if cols <= 0:
+            raise ValueError("linear: the matrix has no columns")
+        if bs.size < n_y:
+            raise ValueError(f"linear: bias has {bs.size} entries, the matrix {n_y} rows")
+        num_vecs = xs.size // cols
         y = np.empty(num_vecs * n_y, dtype=np.float32)
         check(lib.hispmv_linear(self._ctx, matrix_idx, _ptr(xs), xs.size, _ptr(bs), _ptr(y)), "linear")
         return y
@@ -101,22 +133,22 @@ class Engine:
     # ---- beyond the reference: CSR / device inputs, plans ---------------------------------------------
     def create_sparse_handle_csr(self, row_ptr, col_idx, values, rows: int, cols: int) -> int:
         rp, ci, v = _np(row_ptr, np.int32), _np(col_idx, np.int32), _np(values, np.float32)
-        return check(lib.hispmv_add_sparse_csr(self._ctx, _ptr(rp), _ptr(ci), _ptr(v), rows, cols),
+        return check_handle(lib.hispmv_add_sparse_csr(self._ctx, _ptr(rp), _ptr(ci), _ptr(v), rows, cols),
                      "create_sparse_handle_csr")
 
     def create_sparse_handle_csr_dev(self, d_row_ptr: int, d_col: int, d_val: int, rows: int, cols: int) -> int:
-        return check(lib.hispmv_add_sparse_csr_dev(self._ctx, C.c_void_p(d_row_ptr), C.c_void_p(d_col),
+        return check_handle(lib.hispmv_add_sparse_csr_dev(self._ctx, C.c_void_p(d_row_ptr), C.c_void_p(d_col),
                                                    C.c_void_p(d_val), rows, cols), "create_sparse_handle_csr_dev")
 
     def create_sparse_handle_coo_dev(self, rows_t, cols_t, vals_t, rows: int, cols: int) -> int:
-        return check(lib.hispmv_add_sparse_coo_dev(self._ctx, _dptr(rows_t), _dptr(cols_t), _dptr(vals_t),
+        return check_handle(lib.hispmv_add_sparse_coo_dev(self._ctx, _dptr(rows_t), _dptr(cols_t), _dptr(vals_t),
                                                    rows_t.numel(), rows, cols), "create_sparse_handle_coo_dev")
 
     def create_dense_handle_dev(self, a_t, rows: int, cols: int) -> int:
-        return check(lib.hispmv_add_dense_dev(self._ctx, _dptr(a_t), rows, cols), "create_dense_handle_dev")
+        return check_handle(lib.hispmv_add_dense_dev(self._ctx, _dptr(a_t), rows, cols), "create_dense_handle_dev")
 
     def load_mtx(self, path: str) -> int:
-        return check(lib.hispmv_load_mtx(self._ctx, path.encode()), "load_mtx")
+        return check_handle(lib.hispmv_load_mtx(self._ctx, path.encode()), "load_mtx")
 
     def force_kernel(self, matrix_idx: int, kernel: int, lanes: int = 0) -> None:
         check(lib.hispmv_force_kernel(self._ctx, matrix_idx, kernel, lanes), "force_kernel")
@@ -124,29 +156,41 @@ class Engine:
     def run_dev(self, matrix_idx: int, x, bias, y, alpha: float = 1.0, beta: float = 0.0, stream: int = 0) -> None:
         """y = alpha*A@x + beta*bias on torch CUDA tensors, asynchronous on `stream` (a cudaStream_t as int;
         0 is the CUDA default stream, `self.stream` the engine's own)."""
-        check(lib.hispmv_run_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), alpha, beta,
-                                 C.c_void_p(stream)), "run_dev")
+        px, pb, py = self._vecs(matrix_idx, x, bias, y, beta)
+        check(lib.hispmv_run_dev(self._ctx, matrix_idx, px, pb, py, alpha, beta, C.c_void_p(stream)), "run_dev")
+
+    def run_dev_phase(self, matrix_idx: int, x, bias, y, alpha: float, beta: float, phases: int, stream: int = 0) -> None:
+        """run_dev one phase at a time (hispmv_run_dev_phase): 1 = products (blocked matrices), 2 = row sums, 3 = both."""
+        px, pb, py = self._vecs(matrix_idx, x, bias, y, beta if phases & 2 else 0.0)
+        check(lib.hispmv_run_dev_phase(self._ctx, matrix_idx, px, pb, py, alpha, beta, phases, C.c_void_p(stream)),
+              "run_dev_phase")
 
     def linear_dev(self, matrix_idx: int, x, bias, y, relu: bool = False, stream: int = 0) -> None:
-        check(lib.hispmv_linear_dev(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), int(relu),
-                                    C.c_void_p(stream)), "linear_dev")
+        px, pb, py = self._vecs(matrix_idx, x, bias, y, 0.0)
+        check(lib.hispmv_linear_dev(self._ctx, matrix_idx, px, pb, py, int(relu), C.c_void_p(stream)), "linear_dev")
 
     def run_dev_mc(self, matrix_idx: int, x, bias, mc_y: int, alpha: float = 1.0, beta: float = 0.0,
                    relu: bool = False, stream: int = 0) -> None:
         """As run_dev, but y goes through `mc_y`, the NVSwitch multicast address of this rank's first row inside a
         vector replicated on every GPU: the results land on all ranks (the all-gather of a chained layer fused into
         the producing kernel, hispmv_run_dev_mc).  Peers need a barrier before they read."""
-        check(lib.hispmv_run_dev_mc(self._ctx, matrix_idx, _dptr(x), _dptr(bias), C.c_void_p(mc_y), alpha, beta,
-                                    int(relu), C.c_void_p(stream)), "run_dev_mc")
+        px, pb, _ = self._vecs(matrix_idx, x, bias, None, beta)
+        check(lib.hispmv_run_dev_mc(self._ctx, matrix_idx, px, pb, C.c_void_p(mc_y), alpha, beta, int(relu),
+                                    C.c_void_p(stream)), "run_dev_mc")
 
     def run_dev_batch(self, matrix_idx: int, x, bias, y, alpha: float = 1.0, beta: float = 0.0, relu: bool = False,
                       stream: int = 0) -> None:
         """Several right-hand sides in one pass over the matrix: x is (num_vecs, cols), y (num_vecs, local rows), both
         contiguous CUDA tensors (hispmv_run_dev_batch)."""
-        if x.dim() != 2 or y.dim() != 2 or x.shape[0] != y.shape[0]:
-            raise ValueError("expected x (num_vecs, cols) and y (num_vecs, rows)")
-        check(lib.hispmv_run_dev_batch(self._ctx, matrix_idx, _dptr(x), _dptr(bias), _dptr(y), int(x.shape[0]), alpha,
-                                       beta, int(relu), C.c_void_p(stream)), "run_dev_batch")
+        cols, n_y = self._shape(matrix_idx)
+        if x.dim() != 2 or y.dim() != 2 or x.shape[0] != y.shape[0] or x.shape[1] != cols or y.shape[1] != n_y:
+            raise ValueError(f"expected x (num_vecs, {cols}) and y (num_vecs, {n_y})")
+        if bias is None and beta != 0.0:
+            raise ValueError("bias is required when beta != 0")
+        dev = self.device_id
+        check(lib.hispmv_run_dev_batch(self._ctx, matrix_idx, _dptr(x, -1, "x", True, dev),
+                                       _dptr(bias, n_y, "bias", True, dev), _dptr(y, -1, "y", True, dev),
+                                       int(x.shape[0]), alpha, beta, int(relu), C.c_void_p(stream)), "run_dev_batch")
 
     @property
     def stream(self) -> int:
@@ -205,18 +249,22 @@ class Engine:
         o = np.zeros(8, np.int64)
         check(lib.hispmv_plan_blocked_info(self._ctx, matrix_idx, _ptr(o)), "plan_blocked_info")
         d = {"slab_cols": int(o[0]), "num_slabs": int(o[1]), "padded_nnz": int(o[2]), "num_seg": int(o[3]),
-             "max_panel_segs": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "slab_cost": int(o[7])}
+             "max_panel_segs": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "num_pieces": int(o[7])}
         if arrays:
+            n_y = self._shape(matrix_idx)[1]
             d["slab_ptr"] = np.empty(d["num_slabs"] + 1, np.int32)
             d["val"] = np.empty(d["padded_nnz"], np.float32)
             d["lcol"] = np.empty(d["padded_nnz"], np.uint16)
-            d["perm"] = np.empty(d["padded_nnz"], np.uint16)
+            d["flags"] = np.empty(d["padded_nnz"] // 4, np.uint8)
+            d["group_base"] = np.empty(d["padded_nnz"] // 128 + 1, np.int32)
+            d["prow_ptr"] = np.empty(n_y + 1, np.int32)
+            d["perm"] = np.empty(d["num_pieces"], np.uint16)
             d["panel_seg"] = np.empty(d["num_panels"] + 1, np.int32)
             d["seg"] = np.empty((d["num_seg"], 2), np.int32)
             d["work"] = np.empty((d["num_work"], 2), np.int32)
             check(lib.hispmv_plan_blocked(self._ctx, matrix_idx, _ptr(d["slab_ptr"]), _ptr(d["val"]), _ptr(d["lcol"]),
-                                          _ptr(d["perm"]), _ptr(d["panel_seg"]), _ptr(d["seg"]), _ptr(d["work"])),
-                  "plan_blocked")
+                                          _ptr(d["flags"]), _ptr(d["group_base"]), _ptr(d["prow_ptr"]), _ptr(d["perm"]),
+                                          _ptr(d["panel_seg"]), _ptr(d["seg"]), _ptr(d["work"])), "plan_blocked")
         return d
 
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:

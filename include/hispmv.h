@@ -125,7 +125,11 @@ int hispmv_shard_bounds(const int32_t* row_ptr, int32_t rows, int n_parts, int32
  * 256 MiB per HBM channel (fpga_handle.h:12). */
 int hispmv_set_memory_limit(hispmv_ctx* ctx, int64_t bytes);
 
-/* ---- adding matrices: return handle index >= 0, HISPMV_FULL (-1), or another negative status ---- */
+/* ---- adding matrices: return handle index >= 0, HISPMV_FULL (-1), or another negative status ----
+ * COO: unsorted, duplicates kept; an index outside [0,rows) x [0,cols) is refused (HISPMV_ERR_ARG).
+ * CSR: row_ptr[0] = 0, non-decreasing, row_ptr[rows] = nnz, and 0 <= col < cols -- refused otherwise (HISPMV_ERR_ARG);
+ *      a row whose columns are not in non-decreasing order is accepted and re-sorted by (column, value), the order the
+ *      COO path produces (the reference's per-row std::sort, common/src/spmv-helper.cpp:216). */
 int hispmv_add_sparse_coo(hispmv_ctx* ctx, const int32_t* coo_rows, const int32_t* coo_cols, const float* coo_vals,
                           int64_t nnz, int32_t rows, int32_t cols);
 int hispmv_add_sparse_csr(hispmv_ctx* ctx, const int32_t* row_ptr, const int32_t* col_idx, const float* vals,
@@ -160,6 +164,12 @@ int hispmv_run_xdev(hispmv_ctx* ctx, const float* d_x, void* x_stream, const flo
 void* hispmv_stream(hispmv_ctx* ctx);
 int hispmv_run_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha,
                    float beta, void* stream);
+/* hispmv_run_dev one phase at a time, for callers that overlap the phases with their own copies or exchanges (the
+ * reference overlaps host-side fills with the running kernel, pyhispmv/src/fpga_handle.cpp:366-379).  phases: 1 = the
+ * products (needs only x; BLOCKED matrices, a no-op for the one-pass strategies), 2 = row sums + alpha/beta epilogue
+ * (needs bias; the whole operation for the one-pass strategies), 3 = both = hispmv_run_dev. */
+int hispmv_run_dev_phase(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha,
+                         float beta, int phases, void* stream);
 /* y = relu?(A x + bias) for chained layers that stay on the device. */
 int hispmv_linear_dev(hispmv_ctx* ctx, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
                       void* stream);
@@ -204,15 +214,23 @@ int hispmv_plan_slab_csr(hispmv_ctx* ctx, int idx, int slab, int32_t* row_ptr, i
 int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
 /* BLOCKED only (the column tiling of tileAndPad, common/src/spmv-helper.cpp:139-227, as this engine lays it out).
  * out8 = { slab_cols, num_slabs, padded_nnz, num_segments, max segments of a panel, pass-1 work ranges, panels,
- *          slab cost used to balance the ranges }.
- * hispmv_plan_blocked copies the plan to the host (any pointer may be NULL): slab_ptr[num_slabs+1] (slab starts in
- * the slab-major order, multiples of 128), vals / lcol / perm [padded_nnz] (value, column - slab*slab_cols, CSR position
- * - first CSR position of the entry's panel; padding entries are zero), panel_seg[panels+1], seg_start_off
- * [2*num_segments] ((start in slab-major order, entries of the same panel in earlier slabs) per non-empty (panel, slab)
- * segment, panel-major), work[2*ranges] (pass-1 [begin, end) per resident CTA). */
+ *          num_pieces }.
+ * hispmv_plan_blocked copies the plan to the host (any pointer may be NULL):
+ *   slab_ptr[num_slabs+1]      slab starts in the slab-major order (multiples of 128)
+ *   vals / lcol [padded_nnz]   value and column - slab*slab_cols of every entry (padding entries are zero)
+ *   flags[padded_nnz/4]        bit j of byte i: entry 4i+j is the last of its PIECE (consecutive entries of one row
+ *                              inside one 128-entry group); pieces are numbered in slab-major order
+ *   group_base[padded_nnz/128+1]  pieces that end before each group
+ *   prow_ptr[local_rows+1]     CSR-style offsets of every row's pieces (slab order inside a row); the panels
+ *                              (hispmv_plan_tiles / hispmv_plan_tile_chunks) are cut over these, not over nonzeros
+ *   perm[num_pieces]           a piece's position in that per-row order minus the first position of its panel
+ *   panel_seg[panels+1], seg_start_off[2*num_segments]   per non-empty (panel, slab) segment, panel-major:
+ *                              (first piece id, pieces of the same panel in earlier slabs)
+ *   work[2*ranges]             pass-1 [begin, end) per resident CTA */
 int hispmv_plan_blocked_info(hispmv_ctx* ctx, int idx, int64_t* out8);
-int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* perm,
-                        int32_t* panel_seg, int32_t* seg_start_off, int32_t* work);
+int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint8_t* flags,
+                        int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
+                        int32_t* seg_start_off, int32_t* work);
 
 /* ---- x exchange over NVSwitch multicast: store n floats from d_src to a multicast address (every GPU of the
  *      multicast group receives them).  mc_dst comes from a symmetric-memory rendezvous; sm_budget > 0 = that many

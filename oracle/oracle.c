@@ -397,15 +397,90 @@ int64_t oracle_adaptive_split_rows(int rows, const int* row_ptr, int T, int CH, 
  * pb_make_work and select_blocked.  The reference's own column tiling is tileAndPad
  * (common/src/spmv-helper.cpp:139-227: a tile covers as many columns as the on-chip x buffers hold);
  * this is the same idea with the GPU engine's sizes, single-threaded.
- *   slab s      = columns [s*W, (s+1)*W)
- *   panels      = the adaptive tiles (oracle_adaptive_tiles) given by tile_row / tile_chunk / CH
- *   blocked order: slab-major, CSR order inside a slab; every slab starts at a multiple of `align`,
- *                  the gaps are padding (val 0, lcol 0, perm 0)
- *   per entry   : val, lcol = col - s*W, perm = CSR position - first CSR position of the entry's panel
- *   segments    : the non-empty (panel, slab) runs, listed panel-major then by slab, as
- *                 (start in blocked order, number of the panel's entries in earlier slabs)
- * Returns the padded length; *num_seg gets the segment count.  Call with o_val == NULL to size.
+ *   slab s        = columns [s*W, (s+1)*W)
+ *   blocked order : slab-major, CSR order inside a slab; every slab starts at a multiple of G (the group
+ *                   size, 128); the gaps are padding (val 0, lcol 0, no flag)
+ *   per entry     : val, lcol = col - s*W, and an end flag (4 per byte, bit j = entry 4*i+j) on the last
+ *                   entry of every PIECE = maximal run of consecutive entries of one row inside one group
+ *   pieces        : numbered in blocked order; group_base[g] = pieces ending before group g;
+ *                   prow_ptr = CSR-style offsets of the pieces of every row (a row's pieces in slab order);
+ *                   piece_pcsr[q] = position of piece q in that per-row order, piece_slab[q] its slab
+ * oracle_pb_order returns the padded length (sizes with o_val == NULL); *num_pieces gets the piece count.
  * ---------------------------------------------------------------------------------------------- */
+int64_t oracle_pb_order(int rows, int cols, const int* row_ptr, const int* col, const float* val, int W, int G,
+                        int* slab_ptr, float* o_val, uint16_t* o_lcol, uint8_t* o_flags, int* group_base,
+                        int* prow_ptr, int* piece_pcsr, int* piece_slab, int64_t* num_pieces) {
+  const int64_t nnz = row_ptr[rows];
+  const int S = (int)(((int64_t)cols + W - 1) / W);
+  int64_t* cnt = (int64_t*)calloc((size_t)S + 1, sizeof(int64_t));
+  int64_t* start = (int64_t*)calloc((size_t)S + 1, sizeof(int64_t));
+  int64_t j, pos = 0, k, np = 0;
+  int* brow; /* row of every blocked position, -1 for padding */
+  int* fill;
+  int s, r;
+  for (j = 0; j < nnz; ++j) cnt[col[j] / W]++;
+  for (s = 0; s < S; ++s) {
+    start[s] = pos;
+    if (slab_ptr) slab_ptr[s] = (int)pos;
+    pos += cnt[s];
+    pos = (pos + G - 1) / G * G;
+    cnt[s] = 0; /* becomes the fill counter */
+  }
+  if (slab_ptr) slab_ptr[S] = (int)pos;
+  brow = (int*)malloc(sizeof(int) * (size_t)(pos + 1));
+  for (k = 0; k <= pos; ++k) brow[k] = -1;
+  if (o_val) {
+    memset(o_val, 0, sizeof(float) * (size_t)pos);
+    memset(o_lcol, 0, sizeof(uint16_t) * (size_t)pos);
+    memset(o_flags, 0, (size_t)(pos / 4));
+  }
+  for (r = 0; r < rows; ++r)
+    for (j = row_ptr[r]; j < row_ptr[r + 1]; ++j) {
+      const int sl = col[j] / W;
+      const int64_t dst = start[sl] + cnt[sl]++;
+      brow[dst] = r;
+      if (o_val) {
+        o_val[dst] = val[j];
+        o_lcol[dst] = (uint16_t)(col[j] - sl * W);
+      }
+    }
+  /* pieces: an entry ends one when the next position is another row, padding, or the next group */
+  if (prow_ptr) memset(prow_ptr, 0, sizeof(int) * ((size_t)rows + 1));
+  for (k = 0; k < pos; ++k) {
+    if (k % G == 0 && group_base) group_base[k / G] = (int)np;
+    if (brow[k] < 0) continue;
+    if ((k + 1) % G == 0 || brow[k + 1] != brow[k]) {
+      if (o_flags) o_flags[k / 4] |= (uint8_t)(1u << (k % 4));
+      if (prow_ptr) prow_ptr[brow[k] + 1]++;
+      ++np;
+    }
+  }
+  if (group_base) group_base[pos / G] = (int)np;
+  if (num_pieces) *num_pieces = np;
+  if (prow_ptr && piece_pcsr) {
+    int64_t q = 0;
+    for (r = 0; r < rows; ++r) prow_ptr[r + 1] += prow_ptr[r];
+    fill = (int*)calloc((size_t)rows + 1, sizeof(int));
+    s = 0;
+    for (k = 0; k < pos; ++k) {
+      while (s + 1 < S && k >= start[s + 1]) ++s;
+      if (brow[k] < 0) continue;
+      if ((k + 1) % G == 0 || brow[k + 1] != brow[k]) {
+        piece_pcsr[q] = prow_ptr[brow[k]] + fill[brow[k]]++;
+        piece_slab[q] = s;
+        ++q;
+      }
+    }
+    free(fill);
+  } else if (prow_ptr) {
+    for (r = 0; r < rows; ++r) prow_ptr[r + 1] += prow_ptr[r];
+  }
+  free(brow);
+  free(cnt);
+  free(start);
+  return pos;
+}
+
 static void pb_panel_extent(const int* row_ptr, const int* tile_row, const int* tile_chunk, int CH, int64_t t,
                             int* n0, int* n1) {
   if (tile_chunk[t] >= 0) {
@@ -420,75 +495,80 @@ static void pb_panel_extent(const int* row_ptr, const int* tile_row, const int* 
   }
 }
 
-static int cmp_int(const void* a, const void* b) {
-  const int x = *(const int*)a, y = *(const int*)b;
-  return (x > y) - (x < y);
-}
-
-int64_t oracle_pb_plan(int rows, int cols, const int* row_ptr, const int* col, const float* val, int64_t num_panels,
-                       const int* tile_row, const int* tile_chunk, int CH, int W, int align, int* slab_ptr,
-                       float* o_val, uint16_t* o_lcol, uint16_t* o_perm, int* panel_seg, int* seg,
-                       int64_t* num_seg) {
-  const int64_t nnz = row_ptr[rows];
-  const int S = (int)(((int64_t)cols + W - 1) / W);
-  int64_t* cnt = (int64_t*)calloc((size_t)S + 1, sizeof(int64_t));
-  int64_t* start = (int64_t*)calloc((size_t)S + 1, sizeof(int64_t));
-  int* first = (int*)malloc(sizeof(int) * ((size_t)S + 1));
-  int* pcnt = (int*)calloc((size_t)S + 1, sizeof(int));
-  int* touched = (int*)malloc(sizeof(int) * ((size_t)S + 1));
-  int64_t j, pos = 0, nseg = 0, t;
-  int s;
-  for (j = 0; j < nnz; ++j) cnt[col[j] / W]++;
-  for (s = 0; s < S; ++s) {
-    start[s] = pos;
-    if (slab_ptr) slab_ptr[s] = (int)pos;
-    pos += cnt[s];
-    pos = (pos + align - 1) / align * align;
-    cnt[s] = 0; /* becomes the fill counter */
-  }
-  if (slab_ptr) slab_ptr[S] = (int)pos;
-  if (o_val) {
-    memset(o_val, 0, sizeof(float) * (size_t)pos);
-    memset(o_lcol, 0, sizeof(uint16_t) * (size_t)pos);
-    memset(o_perm, 0, sizeof(uint16_t) * (size_t)pos);
-  }
+/* Panels are the adaptive tiles over prow_ptr (pieces instead of nonzeros).  For every piece: perm = its per-row-order
+ * position minus the first position of its panel.  Segments = the non-empty (panel, slab) runs of consecutive piece
+ * ids, listed panel-major then by slab, as (first piece id, number of the panel's pieces in earlier slabs).
+ * Returns the segment count (sizes with seg == NULL). */
+int64_t oracle_pb_segments(int64_t num_pieces, const int* piece_pcsr, const int* piece_slab, int S, const int* prow_ptr,
+                           int64_t num_panels, const int* tile_row, const int* tile_chunk, int CH, uint16_t* perm,
+                           int* panel_seg, int* seg) {
+  /* panel of every per-row-order position */
+  const int64_t total = num_pieces;
+  int* pan_of = (int*)malloc(sizeof(int) * (size_t)(total + 1));
+  int* n0s = (int*)malloc(sizeof(int) * (size_t)(num_panels + 1));
+  int64_t t, q, nseg = 0;
   for (t = 0; t < num_panels; ++t) {
-    int n0, n1, nt = 0, i, off = 0;
-    pb_panel_extent(row_ptr, tile_row, tile_chunk, CH, t, &n0, &n1);
-    if (panel_seg) panel_seg[t] = (int)nseg;
-    for (j = n0; j < n1; ++j) {
-      const int sl = col[j] / W;
-      const int64_t dst = start[sl] + cnt[sl]++;
-      if (pcnt[sl]++ == 0) {
-        first[sl] = (int)dst;
-        touched[nt++] = sl;
-      }
-      if (o_val) {
-        o_val[dst] = val[j];
-        o_lcol[dst] = (uint16_t)(col[j] - sl * W);
-        o_perm[dst] = (uint16_t)(j - n0);
-      }
-    }
-    qsort(touched, (size_t)nt, sizeof(int), cmp_int);
-    for (i = 0; i < nt; ++i) {
-      const int sl = touched[i];
-      if (seg) {
-        seg[2 * nseg] = first[sl];
-        seg[2 * nseg + 1] = off;
-      }
-      off += pcnt[sl];
-      pcnt[sl] = 0;
-      ++nseg;
-    }
+    int n0, n1, i;
+    pb_panel_extent(prow_ptr, tile_row, tile_chunk, CH, t, &n0, &n1);
+    n0s[t] = n0;
+    for (i = n0; i < n1; ++i) pan_of[i] = (int)t;
   }
-  if (panel_seg) panel_seg[num_panels] = (int)nseg;
-  if (num_seg) *num_seg = nseg;
-  free(cnt);
-  free(start);
-  free(first);
-  free(pcnt);
-  free(touched);
-  return pos;
+  for (q = 0; q < total; ++q)
+    if (perm) perm[q] = (uint16_t)(piece_pcsr[q] - n0s[pan_of[piece_pcsr[q]]]);
+  /* runs of equal (slab, panel) in piece-id order; collect them, then order by (panel, slab) with a counting pass */
+  {
+    int64_t nrun = 0, i;
+    int* run_start;
+    int* run_pan;
+    int* run_slab;
+    int* run_len;
+    int64_t* pcount = (int64_t*)calloc((size_t)num_panels + 1, sizeof(int64_t));
+    for (q = 0; q < total; ++q)
+      if (q == 0 || piece_slab[q] != piece_slab[q - 1] || pan_of[piece_pcsr[q]] != pan_of[piece_pcsr[q - 1]]) ++nrun;
+    run_start = (int*)malloc(sizeof(int) * (size_t)(nrun + 1));
+    run_pan = (int*)malloc(sizeof(int) * (size_t)(nrun + 1));
+    run_slab = (int*)malloc(sizeof(int) * (size_t)(nrun + 1));
+    run_len = (int*)malloc(sizeof(int) * (size_t)(nrun + 1));
+    nrun = 0;
+    for (q = 0; q < total; ++q) {
+      if (q == 0 || piece_slab[q] != piece_slab[q - 1] || pan_of[piece_pcsr[q]] != pan_of[piece_pcsr[q - 1]]) {
+        run_start[nrun] = (int)q;
+        run_pan[nrun] = pan_of[piece_pcsr[q]];
+        run_slab[nrun] = piece_slab[q];
+        run_len[nrun] = 0;
+        ++nrun;
+      }
+      run_len[nrun - 1]++;
+    }
+    nseg = nrun;
+    /* runs come slab-major and, inside a slab, by panel: a stable counting sort by panel gives (panel, slab) order */
+    for (i = 0; i < nrun; ++i) pcount[run_pan[i] + 1]++;
+    for (t = 0; t < num_panels; ++t) pcount[t + 1] += pcount[t];
+    if (panel_seg)
+      for (t = 0; t <= num_panels; ++t) panel_seg[t] = (int)pcount[t];
+    if (seg) {
+      int64_t* at = (int64_t*)malloc(sizeof(int64_t) * ((size_t)num_panels + 1));
+      int* off = (int*)calloc((size_t)num_panels + 1, sizeof(int));
+      memcpy(at, pcount, sizeof(int64_t) * ((size_t)num_panels + 1));
+      for (i = 0; i < nrun; ++i) {
+        const int p = run_pan[i];
+        const int64_t d = at[p]++;
+        seg[2 * d] = run_start[i];
+        seg[2 * d + 1] = off[p];
+        off[p] += run_len[i];
+      }
+      free(at);
+      free(off);
+    }
+    free(run_start);
+    free(run_pan);
+    free(run_slab);
+    free(run_len);
+    free(pcount);
+  }
+  free(pan_of);
+  free(n0s);
+  return nseg;
 }
 
 /* Pass-1 work ranges (blocked.cu: pb_make_work): n_cta contiguous pieces of the blocked order, balanced by entries

@@ -74,9 +74,10 @@ def oracle() -> C.CDLL:
     lib.oracle_adaptive_tiles.restype = i64
     lib.oracle_adaptive_split_rows.argtypes = [i, _i32p, i, i, vp]
     lib.oracle_adaptive_split_rows.restype = i64
-    lib.oracle_pb_plan.argtypes = [i, i, _i32p, _i32p, _f32p, i64, _i32p, _i32p, i, i, i, vp, vp, vp, vp, vp, vp,
-                                   C.POINTER(i64)]
-    lib.oracle_pb_plan.restype = i64
+    lib.oracle_pb_order.argtypes = [i, i, _i32p, _i32p, _f32p, i, i, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64)]
+    lib.oracle_pb_order.restype = i64
+    lib.oracle_pb_segments.argtypes = [i64, _i32p, _i32p, i, _i32p, i64, _i32p, _i32p, i, vp, vp, vp]
+    lib.oracle_pb_segments.restype = i64
     lib.oracle_pb_work.argtypes = [i, _i32p, i, i, i64, _i32p]
     lib.oracle_select_blocked.argtypes = [i, i, i64, i64, i64, i]
     lib.oracle_select_blocked.restype = i
@@ -266,31 +267,47 @@ def select_blocked(rows, cols, nnz, near, cmp_, allow_split=1):
 
 
 def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=128, n_cta=0, slab_cost=0):
-    """The blocked strategy's plan for this CSR (oracle_pb_plan / oracle_pb_work) as a dict of numpy arrays."""
+    """The blocked strategy's plan for this CSR (oracle_pb_order / oracle_adaptive_tiles over the pieces /
+    oracle_pb_segments / oracle_pb_work) as a dict of numpy arrays."""
     rp, ci = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32)
     vv = np.ascontiguousarray(vv, np.float32)
+    if ci.size == 0:
+        ci, vv = np.zeros(1, np.int32), np.zeros(1, np.float32)
     rows = rp.size - 1
-    tr, tc, _, _ = adaptive_tiles(rp, B, T, CH)
-    tc = np.ascontiguousarray(tc if tc.size else np.zeros(1, np.int32), np.int32)
-    npan = tr.size - 1
     S = (cols + W - 1) // W
-    nseg = C.c_int64()
+    npieces = C.c_int64()
     slab_ptr = np.zeros(S + 1, np.int32)
-    padded = oracle().oracle_pb_plan(rows, cols, rp, ci, vv, npan, tr, tc, CH, W, align, slab_ptr.ctypes.data, None,
-                                     None, None, None, None, C.byref(nseg))
+    o = oracle()
+    padded = o.oracle_pb_order(rows, cols, rp, ci, vv, W, align, slab_ptr.ctypes.data, None, None, None, None, None,
+                               None, None, C.byref(npieces))
     val = np.zeros(padded, np.float32)
     lcol = np.zeros(padded, np.uint16)
-    perm = np.zeros(padded, np.uint16)
+    flags = np.zeros(padded // 4, np.uint8)
+    group_base = np.zeros(padded // align + 1, np.int32)
+    prow_ptr = np.zeros(rows + 1, np.int32)
+    pcsr = np.zeros(max(npieces.value, 1), np.int32)
+    pslab = np.zeros(max(npieces.value, 1), np.int32)
+    o.oracle_pb_order(rows, cols, rp, ci, vv, W, align, slab_ptr.ctypes.data, val.ctypes.data, lcol.ctypes.data,
+                      flags.ctypes.data, group_base.ctypes.data, prow_ptr.ctypes.data, pcsr.ctypes.data,
+                      pslab.ctypes.data, C.byref(npieces))
+    npc = int(npieces.value)
+    tr, tc, tn, sp = adaptive_tiles(prow_ptr, B, T, CH)
+    tcc = np.ascontiguousarray(tc if tc.size else np.zeros(1, np.int32), np.int32)
+    npan = tr.size - 1
+    perm = np.zeros(max(npc, 1), np.uint16)
     panel_seg = np.zeros(npan + 1, np.int32)
-    seg = np.zeros((max(nseg.value, 1), 2), np.int32)
-    oracle().oracle_pb_plan(rows, cols, rp, ci, vv, npan, tr, tc, CH, W, align, slab_ptr.ctypes.data, val.ctypes.data,
-                            lcol.ctypes.data, perm.ctypes.data, panel_seg.ctypes.data, seg.ctypes.data, C.byref(nseg))
-    d = {"slab_cols": W, "num_slabs": S, "padded_nnz": int(padded), "num_seg": int(nseg.value), "num_panels": npan,
-         "slab_ptr": slab_ptr, "val": val, "lcol": lcol, "perm": perm, "panel_seg": panel_seg,
-         "seg": seg[:nseg.value], "max_panel_segs": int(np.diff(panel_seg).max()) if npan else 0}
+    nseg = o.oracle_pb_segments(npc, pcsr, pslab, S, prow_ptr, npan, tr, tcc, CH, None, None, None)
+    seg = np.zeros((max(nseg, 1), 2), np.int32)
+    o.oracle_pb_segments(npc, pcsr, pslab, S, prow_ptr, npan, tr, tcc, CH, perm.ctypes.data, panel_seg.ctypes.data,
+                         seg.ctypes.data)
+    d = {"slab_cols": W, "num_slabs": S, "padded_nnz": int(padded), "num_pieces": npc, "num_seg": int(nseg),
+         "num_panels": npan, "slab_ptr": slab_ptr, "val": val, "lcol": lcol, "flags": flags, "group_base": group_base,
+         "prow_ptr": prow_ptr, "perm": perm[:npc], "panel_seg": panel_seg, "seg": seg[:nseg],
+         "max_panel_segs": int(np.diff(panel_seg).max()) if npan else 0,
+         "tile_row": tr, "tile_chunk": tc, "tile_first": tn, "split_rows": sp}
     if n_cta:
         work = np.zeros((n_cta, 2), np.int32)
-        oracle().oracle_pb_work(S, slab_ptr, align, n_cta, slab_cost, work.reshape(-1))
+        o.oracle_pb_work(S, slab_ptr, align, n_cta, slab_cost, work.reshape(-1))
         d["work"] = work
     return d
 

@@ -24,17 +24,32 @@ def _powerlaw(rng, rows, cols, heavy=3, max_len=20000):
     return r, c, v
 
 
-def _walk_plan(d, rp, tr, tc, tn, CH, W, cols, x):
+def _walk_plan(d, rows, CH, W, cols, x):
     """numpy emulation of pass 1 + pass 2 over a plan dict: returns A x in float64."""
-    rows = rp.size - 1
+    G = 128
     slab_of = np.zeros(d["padded_nnz"], np.int64)
     for s in range(d["num_slabs"]):
         slab_of[d["slab_ptr"][s]:d["slab_ptr"][s + 1]] = s
     prod = d["val"].astype(np.float64) * x[np.minimum(slab_of * W + d["lcol"], cols - 1)]
+    # pass 1: one partial per piece; pieces never cross a group of G entries
+    fl = np.unpackbits(d["flags"][:, None], axis=1, bitorder="little")[:, :4].reshape(-1).astype(bool)
+    part = np.zeros(d["num_pieces"])
+    q, run = 0, 0.0
+    for k in range(d["padded_nnz"]):
+        if k % G == 0:
+            assert d["group_base"][k // G] == q
+            run = 0.0
+        run += prod[k]
+        if fl[k]:
+            part[q] = run
+            q, run = q + 1, 0.0
+    assert q == d["num_pieces"] == d["group_base"][-1]
+    # pass 2: panels over the per-row piece counts
     y = np.zeros(rows)
+    tr, tc, tn, pr = d["tile_row"], d["tile_chunk"], d["tile_first"], d["prow_ptr"]
     for p in range(d["num_panels"]):
         n0 = int(tn[p])
-        n1 = min(int(rp[tr[p] + 1]), n0 + CH) if tc[p] >= 0 else int(rp[tr[p + 1]])
+        n1 = min(int(pr[tr[p] + 1]), n0 + CH) if tc[p] >= 0 else int(pr[tr[p + 1]])
         n = n1 - n0
         buf = np.full(n, np.nan)
         segs = d["seg"][d["panel_seg"][p]:d["panel_seg"][p + 1]]
@@ -42,31 +57,31 @@ def _walk_plan(d, rp, tr, tc, tn, CH, W, cols, x):
         for i, (st, off) in enumerate(segs):
             ln = offs[i + 1] - off
             assert ln > 0
-            buf[d["perm"][st:st + ln]] = prod[st:st + ln]
-        assert not np.isnan(buf).any()           # every CSR position of the panel is covered exactly once
+            buf[d["perm"][st:st + ln]] = part[st:st + ln]
+        assert not np.isnan(buf).any()           # every piece slot of the panel is filled exactly once
         if tc[p] >= 0:
             y[tr[p]] += buf.sum()
         else:
             for rr in range(tr[p], tr[p + 1]):
-                y[rr] = buf[rp[rr] - n0:rp[rr + 1] - n0].sum()
+                y[rr] = buf[pr[rr] - n0:pr[rr + 1] - n0].sum()
     return y
 
 
-@pytest.mark.parametrize("seed,W,B,T,CH", [(0, 1024, 2048, 256, 512), (1, 4096, 512, 64, 1024), (2, 20000, 4096, 1024, 4096)])
+@pytest.mark.parametrize("seed,W,B,T,CH", [(0, 1024, 2048, 256, 512), (1, 4096, 512, 64, 128), (2, 20000, 4096, 1024, 4096)])
 def test_oracle_blocked_plan_reproduces_the_csr_product(seed, W, B, T, CH):
     rng = np.random.default_rng(seed)
     rows, cols = 4000, 20000 + seed
     r, c, v = _powerlaw(rng, rows, cols, max_len=6000)
     rp, ci, vv = ol.coo_to_csr(rows, r, c, v)
     d = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=7, slab_cost=300)
-    tr, tc, tn, _ = ol.adaptive_tiles(rp, B, T, CH)
     x = rng.standard_normal(cols).astype(np.float32)
-    y = _walk_plan(d, rp, tr, tc, tn, CH, W, cols, x)
+    y = _walk_plan(d, rows, CH, W, cols, x)
     y64, scale = ol.spmv_f64(rp, ci, vv, x)
     assert np.max(np.abs(y - y64) / np.maximum(scale, 1e-30)) < 1e-12
     # layout facts: slab starts aligned, ascending; lcol inside the slab; work ranges tile the blocked order
     assert np.all(d["slab_ptr"] % 128 == 0) and np.all(np.diff(d["slab_ptr"]) >= 0)
-    assert d["lcol"].max() < W
+    assert d["lcol"].max() < W and d["num_pieces"] <= ci.size and np.all(np.diff(d["prow_ptr"]) >= 0)
+    assert np.all((np.diff(d["prow_ptr"]) > 0) == (np.diff(rp) > 0))     # a row has pieces iff it has nonzeros
     w = d["work"]
     assert w[0, 0] == 0 and w[-1, 1] == d["padded_nnz"] and np.array_equal(w[1:, 0], w[:-1, 1])
     assert np.all(w % 128 == 0)
@@ -105,8 +120,8 @@ def _check_run(eng, idx, rp, ci, vv, rows, cols, rng, alpha=ALPHA, beta=BETA):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,params", [(0, "1024,2048,256,512,300"), (1, "4096,512,64,1024,0"),
-                                         (2, "20000,4096,1024,4096,5000"), (3, "49152,16384,1024,32768,32768")])
+@pytest.mark.parametrize("seed,params", [(0, "1024,2048,256,512,300"), (1, "4096,512,64,128,0"),
+                                         (2, "20000,4096,1024,4096,5000"), (3, "49152,8192,4096,8192,32768")])
 def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     """Every integer artefact of the blocked plan (slab starts, blocked order through val / lcol / perm, segment table,
     pass-1 work ranges) equals the sequential restatement; then the run is within tolerance and bit-reproducible."""
@@ -123,15 +138,15 @@ def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     rp, ci, vv = eng.plan_csr(idx)
     got = eng.plan_blocked(idx)
     want = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=got["num_work"], slab_cost=cost)
-    for k in ("slab_cols", "num_slabs", "padded_nnz", "num_seg", "num_panels", "max_panel_segs"):
+    for k in ("slab_cols", "num_slabs", "padded_nnz", "num_pieces", "num_seg", "num_panels", "max_panel_segs"):
         assert got[k] == want[k], k
-    for k in ("slab_ptr", "lcol", "perm", "panel_seg", "seg", "work"):
+    for k in ("slab_ptr", "lcol", "flags", "group_base", "prow_ptr", "perm", "panel_seg", "seg", "work"):
         assert np.array_equal(got[k], want[k]), k
     assert np.array_equal(got["val"].view(np.uint32), want["val"].view(np.uint32))
-    tr2, tc2, tn2, sp2 = ol.adaptive_tiles(rp, B, T, CH)
-    tr, tn = eng.plan_tiles(idx)
-    assert np.array_equal(tr, tr2) and np.array_equal(tn, tn2) and np.array_equal(eng.plan_tile_chunks(idx), tc2)
-    assert np.array_equal(eng.plan_split_rows(idx), sp2)
+    tr, tn = eng.plan_tiles(idx)        # the panels: adaptive tiles over the per-row piece counts
+    assert np.array_equal(tr, want["tile_row"]) and np.array_equal(tn, want["tile_first"])
+    assert np.array_equal(eng.plan_tile_chunks(idx), want["tile_chunk"])
+    assert np.array_equal(eng.plan_split_rows(idx), want["split_rows"])
     assert eng.launches_per_run(idx) == 2
     y1 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
     y2 = _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(7))
@@ -143,7 +158,7 @@ def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
 @pytest.mark.parametrize("kind", ["powerlaw", "regular", "short", "hollow", "one_row", "one_col"])
 def test_blocked_within_tolerance(eng, kind, monkeypatch):
     from hispmv_b200 import capi
-    monkeypatch.setenv("HISPMV_BLOCKED", "8192,4096,512,2048")
+    monkeypatch.setenv("HISPMV_BLOCKED", "8192,4096,512,1024")
     rng = np.random.default_rng(sum(map(ord, kind)))
     rows, cols = 30011, 100003
     if kind == "powerlaw":
@@ -178,7 +193,7 @@ def test_blocked_device_calls_relu_linear_and_unaligned_x(eng, monkeypatch):
     the plain-load staging path and gives the same bits."""
     import torch
     from hispmv_b200 import capi
-    monkeypatch.setenv("HISPMV_BLOCKED", "16384,8192,1024,4096")
+    monkeypatch.setenv("HISPMV_BLOCKED", "16384,8192,1024,2048")
     rng = np.random.default_rng(5)
     rows, cols = 40000, 150001
     r, c, v = _powerlaw(rng, rows, cols)

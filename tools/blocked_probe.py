@@ -96,17 +96,32 @@ def main():
             med, mn = time_runs(eng, idx, x, b, y, args.iters, flush)
             warm, _ = time_runs(eng, idx, x, b, y, args.iters, None)
             err = check_sample(eng, idx, sub, x, b, y, nrows=100000) if rb == 0 else float("nan")
+            ph = [0.0, 0.0]
+            if p is not None:   # the two passes on their own (cold L2 each)
+                stc = torch.cuda.current_stream().cuda_stream
+                for which in (1, 2):
+                    ts = []
+                    for _ in range(args.iters):
+                        flush.add_(1.0)
+                        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                        e0.record()
+                        eng.run_dev_phase(idx, x, b, y, 0.85, -2.06, which, stc)
+                        e1.record()
+                        e1.synchronize()
+                        ts.append(e0.elapsed_time(e1))
+                    ph[which - 1] = float(np.median(ts))
             gbs = bytes_alg / (med * 1e-3) / 1e9
             extra = {}
             if p is not None:
                 extra = eng.plan_blocked(idx, arrays=False)
             row = dict(workload=wl, variant=name, params=p, kernel=info["kernel_name"], ms_med=med, ms_min=mn,
                        ms_warm=warm, gbs=gbs, frac=gbs / peak, err=err, plan_s=t_plan, slabs=info["num_slabs"],
-                       panels=info["num_tiles"], device_bytes=info["device_bytes"], cusparse=cs, **extra)
+                       panels=info["num_tiles"], device_bytes=info["device_bytes"], cusparse=cs, pass1_ms=ph[0],
+                       pass2_ms=ph[1], **extra)
             res.append(row)
             print(f"{wl:8s} {name:9s} {str(p):34s} {info['kernel_name']:9s} med={med:8.4f} ms (warm L2 {warm:8.4f}) "
-                  f"{gbs:7.0f} GB/s frac={gbs/peak:5.3f} err={err:.1e} plan={t_plan:5.1f}s "
-                  f"{'' if not extra else 'segs=%d avg_seg=%.0f' % (extra['num_seg'], d.nnz / max(1, extra['num_seg']))}",
+                  f"{gbs:7.0f} GB/s frac={gbs/peak:5.3f} err={err:.1e} plan={t_plan:5.1f}s p1={ph[0]:.3f} p2={ph[1]:.3f} "
+                  f"{'' if not extra else 'pieces=%d segs=%d avg_seg=%.0f' % (extra['num_pieces'], extra['num_seg'], extra['num_pieces'] / max(1, extra['num_seg']))}",
                   flush=True)
             json.dump(res, open(args.out, "w"), indent=1)
         eng.close()

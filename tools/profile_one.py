@@ -19,7 +19,7 @@ from hispmv_b200 import Engine, capi, synth  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c2")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "adaptive", "rowstage", "merge", "vector", "scalar", "gemv"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "adaptive", "rowstage", "merge", "vector", "scalar", "gemv", "blocked"])
     ap.add_argument("--tile", default="")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--scale", type=float, default=1.0)
@@ -47,7 +47,7 @@ def main():
             r, c, v = nzr.numpy().astype(np.int32), nzc.numpy().astype(np.int32), w[nzr, nzc].numpy()
         idx = eng.create_sparse_handle(r, c, v, rows, cols)
         k = {"auto": capi.KERNEL_AUTO, "adaptive": capi.KERNEL_ADAPTIVE, "rowstage": capi.KERNEL_ROWSTAGE, "merge": capi.KERNEL_MERGE,
-             "vector": capi.KERNEL_CSR_VECTOR, "scalar": capi.KERNEL_CSR_SCALAR}[args.kernel]
+             "vector": capi.KERNEL_CSR_VECTOR, "scalar": capi.KERNEL_CSR_SCALAR, "blocked": capi.KERNEL_BLOCKED}[args.kernel]
         eng.force_kernel(idx, k, args.lanes)
     else:
         spec = {"c2": synth.c2_powerlaw, "c4": synth.c4_stencil, "c5": synth.c5_uniform}[args.config](args.scale)
@@ -55,8 +55,9 @@ def main():
         idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
         d.close()
         k = {"auto": capi.KERNEL_AUTO, "adaptive": capi.KERNEL_ADAPTIVE, "rowstage": capi.KERNEL_ROWSTAGE, "merge": capi.KERNEL_MERGE, "vector": capi.KERNEL_CSR_VECTOR,
-             "scalar": capi.KERNEL_CSR_SCALAR}[args.kernel]
-        eng.force_kernel(idx, k, args.lanes)
+             "scalar": capi.KERNEL_CSR_SCALAR, "blocked": capi.KERNEL_BLOCKED}[args.kernel]
+        if k != capi.KERNEL_AUTO:
+            eng.force_kernel(idx, k, args.lanes)
         rows, cols = spec.rows, spec.cols
     x = torch.rand(cols, device="cuda") + 0.5
     b = torch.rand(rows, device="cuda")

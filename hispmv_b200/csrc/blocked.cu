@@ -519,63 +519,64 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
 namespace {
 
 constexpr int kExpandThreads = 1024;
-constexpr int kExpandWarps = kExpandThreads / 32;
 constexpr int kBulkPiece = 4096;  // floats per cp.async.bulk (one copy costs its issuing thread ~650 cycles: 12 lanes
                                   // issue the 12 pieces of a 48 K-column slab side by side)
 
-// One warp, one group of 128 consecutive entries (lane l holds entries 4l .. 4l+3: products p[], end flags f).
-// Every piece's total goes to stage[rank of the piece inside the group]; returns the number of pieces.
-// Fixed shuffle tree, so the sums are bit-reproducible.
-__device__ __forceinline__ int group_pieces(const float (&p)[4], uint32_t f, int lane, float* __restrict__ stage) {
-  const unsigned b0 = __ballot_sync(kFullMask, f & 1u), b1 = __ballot_sync(kFullMask, f & 2u);
-  const unsigned b2 = __ballot_sync(kFullMask, f & 4u), b3 = __ballot_sync(kFullMask, f & 8u);
-  const int count = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
-  if (count == kPbGroup) {  // every entry is its own piece (hypersparse rows): the products are the partials
-    *reinterpret_cast<float4*>(stage + 4 * lane) = make_float4(p[0], p[1], p[2], p[3]);
-    return count;
+// One warp, one group of 128 consecutive entries: lane l holds entries 4l .. 4l+3 (values v, local columns c, end
+// flags f).  Every piece's total is stored at part[base + rank of the piece inside the group].  Straight-line code (the
+// first version spent 240 warp instructions per group, most of them branches and index arithmetic, and was
+// issue-bound at 35 % of HBM bandwidth); the shuffle tree is fixed, so the sums are bit-reproducible.
+__device__ __forceinline__ void group_pieces(const float4 v, const uint2 c, const uint32_t f, const int base,
+                                             const int lane, const float* __restrict__ s_x,
+                                             float* __restrict__ part) {
+  const float p0 = v.x * s_x[c.x & 0xffffu], p1 = v.y * s_x[c.x >> 16];
+  const float p2 = v.z * s_x[c.y & 0xffffu], p3 = v.w * s_x[c.y >> 16];
+  float* out = part + base;
+  if (__all_sync(kFullMask, f == 0xfu)) {  // every entry is its own piece (hypersparse rows): products are the partials
+    out[4 * lane + 0] = p0;
+    out[4 * lane + 1] = p1;
+    out[4 * lane + 2] = p2;
+    out[4 * lane + 3] = p3;
+    return;
   }
-  // inside the lane: totals of the pieces that end here; `run` = what follows the last end (or all four entries)
-  float out[4];
-  float run = 0.0f;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    run += p[j];
-    out[j] = run;
-    if (f & (1u << j)) run = 0.0f;
-  }
-  // inclusive segmented scan over the lanes of (run, has-an-end): what an open piece has collected up to this lane
-  float sv = run;
-  unsigned sf = f != 0;
+  // inside the lane: s_j = sum of the piece that entry j belongs to, up to and including j
+  const float s0 = p0;
+  const float s1 = (f & 1u) ? p1 : s0 + p1;
+  const float s2 = (f & 2u) ? p2 : s1 + p2;
+  const float s3 = (f & 4u) ? p3 : s2 + p3;
+  // inclusive segmented scan over the lanes of (what the lane leaves open, lane has an end), and the exclusive scan of
+  // the lanes' piece counts on the same shuffles' predicates
+  float sv = (f & 8u) ? 0.0f : s3;
+  unsigned sf = f != 0u;
+  int cnt = __popc(f);
+  int rank = cnt;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const float uv = __shfl_up_sync(kFullMask, sv, d);
     const unsigned uf = __shfl_up_sync(kFullMask, sf, d);
+    const int ur = __shfl_up_sync(kFullMask, rank, d);
     if (lane >= d) {
       if (!sf) sv += uv;
       sf |= uf;
+      rank += ur;
     }
   }
   float carry = __shfl_up_sync(kFullMask, sv, 1);  // the open piece's sum over the lanes before this one
   if (lane == 0) carry = 0.0f;                     // pieces never cross a group
-  const unsigned lt = (1u << lane) - 1u;
-  int rank = __popc(b0 & lt) + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt);
-  bool first = true;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    if (f & (1u << j)) {
-      stage[rank++] = first ? carry + out[j] : out[j];
-      first = false;
-    }
-  }
-  return count;
+  rank -= cnt;                                     // pieces that end in earlier lanes
+  // the first end of the lane closes the piece that came in from the left
+  float* o = out + rank;
+  if (f & 1u) *o++ = s0 + carry;
+  if (f & 2u) *o++ = (f & 1u) ? s1 : s1 + carry;
+  if (f & 4u) *o++ = (f & 3u) ? s2 : s2 + carry;
+  if (f & 8u) *o = (f & 7u) ? s3 : s3 + carry;
 }
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1)
     pb_expand_kernel(PbPlan P, const float* __restrict__ x, int32_t cols) {
   extern __shared__ __align__(128) unsigned char s_raw[];
-  float* s_x = reinterpret_cast<float*>(s_raw);                        // [slab_cols]
-  float* s_stage = s_x + P.slab_cols + (threadIdx.x >> 5) * kPbGroup;  // this warp's 128 partials
+  float* s_x = reinterpret_cast<float*>(s_raw);  // [slab_cols]
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = THREADS / 32;
@@ -583,12 +584,19 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (w.x >= w.y) return;
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
+  const int32_t* __restrict__ slab_ptr = P.slab_ptr;
+  const float* __restrict__ g_val = P.val;
+  const uint16_t* __restrict__ g_lcol = P.lcol;
+  const uint8_t* __restrict__ g_flags = P.flags;
+  const int32_t* __restrict__ g_base = P.group_base;
+  float* __restrict__ g_part = P.part;
+  const int slab_cols = P.slab_cols;
   int s;
   {  // the slab that holds entry w.x: the first s with slab_ptr[s + 1] > w.x
     int lo = 0, hi = P.num_slabs - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (__ldg(P.slab_ptr + mid + 1) <= w.x) lo = mid + 1; else hi = mid;
+      if (__ldg(slab_ptr + mid + 1) <= w.x) lo = mid + 1; else hi = mid;
     }
     s = lo;
   }
@@ -597,10 +605,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint32_t parity = 0;
   int k = w.x;
   while (k < w.y) {
-    const int kend = min(w.y, __ldg(P.slab_ptr + s + 1));
+    const int kend = min(w.y, __ldg(slab_ptr + s + 1));
     if (kend > k) {
-      const int c0 = s * P.slab_cols;
-      const int n = min(P.slab_cols, cols - c0);
+      const int c0 = s * slab_cols;
+      const int n = min(slab_cols, cols - c0);
       const int nb = x_aligned ? (n & ~3) : 0;  // floats that travel by bulk copy (c0 is a multiple of 4)
       if (nb > 0 && tid < 32) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the previous slab was read through the generic proxy
@@ -618,37 +626,29 @@ __global__ void __launch_bounds__(THREADS, 1)
       // groups of this slab's range: warp w takes group g0 + w, g0 + w + WARPS, ...; U groups' loads are in flight at once
       constexpr int U = 4;
       const int g_end = kend / kPbGroup;
-      for (int g = k / kPbGroup + warp; g < g_end; g += WARPS * U) {
+      int g = k / kPbGroup + warp;
+      for (; g + (U - 1) * WARPS < g_end; g += U * WARPS) {
         float4 v[U];
         uint2 c[U];
         uint32_t f[U];
         int base[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int gu = g + u * WARPS;
-          if (gu < g_end) {
-            const int i = gu * kPbGroup + lane * 4;
-            v[u] = ld_stream_f4(P.val + i, ps);
-            c[u] = ld_stream_u2(P.lcol + i, ps);
-            f[u] = __ldg(P.flags + (i >> 2));
-            base[u] = __ldg(P.group_base + gu);
-          }
+          const int i = (g + u * WARPS) * kPbGroup + lane * 4;
+          v[u] = ld_stream_f4(g_val + i, ps);
+          c[u] = ld_stream_u2(g_lcol + i, ps);
+          f[u] = __ldg(g_flags + (i >> 2));
+          base[u] = __ldg(g_base + g + u * WARPS);
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int gu = g + u * WARPS;
-          if (gu < g_end) {  // warp-uniform
-            float p[4];
-            p[0] = v[u].x * s_x[c[u].x & 0xffffu];
-            p[1] = v[u].y * s_x[c[u].x >> 16];
-            p[2] = v[u].z * s_x[c[u].y & 0xffffu];
-            p[3] = v[u].w * s_x[c[u].y >> 16];
-            const int count = group_pieces(p, f[u], lane, s_stage);
-            __syncwarp();
-            for (int i = lane; i < count; i += 32) P.part[base[u] + i] = s_stage[i];
-            __syncwarp();
-          }
-        }
+        for (int u = 0; u < U; ++u) group_pieces(v[u], c[u], f[u], base[u], lane, s_x, g_part);
+      }
+      for (; g < g_end; g += WARPS) {
+        const int i = g * kPbGroup + lane * 4;
+        const float4 v = ld_stream_f4(g_val + i, ps);
+        const uint2 c = ld_stream_u2(g_lcol + i, ps);
+        const uint32_t f = __ldg(g_flags + (i >> 2));
+        group_pieces(v, c, f, __ldg(g_base + g), lane, s_x, g_part);
       }
       __syncthreads();  // every gather from this slab has been issued before the next one overwrites it
     }
@@ -660,18 +660,35 @@ __global__ void __launch_bounds__(THREADS, 1)
 // ================================================================================================================
 // pass 2: one CTA per panel
 // ================================================================================================================
+// The first version of this kernel spent 130 thread instructions per piece (a per-lane segment walk with a shuffle per
+// step, and a lane-per-row reduction whose trip count followed the longest row of each pass) and was issue-bound at
+// 20 % of HBM bandwidth.  Now:
+//   gather   the panel's pieces are visited in flat (slab, row) order, 32 per warp step; s_hint[c] names the segment that
+//            holds flat index 32c, so a lane finds its segment with one or two compares, and its source is one add
+//            (s_seg[].delta = start - off); the partial goes to its place in per-row order (perm)
+//   reduce   every thread adds up C consecutive slots (C odd: no bank conflicts), closing rows as it passes their ends;
+//            a row that spans threads is closed by a segmented scan over the threads' open sums (shuffles inside a warp,
+//            shared memory across the eight warps, fixed order); the closing thread leaves the row's total in the row's
+//            last slot and a final row-per-thread pass applies alpha / beta / ReLU with coalesced bias loads and y stores
 constexpr int kReduceThreads = 256;
-constexpr int kSerialRowPb = 16;
-constexpr int kBiasAhead = 4;  // bias values per lane requested before the walk (rows of the warp's first passes)
+constexpr int kBiasAhead = 8;  // bias values per thread requested before the gather (rows tid, tid + 256, ...)
+
+struct SegS {  // a segment in shared memory
+  int32_t off;    // first flat index of the segment inside the panel
+  int32_t delta;  // piece id of flat index i = i + delta
+};
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 4)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's partials, then its row extents
-  PbSeg* s_seg = reinterpret_cast<PbSeg*>(s_raw + (size_t)P.cap_words * 4);  // [max_panel_segs + 1]
+  SegS* s_seg = reinterpret_cast<SegS*>(s_raw + (size_t)P.cap_words * 4);             // [max_panel_segs + 1]
+  uint16_t* s_hint = reinterpret_cast<uint16_t*>(s_seg + (P.max_panel_segs + 1));     // [cap_words / 32 + 1]
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
+  __shared__ float s_wv[WARPS];
+  __shared__ int s_wf[WARPS];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t = P.panel_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
@@ -681,66 +698,56 @@ __global__ void __launch_bounds__(THREADS, 4)
   const bool is_long = d.chunk >= 0;
   const int trows = d.r1 - d.r0;
   const uint64_t ps = policy_evict_first();
+  const float* __restrict__ g_part = P.part;
+  const uint16_t* __restrict__ g_perm = P.perm;
   for (int i = tid; i < nseg; i += THREADS) {
     const int2 v = __ldg(reinterpret_cast<const int2*>(P.seg) + sp0 + i);
-    s_seg[i].start = v.x;
     s_seg[i].off = v.y;
+    s_seg[i].delta = v.x - v.y;
   }
   if (tid == 0) {
-    s_seg[nseg].start = 0;
     s_seg[nseg].off = n;
+    s_seg[nseg].delta = 0;
   }
   int* s_rp = reinterpret_cast<int*>(s_prod + n);
-  // rows of the panel are dealt to the warps in blocks: warp w owns rows [beg, end)
-  const int rpw = (trows + WARPS - 1) / WARPS;
-  const int beg = warp * rpw, end = min(trows, beg + rpw);
   float bias_pre[kBiasAhead];
   if (!is_long) {
     for (int i = tid; i <= trows; i += THREADS) s_rp[i] = __ldg(P.prow_ptr + d.r0 + i) - d.n0;
 #pragma unroll
-    for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap the walk
-      const int i = beg + a * 32 + lane;
-      bias_pre[a] = (ep.beta != 0.0f && i < end) ? ep.bias[d.r0 + i] : 0.0f;
+    for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
+      const int i = tid + a * THREADS;
+      bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
     }
   }
   __syncthreads();
-
-  // ---- walk the panel's segments: warp w takes the flat range [f0, f1) of the panel's pieces in (slab, row) order --
-  constexpr int U = 8;
-  const int per = (((n + WARPS - 1) / WARPS) + 31) & ~31;
-  const int f0 = min(n, warp * per), f1 = min(n, f0 + per);
-  int cur = 0;
-  if (f0 < f1) {  // the last segment that starts at or before f0
-    int lo = 0, hi = nseg - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (s_seg[mid].off <= f0) lo = mid; else hi = mid - 1;
-    }
-    cur = lo;
+  // s_hint[c] = the segment that holds flat index 32 c
+  for (int sg = tid; sg < nseg; sg += THREADS) {
+    const int o0 = s_seg[sg].off, o1 = s_seg[sg + 1].off;
+    for (int c = (o0 + 31) >> 5; (c << 5) < o1; ++c) s_hint[c] = (uint16_t)sg;
   }
+  __syncthreads();
+
+  // ---- gather: chunk c = flat indices [32 c, 32 c + 32), chunks dealt to the warps round-robin, U in flight ---------
+  constexpr int U = 4;
+  const int nchunks = (n + 31) >> 5;
   float acc = 0.0f;
-  for (int base = f0; base < f1; base += 32 * U) {
-    int addr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * 32 + lane;
-      int sg = cur;
-      addr[u] = -1;
-      if (i < f1) {
-        while (i >= s_seg[sg + 1].off) ++sg;
-        addr[u] = s_seg[sg].start + (i - s_seg[sg].off);
-      }
-      cur = __shfl_sync(kFullMask, sg, 31);
-    }
+  for (int c0 = warp; c0 < nchunks; c0 += WARPS * U) {
     float p[U];
     uint32_t q[U];
+    bool ok[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
+      const int c = c0 + u * WARPS;
+      const int i = (c << 5) + lane;
+      ok[u] = i < n;
       p[u] = 0.0f;
       q[u] = 0;
-      if (addr[u] >= 0) {
-        p[u] = ld_stream_f1(P.part + addr[u], ps);
-        if (!is_long) q[u] = ld_stream_u16(P.perm + addr[u], ps);
+      if (ok[u]) {
+        int sg = s_hint[c];
+        while (i >= s_seg[sg + 1].off) ++sg;
+        const int src = i + s_seg[sg].delta;
+        p[u] = ld_stream_f1(g_part + src, ps);
+        if (!is_long) q[u] = ld_stream_u16(g_perm + src, ps);
       }
     }
     if (is_long) {
@@ -749,7 +756,7 @@ __global__ void __launch_bounds__(THREADS, 4)
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (addr[u] >= 0) s_prod[q[u]] = p[u];
+        if (ok[u]) s_prod[q[u]] = p[u];
     }
   }
   if (is_long) {
@@ -764,46 +771,98 @@ __global__ void __launch_bounds__(THREADS, 4)
   }
   __syncthreads();
 
-  // ---- rows out of the buffer, every row's pieces in slab order -----------------------------------------------------
-  int pass = 0;
-  for (int base = beg; base < end; base += 32, ++pass) {
-    const int i = base + lane;
-    int b = 0, e = 0;
-    float bias = 0.0f;
-    if (i < end) {
-      b = s_rp[i];
-      e = s_rp[i + 1];
+  // ---- reduce: thread tid sums the slots [j0, j1) of the per-row order ------------------------------------------
+  const int C = ((n + THREADS - 1) / THREADS) | 1;
+  const int j0 = min(n, tid * C), j1 = min(n, j0 + C);
+  float lead = 0.0f, run = 0.0f;
+  int lead_slot = -1;     // >= 0: a row that began before j0 ends at this slot, and `lead` is my share of it
+  bool closed = false;    // some row ends inside [j0, j1)
+  if (j0 < j1) {
+    int lo = 0, hi = trows;  // the row that holds slot j0: the last r with s_rp[r] <= j0 (empty rows sort before it)
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_rp[mid] <= j0) lo = mid; else hi = mid;
     }
+    int r = lo;
+    int next_end = s_rp[r + 1];
+    const bool began_before = s_rp[r] < j0;
+    for (int j = j0; j < j1; ++j) {
+      run += s_prod[j];
+      if (j + 1 == next_end) {  // row r ends here
+        if (!closed && began_before) {
+          lead = run;
+          lead_slot = j;
+        } else {
+          s_prod[j] = run;  // the row's total waits in its last slot for the epilogue
+        }
+        closed = true;
+        run = 0.0f;
+        do {
+          ++r;
+          next_end = s_rp[r + 1];
+        } while (next_end == j + 1 && r + 1 < trows);  // skip empty rows
+      }
+    }
+  }
+  // segmented scan over the threads of (what a thread leaves open, thread closed a row): carry = the open row's sum
+  // over the threads before this one
+  float sv = run;            // closed: the tail after the last end; not closed: the whole range
+  unsigned sf = closed;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) {
+    const float uv = __shfl_up_sync(kFullMask, sv, dd);
+    const unsigned uf = __shfl_up_sync(kFullMask, sf, dd);
+    if (lane >= dd) {
+      if (!sf) sv += uv;
+      sf |= uf;
+    }
+  }
+  if (lane == 31) {
+    s_wv[warp] = sv;
+    s_wf[warp] = (int)sf;
+  }
+  float carry = __shfl_up_sync(kFullMask, sv, 1);
+  const unsigned before = __shfl_up_sync(kFullMask, sf, 1);  // some earlier lane of this warp closed a row
+  __syncthreads();
+  if (lead_slot >= 0) {
+    float c_in = 0.0f;
+    bool need_warps = true;
+    if (lane > 0) {
+      c_in = carry;
+      need_warps = !before;
+    }
+    if (need_warps) {  // add the open sums of the warps before this one, back to the last warp that closed a row
+      float wsum = 0.0f;
+      int w0 = warp;
+      while (w0 > 0) {
+        --w0;
+        if (s_wf[w0]) break;
+      }
+      // w0 is the last closing warp before this one (or 0): its tail, then every pass-through warp after it, in order
+      for (int w = w0; w < warp; ++w) wsum += s_wv[w];
+      c_in = wsum + c_in;
+    }
+    s_prod[lead_slot] = c_in + lead;
+  }
+  __syncthreads();
+
+  // ---- epilogue: one thread per row, coalesced ------------------------------------------------------------------
+  int pass = 0;
+  for (int i = tid; i < trows; i += THREADS, ++pass) {
+    const int b = s_rp[i], e = s_rp[i + 1];
+    const float s = e > b ? s_prod[e - 1] : 0.0f;
+    float bias = 0.0f;
     if (pass < kBiasAhead) {
 #pragma unroll
       for (int a = 0; a < kBiasAhead; ++a)
         if (a == pass) bias = bias_pre[a];
-    } else if (i < end && ep.beta != 0.0f) {
+    } else if (ep.beta != 0.0f) {
       bias = ep.bias[d.r0 + i];
     }
-    const int len = e - b;
-    float s = 0.0f;
-    const int mine = len <= kSerialRowPb ? len : 0;
-    const int steps = __reduce_max_sync(kFullMask, mine);
-#pragma unroll 4
-    for (int k = 0; k < steps; ++k)
-      if (k < mine) s += s_prod[b + k];
-    unsigned big = __ballot_sync(kFullMask, len > kSerialRowPb);
-    while (big) {
-      const int j = __ffs(big) - 1;
-      big &= big - 1;
-      const int bj = __shfl_sync(kFullMask, b, j), ej = __shfl_sync(kFullMask, e, j);
-      float pp = 0.0f;
-      for (int k = bj + lane; k < ej; k += 32) pp += s_prod[k];
-      pp = warp_sum(pp);
-      if (lane == j) s = pp;
-    }
-    if (i < end) {
-      float v = ep.alpha * s;
-      if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
-      if (ep.relu) v = fmaxf(v, 0.0f);
-      store_y(y, d.r0 + i, v, ep.y_mc);
-    }
+    float v = ep.alpha * s;
+    if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
+    if (ep.relu) v = fmaxf(v, 0.0f);
+    store_y(y, d.r0 + i, v, ep.y_mc);
   }
 }
 
@@ -811,7 +870,7 @@ __global__ void __launch_bounds__(THREADS, 4)
 
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s) {
   if (P.num_work <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.slab_cols * 4 + (size_t)kExpandWarps * kPbGroup * 4;
+  const size_t smem = (size_t)P.slab_cols * 4;
   static size_t configured = 0;
   if (smem > configured) {
     HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<kExpandThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -827,7 +886,8 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   (void)A;
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.max_panel_segs + 1) * sizeof(PbSeg);
+  const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.max_panel_segs + 1) * sizeof(PbSeg) +
+                      ((size_t)P.cap_words / 32 + 2) * sizeof(uint16_t);
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

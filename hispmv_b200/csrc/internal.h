@@ -228,7 +228,7 @@ struct PbPlan {
   unsigned int* counter = nullptr;
 };
 constexpr int32_t kPbGroup = 128;          // entries a warp handles per step: 4 per lane
-constexpr int32_t kPbMaxSlabCols = 53248;  // 208 KB of x: the largest slab next to the per-warp staging of pass 1
+constexpr int32_t kPbMaxSlabCols = 57344;  // 224 KB of x: the largest slab one CTA's shared memory can hold
 // owned device arrays of a blocked plan (built by pb_order_device + pb_segments_device, freed by pb_free)
 struct PbArrays {
   int32_t slab_cols = 0, num_slabs = 0;

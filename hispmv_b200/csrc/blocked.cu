@@ -73,6 +73,19 @@ __global__ void pb_slab_bounds_kernel(const uint16_t* __restrict__ key, int64_t 
   ustart[s] = (int32_t)lo;
 }
 
+// Storage inside a group of kPbGroup = 512 entries: entry e = 16 * lane + w sits where a warp's coalesced vector loads
+// hand lane `lane` its 16 consecutive entries (val: four 128-bit loads, lcol: two).
+__host__ __device__ __forceinline__ int64_t pb_phys_val(int64_t k) {
+  const int64_t g = k / kPbGroup, e = k % kPbGroup;
+  const int64_t lane = e >> 4, w = e & 15;
+  return g * kPbGroup + (((w >> 2) << 5) + lane) * 4 + (w & 3);
+}
+__host__ __device__ __forceinline__ int64_t pb_phys_lcol(int64_t k) {
+  const int64_t g = k / kPbGroup, e = k % kPbGroup;
+  const int64_t lane = e >> 4, w = e & 15;
+  return g * kPbGroup + (((w >> 3) << 5) + lane) * 8 + (w & 7);
+}
+
 // blocked copy of entry k of the slab-sorted order; brow[dst] = its row (padding positions keep -1)
 __global__ void pb_scatter_kernel(const uint16_t* __restrict__ key, const uint32_t* __restrict__ idx, int64_t nnz,
                                   const int32_t* __restrict__ row_ptr, int32_t rows, const int32_t* __restrict__ col,
@@ -89,8 +102,8 @@ __global__ void pb_scatter_kernel(const uint16_t* __restrict__ key, const uint32
     const int32_t mid = (int32_t)(((int64_t)lo + hi) >> 1);
     if (__ldg(row_ptr + mid) <= j) lo = mid; else hi = mid;
   }
-  o_val[dst] = val[j];
-  o_lcol[dst] = (uint16_t)(col[j] - s * W);
+  o_val[pb_phys_val(dst)] = val[j];
+  o_lcol[pb_phys_lcol(dst)] = (uint16_t)(col[j] - s * W);
   brow[dst] = lo;
 }
 
@@ -103,12 +116,17 @@ __global__ void pb_end_kernel(const int32_t* __restrict__ brow, int64_t padded, 
 }
 
 __global__ void pb_pack_kernel(const int32_t* __restrict__ end, const int32_t* __restrict__ pid, int64_t padded,
-                               uint8_t* __restrict__ flags, int32_t* __restrict__ group_base) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one byte = four entries
-  if (i * 4 >= padded) return;
-  const int4 e = *reinterpret_cast<const int4*>(end + i * 4);
-  flags[i] = (uint8_t)(e.x | (e.y << 1) | (e.z << 2) | (e.w << 3));
-  if ((i * 4) % kPbGroup == 0) group_base[(i * 4) / kPbGroup] = pid[i * 4];
+                               uint16_t* __restrict__ flags, int32_t* __restrict__ group_base) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one word = sixteen entries = one lane's share
+  if (i * 16 >= padded) return;
+  uint32_t f = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int4 e = *reinterpret_cast<const int4*>(end + i * 16 + q * 4);
+    f |= (uint32_t)(e.x | (e.y << 1) | (e.z << 2) | (e.w << 3)) << (4 * q);
+  }
+  flags[i] = (uint16_t)f;
+  if ((i * 16) % kPbGroup == 0) group_base[(i * 16) / kPbGroup] = pid[i * 16];
 }
 
 __global__ void pb_piece_emit_kernel(const int32_t* __restrict__ brow, const int32_t* __restrict__ end,
@@ -316,13 +334,13 @@ int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
   const int64_t ngroups = padded / kPbGroup;
   HISPMV_CUDA(cudaMalloc((void**)&out->d_val, ((size_t)padded + slack) * 4));
   HISPMV_CUDA(cudaMalloc((void**)&out->d_lcol, ((size_t)padded + slack) * 2));
-  HISPMV_CUDA(cudaMalloc((void**)&out->d_flags, (size_t)padded / 4 + slack));
+  HISPMV_CUDA(cudaMalloc((void**)&out->d_flags, (size_t)padded / 8 + slack));
   HISPMV_CUDA(cudaMalloc((void**)&out->d_group_base, ((size_t)ngroups + 1) * 4));
   HISPMV_CUDA(cudaMalloc((void**)&out->d_slab_ptr, ((size_t)S + 1) * 4));
   HISPMV_CUDA(cudaMalloc((void**)&out->d_prow_ptr, ((size_t)rows + 1 + 4) * 4));
   HISPMV_CUDA(cudaMemsetAsync(out->d_val, 0, ((size_t)padded + slack) * 4, stream));
   HISPMV_CUDA(cudaMemsetAsync(out->d_lcol, 0, ((size_t)padded + slack) * 2, stream));
-  HISPMV_CUDA(cudaMemsetAsync(out->d_flags, 0, (size_t)padded / 4 + slack, stream));
+  HISPMV_CUDA(cudaMemsetAsync(out->d_flags, 0, (size_t)padded / 8 + slack, stream));
   HISPMV_CUDA(cudaMemcpyAsync(out->d_slab_ptr, pstart.p, ((size_t)S + 1) * 4, cudaMemcpyDeviceToDevice, stream));
   DevBuf brow, end, pid;
   if ((st = brow.alloc(((size_t)padded + 4) * 4))) return st;
@@ -348,7 +366,7 @@ int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
   HISPMV_CUDA(cudaMemcpyAsync(&h_last[1], pid.as<int32_t>() + (padded - 1), 4, cudaMemcpyDeviceToHost, stream));
   HISPMV_CUDA(cudaStreamSynchronize(stream));
   const int64_t np = (int64_t)h_last[0] + h_last[1];
-  pb_pack_kernel<<<blocks_for(padded / 4, B), B, 0, stream>>>(end.as<int32_t>(), pid.as<int32_t>(), padded, out->d_flags,
+  pb_pack_kernel<<<blocks_for(padded / 16, B), B, 0, stream>>>(end.as<int32_t>(), pid.as<int32_t>(), padded, out->d_flags,
                                                               out->d_group_base);
   const int32_t np32 = (int32_t)np;
   HISPMV_CUDA(cudaMemcpyAsync(out->d_group_base + ngroups, &np32, 4, cudaMemcpyHostToDevice, stream));
@@ -522,54 +540,54 @@ constexpr int kExpandThreads = 1024;
 constexpr int kBulkPiece = 4096;  // floats per cp.async.bulk (one copy costs its issuing thread ~650 cycles: 12 lanes
                                   // issue the 12 pieces of a 48 K-column slab side by side)
 
-// One warp, one group of 128 consecutive entries: lane l holds entries 4l .. 4l+3 (values v, local columns c, end
-// flags f).  Every piece's total is stored at part[base + rank of the piece inside the group].  Straight-line code (the
-// first version spent 240 warp instructions per group, most of them branches and index arithmetic, and was
-// issue-bound at 35 % of HBM bandwidth); the shuffle tree is fixed, so the sums are bit-reproducible.
-__device__ __forceinline__ void group_pieces(const float4 v, const uint2 c, const uint32_t f, const int base,
+// One warp, one group of 512 consecutive entries: lane l holds entries 16 l .. 16 l + 15 (values v[], local columns
+// c[], end flags f).  Every piece's total is stored at part[base + rank of the piece inside the group].
+// History: 4 entries per lane with branches and a staging buffer cost 240 warp instructions per 128 entries and was
+// issue-bound at 35 % of HBM bandwidth; straight-line code 162 (46 %).  Sixteen entries per lane amortise the warp-wide
+// scan (the only cross-lane step) over four times as many entries.  The shuffle tree and the in-lane order are fixed,
+// so the sums are bit-reproducible.
+__device__ __forceinline__ void group_pieces(const float4 (&v)[4], const uint4 (&c)[2], const uint32_t f, const int base,
                                              const int lane, const float* __restrict__ s_x,
                                              float* __restrict__ part) {
-  const float p0 = v.x * s_x[c.x & 0xffffu], p1 = v.y * s_x[c.x >> 16];
-  const float p2 = v.z * s_x[c.y & 0xffffu], p3 = v.w * s_x[c.y >> 16];
-  float* out = part + base;
-  if (__all_sync(kFullMask, f == 0xfu)) {  // every entry is its own piece (hypersparse rows): products are the partials
-    out[4 * lane + 0] = p0;
-    out[4 * lane + 1] = p1;
-    out[4 * lane + 2] = p2;
-    out[4 * lane + 3] = p3;
-    return;
+  float p[16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t w0 = k < 2 ? (k == 0 ? c[0].x : c[0].z) : (k == 2 ? c[1].x : c[1].z);
+    const uint32_t w1 = k < 2 ? (k == 0 ? c[0].y : c[0].w) : (k == 2 ? c[1].y : c[1].w);
+    p[4 * k + 0] = v[k].x * s_x[w0 & 0xffffu];
+    p[4 * k + 1] = v[k].y * s_x[w0 >> 16];
+    p[4 * k + 2] = v[k].z * s_x[w1 & 0xffffu];
+    p[4 * k + 3] = v[k].w * s_x[w1 >> 16];
   }
-  // inside the lane: s_j = sum of the piece that entry j belongs to, up to and including j
-  const float s0 = p0;
-  const float s1 = (f & 1u) ? p1 : s0 + p1;
-  const float s2 = (f & 2u) ? p2 : s1 + p2;
-  const float s3 = (f & 4u) ? p3 : s2 + p3;
-  // inclusive segmented scan over the lanes of (what the lane leaves open, lane has an end), and the exclusive scan of
-  // the lanes' piece counts on the same shuffles' predicates
-  float sv = (f & 8u) ? 0.0f : s3;
-  unsigned sf = f != 0u;
-  int cnt = __popc(f);
-  int rank = cnt;
+  // what the lane leaves open: the sum after its last end (everything when it has no end)
+  float tail = 0.0f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) tail = (f & (1u << j)) ? 0.0f : tail + p[j];
+  // inclusive segmented scan over the lanes of (tail, lane has an end); the piece counts ride in the low bits of the
+  // flag word (bit 31 = some lane up to here has an end)
+  const int cnt = __popc(f);
+  float sv = tail;
+  uint32_t sr = (uint32_t)cnt | (f ? 0x80000000u : 0u);
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const float uv = __shfl_up_sync(kFullMask, sv, d);
-    const unsigned uf = __shfl_up_sync(kFullMask, sf, d);
-    const int ur = __shfl_up_sync(kFullMask, rank, d);
+    const uint32_t ur = __shfl_up_sync(kFullMask, sr, d);
     if (lane >= d) {
-      if (!sf) sv += uv;
-      sf |= uf;
-      rank += ur;
+      if (!(sr & 0x80000000u)) sv += uv;
+      sr = (sr + (ur & 0x7fffffffu)) | (ur & 0x80000000u);
     }
   }
-  float carry = __shfl_up_sync(kFullMask, sv, 1);  // the open piece's sum over the lanes before this one
-  if (lane == 0) carry = 0.0f;                     // pieces never cross a group
-  rank -= cnt;                                     // pieces that end in earlier lanes
-  // the first end of the lane closes the piece that came in from the left
-  float* o = out + rank;
-  if (f & 1u) *o++ = s0 + carry;
-  if (f & 2u) *o++ = (f & 1u) ? s1 : s1 + carry;
-  if (f & 4u) *o++ = (f & 3u) ? s2 : s2 + carry;
-  if (f & 8u) *o = (f & 7u) ? s3 : s3 + carry;
+  float run = __shfl_up_sync(kFullMask, sv, 1);  // the open piece's sum over the lanes before this one
+  if (lane == 0) run = 0.0f;                     // pieces never cross a group
+  float* o = part + base + ((int)(sr & 0x7fffffffu) - cnt);  // pieces that end in earlier lanes come first
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    run += p[j];
+    if (f & (1u << j)) {
+      *o++ = run;
+      run = 0.0f;
+    }
+  }
 }
 
 template <int THREADS>
@@ -587,7 +605,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int32_t* __restrict__ slab_ptr = P.slab_ptr;
   const float* __restrict__ g_val = P.val;
   const uint16_t* __restrict__ g_lcol = P.lcol;
-  const uint8_t* __restrict__ g_flags = P.flags;
+  const uint16_t* __restrict__ g_flags = P.flags;
   const int32_t* __restrict__ g_base = P.group_base;
   float* __restrict__ g_part = P.part;
   const int slab_cols = P.slab_cols;
@@ -623,32 +641,23 @@ __global__ void __launch_bounds__(THREADS, 1)
         parity ^= 1u;
       }
       __syncthreads();
-      // groups of this slab's range: warp w takes group g0 + w, g0 + w + WARPS, ...; U groups' loads are in flight at once
-      constexpr int U = 4;
+      // groups of this slab's range: warp w takes group g0 + w, g0 + w + WARPS, ...
       const int g_end = kend / kPbGroup;
-      int g = k / kPbGroup + warp;
-      for (; g + (U - 1) * WARPS < g_end; g += U * WARPS) {
-        float4 v[U];
-        uint2 c[U];
-        uint32_t f[U];
-        int base[U];
+      for (int g = k / kPbGroup + warp; g < g_end; g += WARPS) {
+        const float* pv = g_val + (size_t)g * kPbGroup + lane * 4;
+        const uint16_t* pc = g_lcol + (size_t)g * kPbGroup + lane * 8;
+        float4 v[4];
+        uint4 c[2];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int i = (g + u * WARPS) * kPbGroup + lane * 4;
-          v[u] = ld_stream_f4(g_val + i, ps);
-          c[u] = ld_stream_u2(g_lcol + i, ps);
-          f[u] = __ldg(g_flags + (i >> 2));
-          base[u] = __ldg(g_base + g + u * WARPS);
+        for (int q = 0; q < 4; ++q) v[q] = ld_stream_f4(pv + q * 128, ps);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int4 t = ld_stream_i4(reinterpret_cast<const int32_t*>(pc + q * 256), ps);
+          c[q] = make_uint4((uint32_t)t.x, (uint32_t)t.y, (uint32_t)t.z, (uint32_t)t.w);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) group_pieces(v[u], c[u], f[u], base[u], lane, s_x, g_part);
-      }
-      for (; g < g_end; g += WARPS) {
-        const int i = g * kPbGroup + lane * 4;
-        const float4 v = ld_stream_f4(g_val + i, ps);
-        const uint2 c = ld_stream_u2(g_lcol + i, ps);
-        const uint32_t f = __ldg(g_flags + (i >> 2));
-        group_pieces(v, c, f, __ldg(g_base + g), lane, s_x, g_part);
+        const uint32_t f = __ldg(g_flags + (size_t)g * 32 + lane);
+        const int base = __ldg(g_base + g);
+        group_pieces(v, c, f, base, lane, s_x, g_part);
       }
       __syncthreads();  // every gather from this slab has been issued before the next one overwrites it
     }
@@ -684,7 +693,8 @@ __global__ void __launch_bounds__(THREADS, 4)
   extern __shared__ __align__(16) unsigned char s_raw[];
   float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's partials, then its row extents
   SegS* s_seg = reinterpret_cast<SegS*>(s_raw + (size_t)P.cap_words * 4);             // [max_panel_segs + 1]
-  uint16_t* s_hint = reinterpret_cast<uint16_t*>(s_seg + (P.max_panel_segs + 1));     // [cap_words / 32 + 1]
+  uint16_t* s_hint = reinterpret_cast<uint16_t*>(s_seg + (P.max_panel_segs + 1));     // [cap_words / 32 + 2]
+  uint8_t* s_end = reinterpret_cast<uint8_t*>(s_hint + (((P.cap_words >> 5) + 3) & ~1));  // [cap_words]: slot ends a row
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
   __shared__ float s_wv[WARPS];
@@ -712,6 +722,7 @@ __global__ void __launch_bounds__(THREADS, 4)
   int* s_rp = reinterpret_cast<int*>(s_prod + n);
   float bias_pre[kBiasAhead];
   if (!is_long) {
+    for (int i = tid; i * 4 < n; i += THREADS) reinterpret_cast<uint32_t*>(s_end)[i] = 0u;
     for (int i = tid; i <= trows; i += THREADS) s_rp[i] = __ldg(P.prow_ptr + d.r0 + i) - d.n0;
 #pragma unroll
     for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
@@ -720,11 +731,16 @@ __global__ void __launch_bounds__(THREADS, 4)
     }
   }
   __syncthreads();
-  // s_hint[c] = the segment that holds flat index 32 c
+  // s_hint[c] = the segment that holds flat index 32 c; s_end[j] = slot j is the last one of its row
   for (int sg = tid; sg < nseg; sg += THREADS) {
     const int o0 = s_seg[sg].off, o1 = s_seg[sg + 1].off;
     for (int c = (o0 + 31) >> 5; (c << 5) < o1; ++c) s_hint[c] = (uint16_t)sg;
   }
+  if (!is_long)
+    for (int i = tid; i < trows; i += THREADS) {
+      const int e = s_rp[i + 1];
+      if (e > s_rp[i]) s_end[e - 1] = 1;
+    }
   __syncthreads();
 
   // ---- gather: chunk c = flat indices [32 c, 32 c + 32), chunks dealt to the warps round-robin, U in flight ---------
@@ -778,17 +794,10 @@ __global__ void __launch_bounds__(THREADS, 4)
   int lead_slot = -1;     // >= 0: a row that began before j0 ends at this slot, and `lead` is my share of it
   bool closed = false;    // some row ends inside [j0, j1)
   if (j0 < j1) {
-    int lo = 0, hi = trows;  // the row that holds slot j0: the last r with s_rp[r] <= j0 (empty rows sort before it)
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_rp[mid] <= j0) lo = mid; else hi = mid;
-    }
-    int r = lo;
-    int next_end = s_rp[r + 1];
-    const bool began_before = s_rp[r] < j0;
+    const bool began_before = j0 > 0 && !s_end[j0 - 1];
     for (int j = j0; j < j1; ++j) {
       run += s_prod[j];
-      if (j + 1 == next_end) {  // row r ends here
+      if (s_end[j]) {  // a row ends here
         if (!closed && began_before) {
           lead = run;
           lead_slot = j;
@@ -797,10 +806,6 @@ __global__ void __launch_bounds__(THREADS, 4)
         }
         closed = true;
         run = 0.0f;
-        do {
-          ++r;
-          next_end = s_rp[r + 1];
-        } while (next_end == j + 1 && r + 1 < trows);  // skip empty rows
       }
     }
   }
@@ -887,7 +892,7 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
   const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.max_panel_segs + 1) * sizeof(PbSeg) +
-                      ((size_t)P.cap_words / 32 + 2) * sizeof(uint16_t);
+                      ((size_t)P.cap_words / 32 + 4) * sizeof(uint16_t) + (size_t)P.cap_words + 16;
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

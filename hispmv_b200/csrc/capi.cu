@@ -99,7 +99,7 @@ struct Matrix {
     int64_t b = ((int64_t)local_rows() + 1) * 4 + (((nnz + 3) & ~3LL) + 4) * 8;
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
     if (pb.d_val)  // val + lcol + flags per entry; perm + one partial per stream lane in use per piece; tables
-      b += pb.padded_nnz * 6 + pb.padded_nnz / 4 + pb.padded_nnz / kPbGroup * 4 + pb.num_pieces * (2 + 4 * (pb.d_part[1] ? 2 : 1)) +
+      b += pb.padded_nnz * 6 + pb.padded_nnz / 8 + pb.padded_nnz / kPbGroup * 4 + pb.num_pieces * (2 + 4 * (pb.d_part[1] ? 2 : 1)) +
            pb.num_seg * 8 + (num_tiles + 1) * 4 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
     for (auto* sm : slabs) b += sm->device_bytes();
     return b;
@@ -1476,7 +1476,7 @@ int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
   return HISPMV_OK;
 }
 
-int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint8_t* flags,
+int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,
                         int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
                         int32_t* seg_start_off, int32_t* work) {
   Matrix* m = get_matrix(c, idx);
@@ -1491,7 +1491,7 @@ int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, 
   if (slab_ptr) HISPMV_CUDA(cudaMemcpy(slab_ptr, a.d_slab_ptr, ((size_t)a.num_slabs + 1) * 4, k));
   if (vals) HISPMV_CUDA(cudaMemcpy(vals, a.d_val, (size_t)a.padded_nnz * 4, k));
   if (lcol) HISPMV_CUDA(cudaMemcpy(lcol, a.d_lcol, (size_t)a.padded_nnz * 2, k));
-  if (flags) HISPMV_CUDA(cudaMemcpy(flags, a.d_flags, (size_t)a.padded_nnz / 4, k));
+  if (flags) HISPMV_CUDA(cudaMemcpy(flags, a.d_flags, (size_t)a.padded_nnz / 8, k));
   if (group_base) HISPMV_CUDA(cudaMemcpy(group_base, a.d_group_base, ((size_t)a.padded_nnz / kPbGroup + 1) * 4, k));
   if (prow_ptr) HISPMV_CUDA(cudaMemcpy(prow_ptr, a.d_prow_ptr, ((size_t)m->local_rows() + 1) * 4, k));
   if (perm) HISPMV_CUDA(cudaMemcpy(perm, a.d_perm, (size_t)a.num_pieces * 2, k));

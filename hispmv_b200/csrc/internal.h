@@ -209,7 +209,7 @@ struct PbPlan {
   const int32_t* slab_ptr = nullptr;   // num_slabs+1 starts in blocked order (device)
   const float* val = nullptr;          // blocked order; padding entries are 0
   const uint16_t* lcol = nullptr;      // column - slab * slab_cols
-  const uint8_t* flags = nullptr;      // padded_nnz/4: bit j of byte i = entry 4i+j ends a piece
+  const uint16_t* flags = nullptr;     // padded_nnz/16: bit j of word i = entry 16i+j ends a piece
   const int32_t* group_base = nullptr; // padded_nnz/kPbGroup + 1: pieces that end before each group
   const uint16_t* perm = nullptr;      // per piece: position in its row's piece order - the panel's first position
   const int32_t* prow_ptr = nullptr;   // rows+1: CSR-style offsets of the pieces of every row
@@ -227,7 +227,7 @@ struct PbPlan {
   float* carry = nullptr;              // split LONG rows: as in AdaptivePlan
   unsigned int* counter = nullptr;
 };
-constexpr int32_t kPbGroup = 128;          // entries a warp handles per step: 4 per lane
+constexpr int32_t kPbGroup = 512;          // entries a warp handles per step: 16 consecutive ones per lane
 constexpr int32_t kPbMaxSlabCols = 57344;  // 224 KB of x: the largest slab one CTA's shared memory can hold
 // owned device arrays of a blocked plan (built by pb_order_device + pb_segments_device, freed by pb_free)
 struct PbArrays {
@@ -237,7 +237,7 @@ struct PbArrays {
   int32_t* d_slab_ptr = nullptr;
   float* d_val = nullptr;
   uint16_t* d_lcol = nullptr;
-  uint8_t* d_flags = nullptr;
+  uint16_t* d_flags = nullptr;
   int32_t* d_group_base = nullptr;
   int32_t* d_prow_ptr = nullptr;
   uint16_t* d_perm = nullptr;

@@ -255,8 +255,8 @@ class Engine:
             d["slab_ptr"] = np.empty(d["num_slabs"] + 1, np.int32)
             d["val"] = np.empty(d["padded_nnz"], np.float32)
             d["lcol"] = np.empty(d["padded_nnz"], np.uint16)
-            d["flags"] = np.empty(d["padded_nnz"] // 4, np.uint8)
-            d["group_base"] = np.empty(d["padded_nnz"] // 128 + 1, np.int32)
+            d["flags"] = np.empty(d["padded_nnz"] // 16, np.uint16)
+            d["group_base"] = np.empty(d["padded_nnz"] // 512 + 1, np.int32)
             d["prow_ptr"] = np.empty(n_y + 1, np.int32)
             d["perm"] = np.empty(d["num_pieces"], np.uint16)
             d["panel_seg"] = np.empty(d["num_panels"] + 1, np.int32)

@@ -216,11 +216,13 @@ int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
  * out8 = { slab_cols, num_slabs, padded_nnz, num_segments, max segments of a panel, pass-1 work ranges, panels,
  *          num_pieces }.
  * hispmv_plan_blocked copies the plan to the host (any pointer may be NULL):
- *   slab_ptr[num_slabs+1]      slab starts in the slab-major order (multiples of 128)
- *   vals / lcol [padded_nnz]   value and column - slab*slab_cols of every entry (padding entries are zero)
- *   flags[padded_nnz/4]        bit j of byte i: entry 4i+j is the last of its PIECE (consecutive entries of one row
- *                              inside one 128-entry group); pieces are numbered in slab-major order
- *   group_base[padded_nnz/128+1]  pieces that end before each group
+ *   slab_ptr[num_slabs+1]      slab starts in the slab-major order (multiples of 512)
+ *   vals / lcol [padded_nnz]   value and column - slab*slab_cols of every entry (padding entries are zero); inside a
+ *                              512-entry group entry e = 16*lane + w is stored at ((w/4)*32 + lane)*4 + w%4 (vals) and
+ *                              ((w/8)*32 + lane)*8 + w%8 (lcol), the order a warp's vector loads consume
+ *   flags[padded_nnz/16]       bit j of word i: entry 16i+j is the last of its PIECE (consecutive entries of one row
+ *                              inside one 512-entry group); pieces are numbered in slab-major order
+ *   group_base[padded_nnz/512+1]  pieces that end before each group
  *   prow_ptr[local_rows+1]     CSR-style offsets of every row's pieces (slab order inside a row); the panels
  *                              (hispmv_plan_tiles / hispmv_plan_tile_chunks) are cut over these, not over nonzeros
  *   perm[num_pieces]           a piece's position in that per-row order minus the first position of its panel
@@ -228,7 +230,7 @@ int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
  *                              (first piece id, pieces of the same panel in earlier slabs)
  *   work[2*ranges]             pass-1 [begin, end) per resident CTA */
 int hispmv_plan_blocked_info(hispmv_ctx* ctx, int idx, int64_t* out8);
-int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint8_t* flags,
+int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,
                         int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
                         int32_t* seg_start_off, int32_t* work);
 

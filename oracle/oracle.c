@@ -399,16 +399,33 @@ int64_t oracle_adaptive_split_rows(int rows, const int* row_ptr, int T, int CH, 
  * this is the same idea with the GPU engine's sizes, single-threaded.
  *   slab s        = columns [s*W, (s+1)*W)
  *   blocked order : slab-major, CSR order inside a slab; every slab starts at a multiple of G (the group
- *                   size, 128); the gaps are padding (val 0, lcol 0, no flag)
- *   per entry     : val, lcol = col - s*W, and an end flag (4 per byte, bit j = entry 4*i+j) on the last
+ *                   size, 512 = 32 lanes x 16 entries); the gaps are padding (val 0, lcol 0, no flag)
+ *   per entry     : val, lcol = col - s*W, and an end flag (16 per word, bit j = entry 16*i+j) on the last
  *                   entry of every PIECE = maximal run of consecutive entries of one row inside one group
+ *   storage       : inside a group, entry e = 16*lane + w is stored where a warp's coalesced vector loads hand
+ *                   lane `lane` its 16 consecutive entries: val at ((w/4)*32 + lane)*4 + w%4, lcol at
+ *                   ((w/8)*32 + lane)*8 + w%8 (pb_phys_val / pb_phys_lcol); flags and piece numbers follow the
+ *                   logical order
  *   pieces        : numbered in blocked order; group_base[g] = pieces ending before group g;
  *                   prow_ptr = CSR-style offsets of the pieces of every row (a row's pieces in slab order);
  *                   piece_pcsr[q] = position of piece q in that per-row order, piece_slab[q] its slab
  * oracle_pb_order returns the padded length (sizes with o_val == NULL); *num_pieces gets the piece count.
  * ---------------------------------------------------------------------------------------------- */
+static int64_t pb_phys_val(int64_t k, int G) {
+  const int64_t g = k / G, e = k % G;
+  const int per = G / 32;
+  const int64_t lane = e / per, w = e % per;
+  return g * G + ((w / 4) * 32 + lane) * 4 + w % 4;
+}
+static int64_t pb_phys_lcol(int64_t k, int G) {
+  const int64_t g = k / G, e = k % G;
+  const int per = G / 32;
+  const int64_t lane = e / per, w = e % per;
+  return g * G + ((w / 8) * 32 + lane) * 8 + w % 8;
+}
+
 int64_t oracle_pb_order(int rows, int cols, const int* row_ptr, const int* col, const float* val, int W, int G,
-                        int* slab_ptr, float* o_val, uint16_t* o_lcol, uint8_t* o_flags, int* group_base,
+                        int* slab_ptr, float* o_val, uint16_t* o_lcol, uint16_t* o_flags, int* group_base,
                         int* prow_ptr, int* piece_pcsr, int* piece_slab, int64_t* num_pieces) {
   const int64_t nnz = row_ptr[rows];
   const int S = (int)(((int64_t)cols + W - 1) / W);
@@ -432,7 +449,7 @@ int64_t oracle_pb_order(int rows, int cols, const int* row_ptr, const int* col, 
   if (o_val) {
     memset(o_val, 0, sizeof(float) * (size_t)pos);
     memset(o_lcol, 0, sizeof(uint16_t) * (size_t)pos);
-    memset(o_flags, 0, (size_t)(pos / 4));
+    memset(o_flags, 0, sizeof(uint16_t) * (size_t)(pos / 16));
   }
   for (r = 0; r < rows; ++r)
     for (j = row_ptr[r]; j < row_ptr[r + 1]; ++j) {
@@ -440,8 +457,8 @@ int64_t oracle_pb_order(int rows, int cols, const int* row_ptr, const int* col, 
       const int64_t dst = start[sl] + cnt[sl]++;
       brow[dst] = r;
       if (o_val) {
-        o_val[dst] = val[j];
-        o_lcol[dst] = (uint16_t)(col[j] - sl * W);
+        o_val[pb_phys_val(dst, G)] = val[j];
+        o_lcol[pb_phys_lcol(dst, G)] = (uint16_t)(col[j] - sl * W);
       }
     }
   /* pieces: an entry ends one when the next position is another row, padding, or the next group */
@@ -450,7 +467,7 @@ int64_t oracle_pb_order(int rows, int cols, const int* row_ptr, const int* col, 
     if (k % G == 0 && group_base) group_base[k / G] = (int)np;
     if (brow[k] < 0) continue;
     if ((k + 1) % G == 0 || brow[k + 1] != brow[k]) {
-      if (o_flags) o_flags[k / 4] |= (uint8_t)(1u << (k % 4));
+      if (o_flags) o_flags[k / 16] |= (uint16_t)(1u << (k % 16));
       if (prow_ptr) prow_ptr[brow[k] + 1]++;
       ++np;
     }

@@ -266,7 +266,7 @@ def select_blocked(rows, cols, nnz, near, cmp_, allow_split=1):
     return oracle().oracle_select_blocked(rows, cols, nnz, near, cmp_, allow_split)
 
 
-def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=128, n_cta=0, slab_cost=0):
+def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
     """The blocked strategy's plan for this CSR (oracle_pb_order / oracle_adaptive_tiles over the pieces /
     oracle_pb_segments / oracle_pb_work) as a dict of numpy arrays."""
     rp, ci = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32)
@@ -282,7 +282,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=128, n_cta=0, slab_cost=0):
                                None, None, C.byref(npieces))
     val = np.zeros(padded, np.float32)
     lcol = np.zeros(padded, np.uint16)
-    flags = np.zeros(padded // 4, np.uint8)
+    flags = np.zeros(padded // 16, np.uint16)
     group_base = np.zeros(padded // align + 1, np.int32)
     prow_ptr = np.zeros(rows + 1, np.int32)
     pcsr = np.zeros(max(npieces.value, 1), np.int32)

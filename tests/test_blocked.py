@@ -26,13 +26,19 @@ def _powerlaw(rng, rows, cols, heavy=3, max_len=20000):
 
 def _walk_plan(d, rows, CH, W, cols, x):
     """numpy emulation of pass 1 + pass 2 over a plan dict: returns A x in float64."""
-    G = 128
+    G = 512
     slab_of = np.zeros(d["padded_nnz"], np.int64)
     for s in range(d["num_slabs"]):
         slab_of[d["slab_ptr"][s]:d["slab_ptr"][s + 1]] = s
-    prod = d["val"].astype(np.float64) * x[np.minimum(slab_of * W + d["lcol"], cols - 1)]
+    # storage inside a group: entry e = 16*lane + w sits where coalesced vector loads hand lane `lane` its 16 entries
+    k = np.arange(d["padded_nnz"], dtype=np.int64)
+    g, e = k // G, k % G
+    lane, w = e // 16, e % 16
+    val = d["val"][g * G + ((w // 4) * 32 + lane) * 4 + w % 4]
+    lcol = d["lcol"][g * G + ((w // 8) * 32 + lane) * 8 + w % 8]
+    prod = val.astype(np.float64) * x[np.minimum(slab_of * W + lcol, cols - 1)]
     # pass 1: one partial per piece; pieces never cross a group of G entries
-    fl = np.unpackbits(d["flags"][:, None], axis=1, bitorder="little")[:, :4].reshape(-1).astype(bool)
+    fl = np.unpackbits(d["flags"].view(np.uint8)[:, None], axis=1, bitorder="little").reshape(-1).astype(bool)
     part = np.zeros(d["num_pieces"])
     q, run = 0, 0.0
     for k in range(d["padded_nnz"]):
@@ -79,12 +85,12 @@ def test_oracle_blocked_plan_reproduces_the_csr_product(seed, W, B, T, CH):
     y64, scale = ol.spmv_f64(rp, ci, vv, x)
     assert np.max(np.abs(y - y64) / np.maximum(scale, 1e-30)) < 1e-12
     # layout facts: slab starts aligned, ascending; lcol inside the slab; work ranges tile the blocked order
-    assert np.all(d["slab_ptr"] % 128 == 0) and np.all(np.diff(d["slab_ptr"]) >= 0)
+    assert np.all(d["slab_ptr"] % 512 == 0) and np.all(np.diff(d["slab_ptr"]) >= 0)
     assert d["lcol"].max() < W and d["num_pieces"] <= ci.size and np.all(np.diff(d["prow_ptr"]) >= 0)
     assert np.all((np.diff(d["prow_ptr"]) > 0) == (np.diff(rp) > 0))     # a row has pieces iff it has nonzeros
     w = d["work"]
     assert w[0, 0] == 0 and w[-1, 1] == d["padded_nnz"] and np.array_equal(w[1:, 0], w[:-1, 1])
-    assert np.all(w % 128 == 0)
+    assert np.all(w % 512 == 0)
 
 
 def test_oracle_select_blocked_rule():

@@ -238,6 +238,27 @@ __global__ void pb_panel_seg_kernel(const uint64_t* __restrict__ seg_key_sorted,
   panel_seg[p] = (int32_t)lo;
 }
 
+// chunks: segment i (in panel-major order, `len` pieces from piece id seg[i].start) becomes ceil(len / kPbChunk) runs
+__global__ void pb_chunk_count_kernel(const int32_t* __restrict__ len_sorted, int64_t nseg, int32_t* __restrict__ cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nseg) cnt[i] = (len_sorted[i] + kPbChunk - 1) / kPbChunk;
+}
+__global__ void pb_chunk_emit_kernel(const PbSeg* __restrict__ seg, const int32_t* __restrict__ len_sorted,
+                                     const int32_t* __restrict__ first, int64_t nseg, int2* __restrict__ chunk) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseg) return;
+  const int32_t len = len_sorted[i], start = seg[i].start;
+  int64_t o = first[i];
+  for (int32_t k = 0; k < len; k += kPbChunk) chunk[o++] = make_int2(start + k, min(kPbChunk, len - k));
+}
+__global__ void pb_panel_chunk_kernel(const int32_t* __restrict__ panel_seg, const int32_t* __restrict__ first,
+                                      int64_t np, int64_t nseg, int32_t total, int32_t* __restrict__ panel_chunk) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > np) return;
+  const int32_t sgi = panel_seg[p];
+  panel_chunk[p] = sgi < nseg ? first[sgi] : total;
+}
+
 __global__ void pb_max_segs_kernel(const int32_t* __restrict__ panel_seg, int64_t np, int* __restrict__ out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int v = 0;
@@ -264,6 +285,8 @@ void pb_free(PbArrays* a) {
   cudaFree(a->d_perm);
   cudaFree(a->d_panel_seg);
   cudaFree(a->d_seg);
+  cudaFree(a->d_panel_chunk);
+  cudaFree(a->d_chunk);
   cudaFree(a->d_work);
   cudaFree(a->d_part[0]);
   cudaFree(a->d_part[1]);
@@ -462,6 +485,27 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
                                                              G.as<int32_t>(), d_desc, S, nseg, a->d_seg);
   pb_panel_seg_kernel<<<blocks_for(num_panels + 1, B), B, 0, stream>>>(skeys.Current(), nseg, num_panels, S,
                                                                       a->d_panel_seg);
+  // the chunk table pass 2 walks: every segment cut into runs of at most kPbChunk pieces
+  DevBuf ccnt, cfirst;
+  if ((st = ccnt.alloc((size_t)nseg * 4)) || (st = cfirst.alloc((size_t)nseg * 4))) return st;
+  pb_chunk_count_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(len_sorted.as<int32_t>(), nseg, ccnt.as<int32_t>());
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, ccnt.as<int32_t>(), cfirst.as<int32_t>(), nseg, stream));
+  if ((st = grow(tmp, tb, need))) return st;
+  HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, ccnt.as<int32_t>(), cfirst.as<int32_t>(), nseg, stream));
+  int32_t h_c[2] = {0, 0};
+  HISPMV_CUDA(cudaMemcpyAsync(&h_c[0], ccnt.as<int32_t>() + (nseg - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaMemcpyAsync(&h_c[1], cfirst.as<int32_t>() + (nseg - 1), 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  const int64_t nchunk = (int64_t)h_c[0] + h_c[1];
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_chunk, ((size_t)nchunk + 8) * sizeof(int2)));
+  HISPMV_CUDA(cudaMemsetAsync(a->d_chunk + nchunk, 0, 8 * sizeof(int2), stream));  // reads past a panel's last pair see count 0
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_panel_chunk, ((size_t)num_panels + 1) * 4));
+  pb_chunk_emit_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(a->d_seg, len_sorted.as<int32_t>(), cfirst.as<int32_t>(),
+                                                              nseg, a->d_chunk);
+  pb_panel_chunk_kernel<<<blocks_for(num_panels + 1, B), B, 0, stream>>>(a->d_panel_seg, cfirst.as<int32_t>(), num_panels,
+                                                                        nseg, (int32_t)nchunk, a->d_panel_chunk);
+  HISPMV_CUDA(cudaGetLastError());
+  a->num_chunks = nchunk;
   DevBuf mx;
   if ((st = mx.alloc(sizeof(int)))) return st;
   HISPMV_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
@@ -536,28 +580,43 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
 // ================================================================================================================
 namespace {
 
-constexpr int kExpandThreads = 1024;
+constexpr int kExpandThreads = 512;
 constexpr int kBulkPiece = 4096;  // floats per cp.async.bulk (one copy costs its issuing thread ~650 cycles: 12 lanes
                                   // issue the 12 pieces of a 48 K-column slab side by side)
 
 // One warp, one group of 512 consecutive entries: lane l holds entries 16 l .. 16 l + 15 (values v[], local columns
-// c[], end flags f).  Every piece's total is stored at part[base + rank of the piece inside the group].
-// History: 4 entries per lane with branches and a staging buffer cost 240 warp instructions per 128 entries and was
-// issue-bound at 35 % of HBM bandwidth; straight-line code 162 (46 %).  Sixteen entries per lane amortise the warp-wide
-// scan (the only cross-lane step) over four times as many entries.  The shuffle tree and the in-lane order are fixed,
-// so the sums are bit-reproducible.
-__device__ __forceinline__ void group_pieces(const float4 (&v)[4], const uint4 (&c)[2], const uint32_t f, const int base,
-                                             const int lane, const float* __restrict__ s_x,
-                                             float* __restrict__ part) {
+// c[], end flags f).  Every piece's total goes to stage[rank of the piece inside the group]; returns the group's piece
+// count.  History (C2, 100 M entries): 4 entries per lane with branches cost 240 warp instructions per 128 entries and
+// was issue-bound at 35 % of HBM bandwidth; straight-line code 162 (46 %); 16 entries per lane amortise the warp-wide
+// scan -- the only cross-lane step -- over four times as many entries (71 M instructions instead of 187 M), but with
+// every lane storing its own pieces the 16 scalar stores of a lane hit 16 different sectors (7.5x write amplification,
+// 286 us): the pieces are staged in shared memory and leave as coalesced 128-byte stores.  The shuffle tree and the
+// in-lane order are fixed, so the sums are bit-reproducible.
+struct GroupRegs {
+  float4 v[4];
+  uint4 c[2];
+  uint32_t f;
+  int base;
+};
+
+__device__ __forceinline__ int group_pieces(const GroupRegs& G, const int lane, const float* __restrict__ s_x,
+                                            float* __restrict__ stage) {
   float p[16];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const uint32_t w0 = k < 2 ? (k == 0 ? c[0].x : c[0].z) : (k == 2 ? c[1].x : c[1].z);
-    const uint32_t w1 = k < 2 ? (k == 0 ? c[0].y : c[0].w) : (k == 2 ? c[1].y : c[1].w);
-    p[4 * k + 0] = v[k].x * s_x[w0 & 0xffffu];
-    p[4 * k + 1] = v[k].y * s_x[w0 >> 16];
-    p[4 * k + 2] = v[k].z * s_x[w1 & 0xffffu];
-    p[4 * k + 3] = v[k].w * s_x[w1 >> 16];
+    const uint32_t w0 = k < 2 ? (k == 0 ? G.c[0].x : G.c[0].z) : (k == 2 ? G.c[1].x : G.c[1].z);
+    const uint32_t w1 = k < 2 ? (k == 0 ? G.c[0].y : G.c[0].w) : (k == 2 ? G.c[1].y : G.c[1].w);
+    p[4 * k + 0] = G.v[k].x * s_x[w0 & 0xffffu];
+    p[4 * k + 1] = G.v[k].y * s_x[w0 >> 16];
+    p[4 * k + 2] = G.v[k].z * s_x[w1 & 0xffffu];
+    p[4 * k + 3] = G.v[k].w * s_x[w1 >> 16];
+  }
+  const uint32_t f = G.f;
+  if (__all_sync(kFullMask, f == 0xffffu)) {  // every entry is its own piece (hypersparse rows): products are the partials
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<float4*>(stage + 16 * lane + 4 * k) = make_float4(p[4 * k], p[4 * k + 1], p[4 * k + 2], p[4 * k + 3]);
+    return kPbGroup;
   }
   // what the lane leaves open: the sum after its last end (everything when it has no end)
   float tail = 0.0f;
@@ -579,7 +638,8 @@ __device__ __forceinline__ void group_pieces(const float4 (&v)[4], const uint4 (
   }
   float run = __shfl_up_sync(kFullMask, sv, 1);  // the open piece's sum over the lanes before this one
   if (lane == 0) run = 0.0f;                     // pieces never cross a group
-  float* o = part + base + ((int)(sr & 0x7fffffffu) - cnt);  // pieces that end in earlier lanes come first
+  const int incl = (int)(sr & 0x7fffffffu);
+  float* o = stage + (incl - cnt);               // pieces that end in earlier lanes come first
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     run += p[j];
@@ -588,6 +648,7 @@ __device__ __forceinline__ void group_pieces(const float4 (&v)[4], const uint4 (
       run = 0.0f;
     }
   }
+  return __shfl_sync(kFullMask, incl, 31);
 }
 
 template <int THREADS>
@@ -598,6 +659,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = THREADS / 32;
+  float* s_stage = s_x + P.slab_cols + warp * kPbGroup;  // this warp's pieces of one group
   const int2 w = P.work[blockIdx.x];
   if (w.x >= w.y) return;
   if (tid == 0) mbar_init(&bar, 1);
@@ -621,6 +683,19 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint64_t ps = policy_evict_first(), pk = policy_evict_last();
   const bool x_aligned = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   uint32_t parity = 0;
+  auto load_group = [&](int g, GroupRegs& G) {
+    const float* pv = g_val + (size_t)g * kPbGroup + lane * 4;
+    const uint16_t* pc = g_lcol + (size_t)g * kPbGroup + lane * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) G.v[q] = ld_stream_f4(pv + q * 128, ps);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int4 t = ld_stream_i4(reinterpret_cast<const int32_t*>(pc + q * 256), ps);
+      G.c[q] = make_uint4((uint32_t)t.x, (uint32_t)t.y, (uint32_t)t.z, (uint32_t)t.w);
+    }
+    G.f = __ldg(g_flags + (size_t)g * 32 + lane);
+    G.base = __ldg(g_base + g);
+  };
   int k = w.x;
   while (k < w.y) {
     const int kend = min(w.y, __ldg(slab_ptr + s + 1));
@@ -635,29 +710,28 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int p = tid * kBulkPiece; p < nb; p += 32 * kBulkPiece)
           bulk_g2s_hint(s_x + p, x + c0 + p, (uint32_t)min(kBulkPiece, nb - p) * 4u, &bar, pk);
       }
+      // groups of this slab's range: warp w takes group g0 + w, g0 + w + WARPS, ...; the next group's loads are issued
+      // before the current one is worked on (the first one's travel with the slab)
+      const int g_end = kend / kPbGroup;
+      int g = k / kPbGroup + warp;
+      GroupRegs cur, nxt;
+      if (g < g_end) load_group(g, cur);
       for (int i = nb + tid; i < n; i += THREADS) s_x[i] = ld_x_keep(x + c0 + i, pk);
       if (nb > 0) {
         if (tid == 0) mbar_wait(&bar, parity);
         parity ^= 1u;
       }
       __syncthreads();
-      // groups of this slab's range: warp w takes group g0 + w, g0 + w + WARPS, ...
-      const int g_end = kend / kPbGroup;
-      for (int g = k / kPbGroup + warp; g < g_end; g += WARPS) {
-        const float* pv = g_val + (size_t)g * kPbGroup + lane * 4;
-        const uint16_t* pc = g_lcol + (size_t)g * kPbGroup + lane * 8;
-        float4 v[4];
-        uint4 c[2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = ld_stream_f4(pv + q * 128, ps);
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int4 t = ld_stream_i4(reinterpret_cast<const int32_t*>(pc + q * 256), ps);
-          c[q] = make_uint4((uint32_t)t.x, (uint32_t)t.y, (uint32_t)t.z, (uint32_t)t.w);
-        }
-        const uint32_t f = __ldg(g_flags + (size_t)g * 32 + lane);
-        const int base = __ldg(g_base + g);
-        group_pieces(v, c, f, base, lane, s_x, g_part);
+      while (g < g_end) {
+        const int gn = g + WARPS;
+        if (gn < g_end) load_group(gn, nxt);
+        const int count = group_pieces(cur, lane, s_x, s_stage);
+        __syncwarp();
+        float* out = g_part + cur.base;
+        for (int i = lane; i < count; i += 32) out[i] = s_stage[i];
+        __syncwarp();
+        cur = nxt;
+        g = gn;
       }
       __syncthreads();  // every gather from this slab has been issued before the next one overwrites it
     }
@@ -669,32 +743,28 @@ __global__ void __launch_bounds__(THREADS, 1)
 // ================================================================================================================
 // pass 2: one CTA per panel
 // ================================================================================================================
-// The first version of this kernel spent 130 thread instructions per piece (a per-lane segment walk with a shuffle per
-// step, and a lane-per-row reduction whose trip count followed the longest row of each pass) and was issue-bound at
-// 20 % of HBM bandwidth.  Now:
-//   gather   the panel's pieces are visited in flat (slab, row) order, 32 per warp step; s_hint[c] names the segment that
-//            holds flat index 32c, so a lane finds its segment with one or two compares, and its source is one add
-//            (s_seg[].delta = start - off); the partial goes to its place in per-row order (perm)
-//   reduce   every thread adds up C consecutive slots (C odd: no bank conflicts), closing rows as it passes their ends;
-//            a row that spans threads is closed by a segmented scan over the threads' open sums (shuffles inside a warp,
-//            shared memory across the eight warps, fixed order); the closing thread leaves the row's total in the row's
-//            last slot and a final row-per-thread pass applies alpha / beta / ReLU with coalesced bias loads and y stores
+// History (C2, 30 M pieces): the first version spent 130 thread instructions per piece (a per-lane segment walk with a
+// shuffle per step, a lane-per-row reduction whose trip count followed the longest row of each pass) and was
+// issue-bound at 20 % of HBM bandwidth; hints + a thread-sequential sweep that tracked row indices still paid for the
+// 31 % empty rows of C2 one by one.  Now:
+//   gather   the plan cuts every (panel, slab) segment into runs of at most 16 pieces (PbPlan::chunk); a half-warp
+//            takes one run per step -- descriptor broadcast, 16 partials and their 16-bit places (perm) coalesced --
+//            and drops each partial at its place in the panel's per-row order; four runs in flight, the next four
+//            descriptors already requested
+//   reduce   s_bits marks the slot that ends each row; every thread adds up C consecutive slots (C odd: no bank
+//            conflicts) and closes rows at the marks; a row that spans threads is closed by a segmented scan over the
+//            threads' open sums (shuffles inside a warp, shared memory across the eight warps, fixed order); the
+//            row's total waits in its last slot and a final row-per-thread pass applies alpha / beta / ReLU with
+//            coalesced bias loads and y stores
 constexpr int kReduceThreads = 256;
-constexpr int kBiasAhead = 8;  // bias values per thread requested before the gather (rows tid, tid + 256, ...)
-
-struct SegS {  // a segment in shared memory
-  int32_t off;    // first flat index of the segment inside the panel
-  int32_t delta;  // piece id of flat index i = i + delta
-};
+constexpr int kBiasAhead = 6;  // bias values per thread requested before the gather (rows tid, tid + 256, ...)
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 4)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's partials, then its row extents
-  SegS* s_seg = reinterpret_cast<SegS*>(s_raw + (size_t)P.cap_words * 4);             // [max_panel_segs + 1]
-  uint16_t* s_hint = reinterpret_cast<uint16_t*>(s_seg + (P.max_panel_segs + 1));     // [cap_words / 32 + 2]
-  uint8_t* s_end = reinterpret_cast<uint8_t*>(s_hint + (((P.cap_words >> 5) + 3) & ~1));  // [cap_words]: slot ends a row
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)P.cap_words * 4);  // [cap_words / 32 + 2]
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
   __shared__ float s_wv[WARPS];
@@ -702,27 +772,29 @@ __global__ void __launch_bounds__(THREADS, 4)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t = P.panel_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
-  const int sp0 = __ldg(P.panel_seg + t);
-  const int nseg = __ldg(P.panel_seg + t + 1) - sp0;
+  const int ch0 = __ldg(P.panel_chunk + t);
+  const int nch = __ldg(P.panel_chunk + t + 1) - ch0;
   const int n = d.n1 - d.n0;
   const bool is_long = d.chunk >= 0;
   const int trows = d.r1 - d.r0;
   const uint64_t ps = policy_evict_first();
   const float* __restrict__ g_part = P.part;
   const uint16_t* __restrict__ g_perm = P.perm;
-  for (int i = tid; i < nseg; i += THREADS) {
-    const int2 v = __ldg(reinterpret_cast<const int2*>(P.seg) + sp0 + i);
-    s_seg[i].off = v.y;
-    s_seg[i].delta = v.x - v.y;
-  }
-  if (tid == 0) {
-    s_seg[nseg].off = n;
-    s_seg[nseg].delta = 0;
+  const int2* __restrict__ g_chunk = P.chunk + ch0;
+
+  // ---- gather: half-warp h takes run h, h + 16, ...; U runs in flight, the next U descriptors on their way ---------
+  constexpr int HALVES = THREADS / 16, U = 4;
+  const int hl = tid & 15, h = tid >> 4;
+  int2 nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int ci = h + u * HALVES;
+    nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
   }
   int* s_rp = reinterpret_cast<int*>(s_prod + n);
   float bias_pre[kBiasAhead];
   if (!is_long) {
-    for (int i = tid; i * 4 < n; i += THREADS) reinterpret_cast<uint32_t*>(s_end)[i] = 0u;
+    for (int i = tid; (i << 5) < n + 32; i += THREADS) s_bits[i] = 0u;
     for (int i = tid; i <= trows; i += THREADS) s_rp[i] = __ldg(P.prow_ptr + d.r0 + i) - d.n0;
 #pragma unroll
     for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
@@ -730,40 +802,24 @@ __global__ void __launch_bounds__(THREADS, 4)
       bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
     }
   }
-  __syncthreads();
-  // s_hint[c] = the segment that holds flat index 32 c; s_end[j] = slot j is the last one of its row
-  for (int sg = tid; sg < nseg; sg += THREADS) {
-    const int o0 = s_seg[sg].off, o1 = s_seg[sg + 1].off;
-    for (int c = (o0 + 31) >> 5; (c << 5) < o1; ++c) s_hint[c] = (uint16_t)sg;
-  }
-  if (!is_long)
-    for (int i = tid; i < trows; i += THREADS) {
-      const int e = s_rp[i + 1];
-      if (e > s_rp[i]) s_end[e - 1] = 1;
-    }
-  __syncthreads();
-
-  // ---- gather: chunk c = flat indices [32 c, 32 c + 32), chunks dealt to the warps round-robin, U in flight ---------
-  constexpr int U = 4;
-  const int nchunks = (n + 31) >> 5;
   float acc = 0.0f;
-  for (int c0 = warp; c0 < nchunks; c0 += WARPS * U) {
-    float p[U];
-    uint32_t q[U];
-    bool ok[U];
+  for (int cb = h; cb < nch; cb += HALVES * U) {
+    int2 cur[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int c = c0 + u * WARPS;
-      const int i = (c << 5) + lane;
-      ok[u] = i < n;
+      cur[u] = nxt[u];
+      const int ci = cb + (u + U) * HALVES;
+      nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
+    }
+    float p[U];
+    uint32_t q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
       p[u] = 0.0f;
       q[u] = 0;
-      if (ok[u]) {
-        int sg = s_hint[c];
-        while (i >= s_seg[sg + 1].off) ++sg;
-        const int src = i + s_seg[sg].delta;
-        p[u] = ld_stream_f1(g_part + src, ps);
-        if (!is_long) q[u] = ld_stream_u16(g_perm + src, ps);
+      if (hl < cur[u].y) {
+        p[u] = ld_stream_f1(g_part + cur[u].x + hl, ps);
+        if (!is_long) q[u] = ld_stream_u16(g_perm + cur[u].x + hl, ps);
       }
     }
     if (is_long) {
@@ -772,7 +828,7 @@ __global__ void __launch_bounds__(THREADS, 4)
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (ok[u]) s_prod[q[u]] = p[u];
+        if (hl < cur[u].y) s_prod[q[u]] = p[u];
     }
   }
   if (is_long) {
@@ -786,6 +842,11 @@ __global__ void __launch_bounds__(THREADS, 4)
     return;
   }
   __syncthreads();
+  for (int i = tid; i < trows; i += THREADS) {  // mark the slot that ends each non-empty row
+    const int e = s_rp[i + 1];
+    if (e > s_rp[i]) atomicOr(&s_bits[(e - 1) >> 5], 1u << ((e - 1) & 31));
+  }
+  __syncthreads();
 
   // ---- reduce: thread tid sums the slots [j0, j1) of the per-row order ------------------------------------------
   const int C = ((n + THREADS - 1) / THREADS) | 1;
@@ -794,18 +855,23 @@ __global__ void __launch_bounds__(THREADS, 4)
   int lead_slot = -1;     // >= 0: a row that began before j0 ends at this slot, and `lead` is my share of it
   bool closed = false;    // some row ends inside [j0, j1)
   if (j0 < j1) {
-    const bool began_before = j0 > 0 && !s_end[j0 - 1];
-    for (int j = j0; j < j1; ++j) {
-      run += s_prod[j];
-      if (s_end[j]) {  // a row ends here
-        if (!closed && began_before) {
-          lead = run;
-          lead_slot = j;
-        } else {
-          s_prod[j] = run;  // the row's total waits in its last slot for the epilogue
+    const bool began_before = j0 > 0 && !((s_bits[(j0 - 1) >> 5] >> ((j0 - 1) & 31)) & 1u);
+    int j = j0;
+    while (j < j1) {
+      const uint32_t word = s_bits[j >> 5];
+      const int stop = min(j1, (j | 31) + 1);
+      for (; j < stop; ++j) {
+        run += s_prod[j];
+        if ((word >> (j & 31)) & 1u) {  // a row ends here
+          if (!closed && began_before) {
+            lead = run;
+            lead_slot = j;
+          } else {
+            s_prod[j] = run;  // the row's total waits in its last slot for the epilogue
+          }
+          closed = true;
+          run = 0.0f;
         }
-        closed = true;
-        run = 0.0f;
       }
     }
   }
@@ -852,30 +918,28 @@ __global__ void __launch_bounds__(THREADS, 4)
   __syncthreads();
 
   // ---- epilogue: one thread per row, coalesced ------------------------------------------------------------------
-  int pass = 0;
-  for (int i = tid; i < trows; i += THREADS, ++pass) {
+  auto finish_row = [&](int i, float bias) {
     const int b = s_rp[i], e = s_rp[i + 1];
-    const float s = e > b ? s_prod[e - 1] : 0.0f;
-    float bias = 0.0f;
-    if (pass < kBiasAhead) {
-#pragma unroll
-      for (int a = 0; a < kBiasAhead; ++a)
-        if (a == pass) bias = bias_pre[a];
-    } else if (ep.beta != 0.0f) {
-      bias = ep.bias[d.r0 + i];
-    }
-    float v = ep.alpha * s;
+    const float sum = e > b ? s_prod[e - 1] : 0.0f;
+    float v = ep.alpha * sum;
     if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
     if (ep.relu) v = fmaxf(v, 0.0f);
     store_y(y, d.r0 + i, v, ep.y_mc);
+  };
+#pragma unroll
+  for (int a = 0; a < kBiasAhead; ++a) {
+    const int i = tid + a * THREADS;
+    if (i < trows) finish_row(i, bias_pre[a]);
   }
+  for (int i = tid + kBiasAhead * THREADS; i < trows; i += THREADS)
+    finish_row(i, ep.beta != 0.0f ? ep.bias[d.r0 + i] : 0.0f);
 }
 
 }  // namespace
 
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s) {
   if (P.num_work <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.slab_cols * 4;
+  const size_t smem = (size_t)P.slab_cols * 4 + (size_t)(kExpandThreads / 32) * kPbGroup * 4;
   static size_t configured = 0;
   if (smem > configured) {
     HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<kExpandThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -891,8 +955,7 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   (void)A;
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.max_panel_segs + 1) * sizeof(PbSeg) +
-                      ((size_t)P.cap_words / 32 + 4) * sizeof(uint16_t) + (size_t)P.cap_words + 16;
+  const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.cap_words / 32 + 4) * sizeof(uint32_t);
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

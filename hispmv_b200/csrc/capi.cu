@@ -100,7 +100,7 @@ struct Matrix {
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
     if (pb.d_val)  // val + lcol + flags per entry; perm + one partial per stream lane in use per piece; tables
       b += pb.padded_nnz * 6 + pb.padded_nnz / 8 + pb.padded_nnz / kPbGroup * 4 + pb.num_pieces * (2 + 4 * (pb.d_part[1] ? 2 : 1)) +
-           pb.num_seg * 8 + (num_tiles + 1) * 4 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
+           pb.num_seg * 8 + pb.num_chunks * 8 + (num_tiles + 1) * 8 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
     for (auto* sm : slabs) b += sm->device_bytes();
     return b;
   }
@@ -744,6 +744,8 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.panel_seg = m->pb.d_panel_seg;
       P.seg = m->pb.d_seg;
       P.max_panel_segs = m->pb.max_panel_segs;
+      P.panel_chunk = m->pb.d_panel_chunk;
+      P.chunk = m->pb.d_chunk;
       P.work = m->pb.d_work;
       P.num_work = m->pb.num_work;
       P.cap_words = (m->tile_items + m->long_threshold + 8 + 1) & ~1;  // even: the segment table behind it is 8-byte aligned
@@ -1469,7 +1471,7 @@ int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
   out8[1] = m->pb.num_slabs;
   out8[2] = m->pb.padded_nnz;
   out8[3] = m->pb.num_seg;
-  out8[4] = m->pb.max_panel_segs;
+  out8[4] = m->pb.num_chunks;
   out8[5] = m->pb.num_work;
   out8[6] = m->num_tiles;
   out8[7] = m->pb.num_pieces;
@@ -1478,7 +1480,7 @@ int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
 
 int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,
                         int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
-                        int32_t* seg_start_off, int32_t* work) {
+                        int32_t* seg_start_off, int32_t* panel_chunk, int32_t* chunk_start_count, int32_t* work) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (m->dense || m->kernel != HISPMV_KERNEL_BLOCKED) {
@@ -1497,6 +1499,8 @@ int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, 
   if (perm) HISPMV_CUDA(cudaMemcpy(perm, a.d_perm, (size_t)a.num_pieces * 2, k));
   if (panel_seg) HISPMV_CUDA(cudaMemcpy(panel_seg, a.d_panel_seg, ((size_t)m->num_tiles + 1) * 4, k));
   if (seg_start_off) HISPMV_CUDA(cudaMemcpy(seg_start_off, a.d_seg, (size_t)a.num_seg * 8, k));
+  if (panel_chunk) HISPMV_CUDA(cudaMemcpy(panel_chunk, a.d_panel_chunk, ((size_t)m->num_tiles + 1) * 4, k));
+  if (chunk_start_count) HISPMV_CUDA(cudaMemcpy(chunk_start_count, a.d_chunk, (size_t)a.num_chunks * 8, k));
   if (work) HISPMV_CUDA(cudaMemcpy(work, a.d_work, (size_t)a.num_work * 8, k));
   return HISPMV_OK;
 }

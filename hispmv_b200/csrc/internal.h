@@ -220,6 +220,8 @@ struct PbPlan {
   const int32_t* panel_seg = nullptr;  // num_panels+1 offsets into seg[]
   const PbSeg* seg = nullptr;          // non-empty (panel, slab) segments, panel-major then slab
   int32_t max_panel_segs = 0;
+  const int32_t* panel_chunk = nullptr;  // num_panels+1 offsets into chunk[]
+  const int2* chunk = nullptr;           // the segments cut into runs of at most kPbChunk pieces: (first piece id, count)
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
   int32_t num_work = 0;
   int32_t cap_words = 0;               // shared-memory words a STREAM panel needs (partials + row extents)
@@ -227,8 +229,9 @@ struct PbPlan {
   float* carry = nullptr;              // split LONG rows: as in AdaptivePlan
   unsigned int* counter = nullptr;
 };
+constexpr int32_t kPbChunk = 16;           // pieces a half-warp of pass 2 fetches per step
 constexpr int32_t kPbGroup = 512;          // entries a warp handles per step: 16 consecutive ones per lane
-constexpr int32_t kPbMaxSlabCols = 57344;  // 224 KB of x: the largest slab one CTA's shared memory can hold
+constexpr int32_t kPbMaxSlabCols = 49152;  // 192 KB of x next to the 32 KB in which pass 1's sixteen warps stage their pieces
 // owned device arrays of a blocked plan (built by pb_order_device + pb_segments_device, freed by pb_free)
 struct PbArrays {
   int32_t slab_cols = 0, num_slabs = 0;
@@ -243,6 +246,9 @@ struct PbArrays {
   uint16_t* d_perm = nullptr;
   int32_t* d_panel_seg = nullptr;
   PbSeg* d_seg = nullptr;
+  int32_t* d_panel_chunk = nullptr;
+  int2* d_chunk = nullptr;
+  int64_t num_chunks = 0;
   int2* d_work = nullptr;
   int32_t num_work = 0;
   float* d_part[2] = {nullptr, nullptr};  // one per stream lane, the second allocated on first use

@@ -249,7 +249,7 @@ class Engine:
         o = np.zeros(8, np.int64)
         check(lib.hispmv_plan_blocked_info(self._ctx, matrix_idx, _ptr(o)), "plan_blocked_info")
         d = {"slab_cols": int(o[0]), "num_slabs": int(o[1]), "padded_nnz": int(o[2]), "num_seg": int(o[3]),
-             "max_panel_segs": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "num_pieces": int(o[7])}
+             "num_chunks": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "num_pieces": int(o[7])}
         if arrays:
             n_y = self._shape(matrix_idx)[1]
             d["slab_ptr"] = np.empty(d["num_slabs"] + 1, np.int32)
@@ -261,10 +261,13 @@ class Engine:
             d["perm"] = np.empty(d["num_pieces"], np.uint16)
             d["panel_seg"] = np.empty(d["num_panels"] + 1, np.int32)
             d["seg"] = np.empty((d["num_seg"], 2), np.int32)
+            d["panel_chunk"] = np.empty(d["num_panels"] + 1, np.int32)
+            d["chunk"] = np.empty((d["num_chunks"], 2), np.int32)
             d["work"] = np.empty((d["num_work"], 2), np.int32)
             check(lib.hispmv_plan_blocked(self._ctx, matrix_idx, _ptr(d["slab_ptr"]), _ptr(d["val"]), _ptr(d["lcol"]),
                                           _ptr(d["flags"]), _ptr(d["group_base"]), _ptr(d["prow_ptr"]), _ptr(d["perm"]),
-                                          _ptr(d["panel_seg"]), _ptr(d["seg"]), _ptr(d["work"])), "plan_blocked")
+                                          _ptr(d["panel_seg"]), _ptr(d["seg"]), _ptr(d["panel_chunk"]), _ptr(d["chunk"]),
+                                          _ptr(d["work"])), "plan_blocked")
         return d
 
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:

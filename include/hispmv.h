@@ -213,8 +213,7 @@ int hispmv_plan_slab_csr(hispmv_ctx* ctx, int idx, int slab, int32_t* row_ptr, i
 /* ADAPTIVE / BLOCKED: per tile (panel), -1 for a STREAM tile or the chunk index of a LONG tile (num_tiles entries). */
 int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
 /* BLOCKED only (the column tiling of tileAndPad, common/src/spmv-helper.cpp:139-227, as this engine lays it out).
- * out8 = { slab_cols, num_slabs, padded_nnz, num_segments, max segments of a panel, pass-1 work ranges, panels,
- *          num_pieces }.
+ * out8 = { slab_cols, num_slabs, padded_nnz, num_segments, num_chunks, pass-1 work ranges, panels, num_pieces }.
  * hispmv_plan_blocked copies the plan to the host (any pointer may be NULL):
  *   slab_ptr[num_slabs+1]      slab starts in the slab-major order (multiples of 512)
  *   vals / lcol [padded_nnz]   value and column - slab*slab_cols of every entry (padding entries are zero); inside a
@@ -228,11 +227,13 @@ int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
  *   perm[num_pieces]           a piece's position in that per-row order minus the first position of its panel
  *   panel_seg[panels+1], seg_start_off[2*num_segments]   per non-empty (panel, slab) segment, panel-major:
  *                              (first piece id, pieces of the same panel in earlier slabs)
+ *   panel_chunk[panels+1], chunk_start_count[2*num_chunks]   the same segments cut into runs of at most 16 pieces,
+ *                              (first piece id, count): what a half-warp of pass 2 fetches per step
  *   work[2*ranges]             pass-1 [begin, end) per resident CTA */
 int hispmv_plan_blocked_info(hispmv_ctx* ctx, int idx, int64_t* out8);
 int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,
                         int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
-                        int32_t* seg_start_off, int32_t* work);
+                        int32_t* seg_start_off, int32_t* panel_chunk, int32_t* chunk_start_count, int32_t* work);
 
 /* ---- x exchange over NVSwitch multicast: store n floats from d_src to a multicast address (every GPU of the
  *      multicast group receives them).  mc_dst comes from a symmetric-memory rendezvous; sm_budget > 0 = that many

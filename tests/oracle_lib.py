@@ -303,8 +303,22 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
     d = {"slab_cols": W, "num_slabs": S, "padded_nnz": int(padded), "num_pieces": npc, "num_seg": int(nseg),
          "num_panels": npan, "slab_ptr": slab_ptr, "val": val, "lcol": lcol, "flags": flags, "group_base": group_base,
          "prow_ptr": prow_ptr, "perm": perm[:npc], "panel_seg": panel_seg, "seg": seg[:nseg],
-         "max_panel_segs": int(np.diff(panel_seg).max()) if npan else 0,
          "tile_row": tr, "tile_chunk": tc, "tile_first": tn, "split_rows": sp}
+    # the chunk table pass 2 walks (blocked.cu: pb_chunk_emit_kernel): every segment cut into runs of <= 16 pieces
+    n0 = tn[:npan].astype(np.int64)
+    n1 = np.where(tc >= 0, np.minimum(prow_ptr[tr[:npan] + 1], n0 + CH), prow_ptr[tr[1:npan + 1]]) if npan else n0
+    chunks, panel_chunk = [], np.zeros(npan + 1, np.int32)
+    for p_ in range(npan):
+        panel_chunk[p_] = len(chunks)
+        segs = d["seg"][panel_seg[p_]:panel_seg[p_ + 1]]
+        offs = list(segs[:, 1]) + [int(n1[p_] - n0[p_])]
+        for i_, (st, off) in enumerate(segs):
+            ln = offs[i_ + 1] - off
+            chunks += [(st + k_, min(16, ln - k_)) for k_ in range(0, ln, 16)]
+    panel_chunk[npan] = len(chunks)
+    d["panel_chunk"] = panel_chunk
+    d["chunk"] = np.asarray(chunks, np.int32).reshape(-1, 2)
+    d["num_chunks"] = len(chunks)
     if n_cta:
         work = np.zeros((n_cta, 2), np.int32)
         o.oracle_pb_work(S, slab_ptr, align, n_cta, slab_cost, work.reshape(-1))

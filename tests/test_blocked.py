@@ -144,9 +144,10 @@ def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     rp, ci, vv = eng.plan_csr(idx)
     got = eng.plan_blocked(idx)
     want = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=got["num_work"], slab_cost=cost)
-    for k in ("slab_cols", "num_slabs", "padded_nnz", "num_pieces", "num_seg", "num_panels", "max_panel_segs"):
+    for k in ("slab_cols", "num_slabs", "padded_nnz", "num_pieces", "num_seg", "num_panels", "num_chunks"):
         assert got[k] == want[k], k
-    for k in ("slab_ptr", "lcol", "flags", "group_base", "prow_ptr", "perm", "panel_seg", "seg", "work"):
+    for k in ("slab_ptr", "lcol", "flags", "group_base", "prow_ptr", "perm", "panel_seg", "seg", "panel_chunk", "chunk",
+              "work"):
         assert np.array_equal(got[k], want[k]), k
     assert np.array_equal(got["val"].view(np.uint32), want["val"].view(np.uint32))
     tr, tn = eng.plan_tiles(idx)        # the panels: adaptive tiles over the per-row piece counts

@@ -756,11 +756,11 @@ __global__ void __launch_bounds__(THREADS, 1)
 //            threads' open sums (shuffles inside a warp, shared memory across the eight warps, fixed order); the
 //            row's total waits in its last slot and a final row-per-thread pass applies alpha / beta / ReLU with
 //            coalesced bias loads and y stores
-constexpr int kReduceThreads = 256;
-constexpr int kBiasAhead = 6;  // bias values per thread requested before the gather (rows tid, tid + 256, ...)
+constexpr int kReduceThreads = 512;
+constexpr int kBiasAhead = 4;  // bias values per thread requested before the gather (rows tid, tid + THREADS, ...)
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 4)
+__global__ void __launch_bounds__(THREADS, 2)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's partials, then its row extents
@@ -782,13 +782,12 @@ __global__ void __launch_bounds__(THREADS, 4)
   const uint16_t* __restrict__ g_perm = P.perm;
   const int2* __restrict__ g_chunk = P.chunk + ch0;
 
-  // ---- gather: half-warp h takes run h, h + 16, ...; U runs in flight, the next U descriptors on their way ---------
-  constexpr int HALVES = THREADS / 16, U = 4;
-  const int hl = tid & 15, h = tid >> 4;
+  // ---- gather: warp w takes run w, w + WARPS, ...; U runs in flight, the next U descriptors on their way -----------
+  constexpr int U = 4;
   int2 nxt[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int ci = h + u * HALVES;
+    const int ci = warp + u * WARPS;
     nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
   }
   int* s_rp = reinterpret_cast<int*>(s_prod + n);
@@ -803,12 +802,12 @@ __global__ void __launch_bounds__(THREADS, 4)
     }
   }
   float acc = 0.0f;
-  for (int cb = h; cb < nch; cb += HALVES * U) {
+  for (int cb = warp; cb < nch; cb += WARPS * U) {
     int2 cur[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       cur[u] = nxt[u];
-      const int ci = cb + (u + U) * HALVES;
+      const int ci = cb + (u + U) * WARPS;
       nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
     }
     float p[U];
@@ -817,9 +816,9 @@ __global__ void __launch_bounds__(THREADS, 4)
     for (int u = 0; u < U; ++u) {
       p[u] = 0.0f;
       q[u] = 0;
-      if (hl < cur[u].y) {
-        p[u] = ld_stream_f1(g_part + cur[u].x + hl, ps);
-        if (!is_long) q[u] = ld_stream_u16(g_perm + cur[u].x + hl, ps);
+      if (lane < cur[u].y) {
+        p[u] = ld_stream_f1(g_part + cur[u].x + lane, ps);
+        if (!is_long) q[u] = ld_stream_u16(g_perm + cur[u].x + lane, ps);
       }
     }
     if (is_long) {
@@ -828,7 +827,7 @@ __global__ void __launch_bounds__(THREADS, 4)
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (hl < cur[u].y) s_prod[q[u]] = p[u];
+        if (lane < cur[u].y) s_prod[q[u]] = p[u];
     }
   }
   if (is_long) {
@@ -848,30 +847,37 @@ __global__ void __launch_bounds__(THREADS, 4)
   }
   __syncthreads();
 
-  // ---- reduce: thread tid sums the slots [j0, j1) of the per-row order ------------------------------------------
+  // ---- reduce: thread tid sums the slots [j0, j0 + C) of the per-row order ----------------------------------------
   const int C = ((n + THREADS - 1) / THREADS) | 1;
-  const int j0 = min(n, tid * C), j1 = min(n, j0 + C);
+  const int j0 = tid * C;
+  auto ends = [&](int j) { return (s_bits[j >> 5] >> (j & 31)) & 1u; };
   float lead = 0.0f, run = 0.0f;
   int lead_slot = -1;     // >= 0: a row that began before j0 ends at this slot, and `lead` is my share of it
-  bool closed = false;    // some row ends inside [j0, j1)
-  if (j0 < j1) {
-    const bool began_before = j0 > 0 && !((s_bits[(j0 - 1) >> 5] >> ((j0 - 1) & 31)) & 1u);
-    int j = j0;
-    while (j < j1) {
-      const uint32_t word = s_bits[j >> 5];
-      const int stop = min(j1, (j | 31) + 1);
-      for (; j < stop; ++j) {
-        run += s_prod[j];
-        if ((word >> (j & 31)) & 1u) {  // a row ends here
-          if (!closed && began_before) {
-            lead = run;
-            lead_slot = j;
-          } else {
-            s_prod[j] = run;  // the row's total waits in its last slot for the epilogue
-          }
-          closed = true;
-          run = 0.0f;
-        }
+  bool closed = false;    // some row ends inside my range
+  int k = 0;              // slots of my range done
+  if (j0 < n && j0 > 0 && !ends(j0 - 1)) {  // the row I start in began in an earlier thread: my share of it first
+    for (; k < C && j0 + k < n; ++k) {
+      lead += s_prod[j0 + k];
+      if (ends(j0 + k)) {
+        lead_slot = j0 + k;
+        closed = true;
+        ++k;
+        break;
+      }
+    }
+    if (!closed) {  // the row runs through my whole range
+      run = lead;
+      lead = 0.0f;
+    }
+  }
+  for (; k < C; ++k) {
+    const int j = j0 + k;
+    if (j < n) {
+      run += s_prod[j];
+      if (ends(j)) {
+        s_prod[j] = run;  // the row's total waits in its last slot for the epilogue
+        run = 0.0f;
+        closed = true;
       }
     }
   }

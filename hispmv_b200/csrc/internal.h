@@ -229,7 +229,7 @@ struct PbPlan {
   float* carry = nullptr;              // split LONG rows: as in AdaptivePlan
   unsigned int* counter = nullptr;
 };
-constexpr int32_t kPbChunk = 16;           // pieces a half-warp of pass 2 fetches per step
+constexpr int32_t kPbChunk = 32;           // pieces a warp of pass 2 fetches per step
 constexpr int32_t kPbGroup = 512;          // entries a warp handles per step: 16 consecutive ones per lane
 constexpr int32_t kPbMaxSlabCols = 49152;  // 192 KB of x next to the 32 KB in which pass 1's sixteen warps stage their pieces
 // owned device arrays of a blocked plan (built by pb_order_device + pb_segments_device, freed by pb_free)
@@ -268,7 +268,7 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
-constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 8192, kPbLongThreshold = 4096, kPbChunkNnz = 8192;
+constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 20480, kPbLongThreshold = 4096, kPbChunkNnz = 16384;
 int select_blocked(int32_t rows, int32_t cols, int64_t nnz, const ColProbe& probe, int allow_split_rows);
 
 // ---- batch.cu: several right-hand sides in one pass over A (x interleaved as xi[c * K + k], K = batch_width(nv)) ----

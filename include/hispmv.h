@@ -227,8 +227,8 @@ int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
  *   perm[num_pieces]           a piece's position in that per-row order minus the first position of its panel
  *   panel_seg[panels+1], seg_start_off[2*num_segments]   per non-empty (panel, slab) segment, panel-major:
  *                              (first piece id, pieces of the same panel in earlier slabs)
- *   panel_chunk[panels+1], chunk_start_count[2*num_chunks]   the same segments cut into runs of at most 16 pieces,
- *                              (first piece id, count): what a half-warp of pass 2 fetches per step
+ *   panel_chunk[panels+1], chunk_start_count[2*num_chunks]   the same segments cut into runs of at most 32 pieces,
+ *                              (first piece id, count): what a warp of pass 2 fetches per step
  *   work[2*ranges]             pass-1 [begin, end) per resident CTA */
 int hispmv_plan_blocked_info(hispmv_ctx* ctx, int idx, int64_t* out8);
 int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,

@@ -304,7 +304,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
          "num_panels": npan, "slab_ptr": slab_ptr, "val": val, "lcol": lcol, "flags": flags, "group_base": group_base,
          "prow_ptr": prow_ptr, "perm": perm[:npc], "panel_seg": panel_seg, "seg": seg[:nseg],
          "tile_row": tr, "tile_chunk": tc, "tile_first": tn, "split_rows": sp}
-    # the chunk table pass 2 walks (blocked.cu: pb_chunk_emit_kernel): every segment cut into runs of <= 16 pieces
+    # the chunk table pass 2 walks (blocked.cu: pb_chunk_emit_kernel): every segment cut into runs of <= 32 pieces
     n0 = tn[:npan].astype(np.int64)
     n1 = np.where(tc >= 0, np.minimum(prow_ptr[tr[:npan] + 1], n0 + CH), prow_ptr[tr[1:npan + 1]]) if npan else n0
     chunks, panel_chunk = [], np.zeros(npan + 1, np.int32)
@@ -314,7 +314,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
         offs = list(segs[:, 1]) + [int(n1[p_] - n0[p_])]
         for i_, (st, off) in enumerate(segs):
             ln = offs[i_ + 1] - off
-            chunks += [(st + k_, min(16, ln - k_)) for k_ in range(0, ln, 16)]
+            chunks += [(st + k_, min(32, ln - k_)) for k_ in range(0, ln, 32)]
     panel_chunk[npan] = len(chunks)
     d["panel_chunk"] = panel_chunk
     d["chunk"] = np.asarray(chunks, np.int32).reshape(-1, 2)

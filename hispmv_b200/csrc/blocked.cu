@@ -239,17 +239,25 @@ __global__ void pb_panel_seg_kernel(const uint64_t* __restrict__ seg_key_sorted,
 }
 
 // chunks: segment i (in panel-major order, `len` pieces from piece id seg[i].start) becomes ceil(len / kPbChunk) runs
-__global__ void pb_chunk_count_kernel(const int32_t* __restrict__ len_sorted, int64_t nseg, int32_t* __restrict__ cnt) {
+// (the last segment of every panel is followed by one empty run, so a warp may read one descriptor past its panel's
+// last run without a bounds check)
+__global__ void pb_chunk_count_kernel(const int32_t* __restrict__ len_sorted, const uint64_t* __restrict__ seg_key_sorted,
+                                      int32_t S, int64_t nseg, int32_t* __restrict__ cnt) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < nseg) cnt[i] = (len_sorted[i] + kPbChunk - 1) / kPbChunk;
+  if (i >= nseg) return;
+  const bool last_of_panel = i + 1 == nseg || seg_key_sorted[i + 1] / (uint64_t)S != seg_key_sorted[i] / (uint64_t)S;
+  cnt[i] = (len_sorted[i] + kPbChunk - 1) / kPbChunk + (last_of_panel ? 1 : 0);
 }
 __global__ void pb_chunk_emit_kernel(const PbSeg* __restrict__ seg, const int32_t* __restrict__ len_sorted,
-                                     const int32_t* __restrict__ first, int64_t nseg, int2* __restrict__ chunk) {
+                                     const int32_t* __restrict__ first, int64_t nseg, int32_t total,
+                                     int2* __restrict__ chunk) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nseg) return;
   const int32_t len = len_sorted[i], start = seg[i].start;
-  int64_t o = first[i];
+  const int32_t end = i + 1 < nseg ? first[i + 1] : total;
+  int32_t o = first[i];
   for (int32_t k = 0; k < len; k += kPbChunk) chunk[o++] = make_int2(start + k, min(kPbChunk, len - k));
+  if (o < end) chunk[o] = make_int2(0, 0);  // the empty run that closes a panel
 }
 __global__ void pb_panel_chunk_kernel(const int32_t* __restrict__ panel_seg, const int32_t* __restrict__ first,
                                       int64_t np, int64_t nseg, int32_t total, int32_t* __restrict__ panel_chunk) {
@@ -488,7 +496,8 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
   // the chunk table pass 2 walks: every segment cut into runs of at most kPbChunk pieces
   DevBuf ccnt, cfirst;
   if ((st = ccnt.alloc((size_t)nseg * 4)) || (st = cfirst.alloc((size_t)nseg * 4))) return st;
-  pb_chunk_count_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(len_sorted.as<int32_t>(), nseg, ccnt.as<int32_t>());
+  pb_chunk_count_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(len_sorted.as<int32_t>(), skeys.Current(), S, nseg,
+                                                               ccnt.as<int32_t>());
   HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, ccnt.as<int32_t>(), cfirst.as<int32_t>(), nseg, stream));
   if ((st = grow(tmp, tb, need))) return st;
   HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, ccnt.as<int32_t>(), cfirst.as<int32_t>(), nseg, stream));
@@ -501,7 +510,7 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
   HISPMV_CUDA(cudaMemsetAsync(a->d_chunk + nchunk, 0, 8 * sizeof(int2), stream));  // reads past a panel's last pair see count 0
   HISPMV_CUDA(cudaMalloc((void**)&a->d_panel_chunk, ((size_t)num_panels + 1) * 4));
   pb_chunk_emit_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(a->d_seg, len_sorted.as<int32_t>(), cfirst.as<int32_t>(),
-                                                              nseg, a->d_chunk);
+                                                              nseg, (int32_t)nchunk, a->d_chunk);
   pb_panel_chunk_kernel<<<blocks_for(num_panels + 1, B), B, 0, stream>>>(a->d_panel_seg, cfirst.as<int32_t>(), num_panels,
                                                                         nseg, (int32_t)nchunk, a->d_panel_chunk);
   HISPMV_CUDA(cudaGetLastError());
@@ -759,12 +768,48 @@ __global__ void __launch_bounds__(THREADS, 1)
 constexpr int kReduceThreads = 512;
 constexpr int kBiasAhead = 4;  // bias values per thread requested before the gather (rows tid, tid + THREADS, ...)
 
+// shared-memory accesses by 32-bit shared address (the compiler otherwise re-derives the dynamic window's base from the
+// generic pointer around every predicated store: four extra instructions per access in the first versions)
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_f32_if(uint32_t addr, float v, bool pred) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %2, 0;\n"
+      "@p st.shared.f32 [%0], %1;\n"
+      "}\n" ::"r"(addr),
+      "f"(v), "r"((uint32_t)pred)
+      : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ldg_stream_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) {
+  uint16_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
+// slot j of the panel's per-row order lives at word j + j / 32: thread t of the sweep owns slots [32 t, 32 t + 32), and
+// the one-word skew per 32 slots keeps the 32 lanes of a warp on 32 different banks
+__device__ __forceinline__ uint32_t skew(uint32_t j) { return j + (j >> 5); }
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  float* s_prod = reinterpret_cast<float*>(s_raw);  // [cap_words]: the panel's partials, then its row extents
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_raw + (size_t)P.cap_words * 4);  // [cap_words / 32 + 2]
+  // [skew(cap_words)] the panel's partials (skewed), then [cap_words / 32 + 2] end marks, then the row extents
+  float* s_prod = reinterpret_cast<float*>(s_raw);
+  const uint32_t sp = smem_u32(s_raw);
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
   __shared__ float s_wv[WARPS];
@@ -773,27 +818,27 @@ __global__ void __launch_bounds__(THREADS, 2)
   const int64_t t = P.panel_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
   const int ch0 = __ldg(P.panel_chunk + t);
-  const int nch = __ldg(P.panel_chunk + t + 1) - ch0;
+  const int nch = max(__ldg(P.panel_chunk + t + 1) - ch0 - 1, 0);  // without the empty run that closes the list
   const int n = d.n1 - d.n0;
   const bool is_long = d.chunk >= 0;
   const int trows = d.r1 - d.r0;
-  const uint64_t ps = policy_evict_first();
-  const float* __restrict__ g_part = P.part;
-  const uint16_t* __restrict__ g_perm = P.perm;
+  const float* __restrict__ part_lane = P.part + lane;
+  const uint16_t* __restrict__ perm_lane = P.perm + lane;
   const int2* __restrict__ g_chunk = P.chunk + ch0;
+  const int nwords = (n + 31) >> 5;
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_prod + skew((uint32_t)n) + 1);
+  int* s_rp = reinterpret_cast<int*>(s_bits + nwords + 1);
 
-  // ---- gather: warp w takes run w, w + WARPS, ...; U runs in flight, the next U descriptors on their way -----------
+  // ---- gather: warp w takes run w, w + WARPS, ...; U runs in flight, the next U descriptors on their way.  The
+  // panel's run list ends with an empty run, so indices past the end are clamped onto it instead of being tested.
   constexpr int U = 4;
   int2 nxt[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int ci = warp + u * WARPS;
-    nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
-  }
-  int* s_rp = reinterpret_cast<int*>(s_prod + n);
+  for (int u = 0; u < U; ++u) nxt[u] = __ldg(g_chunk + min(warp + u * WARPS, nch));
   float bias_pre[kBiasAhead];
   if (!is_long) {
-    for (int i = tid; (i << 5) < n + 32; i += THREADS) s_bits[i] = 0u;
+    for (int i = tid; i <= nwords; i += THREADS) s_bits[i] = 0u;
+    if (tid < 32 && n + tid < 32 * nwords) s_prod[skew((uint32_t)(n + tid))] = 0.0f;  // the last word's unused slots
     for (int i = tid; i <= trows; i += THREADS) s_rp[i] = __ldg(P.prow_ptr + d.r0 + i) - d.n0;
 #pragma unroll
     for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
@@ -801,33 +846,45 @@ __global__ void __launch_bounds__(THREADS, 2)
       bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
     }
   }
+  const uint64_t part_base = reinterpret_cast<uint64_t>(P.part + lane);
+  const uint64_t perm_base = reinterpret_cast<uint64_t>(P.perm + lane);
   float acc = 0.0f;
-  for (int cb = warp; cb < nch; cb += WARPS * U) {
-    int2 cur[U];
+  if (is_long) {  // a chunk of a row with very many pieces: everything is added up, no places needed
+    for (int cb = warp; cb < nch; cb += WARPS * U) {
+      int2 cur[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      cur[u] = nxt[u];
-      const int ci = cb + (u + U) * WARPS;
-      nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
-    }
-    float p[U];
-    uint32_t q[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      p[u] = 0.0f;
-      q[u] = 0;
-      if (lane < cur[u].y) {
-        p[u] = ld_stream_f1(g_part + cur[u].x + lane, ps);
-        if (!is_long) q[u] = ld_stream_u16(g_perm + cur[u].x + lane, ps);
+      for (int u = 0; u < U; ++u) {
+        cur[u] = nxt[u];
+        nxt[u] = __ldg(g_chunk + min(cb + (u + U) * WARPS, nch));
       }
-    }
-    if (is_long) {
+      float p[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        p[u] = 0.0f;
+        if (lane < cur[u].y) p[u] = ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)(uint32_t)cur[u].x << 2)));
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) acc += p[u];
-    } else {
+    }
+  } else {
+    for (int cb = warp; cb < nch; cb += WARPS * U) {
+      int2 cur[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (lane < cur[u].y) s_prod[q[u]] = p[u];
+      for (int u = 0; u < U; ++u) {
+        cur[u] = nxt[u];
+        nxt[u] = __ldg(g_chunk + min(cb + (u + U) * WARPS, nch));
+      }
+      float p[U];
+      uint32_t q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool on = lane < cur[u].y;
+        const uint32_t x = on ? (uint32_t)cur[u].x : 0u;   // idle lanes re-read the panel's... first piece id 0: harmless
+        p[u] = ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)x << 2)));
+        q[u] = ldg_stream_u16(reinterpret_cast<const uint16_t*>(perm_base + ((uint64_t)x << 1)));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) sts_f32_if(sp + 4u * skew(q[u]), p[u], lane < cur[u].y);
     }
   }
   if (is_long) {
@@ -847,44 +904,31 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
   __syncthreads();
 
-  // ---- reduce: thread tid sums the slots [j0, j0 + C) of the per-row order ----------------------------------------
-  const int C = ((n + THREADS - 1) / THREADS) | 1;
-  const int j0 = tid * C;
-  auto ends = [&](int j) { return (s_bits[j >> 5] >> (j & 31)) & 1u; };
-  float lead = 0.0f, run = 0.0f;
-  int lead_slot = -1;     // >= 0: a row that began before j0 ends at this slot, and `lead` is my share of it
-  bool closed = false;    // some row ends inside my range
-  int k = 0;              // slots of my range done
-  if (j0 < n && j0 > 0 && !ends(j0 - 1)) {  // the row I start in began in an earlier thread: my share of it first
-    for (; k < C && j0 + k < n; ++k) {
-      lead += s_prod[j0 + k];
-      if (ends(j0 + k)) {
-        lead_slot = j0 + k;
-        closed = true;
-        ++k;
-        break;
-      }
+  // ---- reduce: thread w sums the 32 slots of word w of the per-row order, closing rows at the marks ----------------
+  float sv = 0.0f;         // what the thread leaves open: the tail after its last end, or its whole word
+  unsigned sf = 0;         // thread closed a row
+  float lead = 0.0f;       // my share of a row that began in an earlier word and ends in mine ...
+  int lead_slot = -1;      // ... at this (skewed) slot
+  for (int w = tid; w < nwords; w += THREADS) {   // one trip unless the panel has more than 32 * THREADS slots
+    const uint32_t bits = s_bits[w];
+    bool pending = w > 0 && !(s_bits[w - 1] >> 31);   // the row my first slot belongs to began before this word
+    const uint32_t base = sp + 4u * (33u * (uint32_t)w);
+    float run = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {  // straight-line: selects and one predicated store per slot, no branches
+      run += lds_f32(base + 4u * k);
+      const bool end = (bits >> k) & 1u;
+      const bool mine = end && pending;
+      lead = mine ? run : lead;
+      lead_slot = mine ? 33 * w + k : lead_slot;
+      sts_f32_if(base + 4u * k, run, end && !pending);  // the row's total waits in its last slot for the epilogue
+      pending = pending && !end;
+      run = end ? 0.0f : run;
     }
-    if (!closed) {  // the row runs through my whole range
-      run = lead;
-      lead = 0.0f;
-    }
+    sv = run;
+    sf = bits != 0u;
   }
-  for (; k < C; ++k) {
-    const int j = j0 + k;
-    if (j < n) {
-      run += s_prod[j];
-      if (ends(j)) {
-        s_prod[j] = run;  // the row's total waits in its last slot for the epilogue
-        run = 0.0f;
-        closed = true;
-      }
-    }
-  }
-  // segmented scan over the threads of (what a thread leaves open, thread closed a row): carry = the open row's sum
-  // over the threads before this one
-  float sv = run;            // closed: the tail after the last end; not closed: the whole range
-  unsigned sf = closed;
+  // segmented scan over the threads of (open sum, closed a row): carry = the open row's sum over the threads before
 #pragma unroll
   for (int dd = 1; dd < 32; dd <<= 1) {
     const float uv = __shfl_up_sync(kFullMask, sv, dd);
@@ -926,7 +970,7 @@ __global__ void __launch_bounds__(THREADS, 2)
   // ---- epilogue: one thread per row, coalesced ------------------------------------------------------------------
   auto finish_row = [&](int i, float bias) {
     const int b = s_rp[i], e = s_rp[i + 1];
-    const float sum = e > b ? s_prod[e - 1] : 0.0f;
+    const float sum = e > b ? s_prod[skew((uint32_t)(e - 1))] : 0.0f;
     float v = ep.alpha * sum;
     if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
     if (ep.relu) v = fmaxf(v, 0.0f);
@@ -961,7 +1005,8 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   (void)A;
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.cap_words * 4 + ((size_t)P.cap_words / 32 + 4) * sizeof(uint32_t);
+  // partials skewed by one word per 32, end marks, row extents: (n + n/32) + (n/32 + 2) + (rows + 1) words, n + rows <= cap
+  const size_t smem = ((size_t)P.cap_words + 2 * ((size_t)P.cap_words / 32) + 16) * 4;
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

@@ -268,7 +268,7 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
-constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 20480, kPbLongThreshold = 4096, kPbChunkNnz = 16384;
+constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 12288, kPbLongThreshold = 4096, kPbChunkNnz = 16384;
 int select_blocked(int32_t rows, int32_t cols, int64_t nnz, const ColProbe& probe, int allow_split_rows);
 
 // ---- batch.cu: several right-hand sides in one pass over A (x interleaved as xi[c * K + k], K = batch_width(nv)) ----

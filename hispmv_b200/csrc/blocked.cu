@@ -246,7 +246,8 @@ __global__ void pb_chunk_count_kernel(const int32_t* __restrict__ len_sorted, co
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nseg) return;
   const bool last_of_panel = i + 1 == nseg || seg_key_sorted[i + 1] / (uint64_t)S != seg_key_sorted[i] / (uint64_t)S;
-  cnt[i] = (len_sorted[i] + kPbChunk - 1) / kPbChunk + (last_of_panel ? 1 : 0);
+  (void)last_of_panel;
+  cnt[i] = (len_sorted[i] + kPbChunk - 1) / kPbChunk;
 }
 __global__ void pb_chunk_emit_kernel(const PbSeg* __restrict__ seg, const int32_t* __restrict__ len_sorted,
                                      const int32_t* __restrict__ first, int64_t nseg, int32_t total,
@@ -518,7 +519,7 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
   DevBuf mx;
   if ((st = mx.alloc(sizeof(int)))) return st;
   HISPMV_CUDA(cudaMemsetAsync(mx.p, 0, sizeof(int), stream));
-  pb_max_segs_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(a->d_panel_seg, num_panels, mx.as<int>());
+  pb_max_segs_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(a->d_panel_chunk, num_panels, mx.as<int>());  // most runs of a panel
   HISPMV_CUDA(cudaGetLastError());
   int h_mx = 0;
   HISPMV_CUDA(cudaMemcpyAsync(&h_mx, mx.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -799,6 +800,31 @@ __device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) {
   return v;
 }
 
+__device__ __forceinline__ float ldg_stream_f32_if(uint64_t addr, bool pred) {  // 0 when the lane is idle
+  float v = 0.0f;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %2, 0;\n"
+      "@p ld.global.nc.L1::no_allocate.f32 %0, [%1];\n"
+      "}\n"
+      : "+f"(v)
+      : "l"(addr), "r"((uint32_t)pred));
+  return v;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u16_if(uint64_t addr, bool pred) {
+  uint16_t v = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.u32 p, %2, 0;\n"
+      "@p ld.global.nc.L1::no_allocate.u16 %0, [%1];\n"
+      "}\n"
+      : "+h"(v)
+      : "l"(addr), "r"((uint32_t)pred));
+  return v;
+}
+
 // slot j of the panel's per-row order lives at word j + j / 32: thread t of the sweep owns slots [32 t, 32 t + 32), and
 // the one-word skew per 32 slots keeps the 32 lanes of a warp on 32 different banks
 __device__ __forceinline__ uint32_t skew(uint32_t j) { return j + (j >> 5); }
@@ -818,7 +844,7 @@ __global__ void __launch_bounds__(THREADS, 2)
   const int64_t t = P.panel_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
   const int ch0 = __ldg(P.panel_chunk + t);
-  const int nch = max(__ldg(P.panel_chunk + t + 1) - ch0 - 1, 0);  // without the empty run that closes the list
+  const int nch = __ldg(P.panel_chunk + t + 1) - ch0;
   const int n = d.n1 - d.n0;
   const bool is_long = d.chunk >= 0;
   const int trows = d.r1 - d.r0;
@@ -829,12 +855,12 @@ __global__ void __launch_bounds__(THREADS, 2)
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_prod + skew((uint32_t)n) + 1);
   int* s_rp = reinterpret_cast<int*>(s_bits + nwords + 1);
 
-  // ---- gather: warp w takes run w, w + WARPS, ...; U runs in flight, the next U descriptors on their way.  The
-  // panel's run list ends with an empty run, so indices past the end are clamped onto it instead of being tested.
-  constexpr int U = 4;
-  int2 nxt[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) nxt[u] = __ldg(g_chunk + min(warp + u * WARPS, nch));
+  // ---- gather: the panel's run descriptors are staged in shared memory (one coalesced load); warp w then takes run
+  // w, w + WARPS, ... with U runs in flight.  Idle lanes of a short run are predicated off -- sending them all to one
+  // dummy address made that L2 line a hot spot (C5's 5-piece runs ran 9x slower).
+  constexpr int U = 8;
+  int2* s_chunk = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(s_rp + trows + 2) + 7) & ~(uintptr_t)7);
+  for (int i = tid; i < nch; i += THREADS) s_chunk[i] = __ldg(g_chunk + i);
   float bias_pre[kBiasAhead];
   if (!is_long) {
     for (int i = tid; i <= nwords; i += THREADS) s_bits[i] = 0u;
@@ -846,45 +872,28 @@ __global__ void __launch_bounds__(THREADS, 2)
       bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
     }
   }
+  __syncthreads();
   const uint64_t part_base = reinterpret_cast<uint64_t>(P.part + lane);
   const uint64_t perm_base = reinterpret_cast<uint64_t>(P.perm + lane);
   float acc = 0.0f;
-  if (is_long) {  // a chunk of a row with very many pieces: everything is added up, no places needed
-    for (int cb = warp; cb < nch; cb += WARPS * U) {
-      int2 cur[U];
+  for (int cb = warp; cb < nch; cb += WARPS * U) {
+    float p[U];
+    uint32_t q[U];
+    bool on[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        cur[u] = nxt[u];
-        nxt[u] = __ldg(g_chunk + min(cb + (u + U) * WARPS, nch));
-      }
-      float p[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        p[u] = 0.0f;
-        if (lane < cur[u].y) p[u] = ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)(uint32_t)cur[u].x << 2)));
-      }
+    for (int u = 0; u < U; ++u) {
+      const int ci = cb + u * WARPS;
+      const int2 cur = ci < nch ? s_chunk[ci] : make_int2(0, 0);
+      on[u] = lane < cur.y;
+      p[u] = ldg_stream_f32_if(part_base + ((uint64_t)(uint32_t)cur.x << 2), on[u]);
+      q[u] = is_long ? 0u : ldg_stream_u16_if(perm_base + ((uint64_t)(uint32_t)cur.x << 1), on[u]);
+    }
+    if (is_long) {
 #pragma unroll
       for (int u = 0; u < U; ++u) acc += p[u];
-    }
-  } else {
-    for (int cb = warp; cb < nch; cb += WARPS * U) {
-      int2 cur[U];
+    } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        cur[u] = nxt[u];
-        nxt[u] = __ldg(g_chunk + min(cb + (u + U) * WARPS, nch));
-      }
-      float p[U];
-      uint32_t q[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const bool on = lane < cur[u].y;
-        const uint32_t x = on ? (uint32_t)cur[u].x : 0u;   // idle lanes re-read the panel's... first piece id 0: harmless
-        p[u] = ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)x << 2)));
-        q[u] = ldg_stream_u16(reinterpret_cast<const uint16_t*>(perm_base + ((uint64_t)x << 1)));
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) sts_f32_if(sp + 4u * skew(q[u]), p[u], lane < cur[u].y);
+      for (int u = 0; u < U; ++u) sts_f32_if(sp + 4u * skew(q[u]), p[u], on[u]);
     }
   }
   if (is_long) {
@@ -1006,7 +1015,7 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
   // partials skewed by one word per 32, end marks, row extents: (n + n/32) + (n/32 + 2) + (rows + 1) words, n + rows <= cap
-  const size_t smem = ((size_t)P.cap_words + 2 * ((size_t)P.cap_words / 32) + 16) * 4;
+  const size_t smem = ((size_t)P.cap_words + 2 * ((size_t)P.cap_words / 32) + 16) * 4 + (size_t)P.max_panel_segs * 8 + 16;
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

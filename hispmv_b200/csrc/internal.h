@@ -219,7 +219,7 @@ struct PbPlan {
   const TileDesc* desc = nullptr;      // the panels (adaptive tiles over prow_ptr)
   const int32_t* panel_seg = nullptr;  // num_panels+1 offsets into seg[]
   const PbSeg* seg = nullptr;          // non-empty (panel, slab) segments, panel-major then slab
-  int32_t max_panel_segs = 0;
+  int32_t max_panel_segs = 0;         // the most runs (chunk[] entries) any panel has: sizes pass 2's shared-memory copy
   const int32_t* panel_chunk = nullptr;  // num_panels+1 offsets into chunk[]
   const int2* chunk = nullptr;           // the segments cut into runs of at most kPbChunk pieces: (first piece id, count)
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced

@@ -315,8 +315,6 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
         for i_, (st, off) in enumerate(segs):
             ln = offs[i_ + 1] - off
             chunks += [(st + k_, min(32, ln - k_)) for k_ in range(0, ln, 32)]
-        if len(segs):
-            chunks.append((0, 0))        # the empty run that closes a panel's list (read without a bounds check)
     panel_chunk[npan] = len(chunks)
     d["panel_chunk"] = panel_chunk
     d["chunk"] = np.asarray(chunks, np.int32).reshape(-1, 2)

@@ -64,6 +64,7 @@ def main() -> int:
     ap.add_argument("--exec_ms", type=float, default=1000.0, help="time budget for the repeated runs (reference: --exec_ms)")
     ap.add_argument("--power_s", type=float, default=0.0, help="seconds of sampled execution (reference: --power_s)")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--dump_y", default="", help="also save the accelerator's result vector (.npy), for the tests")
     a = ap.parse_args()
     import scipy.sparse as sp
     import torch
@@ -94,8 +95,13 @@ def main() -> int:
 
     print("\nComputing on CPU... ")
     if dense is None:
-        rp, ci, vv = eng.plan_csr(idx)
-        m = sp.csr_matrix((vv, ci, rp), shape=(rows, cols))
+        # the CPU side reads the file with an independent reader (scipy), not the engine's own CSR, so that an ingest
+        # error shows up in the error report instead of cancelling out
+        import scipy.io
+        m = sp.csr_matrix(scipy.io.mmread(a.args[0])).astype(np.float32)
+        if m.shape != (rows, cols):
+            print(f"Error: the engine holds {rows}x{cols}, the file says {m.shape[0]}x{m.shape[1]}", file=sys.stderr)
+            return 1
     t0 = time.perf_counter()
     ax = (m @ x) if dense is None else (dense @ x)
     cpu = (np.float32(alpha) * ax.astype(np.float32) + np.float32(beta) * c_in).astype(np.float32)
@@ -161,6 +167,8 @@ def main() -> int:
     eng.run_kernel(x, c_in, y, alpha, beta)
     print()
     print_error_stats(cpu, y)
+    if a.dump_y:
+        np.save(a.dump_y, y)
     eng.close()
     return 0
 

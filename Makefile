@@ -4,11 +4,13 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       := g++
 PY        ?= python
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -Ihispmv_b200/csrc --expt-relaxed-constexpr
+# EXPERIMENTAL=1 also builds the three research kernels of experimental.cu (never selected by the planner)
+EXPERIMENTAL ?= 0
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Iinclude -Ihispmv_b200/csrc --expt-relaxed-constexpr $(if $(filter 1,$(EXPERIMENTAL)),-DHISPMV_EXPERIMENTAL,)
 PKG       := hispmv_b200
 CSRC      := $(PKG)/csrc
 OBJDIR    := build/obj
-OBJS      := $(OBJDIR)/capi.o $(OBJDIR)/spmv.o $(OBJDIR)/adaptive.o $(OBJDIR)/gemv.o $(OBJDIR)/partition.o $(OBJDIR)/synth.o $(OBJDIR)/exchange.o $(OBJDIR)/batch.o $(OBJDIR)/blocked.o
+OBJS      := $(OBJDIR)/capi.o $(OBJDIR)/spmv.o $(OBJDIR)/adaptive.o $(OBJDIR)/gemv.o $(OBJDIR)/partition.o $(OBJDIR)/synth.o $(OBJDIR)/exchange.o $(OBJDIR)/batch.o $(OBJDIR)/blocked.o $(OBJDIR)/experimental.o
 LIB       := $(PKG)/libhispmv_cuda.so
 PYEXT     := $(PKG)/pyhispmv$(shell $(PY) -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
 PYINC     := $(shell $(PY) -c "import sysconfig,pybind11;print('-I'+sysconfig.get_paths()['include'],'-I'+pybind11.get_include())")

@@ -794,34 +794,9 @@ __device__ __forceinline__ float ldg_stream_f32(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) {
-  uint16_t v;
-  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return v;
-}
-
-__device__ __forceinline__ float ldg_stream_f32_if(uint64_t addr, bool pred) {  // 0 when the lane is idle
-  float v = 0.0f;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %2, 0;\n"
-      "@p ld.global.nc.L1::no_allocate.f32 %0, [%1];\n"
-      "}\n"
-      : "+f"(v)
-      : "l"(addr), "r"((uint32_t)pred));
-  return v;
-}
-__device__ __forceinline__ uint32_t ldg_stream_u16_if(uint64_t addr, bool pred) {
-  uint16_t v = 0;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.u32 p, %2, 0;\n"
-      "@p ld.global.nc.L1::no_allocate.u16 %0, [%1];\n"
-      "}\n"
-      : "+h"(v)
-      : "l"(addr), "r"((uint32_t)pred));
+__device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) {  // zero-extended straight into a 32-bit register:
+  uint32_t v;                                                            // a 16-bit destination put a conversion right
+  asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=r"(v) : "l"(p));  // behind every load and serialised them
   return v;
 }
 
@@ -855,12 +830,16 @@ __global__ void __launch_bounds__(THREADS, 2)
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_prod + skew((uint32_t)n) + 1);
   int* s_rp = reinterpret_cast<int*>(s_bits + nwords + 1);
 
-  // ---- gather: the panel's run descriptors are staged in shared memory (one coalesced load); warp w then takes run
-  // w, w + WARPS, ... with U runs in flight.  Idle lanes of a short run are predicated off -- sending them all to one
-  // dummy address made that L2 line a hot spot (C5's 5-piece runs ran 9x slower).
-  constexpr int U = 8;
-  int2* s_chunk = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(s_rp + trows + 2) + 7) & ~(uintptr_t)7);
-  for (int i = tid; i < nch; i += THREADS) s_chunk[i] = __ldg(g_chunk + i);
+  // ---- gather: warp w takes run w, w + WARPS, ...; U runs in flight, the next U descriptors already requested.  Idle
+  // lanes of a short run issue nothing (sending them to one dummy address made that L2 line a hot spot: C5's 5-piece
+  // runs ran 9x slower).
+  constexpr int U = 4;
+  int2 nxt[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int ci = warp + u * WARPS;
+    nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
+  }
   float bias_pre[kBiasAhead];
   if (!is_long) {
     for (int i = tid; i <= nwords; i += THREADS) s_bits[i] = 0u;
@@ -872,28 +851,34 @@ __global__ void __launch_bounds__(THREADS, 2)
       bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
     }
   }
-  __syncthreads();
   const uint64_t part_base = reinterpret_cast<uint64_t>(P.part + lane);
   const uint64_t perm_base = reinterpret_cast<uint64_t>(P.perm + lane);
   float acc = 0.0f;
   for (int cb = warp; cb < nch; cb += WARPS * U) {
-    float p[U];
-    uint32_t q[U];
-    bool on[U];
+    int2 cur[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int ci = cb + u * WARPS;
-      const int2 cur = ci < nch ? s_chunk[ci] : make_int2(0, 0);
-      on[u] = lane < cur.y;
-      p[u] = ldg_stream_f32_if(part_base + ((uint64_t)(uint32_t)cur.x << 2), on[u]);
-      q[u] = is_long ? 0u : ldg_stream_u16_if(perm_base + ((uint64_t)(uint32_t)cur.x << 1), on[u]);
+      cur[u] = nxt[u];
+      const int ci = cb + (u + U) * WARPS;
+      nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
+    }
+    float p[U];
+    uint32_t q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      p[u] = 0.0f;
+      q[u] = 0;
+      if (lane < cur[u].y) {
+        p[u] = ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)(uint32_t)cur[u].x << 2)));
+        if (!is_long) q[u] = ldg_stream_u16(reinterpret_cast<const uint16_t*>(perm_base + ((uint64_t)(uint32_t)cur[u].x << 1)));
+      }
     }
     if (is_long) {
 #pragma unroll
       for (int u = 0; u < U; ++u) acc += p[u];
     } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) sts_f32_if(sp + 4u * skew(q[u]), p[u], on[u]);
+      for (int u = 0; u < U; ++u) sts_f32_if(sp + 4u * skew(q[u]), p[u], lane < cur[u].y);
     }
   }
   if (is_long) {
@@ -1015,7 +1000,7 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
   // partials skewed by one word per 32, end marks, row extents: (n + n/32) + (n/32 + 2) + (rows + 1) words, n + rows <= cap
-  const size_t smem = ((size_t)P.cap_words + 2 * ((size_t)P.cap_words / 32) + 16) * 4 + (size_t)P.max_panel_segs * 8 + 16;
+  const size_t smem = ((size_t)P.cap_words + 2 * ((size_t)P.cap_words / 32) + 16) * 4;
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

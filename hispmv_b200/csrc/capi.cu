@@ -348,7 +348,8 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     m->persistent = false;
     m->pipeline = false;
     m->warptile = false;
-    if (const char* e = getenv("HISPMV_WARPTILE")) {  // "B,T,CH"
+    static const bool research = experimental_kernels_built();  // the research switches need `make EXPERIMENTAL=1`
+    if (const char* e = research ? getenv("HISPMV_WARPTILE") : nullptr) {  // "B,T,CH"
       int b = 0, t = 0, ch = 0;
       if (m->kernel == HISPMV_KERNEL_ADAPTIVE && sscanf(e, "%d,%d,%d", &b, &t, &ch) == 3 && b >= 32 && t >= 16 &&
           b + t <= kWarpTileCap && ch >= 64) {
@@ -358,7 +359,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
         m->chunk_nnz = ch;
       }
     }
-    if (const char* e = getenv("HISPMV_PIPELINE")) {
+    if (const char* e = research ? getenv("HISPMV_PIPELINE") : nullptr) {
       if (atoi(e) > 0 && m->kernel == HISPMV_KERNEL_ADAPTIVE) {
         m->pipeline = true;
         m->tile_items = std::min(m->tile_items, kPipelineRows);
@@ -366,7 +367,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
         m->chunk_nnz = std::min(m->chunk_nnz, kPipelineCap);
       }
     }
-    if (const char* e = getenv("HISPMV_PERSIST")) {  // research switch: the persistent x-window variant (never auto)
+    if (const char* e = research ? getenv("HISPMV_PERSIST") : nullptr) {  // research switch: the persistent x-window variant (never auto)
       const int h = atoi(e);
       if (m->kernel == HISPMV_KERNEL_ADAPTIVE) {
         m->persistent = h > 0;
@@ -893,7 +894,7 @@ Matrix* get_matrix(hispmv_ctx* c, int64_t idx) {
 extern "C" {
 
 const char* hispmv_last_error(void) { return g_last_error.c_str(); }
-int hispmv_version(void) { return 100; }
+int hispmv_version(void) { return 200 + (experimental_kernels_built() ? 1 : 0); }  // odd: research kernels built in
 
 int hispmv_create(hispmv_ctx** out, int device_id, int flags) {
   if (!out) return HISPMV_ERR_ARG;

@@ -168,6 +168,8 @@ constexpr int kAdaptiveStreamItems = 2048, kAdaptiveLongThreshold = 1024, kAdapt
 int launch_adaptive_persistent(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep,
                                int sm_count, cudaStream_t s);
 constexpr int kPersistentMaxHot = 40960;  // floats of x the window may hold next to the four group buffers
+// experimental.cu: research kernels, compiled only with -DHISPMV_EXPERIMENTAL (the default build has refusing stubs)
+bool experimental_kernels_built();
 // One warp per tile (tiles of a few hundred items): stream_items + long_threshold <= kWarpTileCap.
 int launch_warptile(const CsrDev& A, const AdaptivePlan& P, const float* x, float* y, Epilogue ep, cudaStream_t s);
 constexpr int kWarpTileCap = 512;

@@ -108,7 +108,7 @@ typedef struct hispmv_matrix_info {
 } hispmv_matrix_info;
 
 const char* hispmv_last_error(void);
-int hispmv_version(void);
+int hispmv_version(void);   /* 200 = this ABI; +1 when built with the research kernels (make EXPERIMENTAL=1) */
 
 /* device_id: CUDA ordinal.  flags: HISPMV_FLAG_*.  Fails (no fallback) if the device is not sm_100. */
 int hispmv_create(hispmv_ctx** out, int device_id, int flags);

@@ -29,7 +29,7 @@ class MatrixInfo(C.Structure):
         ("max_row_nnz", C.c_int32), ("empty_rows", C.c_int32), ("hist", C.c_int64 * HIST_BINS),
         ("device_bytes", C.c_int64), ("probe_near", C.c_int64), ("probe_cmp", C.c_int64),
         ("x_window_cols", C.c_int32), ("long_threshold", C.c_int32), ("chunk_nnz", C.c_int32),
-        ("num_slabs", C.c_int32), ("slab_cols", C.c_int32), ("reserved_", C.c_int32),
+        ("num_slabs", C.c_int32), ("slab_cols", C.c_int32), ("reserved_", C.c_int32), ("slab_runs", C.c_int64),
     ]
 
 

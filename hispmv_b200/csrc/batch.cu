@@ -9,6 +9,8 @@
 // Sparse rows are walked by sub-warps of LANES lanes (the csr_vector shape), so the path is offered for matrices whose
 // longest row a sub-warp can walk (DNN layers); others keep running vector by vector.  The dense overlay has the same
 // treatment (gemm_lite_kernel): A is streamed once for up to eight vectors, x panels staged in shared memory.
+#include <limits.h>
+
 #include "device_utils.cuh"
 #include "internal.h"
 
@@ -47,7 +49,7 @@ __device__ __forceinline__ void load_xk(const float* __restrict__ xi, int c, flo
 }
 
 template <int K, int LANES>
-__global__ void __launch_bounds__(256) spmm_csr_kernel(CsrDev A, const float* __restrict__ xi, float* __restrict__ y,
+__global__ void __launch_bounds__(256) spmm_csr_kernel(CsrDev A, int skip_len, const float* __restrict__ xi, float* __restrict__ y,
                                                        int nv, Epilogue ep) {
   const uint64_t ps = policy_evict_first();
   const int lane = threadIdx.x & (LANES - 1);
@@ -60,9 +62,11 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(CsrDev A, const float* __
     float acc[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = 0.0f;
-    if (r < A.rows) {
+    bool mine = r < A.rows;
+    if (mine) {
       const int b = A.row_ptr[r], e = A.row_ptr[r + 1];
-      int j = b + lane;
+      mine = e - b <= skip_len;   // longer rows are left to one CTA each (spmm_csr_cta_kernel over the long-row list)
+      int j = mine ? b + lane : e;
       for (; j + LANES < e; j += 2 * LANES) {  // two nonzeros, 2K products in flight per lane
         const int c0 = ld_stream_i1(A.col + j, ps), c1 = ld_stream_i1(A.col + j + LANES, ps);
         const float v0 = ld_stream_f1(A.val + j, ps), v1 = ld_stream_f1(A.val + j + LANES, ps);
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(256) spmm_csr_kernel(CsrDev A, const float* __
     }
 #pragma unroll
     for (int k = 0; k < K; ++k) acc[k] = subwarp_sum<LANES>(acc[k]);
-    if (lane == 0 && r < A.rows) {
+    if (lane == 0 && mine) {
 #pragma unroll
       for (int k = 0; k < K; ++k)
         if (k < nv) y[(int64_t)k * A.rows + r] = finish(acc[k], ep.alpha, ep.beta, ep.bias, r, ep.relu);
@@ -197,12 +201,15 @@ int launch_gemm_lite_k(const DenseDev& A, const float* xp, float* y, int nv, Epi
 // Few, long rows (a 1024 x 8192 layer at density 0.25 has 1024 rows of ~2048 nonzeros): one CTA per row keeps all SMs
 // busy where one warp per row would leave most of them idle.
 template <int K>
-__global__ void __launch_bounds__(256) spmm_csr_cta_kernel(CsrDev A, const float* __restrict__ xi, float* __restrict__ y,
-                                                           int nv, Epilogue ep) {
+__global__ void __launch_bounds__(256) spmm_csr_cta_kernel(CsrDev A, const int32_t* __restrict__ row_list, int64_t n_list,
+                                                           const float* __restrict__ xi, float* __restrict__ y, int nv,
+                                                           Epilogue ep) {
   __shared__ float s_red[8][K];
   const uint64_t ps = policy_evict_first();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int64_t r = blockIdx.x; r < A.rows; r += gridDim.x) {
+  const int64_t count = row_list ? n_list : (int64_t)A.rows;   // every row, or only the listed (long) ones
+  for (int64_t i = blockIdx.x; i < count; i += gridDim.x) {
+    const int64_t r = row_list ? (int64_t)row_list[i] : i;
     const int b = A.row_ptr[r], e = A.row_ptr[r + 1];
     float acc[K];
 #pragma unroll
@@ -245,22 +252,28 @@ __global__ void __launch_bounds__(256) spmm_csr_cta_kernel(CsrDev A, const float
 }
 
 template <int K>
-int launch_spmm_k(const CsrDev& A, int lanes, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s) {
+int launch_spmm_k(const CsrDev& A, int lanes, const int32_t* long_rows, int64_t n_long, int long_len, const float* xi,
+                  float* y, int nv, Epilogue ep, cudaStream_t s) {
   if (lanes > 32) {  // one CTA per row
-    spmm_csr_cta_kernel<K><<<(int)std::min<int64_t>(A.rows, 148 * 16), 256, 0, s>>>(A, xi, y, nv, ep);
+    spmm_csr_cta_kernel<K><<<(int)std::min<int64_t>(A.rows, 148 * 16), 256, 0, s>>>(A, nullptr, 0, xi, y, nv, ep);
     HISPMV_CUDA(cudaGetLastError());
     return HISPMV_OK;
   }
   const int64_t threads = (int64_t)A.rows * lanes;
   const int grid = (int)std::min<int64_t>((threads + 255) / 256, 148 * 64);
+  const int skip = n_long > 0 ? long_len : INT_MAX;
   switch (lanes) {
-    case 2: spmm_csr_kernel<K, 2><<<grid, 256, 0, s>>>(A, xi, y, nv, ep); break;
-    case 4: spmm_csr_kernel<K, 4><<<grid, 256, 0, s>>>(A, xi, y, nv, ep); break;
-    case 8: spmm_csr_kernel<K, 8><<<grid, 256, 0, s>>>(A, xi, y, nv, ep); break;
-    case 16: spmm_csr_kernel<K, 16><<<grid, 256, 0, s>>>(A, xi, y, nv, ep); break;
-    default: spmm_csr_kernel<K, 32><<<grid, 256, 0, s>>>(A, xi, y, nv, ep); break;
+    case 2: spmm_csr_kernel<K, 2><<<grid, 256, 0, s>>>(A, skip, xi, y, nv, ep); break;
+    case 4: spmm_csr_kernel<K, 4><<<grid, 256, 0, s>>>(A, skip, xi, y, nv, ep); break;
+    case 8: spmm_csr_kernel<K, 8><<<grid, 256, 0, s>>>(A, skip, xi, y, nv, ep); break;
+    case 16: spmm_csr_kernel<K, 16><<<grid, 256, 0, s>>>(A, skip, xi, y, nv, ep); break;
+    default: spmm_csr_kernel<K, 32><<<grid, 256, 0, s>>>(A, skip, xi, y, nv, ep); break;
   }
   HISPMV_CUDA(cudaGetLastError());
+  if (n_long > 0) {  // the rows a sub-warp should not walk alone: one CTA each
+    spmm_csr_cta_kernel<K><<<(int)std::min<int64_t>(n_long, 148 * 16), 256, 0, s>>>(A, long_rows, n_long, xi, y, nv, ep);
+    HISPMV_CUDA(cudaGetLastError());
+  }
   return HISPMV_OK;
 }
 
@@ -301,16 +314,45 @@ int launch_interleave_panels(const float* x, int nv, int64_t n, int64_t ld, floa
   return HISPMV_OK;
 }
 
-int launch_spmm_csr(const CsrDev& A, int lanes, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s) {
+namespace {
+__global__ void long_rows_kernel(const int32_t* __restrict__ rp, int32_t rows, int32_t min_len, int32_t* __restrict__ out,
+                                 int* __restrict__ count) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows && rp[r + 1] - rp[r] > min_len) out[atomicAdd(count, 1)] = (int32_t)r;
+}
+}  // namespace
+
+// Rows with more than min_len nonzeros (any order: every row is independent); d_out cudaMalloc'ed by the callee.
+int batch_long_rows_device(const int32_t* d_row_ptr, int32_t rows, int32_t min_len, int64_t max_count, int32_t** d_out,
+                           int64_t* count, cudaStream_t stream) {
+  *d_out = nullptr;
+  *count = 0;
+  if (rows <= 0 || max_count <= 0) return HISPMV_OK;
+  int* d_cnt = nullptr;
+  HISPMV_CUDA(cudaMalloc((void**)d_out, (size_t)max_count * 4));
+  HISPMV_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int)));
+  HISPMV_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), stream));
+  long_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, stream>>>(d_row_ptr, rows, min_len, *d_out, d_cnt);
+  int h = 0;
+  int st = check_cuda(cudaMemcpyAsync(&h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H", __FILE__, __LINE__);
+  if (st == HISPMV_OK) st = check_cuda(cudaStreamSynchronize(stream), "sync", __FILE__, __LINE__);
+  cudaFree(d_cnt);
+  if (st != HISPMV_OK) return st;
+  *count = h;
+  return HISPMV_OK;
+}
+
+int launch_spmm_csr(const CsrDev& A, int lanes, const int32_t* long_rows, int64_t n_long, int long_len, const float* xi,
+                    float* y, int nv, Epilogue ep, cudaStream_t s) {
   if (A.rows <= 0) return HISPMV_OK;
   if (ep.y_mc) {
     set_error("spmm: a multicast y is not supported for batches");
     return HISPMV_ERR_STATE;
   }
   switch (batch_width(nv)) {
-    case 8: return launch_spmm_k<8>(A, lanes, xi, y, nv, ep, s);
-    case 4: return launch_spmm_k<4>(A, lanes, xi, y, nv, ep, s);
-    default: return launch_spmm_k<2>(A, lanes, xi, y, nv, ep, s);
+    case 8: return launch_spmm_k<8>(A, lanes, long_rows, n_long, long_len, xi, y, nv, ep, s);
+    case 4: return launch_spmm_k<4>(A, lanes, long_rows, n_long, long_len, xi, y, nv, ep, s);
+    default: return launch_spmm_k<2>(A, lanes, long_rows, n_long, long_len, xi, y, nv, ep, s);
   }
 }
 

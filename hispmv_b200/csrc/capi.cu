@@ -67,8 +67,11 @@ struct Matrix {
   int adaptive_threads = 256;           // ADAPTIVE: threads per CTA (256; 128 through the development switch)
   int rowstage_threads = 128;           // ROWSTAGE: threads per CTA (128; 256 through the development switch)
   ColProbe probe{};                     // column-locality probe (selector input)
+  int32_t* d_batch_long_rows = nullptr;  // batches: rows with more than kBatchMaxRowNnz nonzeros (one CTA each), built
+  int64_t num_batch_long_rows = -1;      // on the first batch call (-1: not yet)
   PbArrays pb;                          // BLOCKED: the slab-major copy, segment table, pass-1 work ranges, products
   int64_t pb_slab_cost = 0;             // BLOCKED: entries one slab load is worth when pass-1 ranges are balanced
+  int64_t slab_runs = 0;                // selector input: (row, slab) runs for slabs of kPbSlabCols columns (0: not counted)
   // dense
   float* d_a = nullptr;
   int64_t ld = 0;
@@ -111,6 +114,7 @@ struct Matrix {
     cudaFree(d_col);
     cudaFree(d_val);
     cudaFree(d_a);
+    cudaFree(d_batch_long_rows);
   }
 };
 
@@ -218,7 +222,15 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
   m->slab_cols = 0;
   if (!m->forced && m->kernel == HISPMV_KERNEL_ADAPTIVE && !m->is_slab) {
     // scattered gathers over a large x: two streaming passes with x served from shared memory (blocked.cu)
-    int want = select_blocked(m->local_rows(), m->cols, m->nnz, m->probe, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0);
+    // (the run count costs a pass over the column indices, so it is taken only where the cheap conditions already hold)
+    m->slab_runs = 0;
+    int want = select_blocked(m->local_rows(), m->cols, m->nnz, 0, m->probe, (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0);
+    if (want) {
+      st = pb_count_runs_device(m->d_row_ptr, m->d_col, m->local_rows(), kPbSlabCols, &m->slab_runs, c->stream);
+      if (st != HISPMV_OK) return st;
+      want = select_blocked(m->local_rows(), m->cols, m->nnz, m->slab_runs, m->probe,
+                            (c->flags & HISPMV_FLAG_ROW_DIST_NET) != 0);
+    }
     if (const char* e = getenv("HISPMV_BLOCKED_AUTO")) want = want && atoi(e) != 0;  // "0": keep the one-pass kernels
     if (want) m->kernel = HISPMV_KERNEL_BLOCKED;
   }
@@ -804,13 +816,13 @@ int ensure_batch_host_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
   return HISPMV_OK;
 }
 
-// Dense matrices, and sparse ones whose longest row a sub-warp can walk, take several vectors per pass;
+// Every non-empty matrix takes several vectors per pass (rows a sub-warp should not walk alone -- more than
+// kBatchMaxRowNnz nonzeros -- get one CTA each; column-slab and blocked matrices use their plain CSR here);
 // HISPMV_BATCH=0 turns it off.
 bool batch_eligible(const Matrix* m) {
   static const bool off = getenv("HISPMV_BATCH") && atoi(getenv("HISPMV_BATCH")) == 0;
   if (!off && m->dense) return m->local_rows() > 0 && m->cols > 0;
-  return !off && !m->dense && m->slabs.empty() && m->kernel != HISPMV_KERNEL_EMPTY && m->nnz > 0 &&
-         m->local_rows() > 0 && m->stats.max_row_nnz <= kBatchMaxRowNnz;
+  return !off && !m->dense && m->kernel != HISPMV_KERNEL_EMPTY && m->nnz > 0 && m->local_rows() > 0;
 }
 
 // y [nv][rows] = alpha * A x_k + beta * bias for the nv vectors x [nv][cols] (both row-major in HBM), in passes of up to
@@ -864,13 +876,24 @@ int run_matrix_batch(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_
   A.col = m->d_col;
   A.val = m->d_val;
   Epilogue ep{alpha, beta, d_bias, relu};
+  if (m->num_batch_long_rows < 0 && lanes <= 32) {  // first batch on this matrix: list the rows a sub-warp must not walk
+    m->num_batch_long_rows = 0;
+    if (m->stats.max_row_nnz > kBatchMaxRowNnz) {
+      st = batch_long_rows_device(m->d_row_ptr, (int32_t)rows, kBatchMaxRowNnz, m->nnz / kBatchMaxRowNnz + 1,
+                                  &m->d_batch_long_rows, &m->num_batch_long_rows, s);
+      if (st != HISPMV_OK) return st;
+    }
+  }
+  const int64_t n_long = lanes <= 32 ? std::max<int64_t>(m->num_batch_long_rows, 0) : 0;
   for (int64_t v0 = 0; v0 < nv; v0 += kBatchMax) {
     const int g = (int)std::min<int64_t>(kBatchMax, nv - v0);
     if (g == 1) {
       st = run_matrix(c, m, d_x + v0 * m->cols, d_bias, d_y + v0 * rows, alpha, beta, relu, s, lane);
     } else {
       st = launch_interleave(d_x + v0 * m->cols, g, m->cols, m->cols, c->d_xi[lane], s);
-      if (st == HISPMV_OK) st = launch_spmm_csr(A, lanes, c->d_xi[lane], d_y + v0 * rows, g, ep, s);
+      if (st == HISPMV_OK)
+        st = launch_spmm_csr(A, lanes, m->d_batch_long_rows, n_long, kBatchMaxRowNnz, c->d_xi[lane], d_y + v0 * rows, g,
+                             ep, s);
     }
     if (st != HISPMV_OK) return st;
   }
@@ -1372,6 +1395,7 @@ int hispmv_matrix_info_get(hispmv_ctx* c, int idx, hispmv_matrix_info* out) {
     out->long_threshold = m->slabs[0]->long_threshold;
     out->chunk_nnz = m->slabs[0]->chunk_nnz;
   }
+  out->slab_runs = m->dense ? 0 : m->slab_runs;
   out->probe_near = m->dense ? 0 : m->probe.near;
   out->probe_cmp = m->dense ? 0 : m->probe.cmp;
   out->long_threshold = m->dense ? 0 : m->long_threshold;

@@ -271,14 +271,22 @@ int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
 constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 12288, kPbLongThreshold = 4096, kPbChunkNnz = 16384;
-int select_blocked(int32_t rows, int32_t cols, int64_t nnz, const ColProbe& probe, int allow_split_rows);
+// (row, slab) runs of a device CSR for slabs of slab_cols columns: the selector's estimate of the piece count
+int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, int32_t slab_cols, int64_t* runs,
+                         cudaStream_t stream);
+int select_blocked(int32_t rows, int32_t cols, int64_t nnz, int64_t slab_runs, const ColProbe& probe,
+                   int allow_split_rows);
 
 // ---- batch.cu: several right-hand sides in one pass over A (x interleaved as xi[c * K + k], K = batch_width(nv)) ----
 int batch_width(int nv);  // 2, 4 or 8
 // x [nv][n] -> xi [n_pad][K] (rows n..n_pad-1 and vectors nv..K-1 zero)
 int launch_interleave(const float* x, int nv, int64_t n, int64_t n_pad, float* xi, cudaStream_t s);
 // y [nv][rows] = alpha * A x_k + beta * bias (+ReLU); `lanes` lanes walk each row
-int launch_spmm_csr(const CsrDev& A, int lanes, const float* xi, float* y, int nv, Epilogue ep, cudaStream_t s);
+// rows longer than long_len (the list long_rows, built once per matrix by batch_long_rows_device) get one CTA each
+int launch_spmm_csr(const CsrDev& A, int lanes, const int32_t* long_rows, int64_t n_long, int long_len, const float* xi,
+                    float* y, int nv, Epilogue ep, cudaStream_t s);
+int batch_long_rows_device(const int32_t* d_row_ptr, int32_t rows, int32_t min_len, int64_t max_count, int32_t** d_out,
+                           int64_t* count, cudaStream_t stream);
 
 // ---- gemv.cu --------------------------------------------------------------------------------
 struct DenseDev {

@@ -105,6 +105,8 @@ typedef struct hispmv_matrix_info {
   int32_t num_slabs;        /* > 0: x is larger than L2 and the matrix runs as this many column slabs, one launch each */
   int32_t slab_cols;        /* columns per slab */
   int32_t reserved_;
+  int64_t slab_runs;        /* selector input for BLOCKED: (row, 49152-column slab) runs of the matrix; 0 when the cheaper
+                               conditions (size, scattered columns) already ruled the strategy out */
 } hispmv_matrix_info;
 
 const char* hispmv_last_error(void);

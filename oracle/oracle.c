@@ -633,13 +633,25 @@ void oracle_pb_work(int S, const int* slab_ptr, int align, int n_cta, int64_t sl
   }
 }
 
-/* blocked.cu: select_blocked -- scattered columns over a large x on a matrix big enough for two launches */
-int oracle_select_blocked(int rows, int cols, int64_t nnz, int64_t probe_near, int64_t probe_cmp, int allow_split_rows) {
+/* blocked.cu: pb_count_runs_device -- (row, slab) runs: the piece count before group boundaries split any */
+int64_t oracle_pb_count_runs(int rows, const int* row_ptr, const int* col, int W) {
+  int64_t runs = 0;
+  int r, j;
+  for (r = 0; r < rows; ++r)
+    for (j = row_ptr[r]; j < row_ptr[r + 1]; ++j)
+      if (j == row_ptr[r] || col[j] / W != col[j - 1] / W) ++runs;
+  return runs;
+}
+
+/* blocked.cu: select_blocked -- scattered columns over a large x, a matrix big enough for two launches, and rows
+ * concentrated enough that the (row, slab) runs are at most 0.4 of the nonzeros */
+int oracle_select_blocked(int rows, int cols, int64_t nnz, int64_t slab_runs, int64_t probe_near, int64_t probe_cmp,
+                          int allow_split_rows) {
   const int banded = probe_cmp >= 64 && probe_near * 4 >= probe_cmp * 3;
   if (!allow_split_rows || banded || rows <= 0) return 0;
   if ((int64_t)cols < 1000000 || nnz < 16000000) return 0;
   if (((int64_t)cols + 49152 - 1) / 49152 > 4096) return 0;
-  return 1;
+  return slab_runs * 5 <= nnz * 2 ? 1 : 0;
 }
 
 /* nnz-balanced contiguous row blocks: bounds[k] = first row r with row_ptr[r] >= k*nnz/n_parts. */

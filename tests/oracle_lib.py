@@ -79,8 +79,10 @@ def oracle() -> C.CDLL:
     lib.oracle_pb_segments.argtypes = [i64, _i32p, _i32p, i, _i32p, i64, _i32p, _i32p, i, vp, vp, vp]
     lib.oracle_pb_segments.restype = i64
     lib.oracle_pb_work.argtypes = [i, _i32p, i, i, i64, _i32p]
-    lib.oracle_select_blocked.argtypes = [i, i, i64, i64, i64, i]
+    lib.oracle_select_blocked.argtypes = [i, i, i64, i64, i64, i64, i]
     lib.oracle_select_blocked.restype = i
+    lib.oracle_pb_count_runs.argtypes = [i, _i32p, _i32p, i]
+    lib.oracle_pb_count_runs.restype = i64
     lib.oracle_synth_row_len.argtypes = [i, C.c_uint64, _i64p, i64]
     lib.oracle_synth_row_len.restype = i
     lib.oracle_synth_csr.argtypes = [i, C.c_uint64, i, _i64p, i, i, vp, vp, vp]
@@ -262,8 +264,13 @@ def select_slab_cols(cols, nnz, near, cmp_):
     return oracle().oracle_select_slab_cols(cols, nnz, near, cmp_)
 
 
-def select_blocked(rows, cols, nnz, near, cmp_, allow_split=1):
-    return oracle().oracle_select_blocked(rows, cols, nnz, near, cmp_, allow_split)
+def select_blocked(rows, cols, nnz, slab_runs, near, cmp_, allow_split=1):
+    return oracle().oracle_select_blocked(rows, cols, nnz, slab_runs, near, cmp_, allow_split)
+
+
+def pb_count_runs(rp, ci, W=49152):
+    rp, ci = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32)
+    return int(oracle().oracle_pb_count_runs(rp.size - 1, rp, ci if ci.size else np.zeros(1, np.int32), W))
 
 
 def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):

@@ -94,12 +94,21 @@ def test_oracle_blocked_plan_reproduces_the_csr_product(seed, W, B, T, CH):
 
 
 def test_oracle_select_blocked_rule():
-    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 10, 1000) == 1      # C2
-    assert ol.select_blocked(100_000_000, 100_000_000, 1_000_000_000, 0, 1000) == 1   # C5
-    assert ol.select_blocked(20_000_000, 20_000_000, 540_000_000, 990, 1000) == 0     # C4: banded
-    assert ol.select_blocked(65536, 65536, 1_000_000, 10, 1000) == 0                  # C1: small
-    assert ol.select_blocked(8192, 8192, 6_700_000, 10, 1000) == 0                    # C3b: x fits L1
-    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 10, 1000, 0) == 0   # rows may not be split
+    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 30_000_000, 10, 1000) == 1    # C2: 0.3 runs per nonzero
+    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 40_000_000, 10, 1000) == 1
+    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 40_000_001, 10, 1000) == 0
+    assert ol.select_blocked(100_000_000, 100_000_000, 1_000_000_000, 999_000_000, 0, 1000) == 0  # C5: every nonzero a run
+    assert ol.select_blocked(20_000_000, 20_000_000, 540_000_000, 20_000_000, 990, 1000) == 0   # C4: banded
+    assert ol.select_blocked(65536, 65536, 1_000_000, 100_000, 10, 1000) == 0                   # C1: small
+    assert ol.select_blocked(8192, 8192, 6_700_000, 8192, 10, 1000) == 0                        # C3b: x fits L1
+    assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 30_000_000, 10, 1000, 0) == 0  # rows may not be split
+
+
+def test_oracle_run_count():
+    rp = np.array([0, 3, 3, 7], np.int32)
+    ci = np.array([1, 2, 50000, 0, 49151, 49152, 98304], np.int32)
+    assert ol.pb_count_runs(rp, ci, 49152) == 2 + 3
+    assert ol.pb_count_runs(rp, ci, 4) == 2 + 4
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -268,21 +277,31 @@ def test_blocked_host_run_pipelines_panel_ranges(eng):
 
 @pytest.mark.gpu
 def test_blocked_selector_bit_exact(eng):
-    """The selector sends a scattered-column matrix with >= 1 M columns and >= 16 M nonzeros to the blocked strategy
-    and leaves smaller / narrower ones on the one-pass kernels, exactly as oracle_select_blocked says."""
+    """The selector sends a scattered-column matrix with >= 1 M columns, >= 16 M nonzeros and at most 0.4 (row, slab)
+    runs per nonzero to the blocked strategy and leaves the others on the one-pass kernels, exactly as
+    oracle_select_blocked says; the run count itself is bit-exact against the oracle's."""
     import torch
-    for rows, cols, nnz in ((2_000_000, 1_500_000, 16_500_000), (2_000_000, 900_000, 16_500_000),
-                            (1_000_000, 1_500_000, 8_000_000)):
+    cases = ((400_000, 1_500_000, 16_500_000, 40),     # rows concentrated in 40-column bursts: few runs -> blocked
+             (2_000_000, 1_500_000, 16_500_000, 0),    # uniform columns: every nonzero its own run -> one-pass
+             (400_000, 900_000, 16_500_000, 40),       # x too small
+             (200_000, 1_500_000, 8_000_000, 40))      # too few nonzeros
+    for rows, cols, nnz, burst in cases:
         g = torch.Generator(device="cuda").manual_seed(rows + cols)
         r = torch.randint(0, rows, (nnz,), device="cuda", generator=g, dtype=torch.int32)
-        c = torch.randint(0, cols, (nnz,), device="cuda", generator=g, dtype=torch.int32)
+        if burst:   # a row's entries sit in a few bursts of `burst` consecutive columns
+            start = (r.long() * 7919) % (cols - 64)
+            c = (start + torch.randint(0, burst, (nnz,), device="cuda", generator=g)).to(torch.int32)
+        else:
+            c = torch.randint(0, cols, (nnz,), device="cuda", generator=g, dtype=torch.int32)
         v = torch.randn(nnz, device="cuda", generator=g)
         idx = eng.create_sparse_handle_coo_dev(r, c, v, rows, cols)
         info = eng.matrix_info(idx)
-        want = ol.select_blocked(rows, cols, nnz, info["probe_near"], info["probe_cmp"])
-        assert (info["kernel_name"] == "blocked") == bool(want), (rows, cols, nnz, info["kernel_name"])
+        rp, ci, vv = eng.plan_csr(idx)
+        runs = ol.pb_count_runs(rp, ci) if info["slab_runs"] else 0
+        assert info["slab_runs"] == runs
+        want = ol.select_blocked(rows, cols, nnz, runs, info["probe_near"], info["probe_cmp"]) if runs else 0
+        assert (info["kernel_name"] == "blocked") == bool(want), (rows, cols, nnz, info["kernel_name"], runs)
         if want:
             pb = eng.plan_blocked(idx, arrays=False)
             assert pb["slab_cols"] == 49152 and pb["num_slabs"] == (cols + 49151) // 49152
-        rp, ci, vv = eng.plan_csr(idx)
         _check_run(eng, idx, rp, ci, vv, rows, cols, np.random.default_rng(1))

@@ -96,7 +96,9 @@ def test_full_size_spmv_properties(which):
         idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
         info = eng.matrix_info(idx)
         assert info["nnz"] == d.nnz and info["rows"] == spec.rows
-        expect_kernel = {"c2": "adaptive", "c4": "rowstage", "c5": "adaptive"}[which]
+        # C2's rows are concentrated (0.3 (row, slab) runs per nonzero): the two-pass blocked strategy; C5's uniform
+        # columns make every nonzero its own run: one-pass kernel over column slabs; C4 is banded: row-major staging
+        expect_kernel = {"c2": "blocked", "c4": "rowstage", "c5": "adaptive"}[which]
         assert info["kernel_name"] == expect_kernel
         if which == "c5":
             assert info["num_slabs"] >= 2          # x (400 MB) does not fit L2: column slabs
@@ -154,17 +156,29 @@ def test_full_size_spmv_properties(which):
             eng.force_kernel(idx, capi.KERNEL_AUTO)
 
         # --- integer artefacts ---
+        blocked = info["kernel_name"] == "blocked"
         if info["num_slabs"] == 0:
             tr, tn = eng.plan_tiles(idx)
-            assert tn[0] == 0 and tn[-1] == d.nnz and np.all(np.diff(tn) >= 0)
+            # tiles / panels cover the nonzeros (blocked: the PIECES, runs of one row inside a 512-entry group) in order
+            covered = eng.plan_blocked(idx, arrays=False)["num_pieces"] if blocked else d.nnz
+            assert tn[0] == 0 and tn[-1] == covered and np.all(np.diff(tn) >= 0) and covered <= d.nnz
             assert tr[0] == 0 and tr[-1] == spec.rows and np.all(np.diff(tr) >= 0)
         split = eng.plan_split_rows(idx)
         assert np.all(np.diff(split) > 0)
         lens = (rp[1:] - rp[:-1])
         if which == "c2":
+            assert int(lens.max()) == 1_000_000                                  # the clipped head of the power law
+            if blocked:
+                pb = eng.plan_blocked(idx, arrays=False)
+                assert info["slab_runs"] * 5 <= d.nnz * 2 and info["slab_runs"] <= pb["num_pieces"] <= d.nnz // 2
+                # the same matrix on the one-pass kernel: heavy rows are cut into LONG tiles and meet through carries
+                eng.force_kernel(idx, capi.KERNEL_ADAPTIVE)
+                info = eng.matrix_info(idx)
+                split = eng.plan_split_rows(idx)
+                _run(eng, idx, xa, y0, y2)
+                assert _max_err(y2, y64, scale) <= TOL
             long_rows = torch.nonzero(lens >= info["long_threshold"]).flatten().cpu().numpy()   # rows cut into LONG tiles
             assert split.size > 0 and np.isin(split, long_rows).all()
-            assert int(lens.max()) == 1_000_000                                  # the clipped head of the power law
         else:
             assert split.size == 0
     finally:

@@ -15,7 +15,13 @@ LIB       := $(PKG)/libhispmv_cuda.so
 PYEXT     := $(PKG)/pyhispmv$(shell $(PY) -c "import sysconfig;print(sysconfig.get_config_var('EXT_SUFFIX'))")
 PYINC     := $(shell $(PY) -c "import sysconfig,pybind11;print('-I'+sysconfig.get_paths()['include'],'-I'+pybind11.get_include())")
 
-all: $(LIB) $(PYEXT) oracle
+CUSPARSE_REF := tools/libcusparse_ref.so
+
+all: $(LIB) $(PYEXT) $(CUSPARSE_REF) oracle
+
+# comparator only (bench.py's vs_cusparse): the reference's gpu/ baseline call; nothing in the package links it
+$(CUSPARSE_REF): tools/cusparse_ref.cu
+	$(NVCC) -O2 -shared -Xcompiler -fPIC $(ARCH) $< -o $@ -lcusparse
 
 $(OBJDIR)/%.o: $(CSRC)/%.cu $(CSRC)/internal.h $(CSRC)/device_utils.cuh $(CSRC)/tile_device.cuh include/hispmv.h
 	@mkdir -p $(OBJDIR)
@@ -32,7 +38,7 @@ oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf build $(LIB) $(PKG)/pyhispmv*.so
+	rm -rf build $(LIB) $(PKG)/pyhispmv*.so $(CUSPARSE_REF)
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean

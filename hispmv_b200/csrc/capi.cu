@@ -8,6 +8,9 @@
 #include <sstream>
 #include <string>
 #include <algorithm>
+#include <condition_variable>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -122,6 +125,105 @@ struct Matrix {
 
 using namespace hispmv;
 
+namespace {
+
+// Parallel host memcpy for callers that hand in pageable memory (plain numpy arrays through pyhispmv): a few resident
+// threads copy slices of the caller's vector into / out of the context's pinned ring while the previous slice crosses
+// PCIe.  One copy at a time (the plugin is single-threaded, pyhispmv holds the GIL for the whole call).
+class HostCopier {
+ public:
+  explicit HostCopier(int n_threads) {
+    for (int i = 0; i < n_threads; ++i) th_.emplace_back([this, i] { work(i); });
+    tasks_.resize((size_t)n_threads);
+  }
+  ~HostCopier() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    const size_t parts = th_.size() + 1;
+    if (bytes < (1u << 20) || th_.empty()) {
+      memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+    {
+      std::lock_guard<std::mutex> g(m_);
+      for (size_t i = 0; i < th_.size(); ++i) {
+        const size_t off = std::min(bytes, (i + 1) * per);
+        const size_t end = std::min(bytes, (i + 2) * per);
+        tasks_[i] = Task{static_cast<char*>(dst) + off, static_cast<const char*>(src) + off, end - off};
+      }
+      pending_ = (int)th_.size();
+      ++gen_;
+    }
+    cv_.notify_all();
+    memcpy(dst, src, std::min(bytes, per));
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+  }
+
+ private:
+  struct Task {
+    char* d;
+    const char* s;
+    size_t n;
+  };
+  void work(int i) {
+    uint64_t seen = 0;
+    for (;;) {
+      Task t;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        t = tasks_[(size_t)i];
+      }
+      if (t.n) memcpy(t.d, t.s, t.n);
+      {
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::vector<Task> tasks_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  uint64_t gen_ = 0;
+  int pending_ = 0;
+  bool stop_ = false;
+};
+
+constexpr int kPinSlots = 3;
+constexpr size_t kPinSlotBytes = 8u << 20;      // slice of a pageable vector in flight
+constexpr int64_t kSmallCallBytes = 1 << 20;    // x + bias + y up to this size take the one-graph path
+
+// One captured launch sequence of the small host-buffer call: H2D (x | bias) -> kernel(s) -> D2H y
+struct SmallGraph {
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+};
+struct SmallKey {
+  const void* m;
+  uint32_t alpha, beta;
+  int has_bias;
+  bool operator<(const SmallKey& o) const {
+    if (m != o.m) return m < o.m;
+    if (alpha != o.alpha) return alpha < o.alpha;
+    if (beta != o.beta) return beta < o.beta;
+    return has_bias < o.has_bias;
+  }
+};
+
+}  // namespace
+
 struct hispmv_ctx {
   int device = 0;
   int flags = 0;
@@ -148,6 +250,24 @@ struct hispmv_ctx {
   float* d_y[2] = {nullptr, nullptr};
   float* d_bias = nullptr;
   int64_t cap_x = 0, cap_y = 0;
+  // callers with pageable memory: pinned ring + copier threads (created on first use)
+  char* h_pin[kPinSlots] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_pin[kPinSlots] = {nullptr, nullptr, nullptr};
+  HostCopier* copier = nullptr;
+  // small calls (a DNN layer's vectors): pinned (x | bias | y) + device (x | bias), one CUDA graph per (matrix, alpha, beta)
+  float* h_small = nullptr;
+  float* d_small = nullptr;
+  int64_t cap_small = 0;            // floats in h_small / d_small
+  std::map<SmallKey, SmallGraph> small_graphs;
+  std::map<const void*, int> small_seen;   // eager runs before a matrix's calls are captured
+
+  void drop_small_graphs() {
+    for (auto& kv : small_graphs) {
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    small_graphs.clear();
+  }
 
   int64_t used_bytes() const {
     int64_t b = 0;
@@ -202,6 +322,139 @@ int ensure_staging(hispmv_ctx* c, int64_t n_x, int64_t n_y) {
     if (st != HISPMV_OK) return scratch(st);
     c->cap_y = n_y;
   }
+  return HISPMV_OK;
+}
+
+// ---- host-buffer plumbing ------------------------------------------------------------------------------------------
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_pin_ring(hispmv_ctx* c) {
+  if (c->h_pin[0]) return HISPMV_OK;
+  for (int i = 0; i < kPinSlots; ++i) {
+    int st = check_cuda(cudaMallocHost((void**)&c->h_pin[i], kPinSlotBytes), "cudaMallocHost(pinned ring)", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaEventCreateWithFlags(&c->ev_pin[i], cudaEventDisableTiming), "event", __FILE__, __LINE__);
+    if (st != HISPMV_OK) return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st;
+  }
+  if (!c->copier) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    c->copier = new HostCopier((int)std::max(1u, std::min(7u, hw > 1 ? hw / 2 : 1u)));
+  }
+  return HISPMV_OK;
+}
+
+// pageable host -> device through the pinned ring: the copier threads fill slot k while slot k-1 crosses PCIe
+int staged_h2d(hispmv_ctx* c, void* d_dst, const void* h_src, size_t bytes, cudaStream_t s) {
+  int st = ensure_pin_ring(c);
+  if (st != HISPMV_OK) return st;
+  int k = 0;
+  for (size_t off = 0; off < bytes; off += kPinSlotBytes, ++k) {
+    const int slot = k % kPinSlots;
+    const size_t len = std::min(kPinSlotBytes, bytes - off);
+    if (k >= kPinSlots) HISPMV_CUDA(cudaEventSynchronize(c->ev_pin[slot]));  // its previous slice has left the slot
+    c->copier->copy(c->h_pin[slot], static_cast<const char*>(h_src) + off, len);
+    HISPMV_CUDA(cudaMemcpyAsync(static_cast<char*>(d_dst) + off, c->h_pin[slot], len, cudaMemcpyHostToDevice, s));
+    HISPMV_CUDA(cudaEventRecord(c->ev_pin[slot], s));
+  }
+  // the ring is free again for whoever comes next (the slots still in flight are waited for here: at most kPinSlots)
+  for (int i = 0; i < std::min(k, kPinSlots); ++i) HISPMV_CUDA(cudaEventSynchronize(c->ev_pin[i]));
+  return HISPMV_OK;
+}
+
+// device -> pageable host: slice k+1 crosses PCIe while the copier threads move slice k out of its slot
+int staged_d2h(hispmv_ctx* c, void* h_dst, const void* d_src, size_t bytes, cudaStream_t s) {
+  int st = ensure_pin_ring(c);
+  if (st != HISPMV_OK) return st;
+  const int n = (int)((bytes + kPinSlotBytes - 1) / kPinSlotBytes);
+  auto len_of = [&](int k) { return std::min(kPinSlotBytes, bytes - (size_t)k * kPinSlotBytes); };
+  for (int k = 0; k <= n; ++k) {
+    if (k < n) {
+      const int slot = k % kPinSlots;
+      HISPMV_CUDA(cudaMemcpyAsync(c->h_pin[slot], static_cast<const char*>(d_src) + (size_t)k * kPinSlotBytes, len_of(k),
+                                  cudaMemcpyDeviceToHost, s));
+      HISPMV_CUDA(cudaEventRecord(c->ev_pin[slot], s));
+    }
+    if (k >= 1) {
+      const int slot = (k - 1) % kPinSlots;
+      HISPMV_CUDA(cudaEventSynchronize(c->ev_pin[slot]));
+      c->copier->copy(static_cast<char*>(h_dst) + (size_t)(k - 1) * kPinSlotBytes, c->h_pin[slot], len_of(k - 1));
+    }
+  }
+  return HISPMV_OK;
+}
+
+int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
+               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1, int y_mc = 0,
+               int phases = 3);
+
+// The small host-buffer call (a DNN layer's vectors: tens of kilobytes).  Everything is latency here, so the call is
+// one memcpy into pinned memory, ONE graph launch -- H2D of (x | bias), the kernel(s), D2H of y, captured once per
+// (matrix, alpha, beta) -- one stream synchronisation and one memcpy out.  The first call on a matrix runs the same
+// sequence eagerly (lazy per-kernel attributes are set outside any capture).
+int small_call(hispmv_ctx* c, Matrix* m, const float* x, const float* bias, float* y, float alpha, float beta) {
+  const int64_t cols = m->cols, n_y = m->local_rows();
+  const int64_t cpad = (cols + 3) & ~3LL, ypad = (n_y + 3) & ~3LL;
+  const int64_t need = cpad + 2 * ypad + 4;
+  if (need > c->cap_small) {
+    c->drop_small_graphs();
+    c->cap_small = 0;
+    if (c->h_small) cudaFreeHost(c->h_small);
+    cudaFree(c->d_small);
+    c->h_small = nullptr;
+    c->d_small = nullptr;
+    const int64_t cap = std::max<int64_t>(need, 1 << 16);
+    int st = check_cuda(cudaMallocHost((void**)&c->h_small, (size_t)cap * 4), "cudaMallocHost(small)", __FILE__, __LINE__);
+    if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)&c->d_small, (size_t)cap * 4), "cudaMalloc(small)", __FILE__, __LINE__);
+    if (st != HISPMV_OK) return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st;
+    c->cap_small = cap;
+  }
+  float *hx = c->h_small, *hb = hx + cpad, *hy = hb + ypad;
+  float *dx = c->d_small, *db = dx + cpad, *dy = db + ypad;
+  if (cols > 0) memcpy(hx, x, (size_t)cols * 4);
+  if (bias && n_y > 0) memcpy(hb, bias, (size_t)n_y * 4);
+  cudaStream_t s = c->stream;
+  const size_t up = (size_t)(bias ? cpad + n_y : cols) * 4;
+  auto enqueue = [&]() -> int {
+    if (up > 0) HISPMV_CUDA(cudaMemcpyAsync(dx, hx, up, cudaMemcpyHostToDevice, s));
+    int st = run_matrix(c, m, dx, bias ? db : nullptr, dy, alpha, beta, 0, s, 0, 0, -1, 0, 3);
+    if (st != HISPMV_OK) return st;
+    if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(hy, dy, (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
+    return HISPMV_OK;
+  };
+  uint32_t ab, bb;
+  memcpy(&ab, &alpha, 4);
+  memcpy(&bb, &beta, 4);
+  const SmallKey key{m, ab, bb, bias != nullptr};
+  static const bool no_graph = getenv("HISPMV_SMALL_GRAPH") && atoi(getenv("HISPMV_SMALL_GRAPH")) == 0;
+  auto it = c->small_graphs.find(key);
+  if (it == c->small_graphs.end() && !no_graph && c->small_seen[m]++ >= 1) {
+    SmallGraph g;
+    HISPMV_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int st = enqueue();
+    const cudaError_t e = cudaStreamEndCapture(s, &g.graph);
+    if (st == HISPMV_OK && e == cudaSuccess && g.graph &&
+        cudaGraphInstantiate(&g.exec, g.graph, 0) == cudaSuccess) {
+      it = c->small_graphs.emplace(key, g).first;
+    } else {  // not capturable (should not happen): stay on the eager sequence for this matrix
+      if (g.graph) cudaGraphDestroy(g.graph);
+      cudaGetLastError();
+      c->small_seen[m] = -(1 << 30);
+    }
+  }
+  if (it != c->small_graphs.end()) {
+    HISPMV_CUDA(cudaGraphLaunch(it->second.exec, s));
+  } else {
+    const int st = enqueue();
+    if (st != HISPMV_OK) return st;
+  }
+  HISPMV_CUDA(cudaStreamSynchronize(s));
+  if (n_y > 0) memcpy(y, hy, (size_t)n_y * 4);
   return HISPMV_OK;
 }
 
@@ -634,8 +887,7 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
 // Device-pointer callers get lane 0: one run in flight per matrix handle, as with the reference's xrt::run.
 // `phases`: BLOCKED only -- bit 0 runs pass 1 (products of the whole matrix), bit 1 pass 2 over the given panels.
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
-               int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1, int y_mc = 0,
-               int phases = 3) {
+               int relu, cudaStream_t s, int lane, int64_t tile_begin, int64_t tile_count, int y_mc, int phases) {
   Epilogue ep{alpha, beta, d_bias, relu};
   ep.y_mc = y_mc;
   if (y_mc && !m->dense && (m->kernel == HISPMV_KERNEL_MERGE || !m->slabs.empty() || m->pipeline)) {
@@ -971,6 +1223,14 @@ void hispmv_destroy(hispmv_ctx* c) {
   cudaFree(c->d_xi[1]);
   cudaFree(c->d_xb);
   cudaFree(c->d_yb);
+  c->drop_small_graphs();
+  if (c->h_small) cudaFreeHost(c->h_small);
+  cudaFree(c->d_small);
+  delete c->copier;
+  for (int i = 0; i < kPinSlots; ++i) {
+    if (c->h_pin[i]) cudaFreeHost(c->h_pin[i]);
+    if (c->ev_pin[i]) cudaEventDestroy(c->ev_pin[i]);
+  }
   cudaEventDestroy(c->ev_bias);
   cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->stream2);
@@ -1070,6 +1330,8 @@ int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
     return HISPMV_ERR_ARG;
   }
   DeviceGuard g(c->device);
+  c->drop_small_graphs();  // captured launches of the old plan
+  c->small_seen.erase(m);
   m->forced = kernel != HISPMV_KERNEL_AUTO;
   m->kernel = kernel;
   m->lanes = lanes;
@@ -1185,7 +1447,36 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
                      !m->pipeline && !m->persistent && !m->warptile && m->slabs.empty();
   int chunks = 1;
   if (tiled && n_y >= (1 << 20) && m->num_tiles >= 64) chunks = n_y >= (1 << 22) ? 8 : 4;
+  // Callers with PAGEABLE memory (plain numpy arrays through pyhispmv.FpgaHandle.run_kernel): cudaMemcpyAsync on such
+  // pointers is staged by the driver one copy after the other (C2: 8.9 ms per call against 1.9 ms from pinned memory),
+  // so large vectors go through the context's own pinned ring, filled and drained by a few copier threads while the
+  // neighbouring slice crosses PCIe.
+  const bool big = (int64_t)m->cols * 4 >= (4 << 20) || n_y * 4 >= (4 << 20);
+  const bool pageable = big && ((x_host && is_pageable(x_host)) || (bias && is_pageable(bias)) || is_pageable(y));
+  if (pageable) {
+    cudaStream_t s_up = c->stream2;
+    if (x_host && m->cols > 0) {
+      st = staged_h2d(c, c->d_x[0], x_host, (size_t)m->cols * 4, s_up);
+      if (st != HISPMV_OK) return st;
+    }
+    if (bias && n_y > 0) {
+      st = staged_h2d(c, c->d_bias, bias, (size_t)n_y * 4, s_up);
+      if (st != HISPMV_OK) return st;
+    }
+    HISPMV_CUDA(cudaEventRecord(c->ev_pipe[1], s_up));
+    HISPMV_CUDA(cudaStreamWaitEvent(s, c->ev_pipe[1], 0));
+    st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s);
+    if (st != HISPMV_OK) return st;
+    if (n_y > 0) {
+      st = staged_d2h(c, y, c->d_y[0], (size_t)n_y * 4, s);
+      if (st != HISPMV_OK) return st;
+    }
+    HISPMV_CUDA(cudaStreamSynchronize(s));
+    return HISPMV_OK;
+  }
   if (chunks == 1) {
+    if (x_host && ((int64_t)m->cols + 2 * n_y) * 4 <= kSmallCallBytes && n_y > 0)
+      return small_call(c, m, x_host, bias, y, alpha, beta);
     if (x_host && m->cols > 0)
       HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s));
     if (bias && n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(c->d_bias, bias, (size_t)n_y * 4, cudaMemcpyHostToDevice, s));
@@ -1318,6 +1609,8 @@ int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const f
   DeviceGuard g(c->device);
   const int64_t num_vecs = x_len / m->cols;  // reference: integer division, remainder ignored (fpga_handle.cpp:336)
   const int64_t n_y = m->local_rows();
+  if (num_vecs == 1 && n_y > 0 && ((int64_t)m->cols + 2 * n_y) * 4 <= kSmallCallBytes)
+    return small_call(c, m, x, bias, y_out, 1.0f, 1.0f);  // batch 1, a layer of model_test: one graph launch
   int st = ensure_staging(c, m->cols, n_y);
   if (st != HISPMV_OK) return st;
   cudaStream_t lanes[2] = {c->stream, c->stream2};

@@ -273,6 +273,15 @@ def test_blocked_host_run_pipelines_panel_ranges(eng):
                 torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(yd.cpu().numpy().view(np.uint32), y_host.view(np.uint32))
+    # pinned host buffers: pass 1 once, then pass 2 range by range around the bias / y copies
+    import ctypes as C
+    from hispmv_b200.capi import lib, check
+    xp, bp = torch.from_numpy(x).pin_memory(), torch.from_numpy(y0).pin_memory()
+    yp = torch.full((rows,), float("nan")).pin_memory()
+    eng.select_matrix(idx)
+    check(lib.hispmv_run(eng._ctx, C.c_void_p(xp.data_ptr()), C.c_void_p(bp.data_ptr()), C.c_void_p(yp.data_ptr()),
+                         float(ALPHA), float(BETA)), "hispmv_run")
+    assert np.array_equal(yp.numpy().view(np.uint32), y_host.view(np.uint32))
 
 
 @pytest.mark.gpu

@@ -644,9 +644,24 @@ def test_device_chain_batched_forward(eng):
         assert np.abs(out - one).max() <= 1e-4 * max(1.0, np.abs(one).max())
 
 
+def _run_pinned(eng, x, y0, alpha, beta):
+    """hispmv_run with PINNED host buffers (the range-pipelined path); plain numpy arrays are pageable and take the
+    staged path."""
+    import ctypes as C
+    import torch
+    from hispmv_b200.capi import lib, check
+    xp, bp = torch.from_numpy(x).pin_memory(), torch.from_numpy(y0).pin_memory()
+    yp = torch.full((y0.size,), float("nan")).pin_memory()
+    check(lib.hispmv_run(eng._ctx, C.c_void_p(xp.data_ptr()), C.c_void_p(bp.data_ptr()), C.c_void_p(yp.data_ptr()),
+                         float(alpha), float(beta)), "hispmv_run")
+    return yp.numpy().copy()
+
+
 def test_host_run_pipelines_row_ranges(eng):
-    """hispmv_run on a matrix with > 2^20 rows cuts the rows into ranges at tile boundaries and overlaps bias upload,
-    kernel and y download of different ranges: same result as the device-resident single launch, bit for bit."""
+    """hispmv_run on a matrix with > 2^20 rows: from pinned memory the rows are cut into ranges at tile boundaries and
+    bias upload, kernel and y download of different ranges overlap; from pageable memory (plain numpy arrays, the way
+    the plugin is called) the vectors go through the context's pinned ring.  Both give the device-resident single
+    launch's result, bit for bit."""
     import torch
     from hispmv_b200 import synth
     spec = synth.c2_powerlaw(0.13)                       # 1.3 M rows, ~13 M nnz, rows of up to 520 k nonzeros
@@ -664,11 +679,51 @@ def test_host_run_pipelines_row_ranges(eng):
                 torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     assert np.array_equal(y.view(np.uint32), yd.cpu().numpy().view(np.uint32))
+    assert np.array_equal(_run_pinned(eng, x, y0, ALPHA, BETA).view(np.uint32), y.view(np.uint32))
     n = 300000
     rp, ci, vv = ol.synth_csr(spec.kind, spec.seed, spec.cols, spec.params, 0, n)
     y64, scale = ol.spmv_f64(rp, ci, vv, x, y0[:n], ALPHA, BETA)
     err, at = ol.max_scaled_error(y[:n], y64, scale)
     assert err <= TOL, (err, at)
+
+
+def test_small_calls_are_one_graph_launch_and_stay_exact(eng, monkeypatch):
+    """A DNN layer's vectors (tens of KB): from the second call on, run_kernel / linear replay one captured graph (H2D,
+    kernel, D2H).  Results are bit-identical to the eager sequence (HISPMV_SMALL_GRAPH=0 keeps every call eager: checked
+    in a second engine), for changing x / bias, two alpha-beta pairs and a re-planned matrix."""
+    from hispmv_b200 import Engine, capi
+    rng = np.random.default_rng(31)
+    rows, cols = 3000, 5000
+    r, c, v = _matrix(rng, "powerlaw", rows, cols)
+    idx = eng.create_sparse_handle(r, c, v, rows, cols)
+    rp, ci, vv = eng.plan_csr(idx)
+    eng.select_matrix(idx)
+    outs = []
+    for k in range(5):
+        x = rng.standard_normal(cols).astype(np.float32)
+        b = rng.standard_normal(rows).astype(np.float32)
+        for alpha, beta in ((0.85, -2.06), (1.0, 0.0)):
+            y = np.full(rows, np.nan, np.float32)
+            eng.run_kernel(x, b, y, alpha, beta)
+            y64, scale = ol.spmv_f64(rp, ci, vv, x, b, np.float32(alpha), np.float32(beta))
+            assert ol.max_scaled_error(y, y64, scale)[0] <= TOL
+            outs.append((x, b, alpha, beta, y))
+        yl = eng.linear(idx, x, b)
+        y64, scale = ol.spmv_f64(rp, ci, vv, x, b, 1.0, 1.0)
+        assert ol.max_scaled_error(yl, y64, scale)[0] <= TOL
+        if k == 2:
+            eng.force_kernel(idx, capi.KERNEL_MERGE)     # the captured launches of the old plan are dropped
+    monkeypatch.setenv("HISPMV_SMALL_GRAPH", "0")         # read once per process: only a fresh check of the values
+    e2 = Engine(0)
+    try:
+        i2 = e2.create_sparse_handle(r, c, v, rows, cols)
+        e2.select_matrix(i2)
+        x, b, alpha, beta, y = outs[0]
+        y2 = np.zeros(rows, np.float32)
+        e2.run_kernel(x, b, y2, alpha, beta)
+        assert np.array_equal(y.view(np.uint32), y2.view(np.uint32))
+    finally:
+        e2.close()
 
 
 def test_run_xdev_matches_run_and_respects_the_x_stream(eng, monkeypatch):

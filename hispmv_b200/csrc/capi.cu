@@ -1941,23 +1941,34 @@ int hispmv_parse_mtx(const char* path, int32_t* rows_out, int32_t* cols_out, int
     ck.r.reserve(guess);
     ck.c.reserve(guess);
     ck.v.reserve(guess);
+    // One entry per LINE, as the reference's getline loop reads them (common/src/spmv-helper.cpp:92-97): a number is
+    // only looked for inside its own line (strtol / strtof would otherwise skip the newline and borrow tokens from the
+    // next line), and a line that does not hold "row col [value]" is skipped, as oracle_load_mtx skips it.
+    auto blanks = [](const char* a, const char* b) {
+      while (a < b && (*a == ' ' || *a == '\t' || *a == '\r')) ++a;
+      return a;
+    };
     while (s < e) {
+      const char* nl = (const char*)memchr(s, '\n', (size_t)(e - s));
+      const char* le = nl ? nl : e;          // the line is [s, le); the last one may lack its newline
+      const char* next = nl ? nl + 1 : e;
       char* q;
-      while (s < e && (*s == ' ' || *s == '\t' || *s == '\r' || *s == '\n')) ++s;
-      if (s >= e) break;
-      const long r = strtol(s, &q, 10);
-      if (q == s) { ck.stopped = true; break; }
-      s = q;
-      const long cc = strtol(s, &q, 10);
-      if (q == s) { ck.stopped = true; break; }
-      s = q;
+      const char* a = blanks(s, le);
+      s = next;
+      if (a >= le) continue;
+      const long r = strtol(a, &q, 10);
+      if (q == a) continue;
+      a = blanks(q, le);
+      if (a >= le) continue;
+      const long cc = strtol(a, &q, 10);
+      if (q == a) continue;
       float v = 1.0f;
       if (!pattern) {
-        v = strtof(s, &q);
-        if (q == s) { ck.stopped = true; break; }
-        s = q;
+        a = blanks(q, le);
+        if (a >= le) continue;
+        v = strtof(a, &q);
+        if (q == a) continue;
       }
-      while (s < e && *s != '\n') ++s;  // rest of the line
       if (v == 0) continue;
       ck.r.push_back((int32_t)(r - 1));
       ck.c.push_back((int32_t)(cc - 1));

@@ -77,7 +77,9 @@ def test_matches_the_reference_readers(tmp_path):
             assert _same(got, (r2, c2, v2, rr.value, cc.value)), (name, pre)
 
 
-def test_a_line_that_does_not_parse_ends_the_file(tmp_path, monkeypatch):
+def test_a_line_that_does_not_parse_is_skipped(tmp_path, monkeypatch):
+    """The reference's stream extraction leaves such a line undefined (uninitialised column and value,
+    common/src/spmv-helper.cpp:92-97); the oracle's reader skips it and so does the product, whatever the thread count."""
     body = "".join(f"{i % 50 + 1} {i % 40 + 1} {i + 0.5}\n" for i in range(3000))
     text = "%%MatrixMarket matrix coordinate real general\n50 40 6001\n" + body + "oops\n" + body
     p = tmp_path / "broken.mtx"
@@ -85,7 +87,8 @@ def test_a_line_that_does_not_parse_ends_the_file(tmp_path, monkeypatch):
     for threads in ("1", "5"):
         monkeypatch.setenv("HISPMV_MTX_THREADS", threads)
         r, c, v, nr, nc = parse_mtx(str(p))
-        assert (nr, nc) == (50, 40) and r.size == 3000 and v[-1] == np.float32(2999.5)
+        assert (nr, nc) == (50, 40) and r.size == 6000 and v[2999] == np.float32(2999.5) and v[3000] == np.float32(0.5)
+        assert _same(parse_mtx(str(p)), ol.load_mtx(str(p)))
 
 
 def test_errors_carry_the_reference_messages(tmp_path):
@@ -137,3 +140,25 @@ def test_random_well_formed_files_match_the_oracle(tmp_path, monkeypatch):
         assert _same(parse_mtx(str(p)), ol.load_mtx(str(p)))
 
     run()
+
+
+def test_entries_are_parsed_line_by_line(tmp_path, monkeypatch):
+    """A short line does not borrow tokens from the next one, a line that is not "row col [value]" is skipped (as the
+    oracle skips it; the reference's stream extraction leaves it undefined), and a last line without its newline is
+    kept -- the one documented difference from the reference readers, whose `!file.eof()` loop
+    (common/src/spmv-helper.cpp:92) drops it."""
+    text = ("%%MatrixMarket matrix coordinate real general\n4 4 6\n"
+            "1 1 1.5\n"
+            "2\n"                 # short line: must not take "3 3" from the next line as its column and value
+            "3 3 2.5\n"
+            "x y z\n"             # not an entry
+            "4 2\n"               # value missing
+            "2 4 -3.25")          # no trailing newline
+    p = tmp_path / "lines.mtx"
+    p.write_text(text)
+    for threads in ("1", "3"):
+        monkeypatch.setenv("HISPMV_MTX_THREADS", threads)
+        r, c, v, nr, nc = parse_mtx(str(p))
+        assert (nr, nc) == (4, 4)
+        assert r.tolist() == [0, 2, 1] and c.tolist() == [0, 2, 3] and v.tolist() == [1.5, 2.5, -3.25]
+        assert _same(parse_mtx(str(p)), ol.load_mtx(str(p)))

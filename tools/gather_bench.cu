@@ -97,7 +97,7 @@ float run(int grid, int threads, const int32_t* idx, int64_t n, const float* tab
   return best;
 }
 
-int main() {
+int main(int argc, char** argv) {
   cudaDeviceProp p;
   CK(cudaGetDeviceProperties(&p, 0));
   const int sms = p.multiProcessorCount;
@@ -111,6 +111,17 @@ int main() {
   CK(cudaMemset(tab, 0, table * 4 + 64));
   make_idx<<<(int)((n + 255) / 256), 256>>>(idx, n, table);
   CK(cudaDeviceSynchronize());
+  if (argc > 1 && argv[1][0] == 'n') {
+    // `gather_bench ncu`: the two launches ncu --set full looks at (which lts__ / l1tex__ unit sits at its peak when the
+    // chip answers ~277 G scattered sectors per second?): uniform indices, then 25 % of them inside a 32 KB head
+    const float a = run<1>(sms * 2, 1024, idx, n, tab, 0, out);
+    make_hot<<<(int)((n + 255) / 256), 256>>>(idx, n, 8192, 25);
+    CK(cudaDeviceSynchronize());
+    const float b = run<1>(sms * 2, 1024, idx, n, tab, 0, out);
+    printf("ncu mode: uniform %7.2f G gathers/s | 25%% in a 32 KB head %7.2f G gathers/s (nc.L1::no_allocate, %d SMs x 2 CTAs x 1024)\n",
+           n / a / 1e6, n / b / 1e6, sms);
+    return 0;
+  }
   printf("A/B/C: uniform random gathers from a 40 MB table, %lld gathers\n", (long long)n);
   for (int frac : {4, 2, 1}) {
     const int use = sms / frac;

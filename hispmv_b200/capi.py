@@ -51,6 +51,9 @@ def _load() -> C.CDLL:
         "hispmv_last_error": (C.c_char_p, []),
         "hispmv_version": (C.c_int, []),
         "hispmv_create": (C.c_int, [pp, C.c_int, C.c_int]),
+        "hispmv_create_multi": (C.c_int, [pp, C.c_int, C.c_int, C.c_int]),
+        "hispmv_multi_gpus": (C.c_int, [p]),
+        "hispmv_multi_child": (C.c_void_p, [p, C.c_int]),
         "hispmv_destroy": (None, [p]),
         "hispmv_set_shard": (C.c_int, [p, C.c_int, C.c_int]),
         "hispmv_shard_bounds": (C.c_int, [p, i32, C.c_int, p]),
@@ -103,7 +106,7 @@ def _load() -> C.CDLL:
 
 lib = _load()
 EXPORTED = [
-    "hispmv_last_error", "hispmv_version", "hispmv_create", "hispmv_destroy", "hispmv_set_shard",
+    "hispmv_last_error", "hispmv_version", "hispmv_create", "hispmv_create_multi", "hispmv_multi_gpus", "hispmv_multi_child", "hispmv_destroy", "hispmv_set_shard",
     "hispmv_shard_bounds", "hispmv_set_memory_limit", "hispmv_add_sparse_coo", "hispmv_add_sparse_csr",
     "hispmv_add_dense", "hispmv_add_sparse_coo_dev", "hispmv_add_sparse_csr_dev", "hispmv_add_dense_dev",
     "hispmv_commit", "hispmv_num_matrices", "hispmv_select", "hispmv_force_kernel", "hispmv_run",

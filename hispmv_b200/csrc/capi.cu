@@ -260,6 +260,9 @@ struct hispmv_ctx {
   int64_t cap_small = 0;            // floats in h_small / d_small
   std::map<SmallKey, SmallGraph> small_graphs;
   std::map<const void*, int> small_seen;   // eager runs before a matrix's calls are captured
+  // single-process multi-GPU (hispmv_create_multi): this context owns one child per GPU, child k holding row block k of
+  // every matrix; the parent holds no matrix of its own and only fans the host-buffer calls out
+  std::vector<hispmv_ctx*> kids;
 
   void drop_small_graphs() {
     for (auto& kv : small_graphs) {
@@ -456,6 +459,59 @@ int small_call(hispmv_ctx* c, Matrix* m, const float* x, const float* bias, floa
   HISPMV_CUDA(cudaStreamSynchronize(s));
   if (n_y > 0) memcpy(y, hy, (size_t)n_y * 4);
   return HISPMV_OK;
+}
+
+// ---- single-process multi-GPU --------------------------------------------------------------------------------------
+// fn(kid, k) on every child, one host thread per GPU (the calls block: copies inside); the first failure wins and its
+// error text is carried over to the calling thread
+template <class F>
+int for_each_kid(hispmv_ctx* c, F fn) {
+  const size_t n = c->kids.size();
+  std::vector<int> st(n, HISPMV_OK);
+  std::vector<std::string> err(n);
+  std::vector<std::thread> th;
+  for (size_t k = 1; k < n; ++k)
+    th.emplace_back([&, k] {
+      st[k] = fn(c->kids[k], (int)k);
+      if (st[k] < 0) err[k] = g_last_error;
+    });
+  st[0] = fn(c->kids[0], 0);
+  if (st[0] < 0) err[0] = g_last_error;
+  for (auto& t : th) t.join();
+  for (size_t k = 0; k < n; ++k)
+    if (st[k] < 0) {
+      g_last_error = err[k];
+      return st[k];
+    }
+  return st[0];
+}
+
+// add a matrix from HOST arrays to every child (each keeps its own row block); on any failure the children that had
+// taken it drop it again, so the handle indices stay aligned
+template <class F>
+int multi_add(hispmv_ctx* c, F add) {
+  const int r = for_each_kid(c, [&](hispmv_ctx* kid, int) { return add(kid); });
+  const size_t want = c->kids[0]->mats.size();
+  bool aligned = true;
+  for (auto* kid : c->kids) aligned = aligned && kid->mats.size() == want;
+  if (r < 0 || !aligned) {
+    size_t least = want;
+    for (auto* kid : c->kids) least = std::min(least, kid->mats.size());
+    for (auto* kid : c->kids)
+      while (kid->mats.size() > least) {
+        DeviceGuard g(kid->device);
+        delete kid->mats.back();
+        kid->mats.pop_back();
+      }
+    return r < 0 ? r : HISPMV_ERR_STATE;
+  }
+  return r;
+}
+
+int multi_refuse(const char* what) {
+  set_error(std::string(what) + ": not available on a multi-GPU handle (hispmv_create_multi); use hispmv_multi_child "
+            "for the per-GPU contexts");
+  return HISPMV_ERR_STATE;
 }
 
 // Build (or rebuild) the execution plan of a sparse matrix: histogram -> selector -> merge tiles.
@@ -750,6 +806,10 @@ int add_coo_common(hispmv_ctx* c, const int32_t* r, const int32_t* cc, const flo
     set_error("add_sparse_coo: bad arguments");
     return HISPMV_ERR_ARG;
   }
+  if (!c->kids.empty()) {
+    if (on_device) return multi_refuse("add_sparse_coo_dev");
+    return multi_add(c, [&](hispmv_ctx* kid) { return add_coo_common(kid, r, cc, v, nnz, rows, cols, false); });
+  }
   DeviceGuard g(c->device);
   int st = check_capacity(c, nnz * 8 + ((int64_t)rows + 1) * 4);
   if (st != HISPMV_OK) return st;
@@ -783,6 +843,10 @@ int add_csr_common(hispmv_ctx* c, const int32_t* row_ptr, const int32_t* col, co
   if (!c || rows < 0 || cols < 0 || !row_ptr) {
     set_error("add_sparse_csr: bad arguments");
     return HISPMV_ERR_ARG;
+  }
+  if (!c->kids.empty()) {
+    if (on_device) return multi_refuse("add_sparse_csr_dev");
+    return multi_add(c, [&](hispmv_ctx* kid) { return add_csr_common(kid, row_ptr, col, val, rows, cols, false); });
   }
   DeviceGuard g(c->device);
   const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -853,6 +917,10 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
     // the reference asserts dense_overlay in prepareDenseMtxForFPGA (common/src/spmv-helper.cpp:718)
     set_error("create_dense_handle needs dense_overlay=True");
     return HISPMV_ERR_STATE;
+  }
+  if (!c->kids.empty()) {
+    if (on_device) return multi_refuse("add_dense_dev");
+    return multi_add(c, [&](hispmv_ctx* kid) { return add_dense_common(kid, a, rows, cols, false); });
   }
   DeviceGuard g(c->device);
   Matrix* m = new Matrix();
@@ -1157,11 +1225,12 @@ Matrix* get_matrix(hispmv_ctx* c, int64_t idx) {
     set_error("null context");
     return nullptr;
   }
-  if (idx < 0 || idx >= (int64_t)c->mats.size()) {
+  const std::vector<Matrix*>& mats = c->kids.empty() ? c->mats : c->kids[0]->mats;  // multi-GPU: child 0's block
+  if (idx < 0 || idx >= (int64_t)mats.size()) {
     set_error("Matrix idx out of range");
     return nullptr;
   }
-  return c->mats[(size_t)idx];
+  return mats[(size_t)idx];
 }
 
 }  // namespace
@@ -1208,8 +1277,47 @@ int hispmv_create(hispmv_ctx** out, int device_id, int flags) {
   return HISPMV_OK;
 }
 
+int hispmv_create_multi(hispmv_ctx** out, int first_device, int n_gpus, int flags) {
+  if (!out) return HISPMV_ERR_ARG;
+  *out = nullptr;
+  if (n_gpus < 1) {
+    set_error("hispmv_create_multi: n_gpus must be at least 1");
+    return HISPMV_ERR_ARG;
+  }
+  hispmv_ctx* parent = nullptr;
+  int st = hispmv_create(&parent, first_device, flags);
+  if (st != HISPMV_OK) return st;
+  // HISPMV_MULTI_WRAP=1 (tests on a box with fewer GPUs): child k sits on device (first_device + k) mod device count
+  int n_dev = 1;
+  cudaGetDeviceCount(&n_dev);
+  const bool wrap = getenv("HISPMV_MULTI_WRAP") && atoi(getenv("HISPMV_MULTI_WRAP")) != 0 && n_dev > 0;
+  for (int k = 0; k < n_gpus && st == HISPMV_OK; ++k) {
+    hispmv_ctx* kid = nullptr;
+    st = hispmv_create(&kid, wrap ? (first_device + k) % n_dev : first_device + k, flags);
+    if (st == HISPMV_OK) {
+      parent->kids.push_back(kid);
+      st = hispmv_set_shard(kid, k, n_gpus);
+    }
+  }
+  if (st != HISPMV_OK) {
+    const std::string keep = g_last_error;
+    hispmv_destroy(parent);
+    g_last_error = keep;
+    return st;
+  }
+  *out = parent;
+  return HISPMV_OK;
+}
+
+int hispmv_multi_gpus(hispmv_ctx* c) { return c ? (int)c->kids.size() : HISPMV_ERR_ARG; }
+hispmv_ctx* hispmv_multi_child(hispmv_ctx* c, int k) {
+  return (c && k >= 0 && k < (int)c->kids.size()) ? c->kids[(size_t)k] : nullptr;
+}
+
 void hispmv_destroy(hispmv_ctx* c) {
   if (!c) return;
+  for (auto* kid : c->kids) hispmv_destroy(kid);
+  c->kids.clear();
   DeviceGuard g(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->stream2);
@@ -1245,6 +1353,7 @@ int hispmv_set_shard(hispmv_ctx* c, int part, int n_parts) {
     set_error("set_shard: need 0 <= part < n_parts");
     return HISPMV_ERR_ARG;
   }
+  if (!c->kids.empty()) return multi_refuse("set_shard");  // the children are the shards
   c->shard_part = part;
   c->shard_parts = n_parts;
   return HISPMV_OK;
@@ -1268,6 +1377,7 @@ int hispmv_shard_bounds(const int32_t* row_ptr, int32_t rows, int n_parts, int32
 int hispmv_set_memory_limit(hispmv_ctx* c, int64_t bytes) {
   if (!c || bytes < 0) return HISPMV_ERR_ARG;
   c->mem_limit = bytes;
+  for (auto* kid : c->kids) kid->mem_limit = bytes;  // per GPU
   return HISPMV_OK;
 }
 
@@ -1298,23 +1408,37 @@ int hispmv_commit(hispmv_ctx* c) {
   if (!c) return HISPMV_ERR_ARG;
   // Matrices are uploaded and planned when they are added (the GPU has no separate "sync BO" step), so
   // commit only fences outstanding work.  Idempotent; handles may still be added afterwards.
+  if (!c->kids.empty()) {
+    for (auto* kid : c->kids) {
+      const int st = hispmv_commit(kid);
+      if (st != HISPMV_OK) return st;
+    }
+    c->committed = true;
+    return HISPMV_OK;
+  }
   DeviceGuard g(c->device);
   HISPMV_CUDA(cudaStreamSynchronize(c->stream));
   c->committed = true;
   return HISPMV_OK;
 }
 
-int hispmv_num_matrices(hispmv_ctx* c) { return c ? (int)c->mats.size() : HISPMV_ERR_ARG; }
+int hispmv_num_matrices(hispmv_ctx* c) {
+  if (!c) return HISPMV_ERR_ARG;
+  return (int)(c->kids.empty() ? c->mats.size() : c->kids[0]->mats.size());
+}
 
 int hispmv_select(hispmv_ctx* c, uint32_t idx) {
   if (!get_matrix(c, idx)) return c ? HISPMV_ERR_INDEX : HISPMV_ERR_ARG;
   c->selected = (int)idx;
+  for (auto* kid : c->kids) kid->selected = (int)idx;
   return HISPMV_OK;
 }
 
 int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
+  if (!c->kids.empty())
+    return for_each_kid(c, [&](hispmv_ctx* kid, int) { return hispmv_force_kernel(kid, idx, kernel, lanes); });
   if (m->dense) {
     set_error("force_kernel: dense handles always use the GeMV kernel");
     return HISPMV_ERR_ARG;
@@ -1340,6 +1464,7 @@ int hispmv_force_kernel(hispmv_ctx* c, int idx, int kernel, int lanes) {
 
 int hispmv_run_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
                    void* stream) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_run_dev");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);
@@ -1348,6 +1473,7 @@ int hispmv_run_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias
 
 int hispmv_run_dev_phase(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, float alpha,
                          float beta, int phases, void* stream) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_run_dev_phase");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (phases < 1 || phases > 3) {
@@ -1362,6 +1488,7 @@ int hispmv_run_dev_phase(hispmv_ctx* c, int idx, const float* d_x, const float* 
 
 int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, int relu,
                       void* stream) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_linear_dev");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);
@@ -1370,6 +1497,7 @@ int hispmv_linear_dev(hispmv_ctx* c, int idx, const float* d_x, const float* d_b
 
 int hispmv_run_dev_mc(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* mc_y, float alpha,
                       float beta, int relu, void* stream) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_run_dev_mc");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (!mc_y) {
@@ -1382,6 +1510,7 @@ int hispmv_run_dev_mc(hispmv_ctx* c, int idx, const float* d_x, const float* d_b
 
 int hispmv_run_dev_batch(hispmv_ctx* c, int idx, const float* d_x, const float* d_bias, float* d_y, int64_t num_vecs,
                          float alpha, float beta, int relu, void* stream) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_run_dev_batch");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (num_vecs < 0 || (num_vecs > 0 && (!d_x || !d_y))) {
@@ -1396,6 +1525,10 @@ void* hispmv_stream(hispmv_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 int hispmv_sync(hispmv_ctx* c) {
   if (!c) return HISPMV_ERR_ARG;
+  for (auto* kid : c->kids) {
+    const int st = hispmv_sync(kid);
+    if (st != HISPMV_OK) return st;
+  }
   DeviceGuard g(c->device);
   HISPMV_CUDA(cudaStreamSynchronize(c->stream));
   HISPMV_CUDA(cudaStreamSynchronize(c->stream2));
@@ -1406,6 +1539,11 @@ int hispmv_sync(hispmv_ctx* c) {
 int hispmv_launches_per_run(hispmv_ctx* c, int idx) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
+  if (!c->kids.empty()) {  // per step: every GPU's launches
+    int total = 0;
+    for (auto* kid : c->kids) total += std::max(0, hispmv_launches_per_run(kid, idx));
+    return total;
+  }
   if (m->local_rows() <= 0) return 0;
   if (!m->dense && m->kernel == HISPMV_KERNEL_MERGE) return m->num_tiles > 1 ? 2 : 1;
   if (!m->slabs.empty()) return (int)m->slabs.size();
@@ -1427,6 +1565,16 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
   if ((!x_host && !d_x_ext) || !y || (beta != 0.0f && !bias)) {
     set_error("run: null vector");
     return HISPMV_ERR_ARG;
+  }
+  if (!c->kids.empty()) {
+    // every GPU takes the whole x and its own block of bias and y, concurrently; rows are independent, so the blocks
+    // of y are simply written side by side (the reference's handle is single-device, fpga_handle.cpp:55)
+    if (d_x_ext) return multi_refuse("run_xdev");
+    return for_each_kid(c, [&](hispmv_ctx* kid, int) {
+      const Matrix* km = kid->mats[(size_t)kid->selected];
+      return run_host_step(kid, x_host, nullptr, nullptr, bias ? bias + km->row_begin : nullptr, y + km->row_begin, alpha,
+                           beta);
+    });
   }
   Matrix* m = c->mats[(size_t)c->selected];
   DeviceGuard g(c->device);
@@ -1606,6 +1754,25 @@ int hispmv_linear(hispmv_ctx* c, int idx, const float* x, int64_t x_len, const f
     set_error("linear: matrix has no columns");
     return HISPMV_ERR_ARG;
   }
+  if (!c->kids.empty()) {
+    const int64_t nv = x_len / m->cols;
+    const int64_t rows = m->rows;
+    if (nv == 1)  // one vector: the blocks of y sit side by side
+      return for_each_kid(c, [&](hispmv_ctx* kid, int) {
+        const Matrix* km = kid->mats[(size_t)idx];
+        return hispmv_linear(kid, idx, x, x_len, bias + km->row_begin, y_out + km->row_begin);
+      });
+    return for_each_kid(c, [&](hispmv_ctx* kid, int) {  // several: [vector][block] per GPU, interleaved into [vector][row]
+      const Matrix* km = kid->mats[(size_t)idx];
+      const int64_t nl = km->local_rows();
+      std::vector<float> tmp((size_t)std::max<int64_t>(1, nv * nl));
+      const int st = hispmv_linear(kid, idx, x, x_len, bias + km->row_begin, tmp.data());
+      if (st != HISPMV_OK) return st;
+      for (int64_t v = 0; v < nv; ++v)
+        if (nl > 0) memcpy(y_out + v * rows + km->row_begin, tmp.data() + v * nl, (size_t)nl * 4);
+      return (int)HISPMV_OK;
+    });
+  }
   DeviceGuard g(c->device);
   const int64_t num_vecs = x_len / m->cols;  // reference: integer division, remainder ignored (fpga_handle.cpp:336)
   const int64_t n_y = m->local_rows();
@@ -1657,6 +1824,25 @@ int hispmv_matrix_info_get(hispmv_ctx* c, int idx, hispmv_matrix_info* out) {
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (!out) return HISPMV_ERR_ARG;
+  if (!c->kids.empty()) {  // child 0's plan facts, the whole matrix's extent and totals
+    int st = hispmv_matrix_info_get(c->kids[0], idx, out);
+    if (st != HISPMV_OK) return st;
+    out->row_begin = 0;
+    out->row_end = out->rows;
+    for (size_t k = 1; k < c->kids.size(); ++k) {
+      hispmv_matrix_info o;
+      st = hispmv_matrix_info_get(c->kids[k], idx, &o);
+      if (st != HISPMV_OK) return st;
+      out->nnz += o.nnz;
+      out->num_tiles += o.num_tiles;
+      out->num_split_rows += o.num_split_rows;
+      out->device_bytes += o.device_bytes;
+      out->empty_rows += o.empty_rows;
+      out->max_row_nnz = std::max(out->max_row_nnz, o.max_row_nnz);
+      for (int i = 0; i < HISPMV_HIST_BINS; ++i) out->hist[i] += o.hist[i];
+    }
+    return HISPMV_OK;
+  }
   memset(out, 0, sizeof(*out));
   out->rows = m->rows;
   out->cols = m->cols;
@@ -1697,6 +1883,7 @@ int hispmv_matrix_info_get(hispmv_ctx* c, int idx, hispmv_matrix_info* out) {
 }
 
 int hispmv_plan_csr(hispmv_ctx* c, int idx, int32_t* row_ptr, int32_t* col_idx, float* vals) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_csr");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (m->dense) {
@@ -1711,6 +1898,7 @@ int hispmv_plan_csr(hispmv_ctx* c, int idx, int32_t* row_ptr, int32_t* col_idx, 
 }
 
 int hispmv_plan_tiles(hispmv_ctx* c, int idx, int32_t* tile_row, int64_t* tile_nnz) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_tiles");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (!m->d_tile_row) {
@@ -1749,6 +1937,7 @@ int64_t hispmv_plan_slab_nnz(hispmv_ctx* c, int idx, int slab) {
 }
 
 int hispmv_plan_slab_csr(hispmv_ctx* c, int idx, int slab, int32_t* row_ptr, int32_t* col_idx, float* vals) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_slab_csr");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (slab < 0 || slab >= (int)m->slabs.size()) {
@@ -1764,6 +1953,7 @@ int hispmv_plan_slab_csr(hispmv_ctx* c, int idx, int slab, int32_t* row_ptr, int
 }
 
 int hispmv_plan_tile_chunks(hispmv_ctx* c, int idx, int32_t* chunk_out) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_tile_chunks");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if ((m->kernel != HISPMV_KERNEL_ADAPTIVE && m->kernel != HISPMV_KERNEL_ROWSTAGE &&
@@ -1778,6 +1968,7 @@ int hispmv_plan_tile_chunks(hispmv_ctx* c, int idx, int32_t* chunk_out) {
 }
 
 int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_blocked_info");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (!out8) return HISPMV_ERR_ARG;
@@ -1799,6 +1990,7 @@ int hispmv_plan_blocked_info(hispmv_ctx* c, int idx, int64_t* out8) {
 int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,
                         int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
                         int32_t* seg_start_off, int32_t* panel_chunk, int32_t* chunk_start_count, int32_t* work) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_blocked");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   if (m->dense || m->kernel != HISPMV_KERNEL_BLOCKED) {
@@ -1824,6 +2016,7 @@ int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, 
 }
 
 int hispmv_plan_split_rows(hispmv_ctx* c, int idx, int32_t* rows_out) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_split_rows");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
   DeviceGuard g(c->device);

@@ -6,6 +6,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -35,7 +36,12 @@ class FpgaHandle {
     int flags = 0;
     if (dense_overlay) flags |= HISPMV_FLAG_DENSE_OVERLAY;
     if (row_dist_net) flags |= HISPMV_FLAG_ROW_DIST_NET;
-    if (hispmv_create(&ctx_, device_id, flags) != HISPMV_OK) fail("FpgaHandle");
+    // HISPMV_GPUS=G in the environment: the same single handle over the GPUs device_id .. device_id + G - 1 (every
+    // matrix row-sharded, run_kernel / linear fan out); nothing else about the API changes
+    int gpus = 1;
+    if (const char* e = std::getenv("HISPMV_GPUS")) gpus = std::atoi(e);
+    const int st = gpus > 1 ? hispmv_create_multi(&ctx_, device_id, gpus, flags) : hispmv_create(&ctx_, device_id, flags);
+    if (st != HISPMV_OK) fail("FpgaHandle");
   }
   ~FpgaHandle() { hispmv_destroy(ctx_); }
   FpgaHandle(const FpgaHandle&) = delete;

@@ -45,10 +45,16 @@ class Engine:
     """One GPU, many matrices.  Mirrors FpgaHandle (pyhispmv/include/fpga_handle.h:9-74)."""
 
     def __init__(self, device_id: int = 0, dense_overlay: bool = True, row_dist_net: bool = True,
-                 shard: Optional[Sequence[int]] = None, memory_limit: int = 0):
+                 shard: Optional[Sequence[int]] = None, memory_limit: int = 0, n_gpus: int = 1):
+        """n_gpus > 1: one handle over the GPUs device_id .. device_id + n_gpus - 1 in this process
+        (hispmv_create_multi): the host-buffer calls shard every matrix by rows and run the blocks concurrently."""
         flags = (capi.FLAG_DENSE_OVERLAY if dense_overlay else 0) | (capi.FLAG_ROW_DIST_NET if row_dist_net else 0)
         ctx = C.c_void_p()
-        check(lib.hispmv_create(C.byref(ctx), device_id, flags), "hispmv_create")
+        if n_gpus > 1:
+            check(lib.hispmv_create_multi(C.byref(ctx), device_id, n_gpus, flags), "hispmv_create_multi")
+        else:
+            check(lib.hispmv_create(C.byref(ctx), device_id, flags), "hispmv_create")
+        self.n_gpus = max(1, n_gpus)
         self._ctx = ctx
         self.device_id = device_id
         if shard is not None:

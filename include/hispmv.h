@@ -114,6 +114,17 @@ int hispmv_version(void);   /* 200 = this ABI; +1 when built with the research k
 
 /* device_id: CUDA ordinal.  flags: HISPMV_FLAG_*.  Fails (no fallback) if the device is not sm_100. */
 int hispmv_create(hispmv_ctx** out, int device_id, int flags);
+/* One handle, n_gpus devices (first_device .. first_device + n_gpus - 1) in ONE process -- the single-handle model of
+ * the reference's FpgaHandle (pyhispmv/src/fpga_handle.cpp:40-154) over several GPUs: every matrix added from host
+ * arrays is cut into n_gpus nnz-balanced row blocks (the split points of hispmv_set_shard), one per GPU; hispmv_run /
+ * hispmv_linear send the whole x and each GPU's block of bias to its GPU, run the blocks concurrently (one host thread
+ * per GPU) and write the blocks of y side by side into the caller's vector.  The host-buffer surface (add_*, load_mtx,
+ * commit, select, run, linear, matrix_info, force_kernel, sync) works on such a handle; the device-pointer and plan
+ * calls answer HISPMV_ERR_STATE -- reach the per-GPU contexts with hispmv_multi_child.  The one-process-per-GPU model
+ * (hispmv_set_shard + a collective library outside this ABI) remains the one for device-resident pipelines. */
+int hispmv_create_multi(hispmv_ctx** out, int first_device, int n_gpus, int flags);
+int hispmv_multi_gpus(hispmv_ctx* ctx);                    /* 0 for a plain handle */
+hispmv_ctx* hispmv_multi_child(hispmv_ctx* ctx, int k);    /* owned by ctx; NULL when out of range */
 void hispmv_destroy(hispmv_ctx* ctx);
 
 /* Row-block sharding for one-process-per-GPU runs: after this call every matrix added keeps only part

@@ -591,12 +591,18 @@ def _mlp(seed=0, sizes=(512, 1024, 1024, 256)):
     return m
 
 
-def test_model_test_flow_through_plugin():
+@pytest.mark.parametrize("gpus", [1, 2])
+def test_model_test_flow_through_plugin(gpus, monkeypatch):
     """apps/model_test.py:53-90: replace_layers(cpu_model, fpga), one forward of a random input, compare with the
-    CPU model.  Tolerance as apps/general_test.py:106 (rtol 1e-3), plus the north-star bar per layer output."""
+    CPU model.  Tolerance as apps/general_test.py:106 (rtol 1e-3), plus the north-star bar per layer output.
+    gpus = 2: the same unchanged caller with HISPMV_GPUS=2 in the environment -- one FpgaHandle, every layer row-sharded
+    over two GPUs (over the one GPU twice, HISPMV_MULTI_WRAP, where the box has a single one)."""
     import torch
     import pyhispmv
     from hispmv_b200.layers import FpgaLayerManager
+    if gpus > 1:
+        monkeypatch.setenv("HISPMV_GPUS", str(gpus))
+        monkeypatch.setenv("HISPMV_MULTI_WRAP", "1")
     cpu_model = _mlp()
     fpga = pyhispmv.FpgaHandle("unused.xclbin", 0, 24, 1, 1, 2, 5, True, False, True)
     fpga_model = FpgaLayerManager().replace_layers(cpu_model, fpga)
@@ -610,6 +616,72 @@ def test_model_test_flow_through_plugin():
     xb = torch.randn((3, 512))
     with torch.no_grad():
         assert np.allclose(fpga_model(xb).numpy(), cpu_model(xb).numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_one_handle_over_several_gpus(monkeypatch, tmp_path):
+    """hispmv_create_multi: ONE handle in ONE process over several GPUs (the reference's single-handle model): matrices
+    are row-sharded at the oracle's nnz-balanced split points, run_kernel / linear fan out and write the blocks of y side
+    by side; results within the bar, handle indices aligned, -1 (memory full) rolls back on every GPU, device-pointer
+    calls refuse.  On a one-GPU box the children share the GPU (HISPMV_MULTI_WRAP)."""
+    import ctypes as C
+    import torch
+    from hispmv_b200 import Engine, capi
+    from hispmv_b200.capi import lib, HispmvError
+    monkeypatch.setenv("HISPMV_MULTI_WRAP", "1")
+    rng = np.random.default_rng(77)
+    e = Engine(0, n_gpus=3)
+    try:
+        assert lib.hispmv_multi_gpus(e._ctx) == 3
+        rows, cols = 30011, 20011
+        r, c, v = _matrix(rng, "powerlaw", rows, cols)
+        idx = e.create_sparse_handle(r, c, v, rows, cols)
+        a = rng.standard_normal((700, 1300)).astype(np.float32)
+        di = e.create_dense_handle(a.reshape(-1), 700, 1300)
+        assert (idx, di) == (0, 1) and e.num_matrices() == 2
+        rp, ci, vv = ol.coo_to_csr(rows, r, c, v)
+        info = e.matrix_info(idx)
+        assert (info["row_begin"], info["row_end"], info["nnz"]) == (0, rows, ci.size)
+        bounds = ol.shard_bounds(rp, 3)
+        for k in range(3):   # every child holds exactly the oracle's block
+            kid = lib.hispmv_multi_child(e._ctx, k)
+            ki = capi.MatrixInfo()
+            assert lib.hispmv_matrix_info_get(C.c_void_p(kid), idx, C.byref(ki)) == 0
+            assert (ki.row_begin, ki.row_end) == (int(bounds[k]), int(bounds[k + 1]))
+        e.load_matrices()
+        x = rng.standard_normal(cols).astype(np.float32)
+        b = rng.standard_normal(rows).astype(np.float32)
+        y = np.full(rows, np.nan, np.float32)
+        e.select_matrix(idx)
+        e.run_kernel(x, b, y, float(ALPHA), float(BETA))
+        y64, scale = ol.spmv_f64(rp, ci, vv, x, b, ALPHA, BETA)
+        assert ol.max_scaled_error(y, y64, scale)[0] <= TOL
+        X = rng.standard_normal((3, cols)).astype(np.float32)
+        Y = e.linear(idx, X.reshape(-1), b).reshape(3, rows)
+        for k in range(3):
+            y64, scale = ol.spmv_f64(rp, ci, vv, X[k], b, 1.0, 1.0)
+            assert ol.max_scaled_error(Y[k], y64, scale)[0] <= TOL
+        xd = rng.standard_normal(1300).astype(np.float32)
+        bd = rng.standard_normal(700).astype(np.float32)
+        yd = e.linear(di, xd, bd)
+        y64, scale = ol.gemv_f64(a, 700, 1300, xd, bd, 1.0, 1.0)
+        assert ol.max_scaled_error(yd, y64, scale)[0] <= TOL
+        e.force_kernel(idx, capi.KERNEL_MERGE)
+        y2 = np.zeros(rows, np.float32)
+        e.run_kernel(x, b, y2, float(ALPHA), float(BETA))
+        y64, scale = ol.spmv_f64(rp, ci, vv, x, b, ALPHA, BETA)
+        assert ol.max_scaled_error(y2, y64, scale)[0] <= TOL
+        # device-pointer calls belong to the per-GPU contexts
+        t = torch.zeros(cols, device="cuda")
+        with pytest.raises(HispmvError, match="multi-GPU handle"):
+            e.run_dev(idx, t, None, torch.zeros(rows, device="cuda"), 1.0, 0.0)
+        # memory full: -1, and no child keeps a half-added matrix
+        lib.hispmv_set_memory_limit(e._ctx, 1 << 20)
+        assert e.create_sparse_handle(r, c, v, rows, cols) == -1
+        assert e.num_matrices() == 2
+        for k in range(3):
+            assert lib.hispmv_num_matrices(C.c_void_p(lib.hispmv_multi_child(e._ctx, k))) == 2
+    finally:
+        e.close()
 
 
 @pytest.mark.parametrize("graph", [False, True])

@@ -1016,22 +1016,29 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   return HISPMV_OK;
 }
 
-// Selector input: how many (row, slab) runs the matrix has = the number of pieces before group boundaries split any --
-// one warp per row counts the slab changes along the row's (sorted) columns.
+// Selector input: how many (row, slab) runs the matrix has = the number of pieces before group boundaries split any.
+// runs = non-empty rows + slab changes between neighbouring entries - the changes that fall on a row start: two flat,
+// coalesced passes (one warp walking each row took 16 ms on C2, whose longest rows hold a million entries).
 namespace {
-__global__ void pb_runs_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ col, int32_t rows, int32_t W,
-                               unsigned long long* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  unsigned long long mine = 0;
-  for (int64_t r = warp; r < rows; r += nwarps) {
+__global__ void pb_runs_rows_kernel(const int32_t* __restrict__ rp, const int32_t* __restrict__ col, int32_t rows, int32_t W,
+                                    unsigned long long* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = 0;  // +1 for a non-empty row, -1 when the slab change at its first entry was counted by the entry pass
+  if (r < rows) {
     const int b = rp[r], e = rp[r + 1];
-    for (int j = b + lane; j < e; j += 32) mine += (j == b || col[j] / W != col[j - 1] / W) ? 1u : 0u;
+    if (e > b) v = 1 - ((b > 0 && col[b] / W != col[b - 1] / W) ? 1 : 0);
   }
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(kFullMask, mine, d);
-  if (lane == 0 && mine) atomicAdd(out, mine);
+  v = __reduce_add_sync(kFullMask, v);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(out, (unsigned long long)(long long)v);
+}
+__global__ void pb_runs_entries_kernel(const int32_t* __restrict__ col, int64_t nnz, int32_t W,
+                                       unsigned long long* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  unsigned int mine = 0;
+  for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; j < nnz; j += stride)
+    mine += col[j] / W != col[j - 1] / W ? 1u : 0u;
+  mine = __reduce_add_sync(kFullMask, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
 }
 }  // namespace
 
@@ -1043,8 +1050,15 @@ int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t
   int st;
   if ((st = b.alloc(sizeof(unsigned long long)))) return st;
   HISPMV_CUDA(cudaMemsetAsync(b.p, 0, sizeof(unsigned long long), stream));
-  const int grid = (int)std::min<int64_t>(blocks_for((int64_t)rows * 32, 256), 148 * 32);
-  pb_runs_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_col, rows, slab_cols, b.as<unsigned long long>());
+  int32_t nnz = 0;
+  HISPMV_CUDA(cudaMemcpyAsync(&nnz, d_row_ptr + rows, 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  pb_runs_rows_kernel<<<blocks_for(rows, 256), 256, 0, stream>>>(d_row_ptr, d_col, rows, slab_cols,
+                                                                 b.as<unsigned long long>());
+  if (nnz > 1) {
+    const int grid = (int)std::min<int64_t>(blocks_for(nnz, 256), 148 * 32);
+    pb_runs_entries_kernel<<<grid, 256, 0, stream>>>(d_col, nnz, slab_cols, b.as<unsigned long long>());
+  }
   HISPMV_CUDA(cudaGetLastError());
   unsigned long long h = 0;
   HISPMV_CUDA(cudaMemcpyAsync(&h, b.p, sizeof(h), cudaMemcpyDeviceToHost, stream));

@@ -80,6 +80,35 @@ def test_coo_to_csr_bit_exact(eng, rows, cols, nnz, dup):
     assert (info["kernel"], info["probe_near"], info["probe_cmp"]) == (k, near, cmp_)
 
 
+def test_csr_input_is_validated_and_unsorted_rows_are_resorted(eng):
+    """hispmv_add_sparse_csr: a row_ptr that is not monotone from 0 to nnz or a column outside [0, cols) is refused; rows
+    whose columns are out of order come out exactly as the COO path orders them (the reference's per-row sort)."""
+    from hispmv_b200.capi import HispmvError
+    rng = np.random.default_rng(3)
+    rows, cols = 500, 900
+    lens = rng.integers(0, 40, rows)
+    rp = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    r = np.repeat(np.arange(rows, dtype=np.int32), lens)
+    c = rng.integers(0, cols, r.size).astype(np.int32)          # unsorted inside every row, with duplicates
+    v = rng.standard_normal(r.size).astype(np.float32)
+    idx = eng.create_sparse_handle_csr(rp, c, v, rows, cols)
+    got = eng.plan_csr(idx)
+    want = ol.coo_to_csr(rows, r, c, v)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    _check_run(eng, idx, *want, rows, cols, rng)
+    bad_rp = rp.copy()
+    bad_rp[10], bad_rp[11] = bad_rp[11] + 5, bad_rp[10]
+    with pytest.raises(HispmvError, match="row_ptr"):
+        eng.create_sparse_handle_csr(bad_rp, c, v, rows, cols)
+    bad_c = c.copy()
+    bad_c[r.size // 2] = cols
+    with pytest.raises(HispmvError, match="column index"):
+        eng.create_sparse_handle_csr(rp, bad_c, v, rows, cols)
+    n_before = eng.num_matrices()
+    cs = want[1]                                               # sorted input is taken as it is
+    assert eng.create_sparse_handle_csr(want[0], cs, want[2], rows, cols) == n_before
+
+
 def test_coo_index_out_of_range_is_refused(eng):
     from hispmv_b200.capi import HispmvError
     with pytest.raises(HispmvError):

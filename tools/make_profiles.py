@@ -49,6 +49,8 @@ def full(rep, tag, rnd):
     rows = list(csv.reader(io.StringIO(raw)))
     h, units = rows[0], rows[1]
     traffic = {}
+    add = tag.endswith("+")        # "tag+": the report holds the launches of ONE step -- their traffic is added up
+    tag = tag.rstrip("+")
     with open(os.path.join(ROOT, "profiles", f"{rnd}_{tag}_ncu.txt"), "w") as f:
         f.write(f"# ncu --set full --clock-control none : {os.path.basename(rep)}\n")
         for vals in rows[2:]:
@@ -61,7 +63,8 @@ def full(rep, tag, rnd):
             def get(m):
                 i = h.index(m)
                 return float(vals[i].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
-            traffic[tag + "_dram_bytes_per_launch"] = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
+            traffic[tag + "_dram_bytes_per_launch"] = (traffic.get(tag + "_dram_bytes_per_launch", 0.0) if add else 0.0) + \
+                get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
             m = "l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum"
             if m in h:
                 traffic[tag + "_l1_miss_sectors_per_launch"] = float(vals[h.index(m)].replace(",", ""))

@@ -10,7 +10,12 @@ WANT = [
     'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
     'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum',
     'l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_miss.sum',
-    'lts__t_sectors_srcunit_tex_op_read.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+    'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors.sum', 'l1tex__m_xbar2l1tex_read_sectors_mem_lg_op_ld.sum',
+    'l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'lts__xbar2lts_cycles_active.avg.pct_of_peak_sustained_elapsed', 'lts__lts2xbar_cycles_active.avg.pct_of_peak_sustained_elapsed',
+    'lts__t_tag_requests.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.max.pct_of_peak_sustained_elapsed',
+    'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'lts__t_sectors_srcunit_tex_op_write.sum',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
     'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
     'launch__shared_mem_per_block_static', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_shared_mem',
     'launch__occupancy_limit_registers', 'launch__occupancy_limit_warps', 'launch__waves_per_multiprocessor',

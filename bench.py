@@ -74,6 +74,8 @@ def workload_name(spec, n_gpus):
     else:
         base = (f"C2 power-law CSR {spec.rows}x{spec.cols} fp32, row len ~ min(1M, 0.6912/u), cols ~ Zipf(0.8), "
                 f"seed {spec.seed}")
+        if spec.params[2] >> 8:
+            base += f", {spec.rows // (spec.params[2] >> 8)} stacked blocks with C2's row lengths (same nnz per block)"
     return base + (f", {n_gpus} nnz-balanced row blocks" if n_gpus > 1 else "")
 
 
@@ -149,7 +151,7 @@ def run_reference(args):
         sample_rows = max(1, full.rows // 10)
     else:
         base = wl.c2_powerlaw(args.scale)
-        full = wl.SynthSpec(base.name, base.kind, base.seed, base.rows * world, base.cols, base.params)
+        full = wl.c2_weak(world, args.scale)
         sample_rows = base.rows   # bounded sample: the first 10 M rows = exactly the N=1 matrix (rows are hash-generated)
     spec = wl.SynthSpec(full.name, full.kind, full.seed, sample_rows, full.cols, full.params)
     threads = os.cpu_count() or 1
@@ -590,6 +592,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     affinity = "not requested"
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         if not args.no_numa_bind:
             from hispmv_b200.sharded import bind_to_gpu_numa
@@ -601,8 +604,7 @@ def run_ours(args):
         spec = wl.c5_uniform(args.scale)
         scaling = "strong"
     else:                       # BASELINE configs[1] per GPU (weak scaling)
-        base = wl.c2_powerlaw(args.scale)
-        spec = wl.SynthSpec(base.name, base.kind, base.seed, base.rows * world, base.cols, base.params)
+        spec = wl.c2_weak(world, args.scale)   # N stacked blocks of C2's shape, 100.0 M nonzeros each
         scaling = "weak"
     main = run_sparse(args, ctx, spec, args.workload, args.steps, args.warmup, True, world == 1 and not args.no_cpu,
                       clocks_for=True)

@@ -34,7 +34,8 @@ struct SynthParams {
 __device__ __forceinline__ int32_t synth_row_len(const SynthParams& sp, int64_t r) {
   switch (sp.kind) {
     case HISPMV_SYNTH_POWERLAW: {
-      const uint64_t u = hash_row(sp.seed, r) >> 32;
+      const int64_t period = sp.p2 >> 8;   // > 0: the row-length sequence repeats (weak-scaling stacks of one shape)
+      const uint64_t u = hash_row(sp.seed, period > 0 ? r % period : r) >> 32;
       const uint64_t len = (uint64_t)sp.p0 / (u + 1);
       return (int32_t)(len < (uint64_t)sp.p1 ? len : (uint64_t)sp.p1);
     }
@@ -73,7 +74,7 @@ __device__ __forceinline__ void synth_entry(const SynthParams& sp, int64_t r, in
   const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
   const double q = __ddiv_rn(__dadd_rn((double)k, u), (double)len);
   double w = q;
-  const int gamma = sp.kind == HISPMV_SYNTH_POWERLAW ? (int)sp.p2 : 1;
+  const int gamma = sp.kind == HISPMV_SYNTH_POWERLAW ? (int)(sp.p2 & 0xFF) : 1;
   for (int g = 1; g < gamma; ++g) w = __dmul_rn(w, q);
   int64_t c = (int64_t)__dmul_rn(w, (double)sp.cols);
   if (c >= sp.cols) c = sp.cols - 1;
@@ -150,8 +151,8 @@ int make_params(int kind, uint64_t seed, int32_t rows, int32_t cols, const int64
       return HISPMV_ERR_ARG;
     }
   } else if (kind == HISPMV_SYNTH_POWERLAW) {
-    if (sp->p0 < 1 || sp->p1 < 0 || sp->p2 < 1 || sp->p2 > 16) {
-      set_error("synth: powerlaw needs K >= 1, clip >= 0, 1 <= gamma <= 16");
+    if (sp->p0 < 1 || sp->p1 < 0 || (sp->p2 & 0xFF) < 1 || (sp->p2 & 0xFF) > 16 || sp->p2 < 0) {
+      set_error("synth: powerlaw needs K >= 1, clip >= 0, 1 <= gamma <= 16 (params[2] = gamma | period << 8)");
       return HISPMV_ERR_ARG;
     }
   } else if (kind != HISPMV_SYNTH_UNIFORM) {

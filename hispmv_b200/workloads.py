@@ -42,6 +42,17 @@ def c2_powerlaw(scale: float = 1.0) -> SynthSpec:
     return SynthSpec("C2_powerlaw", SYNTH_POWERLAW, 1, n, n, (_K_C2, clip, 5))
 
 
+def c2_weak(world: int, scale: float = 1.0) -> SynthSpec:
+    """The weak-scaling workload at N GPUs: N stacked blocks of C2's shape.  Block k has C2's row-length sequence
+    (params[2] carries the period, include/hispmv_synth.h) and its own entries, so every block -- and with nnz-balanced
+    row blocks every GPU -- holds exactly C2's 100.0 M nonzeros.  world = 1 is C2 itself."""
+    base = c2_powerlaw(scale)
+    if world <= 1:
+        return base
+    k, clip, gamma = base.params
+    return SynthSpec(base.name, base.kind, base.seed, base.rows * world, base.cols, (k, clip, gamma | (base.rows << 8)))
+
+
 def c4_stencil(scale: float = 1.0) -> SynthSpec:
     """C4: 27-point stencil on a 272^3 grid (20.1M rows, ~540M nnz), banded / FEM-like."""
     g = max(4, int(round(272 * scale ** (1.0 / 3.0))))

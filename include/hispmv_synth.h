@@ -21,7 +21,8 @@ extern "C" {
 enum {
   /* row length = min(clip, K / (u32+1)) with u32 = hash(seed,row)>>32: P(len >= L) ~ (K/2^32)/L  (alpha = 2)
    * column     = floor(cols * q^gamma), q = (k + u)/len stratified  (gamma = 1 uniform, 5 ~ Zipf s = 0.8)
-   * params = { K, clip, gamma } */
+   * params = { K, clip, gamma | period << 8 }: period > 0 makes row r as long as row r % period (the entries still
+   * depend on r), so N stacked blocks of `period` rows hold the same number of nonzeros each (weak scaling) */
   HISPMV_SYNTH_POWERLAW = 1,
   /* row length = base + popcount(hash & mask), columns uniform stratified.  params = { base, mask } */
   HISPMV_SYNTH_UNIFORM = 2,

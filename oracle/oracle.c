@@ -690,7 +690,8 @@ enum { SYNTH_POWERLAW = 1, SYNTH_UNIFORM = 2, SYNTH_STENCIL27 = 3 };
 
 int oracle_synth_row_len(int kind, uint64_t seed, const int64_t* p, int64_t r) {
   if (kind == SYNTH_POWERLAW) {
-    const uint64_t u = hash_row(seed, r) >> 32;
+    const int64_t period = p[2] >> 8; /* > 0: the row-length sequence repeats every `period` rows */
+    const uint64_t u = hash_row(seed, period > 0 ? r % period : r) >> 32;
     const uint64_t len = (uint64_t)p[0] / (u + 1);
     return (int)(len < (uint64_t)p[1] ? len : (uint64_t)p[1]);
   }
@@ -728,7 +729,7 @@ void oracle_synth_entry(int kind, uint64_t seed, int cols, const int64_t* p, int
     const double u = (double)(h >> 11) * (1.0 / 9007199254740992.0);
     const double q = ((double)k + u) / (double)len;
     double w = q;
-    const int gamma = kind == SYNTH_POWERLAW ? (int)p[2] : 1;
+    const int gamma = kind == SYNTH_POWERLAW ? (int)(p[2] & 0xFF) : 1;
     int g;
     int64_t c;
     for (g = 1; g < gamma; ++g) w = w * q;

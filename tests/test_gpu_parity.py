@@ -520,10 +520,11 @@ def test_load_mtx_on_device(eng, tmp_path):
 # ---------------------------------------------------------------------------------------------------
 # synthetic generators: device output bit-exact against the CPU restatement
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("which", ["c2", "c4", "c5"])
+@pytest.mark.parametrize("which", ["c2", "c2_weak3", "c4", "c5"])
 def test_synth_generators_bit_exact(eng, which):
-    from hispmv_b200 import synth
-    spec = {"c2": synth.c2_powerlaw(0.002), "c4": synth.c4_stencil(0.0004), "c5": synth.c5_uniform(0.0002)}[which]
+    from hispmv_b200 import synth, workloads
+    spec = {"c2": synth.c2_powerlaw(0.002), "c2_weak3": workloads.c2_weak(3, 0.002), "c4": synth.c4_stencil(0.0004),
+            "c5": synth.c5_uniform(0.0002)}[which]
     d = synth.DeviceCSR(spec)
     idx = eng.create_sparse_handle_csr_dev(d.row_ptr, d.col, d.val, spec.rows, spec.cols)
     rp, ci, vv = eng.plan_csr(idx)
@@ -542,6 +543,11 @@ def test_synth_generators_bit_exact(eng, which):
     assert blk.nnz == rp2[b1] - rp2[b0]
     bounds, total = synth.synth_shard_bounds(spec, 4)
     assert total == ci2.size and np.array_equal(bounds, ol.shard_bounds(rp2, 4))
+    if which == "c2_weak3":   # three stacked blocks with the same row lengths: nnz-balanced thirds are the blocks
+        b3, _ = synth.synth_shard_bounds(spec, 3)
+        n = spec.rows // 3
+        assert np.array_equal(np.diff(rp2)[:n], np.diff(rp2)[n:2 * n]) and rp2[n] * 3 == ci2.size
+        assert b3[0] == 0 and b3[3] == spec.rows and rp2[b3[1]] == rp2[n] and rp2[b3[2]] == rp2[2 * n]
     d.close()
     blk.close()
 
@@ -789,10 +795,12 @@ def test_host_run_pipelines_row_ranges(eng):
 
 
 def test_small_calls_are_one_graph_launch_and_stay_exact(eng, monkeypatch):
-    """A DNN layer's vectors (tens of KB): from the second call on, run_kernel / linear replay one captured graph (H2D,
-    kernel, D2H).  Results are bit-identical to the eager sequence (HISPMV_SMALL_GRAPH=0 keeps every call eager: checked
-    in a second engine), for changing x / bias, two alpha-beta pairs and a re-planned matrix."""
+    """A DNN layer's vectors (tens of KB) go through one pinned block and one stream synchronisation; with
+    HISPMV_SMALL_GRAPH=1, from the second call on, run_kernel / linear replay one captured graph (H2D, kernel, D2H).
+    Results are bit-identical to the eager sequence (the default: checked in a second engine), for changing x / bias,
+    two alpha-beta pairs and a re-planned matrix."""
     from hispmv_b200 import Engine, capi
+    monkeypatch.setenv("HISPMV_SMALL_GRAPH", "1")
     rng = np.random.default_rng(31)
     rows, cols = 3000, 5000
     r, c, v = _matrix(rng, "powerlaw", rows, cols)
@@ -814,7 +822,7 @@ def test_small_calls_are_one_graph_launch_and_stay_exact(eng, monkeypatch):
         assert ol.max_scaled_error(yl, y64, scale)[0] <= TOL
         if k == 2:
             eng.force_kernel(idx, capi.KERNEL_MERGE)     # the captured launches of the old plan are dropped
-    monkeypatch.setenv("HISPMV_SMALL_GRAPH", "0")         # read once per process: only a fresh check of the values
+    monkeypatch.delenv("HISPMV_SMALL_GRAPH")              # the default: every call eager
     e2 = Engine(0)
     try:
         i2 = e2.create_sparse_handle(r, c, v, rows, cols)

@@ -83,6 +83,7 @@ def _load() -> C.CDLL:
         "hispmv_plan_tile_chunks": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_blocked_info": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_blocked": (C.c_int, [p, C.c_int, p, p, p, p, p, p, p, p, p, p, p, p]),
+        "hispmv_plan_blocked_stage": (C.c_int, [p, C.c_int, p, p, p, p, p]),
         "hispmv_plan_slab_nnz": (i64, [p, C.c_int, C.c_int]),
         "hispmv_plan_slab_csr": (C.c_int, [p, C.c_int, C.c_int, p, p, p]),
         "hispmv_load_mtx": (C.c_int, [p, C.c_char_p]),
@@ -111,7 +112,7 @@ EXPORTED = [
     "hispmv_add_dense", "hispmv_add_sparse_coo_dev", "hispmv_add_sparse_csr_dev", "hispmv_add_dense_dev",
     "hispmv_commit", "hispmv_num_matrices", "hispmv_select", "hispmv_force_kernel", "hispmv_run",
     "hispmv_linear", "hispmv_run_dev", "hispmv_run_dev_phase", "hispmv_linear_dev", "hispmv_sync", "hispmv_stream", "hispmv_launches_per_run",
-    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_plan_blocked_info", "hispmv_plan_blocked", "hispmv_plan_slab_nnz", "hispmv_plan_slab_csr", "hispmv_load_mtx", "hispmv_parse_mtx", "hispmv_parse_mtx_free", "hispmv_multicast_copy", "hispmv_run_xdev", "hispmv_run_dev_mc", "hispmv_run_dev_batch",
+    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_plan_blocked_info", "hispmv_plan_blocked", "hispmv_plan_blocked_stage", "hispmv_plan_slab_nnz", "hispmv_plan_slab_csr", "hispmv_load_mtx", "hispmv_parse_mtx", "hispmv_parse_mtx_free", "hispmv_multicast_copy", "hispmv_run_xdev", "hispmv_run_dev_mc", "hispmv_run_dev_batch",
     "hispmv_synth_count", "hispmv_synth_shard_bounds", "hispmv_synth_csr", "hispmv_synth_free",
 ]
 

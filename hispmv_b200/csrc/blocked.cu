@@ -276,6 +276,80 @@ __global__ void pb_max_segs_kernel(const int32_t* __restrict__ panel_seg, int64_
   if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
+// ---- the staged gather of pass 2 (round-2 v10): every (panel, slab) segment of a STREAM panel is fetched by ONE bulk copy
+// of the 16-byte-aligned range of part[] that covers it, into the panel's staging area in shared memory; perm2 holds the
+// panel-relative slot of every staged position (0xFFFF for the alignment padding), end_bits one bit per slot that ends a
+// row.  Segments of LONG panels are not staged (length 0).
+__global__ void pb_stage_len_kernel(const PbSeg* __restrict__ seg, const int32_t* __restrict__ len_sorted,
+                                    const uint64_t* __restrict__ key_sorted, const TileDesc* __restrict__ desc, int32_t S,
+                                    int64_t nseg, int32_t* __restrict__ alen) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nseg) return;
+  const int64_t t = (int64_t)(key_sorted[i] / (uint64_t)S);
+  const int32_t b = seg[i].start, e = b + len_sorted[i];
+  alen[i] = __ldg(&desc[t].chunk) >= 0 ? 0 : ((e + 3) & ~3) - (b & ~3);
+}
+
+__global__ void pb_bit_words_kernel(const TileDesc* __restrict__ desc, int64_t npan, int32_t* __restrict__ words) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= npan) return;
+  const TileDesc d = desc[t];
+  words[t] = d.chunk >= 0 ? 0 : (d.n1 - d.n0 + 31) >> 5;
+}
+
+__global__ void pb_panel_aux_kernel(const int32_t* __restrict__ panel_seg, const int32_t* __restrict__ gpos,
+                                    const int32_t* __restrict__ bbase, int64_t npan, int64_t nseg, int32_t pos_total,
+                                    int32_t bit_total, int2* __restrict__ aux) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > npan) return;
+  const int32_t sgi = t < npan ? panel_seg[t] : (int32_t)nseg;
+  aux[t] = make_int2(sgi < nseg ? gpos[sgi] : pos_total, t < npan ? bbase[t] : bit_total);
+}
+
+// one warp per segment: its copy descriptor and the slots of its staged positions
+__global__ void pb_seg_copy_kernel(const PbSeg* __restrict__ seg, const int32_t* __restrict__ len_sorted,
+                                   const uint64_t* __restrict__ key_sorted, const int32_t* __restrict__ alen,
+                                   const int32_t* __restrict__ gpos, const int2* __restrict__ aux,
+                                   const uint16_t* __restrict__ perm, int32_t S, int64_t nseg, int2* __restrict__ seg_copy,
+                                   uint16_t* __restrict__ perm2) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= nseg) return;
+  const int64_t t = (int64_t)(key_sorted[i] / (uint64_t)S);
+  const int32_t b = seg[i].start, e = b + len_sorted[i], a0 = b & ~3, al = alen[i], g = gpos[i];
+  if (lane == 0) seg_copy[i] = make_int2(a0, ((g - aux[t].x) >> 2) | ((al >> 2) << 16));
+  for (int32_t j = lane; j < al; j += 32) {
+    const int32_t q = a0 + j;
+    perm2[(int64_t)g + j] = (q >= b && q < e) ? perm[q] : (uint16_t)0xFFFF;
+  }
+}
+
+__global__ void pb_end_bits_kernel(const int32_t* __restrict__ prow_ptr, int32_t rows, const TileDesc* __restrict__ desc,
+                                   int64_t npan, const int2* __restrict__ aux, uint32_t* __restrict__ bits) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const int32_t b = prow_ptr[r], e = prow_ptr[r + 1];
+  if (e <= b) return;
+  const int32_t t = pb_panel_of(desc, npan, e - 1);  // the panel that holds the row's last piece
+  const TileDesc d = desc[t];
+  if (d.chunk >= 0) return;
+  const int32_t j = e - 1 - d.n0;
+  atomicOr(&bits[(int64_t)aux[t].y + (j >> 5)], 1u << (j & 31));
+}
+
+// shared-memory words pass 2 needs for its largest STREAM panel: skewed slots + staging area
+__global__ void pb_reduce_words_kernel(const TileDesc* __restrict__ desc, const int2* __restrict__ aux, int64_t npan,
+                                       int* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int v = 0;
+  if (t < npan && desc[t].chunk < 0) {
+    const int n = desc[t].n1 - desc[t].n0;
+    v = ((n + 31) >> 5) * 33 + 4 + (aux[t + 1].x - aux[t].x);
+  }
+  v = __reduce_max_sync(kFullMask, v);
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
 int grow(DevBuf& tmp, size_t& have, size_t want) {
   if (want <= have) return HISPMV_OK;
   have = want;
@@ -296,6 +370,10 @@ void pb_free(PbArrays* a) {
   cudaFree(a->d_seg);
   cudaFree(a->d_panel_chunk);
   cudaFree(a->d_chunk);
+  cudaFree(a->d_seg_copy);
+  cudaFree(a->d_perm2);
+  cudaFree(a->d_panel_aux);
+  cudaFree(a->d_end_bits);
   cudaFree(a->d_work);
   cudaFree(a->d_part[0]);
   cudaFree(a->d_part[1]);
@@ -436,7 +514,7 @@ int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float*
   return HISPMV_OK;
 }
 
-int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, cudaStream_t stream) {
+int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, int32_t rows, cudaStream_t stream) {
   const int64_t np = a->num_pieces;
   const int32_t S = a->num_slabs;
   const int B = 256;
@@ -526,6 +604,53 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
   HISPMV_CUDA(cudaStreamSynchronize(stream));
   a->num_seg = nseg;
   a->max_panel_segs = h_mx;
+  // the staged gather: aligned copy ranges, their places in each panel's staging area, perm2, end bits
+  {
+    DevBuf alen, gpos, bw, bbase, mw;
+    if ((st = alen.alloc((size_t)nseg * 4)) || (st = gpos.alloc((size_t)nseg * 4)) ||
+        (st = bw.alloc((size_t)num_panels * 4)) || (st = bbase.alloc((size_t)num_panels * 4)) || (st = mw.alloc(sizeof(int))))
+      return st;
+    pb_stage_len_kernel<<<blocks_for(nseg, B), B, 0, stream>>>(a->d_seg, len_sorted.as<int32_t>(), skeys.Current(), d_desc, S,
+                                                               nseg, alen.as<int32_t>());
+    pb_bit_words_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(d_desc, num_panels, bw.as<int32_t>());
+    HISPMV_CUDA(cudaGetLastError());
+    HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, alen.as<int32_t>(), gpos.as<int32_t>(), nseg, stream));
+    if ((st = grow(tmp, tb, need))) return st;
+    HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, alen.as<int32_t>(), gpos.as<int32_t>(), nseg, stream));
+    HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, need, bw.as<int32_t>(), bbase.as<int32_t>(), num_panels, stream));
+    if ((st = grow(tmp, tb, need))) return st;
+    HISPMV_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, need, bw.as<int32_t>(), bbase.as<int32_t>(), num_panels, stream));
+    int32_t h_t[4] = {0, 0, 0, 0};
+    HISPMV_CUDA(cudaMemcpyAsync(&h_t[0], alen.as<int32_t>() + (nseg - 1), 4, cudaMemcpyDeviceToHost, stream));
+    HISPMV_CUDA(cudaMemcpyAsync(&h_t[1], gpos.as<int32_t>() + (nseg - 1), 4, cudaMemcpyDeviceToHost, stream));
+    HISPMV_CUDA(cudaMemcpyAsync(&h_t[2], bw.as<int32_t>() + (num_panels - 1), 4, cudaMemcpyDeviceToHost, stream));
+    HISPMV_CUDA(cudaMemcpyAsync(&h_t[3], bbase.as<int32_t>() + (num_panels - 1), 4, cudaMemcpyDeviceToHost, stream));
+    HISPMV_CUDA(cudaStreamSynchronize(stream));
+    a->stage_total = (int64_t)h_t[0] + h_t[1];
+    a->bit_words = (int64_t)h_t[2] + h_t[3];
+    HISPMV_CUDA(cudaMalloc((void**)&a->d_seg_copy, ((size_t)nseg + 1) * sizeof(int2)));
+    HISPMV_CUDA(cudaMalloc((void**)&a->d_perm2, ((size_t)a->stage_total + 64) * 2));
+    HISPMV_CUDA(cudaMalloc((void**)&a->d_panel_aux, ((size_t)num_panels + 1) * sizeof(int2)));
+    HISPMV_CUDA(cudaMalloc((void**)&a->d_end_bits, ((size_t)a->bit_words + 4) * 4));
+    HISPMV_CUDA(cudaMemsetAsync(a->d_end_bits, 0, ((size_t)a->bit_words + 4) * 4, stream));
+    HISPMV_CUDA(cudaMemsetAsync(a->d_perm2 + a->stage_total, 0xFF, 64 * 2, stream));
+    HISPMV_CUDA(cudaMemsetAsync(mw.p, 0, sizeof(int), stream));
+    pb_panel_aux_kernel<<<blocks_for(num_panels + 1, B), B, 0, stream>>>(a->d_panel_seg, gpos.as<int32_t>(),
+                                                                        bbase.as<int32_t>(), num_panels, nseg,
+                                                                        (int32_t)a->stage_total, (int32_t)a->bit_words,
+                                                                        a->d_panel_aux);
+    pb_seg_copy_kernel<<<blocks_for(nseg * 32, B), B, 0, stream>>>(a->d_seg, len_sorted.as<int32_t>(), skeys.Current(),
+                                                                   alen.as<int32_t>(), gpos.as<int32_t>(), a->d_panel_aux,
+                                                                   a->d_perm, S, nseg, a->d_seg_copy, a->d_perm2);
+    pb_end_bits_kernel<<<blocks_for(rows, B), B, 0, stream>>>(a->d_prow_ptr, rows, d_desc, num_panels, a->d_panel_aux,
+                                                              a->d_end_bits);
+    pb_reduce_words_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(d_desc, a->d_panel_aux, num_panels, mw.as<int>());
+    HISPMV_CUDA(cudaGetLastError());
+    int h_mw = 0;
+    HISPMV_CUDA(cudaMemcpyAsync(&h_mw, mw.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    HISPMV_CUDA(cudaStreamSynchronize(stream));
+    a->reduce_words = h_mw;
+  }
   cudaFree(a->d_piece_pcsr);
   cudaFree(a->d_piece_slab);
   a->d_piece_pcsr = nullptr;
@@ -804,84 +929,61 @@ __device__ __forceinline__ uint32_t ldg_stream_u16(const uint16_t* p) {  // zero
 // the one-word skew per 32 slots keeps the 32 lanes of a warp on 32 different banks
 __device__ __forceinline__ uint32_t skew(uint32_t j) { return j + (j >> 5); }
 
+// 64-bit streaming load of four 16-bit places
+__device__ __forceinline__ uint2 ldg_stream_u2x32(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  // [skew(cap_words)] the panel's partials (skewed), then [cap_words / 32 + 2] end marks, then the row extents
+  // STREAM panel: [33 * nwords] the panel's partials in per-row order (skewed), then the staging area the bulk copies fill
   float* s_prod = reinterpret_cast<float*>(s_raw);
   const uint32_t sp = smem_u32(s_raw);
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
   __shared__ float s_wv[WARPS];
   __shared__ int s_wf[WARPS];
+  __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t = P.panel_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
-  const int ch0 = __ldg(P.panel_chunk + t);
-  const int nch = __ldg(P.panel_chunk + t + 1) - ch0;
   const int n = d.n1 - d.n0;
   const bool is_long = d.chunk >= 0;
   const int trows = d.r1 - d.r0;
-  const float* __restrict__ part_lane = P.part + lane;
-  const uint16_t* __restrict__ perm_lane = P.perm + lane;
-  const int2* __restrict__ g_chunk = P.chunk + ch0;
-  const int nwords = (n + 31) >> 5;
-  uint32_t* s_bits = reinterpret_cast<uint32_t*>(s_prod + skew((uint32_t)n) + 1);
-  int* s_rp = reinterpret_cast<int*>(s_bits + nwords + 1);
 
-  // ---- gather: warp w takes run w, w + WARPS, ...; U runs in flight, the next U descriptors already requested.  Idle
-  // lanes of a short run issue nothing (sending them to one dummy address made that L2 line a hot spot: C5's 5-piece
-  // runs ran 9x slower).
-  constexpr int U = 4;
-  int2 nxt[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int ci = warp + u * WARPS;
-    nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
-  }
-  float bias_pre[kBiasAhead];
-  if (!is_long) {
-    for (int i = tid; i <= nwords; i += THREADS) s_bits[i] = 0u;
-    if (tid < 32 && n + tid < 32 * nwords) s_prod[skew((uint32_t)(n + tid))] = 0.0f;  // the last word's unused slots
-    for (int i = tid; i <= trows; i += THREADS) s_rp[i] = __ldg(P.prow_ptr + d.r0 + i) - d.n0;
-#pragma unroll
-    for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
-      const int i = tid + a * THREADS;
-      bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
-    }
-  }
-  const uint64_t part_base = reinterpret_cast<uint64_t>(P.part + lane);
-  const uint64_t perm_base = reinterpret_cast<uint64_t>(P.perm + lane);
-  float acc = 0.0f;
-  for (int cb = warp; cb < nch; cb += WARPS * U) {
-    int2 cur[U];
+  if (is_long) {
+    // ---- a chunk of a LONG row: every piece goes into one sum.  Warp w takes run w, w + WARPS, ... of the chunk table,
+    // U runs in flight, the next U descriptors already requested.  Idle lanes of a short run issue nothing (sending
+    // them to one dummy address made that L2 line a hot spot).
+    const int ch0 = __ldg(P.panel_chunk + t);
+    const int nch = __ldg(P.panel_chunk + t + 1) - ch0;
+    const int2* __restrict__ g_chunk = P.chunk + ch0;
+    constexpr int U = 4;
+    int2 nxt[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      cur[u] = nxt[u];
-      const int ci = cb + (u + U) * WARPS;
+      const int ci = warp + u * WARPS;
       nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
     }
-    float p[U];
-    uint32_t q[U];
+    const uint64_t part_base = reinterpret_cast<uint64_t>(P.part + lane);
+    float acc = 0.0f;
+    for (int cb = warp; cb < nch; cb += WARPS * U) {
+      int2 cur[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      p[u] = 0.0f;
-      q[u] = 0;
-      if (lane < cur[u].y) {
-        p[u] = ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)(uint32_t)cur[u].x << 2)));
-        if (!is_long) q[u] = ldg_stream_u16(reinterpret_cast<const uint16_t*>(perm_base + ((uint64_t)(uint32_t)cur[u].x << 1)));
+      for (int u = 0; u < U; ++u) {
+        cur[u] = nxt[u];
+        const int ci = cb + (u + U) * WARPS;
+        nxt[u] = ci < nch ? __ldg(g_chunk + ci) : make_int2(0, 0);
       }
-    }
-    if (is_long) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) acc += p[u];
-    } else {
-#pragma unroll
-      for (int u = 0; u < U; ++u) sts_f32_if(sp + 4u * skew(q[u]), p[u], lane < cur[u].y);
+      for (int u = 0; u < U; ++u)
+        if (lane < cur[u].y)
+          acc += ldg_stream_f32(reinterpret_cast<const float*>(part_base + ((uint64_t)(uint32_t)cur[u].x << 2)));
     }
-  }
-  if (is_long) {
     acc = warp_sum(acc);
     if (lane == 0) s_red[warp] = acc;
     __syncthreads();
@@ -891,11 +993,86 @@ __global__ void __launch_bounds__(THREADS, 2)
     finish_chunk(P.carry, P.counter, d, t, total, lane, y, ep);
     return;
   }
-  __syncthreads();
-  for (int i = tid; i < trows; i += THREADS) {  // mark the slot that ends each non-empty row
-    const int e = s_rp[i + 1];
-    if (e > s_rp[i]) atomicOr(&s_bits[(e - 1) >> 5], 1u << ((e - 1) & 31));
+
+  // ---- STREAM panel.  Gather: the panel's pieces are one contiguous run of part[] per column slab; ONE bulk copy per
+  // run (its 16-byte-aligned cover, issued by as many threads as there are runs, all landing on one mbarrier) brings
+  // them into the staging area -- 16-25 G runs/s chip-wide against ~4 G/s for warps walking a run table
+  // (tools/bulk_small_bench.cu) -- and no thread waits on a global load in between.
+  const int nwords = (n + 31) >> 5;
+  const int sg0 = __ldg(P.panel_seg + t);
+  const int nsg = __ldg(P.panel_seg + t + 1) - sg0;
+  const int2 aux0 = __ldg(P.panel_aux + t), aux1 = __ldg(P.panel_aux + t + 1);
+  const int L = aux1.x - aux0.x;                       // staged positions (a multiple of 4)
+  const uint32_t stage = sp + 4u * (uint32_t)((nwords * 33 + 3) & ~3);
+  const uint32_t bar = smem_u32(&s_bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * (uint32_t)L) : "memory");
   }
+  __syncthreads();  // the barrier exists (and expects the bytes) before any copy can complete on it
+  for (int i = tid; i < nsg; i += THREADS) {
+    const int2 sc = __ldg(P.seg_copy + sg0 + i);
+    const uint32_t bytes = ((uint32_t)sc.y >> 16) << 4;
+    if (bytes)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       stage + (((uint32_t)sc.y & 0xFFFFu) << 4)),
+                   "l"(P.part + sc.x), "r"(bytes), "r"(bar)
+                   : "memory");
+  }
+  // while the copies fly: the places of my staged positions (positions 4 * (tid + a * THREADS) .. + 3), the end marks of
+  // my word of slots, bias and row extents for the epilogue
+  constexpr int A = 4;  // staged quads per thread held in registers; longer panels read the rest in the loop
+  uint2 places[A];
+  const uint16_t* perm2 = P.perm2 + aux0.x;
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    const int q4 = tid + a * THREADS;
+    places[a] = 4 * q4 < L ? ldg_stream_u2x32(perm2 + 4 * q4) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+  }
+  const uint32_t* __restrict__ g_bits = P.end_bits + aux0.y;
+  uint32_t my_bits = 0, prev_bits = 0x80000000u;
+  if (tid < nwords) {
+    my_bits = __ldg(g_bits + tid);
+    if (tid > 0) prev_bits = __ldg(g_bits + tid - 1);
+  }
+  float bias_pre[kBiasAhead];
+  int ext_b[kBiasAhead], ext_e[kBiasAhead];
+#pragma unroll
+  for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
+    const int i = tid + a * THREADS;
+    bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
+    ext_b[a] = i < trows ? __ldg(P.prow_ptr + d.r0 + i) : 0;
+    ext_e[a] = i < trows ? __ldg(P.prow_ptr + d.r0 + i + 1) : 0;
+  }
+  if (tid < 32 && n + tid < 32 * nwords) s_prod[skew((uint32_t)(n + tid))] = 0.0f;  // the last word's unused slots
+  if (tid == 0) {  // one thread polls; the CTA parks on the barrier below
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(bar), "r"(0u)
+          : "memory");
+    }
+  }
+  __syncthreads();
+  // scatter: staged position -> its slot in the panel's per-row order
+  auto drop4 = [&](int q4, uint2 pl) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stage + 16u * (uint32_t)q4) : "memory");
+    const uint32_t p0 = pl.x & 0xFFFFu, p1 = pl.x >> 16, p2 = pl.y & 0xFFFFu, p3 = pl.y >> 16;
+    sts_f32_if(sp + 4u * skew(p0), v.x, p0 != 0xFFFFu);
+    sts_f32_if(sp + 4u * skew(p1), v.y, p1 != 0xFFFFu);
+    sts_f32_if(sp + 4u * skew(p2), v.z, p2 != 0xFFFFu);
+    sts_f32_if(sp + 4u * skew(p3), v.w, p3 != 0xFFFFu);
+  };
+#pragma unroll
+  for (int a = 0; a < A; ++a) {
+    const int q4 = tid + a * THREADS;
+    if (4 * q4 < L) drop4(q4, places[a]);
+  }
+  for (int q4 = tid + A * THREADS; 4 * q4 < L; q4 += THREADS) drop4(q4, ldg_stream_u2x32(perm2 + 4 * q4));
   __syncthreads();
 
   // ---- reduce: thread w sums the 32 slots of word w of the per-row order, closing rows at the marks ----------------
@@ -904,8 +1081,8 @@ __global__ void __launch_bounds__(THREADS, 2)
   float lead = 0.0f;       // my share of a row that began in an earlier word and ends in mine ...
   int lead_slot = -1;      // ... at this (skewed) slot
   for (int w = tid; w < nwords; w += THREADS) {   // one trip unless the panel has more than 32 * THREADS slots
-    const uint32_t bits = s_bits[w];
-    bool pending = w > 0 && !(s_bits[w - 1] >> 31);   // the row my first slot belongs to began before this word
+    const uint32_t bits = w == tid ? my_bits : __ldg(g_bits + w);
+    bool pending = w > 0 && !((w == tid ? prev_bits : __ldg(g_bits + w - 1)) >> 31);   // my first slot's row began before this word
     const uint32_t base = sp + 4u * (33u * (uint32_t)w);
     float run = 0.0f;
 #pragma unroll
@@ -962,9 +1139,8 @@ __global__ void __launch_bounds__(THREADS, 2)
   __syncthreads();
 
   // ---- epilogue: one thread per row, coalesced ------------------------------------------------------------------
-  auto finish_row = [&](int i, float bias) {
-    const int b = s_rp[i], e = s_rp[i + 1];
-    const float sum = e > b ? s_prod[skew((uint32_t)(e - 1))] : 0.0f;
+  auto finish_row = [&](int i, float bias, int b, int e) {
+    const float sum = e > b ? s_prod[skew((uint32_t)(e - 1 - d.n0))] : 0.0f;
     float v = ep.alpha * sum;
     if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
     if (ep.relu) v = fmaxf(v, 0.0f);
@@ -973,10 +1149,10 @@ __global__ void __launch_bounds__(THREADS, 2)
 #pragma unroll
   for (int a = 0; a < kBiasAhead; ++a) {
     const int i = tid + a * THREADS;
-    if (i < trows) finish_row(i, bias_pre[a]);
+    if (i < trows) finish_row(i, bias_pre[a], ext_b[a], ext_e[a]);
   }
   for (int i = tid + kBiasAhead * THREADS; i < trows; i += THREADS)
-    finish_row(i, ep.beta != 0.0f ? ep.bias[d.r0 + i] : 0.0f);
+    finish_row(i, ep.beta != 0.0f ? ep.bias[d.r0 + i] : 0.0f, __ldg(P.prow_ptr + d.r0 + i), __ldg(P.prow_ptr + d.r0 + i + 1));
 }
 
 }  // namespace
@@ -999,8 +1175,8 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   (void)A;
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
-  // partials skewed by one word per 32, end marks, row extents: (n + n/32) + (n/32 + 2) + (rows + 1) words, n + rows <= cap
-  const size_t smem = ((size_t)P.cap_words + 2 * ((size_t)P.cap_words / 32) + 16) * 4;
+  // the largest STREAM panel: slots skewed by one word per 32, then the staging area (pb_reduce_words_kernel)
+  const size_t smem = ((size_t)P.reduce_words + 8) * 4;
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;

@@ -106,7 +106,7 @@ struct Matrix {
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
     if (pb.d_val)  // val + lcol + flags per entry; perm + one partial per stream lane in use per piece; tables
       b += pb.padded_nnz * 6 + pb.padded_nnz / 8 + pb.padded_nnz / kPbGroup * 4 + pb.num_pieces * (2 + 4 * (pb.d_part[1] ? 2 : 1)) +
-           pb.num_seg * 8 + pb.num_chunks * 8 + (num_tiles + 1) * 8 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
+           pb.num_seg * 16 + pb.num_chunks * 8 + pb.stage_total * 2 + pb.bit_words * 4 + (num_tiles + 1) * 8 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
     for (auto* sm : slabs) b += sm->device_bytes();
     return b;
   }
@@ -631,7 +631,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
       HISPMV_CUDA(fill_u32_device(reinterpret_cast<uint32_t*>(m->d_carry), kCarryEmptyBits, n, c->stream));
       HISPMV_CUDA(cudaMalloc((void**)&m->d_counter, (n + 8) * sizeof(unsigned int)));
       HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, (n + 8) * sizeof(unsigned int), c->stream));
-      st = pb_segments_device(&m->pb, m->d_desc, m->num_tiles, c->stream);
+      st = pb_segments_device(&m->pb, m->d_desc, m->num_tiles, m->local_rows(), c->stream);
       if (st != HISPMV_OK) return st;
       st = pb_make_work(&m->pb, c->sm_count, m->pb_slab_cost, c->stream);
       if (st != HISPMV_OK) return st;
@@ -1083,6 +1083,11 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.max_panel_segs = m->pb.max_panel_segs;
       P.panel_chunk = m->pb.d_panel_chunk;
       P.chunk = m->pb.d_chunk;
+      P.seg_copy = m->pb.d_seg_copy;
+      P.perm2 = m->pb.d_perm2;
+      P.panel_aux = m->pb.d_panel_aux;
+      P.end_bits = m->pb.d_end_bits;
+      P.reduce_words = m->pb.reduce_words;
       P.work = m->pb.d_work;
       P.num_work = m->pb.num_work;
       P.cap_words = (m->tile_items + m->long_threshold + 8 + 1) & ~1;  // even: the segment table behind it is 8-byte aligned
@@ -2016,6 +2021,31 @@ int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, 
   if (panel_chunk) HISPMV_CUDA(cudaMemcpy(panel_chunk, a.d_panel_chunk, ((size_t)m->num_tiles + 1) * 4, k));
   if (chunk_start_count) HISPMV_CUDA(cudaMemcpy(chunk_start_count, a.d_chunk, (size_t)a.num_chunks * 8, k));
   if (work) HISPMV_CUDA(cudaMemcpy(work, a.d_work, (size_t)a.num_work * 8, k));
+  return HISPMV_OK;
+}
+
+int hispmv_plan_blocked_stage(hispmv_ctx* c, int idx, int64_t* out4, int32_t* seg_copy, uint16_t* perm2,
+                              int32_t* panel_aux, uint32_t* end_bits) {
+  if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_blocked_stage");
+  Matrix* m = get_matrix(c, idx);
+  if (!m) return HISPMV_ERR_INDEX;
+  if (m->dense || m->kernel != HISPMV_KERNEL_BLOCKED) {
+    set_error("plan_blocked: matrix is not planned for the blocked strategy");
+    return HISPMV_ERR_STATE;
+  }
+  DeviceGuard g(c->device);
+  const PbArrays& a = m->pb;
+  const cudaMemcpyKind k = cudaMemcpyDeviceToHost;
+  if (out4) {
+    out4[0] = a.stage_total;
+    out4[1] = a.bit_words;
+    out4[2] = a.reduce_words;
+    out4[3] = a.num_seg;
+  }
+  if (seg_copy) HISPMV_CUDA(cudaMemcpy(seg_copy, a.d_seg_copy, (size_t)a.num_seg * 8, k));
+  if (perm2) HISPMV_CUDA(cudaMemcpy(perm2, a.d_perm2, (size_t)a.stage_total * 2, k));
+  if (panel_aux) HISPMV_CUDA(cudaMemcpy(panel_aux, a.d_panel_aux, ((size_t)m->num_tiles + 1) * 8, k));
+  if (end_bits) HISPMV_CUDA(cudaMemcpy(end_bits, a.d_end_bits, (size_t)a.bit_words * 4, k));
   return HISPMV_OK;
 }
 

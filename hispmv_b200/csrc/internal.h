@@ -224,6 +224,12 @@ struct PbPlan {
   int32_t max_panel_segs = 0;         // the most runs (chunk[] entries) any panel has: sizes pass 2's shared-memory copy
   const int32_t* panel_chunk = nullptr;  // num_panels+1 offsets into chunk[]
   const int2* chunk = nullptr;           // the segments cut into runs of at most kPbChunk pieces: (first piece id, count)
+  // the staged gather of pass 2 (STREAM panels): one bulk copy per segment into the panel's staging area
+  const int2* seg_copy = nullptr;      // per segment: {first piece of the aligned range, staging offset/4 | length/4 << 16}
+  const uint16_t* perm2 = nullptr;     // per staged position (panel-major): slot in the panel, 0xFFFF = alignment padding
+  const int2* panel_aux = nullptr;     // num_panels+1: {first staged position, first word of end_bits}
+  const uint32_t* end_bits = nullptr;  // per STREAM panel, one bit per slot: this slot ends a row
+  int32_t reduce_words = 0;            // shared-memory words of the largest STREAM panel (skewed slots + staging)
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
   int32_t num_work = 0;
   int32_t cap_words = 0;               // shared-memory words a STREAM panel needs (partials + row extents)
@@ -251,6 +257,12 @@ struct PbArrays {
   int32_t* d_panel_chunk = nullptr;
   int2* d_chunk = nullptr;
   int64_t num_chunks = 0;
+  int2* d_seg_copy = nullptr;
+  uint16_t* d_perm2 = nullptr;
+  int2* d_panel_aux = nullptr;
+  uint32_t* d_end_bits = nullptr;
+  int64_t stage_total = 0, bit_words = 0;
+  int32_t reduce_words = 0;
   int2* d_work = nullptr;
   int32_t num_work = 0;
   float* d_part[2] = {nullptr, nullptr};  // one per stream lane, the second allocated on first use
@@ -264,7 +276,7 @@ void pb_free(PbArrays* a);
 // (oracle_pb_order, oracle_pb_segments).
 int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
                     int64_t nnz, int32_t slab_cols, PbArrays* out, cudaStream_t stream);
-int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, cudaStream_t stream);
+int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, int32_t rows, cudaStream_t stream);
 // pass-1 work ranges for `n_cta` resident CTAs: contiguous, balanced by entries + slab_cost per slab (re)load
 int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream);
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);

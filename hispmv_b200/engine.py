@@ -256,6 +256,9 @@ class Engine:
         check(lib.hispmv_plan_blocked_info(self._ctx, matrix_idx, _ptr(o)), "plan_blocked_info")
         d = {"slab_cols": int(o[0]), "num_slabs": int(o[1]), "padded_nnz": int(o[2]), "num_seg": int(o[3]),
              "num_chunks": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "num_pieces": int(o[7])}
+        o4 = np.zeros(4, np.int64)
+        check(lib.hispmv_plan_blocked_stage(self._ctx, matrix_idx, _ptr(o4), None, None, None, None), "plan_blocked_stage")
+        d["stage_total"], d["bit_words"], d["reduce_words"] = int(o4[0]), int(o4[1]), int(o4[2])
         if arrays:
             n_y = self._shape(matrix_idx)[1]
             d["slab_ptr"] = np.empty(d["num_slabs"] + 1, np.int32)
@@ -274,6 +277,12 @@ class Engine:
                                           _ptr(d["flags"]), _ptr(d["group_base"]), _ptr(d["prow_ptr"]), _ptr(d["perm"]),
                                           _ptr(d["panel_seg"]), _ptr(d["seg"]), _ptr(d["panel_chunk"]), _ptr(d["chunk"]),
                                           _ptr(d["work"])), "plan_blocked")
+            d["seg_copy"] = np.empty((d["num_seg"], 2), np.int32)
+            d["perm2"] = np.empty(d["stage_total"], np.uint16)
+            d["panel_aux"] = np.empty((d["num_panels"] + 1, 2), np.int32)
+            d["end_bits"] = np.empty(d["bit_words"], np.uint32)
+            check(lib.hispmv_plan_blocked_stage(self._ctx, matrix_idx, None, _ptr(d["seg_copy"]), _ptr(d["perm2"]),
+                                                _ptr(d["panel_aux"]), _ptr(d["end_bits"])), "plan_blocked_stage")
         return d
 
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:

@@ -326,6 +326,38 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
     d["panel_chunk"] = panel_chunk
     d["chunk"] = np.asarray(chunks, np.int32).reshape(-1, 2)
     d["num_chunks"] = len(chunks)
+    # how pass 2 stages a STREAM panel (blocked.cu: pb_stage_len_kernel .. pb_end_bits_kernel): per segment one copy of
+    # the 4-piece-aligned range of partial sums that covers it; perm2 = the slot of every staged position (0xFFFF = padding)
+    seg_copy = np.zeros((nseg, 2), np.int32)
+    panel_aux = np.zeros((npan + 1, 2), np.int32)
+    perm2, bits = [], []
+    for p_ in range(npan):
+        panel_aux[p_] = (len(perm2), len(bits))
+        if tc[p_] >= 0:
+            continue                                   # LONG panel: nothing staged, no end marks
+        segs = d["seg"][panel_seg[p_]:panel_seg[p_ + 1]]
+        npc_p = int(n1[p_] - n0[p_])
+        offs = list(segs[:, 1]) + [npc_p]
+        base = len(perm2)
+        for i_, (st, off) in enumerate(segs):
+            ln = offs[i_ + 1] - off
+            a0, a1 = st & ~3, (st + ln + 3) & ~3
+            seg_copy[panel_seg[p_] + i_] = (a0, ((len(perm2) - base) >> 2) | (((a1 - a0) >> 2) << 16))
+            perm2 += [int(perm[q]) if st <= q < st + ln else 0xFFFF for q in range(a0, a1)]
+        w = np.zeros((npc_p + 31) // 32, np.uint32)
+        for r_ in range(tr[p_], tr[p_ + 1]):
+            if prow_ptr[r_ + 1] > prow_ptr[r_]:
+                j = int(prow_ptr[r_ + 1] - 1 - n0[p_])
+                w[j >> 5] |= np.uint32(1 << (j & 31))
+        bits += list(w)
+    panel_aux[npan] = (len(perm2), len(bits))
+    for p_ in range(npan):                             # LONG segments: the aligned start, no length
+        if tc[p_] >= 0:
+            for i_ in range(panel_seg[p_], panel_seg[p_ + 1]):
+                seg_copy[i_] = (d["seg"][i_, 0] & ~3, 0)
+    d["seg_copy"], d["perm2"] = seg_copy, np.asarray(perm2, np.uint16)
+    d["panel_aux"], d["end_bits"] = panel_aux, np.asarray(bits, np.uint32)
+    d["stage_total"], d["bit_words"] = len(perm2), len(bits)
     if n_cta:
         work = np.zeros((n_cta, 2), np.int32)
         o.oracle_pb_work(S, slab_ptr, align, n_cta, slab_cost, work.reshape(-1))

@@ -67,9 +67,33 @@ def _walk_plan(d, rows, CH, W, cols, x):
         assert not np.isnan(buf).any()           # every piece slot of the panel is filled exactly once
         if tc[p] >= 0:
             y[tr[p]] += buf.sum()
-        else:
-            for rr in range(tr[p], tr[p + 1]):
-                y[rr] = buf[pr[rr] - n0:pr[rr + 1] - n0].sum()
+            assert np.all(d["seg_copy"][d["panel_seg"][p]:d["panel_seg"][p + 1], 1] == 0)
+            continue
+        # the way the kernel does it: one copy per segment of the aligned range that covers it into the staging area,
+        # every staged position dropped at its slot (perm2), rows closed at the end marks
+        pos0, bit0 = d["panel_aux"][p]
+        pos1, bit1 = d["panel_aux"][p + 1]
+        stage = np.full(pos1 - pos0, np.nan)
+        padded = np.concatenate([part, np.full(8, np.nan)])      # the copies may read past the last piece
+        for a0, packed in d["seg_copy"][d["panel_seg"][p]:d["panel_seg"][p + 1]]:
+            so, ln = 4 * (packed & 0xFFFF), 4 * ((packed >> 16) & 0xFFFF)
+            assert a0 % 4 == 0 and ln > 0
+            stage[so:so + ln] = padded[a0:a0 + ln]
+        slots = np.full(n, np.nan)
+        pl = d["perm2"][pos0:pos1]
+        keep = pl != 0xFFFF
+        assert keep.sum() == n and len(set(pl[keep])) == n
+        slots[pl[keep]] = stage[keep]
+        assert np.array_equal(slots, buf)
+        words = d["end_bits"][bit0:bit1]
+        assert words.size == (n + 31) // 32
+        ends = np.unpackbits(words.view(np.uint8), bitorder="little")[:n].astype(bool) if n else np.zeros(0, bool)
+        want_ends = np.zeros(n, bool)
+        for rr in range(tr[p], tr[p + 1]):
+            y[rr] = buf[pr[rr] - n0:pr[rr + 1] - n0].sum()
+            if pr[rr + 1] > pr[rr]:
+                want_ends[pr[rr + 1] - 1 - n0] = True
+        assert np.array_equal(ends, want_ends)
     return y
 
 
@@ -155,8 +179,10 @@ def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     want = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=got["num_work"], slab_cost=cost)
     for k in ("slab_cols", "num_slabs", "padded_nnz", "num_pieces", "num_seg", "num_panels", "num_chunks"):
         assert got[k] == want[k], k
+    for k in ("stage_total", "bit_words"):
+        assert got[k] == want[k], k
     for k in ("slab_ptr", "lcol", "flags", "group_base", "prow_ptr", "perm", "panel_seg", "seg", "panel_chunk", "chunk",
-              "work"):
+              "seg_copy", "perm2", "panel_aux", "end_bits", "work"):
         assert np.array_equal(got[k], want[k]), k
     assert np.array_equal(got["val"].view(np.uint32), want["val"].view(np.uint32))
     tr, tn = eng.plan_tiles(idx)        # the panels: adaptive tiles over the per-row piece counts

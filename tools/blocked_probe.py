@@ -121,7 +121,7 @@ def main():
             res.append(row)
             print(f"{wl:8s} {name:9s} {str(p):34s} {info['kernel_name']:9s} med={med:8.4f} ms (warm L2 {warm:8.4f}) "
                   f"{gbs:7.0f} GB/s frac={gbs/peak:5.3f} err={err:.1e} plan={t_plan:5.1f}s p1={ph[0]:.3f} p2={ph[1]:.3f} "
-                  f"{'' if not extra else 'pieces=%d segs=%d chunks=%d' % (extra['num_pieces'], extra['num_seg'], extra['num_chunks'])}",
+                  f"{'' if not extra else 'pieces=%d segs=%d chunks=%d staged=%d smem=%dK' % (extra['num_pieces'], extra['num_seg'], extra['num_chunks'], extra['stage_total'], extra['reduce_words'] * 4 // 1024)}",
                   flush=True)
             json.dump(res, open(args.out, "w"), indent=1)
         eng.close()

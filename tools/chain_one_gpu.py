@@ -69,10 +69,28 @@ def main():
         with torch.no_grad():
             yp = fmodel(x.view(1, -1)).numpy().reshape(-1)
             assert np.abs(yp - ref).max() <= 1e-4 * np.abs(ref).max()
-            t0 = time.perf_counter()
-            for _ in range(50):
+            for _ in range(20):
                 fmodel(x.view(1, -1))
-            out["plugin path (host buffers per layer)"] = (time.perf_counter() - t0) / 50 * 1e6
+            t0 = time.perf_counter()
+            for _ in range(200):
+                fmodel(x.view(1, -1))
+            out["plugin path (host buffers per layer)"] = (time.perf_counter() - t0) / 200 * 1e6
+            # where it goes: the three fpga.linear calls on their own (numpy in, numpy out), the rest is torch glue
+            from hispmv_b200.layers import FpgaLinear
+            total = 0.0
+            for name, mod in fmodel.named_modules():
+                if isinstance(mod, FpgaLinear):
+                    cols = {"dense": 4096, "sparse1": 8192, "sparse2": 8192}.get(name.split(".")[-1], 4096)
+                    xin = np.random.default_rng(1).standard_normal(cols).astype(np.float32)
+                    for _ in range(20):
+                        fpga.linear(mod.matrix_idx, xin, mod.bias_npy)
+                    t0 = time.perf_counter()
+                    for _ in range(300):
+                        fpga.linear(mod.matrix_idx, xin, mod.bias_npy)
+                    us = (time.perf_counter() - t0) / 300 * 1e6
+                    total += us
+                    out[f"  fpga.linear alone: {name}"] = us
+            out["  three fpga.linear calls"] = total
     flops = 2 * (8192 * 4096 + int(model.sparse1.weight._nnz()) + int(model.sparse2.weight._nnz()))
     print(f"chain_one_gpu: CPU model (torch, {torch.get_num_threads()} threads) {cpu_us:.0f} us per pass")
     for name, us in out.items():

@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 //            row's total waits in its last slot and a final row-per-thread pass applies alpha / beta / ReLU with
 //            coalesced bias loads and y stores
 constexpr int kReduceThreads = 512;
-constexpr int kBiasAhead = 4;  // bias values per thread requested before the gather (rows tid, tid + THREADS, ...)
+constexpr int kRowsAhead = 6;  // rows per thread (of 512) whose bias and extent are requested before the gather
 
 // shared-memory accesses by 32-bit shared address (the compiler otherwise re-derives the dynamic window's base from the
 // generic pointer around every predicated store: four extra instructions per access in the first versions)
@@ -937,7 +937,7 @@ __device__ __forceinline__ uint2 ldg_stream_u2x32(const void* p) {
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   // STREAM panel: [33 * nwords] the panel's partials in per-row order (skewed), then the staging area the bulk copies fill
@@ -1022,7 +1022,7 @@ __global__ void __launch_bounds__(THREADS, 2)
   }
   // while the copies fly: the places of my staged positions (positions 4 * (tid + a * THREADS) .. + 3), the end marks of
   // my word of slots, bias and row extents for the epilogue
-  constexpr int A = 4;  // staged quads per thread held in registers; longer panels read the rest in the loop
+  constexpr int A = 4 * 512 / THREADS > 6 ? 6 : 4 * 512 / THREADS;  // staged quads per thread held in registers; longer panels read the rest in the loop
   uint2 places[A];
   const uint16_t* perm2 = P.perm2 + aux0.x;
 #pragma unroll
@@ -1031,19 +1031,23 @@ __global__ void __launch_bounds__(THREADS, 2)
     places[a] = 4 * q4 < L ? ldg_stream_u2x32(perm2 + 4 * q4) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
   }
   const uint32_t* __restrict__ g_bits = P.end_bits + aux0.y;
-  uint32_t my_bits = 0, prev_bits = 0x80000000u;
-  if (tid < nwords) {
-    my_bits = __ldg(g_bits + tid);
-    if (tid > 0) prev_bits = __ldg(g_bits + tid - 1);
-  }
-  float bias_pre[kBiasAhead];
-  int ext_b[kBiasAhead], ext_e[kBiasAhead];
+  // thread w owns word w of the slots (the launcher picks THREADS >= nwords): its end marks and the last bit of the word before
+  const uint32_t my_bits = tid < nwords ? __ldg(g_bits + tid) : 0u;
+  const uint32_t prev_bits = (tid < nwords && tid > 0) ? __ldg(g_bits + tid - 1) : 0x80000000u;
+  constexpr int RA = kRowsAhead * 512 / THREADS;
+  float bias_pre[RA];
+  int last_slot[RA];  // the slot that holds the row's total after the sweep, -1 for a row without pieces
 #pragma unroll
-  for (int a = 0; a < kBiasAhead; ++a) {  // their DRAM round trips overlap everything up to the epilogue
+  for (int a = 0; a < RA; ++a) {  // their DRAM round trips overlap everything up to the epilogue
     const int i = tid + a * THREADS;
     bias_pre[a] = (ep.beta != 0.0f && i < trows) ? ep.bias[d.r0 + i] : 0.0f;
-    ext_b[a] = i < trows ? __ldg(P.prow_ptr + d.r0 + i) : 0;
-    ext_e[a] = i < trows ? __ldg(P.prow_ptr + d.r0 + i + 1) : 0;
+    const int b = i < trows ? __ldg(P.prow_ptr + d.r0 + i) : 0;
+    const int e = i < trows ? __ldg(P.prow_ptr + d.r0 + i + 1) : 0;
+    last_slot[a] = e > b ? e - 1 - d.n0 : -1;
+  }
+  for (int i = tid + RA * THREADS; i < trows; i += THREADS) {  // rows beyond those: at least have the lines on their way
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.prow_ptr + d.r0 + i));
+    if (ep.beta != 0.0f) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.bias + d.r0 + i));
   }
   if (tid < 32 && n + tid < 32 * nwords) s_prod[skew((uint32_t)(n + tid))] = 0.0f;  // the last word's unused slots
   if (tid == 0) {  // one thread polls; the CTA parks on the barrier below
@@ -1080,9 +1084,10 @@ __global__ void __launch_bounds__(THREADS, 2)
   unsigned sf = 0;         // thread closed a row
   float lead = 0.0f;       // my share of a row that began in an earlier word and ends in mine ...
   int lead_slot = -1;      // ... at this (skewed) slot
-  for (int w = tid; w < nwords; w += THREADS) {   // one trip unless the panel has more than 32 * THREADS slots
-    const uint32_t bits = w == tid ? my_bits : __ldg(g_bits + w);
-    bool pending = w > 0 && !((w == tid ? prev_bits : __ldg(g_bits + w - 1)) >> 31);   // my first slot's row began before this word
+  if (tid < nwords) {
+    const int w = tid;
+    const uint32_t bits = my_bits;
+    bool pending = w > 0 && !(prev_bits >> 31);   // my first slot's row began before this word
     const uint32_t base = sp + 4u * (33u * (uint32_t)w);
     float run = 0.0f;
 #pragma unroll
@@ -1139,36 +1144,52 @@ __global__ void __launch_bounds__(THREADS, 2)
   __syncthreads();
 
   // ---- epilogue: one thread per row, coalesced ------------------------------------------------------------------
-  auto finish_row = [&](int i, float bias, int b, int e) {
-    const float sum = e > b ? s_prod[skew((uint32_t)(e - 1 - d.n0))] : 0.0f;
+  auto finish_row = [&](int i, float bias, int slot) {
+    const float sum = slot >= 0 ? s_prod[skew((uint32_t)slot)] : 0.0f;
     float v = ep.alpha * sum;
     if (ep.beta != 0.0f) v = fmaf(ep.beta, bias, v);
     if (ep.relu) v = fmaxf(v, 0.0f);
     store_y(y, d.r0 + i, v, ep.y_mc);
   };
 #pragma unroll
-  for (int a = 0; a < kBiasAhead; ++a) {
+  for (int a = 0; a < RA; ++a) {
     const int i = tid + a * THREADS;
-    if (i < trows) finish_row(i, bias_pre[a], ext_b[a], ext_e[a]);
+    if (i < trows) finish_row(i, bias_pre[a], last_slot[a]);
   }
-  for (int i = tid + kBiasAhead * THREADS; i < trows; i += THREADS)
-    finish_row(i, ep.beta != 0.0f ? ep.bias[d.r0 + i] : 0.0f, __ldg(P.prow_ptr + d.r0 + i), __ldg(P.prow_ptr + d.r0 + i + 1));
+  for (int i = tid + RA * THREADS; i < trows; i += THREADS) {
+    const int b = __ldg(P.prow_ptr + d.r0 + i), e = __ldg(P.prow_ptr + d.r0 + i + 1);
+    finish_row(i, ep.beta != 0.0f ? ep.bias[d.r0 + i] : 0.0f, e > b ? e - 1 - d.n0 : -1);
+  }
 }
 
 }  // namespace
 
-int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s) {
-  if (P.num_work <= 0) return HISPMV_OK;
-  const size_t smem = (size_t)P.slab_cols * 4 + (size_t)(kExpandThreads / 32) * kPbGroup * 4;
+template <int THREADS>
+int launch_pb_expand_t(const PbPlan& P, int32_t cols, const float* x, size_t smem, cudaStream_t s) {
   static size_t configured = 0;
   if (smem > configured) {
-    HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<kExpandThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+    HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  pb_expand_kernel<kExpandThreads><<<P.num_work, kExpandThreads, smem, s>>>(P, x, cols);
+  pb_expand_kernel<THREADS><<<P.num_work, THREADS, smem, s>>>(P, x, cols);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
+}
+
+// The kernel is bound by the latency of its shared-memory gathers, so it runs as many warps as fit next to the x slice:
+// every warp needs a 2 KB stage for its pieces (HISPMV_PB_EXPAND_THREADS overrides).
+int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s) {
+  if (P.num_work <= 0) return HISPMV_OK;
+  static const int forced = getenv("HISPMV_PB_EXPAND_THREADS") ? atoi(getenv("HISPMV_PB_EXPAND_THREADS")) : 0;
+  const size_t room = (size_t)227 * 1024 - (size_t)P.slab_cols * 4;
+  int threads = 512;
+  if (room >= 24 * kPbGroup * 4) threads = 768;
+  else if (room >= 20 * kPbGroup * 4) threads = 640;
+  if (forced == 512 || forced == 640 || forced == 768) threads = std::min(threads, forced);
+  const size_t smem = (size_t)P.slab_cols * 4 + (size_t)(threads / 32) * kPbGroup * 4;
+  if (threads == 768) return launch_pb_expand_t<768>(P, cols, x, smem, s);
+  if (threads == 640) return launch_pb_expand_t<640>(P, cols, x, smem, s);
+  return launch_pb_expand_t<512>(P, cols, x, smem, s);
 }
 
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s) {
@@ -1181,13 +1202,30 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
     set_error("blocked plan: a panel does not fit shared memory");
     return HISPMV_ERR_STATE;
   }
-  static size_t configured = 0;
-  if (smem > configured) {
-    HISPMV_CUDA(cudaFuncSetAttribute(pb_reduce_kernel<kReduceThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
-    configured = smem;
+  // One thread sweeps one 32-slot word, so a panel may hold at most 32 * THREADS slots (cap_words bounds every panel).
+  const int max_slots = P.cap_words;
+  if (max_slots > 32 * kReduceThreads) {
+    set_error("blocked plan: panel_items + long_threshold must not exceed 16384");
+    return HISPMV_ERR_STATE;
   }
-  pb_reduce_kernel<kReduceThreads><<<(unsigned)count, kReduceThreads, smem, s>>>(P, y, ep);
+  // panels small enough for four CTAs per SM run with 256 threads each: while one CTA waits for its copies the
+  // others sweep (HISPMV_PB_THREADS overrides)
+  static const int forced = getenv("HISPMV_PB_THREADS") ? atoi(getenv("HISPMV_PB_THREADS")) : 0;
+  const bool fits256 = max_slots <= 32 * 256;
+  const bool small = fits256 && (forced ? forced == 256 : smem + 1024 <= (size_t)(228 * 1024) / 4);
+  static size_t configured[2] = {0, 0};
+  if (smem > configured[small]) {
+    if (small)
+      HISPMV_CUDA(cudaFuncSetAttribute(pb_reduce_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      HISPMV_CUDA(cudaFuncSetAttribute(pb_reduce_kernel<kReduceThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    configured[small] = smem;
+  }
+  if (small)
+    pb_reduce_kernel<256><<<(unsigned)count, 256, smem, s>>>(P, y, ep);
+  else
+    pb_reduce_kernel<kReduceThreads><<<(unsigned)count, kReduceThreads, smem, s>>>(P, y, ep);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }

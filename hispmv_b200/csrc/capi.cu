@@ -599,7 +599,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     if (const char* e = getenv("HISPMV_BLOCKED")) {  // "W,B,T,CH[,SLABCOST]" (development sweeps)
       int w = 0, b = 0, t = 0, ch = 0, sc = -1;
       if (sscanf(e, "%d,%d,%d,%d,%d", &w, &b, &t, &ch, &sc) >= 4 && w >= 1024 && w <= kPbMaxSlabCols && (w & 3) == 0 &&
-          b >= 256 && t >= 16 && b + t <= 56000 && ch >= 128 && ch <= 65535) {
+          b >= 256 && t >= 16 && b + t <= 16384 && ch >= 128 && ch <= 65535) {
         W = w;
         m->tile_items = b;
         m->long_threshold = t;
@@ -1090,7 +1090,7 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.reduce_words = m->pb.reduce_words;
       P.work = m->pb.d_work;
       P.num_work = m->pb.num_work;
-      P.cap_words = (m->tile_items + m->long_threshold + 8 + 1) & ~1;  // even: the segment table behind it is 8-byte aligned
+      P.cap_words = m->tile_items + m->long_threshold;  // no STREAM panel holds more slots than this
       P.panel_begin = tile_begin;
       P.panel_count = tile_count;
       P.carry = m->d_carry + (size_t)lane * m->num_tiles;

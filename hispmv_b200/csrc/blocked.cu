@@ -660,25 +660,34 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
 
 // Pass-1 work ranges: n_cta contiguous pieces of the blocked order, balanced by entries + slab_cost per slab a CTA
 // has to stage (a CTA that walks many thin slabs of the column tail spends its time loading x, not streaming).
-int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream) {
+int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, int64_t piece_cost16, cudaStream_t stream) {
   cudaFree(a->d_work);
   a->d_work = nullptr;
   a->num_work = 0;
   if (n_cta < 1) n_cta = 1;
   const int32_t S = a->num_slabs;
   const int32_t* sp = a->h_slab_ptr;
+  const int64_t ngroups = a->padded_nnz / kPbGroup;
+  std::vector<int32_t> gb((size_t)ngroups + 1);
+  HISPMV_CUDA(cudaMemcpyAsync(gb.data(), a->d_group_base, ((size_t)ngroups + 1) * 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  // a group costs its 512 entries plus piece_cost16/16 entries for every piece it ends (a piece is a scan step, a
+  // staged value and 4 bytes stored: groups of the thin column tail, where nearly every entry is a piece, take longer)
+  auto group_cost = [&](int64_t g) { return (int64_t)kPbGroup + piece_cost16 * (int64_t)(gb[(size_t)g + 1] - gb[(size_t)g]) / 16; };
   int64_t slabs_used = 0;
   for (int32_t s = 0; s < S; ++s) slabs_used += sp[s + 1] > sp[s];
-  int64_t remaining = a->padded_nnz + slab_cost * slabs_used;
+  int64_t remaining = slab_cost * slabs_used;
+  for (int64_t g = 0; g < ngroups; ++g) remaining += group_cost(g);
   std::vector<int2> work((size_t)n_cta);
-  int64_t k = 0;
+  int64_t g = 0;
   int32_t s = 0;
   for (int b = 0; b < n_cta; ++b) {
-    const int64_t k0 = k;
+    const int64_t g0 = g;
     int64_t budget = (remaining + (n_cta - b) - 1) / (n_cta - b);
     int64_t spent = 0;
     bool fresh = true;  // the CTA has to stage the slab it starts in, even when the previous CTA already paid for it
-    while (k < a->padded_nnz && (budget > 0 || b == n_cta - 1)) {
+    while (g < ngroups && (budget > 0 || b == n_cta - 1)) {
+      const int64_t k = g * kPbGroup;
       while (s < S && sp[s + 1] <= k) {
         ++s;
         fresh = true;
@@ -690,16 +699,15 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream)
           spent += slab_cost;
         }
         fresh = false;
-        if (budget <= 0 && k > k0 && b != n_cta - 1) break;
+        if (budget <= 0 && g > g0 && b != n_cta - 1) break;
       }
-      int64_t take = (int64_t)sp[s + 1] - k;
-      if (b != n_cta - 1) take = std::min<int64_t>(take, std::max<int64_t>(kPbGroup, (budget + kPbGroup - 1) / kPbGroup * kPbGroup));
-      k += take;
-      budget -= take;
-      spent += take;
+      const int64_t c = group_cost(g);
+      ++g;
+      budget -= c;
+      spent += c;
     }
-    if (b == n_cta - 1) k = a->padded_nnz;
-    work[(size_t)b] = make_int2((int)k0, (int)k);
+    if (b == n_cta - 1) g = ngroups;
+    work[(size_t)b] = make_int2((int)(g0 * kPbGroup), (int)(g * kPbGroup));
     remaining -= spent;
     if (remaining < 0) remaining = 0;
   }

@@ -74,6 +74,7 @@ struct Matrix {
   int64_t num_batch_long_rows = -1;      // on the first batch call (-1: not yet)
   PbArrays pb;                          // BLOCKED: the slab-major copy, segment table, pass-1 work ranges, products
   int64_t pb_slab_cost = 0;             // BLOCKED: entries one slab load is worth when pass-1 ranges are balanced
+  int64_t pb_piece_cost16 = 0;          // ... and sixteenths of an entry one piece is worth
   int64_t slab_runs = 0;                // selector input: (row, slab) runs for slabs of kPbSlabCols columns (0: not counted)
   // dense
   float* d_a = nullptr;
@@ -596,15 +597,17 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     m->long_threshold = kPbLongThreshold;
     m->chunk_nnz = kPbChunkNnz;
     m->pb_slab_cost = 0;
-    if (const char* e = getenv("HISPMV_BLOCKED")) {  // "W,B,T,CH[,SLABCOST]" (development sweeps)
-      int w = 0, b = 0, t = 0, ch = 0, sc = -1;
-      if (sscanf(e, "%d,%d,%d,%d,%d", &w, &b, &t, &ch, &sc) >= 4 && w >= 1024 && w <= kPbMaxSlabCols && (w & 3) == 0 &&
+    m->pb_piece_cost16 = kPbPieceCost16;
+    if (const char* e = getenv("HISPMV_BLOCKED")) {  // "W,B,T,CH[,SLABCOST[,PIECECOST16]]" (development sweeps)
+      int w = 0, b = 0, t = 0, ch = 0, sc = -1, pc = -1;
+      if (sscanf(e, "%d,%d,%d,%d,%d,%d", &w, &b, &t, &ch, &sc, &pc) >= 4 && w >= 1024 && w <= kPbMaxSlabCols && (w & 3) == 0 &&
           b >= 256 && t >= 16 && b + t <= 16384 && ch >= 128 && ch <= 65535) {
         W = w;
         m->tile_items = b;
         m->long_threshold = t;
         m->chunk_nnz = ch;
         if (sc >= 0) m->pb_slab_cost = sc;
+        if (pc >= 0) m->pb_piece_cost16 = pc;
       }
     }
     if (m->nnz <= 0 || m->local_rows() <= 0) {
@@ -633,7 +636,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
       HISPMV_CUDA(cudaMemsetAsync(m->d_counter, 0, (n + 8) * sizeof(unsigned int), c->stream));
       st = pb_segments_device(&m->pb, m->d_desc, m->num_tiles, m->local_rows(), c->stream);
       if (st != HISPMV_OK) return st;
-      st = pb_make_work(&m->pb, c->sm_count, m->pb_slab_cost, c->stream);
+      st = pb_make_work(&m->pb, c->sm_count, m->pb_slab_cost, m->pb_piece_cost16, c->stream);
       if (st != HISPMV_OK) return st;
       HISPMV_CUDA(cudaMalloc((void**)&m->pb.d_part[0], ((size_t)m->pb.num_pieces + 64) * 4));
     }

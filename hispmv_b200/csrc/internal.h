@@ -277,12 +277,14 @@ void pb_free(PbArrays* a);
 int pb_order_device(const int32_t* d_row_ptr, const int32_t* d_col, const float* d_val, int32_t rows, int32_t cols,
                     int64_t nnz, int32_t slab_cols, PbArrays* out, cudaStream_t stream);
 int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, int32_t rows, cudaStream_t stream);
-// pass-1 work ranges for `n_cta` resident CTAs: contiguous, balanced by entries + slab_cost per slab (re)load
-int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, cudaStream_t stream);
+// pass-1 work ranges for `n_cta` resident CTAs: contiguous, balanced by entries + piece_cost16/16 per piece + slab_cost
+// per slab (re)load
+int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, int64_t piece_cost16, cudaStream_t stream);
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
 constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 6144, kPbLongThreshold = 1024, kPbChunkNnz = 8192;
+constexpr int64_t kPbPieceCost16 = 0;  // pass-1 balance: sixteenths of an entry one piece is worth
 // (row, slab) runs of a device CSR for slabs of slab_cols columns: the selector's estimate of the piece count
 int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, int32_t slab_cols, int64_t* runs,
                          cudaStream_t stream);

@@ -588,20 +588,24 @@ int64_t oracle_pb_segments(int64_t num_pieces, const int* piece_pcsr, const int*
   return nseg;
 }
 
-/* Pass-1 work ranges (blocked.cu: pb_make_work): n_cta contiguous pieces of the blocked order, balanced by entries
- * plus slab_cost for every slab a piece is the first to touch.  work gets 2*n_cta ints. */
-void oracle_pb_work(int S, const int* slab_ptr, int align, int n_cta, int64_t slab_cost, int* work) {
-  const int64_t total = slab_ptr[S];
-  int64_t used = 0, remaining, k = 0;
+/* Pass-1 work ranges (blocked.cu: pb_make_work): n_cta contiguous runs of groups of the blocked order, balanced by
+ * entries (align per group) + piece_cost16/16 per piece a group ends + slab_cost for every slab a range is the first
+ * to touch.  group_base has total/align + 1 entries (oracle_pb_order).  work gets 2*n_cta ints. */
+void oracle_pb_work(int S, const int* slab_ptr, int align, const int* group_base, int n_cta, int64_t slab_cost,
+                    int64_t piece_cost16, int* work) {
+  const int64_t ngroups = slab_ptr[S] / align;
+  int64_t used = 0, remaining, g = 0, i;
   int s = 0, b;
   for (b = 0; b < S; ++b) used += slab_ptr[b + 1] > slab_ptr[b];
-  remaining = total + slab_cost * used;
+  remaining = slab_cost * used;
+  for (i = 0; i < ngroups; ++i) remaining += align + piece_cost16 * (group_base[i + 1] - group_base[i]) / 16;
   for (b = 0; b < n_cta; ++b) {
-    const int64_t k0 = k;
+    const int64_t g0 = g;
     int64_t budget = (remaining + (n_cta - b) - 1) / (n_cta - b), spent = 0;
     int fresh = 1;
-    while (k < total && (budget > 0 || b == n_cta - 1)) {
-      int64_t take;
+    while (g < ngroups && (budget > 0 || b == n_cta - 1)) {
+      const int64_t k = g * align;
+      int64_t c;
       while (s < S && slab_ptr[s + 1] <= k) {
         ++s;
         fresh = 1;
@@ -613,21 +617,16 @@ void oracle_pb_work(int S, const int* slab_ptr, int align, int n_cta, int64_t sl
           spent += slab_cost;
         }
         fresh = 0;
-        if (budget <= 0 && k > k0 && b != n_cta - 1) break;
+        if (budget <= 0 && g > g0 && b != n_cta - 1) break;
       }
-      take = (int64_t)slab_ptr[s + 1] - k;
-      if (b != n_cta - 1) {
-        int64_t cap = (budget + align - 1) / align * align;
-        if (cap < align) cap = align;
-        if (take > cap) take = cap;
-      }
-      k += take;
-      budget -= take;
-      spent += take;
+      c = align + piece_cost16 * (group_base[g + 1] - group_base[g]) / 16;
+      ++g;
+      budget -= c;
+      spent += c;
     }
-    if (b == n_cta - 1) k = total;
-    work[2 * b] = (int)k0;
-    work[2 * b + 1] = (int)k;
+    if (b == n_cta - 1) g = ngroups;
+    work[2 * b] = (int)(g0 * align);
+    work[2 * b + 1] = (int)(g * align);
     remaining -= spent;
     if (remaining < 0) remaining = 0;
   }

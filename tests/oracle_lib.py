@@ -78,7 +78,7 @@ def oracle() -> C.CDLL:
     lib.oracle_pb_order.restype = i64
     lib.oracle_pb_segments.argtypes = [i64, _i32p, _i32p, i, _i32p, i64, _i32p, _i32p, i, vp, vp, vp]
     lib.oracle_pb_segments.restype = i64
-    lib.oracle_pb_work.argtypes = [i, _i32p, i, i, i64, _i32p]
+    lib.oracle_pb_work.argtypes = [i, _i32p, i, _i32p, i, i64, i64, _i32p]
     lib.oracle_select_blocked.argtypes = [i, i, i64, i64, i64, i64, i]
     lib.oracle_select_blocked.restype = i
     lib.oracle_pb_count_runs.argtypes = [i, _i32p, _i32p, i]
@@ -273,7 +273,7 @@ def pb_count_runs(rp, ci, W=49152):
     return int(oracle().oracle_pb_count_runs(rp.size - 1, rp, ci if ci.size else np.zeros(1, np.int32), W))
 
 
-def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
+def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0, piece_cost16=0):
     """The blocked strategy's plan for this CSR (oracle_pb_order / oracle_adaptive_tiles over the pieces /
     oracle_pb_segments / oracle_pb_work) as a dict of numpy arrays."""
     rp, ci = np.ascontiguousarray(rp, np.int32), np.ascontiguousarray(ci, np.int32)
@@ -360,7 +360,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0):
     d["stage_total"], d["bit_words"] = len(perm2), len(bits)
     if n_cta:
         work = np.zeros((n_cta, 2), np.int32)
-        o.oracle_pb_work(S, slab_ptr, align, n_cta, slab_cost, work.reshape(-1))
+        o.oracle_pb_work(S, slab_ptr, align, group_base, n_cta, slab_cost, piece_cost16, work.reshape(-1))
         d["work"] = work
     return d
 

@@ -103,7 +103,7 @@ def test_oracle_blocked_plan_reproduces_the_csr_product(seed, W, B, T, CH):
     rows, cols = 4000, 20000 + seed
     r, c, v = _powerlaw(rng, rows, cols, max_len=6000)
     rp, ci, vv = ol.coo_to_csr(rows, r, c, v)
-    d = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=7, slab_cost=300)
+    d = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=7, slab_cost=300, piece_cost16=24)
     x = rng.standard_normal(cols).astype(np.float32)
     y = _walk_plan(d, rows, CH, W, cols, x)
     y64, scale = ol.spmv_f64(rp, ci, vv, x)
@@ -159,14 +159,14 @@ def _check_run(eng, idx, rp, ci, vv, rows, cols, rng, alpha=ALPHA, beta=BETA):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,params", [(0, "1024,2048,256,512,300"), (1, "4096,512,64,128,0"),
-                                         (2, "20000,4096,1024,4096,5000"), (3, "49152,8192,4096,8192,32768")])
+@pytest.mark.parametrize("seed,params", [(0, "1024,2048,256,512,300,0"), (1, "4096,512,64,128,0,16"),
+                                         (2, "20000,4096,1024,4096,5000,40"), (3, "49152,8192,4096,8192,32768,8")])
 def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     """Every integer artefact of the blocked plan (slab starts, blocked order through val / lcol / perm, segment table,
     pass-1 work ranges) equals the sequential restatement; then the run is within tolerance and bit-reproducible."""
     from hispmv_b200 import capi
     monkeypatch.setenv("HISPMV_BLOCKED", params)
-    W, B, T, CH, cost = (int(t) for t in params.split(","))
+    W, B, T, CH, cost, pcost = (int(t) for t in params.split(","))
     rng = np.random.default_rng(seed)
     rows, cols = 30000, 200003 + seed
     r, c, v = _powerlaw(rng, rows, cols)
@@ -176,7 +176,7 @@ def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     assert info["kernel_name"] == "blocked" and (info["tile_items"], info["long_threshold"], info["chunk_nnz"]) == (B, T, CH)
     rp, ci, vv = eng.plan_csr(idx)
     got = eng.plan_blocked(idx)
-    want = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=got["num_work"], slab_cost=cost)
+    want = ol.pb_plan(rp, ci, vv, cols, B, T, CH, W, n_cta=got["num_work"], slab_cost=cost, piece_cost16=pcost)
     for k in ("slab_cols", "num_slabs", "padded_nnz", "num_pieces", "num_seg", "num_panels", "num_chunks"):
         assert got[k] == want[k], k
     for k in ("stage_total", "bit_words"):

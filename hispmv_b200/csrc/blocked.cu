@@ -805,6 +805,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   float* s_stage = s_x + P.slab_cols + warp * kPbGroup;  // this warp's pieces of one group
   const int2 w = P.work[blockIdx.x];
   if (w.x >= w.y) return;
+  long long dbg_t0 = 0, dbg_loads = 0;
+  if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   const int32_t* __restrict__ slab_ptr = P.slab_ptr;
@@ -877,9 +879,17 @@ __global__ void __launch_bounds__(THREADS, 1)
         g = gn;
       }
       __syncthreads();  // every gather from this slab has been issued before the next one overwrites it
+      ++dbg_loads;
     }
     k = kend;
     ++s;
+  }
+  if (P.dbg && tid == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    P.dbg[3 * blockIdx.x] = t1 - dbg_t0;
+    P.dbg[3 * blockIdx.x + 1] = dbg_loads;
+    P.dbg[3 * blockIdx.x + 2] = (w.y - w.x) / kPbGroup;
   }
 }
 
@@ -1178,6 +1188,27 @@ int launch_pb_expand_t(const PbPlan& P, int32_t cols, const float* x, size_t sme
   if (smem > configured) {
     HISPMV_CUDA(cudaFuncSetAttribute(pb_expand_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
+  }
+  static const bool debug = getenv("HISPMV_PB_DEBUG") != nullptr;
+  if (debug) {  // development: how long every CTA was busy (static ranges: the slowest one is the kernel's duration)
+    static int calls = 0;
+    PbPlan Q = P;
+    HISPMV_CUDA(cudaMallocManaged((void**)&Q.dbg, (size_t)P.num_work * 3 * sizeof(long long)));
+    pb_expand_kernel<THREADS><<<P.num_work, THREADS, smem, s>>>(Q, x, cols);
+    HISPMV_CUDA(cudaStreamSynchronize(s));
+    if (++calls == 5) {
+      long long mx = 0, sum = 0;
+      for (int i = 0; i < P.num_work; ++i) {
+        mx = std::max(mx, Q.dbg[3 * i]);
+        sum += Q.dbg[3 * i];
+      }
+      fprintf(stderr, "pb_expand: %d CTAs, busy ns avg %.0f max %lld\n", P.num_work, (double)sum / P.num_work, mx);
+      for (int i = 0; i < P.num_work; ++i)
+        fprintf(stderr, "  cta %3d  ns %7lld  slab loads %3lld  groups %6lld  ns/group %.1f\n", i, Q.dbg[3 * i], Q.dbg[3 * i + 1],
+                Q.dbg[3 * i + 2], (double)Q.dbg[3 * i] / (double)std::max<long long>(1, Q.dbg[3 * i + 2]));
+    }
+    cudaFree(Q.dbg);
+    return HISPMV_OK;
   }
   pb_expand_kernel<THREADS><<<P.num_work, THREADS, smem, s>>>(P, x, cols);
   HISPMV_CUDA(cudaGetLastError());

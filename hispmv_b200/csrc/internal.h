@@ -231,6 +231,7 @@ struct PbPlan {
   const uint32_t* end_bits = nullptr;  // per STREAM panel, one bit per slot: this slot ends a row
   int32_t reduce_words = 0;            // shared-memory words of the largest STREAM panel (skewed slots + staging)
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
+  long long* dbg = nullptr;            // development (HISPMV_PB_DEBUG): per pass-1 CTA {ns busy, slab loads, groups}
   int32_t num_work = 0;
   int32_t cap_words = 0;               // upper bound on the slots of a STREAM panel (panel items + long threshold)
   int64_t panel_begin = 0, panel_count = -1;  // pass 2: launch only these panels (host-buffer pipeline)
@@ -284,7 +285,7 @@ int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
 constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 6144, kPbLongThreshold = 1024, kPbChunkNnz = 8192;
-constexpr int64_t kPbPieceCost16 = 0;  // pass-1 balance: sixteenths of an entry one piece is worth
+constexpr int64_t kPbPieceCost16 = 12;  // pass-1 balance: sixteenths of an entry one piece is worth
 // (row, slab) runs of a device CSR for slabs of slab_cols columns: the selector's estimate of the piece count
 int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, int32_t slab_cols, int64_t* runs,
                          cudaStream_t stream);

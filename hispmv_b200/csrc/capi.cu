@@ -258,6 +258,8 @@ struct hispmv_ctx {
   // small calls (a DNN layer's vectors): pinned (x | bias | y) + device (x | bias), one CUDA graph per (matrix, alpha, beta)
   float* h_small = nullptr;
   float* d_small = nullptr;
+  float* dh_small = nullptr;   // device view of h_small (mapped pinned memory)
+  bool small_direct = false;
   int64_t cap_small = 0;            // floats in h_small / d_small
   std::map<SmallKey, SmallGraph> small_graphs;
   std::map<const void*, int> small_seen;   // eager runs before a matrix's calls are captured
@@ -413,9 +415,13 @@ int small_call(hispmv_ctx* c, Matrix* m, const float* x, const float* bias, floa
     c->h_small = nullptr;
     c->d_small = nullptr;
     const int64_t cap = std::max<int64_t>(need, 1 << 16);
-    int st = check_cuda(cudaMallocHost((void**)&c->h_small, (size_t)cap * 4), "cudaMallocHost(small)", __FILE__, __LINE__);
+    int st = check_cuda(cudaHostAlloc((void**)&c->h_small, (size_t)cap * 4, cudaHostAllocMapped), "cudaHostAlloc(small)",
+                        __FILE__, __LINE__);
     if (st == HISPMV_OK) st = check_cuda(cudaMalloc((void**)&c->d_small, (size_t)cap * 4), "cudaMalloc(small)", __FILE__, __LINE__);
     if (st != HISPMV_OK) return st == HISPMV_FULL ? HISPMV_ERR_CUDA : st;
+    c->dh_small = nullptr;  // the device's view of the pinned block (the same address under unified addressing)
+    c->small_direct = cudaHostGetDevicePointer((void**)&c->dh_small, c->h_small, 0) == cudaSuccess && c->dh_small;
+    if (!c->small_direct) cudaGetLastError();
     c->cap_small = cap;
   }
   float *hx = c->h_small, *hb = hx + cpad, *hy = hb + ypad;
@@ -423,12 +429,20 @@ int small_call(hispmv_ctx* c, Matrix* m, const float* x, const float* bias, floa
   if (cols > 0) memcpy(hx, x, (size_t)cols * 4);
   if (bias && n_y > 0) memcpy(hb, bias, (size_t)n_y * 4);
   cudaStream_t s = c->stream;
-  const size_t up = (size_t)(bias ? cpad + n_y : cols) * 4;
+  // One-launch strategies that never read y back take bias straight from the pinned block and write y straight into it
+  // (mapped host memory: coalesced reads, posted writes): the call is one small copy of x up, one kernel, one
+  // synchronisation -- no copy engine on the way back.  HISPMV_SMALL_DIRECT=0 keeps the three-copy sequence.
+  static const bool direct_ok = !(getenv("HISPMV_SMALL_DIRECT") && atoi(getenv("HISPMV_SMALL_DIRECT")) == 0);
+  const bool one_launch = m->dense || (m->slabs.empty() && (m->kernel == HISPMV_KERNEL_ADAPTIVE || m->kernel == HISPMV_KERNEL_ROWSTAGE ||
+                                                           m->kernel == HISPMV_KERNEL_CSR_SCALAR || m->kernel == HISPMV_KERNEL_CSR_VECTOR));
+  const bool direct = direct_ok && one_launch && c->small_direct;
+  const size_t up = (size_t)((bias && !direct) ? cpad + n_y : cols) * 4;
   auto enqueue = [&]() -> int {
     if (up > 0) HISPMV_CUDA(cudaMemcpyAsync(dx, hx, up, cudaMemcpyHostToDevice, s));
-    int st = run_matrix(c, m, dx, bias ? db : nullptr, dy, alpha, beta, 0, s, 0, 0, -1, 0, 3);
+    int st = run_matrix(c, m, dx, bias ? (direct ? c->dh_small + cpad : db) : nullptr, direct ? c->dh_small + cpad + ypad : dy,
+                        alpha, beta, 0, s, 0, 0, -1, 0, 3);
     if (st != HISPMV_OK) return st;
-    if (n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(hy, dy, (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
+    if (!direct && n_y > 0) HISPMV_CUDA(cudaMemcpyAsync(hy, dy, (size_t)n_y * 4, cudaMemcpyDeviceToHost, s));
     return HISPMV_OK;
   };
   uint32_t ab, bb;

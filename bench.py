@@ -58,6 +58,15 @@ def workloads():
     return mod
 
 
+_OUT = None
+
+
+def emit(line) -> None:
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measured_peak():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -186,7 +195,7 @@ def run_reference(args):
         "e2e": {"value": gflops, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -292,16 +301,29 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
             dist.barrier()
         torch.cuda.synchronize()
 
+    two_pass = info["kernel_name"] == "blocked"
+    ev_p1 = [torch.cuda.Event() for _ in range(2)]     # pass 1 of the step reading x buffer k has finished
+
     def steps_device(n):
-        """n pipelined steps; work is on the comp / comm streams."""
+        """n pipelined steps; work is on the comp / comm streams.  The exchange of step k+1 runs under the SpMV of step
+        k; with the two-pass strategy it is held back until pass 1 of step k has finished: pass 1 fills every SM's
+        shared memory (one CTA per SM), so an exchange CTA that got there first would push a pass-1 CTA into a second
+        wave -- under pass 2 (four small CTAs per SM) it fits beside them."""
         for k in range(n):
             cur = k & 1
             if world > 1:
                 comm.wait_event(ev_done[cur])              # this rank's replica is free again (SpMV k-2 done)
+                if two_pass and k > 0:
+                    comm.wait_event(ev_p1[cur ^ 1])        # pass 1 of step k-1 is out of the way
                 xrep.replicate(k, x_src, comm)
                 ev_x[cur].record(comm)
                 comp.wait_event(ev_x[cur])
-            eng.run_dev(idx, xbuf[cur], bias, y, ALPHA, BETA, comp.cuda_stream)
+            if two_pass and world > 1:
+                eng.run_dev_phase(idx, xbuf[cur], bias, y, ALPHA, BETA, 1, comp.cuda_stream)
+                ev_p1[cur].record(comp)
+                eng.run_dev_phase(idx, xbuf[cur], bias, y, ALPHA, BETA, 2, comp.cuda_stream)
+            else:
+                eng.run_dev(idx, xbuf[cur], bias, y, ALPHA, BETA, comp.cuda_stream)
             ev_done[cur].record(comp)
 
     # -------- device-resident timing -------------------------------------------------------------------
@@ -454,13 +476,16 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
         if phase_ms:
             pb = eng.plan_blocked(idx, arrays=False)
             b1 = 6.25 * pb["padded_nnz"] + 4 * pb["num_pieces"] + 4 * spec.cols
-            b2 = 6 * pb["num_pieces"] + 12 * n_local + 8 * pb["num_chunks"]
+            # pass 2: staged partial sums (aligned covers) + their 16-bit places, segment descriptors, end marks, and per
+            # row bias + piece extent in, y out
+            b2 = 6 * pb["stage_total"] + 8 * pb["num_seg"] + 4 * pb["bit_words"] + 12 * n_local
             rec["kernels"] = [
                 {"name": "pb_expand_kernel", "ms": phase_ms[0], "actual_bytes": b1,
                  "actual_gbs": b1 / (phase_ms[0] * 1e-3) / 1e9, "frac_of_peak": b1 / (phase_ms[0] * 1e-3) / 1e9 / peak},
                 {"name": "pb_reduce_kernel", "ms": phase_ms[1], "actual_bytes": b2,
                  "actual_gbs": b2 / (phase_ms[1] * 1e-3) / 1e9, "frac_of_peak": b2 / (phase_ms[1] * 1e-3) / 1e9 / peak}]
             rec["config"]["pieces"] = pb["num_pieces"]
+            rec["config"]["segments"] = pb["num_seg"]
             rec["config"]["slabs"] = pb["num_slabs"]
         if cus and "cusparse_ms" in cus:
             cus["ours_ms"] = kernel_ms
@@ -652,7 +677,7 @@ def run_ours(args):
             if isinstance(rec, dict) and rec.get("e2e") and not rec["e2e"]["bit_identical_to_device_path"]:
                 bad.append(f"{name}: host-buffer path differs from the device-resident path")
         line["parity_ok"] = not bad
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -702,6 +727,12 @@ def main():
                     help="the other BASELINE shapes reported under 'configs': auto (c5 at every N; c4, gemv8192, c1 too at "
                          "N=1), a comma list, or '' for none")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: libraries that write to file descriptor 1 (NCCL prints its
+    # version there) are sent to stderr, the line itself goes to a private copy of the original stdout
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -302,6 +302,7 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
         torch.cuda.synchronize()
 
     two_pass = info["kernel_name"] == "blocked"
+    hold_exchange = os.environ.get("HISPMV_BENCH_HOLD_EXCHANGE", "1") != "0"   # development switch
     ev_p1 = [torch.cuda.Event() for _ in range(2)]     # pass 1 of the step reading x buffer k has finished
 
     def steps_device(n):
@@ -313,7 +314,7 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
             cur = k & 1
             if world > 1:
                 comm.wait_event(ev_done[cur])              # this rank's replica is free again (SpMV k-2 done)
-                if two_pass and k > 0:
+                if two_pass and k > 0 and hold_exchange:
                     comm.wait_event(ev_p1[cur ^ 1])        # pass 1 of step k-1 is out of the way
                 xrep.replicate(k, x_src, comm)
                 ev_x[cur].record(comm)

@@ -2,6 +2,8 @@
 // switch delivers the stores to every GPU of the group -- no SM on the receiving side runs anything, and the sender's
 // NVLink egress carries x once instead of once per peer.  The multicast mapping itself comes from
 // torch.distributed._symmetric_memory (device memory + rendezvous are plumbing); the store kernel is ours.
+#include <cstdlib>
+
 #include "device_utils.cuh"
 #include "internal.h"
 
@@ -48,7 +50,11 @@ extern "C" int hispmv_multicast_copy(void* mc_dst, const float* d_src, int64_t n
     return HISPMV_OK;
   }
   const int grid = sm_budget > 0 ? sm_budget : 32;
-  multicast_copy_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(static_cast<float*>(mc_dst), d_src, n / 4, n);
+  // threads per CTA: 512 by default; small CTAs (HISPMV_MC_THREADS=128 with one CTA per SM) fit beside kernels that
+  // leave few registers free, so every SM carries the same small share of the copy
+  static const int forced = getenv("HISPMV_MC_THREADS") ? atoi(getenv("HISPMV_MC_THREADS")) : 0;
+  const int threads = (forced == 64 || forced == 128 || forced == 256) ? forced : 512;
+  multicast_copy_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(static_cast<float*>(mc_dst), d_src, n / 4, n);
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
 }

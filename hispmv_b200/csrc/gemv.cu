@@ -12,6 +12,7 @@
 //     (R*unroll independent 16-byte loads in flight per thread); a shuffle + shared-memory reduction
 //     finishes each group of R rows.  Row blocks are sized so the grid is one wave of
 //     sm_count * CTAS_PER_SM CTAs.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -35,7 +36,7 @@ __device__ __forceinline__ float4 load_x4(const float* __restrict__ x, int c, in
 template <int THREADS, int R, bool STAGE_X>
 __global__ void __launch_bounds__(THREADS)
     gemv_rowblock_kernel(DenseDev A, const float* __restrict__ x, float* __restrict__ y, Epilogue ep,
-                         int rows_per_cta) {
+                         int groups_base, int groups_rem) {
   constexpr int WARPS = THREADS / 32;
   extern __shared__ __align__(16) float s_x[];  // STAGE_X: ld floats (cols rounded up to 4, tail zeroed)
   __shared__ float s_red[2][WARPS][R];
@@ -64,8 +65,12 @@ __global__ void __launch_bounds__(THREADS)
     __syncthreads();
   }
 
-  const int64_t rbeg = (int64_t)blockIdx.x * rows_per_cta;
-  const int64_t rend = min((int64_t)A.rows, rbeg + rows_per_cta);
+  // CTA b owns groups_base (+1 for the first groups_rem CTAs) consecutive groups of R rows: the SMs' shares differ by
+  // at most one group (equal row blocks of ceil(rows / grid) left some SMs a whole CTA short: 8 % on 8192 rows)
+  const int64_t b = blockIdx.x;
+  const int64_t gbeg = b * groups_base + min(b, (int64_t)groups_rem);
+  const int64_t rbeg = gbeg * R;
+  const int64_t rend = min((int64_t)A.rows, (gbeg + groups_base + (b < groups_rem ? 1 : 0)) * R);
   int buf = 0;
   for (int64_t r = rbeg; r < rend; r += R) {
     float acc[R];
@@ -122,15 +127,18 @@ __global__ void __launch_bounds__(THREADS)
 
 namespace {
 template <int R, bool STAGE>
-int launch_gemv_inst(const DenseDev& A, const float* x, float* y, Epilogue ep, int64_t grid, int rows_per_cta,
-                     size_t x_bytes, cudaStream_t s) {
+int launch_gemv_inst(const DenseDev& A, const float* x, float* y, Epilogue ep, int64_t max_grid, size_t x_bytes,
+                     cudaStream_t s) {
   constexpr int THREADS = 256;
+  const int64_t groups = ((int64_t)A.rows + R - 1) / R;
+  const int64_t grid = std::min<int64_t>(max_grid, groups);
+  const int groups_base = (int)(groups / grid), groups_rem = (int)(groups % grid);
   auto k = gemv_rowblock_kernel<THREADS, R, STAGE>;
   if (STAGE) {
     HISPMV_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    k<<<(int)grid, THREADS, x_bytes, s>>>(A, x, y, ep, rows_per_cta);
+    k<<<(int)grid, THREADS, x_bytes, s>>>(A, x, y, ep, groups_base, groups_rem);
   } else {
-    k<<<(int)grid, THREADS, 0, s>>>(A, x, y, ep, rows_per_cta);
+    k<<<(int)grid, THREADS, 0, s>>>(A, x, y, ep, groups_base, groups_rem);
   }
   HISPMV_CUDA(cudaGetLastError());
   return HISPMV_OK;
@@ -157,18 +165,15 @@ int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm
   if (stage) {
     while (ctas_per_sm > 1 && (x_bytes + 1024) * ctas_per_sm > 200 * 1024) --ctas_per_sm;
   }
-  int64_t grid = (int64_t)sm_count * ctas_per_sm;
-  if (grid > A.rows) grid = A.rows;
-  const int rows_per_cta = (int)((A.rows + grid - 1) / grid);
-  grid = (A.rows + rows_per_cta - 1) / rows_per_cta;
+  const int64_t grid = (int64_t)sm_count * ctas_per_sm;  // one wave; launch_gemv_inst spreads the row groups over it
   if (stage) {
-    if (r == 2) return launch_gemv_inst<2, true>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
-    if (r == 8) return launch_gemv_inst<8, true>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
-    return launch_gemv_inst<4, true>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
+    if (r == 2) return launch_gemv_inst<2, true>(A, x, y, ep, grid, x_bytes, s);
+    if (r == 8) return launch_gemv_inst<8, true>(A, x, y, ep, grid, x_bytes, s);
+    return launch_gemv_inst<4, true>(A, x, y, ep, grid, x_bytes, s);
   }
-  if (r == 2) return launch_gemv_inst<2, false>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
-  if (r == 8) return launch_gemv_inst<8, false>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
-  return launch_gemv_inst<4, false>(A, x, y, ep, grid, rows_per_cta, x_bytes, s);
+  if (r == 2) return launch_gemv_inst<2, false>(A, x, y, ep, grid, x_bytes, s);
+  if (r == 8) return launch_gemv_inst<8, false>(A, x, y, ep, grid, x_bytes, s);
+  return launch_gemv_inst<4, false>(A, x, y, ep, grid, x_bytes, s);
 }
 
 }  // namespace hispmv

@@ -63,10 +63,12 @@ def main():
     b = torch.rand(rows, device="cuda")
     y = torch.empty(rows, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    flush = torch.empty(256 * 1024 * 1024 // 4, device="cuda") if args.flush else None
+    flush = torch.zeros(256 * 1024 * 1024 // 4, device="cuda") if args.flush else None
+    flush_r = torch.zeros(256 * 1024 * 1024 // 4, device="cuda") if args.flush else None
     for _ in range(args.runs):
         if flush is not None:
-            flush.add_(1.0)          # cold L2 for the next run
+            flush.add_(1.0)          # cold L2 for the next run ...
+            _ = flush_r.sum()        # ... and clean (the flush's dirty lines are written back before the kernel)
         eng.run_dev(idx, x, b, y, 0.85, -2.06, st)
     torch.cuda.synchronize()
     print(eng.matrix_info(idx)["kernel_name"], float(y.sum()))

@@ -37,7 +37,8 @@ def time_runs(eng, idx, x, b, y, iters, flush):
     times = []
     for _ in range(iters):
         if flush is not None:
-            flush.add_(1.0)
+            flush[0].add_(1.0)       # cold L2 ...
+            _ = flush[1].sum()       # ... and clean: the flush's dirty lines are written back before the timed kernel
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record()
         eng.run_dev(idx, x, b, y, 0.85, -2.06, st)
@@ -84,7 +85,8 @@ def main():
     results = []
     if os.environ.get("HISPMV_NOCHECK"):
         args.no_check = True
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")
+    flush = (torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda"),
+             torch.zeros(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda"))
     for name in args.configs.split(","):
         host_csr = None
         t0 = time.time()

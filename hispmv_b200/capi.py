@@ -83,7 +83,7 @@ def _load() -> C.CDLL:
         "hispmv_plan_tile_chunks": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_blocked_info": (C.c_int, [p, C.c_int, p]),
         "hispmv_plan_blocked": (C.c_int, [p, C.c_int, p, p, p, p, p, p, p, p, p, p, p, p]),
-        "hispmv_plan_blocked_stage": (C.c_int, [p, C.c_int, p, p, p, p, p]),
+        "hispmv_plan_blocked_stage": (C.c_int, [p, C.c_int, p, p, p, p, p, p]),
         "hispmv_plan_slab_nnz": (i64, [p, C.c_int, C.c_int]),
         "hispmv_plan_slab_csr": (C.c_int, [p, C.c_int, C.c_int, p, p, p]),
         "hispmv_load_mtx": (C.c_int, [p, C.c_char_p]),

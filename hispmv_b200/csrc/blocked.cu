@@ -311,7 +311,7 @@ __global__ void pb_seg_copy_kernel(const PbSeg* __restrict__ seg, const int32_t*
                                    const uint64_t* __restrict__ key_sorted, const int32_t* __restrict__ alen,
                                    const int32_t* __restrict__ gpos, const int2* __restrict__ aux,
                                    const uint16_t* __restrict__ perm, int32_t S, int64_t nseg, int2* __restrict__ seg_copy,
-                                   uint16_t* __restrict__ perm2) {
+                                   uint16_t* __restrict__ perm2, int32_t* __restrict__ chunk_src) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= nseg) return;
@@ -321,6 +321,7 @@ __global__ void pb_seg_copy_kernel(const PbSeg* __restrict__ seg, const int32_t*
   for (int32_t j = lane; j < al; j += 32) {
     const int32_t q = a0 + j;
     perm2[(int64_t)g + j] = (q >= b && q < e) ? perm[q] : (uint16_t)0xFFFF;
+    if ((j & 3) == 0) chunk_src[((int64_t)g + j) >> 2] = q;  // where each staged quad of partial sums comes from
   }
 }
 
@@ -337,14 +338,14 @@ __global__ void pb_end_bits_kernel(const int32_t* __restrict__ prow_ptr, int32_t
   atomicOr(&bits[(int64_t)aux[t].y + (j >> 5)], 1u << (j & 31));
 }
 
-// shared-memory words pass 2 needs for its largest STREAM panel: skewed slots + staging area
+// shared-memory words pass 2 needs for its largest STREAM panel: the skewed slots
 __global__ void pb_reduce_words_kernel(const TileDesc* __restrict__ desc, const int2* __restrict__ aux, int64_t npan,
                                        int* __restrict__ out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int v = 0;
   if (t < npan && desc[t].chunk < 0) {
     const int n = desc[t].n1 - desc[t].n0;
-    v = ((n + 31) >> 5) * 33 + 4 + (aux[t + 1].x - aux[t].x);
+    v = ((n + 31) >> 5) * 33 + 4;
   }
   v = __reduce_max_sync(kFullMask, v);
   if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
@@ -372,6 +373,7 @@ void pb_free(PbArrays* a) {
   cudaFree(a->d_chunk);
   cudaFree(a->d_seg_copy);
   cudaFree(a->d_perm2);
+  cudaFree(a->d_chunk_src);
   cudaFree(a->d_panel_aux);
   cudaFree(a->d_end_bits);
   cudaFree(a->d_work);
@@ -630,6 +632,8 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
     a->bit_words = (int64_t)h_t[2] + h_t[3];
     HISPMV_CUDA(cudaMalloc((void**)&a->d_seg_copy, ((size_t)nseg + 1) * sizeof(int2)));
     HISPMV_CUDA(cudaMalloc((void**)&a->d_perm2, ((size_t)a->stage_total + 64) * 2));
+    HISPMV_CUDA(cudaMalloc((void**)&a->d_chunk_src, ((size_t)a->stage_total / 4 + 16) * 4));
+    HISPMV_CUDA(cudaMemsetAsync(a->d_chunk_src + a->stage_total / 4, 0, 16 * 4, stream));
     HISPMV_CUDA(cudaMalloc((void**)&a->d_panel_aux, ((size_t)num_panels + 1) * sizeof(int2)));
     HISPMV_CUDA(cudaMalloc((void**)&a->d_end_bits, ((size_t)a->bit_words + 4) * 4));
     HISPMV_CUDA(cudaMemsetAsync(a->d_end_bits, 0, ((size_t)a->bit_words + 4) * 4, stream));
@@ -641,7 +645,8 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
                                                                         a->d_panel_aux);
     pb_seg_copy_kernel<<<blocks_for(nseg * 32, B), B, 0, stream>>>(a->d_seg, len_sorted.as<int32_t>(), skeys.Current(),
                                                                    alen.as<int32_t>(), gpos.as<int32_t>(), a->d_panel_aux,
-                                                                   a->d_perm, S, nseg, a->d_seg_copy, a->d_perm2);
+                                                                   a->d_perm, S, nseg, a->d_seg_copy, a->d_perm2,
+                                                                   a->d_chunk_src);
     pb_end_bits_kernel<<<blocks_for(rows, B), B, 0, stream>>>(a->d_prow_ptr, rows, d_desc, num_panels, a->d_panel_aux,
                                                               a->d_end_bits);
     pb_reduce_words_kernel<<<blocks_for(num_panels, B), B, 0, stream>>>(d_desc, a->d_panel_aux, num_panels, mw.as<int>());
@@ -958,14 +963,13 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
-  // STREAM panel: [33 * nwords] the panel's partials in per-row order (skewed), then the staging area the bulk copies fill
+  // STREAM panel: [33 * nwords] the panel's partials in per-row order (skewed)
   float* s_prod = reinterpret_cast<float*>(s_raw);
   const uint32_t sp = smem_u32(s_raw);
   constexpr int WARPS = THREADS / 32;
   __shared__ float s_red[WARPS];
   __shared__ float s_wv[WARPS];
   __shared__ int s_wf[WARPS];
-  __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t t = P.panel_begin + blockIdx.x;
   const TileDesc d = load_desc(P.desc + t);
@@ -1012,41 +1016,25 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
     return;
   }
 
-  // ---- STREAM panel.  Gather: the panel's pieces are one contiguous run of part[] per column slab; ONE bulk copy per
-  // run (its 16-byte-aligned cover, issued by as many threads as there are runs, all landing on one mbarrier) brings
-  // them into the staging area -- 16-25 G runs/s chip-wide against ~4 G/s for warps walking a run table
-  // (tools/bulk_small_bench.cu) -- and no thread waits on a global load in between.
+  // ---- STREAM panel.  Gather: the panel's pieces are one contiguous run of part[] per column slab.  The plan lists the
+  // 16-byte-aligned quads of partial sums that cover those runs in panel-major order (chunk_src) next to the slots of
+  // their four values (perm2, 0xFFFF = alignment padding), so the gather is flat: thread q takes quad q, q + THREADS,
+  // ...: one index, one 128-bit load, four predicated shared-memory stores -- no run descriptors, no per-run
+  // instructions (warps walking a run table: 33 M warp instructions on C2; one bulk copy per run: 27 M, the copies are
+  // issued lane by lane through the uniform datapath; this: 5 M).
   const int nwords = (n + 31) >> 5;
-  const int sg0 = __ldg(P.panel_seg + t);
-  const int nsg = __ldg(P.panel_seg + t + 1) - sg0;
   const int2 aux0 = __ldg(P.panel_aux + t), aux1 = __ldg(P.panel_aux + t + 1);
-  const int L = aux1.x - aux0.x;                       // staged positions (a multiple of 4)
-  const uint32_t stage = sp + 4u * (uint32_t)((nwords * 33 + 3) & ~3);
-  const uint32_t bar = smem_u32(&s_bar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * (uint32_t)L) : "memory");
-  }
-  __syncthreads();  // the barrier exists (and expects the bytes) before any copy can complete on it
-  for (int i = tid; i < nsg; i += THREADS) {
-    const int2 sc = __ldg(P.seg_copy + sg0 + i);
-    const uint32_t bytes = ((uint32_t)sc.y >> 16) << 4;
-    if (bytes)
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       stage + (((uint32_t)sc.y & 0xFFFFu) << 4)),
-                   "l"(P.part + sc.x), "r"(bytes), "r"(bar)
-                   : "memory");
-  }
-  // while the copies fly: the places of my staged positions (positions 4 * (tid + a * THREADS) .. + 3), the end marks of
-  // my word of slots, bias and row extents for the epilogue
-  constexpr int A = 4 * 512 / THREADS > 6 ? 6 : 4 * 512 / THREADS;  // staged quads per thread held in registers; longer panels read the rest in the loop
-  uint2 places[A];
+  const int nq = (aux1.x - aux0.x) >> 2;               // staged quads
+  constexpr int A = 4 * 512 / THREADS > 6 ? 6 : 4 * 512 / THREADS;  // quads per thread whose index and slots are requested up front
   const uint16_t* perm2 = P.perm2 + aux0.x;
+  const int32_t* __restrict__ csrc = P.chunk_src + (aux0.x >> 2);
+  int src[A];
+  uint2 places[A];
 #pragma unroll
   for (int a = 0; a < A; ++a) {
     const int q4 = tid + a * THREADS;
-    places[a] = 4 * q4 < L ? ldg_stream_u2x32(perm2 + 4 * q4) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    src[a] = q4 < nq ? __ldg(csrc + q4) : 0;
+    places[a] = q4 < nq ? ldg_stream_u2x32(perm2 + 4 * q4) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
   }
   const uint32_t* __restrict__ g_bits = P.end_bits + aux0.y;
   // thread w owns word w of the slots (the launcher picks THREADS >= nwords): its end marks and the last bit of the word before
@@ -1068,33 +1056,27 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
     if (ep.beta != 0.0f) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.bias + d.r0 + i));
   }
   if (tid < 32 && n + tid < 32 * nwords) s_prod[skew((uint32_t)(n + tid))] = 0.0f;  // the last word's unused slots
-  if (tid == 0) {  // one thread polls; the CTA parks on the barrier below
-    uint32_t done = 0;
-    while (!done) {
-      asm volatile(
-          "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-          : "=r"(done)
-          : "r"(bar), "r"(0u)
-          : "memory");
-    }
-  }
-  __syncthreads();
-  // scatter: staged position -> its slot in the panel's per-row order
-  auto drop4 = [&](int q4, uint2 pl) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stage + 16u * (uint32_t)q4) : "memory");
+  const float* __restrict__ part = P.part;
+  const uint64_t ps = policy_evict_first();
+  auto drop4 = [&](const float4& v, uint2 pl) {  // four partial sums -> their slots in the panel's per-row order
     const uint32_t p0 = pl.x & 0xFFFFu, p1 = pl.x >> 16, p2 = pl.y & 0xFFFFu, p3 = pl.y >> 16;
     sts_f32_if(sp + 4u * skew(p0), v.x, p0 != 0xFFFFu);
     sts_f32_if(sp + 4u * skew(p1), v.y, p1 != 0xFFFFu);
     sts_f32_if(sp + 4u * skew(p2), v.z, p2 != 0xFFFFu);
     sts_f32_if(sp + 4u * skew(p3), v.w, p3 != 0xFFFFu);
   };
+  constexpr int V = 3;  // 128-bit loads in flight per thread
 #pragma unroll
-  for (int a = 0; a < A; ++a) {
-    const int q4 = tid + a * THREADS;
-    if (4 * q4 < L) drop4(q4, places[a]);
+  for (int a0 = 0; a0 < A; a0 += V) {
+    float4 v[V];
+#pragma unroll
+    for (int a = a0; a < a0 + V && a < A; ++a)
+      v[a - a0] = tid + a * THREADS < nq ? ld_stream_f4(part + src[a], ps) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = a0; a < a0 + V && a < A; ++a) drop4(v[a - a0], places[a]);
   }
-  for (int q4 = tid + A * THREADS; 4 * q4 < L; q4 += THREADS) drop4(q4, ldg_stream_u2x32(perm2 + 4 * q4));
+  for (int q4 = tid + A * THREADS; q4 < nq; q4 += THREADS)
+    drop4(ld_stream_f4(part + __ldg(csrc + q4), ps), ldg_stream_u2x32(perm2 + 4 * q4));
   __syncthreads();
 
   // ---- reduce: thread w sums the 32 slots of word w of the per-row order, closing rows at the marks ----------------
@@ -1235,7 +1217,7 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
   (void)A;
   const int64_t count = P.panel_count < 0 ? P.num_panels - P.panel_begin : P.panel_count;
   if (count <= 0) return HISPMV_OK;
-  // the largest STREAM panel: slots skewed by one word per 32, then the staging area (pb_reduce_words_kernel)
+  // the largest STREAM panel: slots skewed by one word per 32 (pb_reduce_words_kernel)
   const size_t smem = ((size_t)P.reduce_words + 8) * 4;
   if (smem > 227 * 1024) {
     set_error("blocked plan: a panel does not fit shared memory");

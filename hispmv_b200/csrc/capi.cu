@@ -13,6 +13,9 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "internal.h"
 
@@ -107,7 +110,7 @@ struct Matrix {
     if (d_tile_row) b += (num_tiles + 1) * 12 + num_tiles * 16 + num_split * 4 + (d_desc ? num_tiles * 32 : 0);
     if (pb.d_val)  // val + lcol + flags per entry; perm + one partial per stream lane in use per piece; tables
       b += pb.padded_nnz * 6 + pb.padded_nnz / 8 + pb.padded_nnz / kPbGroup * 4 + pb.num_pieces * (2 + 4 * (pb.d_part[1] ? 2 : 1)) +
-           pb.num_seg * 16 + pb.num_chunks * 8 + pb.stage_total * 2 + pb.bit_words * 4 + (num_tiles + 1) * 8 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
+           pb.num_seg * 16 + pb.num_chunks * 8 + pb.stage_total * 3 + pb.bit_words * 4 + (num_tiles + 1) * 8 + (pb.num_slabs + 1) * 4 + ((int64_t)local_rows() + 1) * 4;
     for (auto* sm : slabs) b += sm->device_bytes();
     return b;
   }
@@ -131,6 +134,42 @@ namespace {
 // Parallel host memcpy for callers that hand in pageable memory (plain numpy arrays through pyhispmv): a few resident
 // threads copy slices of the caller's vector into / out of the context's pinned ring while the previous slice crosses
 // PCIe.  One copy at a time (the plugin is single-threaded, pyhispmv holds the GIL for the whole call).
+// memcpy for megabyte pieces between pageable and pinned memory: non-temporal stores, so the destination lines are not
+// read for ownership first (a plain memcpy of a 1 MB piece stays below glibc's own non-temporal threshold and moves
+// three bytes over the memory bus for every byte copied)
+static void stream_copy(void* dst, const void* src, size_t n) {
+#if defined(__SSE2__)
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+  if (n < 4096 + head) {
+    memcpy(dst, src, n);
+    return;
+  }
+  memcpy(d, s, head);
+  d += head;
+  s += head;
+  n -= head;
+  const size_t blocks = n / 64;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s) + 0);
+    const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s) + 1);
+    const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s) + 2);
+    const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s) + 3);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d) + 0, a);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d) + 1, b);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d) + 2, c);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d) + 3, e);
+    s += 64;
+    d += 64;
+  }
+  _mm_sfence();
+  memcpy(d, s, n - blocks * 64);
+#else
+  memcpy(dst, src, n);
+#endif
+}
+
 class HostCopier {
  public:
   explicit HostCopier(int n_threads) {
@@ -164,7 +203,7 @@ class HostCopier {
       ++gen_;
     }
     cv_.notify_all();
-    memcpy(dst, src, std::min(bytes, per));
+    stream_copy(dst, src, std::min(bytes, per));
     std::unique_lock<std::mutex> g(m_);
     done_.wait(g, [this] { return pending_ == 0; });
   }
@@ -186,7 +225,7 @@ class HostCopier {
         if (stop_) return;
         t = tasks_[(size_t)i];
       }
-      if (t.n) memcpy(t.d, t.s, t.n);
+      if (t.n) stream_copy(t.d, t.s, t.n);
       {
         std::lock_guard<std::mutex> g(m_);
         if (--pending_ == 0) done_.notify_all();
@@ -1102,6 +1141,7 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.chunk = m->pb.d_chunk;
       P.seg_copy = m->pb.d_seg_copy;
       P.perm2 = m->pb.d_perm2;
+      P.chunk_src = m->pb.d_chunk_src;
       P.panel_aux = m->pb.d_panel_aux;
       P.end_bits = m->pb.d_end_bits;
       P.reduce_words = m->pb.reduce_words;
@@ -2042,7 +2082,7 @@ int hispmv_plan_blocked(hispmv_ctx* c, int idx, int32_t* slab_ptr, float* vals, 
 }
 
 int hispmv_plan_blocked_stage(hispmv_ctx* c, int idx, int64_t* out4, int32_t* seg_copy, uint16_t* perm2,
-                              int32_t* panel_aux, uint32_t* end_bits) {
+                              int32_t* panel_aux, uint32_t* end_bits, int32_t* chunk_src) {
   if (c && !c->kids.empty()) return multi_refuse("hispmv_plan_blocked_stage");
   Matrix* m = get_matrix(c, idx);
   if (!m) return HISPMV_ERR_INDEX;
@@ -2061,6 +2101,7 @@ int hispmv_plan_blocked_stage(hispmv_ctx* c, int idx, int64_t* out4, int32_t* se
   }
   if (seg_copy) HISPMV_CUDA(cudaMemcpy(seg_copy, a.d_seg_copy, (size_t)a.num_seg * 8, k));
   if (perm2) HISPMV_CUDA(cudaMemcpy(perm2, a.d_perm2, (size_t)a.stage_total * 2, k));
+  if (chunk_src) HISPMV_CUDA(cudaMemcpy(chunk_src, a.d_chunk_src, (size_t)a.stage_total, k));
   if (panel_aux) HISPMV_CUDA(cudaMemcpy(panel_aux, a.d_panel_aux, ((size_t)m->num_tiles + 1) * 8, k));
   if (end_bits) HISPMV_CUDA(cudaMemcpy(end_bits, a.d_end_bits, (size_t)a.bit_words * 4, k));
   return HISPMV_OK;

@@ -224,12 +224,14 @@ struct PbPlan {
   int32_t max_panel_segs = 0;         // the most runs (chunk[] entries) any panel has: sizes pass 2's shared-memory copy
   const int32_t* panel_chunk = nullptr;  // num_panels+1 offsets into chunk[]
   const int2* chunk = nullptr;           // the segments cut into runs of at most kPbChunk pieces: (first piece id, count)
-  // the staged gather of pass 2 (STREAM panels): one bulk copy per segment into the panel's staging area
-  const int2* seg_copy = nullptr;      // per segment: {first piece of the aligned range, staging offset/4 | length/4 << 16}
-  const uint16_t* perm2 = nullptr;     // per staged position (panel-major): slot in the panel, 0xFFFF = alignment padding
+  // the gather of pass 2 (STREAM panels): the 16-byte-aligned quads of partial sums that cover the panel's segments,
+  // panel-major
+  const int32_t* chunk_src = nullptr;  // per quad: its first piece id (a multiple of 4)
+  const int2* seg_copy = nullptr;      // per segment: {first piece of the aligned range, panel-relative quad | quads << 16}
+  const uint16_t* perm2 = nullptr;     // per position of those quads: slot in the panel, 0xFFFF = alignment padding
   const int2* panel_aux = nullptr;     // num_panels+1: {first staged position, first word of end_bits}
   const uint32_t* end_bits = nullptr;  // per STREAM panel, one bit per slot: this slot ends a row
-  int32_t reduce_words = 0;            // shared-memory words of the largest STREAM panel (skewed slots + staging)
+  int32_t reduce_words = 0;            // shared-memory words of the largest STREAM panel (skewed slots)
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
   long long* dbg = nullptr;            // development (HISPMV_PB_DEBUG): per pass-1 CTA {ns busy, slab loads, groups}
   int32_t num_work = 0;
@@ -260,6 +262,7 @@ struct PbArrays {
   int64_t num_chunks = 0;
   int2* d_seg_copy = nullptr;
   uint16_t* d_perm2 = nullptr;
+  int32_t* d_chunk_src = nullptr;
   int2* d_panel_aux = nullptr;
   uint32_t* d_end_bits = nullptr;
   int64_t stage_total = 0, bit_words = 0;

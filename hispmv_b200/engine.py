@@ -257,7 +257,7 @@ class Engine:
         d = {"slab_cols": int(o[0]), "num_slabs": int(o[1]), "padded_nnz": int(o[2]), "num_seg": int(o[3]),
              "num_chunks": int(o[4]), "num_work": int(o[5]), "num_panels": int(o[6]), "num_pieces": int(o[7])}
         o4 = np.zeros(4, np.int64)
-        check(lib.hispmv_plan_blocked_stage(self._ctx, matrix_idx, _ptr(o4), None, None, None, None), "plan_blocked_stage")
+        check(lib.hispmv_plan_blocked_stage(self._ctx, matrix_idx, _ptr(o4), None, None, None, None, None), "plan_blocked_stage")
         d["stage_total"], d["bit_words"], d["reduce_words"] = int(o4[0]), int(o4[1]), int(o4[2])
         if arrays:
             n_y = self._shape(matrix_idx)[1]
@@ -281,8 +281,10 @@ class Engine:
             d["perm2"] = np.empty(d["stage_total"], np.uint16)
             d["panel_aux"] = np.empty((d["num_panels"] + 1, 2), np.int32)
             d["end_bits"] = np.empty(d["bit_words"], np.uint32)
+            d["chunk_src"] = np.empty(d["stage_total"] // 4, np.int32)
             check(lib.hispmv_plan_blocked_stage(self._ctx, matrix_idx, None, _ptr(d["seg_copy"]), _ptr(d["perm2"]),
-                                                _ptr(d["panel_aux"]), _ptr(d["end_bits"])), "plan_blocked_stage")
+                                                _ptr(d["panel_aux"]), _ptr(d["end_bits"]), _ptr(d["chunk_src"])),
+                  "plan_blocked_stage")
         return d
 
     def plan_split_rows(self, matrix_idx: int) -> np.ndarray:

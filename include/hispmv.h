@@ -243,20 +243,21 @@ int hispmv_plan_tile_chunks(hispmv_ctx* ctx, int idx, int32_t* chunk_out);
  *   panel_chunk[panels+1], chunk_start_count[2*num_chunks]   the same segments cut into runs of at most 32 pieces,
  *                              (first piece id, count): what a warp of pass 2 fetches per step
  *   work[2*ranges]             pass-1 [begin, end) per resident CTA
- *   (hispmv_plan_blocked_stage) how pass 2 fetches a STREAM panel: one bulk copy per segment of the 16-byte-aligned
- *   range of partial sums that covers it, into the staging area of the panel in shared memory:
- *   out4 = { staged positions in total, end-mark words in total, shared-memory words of the largest panel, segments }
- *   seg_copy[2*num_segments]   (first piece id of the aligned range, staging offset/4 | length/4 << 16); length 0 for
- *                              segments of LONG panels (those are summed through the chunk table)
- *   perm2[staged positions]    the slot (perm) of every staged position, panel-major; 0xFFFF = alignment padding
- *   panel_aux[2*(panels+1)]    (first staged position, first end-mark word) of every panel
+ *   (hispmv_plan_blocked_stage) how pass 2 fetches a STREAM panel: the 16-byte-aligned quads of partial sums that
+ *   cover its segments, listed panel by panel:
+ *   out4 = { positions (4 per quad) in total, end-mark words in total, shared-memory words of the largest panel, segments }
+ *   seg_copy[2*num_segments]   (first piece id of the aligned range, panel-relative first quad | quads << 16); no quads
+ *                              for segments of LONG panels (those are summed through the chunk table)
+ *   chunk_src[positions/4]     the first piece id of every quad
+ *   perm2[positions]           the slot (perm) of every position, 0xFFFF = alignment padding
+ *   panel_aux[2*(panels+1)]    (first position, first end-mark word) of every panel
  *   end_bits[words]            per STREAM panel, bit j of its words: slot j ends a row */
 int hispmv_plan_blocked_info(hispmv_ctx* ctx, int idx, int64_t* out8);
 int hispmv_plan_blocked(hispmv_ctx* ctx, int idx, int32_t* slab_ptr, float* vals, uint16_t* lcol, uint16_t* flags,
                         int32_t* group_base, int32_t* prow_ptr, uint16_t* perm, int32_t* panel_seg,
                         int32_t* seg_start_off, int32_t* panel_chunk, int32_t* chunk_start_count, int32_t* work);
 int hispmv_plan_blocked_stage(hispmv_ctx* ctx, int idx, int64_t* out4, int32_t* seg_copy, uint16_t* perm2,
-                              int32_t* panel_aux, uint32_t* end_bits);
+                              int32_t* panel_aux, uint32_t* end_bits, int32_t* chunk_src);
 
 /* ---- x exchange over NVSwitch multicast: store n floats from d_src to a multicast address (every GPU of the
  *      multicast group receives them).  mc_dst comes from a symmetric-memory rendezvous; sm_budget > 0 = that many

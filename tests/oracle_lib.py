@@ -330,7 +330,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0, piec
     # the 4-piece-aligned range of partial sums that covers it; perm2 = the slot of every staged position (0xFFFF = padding)
     seg_copy = np.zeros((nseg, 2), np.int32)
     panel_aux = np.zeros((npan + 1, 2), np.int32)
-    perm2, bits = [], []
+    perm2, bits, chunk_src = [], [], []
     for p_ in range(npan):
         panel_aux[p_] = (len(perm2), len(bits))
         if tc[p_] >= 0:
@@ -344,6 +344,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0, piec
             a0, a1 = st & ~3, (st + ln + 3) & ~3
             seg_copy[panel_seg[p_] + i_] = (a0, ((len(perm2) - base) >> 2) | (((a1 - a0) >> 2) << 16))
             perm2 += [int(perm[q]) if st <= q < st + ln else 0xFFFF for q in range(a0, a1)]
+            chunk_src += list(range(a0, a1, 4))
         w = np.zeros((npc_p + 31) // 32, np.uint32)
         for r_ in range(tr[p_], tr[p_ + 1]):
             if prow_ptr[r_ + 1] > prow_ptr[r_]:
@@ -357,6 +358,7 @@ def pb_plan(rp, ci, vv, cols, B, T, CH, W, align=512, n_cta=0, slab_cost=0, piec
                 seg_copy[i_] = (d["seg"][i_, 0] & ~3, 0)
     d["seg_copy"], d["perm2"] = seg_copy, np.asarray(perm2, np.uint16)
     d["panel_aux"], d["end_bits"] = panel_aux, np.asarray(bits, np.uint32)
+    d["chunk_src"] = np.asarray(chunk_src, np.int32)
     d["stage_total"], d["bit_words"] = len(perm2), len(bits)
     if n_cta:
         work = np.zeros((n_cta, 2), np.int32)

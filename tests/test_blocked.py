@@ -69,16 +69,19 @@ def _walk_plan(d, rows, CH, W, cols, x):
             y[tr[p]] += buf.sum()
             assert np.all(d["seg_copy"][d["panel_seg"][p]:d["panel_seg"][p + 1], 1] == 0)
             continue
-        # the way the kernel does it: one copy per segment of the aligned range that covers it into the staging area,
-        # every staged position dropped at its slot (perm2), rows closed at the end marks
+        # the way the kernel does it: the aligned quads of partial sums that cover the panel's segments (chunk_src; the
+        # same ranges per segment in seg_copy), every position dropped at its slot (perm2), rows closed at the end marks
         pos0, bit0 = d["panel_aux"][p]
         pos1, bit1 = d["panel_aux"][p + 1]
         stage = np.full(pos1 - pos0, np.nan)
-        padded = np.concatenate([part, np.full(8, np.nan)])      # the copies may read past the last piece
+        padded = np.concatenate([part, np.full(8, np.nan)])      # the quads may read past the last piece
+        for q, a0 in enumerate(d["chunk_src"][pos0 // 4:pos1 // 4]):
+            assert a0 % 4 == 0
+            stage[4 * q:4 * q + 4] = padded[a0:a0 + 4]
         for a0, packed in d["seg_copy"][d["panel_seg"][p]:d["panel_seg"][p + 1]]:
             so, ln = 4 * (packed & 0xFFFF), 4 * ((packed >> 16) & 0xFFFF)
             assert a0 % 4 == 0 and ln > 0
-            stage[so:so + ln] = padded[a0:a0 + ln]
+            assert np.array_equal(stage[so:so + ln], padded[a0:a0 + ln], equal_nan=True)
         slots = np.full(n, np.nan)
         pl = d["perm2"][pos0:pos1]
         keep = pl != 0xFFFF
@@ -182,7 +185,7 @@ def test_blocked_plan_bit_exact(eng, seed, params, monkeypatch):
     for k in ("stage_total", "bit_words"):
         assert got[k] == want[k], k
     for k in ("slab_ptr", "lcol", "flags", "group_base", "prow_ptr", "perm", "panel_seg", "seg", "panel_chunk", "chunk",
-              "seg_copy", "perm2", "panel_aux", "end_bits", "work"):
+              "seg_copy", "perm2", "chunk_src", "panel_aux", "end_bits", "work"):
         assert np.array_equal(got[k], want[k]), k
     assert np.array_equal(got["val"].view(np.uint32), want["val"].view(np.uint32))
     tr, tn = eng.plan_tiles(idx)        # the panels: adaptive tiles over the per-row piece counts

@@ -894,7 +894,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     P.dbg[3 * blockIdx.x] = t1 - dbg_t0;
     P.dbg[3 * blockIdx.x + 1] = dbg_loads;
-    P.dbg[3 * blockIdx.x + 2] = (w.y - w.x) / kPbGroup;
+    P.dbg[3 * blockIdx.x + 2] = (long long)((w.y - w.x) / kPbGroup) |
+                                ((long long)(__ldg(g_base + w.y / kPbGroup) - __ldg(g_base + w.x / kPbGroup)) << 32);
   }
 }
 
@@ -960,7 +961,7 @@ __device__ __forceinline__ uint2 ldg_stream_u2x32(const void* p) {
 }
 
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 2)
     pb_reduce_kernel(PbPlan P, float* __restrict__ y, Epilogue ep) {
   extern __shared__ __align__(16) unsigned char s_raw[];
   // STREAM panel: [33 * nwords] the panel's partials in per-row order (skewed)
@@ -1025,7 +1026,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
   const int nwords = (n + 31) >> 5;
   const int2 aux0 = __ldg(P.panel_aux + t), aux1 = __ldg(P.panel_aux + t + 1);
   const int nq = (aux1.x - aux0.x) >> 2;               // staged quads
-  constexpr int A = 4 * 512 / THREADS > 6 ? 6 : 4 * 512 / THREADS;  // quads per thread whose index and slots are requested up front
+  constexpr int A = THREADS == 256 ? 3 : 4;  // quads per thread whose index and slots are requested up front
   const uint16_t* perm2 = P.perm2 + aux0.x;
   const int32_t* __restrict__ csrc = P.chunk_src + (aux0.x >> 2);
   int src[A];
@@ -1040,7 +1041,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
   // thread w owns word w of the slots (the launcher picks THREADS >= nwords): its end marks and the last bit of the word before
   const uint32_t my_bits = tid < nwords ? __ldg(g_bits + tid) : 0u;
   const uint32_t prev_bits = (tid < nwords && tid > 0) ? __ldg(g_bits + tid - 1) : 0x80000000u;
-  constexpr int RA = kRowsAhead * 512 / THREADS;
+  constexpr int RA = THREADS == 256 ? 6 : kRowsAhead;
   float bias_pre[RA];
   int last_slot[RA];  // the slot that holds the row's total after the sweep, -1 for a row without pieces
 #pragma unroll
@@ -1185,9 +1186,11 @@ int launch_pb_expand_t(const PbPlan& P, int32_t cols, const float* x, size_t sme
         sum += Q.dbg[3 * i];
       }
       fprintf(stderr, "pb_expand: %d CTAs, busy ns avg %.0f max %lld\n", P.num_work, (double)sum / P.num_work, mx);
-      for (int i = 0; i < P.num_work; ++i)
-        fprintf(stderr, "  cta %3d  ns %7lld  slab loads %3lld  groups %6lld  ns/group %.1f\n", i, Q.dbg[3 * i], Q.dbg[3 * i + 1],
-                Q.dbg[3 * i + 2], (double)Q.dbg[3 * i] / (double)std::max<long long>(1, Q.dbg[3 * i + 2]));
+      for (int i = 0; i < P.num_work; ++i) {
+        const long long groups = Q.dbg[3 * i + 2] & 0xffffffffll, pieces = Q.dbg[3 * i + 2] >> 32;
+        fprintf(stderr, "  cta %3d  ns %7lld  slab loads %3lld  groups %6lld  pieces %8lld  ns/group %.1f\n", i, Q.dbg[3 * i],
+                Q.dbg[3 * i + 1], groups, pieces, (double)Q.dbg[3 * i] / (double)std::max<long long>(1, groups));
+      }
     }
     cudaFree(Q.dbg);
     return HISPMV_OK;
@@ -1229,11 +1232,12 @@ int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cu
     set_error("blocked plan: panel_items + long_threshold must not exceed 16384");
     return HISPMV_ERR_STATE;
   }
-  // panels small enough for four CTAs per SM run with 256 threads each: while one CTA waits for its copies the
-  // others sweep (HISPMV_PB_THREADS overrides)
+  // panels of up to 8192 slots run with 256 threads, six CTAs per SM: every panel is a chain of three dependent memory
+  // round trips (descriptor -> quad indices -> partial sums), so what counts is how many panels an SM has in flight
+  // (HISPMV_PB_THREADS=512 overrides)
   static const int forced = getenv("HISPMV_PB_THREADS") ? atoi(getenv("HISPMV_PB_THREADS")) : 0;
   const bool fits256 = max_slots <= 32 * 256;
-  const bool small = fits256 && (forced ? forced == 256 : smem + 1024 <= (size_t)(228 * 1024) / 4);
+  const bool small = fits256 && forced != 512;  // <= 34 KB of slots: six CTAs of 256 threads per SM
   static size_t configured[2] = {0, 0};
   if (smem > configured[small]) {
     if (small)

@@ -649,7 +649,7 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
     m->tile_items = kPbPanelItems;
     m->long_threshold = kPbLongThreshold;
     m->chunk_nnz = kPbChunkNnz;
-    m->pb_slab_cost = 0;
+    m->pb_slab_cost = kPbSlabCost;
     m->pb_piece_cost16 = kPbPieceCost16;
     if (const char* e = getenv("HISPMV_BLOCKED")) {  // "W,B,T,CH[,SLABCOST[,PIECECOST16]]" (development sweeps)
       int w = 0, b = 0, t = 0, ch = 0, sc = -1, pc = -1;

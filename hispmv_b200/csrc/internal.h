@@ -288,7 +288,9 @@ int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
 constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 6144, kPbLongThreshold = 1024, kPbChunkNnz = 8192;
-constexpr int64_t kPbPieceCost16 = 12;  // pass-1 balance: sixteenths of an entry one piece is worth
+// pass-1 balance, fitted to the CTAs' busy times on C2 (HISPMV_PB_DEBUG): a piece is worth 6/16 of an entry (97 ns per
+// group, 0.073 ns per piece), staging a slab's x slice 15 000 entries (2.9 us)
+constexpr int64_t kPbPieceCost16 = 6, kPbSlabCost = 15000;
 // (row, slab) runs of a device CSR for slabs of slab_cols columns: the selector's estimate of the piece count
 int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t rows, int32_t slab_cols, int64_t* runs,
                          cudaStream_t stream);

@@ -9,12 +9,13 @@ A step is one pass y = alpha*A*x + beta*y0 over the whole matrix.
   headline (top-level keys)
     N = 1   the C2 matrix on one B200.
     N > 1   weak scaling: the matrix has N x 10M rows (same generator, same 10M columns), split into nnz-balanced
-            contiguous row blocks, one per rank (one process per GPU, torchrun).  x is produced on rank 0 and replicated
-            every step (NVSwitch multicast store, NCCL broadcast above 64 MB); the exchange of step k+1 runs on a
-            second stream under the SpMV of step k.
+            contiguous row blocks, one per rank (one process per GPU, torchrun).  Every step's x is replicated on all
+            ranks: by default every rank contributes its 1/N block (the shape of an SpMV chain, where each rank produces a
+            block of the next x; --x-source root: rank 0 holds all of it) through NVSwitch multicast stores, NCCL above
+            64 MB; the exchange of step k+1 runs on a second stream under the SpMV of step k.
   "configs"
     c5      BASELINE configs[4]: ONE 100M x 100M, 1B-nnz uniform matrix, strong-scaled over the N ranks (at N = 1 the
-            whole matrix on one GPU), x replicated from rank 0 every step.
+            whole matrix on one GPU), x exchanged every step as in the headline.
     c4, c1, gemv8192 (N = 1 only): configs[3], configs[0] and the 8192^2 GeMV of configs[2].
 `value` is device-resident whole-job throughput (CUDA events, max over ranks).  `e2e` is the same metric through the
 plugin's host-buffer call (hispmv_run: x and bias from pinned host memory, y back to the host, every step; at N > 1
@@ -332,7 +333,10 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
                 comm.wait_event(ev_done[cur])              # this rank's replica is free again (SpMV k-2 done)
                 if two_pass and k > 0 and hold_exchange:
                     comm.wait_event(ev_p1[cur ^ 1])        # pass 1 of step k-1 is out of the way
-                xrep.replicate(k, x_src, comm)
+                if args.x_source == "distributed":
+                    xrep.allgather_slices(k, x_src, comm)   # every rank contributes its 1/N of x
+                else:
+                    xrep.replicate(k, x_src, comm)          # rank 0 holds x
                 ev_x[cur].record(comm)
                 comp.wait_event(ev_x[cur])
             if two_pass and world > 1:
@@ -468,10 +472,13 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
                        "l2": f"matrix stream is {8 * local_nnz / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 "
                              "(no flush needed between steps)",
                        "x_exchange": "none (N=1)" if world == 1 else (
-                           ("one store of x from rank 0 to the NVSwitch multicast address each step "
+                           (("every rank stores its 1/N block of x" if args.x_source == "distributed" else
+                             "one store of x from rank 0") + " to the NVSwitch multicast address each step "
                             f"(hispmv_multicast_copy, {'copy engine' if xrep.mc_ctas < 0 else str(xrep.mc_ctas or 32) + ' CTAs of multimem.st'}, "
                             "symmetric-memory replicas, two device barriers)"
-                            if xrep.mode == "multicast" else "NCCL broadcast of x from rank 0 each step")
+                            if xrep.mode == "multicast" else
+                            ("NCCL all-gather of the ranks' blocks of x each step" if args.x_source == "distributed" else
+                             "NCCL broadcast of x from rank 0 each step"))
                            + ", double-buffered under the previous step's SpMV")},
             "gb_per_s": (8 * total_nnz + 4 * spec.cols + 4 * spec.rows) / (ms_step * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -738,6 +745,10 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's local CPUs")
     ap.add_argument("--x-exchange", default="auto", choices=["auto", "multicast", "nccl"],
                     help="N>1: how x reaches every rank each step (auto = NVSwitch multicast if available, else NCCL)")
+    ap.add_argument("--x-source", default="distributed", choices=["distributed", "root"],
+                    help="N>1: where each step's x comes from: 'distributed' = every rank holds 1/N of it (the shape of an "
+                         "SpMV chain: each rank produces a block of the next x) and the blocks are all-gathered; 'root' = "
+                         "rank 0 holds all of it and replicates it (round 1's exchange)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="the headline: c2 (default: configs[1], weak scaling) or c5 (configs[4], strong scaling)")
     ap.add_argument("--configs", default="auto",

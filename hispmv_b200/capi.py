@@ -90,6 +90,7 @@ def _load() -> C.CDLL:
         "hispmv_parse_mtx": (C.c_int, [C.c_char_p, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), pp, pp, pp]),
         "hispmv_parse_mtx_free": (None, [p, p, p]),
         "hispmv_multicast_copy": (C.c_int, [p, p, i64, C.c_int, p]),
+        "hispmv_peer_copy": (C.c_int, [p, C.c_int, p, i64, C.c_int, p]),
         "hispmv_run_xdev": (C.c_int, [p, p, p, p, p, f32, f32]),
         "hispmv_run_dev_mc": (C.c_int, [p, C.c_int, p, p, p, f32, f32, C.c_int, p]),
         "hispmv_run_dev_batch": (C.c_int, [p, C.c_int, p, p, p, i64, f32, f32, C.c_int, p]),
@@ -112,7 +113,7 @@ EXPORTED = [
     "hispmv_add_dense", "hispmv_add_sparse_coo_dev", "hispmv_add_sparse_csr_dev", "hispmv_add_dense_dev",
     "hispmv_commit", "hispmv_num_matrices", "hispmv_select", "hispmv_force_kernel", "hispmv_run",
     "hispmv_linear", "hispmv_run_dev", "hispmv_run_dev_phase", "hispmv_linear_dev", "hispmv_sync", "hispmv_stream", "hispmv_launches_per_run",
-    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_plan_blocked_info", "hispmv_plan_blocked", "hispmv_plan_blocked_stage", "hispmv_plan_slab_nnz", "hispmv_plan_slab_csr", "hispmv_load_mtx", "hispmv_parse_mtx", "hispmv_parse_mtx_free", "hispmv_multicast_copy", "hispmv_run_xdev", "hispmv_run_dev_mc", "hispmv_run_dev_batch",
+    "hispmv_matrix_info_get", "hispmv_plan_csr", "hispmv_plan_tiles", "hispmv_plan_split_rows", "hispmv_plan_tile_chunks", "hispmv_plan_blocked_info", "hispmv_plan_blocked", "hispmv_plan_blocked_stage", "hispmv_plan_slab_nnz", "hispmv_plan_slab_csr", "hispmv_load_mtx", "hispmv_parse_mtx", "hispmv_parse_mtx_free", "hispmv_multicast_copy", "hispmv_peer_copy", "hispmv_run_xdev", "hispmv_run_dev_mc", "hispmv_run_dev_batch",
     "hispmv_synth_count", "hispmv_synth_shard_bounds", "hispmv_synth_csr", "hispmv_synth_free",
 ]
 

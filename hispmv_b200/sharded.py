@@ -124,6 +124,10 @@ class XReplicator:
         # step 16 CTAs are the best measured (N=2, C2: 1086 GFLOP/s; 32 CTAs 1082, 8 CTAs 1074, copy engine 984 --
         # its transfer is as fast in isolation but overlaps the SpMV worse; profiles/r1_exchange_probe.txt)
         self.mc_ctas = int(os.environ.get("HISPMV_MC_CTAS", "16")) if mc_ctas is None else mc_ctas
+        # allgather_slices: "peer" = every rank stores its block into every replica with plain stores (hispmv_peer_copy),
+        # "multicast" = one multimem.st stream per rank
+        self.slice_path = os.environ.get("HISPMV_SLICE_PATH", "peer")
+        self.peer_ctas = int(os.environ.get("HISPMV_PEER_CTAS", "0")) or max(2, 16 // max(1, dist.get_world_size(group)))
         if mode == "auto" and 4 * n > self.AUTO_MULTICAST_BYTES:
             mode = "nccl"
         if mode in ("auto", "multicast"):
@@ -171,6 +175,43 @@ class XReplicator:
                 check(lib.hispmv_multicast_copy(C.c_void_p(mc), C.c_void_p(src_on_root.data_ptr()), self.n, self.mc_ctas,
                                                 C.c_void_p(stream.cuda_stream)), "multicast_copy")
             self._hdl.barrier(channel=2 + cur)      # the stores have landed everywhere
+
+    def allgather_slices(self, k: int, x_local: torch.Tensor, stream: Optional[torch.cuda.Stream]) -> None:
+        """Enqueue on `stream` the exchange that fills replica k on every rank when x is DISTRIBUTED: rank r holds (at
+        least) elements slice_bounds(r) of x in `x_local` (a full-length device vector of which only that slice is
+        read) -- the shape of an SpMV chain, where every rank produces a block of the next x.  Every rank stores its
+        slice once to the multicast address (multimem.st): per-rank egress is n/N, every GPU's ingress n (N-1)/N, and
+        no single root's link carries the whole vector (one root tops out at ~330-400 GB/s through the switch at N=8;
+        eight roots of 1/8 each finish in about a third of the time).  mode "nccl": all_gather_into_tensor."""
+        lo, hi = self.slice_bounds()
+        with self._on(stream):
+            if self.mode == "nccl":
+                world = dist.get_world_size(self.group)
+                per = self.slice_bounds(0)[1]
+                if not hasattr(self, "_mine"):
+                    self._gath = torch.empty(world * max(per, 4), dtype=torch.float32, device=self.device)
+                    self._mine = torch.zeros(max(per, 4), dtype=torch.float32, device=self.device)
+                if hi > lo:
+                    self._mine[:hi - lo].copy_(x_local[lo:hi])
+                dist.all_gather_into_tensor(self._gath, self._mine, group=self.group)
+                self.buffer(k).copy_(self._gath[:self.n])
+                return
+            import ctypes as C
+            from .capi import lib, check
+            cur = k & 1
+            self._hdl.barrier(channel=cur)          # every rank is done reading replica `cur`
+            if hi > lo:
+                off = (cur * self.npad + lo) * 4
+                if self.slice_path == "peer":       # unicast stores into every replica (this rank's included)
+                    world = dist.get_world_size(self.group)
+                    ptrs = (C.c_void_p * world)(*[int(self._hdl.buffer_ptrs[r]) + off for r in range(world)])
+                    check(lib.hispmv_peer_copy(ptrs, world, C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo,
+                                               self.peer_ctas, C.c_void_p(stream.cuda_stream)), "peer_copy")
+                else:
+                    check(lib.hispmv_multicast_copy(C.c_void_p(self._hdl.multicast_ptr + off),
+                                                    C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo, self.mc_ctas,
+                                                    C.c_void_p(stream.cuda_stream)), "multicast_copy")
+            self._hdl.barrier(channel=2 + cur)      # every slice has landed everywhere
 
     # ---- host-resident x: every rank holds the same x in (pinned) host memory --------------------------------
     def slice_bounds(self, rank: Optional[int] = None):

@@ -264,6 +264,10 @@ int hispmv_plan_blocked_stage(hispmv_ctx* ctx, int idx, int64_t* out4, int32_t* 
  *      CTAs of multimem.st stores, 0 = 32 CTAs, < 0 = a copy engine writes to the multicast address (no SM used).
  *      Asynchronous on `stream`; peers need a barrier on the same group before they read. ---- */
 int hispmv_multicast_copy(void* mc_dst, const float* d_src, int64_t n, int sm_budget, void* stream);
+/* The same n floats stored into n_peers peer buffers (device pointers of this or other GPUs, peer-mapped: the replicas
+ * of a symmetric-memory rendezvous) with plain stores over NVLink, ctas_per_peer CTAs each (0 = 2).  The all-gather of
+ * a distributed x: every rank sends its block to every replica, its own included. */
+int hispmv_peer_copy(void* const* peer_dst, int n_peers, const float* d_src, int64_t n, int ctas_per_peer, void* stream);
 
 /* ---- Matrix Market ingest: real/integer/pattern x general/symmetric/skew-symmetric ---- */
 int hispmv_load_mtx(hispmv_ctx* ctx, const char* path);

@@ -75,6 +75,9 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
         poisoned[hi:] = float("nan")
         sent = rep.gather_from_host(1, poisoned, None)
         assert sent == 4 * (hi - lo) and torch.equal(rep.buffer(1), xs)
+        rep.buffer(0).zero_()                               # distributed x: every rank contributes only its own block
+        rep.allgather_slices(0, poisoned, None)
+        assert torch.equal(rep.buffer(0), xs)
         open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()

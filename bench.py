@@ -392,7 +392,10 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record(comm)
         for k in range(steps):
-            xrep.replicate(k, x_src, comm)
+            if args.x_source == "distributed":
+                xrep.allgather_slices(k, x_src, comm)
+            else:
+                xrep.replicate(k, x_src, comm)
         b1.record(comm)
         barrier()
         bcast_ms = b0.elapsed_time(b1) / steps

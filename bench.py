@@ -300,7 +300,8 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
     dcsr.close()
     if world > 1:
         from hispmv_b200.sharded import XReplicator
-        xrep = XReplicator(spec.cols, torch.device("cuda", local), mode=args.x_exchange)
+        xrep = XReplicator(spec.cols, torch.device("cuda", local), mode=args.x_exchange,
+                           distributed=args.x_source == "distributed")
         xbuf = [xrep.buffer(0), xrep.buffer(1)]
     else:
         xrep = None

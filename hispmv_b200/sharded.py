@@ -113,7 +113,8 @@ class XReplicator:
 
     AUTO_MULTICAST_BYTES = 64 << 20
 
-    def __init__(self, n: int, device, group=None, mode: str = "auto", root: int = 0, mc_ctas: Optional[int] = None):
+    def __init__(self, n: int, device, group=None, mode: str = "auto", root: int = 0, mc_ctas: Optional[int] = None,
+                 distributed: bool = False):
         import os
         self.n, self.device, self.group, self.root = n, device, group, root
         self.rank = dist.get_rank(group)
@@ -126,9 +127,13 @@ class XReplicator:
         self.mc_ctas = int(os.environ.get("HISPMV_MC_CTAS", "16")) if mc_ctas is None else mc_ctas
         # allgather_slices: "peer" = every rank stores its block into every replica with plain stores (hispmv_peer_copy),
         # "multicast" = one multimem.st stream per rank
-        self.slice_path = os.environ.get("HISPMV_SLICE_PATH", "peer")
+        # Measured at N=8 on C2 (profiles/r2_n8_exchange_sweep.txt): multicast slices from 4 CTAs per rank 0.2646 ms per
+        # step, from 16 CTAs 0.2658, peer stores 0.31-0.40, one root 0.2916.
+        self.slice_path = os.environ.get("HISPMV_SLICE_PATH", "multicast")
+        self.slice_ctas = int(os.environ.get("HISPMV_SLICE_CTAS", "0"))     # 0: by slice size, see allgather_slices
         self.peer_ctas = int(os.environ.get("HISPMV_PEER_CTAS", "0")) or max(2, 16 // max(1, dist.get_world_size(group)))
-        if mode == "auto" and 4 * n > self.AUTO_MULTICAST_BYTES:
+        # the size rule is about ONE root pushing the whole vector; blocks of a distributed x go through multicast at any size
+        if mode == "auto" and 4 * n > self.AUTO_MULTICAST_BYTES and not distributed:
             mode = "nccl"
         if mode in ("auto", "multicast"):
             try:
@@ -207,9 +212,10 @@ class XReplicator:
                     ptrs = (C.c_void_p * world)(*[int(self._hdl.buffer_ptrs[r]) + off for r in range(world)])
                     check(lib.hispmv_peer_copy(ptrs, world, C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo,
                                                self.peer_ctas, C.c_void_p(stream.cuda_stream)), "peer_copy")
-                else:
+                else:                               # one CTA per ~1.25 MB of the slice, 4..16: few CTAs, short kernel
+                    ctas = self.slice_ctas or max(4, min(16, -(-(hi - lo) * 4 // (1280 * 1024))))
                     check(lib.hispmv_multicast_copy(C.c_void_p(self._hdl.multicast_ptr + off),
-                                                    C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo, self.mc_ctas,
+                                                    C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo, ctas,
                                                     C.c_void_p(stream.cuda_stream)), "multicast_copy")
             self._hdl.barrier(channel=2 + cur)      # every slice has landed everywhere
 

@@ -68,6 +68,16 @@ def _worker(rank: int, world: int, port: int, out_dir: str):
             sent = rep.gather_from_host(1, host, comm_stream)
             comm_stream.synchronize()
             assert sent == 4 * (hi - lo) and torch.equal(rep.buffer(1).cpu(), xs), mode
+            # distributed x: every rank contributes only its own block (multicast slices, peer stores, NCCL all-gather)
+            mine = host.cuda()                            # NaN outside this rank's slice
+            for path in (("multicast", "peer") if rep.mode == "multicast" else ("nccl",)):
+                rep.slice_path = path
+                rep.buffer(0).fill_(-1.0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                rep.allgather_slices(0, mine, comm_stream)
+                comm_stream.synchronize()
+                assert torch.equal(rep.buffer(0).cpu(), xs), (mode, path)
         assert modes[1] == "nccl"
 
         # ---- row-sharded SpMV: device-resident and host-buffer calls against the oracle ----

@@ -298,10 +298,12 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
     x_src = x_host.cuda()                     # x as rank 0 produces it
     cus = Cusparse().time(dcsr, spec.cols, x_src, min(steps, 50)) if rank == 0 else None
     dcsr.close()
+    x_source = "none"
     if world > 1:
         from hispmv_b200.sharded import XReplicator
+        x_source = args.x_source if args.x_source != "auto" else ("distributed" if 4 * spec.cols <= (64 << 20) else "root")
         xrep = XReplicator(spec.cols, torch.device("cuda", local), mode=args.x_exchange,
-                           distributed=args.x_source == "distributed")
+                           distributed=x_source == "distributed")
         xbuf = [xrep.buffer(0), xrep.buffer(1)]
     else:
         xrep = None
@@ -334,7 +336,7 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
                 comm.wait_event(ev_done[cur])              # this rank's replica is free again (SpMV k-2 done)
                 if two_pass and k > 0 and hold_exchange:
                     comm.wait_event(ev_p1[cur ^ 1])        # pass 1 of step k-1 is out of the way
-                if args.x_source == "distributed":
+                if x_source == "distributed":
                     xrep.allgather_slices(k, x_src, comm)   # every rank contributes its 1/N of x
                 else:
                     xrep.replicate(k, x_src, comm)          # rank 0 holds x
@@ -393,7 +395,7 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
         b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         b0.record(comm)
         for k in range(steps):
-            if args.x_source == "distributed":
+            if x_source == "distributed":
                 xrep.allgather_slices(k, x_src, comm)
             else:
                 xrep.replicate(k, x_src, comm)
@@ -476,12 +478,12 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
                        "l2": f"matrix stream is {8 * local_nnz / 1e6:.0f} MB per step per GPU, larger than the 126 MB L2 "
                              "(no flush needed between steps)",
                        "x_exchange": "none (N=1)" if world == 1 else (
-                           (("every rank stores its 1/N block of x" if args.x_source == "distributed" else
+                           (("every rank stores its 1/N block of x" if x_source == "distributed" else
                              "one store of x from rank 0") + " to the NVSwitch multicast address each step "
                             f"(hispmv_multicast_copy, {'copy engine' if xrep.mc_ctas < 0 else str(xrep.mc_ctas or 32) + ' CTAs of multimem.st'}, "
                             "symmetric-memory replicas, two device barriers)"
                             if xrep.mode == "multicast" else
-                            ("NCCL all-gather of the ranks' blocks of x each step" if args.x_source == "distributed" else
+                            ("NCCL all-gather of the ranks' blocks of x each step" if x_source == "distributed" else
                              "NCCL broadcast of x from rank 0 each step"))
                            + ", double-buffered under the previous step's SpMV")},
             "gb_per_s": (8 * total_nnz + 4 * spec.cols + 4 * spec.rows) / (ms_step * 1e-3) / 1e9,
@@ -749,10 +751,11 @@ def main():
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's local CPUs")
     ap.add_argument("--x-exchange", default="auto", choices=["auto", "multicast", "nccl"],
                     help="N>1: how x reaches every rank each step (auto = NVSwitch multicast if available, else NCCL)")
-    ap.add_argument("--x-source", default="distributed", choices=["distributed", "root"],
+    ap.add_argument("--x-source", default="auto", choices=["auto", "distributed", "root"],
                     help="N>1: where each step's x comes from: 'distributed' = every rank holds 1/N of it (the shape of an "
                          "SpMV chain: each rank produces a block of the next x) and the blocks are all-gathered; 'root' = "
-                         "rank 0 holds all of it and replicates it (round 1's exchange)")
+                         "rank 0 holds all of it and replicates it (round 1's exchange); 'auto' = distributed up to 64 MB "
+                         "of x, root above (measured at N=8: C2 6669 vs 6035 GFLOP/s, C5 1425 vs 1578)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="the headline: c2 (default: configs[1], weak scaling) or c5 (configs[4], strong scaling)")
     ap.add_argument("--configs", default="auto",

@@ -1026,7 +1026,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 2)
   const int nwords = (n + 31) >> 5;
   const int2 aux0 = __ldg(P.panel_aux + t), aux1 = __ldg(P.panel_aux + t + 1);
   const int nq = (aux1.x - aux0.x) >> 2;               // staged quads
-  constexpr int A = THREADS == 256 ? 3 : 4;  // quads per thread whose index and slots are requested up front
+  constexpr int A = THREADS == 256 ? 6 : 4;  // quads per thread whose index and slots are requested up front
   const uint16_t* perm2 = P.perm2 + aux0.x;
   const int32_t* __restrict__ csrc = P.chunk_src + (aux0.x >> 2);
   int src[A];
@@ -1041,7 +1041,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 6 : 2)
   // thread w owns word w of the slots (the launcher picks THREADS >= nwords): its end marks and the last bit of the word before
   const uint32_t my_bits = tid < nwords ? __ldg(g_bits + tid) : 0u;
   const uint32_t prev_bits = (tid < nwords && tid > 0) ? __ldg(g_bits + tid - 1) : 0x80000000u;
-  constexpr int RA = THREADS == 256 ? 6 : kRowsAhead;
+  constexpr int RA = THREADS == 256 ? 3 : kRowsAhead;
   float bias_pre[RA];
   int last_slot[RA];  // the slot that holds the row's total after the sweep, -1 for a row without pieces
 #pragma unroll

@@ -287,7 +287,7 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, int64_t piece_cost16
 int launch_pb_expand(const PbPlan& P, int32_t cols, const float* x, cudaStream_t s);
 int launch_pb_reduce(const CsrDev& A, const PbPlan& P, float* y, Epilogue ep, cudaStream_t s);
 // Slab width / panel parameters of the blocked strategy, and whether the selector prefers it (restated in oracle/).
-constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 6144, kPbLongThreshold = 1024, kPbChunkNnz = 8192;
+constexpr int32_t kPbSlabCols = 49152, kPbPanelItems = 7168, kPbLongThreshold = 1024, kPbChunkNnz = 8192;
 // pass-1 balance, fitted to the CTAs' busy times on C2 (HISPMV_PB_DEBUG): a piece is worth 6/16 of an entry (97 ns per
 // group, 0.073 ns per piece), staging a slab's x slice 15 000 entries (2.9 us)
 constexpr int64_t kPbPieceCost16 = 6, kPbSlabCost = 15000;

@@ -611,6 +611,11 @@ int plan_sparse(hispmv_ctx* c, Matrix* m) {
         sm->is_slab = true;
         sm->forced = true;
         sm->kernel = HISPMV_KERNEL_ADAPTIVE;
+        if (const char* e = getenv("HISPMV_SLAB_KERNEL")) {  // development: "scalar" / "vector2" / "vector4"
+          if (!strcmp(e, "scalar")) sm->kernel = HISPMV_KERNEL_CSR_SCALAR;
+          if (!strcmp(e, "vector2")) { sm->kernel = HISPMV_KERNEL_CSR_VECTOR; sm->lanes = 2; }
+          if (!strcmp(e, "vector4")) { sm->kernel = HISPMV_KERNEL_CSR_VECTOR; sm->lanes = 4; }
+        }
         sm->rows = m->rows;
         sm->cols = m->cols;
         sm->row_begin = m->row_begin;

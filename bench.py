@@ -480,7 +480,7 @@ def run_sparse(args, dist_ctx, spec, label, steps, warmup, do_e2e, do_cpu, clock
                        "x_exchange": "none (N=1)" if world == 1 else (
                            (("every rank stores its 1/N block of x" if x_source == "distributed" else
                              "one store of x from rank 0") + " to the NVSwitch multicast address each step "
-                            f"(hispmv_multicast_copy, {'copy engine' if xrep.mc_ctas < 0 else str(xrep.mc_ctas or 32) + ' CTAs of multimem.st'}, "
+                            f"(hispmv_multicast_copy, {'copy engine' if xrep.mc_ctas < 0 else str(xrep.slice_cta_count() if x_source == 'distributed' else (xrep.mc_ctas or 32)) + ' CTAs of multimem.st'}, "
                             "symmetric-memory replicas, two device barriers)"
                             if xrep.mode == "multicast" else
                             ("NCCL all-gather of the ranks' blocks of x each step" if x_source == "distributed" else

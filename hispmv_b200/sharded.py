@@ -181,6 +181,12 @@ class XReplicator:
                                                 C.c_void_p(stream.cuda_stream)), "multicast_copy")
             self._hdl.barrier(channel=2 + cur)      # the stores have landed everywhere
 
+    def slice_cta_count(self) -> int:
+        """CTAs of multimem.st per rank for allgather_slices: one per ~1.25 MB of the slice, 4..16 (few CTAs, short
+        kernel: at N=8 four CTAs per rank beat sixteen)."""
+        lo, hi = self.slice_bounds()
+        return self.slice_ctas or max(4, min(16, -(-(hi - lo) * 4 // (1280 * 1024))))
+
     def allgather_slices(self, k: int, x_local: torch.Tensor, stream: Optional[torch.cuda.Stream]) -> None:
         """Enqueue on `stream` the exchange that fills replica k on every rank when x is DISTRIBUTED: rank r holds (at
         least) elements slice_bounds(r) of x in `x_local` (a full-length device vector of which only that slice is
@@ -212,8 +218,8 @@ class XReplicator:
                     ptrs = (C.c_void_p * world)(*[int(self._hdl.buffer_ptrs[r]) + off for r in range(world)])
                     check(lib.hispmv_peer_copy(ptrs, world, C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo,
                                                self.peer_ctas, C.c_void_p(stream.cuda_stream)), "peer_copy")
-                else:                               # one CTA per ~1.25 MB of the slice, 4..16: few CTAs, short kernel
-                    ctas = self.slice_ctas or max(4, min(16, -(-(hi - lo) * 4 // (1280 * 1024))))
+                else:
+                    ctas = self.slice_cta_count()
                     check(lib.hispmv_multicast_copy(C.c_void_p(self._hdl.multicast_ptr + off),
                                                     C.c_void_p(x_local.data_ptr() + lo * 4), hi - lo, ctas,
                                                     C.c_void_p(stream.cuda_stream)), "multicast_copy")

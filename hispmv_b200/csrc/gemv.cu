@@ -150,10 +150,10 @@ int launch_gemv(const DenseDev& A, const float* x, float* y, Epilogue ep, int sm
   const size_t x_bytes = (size_t)A.ld * sizeof(float);
   // x is read through L1 by default: staging it in shared memory (TMA bulk copy + mbarrier, kept as an option:
   // HISPMV_GEMV=c,r,1) costs a start-up barrier per CTA and measured slower on every shape (50000 x 10000: 0.381 ms
-  // staged, 0.316 ms through L1).  Five CTAs of 256 threads per SM, four rows per group: 0.98 of the measured HBM
-  // peak on that shape; 8192^2 0.77-0.85, 8192 x 4096 0.69-0.72 (launch + ramp are a third of a 30 us kernel).
+  // staged, 0.316 ms through L1).  Eight CTAs of 256 threads per SM, two rows per group: 1.0 of the measured HBM
+  // peak on that shape; 8192^2 0.87, 8192 x 4096 0.73 (launch + ramp are a quarter of a 29 us kernel).
   bool stage = false;
-  int ctas_per_sm = 5, r = 4;
+  int ctas_per_sm = 8, r = 2;  // round-2 sweep (profiles/r2_gemv_sweep.txt): 8 x 2 beats 5 x 4 by 3-5 % on 8192^2 and 50000 x 10000
   if (const char* e = getenv("HISPMV_GEMV")) {  // "CTAS_PER_SM,R,STAGE" (development sweeps)
     int c = 0, rr = 0, st = 0;
     if (sscanf(e, "%d,%d,%d", &c, &rr, &st) == 3 && c >= 1 && c <= 8 && (rr == 2 || rr == 4 || rr == 8)) {

@@ -1306,12 +1306,13 @@ int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t
   return HISPMV_OK;
 }
 
-// The blocked strategy streams 6.25 bytes per nonzero in pass 1 and about 10 bytes per PIECE over both passes, instead
+// The blocked strategy streams 6.25 bytes per nonzero in pass 1 and about 14 bytes per PIECE over both passes, instead
 // of 8 bytes per nonzero plus a 32-byte L2 sector per scattered gather.  It wins when the gathers are scattered (not
 // banded), x is far larger than an SM's L1, the matrix is large enough to fill two launches, and the rows are
-// concentrated enough that pieces are few: measured on B200 (profiles/r2_blocked_probe.txt), C2 -- 0.30 (row, slab) runs
-// per nonzero -- runs 12 % faster than the one-pass kernel and 14 % faster than cuSPARSE, while uniform columns (1.0 run
-// per nonzero: every nonzero its own piece) run 30 % slower.  Rule: runs <= 0.4 nnz.  Integer rule, restated in
+// concentrated enough that pieces are few.  Measured on B200 (profiles/r2_blocked_crossover.txt, 100 M nonzeros): about
+// 1.5 ns per nonzero + 3.2 ns per piece against 3.7-4.3 ns per nonzero for the one-pass kernel: 1.5x faster from 0.30
+// to 0.40 runs per nonzero (power-law rows, any column skew), 7 % slower at 1.0 (uniform rows and columns: every
+// nonzero its own piece); the break-even is near 0.8.  Rule: runs <= 0.6 nnz.  Integer rule, restated in
 // oracle/oracle.c (oracle_select_blocked).
 int select_blocked(int32_t rows, int32_t cols, int64_t nnz, int64_t slab_runs, const ColProbe& probe,
                    int allow_split_rows) {
@@ -1319,7 +1320,7 @@ int select_blocked(int32_t rows, int32_t cols, int64_t nnz, int64_t slab_runs, c
   if (!allow_split_rows || banded || rows <= 0) return 0;
   if ((int64_t)cols < 1000000 || nnz < 16000000) return 0;
   if (((int64_t)cols + kPbSlabCols - 1) / kPbSlabCols > 4096) return 0;
-  return slab_runs * 5 <= nnz * 2 ? 1 : 0;
+  return slab_runs * 5 <= nnz * 3 ? 1 : 0;
 }
 
 }  // namespace hispmv

@@ -1312,13 +1312,14 @@ int pb_count_runs_device(const int32_t* d_row_ptr, const int32_t* d_col, int32_t
 // concentrated enough that pieces are few.  Measured on B200 (profiles/r2_blocked_crossover.txt, 100 M nonzeros): about
 // 1.5 ns per nonzero + 3.2 ns per piece against 3.7-4.3 ns per nonzero for the one-pass kernel: 1.5x faster from 0.30
 // to 0.40 runs per nonzero (power-law rows, any column skew), 7 % slower at 1.0 (uniform rows and columns: every
-// nonzero its own piece); the break-even is near 0.8.  Rule: runs <= 0.6 nnz.  Integer rule, restated in
-// oracle/oracle.c (oracle_select_blocked).
+// nonzero its own piece); the break-even is near 0.8.  Rule: runs <= 0.6 nnz.  The column threshold is where x leaves an
+// SM's L1: from 100 000 to 10 M columns the ratio stays 1.5-1.6 (profiles/r2_blocked_cols_sweep.txt).  Integer rule,
+// restated in oracle/oracle.c (oracle_select_blocked).
 int select_blocked(int32_t rows, int32_t cols, int64_t nnz, int64_t slab_runs, const ColProbe& probe,
                    int allow_split_rows) {
   const bool banded = probe.cmp >= 64 && probe.near * 4 >= probe.cmp * 3;
   if (!allow_split_rows || banded || rows <= 0) return 0;
-  if ((int64_t)cols < 1000000 || nnz < 16000000) return 0;
+  if ((int64_t)cols < 100000 || nnz < 16000000) return 0;
   if (((int64_t)cols + kPbSlabCols - 1) / kPbSlabCols > 4096) return 0;
   return slab_runs * 5 <= nnz * 3 ? 1 : 0;
 }

@@ -642,13 +642,13 @@ int64_t oracle_pb_count_runs(int rows, const int* row_ptr, const int* col, int W
   return runs;
 }
 
-/* blocked.cu: select_blocked -- scattered columns over a large x, a matrix big enough for two launches, and rows
+/* blocked.cu: select_blocked -- scattered columns over an x beyond an SM's L1 (>= 100 000 columns), a matrix big enough for two launches, and rows
  * concentrated enough that the (row, slab) runs are at most 0.6 of the nonzeros */
 int oracle_select_blocked(int rows, int cols, int64_t nnz, int64_t slab_runs, int64_t probe_near, int64_t probe_cmp,
                           int allow_split_rows) {
   const int banded = probe_cmp >= 64 && probe_near * 4 >= probe_cmp * 3;
   if (!allow_split_rows || banded || rows <= 0) return 0;
-  if ((int64_t)cols < 1000000 || nnz < 16000000) return 0;
+  if ((int64_t)cols < 100000 || nnz < 16000000) return 0;
   if (((int64_t)cols + 49152 - 1) / 49152 > 4096) return 0;
   return slab_runs * 5 <= nnz * 3 ? 1 : 0;
 }

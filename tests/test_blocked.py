@@ -128,6 +128,8 @@ def test_oracle_select_blocked_rule():
     assert ol.select_blocked(20_000_000, 20_000_000, 540_000_000, 20_000_000, 990, 1000) == 0   # C4: banded
     assert ol.select_blocked(65536, 65536, 1_000_000, 100_000, 10, 1000) == 0                   # C1: small
     assert ol.select_blocked(8192, 8192, 6_700_000, 8192, 10, 1000) == 0                        # C3b: x fits L1
+    assert ol.select_blocked(10_000_000, 99_999, 100_000_000, 20_000_000, 10, 1000) == 0        # x below 100 000 columns
+    assert ol.select_blocked(10_000_000, 100_000, 100_000_000, 20_000_000, 10, 1000) == 1
     assert ol.select_blocked(10_000_000, 10_000_000, 100_000_000, 30_000_000, 10, 1000, 0) == 0  # rows may not be split
 
 
@@ -315,13 +317,13 @@ def test_blocked_host_run_pipelines_panel_ranges(eng):
 
 @pytest.mark.gpu
 def test_blocked_selector_bit_exact(eng):
-    """The selector sends a scattered-column matrix with >= 1 M columns, >= 16 M nonzeros and at most 0.6 (row, slab)
+    """The selector sends a scattered-column matrix with >= 100 000 columns, >= 16 M nonzeros and at most 0.6 (row, slab)
     runs per nonzero to the blocked strategy and leaves the others on the one-pass kernels, exactly as
     oracle_select_blocked says; the run count itself is bit-exact against the oracle's."""
     import torch
     cases = ((400_000, 1_500_000, 16_500_000, 40),     # rows concentrated in 40-column bursts: few runs -> blocked
              (2_000_000, 1_500_000, 16_500_000, 0),    # uniform columns: every nonzero its own run -> one-pass
-             (400_000, 900_000, 16_500_000, 40),       # x too small
+             (400_000, 90_000, 16_500_000, 40),        # x too small (below 100 000 columns)
              (200_000, 1_500_000, 8_000_000, 40))      # too few nonzeros
     for rows, cols, nnz, burst in cases:
         g = torch.Generator(device="cuda").manual_seed(rows + cols)

@@ -665,33 +665,28 @@ int pb_segments_device(PbArrays* a, const TileDesc* d_desc, int64_t num_panels, 
 
 // Pass-1 work ranges: n_cta contiguous pieces of the blocked order, balanced by entries + slab_cost per slab a CTA
 // has to stage (a CTA that walks many thin slabs of the column tail spends its time loading x, not streaming).
-int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, int64_t piece_cost16, cudaStream_t stream) {
-  cudaFree(a->d_work);
-  a->d_work = nullptr;
-  a->num_work = 0;
-  if (n_cta < 1) n_cta = 1;
+namespace {
+// n_cta contiguous runs of the groups [g_begin, g_end), balanced by entries + pieces + slab loads (see pb_make_work)
+void pb_partition_groups(const PbArrays* a, const std::vector<int32_t>& gb, int64_t g_begin, int64_t g_end, int n_cta,
+                         int64_t slab_cost, int64_t piece_cost16, int2* work) {
   const int32_t S = a->num_slabs;
   const int32_t* sp = a->h_slab_ptr;
-  const int64_t ngroups = a->padded_nnz / kPbGroup;
-  std::vector<int32_t> gb((size_t)ngroups + 1);
-  HISPMV_CUDA(cudaMemcpyAsync(gb.data(), a->d_group_base, ((size_t)ngroups + 1) * 4, cudaMemcpyDeviceToHost, stream));
-  HISPMV_CUDA(cudaStreamSynchronize(stream));
   // a group costs its 512 entries plus piece_cost16/16 entries for every piece it ends (a piece is a scan step, a
   // staged value and 4 bytes stored: groups of the thin column tail, where nearly every entry is a piece, take longer)
   auto group_cost = [&](int64_t g) { return (int64_t)kPbGroup + piece_cost16 * (int64_t)(gb[(size_t)g + 1] - gb[(size_t)g]) / 16; };
   int64_t slabs_used = 0;
-  for (int32_t s = 0; s < S; ++s) slabs_used += sp[s + 1] > sp[s];
+  for (int32_t s = 0; s < S; ++s)
+    slabs_used += sp[s + 1] > sp[s] && (int64_t)sp[s + 1] > g_begin * kPbGroup && (int64_t)sp[s] < g_end * kPbGroup;
   int64_t remaining = slab_cost * slabs_used;
-  for (int64_t g = 0; g < ngroups; ++g) remaining += group_cost(g);
-  std::vector<int2> work((size_t)n_cta);
-  int64_t g = 0;
+  for (int64_t g = g_begin; g < g_end; ++g) remaining += group_cost(g);
+  int64_t g = g_begin;
   int32_t s = 0;
   for (int b = 0; b < n_cta; ++b) {
     const int64_t g0 = g;
     int64_t budget = (remaining + (n_cta - b) - 1) / (n_cta - b);
     int64_t spent = 0;
     bool fresh = true;  // the CTA has to stage the slab it starts in, even when the previous CTA already paid for it
-    while (g < ngroups && (budget > 0 || b == n_cta - 1)) {
+    while (g < g_end && (budget > 0 || b == n_cta - 1)) {
       const int64_t k = g * kPbGroup;
       while (s < S && sp[s + 1] <= k) {
         ++s;
@@ -711,13 +706,41 @@ int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, int64_t piece_cost16
       budget -= c;
       spent += c;
     }
-    if (b == n_cta - 1) g = ngroups;
-    work[(size_t)b] = make_int2((int)(g0 * kPbGroup), (int)(g * kPbGroup));
+    if (b == n_cta - 1) g = g_end;
+    work[b] = make_int2((int)(g0 * kPbGroup), (int)(g * kPbGroup));
     remaining -= spent;
     if (remaining < 0) remaining = 0;
   }
-  HISPMV_CUDA(cudaMalloc((void**)&a->d_work, (size_t)n_cta * sizeof(int2)));
-  HISPMV_CUDA(cudaMemcpyAsync(a->d_work, work.data(), (size_t)n_cta * sizeof(int2), cudaMemcpyHostToDevice, stream));
+}
+}  // namespace
+
+int pb_make_work(PbArrays* a, int n_cta, int64_t slab_cost, int64_t piece_cost16, cudaStream_t stream) {
+  cudaFree(a->d_work);
+  a->d_work = nullptr;
+  a->num_work = 0;
+  a->head_cols = 0;
+  if (n_cta < 1) n_cta = 1;
+  const int32_t S = a->num_slabs;
+  const int32_t* sp = a->h_slab_ptr;
+  const int64_t ngroups = a->padded_nnz / kPbGroup;
+  std::vector<int32_t> gb((size_t)ngroups + 1);
+  HISPMV_CUDA(cudaMemcpyAsync(gb.data(), a->d_group_base, ((size_t)ngroups + 1) * 4, cudaMemcpyDeviceToHost, stream));
+  HISPMV_CUDA(cudaStreamSynchronize(stream));
+  // [0, n_cta): the whole blocked order.  [n_cta, 3 n_cta): the same order in two parts for the host-buffer call -- the
+  // HEAD slabs (the fewest that hold two thirds of the entries, at most a quarter of the columns) and the rest, each cut
+  // into n_cta ranges of its own, so that pass 1 over the head runs while the rest of x is still crossing PCIe and the
+  // tail part, once x is complete, is spread over all SMs
+  std::vector<int2> work((size_t)3 * n_cta);
+  pb_partition_groups(a, gb, 0, ngroups, n_cta, slab_cost, piece_cost16, work.data());
+  int32_t sh = 0;
+  while (sh < S && (int64_t)sp[sh] * 3 < (int64_t)a->padded_nnz * 2 && (int64_t)(sh + 1) * 4 <= (int64_t)S) ++sh;
+  if (sh > 0 && sh < S && sp[sh] > 0 && sp[sh] < a->padded_nnz) {
+    pb_partition_groups(a, gb, 0, sp[sh] / kPbGroup, n_cta, slab_cost, piece_cost16, work.data() + n_cta);
+    pb_partition_groups(a, gb, sp[sh] / kPbGroup, ngroups, n_cta, slab_cost, piece_cost16, work.data() + 2 * n_cta);
+    a->head_cols = (int64_t)sh * a->slab_cols;
+  }
+  HISPMV_CUDA(cudaMalloc((void**)&a->d_work, work.size() * sizeof(int2)));
+  HISPMV_CUDA(cudaMemcpyAsync(a->d_work, work.data(), work.size() * sizeof(int2), cudaMemcpyHostToDevice, stream));
   HISPMV_CUDA(cudaStreamSynchronize(stream));
   a->num_work = n_cta;
   return HISPMV_OK;
@@ -808,7 +831,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = THREADS / 32;
   float* s_stage = s_x + P.slab_cols + warp * kPbGroup;  // this warp's pieces of one group
-  const int2 w = P.work[blockIdx.x];
+  const int2 w = P.work[P.work_begin + blockIdx.x];
   if (w.x >= w.y) return;
   long long dbg_t0 = 0, dbg_loads = 0;
   if (P.dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));

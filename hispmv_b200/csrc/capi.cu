@@ -278,7 +278,7 @@ struct hispmv_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // second lane for pipelined linear(); H2D lane of the pipelined run()
   cudaStream_t stream3 = nullptr;  // D2H lane of the pipelined run()
-  cudaEvent_t ev_pipe[2 * kMaxRunChunks + 1] = {};  // x ready, bias range ready x16, kernel range done x16
+  cudaEvent_t ev_pipe[2 * kMaxRunChunks + 2] = {};  // x ready, bias range ready x16, kernel range done x16, x head ready
   cudaEvent_t ev_bias = nullptr;
   int shard_part = 0, shard_parts = 1;
   int64_t mem_limit = 0;
@@ -436,7 +436,7 @@ int staged_d2h(hispmv_ctx* c, void* h_dst, const void* d_src, size_t bytes, cuda
 
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
                int relu, cudaStream_t s, int lane = 0, int64_t tile_begin = 0, int64_t tile_count = -1, int y_mc = 0,
-               int phases = 3);
+               int phases = 3, int work_part = 0);
 
 // The small host-buffer call (a DNN layer's vectors: tens of kilobytes).  Everything is latency here, so the call is
 // one memcpy into pinned memory, H2D of (x | bias), the kernel(s), D2H of y, one stream synchronisation and one memcpy
@@ -1020,7 +1020,8 @@ int add_dense_common(hispmv_ctx* c, const float* a, int32_t rows, int32_t cols, 
 // Device-pointer callers get lane 0: one run in flight per matrix handle, as with the reference's xrt::run.
 // `phases`: BLOCKED only -- bit 0 runs pass 1 (products of the whole matrix), bit 1 pass 2 over the given panels.
 int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, float* d_y, float alpha, float beta,
-               int relu, cudaStream_t s, int lane, int64_t tile_begin, int64_t tile_count, int y_mc, int phases) {
+               int relu, cudaStream_t s, int lane, int64_t tile_begin, int64_t tile_count, int y_mc, int phases,
+               int work_part) {
   Epilogue ep{alpha, beta, d_bias, relu};
   ep.y_mc = y_mc;
   if (y_mc && !m->dense && (m->kernel == HISPMV_KERNEL_MERGE || !m->slabs.empty() || m->pipeline)) {
@@ -1152,6 +1153,7 @@ int run_matrix(hispmv_ctx* c, Matrix* m, const float* d_x, const float* d_bias, 
       P.reduce_words = m->pb.reduce_words;
       P.work = m->pb.d_work;
       P.num_work = m->pb.num_work;
+      P.work_begin = (work_part == 1 || work_part == 2) && m->pb.head_cols > 0 ? work_part * m->pb.num_work : 0;
       P.cap_words = m->tile_items + m->long_threshold;  // no STREAM panel holds more slots than this
       P.panel_begin = tile_begin;
       P.panel_count = tile_count;
@@ -1758,12 +1760,37 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
     tname.push_back(what);
   };
   mark(s_up, "start");
+  const bool two_pass = m->kernel == HISPMV_KERNEL_BLOCKED;
+  // BLOCKED with x in host memory: the HEAD slabs hold most of the entries in a small part of x (C2: two thirds of the
+  // entries in the first few megabytes), so x goes up in two pieces and pass 1 over the head runs while the rest of x
+  // is still crossing PCIe; pass 1 over the remaining slabs, cut into one range per SM of its own, follows when x is
+  // complete.  Either way pass 1 does not wait for the first bias range.
+  static const bool split_ok = !(getenv("HISPMV_RUN_SPLIT_X") && atoi(getenv("HISPMV_RUN_SPLIT_X")) == 0);
+  const int64_t head = two_pass && x_host && split_ok ? std::min<int64_t>(m->pb.head_cols, m->cols) : 0;
   if (x_host) {
     cudaEvent_t ev_x = c->ev_pipe[0];
-    HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s_up));
+    if (head > 0 && head < m->cols) {
+      cudaEvent_t ev_h = c->ev_pipe[1 + 2 * kMaxRunChunks];
+      HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)head * 4, cudaMemcpyHostToDevice, s_up));
+      HISPMV_CUDA(cudaEventRecord(ev_h, s_up));
+      HISPMV_CUDA(cudaStreamWaitEvent(s, ev_h, 0));
+      mark(s_up, "x head up");
+      st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, 0, -1, 0, 1, 1);
+      if (st != HISPMV_OK) return st;
+      mark(s, "pass 1 head");
+      HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0] + head, x_host + head, (size_t)(m->cols - head) * 4, cudaMemcpyHostToDevice, s_up));
+    } else {
+      HISPMV_CUDA(cudaMemcpyAsync(c->d_x[0], x_host, (size_t)m->cols * 4, cudaMemcpyHostToDevice, s_up));
+    }
     HISPMV_CUDA(cudaEventRecord(ev_x, s_up));
     HISPMV_CUDA(cudaStreamWaitEvent(s, ev_x, 0));
     mark(s_up, "x up");
+  }
+  if (two_pass) {  // pass 1 needs only x: it starts as soon as x is up, under the upload of the first bias range
+    st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, 0, -1, 0, 1,
+                    head > 0 && head < m->cols ? 2 : 0);  // (pass 1 never reads bias: only the pointer check sees it)
+    if (st != HISPMV_OK) return st;
+    mark(s, "pass 1");
   }
   for (int i = 0; i < chunks; ++i) {
     const int64_t r0 = m->h_tile_row[(size_t)tb[i]], r1 = m->h_tile_row[(size_t)tb[i + 1]];
@@ -1774,9 +1801,9 @@ static int run_host_step(hispmv_ctx* c, const float* x_host, const float* d_x_ex
       HISPMV_CUDA(cudaStreamWaitEvent(s, ev_b, 0));
       mark(s_up, "bias up " + std::to_string(i));
     }
-    // BLOCKED: pass 1 needs only x and runs once, ahead of the first range; pass 2 follows range by range
+    // BLOCKED: pass 1 ran once, ahead of the first range; pass 2 follows range by range
     st = run_matrix(c, m, d_x, bias ? c->d_bias : nullptr, c->d_y[0], alpha, beta, 0, s, 0, tb[i],
-                    tb[i + 1] - tb[i], 0, i == 0 ? 3 : 2);
+                    tb[i + 1] - tb[i], 0, two_pass ? 2 : 3);
     if (st != HISPMV_OK) return st;
     HISPMV_CUDA(cudaEventRecord(ev_k, s));
     HISPMV_CUDA(cudaStreamWaitEvent(s_down, ev_k, 0));

@@ -233,6 +233,8 @@ struct PbPlan {
   const uint32_t* end_bits = nullptr;  // per STREAM panel, one bit per slot: this slot ends a row
   int32_t reduce_words = 0;            // shared-memory words of the largest STREAM panel (skewed slots)
   const int2* work = nullptr;          // pass 1: [k0, k1) in blocked order per CTA, cost-balanced
+  int32_t work_begin = 0;              // first entry of work[] this launch uses (0: whole order; num_work / 2 num_work:
+                                       // the head / tail part of the two-part host-buffer schedule)
   long long* dbg = nullptr;            // development (HISPMV_PB_DEBUG): per pass-1 CTA {ns busy, slab loads, groups}
   int32_t num_work = 0;
   int32_t cap_words = 0;               // upper bound on the slots of a STREAM panel (panel items + long threshold)
@@ -267,8 +269,9 @@ struct PbArrays {
   uint32_t* d_end_bits = nullptr;
   int64_t stage_total = 0, bit_words = 0;
   int32_t reduce_words = 0;
-  int2* d_work = nullptr;
+  int2* d_work = nullptr;              // 3 * num_work ranges: whole order, head part, tail part (pb_make_work)
   int32_t num_work = 0;
+  int64_t head_cols = 0;               // columns of x the head part needs (0: no two-part schedule)
   float* d_part[2] = {nullptr, nullptr};  // one per stream lane, the second allocated on first use
   int32_t* h_slab_ptr = nullptr;          // host copy (num_slabs+1), new[]
   int32_t* d_piece_pcsr = nullptr;        // between the two build stages only
